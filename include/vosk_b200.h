@@ -1,0 +1,56 @@
+/* vosk_b200.h — additive C surface of the B200 engine (nothing here exists in the reference).
+ *
+ * The reference's batch ABI has no model-path argument [REF src/vosk_api.cc:198-205], no partial
+ * result (only a disabled callback [REF src/batch_recognizer.cc:120-137]) and no way to observe
+ * intermediates.  These entry points add exactly that, for parity tests and measurement; existing
+ * bindings never see them.
+ */
+#ifndef VOSK_B200_H
+#define VOSK_B200_H
+#include <stdint.h>
+
+#include "vosk_api.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Like vosk_batch_model_new but with an explicit model directory and "key=value,key=value"
+ * options: frames-per-chunk, max-batch-size, num-channels, beam, lattice-beam, max-active,
+ * min-active, tok-cap, cand-cap, hash-size, max-seconds, log-tokens-per-frame, tensor-cores,
+ * debug-capture, devices (GPU indices separated by ':' or "all").
+ * Env VOSK_BATCH_OPTIONS / VOSK_BATCH_DEVICES are applied first.  NULL on failure. */
+VoskBatchModel *vosk_batch_model_new_ex(const char *model_dir, const char *options);
+
+/* Text of the last error raised while constructing a model on this thread ("" if none). */
+const char *vosk_b200_last_error(void);
+
+/* Samples per chunk (frames-per-chunk x 160), as BatchModel::samples_per_chunk_ [REF src/batch_model.cc:98]. */
+int vosk_batch_model_samples_per_chunk(VoskBatchModel *model);
+
+/* Cumulative counters since creation / the last reset, summed over the model's engines:
+ * [0] audio seconds, [1] steps, [2] lanes, [3] kernel launches, [4] tokens expanded,
+ * [5] emitting arcs, [6] epsilon arcs, [7] tokens created, [8..11] device ms features / i-vector /
+ * network / search (only when timing is on), [12] GEMM launches.  Returns the number written. */
+int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n);
+void vosk_batch_model_reset_stats(VoskBatchModel *model);
+void vosk_batch_model_set_timing(VoskBatchModel *model, int on);
+
+/* Device-resident run (kernel-level measurement): uploads num_streams x samples_per_stream int16
+ * samples to HBM (untimed), then decodes all streams in lockstep with no host<->device sample
+ * traffic and returns the elapsed device time in milliseconds (CUDA events), < 0 on error.
+ * Result texts are kept until the next call; fetch with vosk_batch_model_resident_result. */
+double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream);
+const char *vosk_batch_model_resident_result(VoskBatchModel *model, int stream);
+
+/* Test taps.  Enable before the first accept_waveform on a model created with debug-capture=1;
+ * after finish_stream + wait, fetch "mfcc" [T][40], "ivectors" [chunks][D], "loglikes" [N][pdfs] (f32),
+ * "frame_off" [N+2], "tok_state", "tok_arc", "tok_prev" (i32), "tok_cost" (f32), "error" (i32).
+ * Returns the size in bytes (copies min(size, cap_bytes)), or -1 for an unknown name. */
+void vosk_batch_recognizer_debug_capture(VoskBatchRecognizer *recognizer);
+int64_t vosk_batch_recognizer_debug_get(VoskBatchRecognizer *recognizer, const char *what, void *out, int64_t cap_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOSK_B200_H */

@@ -1,0 +1,68 @@
+"""Shared helpers of the parity tests: run streams through the engine's C ABI with the test taps on."""
+import json
+
+import numpy as np
+
+
+def feed_round_robin(recs, waves, bytes_per_call=8000):
+    """Feeds like the reference's only batch driver [REF python/example/test_gpu_batch.py:27-51]."""
+    pos = [0] * len(recs)
+    ended = set()
+    while len(ended) < len(recs):
+        for i, r in enumerate(recs):
+            if i in ended:
+                continue
+            data = waves[i][pos[i]:pos[i] + bytes_per_call // 2].tobytes()
+            pos[i] += bytes_per_call // 2
+            if not data:
+                r.FinishStream()
+                ended.add(i)
+                continue
+            r.AcceptWaveform(data)
+
+
+def run_engine(model_dir, waves, options="", capture=True, bytes_per_call=8000):
+    import vosk
+    opts = "debug-capture=1," + options if capture else options
+    model = vosk.BatchModel(model_dir, options=opts)
+    recs = [vosk.BatchRecognizer(model, 16000.0) for _ in waves]
+    if capture:
+        for r in recs:
+            r.DebugCapture()
+    feed_round_robin(recs, waves, bytes_per_call)
+    model.Wait()
+    out = []
+    for r in recs:
+        d = {"text": r.Result()}
+        if capture:
+            d["mfcc"] = r.DebugGet("mfcc", np.float32).reshape(-1, 40)
+            d["ivectors"] = r.DebugGet("ivectors", np.float32)
+            d["loglikes"] = r.DebugGet("loglikes", np.float32)
+            for k in ("frame_off", "tok_state", "tok_arc", "tok_prev"):
+                d[k] = r.DebugGet(k, np.int32)
+            d["tok_cost"] = r.DebugGet("tok_cost", np.float32)
+            d["error"] = int(r.DebugGet("error", np.int32)[0])
+        out.append(d)
+    stats = model.Stats()
+    del recs
+    del model
+    return out, stats
+
+
+def canonical_tokens(frame_off, state, cost, arc, prev):
+    """Per frame: sort by state id and renumber the back pointers (DESIGN.md canonical token order)."""
+    n = len(state)
+    new_index = np.full(n, -1, dtype=np.int64)
+    order_all = np.zeros(n, dtype=np.int64)
+    for f in range(len(frame_off) - 1):
+        lo, hi = int(frame_off[f]), int(frame_off[f + 1])
+        o = lo + np.argsort(state[lo:hi], kind="stable")
+        order_all[lo:hi] = o
+        new_index[o] = np.arange(lo, hi)
+    p = prev[order_all].astype(np.int64)
+    p = np.where(p >= 0, new_index[np.maximum(p, 0)], p)
+    return state[order_all], cost[order_all], arc[order_all], p
+
+
+def words_of(text):
+    return json.loads(text).get("text", "")

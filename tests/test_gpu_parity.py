@@ -1,0 +1,93 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+# audio lengths (seconds): shorter than a chunk, not frame aligned, multi-chunk, exact multiple of a chunk
+LENGTHS = [0.3, 0.52, 1.3, 2.04, 3.7]
+
+
+def _waves(lengths, seed0=100):
+    import vbmodel
+    return [vbmodel.synth_audio(s, seed0 + i) for i, s in enumerate(lengths)]
+
+
+def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3):
+    ref = oracle.recognize(model, wave, frames_per_chunk=fpc, stages=True)
+    D = int(model["cfg"]["ivector-dim"])
+    P = int(model["cfg"]["num-pdfs"])
+    assert got["error"] == 0
+    assert got["mfcc"].shape == ref["mfcc"].shape
+    if len(ref["mfcc"]):
+        # fp32 FFT vs the oracle's double FFT: error relative to the frame's spectral peak
+        assert np.abs(got["mfcc"] - ref["mfcc"]).max() < 2e-3
+    iv = got["ivectors"].reshape(-1, D)
+    assert iv.shape == ref["ivectors"].shape
+    assert np.abs(iv - ref["ivectors"]).max() < 2e-3
+    ll = got["loglikes"].reshape(-1, P)
+    assert ll.shape == ref["loglikes"].shape
+    if ll.size:
+        # acoustic log-likelihoods within 1e-3 absolute (north_star tolerance)
+        assert np.abs(ll - ref["loglikes"]).max() < tol_ll
+    # search: oracle decoder on the ENGINE's log-likelihoods must agree bit for bit
+    dec = oracle.decode(model, ll) if ll.size else None
+    if dec is not None:
+        fo = got["frame_off"]
+        assert len(fo) == dec["frames"] + 2
+        np.testing.assert_array_equal(fo.astype(np.int64), dec["offsets"])
+        st, co, ar, pv = helpers.canonical_tokens(fo, got["tok_state"], got["tok_cost"], got["tok_arc"], got["tok_prev"])
+        np.testing.assert_array_equal(st, dec["state"])
+        np.testing.assert_array_equal(ar, dec["arc"])
+        np.testing.assert_array_equal(co.view(np.uint32), dec["cost"].view(np.uint32))
+        np.testing.assert_array_equal(pv, dec["prev"])
+        assert got["text"] == oracle.result_json(model, dec["best_arcs"])
+    # end to end: identical transcript and word timings against the pure-oracle pipeline
+    assert got["text"] == ref["text"]
+
+
+@pytest.mark.parametrize("fpc", [51, 9])
+def test_tiny_model_all_stages(model_root, oracle_lib, fpc):
+    import vbmodel
+    mdir = model_root("tiny")
+    model = vbmodel.load_model_dir(mdir)
+    waves = _waves(LENGTHS)
+    got, _ = helpers.run_engine(mdir, waves, options=f"frames-per-chunk={fpc},num-channels=8,max-batch-size=8,max-seconds=8,tensor-cores=0")
+    for w, g in zip(waves, got):
+        _check_stream(model, oracle_lib, w, g, fpc)
+
+
+def test_tiny_more_streams_than_lanes_and_channels(model_root, oracle_lib):
+    import vbmodel
+    mdir = model_root("tiny")
+    model = vbmodel.load_model_dir(mdir)
+    waves = _waves([1.1, 0.7, 2.2, 1.6, 0.9, 1.3, 2.9], seed0=300)
+    got, _ = helpers.run_engine(mdir, waves, options="num-channels=3,max-batch-size=2,max-seconds=8,tensor-cores=0")
+    for w, g in zip(waves, got):
+        _check_stream(model, oracle_lib, w, g, 51)
+
+
+def test_small_model_all_stages(model_root, oracle_lib):
+    import vbmodel
+    mdir = model_root("small")
+    model = vbmodel.load_model_dir(mdir)
+    waves = _waves([2.5, 4.2, 0.9], seed0=500)
+    got, _ = helpers.run_engine(mdir, waves, options="num-channels=4,max-batch-size=4,max-seconds=10,tensor-cores=0")
+    for w, g in zip(waves, got):
+        _check_stream(model, oracle_lib, w, g, 51)
+
+
+def test_max_active_binds(model_root, oracle_lib):
+    """Small beam budget: max_active / min_active order statistics must select exactly the oracle's tokens."""
+    import vbmodel
+    mdir = model_root("small")
+    model = vbmodel.load_model_dir(mdir)
+    model["conf"]["max-active"] = "300"
+    model["conf"]["min-active"] = "50"
+    model["conf"]["beam"] = "20"
+    waves = _waves([2.0, 3.1], seed0=700)
+    got, _ = helpers.run_engine(mdir, waves, options="num-channels=2,max-batch-size=2,max-seconds=10,max-active=300,min-active=50,beam=20,tensor-cores=0")
+    for w, g in zip(waves, got):
+        _check_stream(model, oracle_lib, w, g, 51)

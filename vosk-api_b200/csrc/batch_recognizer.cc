@@ -1,0 +1,75 @@
+// batch_recognizer.cc — see batch_recognizer.h.  Replaces [REF src/batch_recognizer.cc].
+#include "batch_recognizer.h"
+
+#include <algorithm>
+#include <cmath>
+
+using namespace vb;
+
+BatchRecognizer::BatchRecognizer(BatchModel *model, float sample_frequency)
+    : model_(model), sample_frequency_(sample_frequency), sink_(std::make_shared<Sink>()),
+      // [REF src/batch_recognizer.cc:27-29]
+      resampler_(sample_frequency, 16000.0f, std::min(sample_frequency / 2, 16000.0f / 2), 6) {
+    id_ = model->GetID(this);
+    stream_ = model->engine_for(id_).open_stream();
+    std::shared_ptr<Sink> sink = sink_;
+    const Model *m = &model->model();
+    stream_->on_result = [sink, m](const BestPath &bp) {
+        std::vector<WordSpan> words = align_words(*m, bp.arcs);
+        std::lock_guard<std::mutex> lk(sink->mu);
+        sink->results.push(sink->nlsml ? result_nlsml(*m, words) : result_json(*m, words, 0.0f));
+    };
+}
+
+BatchRecognizer::~BatchRecognizer() {}
+
+void BatchRecognizer::EnableCapture() { stream_->capture.reset(new Capture); }
+
+void BatchRecognizer::SetNLSML(bool nlsml) {
+    std::lock_guard<std::mutex> lk(sink_->mu);
+    sink_->nlsml = nlsml;
+}
+
+void BatchRecognizer::AcceptWaveform(const char *data, int len) {
+    if (finished_ || len < 2) return;
+    const int n = len / 2;  // odd trailing byte ignored, as in the reference (len / 2)
+    const int16_t *pcm = reinterpret_cast<const int16_t *>(data);
+    if (resampler_.identity()) {
+        buffer_.insert(buffer_.end(), pcm, pcm + n);
+    } else {
+        std::vector<float> in(n), out;
+        for (int i = 0; i < n; i++) in[i] = pcm[i];
+        resampler_.resample_flush(in, &out);
+        for (float v : out) buffer_.push_back((int16_t)std::lrintf(std::max(-32768.f, std::min(32767.f, v))));
+    }
+    const int spc = model_->samples_per_chunk();
+    size_t i = 0;
+    Engine &eng = model_->engine_for(id_);
+    while (i + spc <= buffer_.size()) {
+        eng.push(stream_, buffer_.data() + i, spc, false);
+        i += spc;
+    }
+    if (i) buffer_.erase(buffer_.begin(), buffer_.begin() + i);
+}
+
+void BatchRecognizer::FinishStream() {
+    if (finished_) return;
+    finished_ = true;
+    // whatever is buffered (possibly nothing) goes out flagged last [REF src/batch_recognizer.cc:37-41]
+    model_->engine_for(id_).push(stream_, buffer_.data(), (int)buffer_.size(), true);
+    buffer_.clear();
+}
+
+const char *BatchRecognizer::FrontResult() {
+    std::lock_guard<std::mutex> lk(sink_->mu);
+    if (sink_->results.empty()) return "";
+    front_ = sink_->results.front();
+    return front_.c_str();
+}
+
+void BatchRecognizer::Pop() {
+    std::lock_guard<std::mutex> lk(sink_->mu);
+    if (!sink_->results.empty()) sink_->results.pop();
+}
+
+int BatchRecognizer::GetNumPendingChunks() { return stream_->pending_chunks.load(); }

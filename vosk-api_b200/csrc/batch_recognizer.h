@@ -1,0 +1,46 @@
+// batch_recognizer.h — BatchRecognizer: same public surface as the reference class
+// [REF src/batch_recognizer.h:28-53], rebuilt over vb::Engine streams.
+#pragma once
+#include <memory>
+#include <mutex>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include "batch_model.h"
+#include "vb_result.h"
+
+class BatchRecognizer {
+   public:
+    BatchRecognizer(BatchModel *model, float sample_frequency);
+    ~BatchRecognizer();
+
+    void AcceptWaveform(const char *data, int len);  // [REF src/batch_recognizer.cc:115-181]
+    int GetNumPendingChunks();                       // [REF :199-202]
+    const char *FrontResult();                       // [REF :183-189]
+    void Pop();                                      // [REF :191-197]
+    void FinishStream();                             // [REF :37-41]
+    void SetNLSML(bool nlsml);                       // [REF :109-112]
+
+    void EnableCapture();                            // additive: test taps (include/vosk_b200.h)
+    vb::Capture *capture() { return stream_->capture.get(); }
+
+   private:
+    // results are produced on the engine worker thread and consumed on the caller's thread: unlike the
+    // reference's unguarded std::queue [REF src/batch_recognizer.h:50] this one is locked, and it is
+    // shared so a result arriving after the recognizer was freed has somewhere safe to land.
+    struct Sink {
+        std::mutex mu;
+        std::queue<std::string> results;
+        bool nlsml = false;
+    };
+    BatchModel *model_;
+    uint64_t id_;
+    float sample_frequency_;
+    std::shared_ptr<Sink> sink_;
+    std::shared_ptr<vb::Stream> stream_;
+    vb::LinearResampler resampler_;
+    std::vector<int16_t> buffer_;
+    std::string front_;  // keeps the string returned by FrontResult alive until Pop
+    bool finished_ = false;
+};

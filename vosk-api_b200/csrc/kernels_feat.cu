@@ -1,0 +1,432 @@
+// kernels_feat.cu — K1: fused framing / DC removal / pre-emphasis / Povey window / 512-pt FFT / power /
+// mel / log / DCT / lifter, and K1c: online CMN + i-vector statistics + per-chunk solve.
+//
+// Replaces Kaldi cudafeat as driven by the reference's batch pipeline (use_gpu_feature_extraction=true,
+// feature_type="mfcc", mfcc.conf, ivector.conf — [REF src/batch_model.cc:73-77]); options from
+// [REF training/conf/mfcc.conf:1-7] and [REF src/model.cc:250-260].
+//
+// Layout: one CTA per lane (= one stream's chunk).  The lane's samples (carried tail + new chunk) are staged
+// once in shared memory with coalesced 16-byte loads; each warp then owns whole frames, so the FFT, the mel
+// projection and the DCT never leave the SM.  Output rows go straight into the acoustic model's input ring
+// (edge padding rows included), so no separate "build batch with context" pass exists.
+#include <cfloat>
+
+#include "vb_kernels.h"
+
+namespace vb {
+
+__device__ __forceinline__ int ring_slot(const NodeDesc &n, int t) { return ((t - n.t_start) / n.step) & (n.ring - 1); }
+__device__ __forceinline__ float *ring_row(const NodeDesc &n, int ch, int t) {
+    return n.buf + ((size_t)ch * n.ring + ring_slot(n, t)) * n.dim;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+constexpr int kFeatThreads = 256;
+constexpr int kFeatWarps = kFeatThreads / 32;
+
+// dynamic smem layout (floats): wave[kCarryMax + spc] | fft[kFeatWarps][2][512] | logmel[kFeatWarps][40]
+//                               | window[400] | tw[512] | dct_t[1600] | lifter[40]
+extern "C" int vbk_feat_smem_bytes(int spc) {
+    return (int)sizeof(float) * (kCarryMax + spc + kFeatWarps * 1024 + kFeatWarps * 40 + 400 + 512 + 1600 + 40);
+}
+
+__global__ void __launch_bounds__(kFeatThreads) mfcc_kernel(FeatArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const LaneDesc ln = a.lanes[blockIdx.x];
+    const int spc = a.samples_per_chunk;
+    float *wave = sm;
+    float *fft = wave + kCarryMax + spc;
+    float *logmel = fft + kFeatWarps * 1024;
+    float *window = logmel + kFeatWarps * 40;
+    float *tw = window + 400;
+    float *dct_t = tw + 512;
+    float *lifter = dct_t + 1600;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 400; i += kFeatThreads) window[i] = a.tab.window[i];
+    for (int i = tid; i < 512; i += kFeatThreads) tw[i] = a.tab.twiddle[i];
+    for (int i = tid; i < 1600; i += kFeatThreads) dct_t[i] = a.tab.dct_t[i];
+    if (tid < 40) lifter[tid] = a.tab.lifter[tid];
+    // stage samples: carried tail then the new chunk (int16 -> float, values unscaled [REF src/batch_recognizer.cc:153-155])
+    int16_t *carry = a.carry + (size_t)ln.channel * kCarryMax;
+    for (int i = tid; i < ln.carry; i += kFeatThreads) wave[i] = (float)carry[i];
+    {
+        const int16_t *src = a.staging + (size_t)ln.src_row * a.src_stride + ln.src_off;
+        const int n8 = (reinterpret_cast<uintptr_t>(src) & 15) ? 0 : ln.n_samples >> 3;
+        const int4 *src4 = reinterpret_cast<const int4 *>(src);  // 16-byte path when the row start is aligned
+        for (int i = tid; i < n8; i += kFeatThreads) {
+            int4 v = __ldg(src4 + i);
+            const short *h = reinterpret_cast<const short *>(&v);
+            float *d = wave + ln.carry + i * 8;
+#pragma unroll
+            for (int j = 0; j < 8; j++) d[j] = (float)h[j];
+        }
+        for (int i = (n8 << 3) + tid; i < ln.n_samples; i += kFeatThreads) wave[ln.carry + i] = (float)src[i];
+    }
+    __syncthreads();
+    const int total = ln.carry + ln.n_samples;
+    const int nf = ln.frames_after - ln.frames_before;
+    float *re = fft + warp * 1024, *im = re + 512;
+    for (int f = warp; f < nf; f += kFeatWarps) {
+        const float *w = wave + f * kFrameShift;
+        float s = 0.f;
+        for (int i = lane; i < kFrameLen; i += 32) s += w[i];
+        const float mean = warp_sum(s) / kFrameLen;
+        // bit-reversed scatter of the windowed, pre-emphasised frame; zero padding 400..511
+        for (int i = lane; i < kFftSize; i += 32) {
+            float v = 0.f;
+            if (i < kFrameLen) {
+                float x = w[i] - mean;
+                float xp = (i > 0 ? w[i - 1] : w[0]) - mean;
+                v = (x - 0.97f * xp) * window[i];
+            }
+            int r = __brev((unsigned)i) >> 23;
+            re[r] = v;
+            im[r] = 0.f;
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int len = 2; len <= kFftSize; len <<= 1) {
+            const int half = len >> 1, tstep = kFftSize / len;
+            for (int b = lane; b < kFftSize / 2; b += 32) {
+                int k = b & (half - 1);
+                int i0 = ((b - k) << 1) + k, i1 = i0 + half;
+                float wr = tw[2 * k * tstep], wi = tw[2 * k * tstep + 1];
+                float xr = re[i1] * wr - im[i1] * wi, xi = re[i1] * wi + im[i1] * wr;
+                float ar = re[i0], ai = im[i0];
+                re[i1] = ar - xr;
+                im[i1] = ai - xi;
+                re[i0] = ar + xr;
+                im[i0] = ai + xi;
+            }
+            __syncwarp();
+        }
+        for (int i = lane; i < 256; i += 32) re[i] = re[i] * re[i] + im[i] * im[i];
+        __syncwarp();
+        for (int j = lane; j < kNumMel; j += 32) {
+            const int st = a.tab.mel_start[j], n = a.tab.mel_len[j];
+            const float *mw = a.tab.mel_w + j * kMelMaxLen;
+            float e = 0.f;
+            for (int i = 0; i < n; i++) e += __ldg(mw + i) * re[st + i];
+            logmel[warp * 40 + j] = logf(fmaxf(e, FLT_EPSILON));
+        }
+        __syncwarp();
+        const int t = ln.frames_before + f;
+        float *out = ring_row(a.in_node, ln.channel, t);
+        for (int k = lane; k < kNumCeps; k += 32) {
+            float c = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < kNumMel; j++) c += dct_t[j * 40 + k] * logmel[warp * 40 + j];
+            out[k] = c * lifter[k];
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // new carry = samples from the start of the next frame
+    const int next_start = nf > 0 ? nf * kFrameShift : 0;
+    const int keep = (ln.frames_after > 0 || total >= kFrameLen) ? total - next_start : total;
+    if (!ln.last)
+        for (int i = tid; i < keep && i < kCarryMax; i += kFeatThreads) carry[i] = (int16_t)wave[next_start + i];
+    // edge padding of the model input: repeat first / last frame over the model context
+    if (ln.first && ln.frames_after > 0 && ln.frames_before == 0) {
+        const float *src = ring_row(a.in_node, ln.channel, 0);
+        for (int i = tid; i < a.context * 40; i += kFeatThreads) ring_row(a.in_node, ln.channel, -a.context + i / 40)[i % 40] = src[i % 40];
+    }
+    if (ln.last && ln.frames_after > 0) {
+        const float *src = ring_row(a.in_node, ln.channel, ln.frames_after - 1);
+        for (int i = tid; i < a.context * 40; i += kFeatThreads) ring_row(a.in_node, ln.channel, ln.frames_after + i / 40)[i % 40] = src[i % 40];
+    }
+}
+
+extern "C" cudaError_t vbk_mfcc(const FeatArgs *a, cudaStream_t s) {
+    if (a->num_lanes <= 0) return cudaSuccess;
+    static int configured = 0;
+    int smem = vbk_feat_smem_bytes(a->samples_per_chunk);
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(mfcc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    mfcc_kernel<<<a->num_lanes, kFeatThreads, smem, s>>>(*a);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================
+// K1c — online CMN (600-frame window, global-stats smoothing), splice +-3, LDA, diag-UBM top-N posteriors,
+// i-vector statistics (double accumulation), per-chunk Cholesky solve.  One CTA per lane, one warp per frame.
+// =====================================================================================================
+constexpr int kIvThreads = 256;
+constexpr int kIvWarps = kIvThreads / 32;
+constexpr int kMaxGselect = 8;
+constexpr int kMaxIvecPerLane = 4;  // ivec_dim <= 128
+
+// dynamic smem: gamma[kIvWarps][G] floats | splice[kIvWarps][2][splice_dim] | feat[kIvWarps][2][F] |
+//               linw[kIvWarps][D] | glist[G] ints | doubles: A[D*D] b[D]
+static int ivec_smem_bytes(int G, int S, int F, int D) {
+    size_t fl = (size_t)kIvWarps * G + (size_t)kIvWarps * 2 * S + (size_t)kIvWarps * 2 * F + (size_t)kIvWarps * D + G + 8;
+    fl = (fl + 1) & ~(size_t)1;
+    return (int)(fl * 4 + ((size_t)D * D + D) * 8);
+}
+
+__global__ void __launch_bounds__(kIvThreads) ivector_kernel(IvecArgs a) {
+    extern __shared__ __align__(16) float smf[];
+    const LaneDesc ln = a.lanes[blockIdx.x];
+    const IvecModel &m = a.m;
+    const int F = m.feat_dim, D = m.ivec_dim, G = m.num_gauss, S = m.splice_dim;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *gamma = smf;
+    float *splice = gamma + kIvWarps * G;
+    float *feat = splice + kIvWarps * 2 * S;
+    float *linw = feat + kIvWarps * 2 * F;
+    int *glist = reinterpret_cast<int *>(linw + kIvWarps * D);
+    size_t fl = (size_t)kIvWarps * G + (size_t)kIvWarps * 2 * S + (size_t)kIvWarps * 2 * F + (size_t)kIvWarps * D + G + 8;
+    fl = (fl + 1) & ~(size_t)1;
+    double *A = reinterpret_cast<double *>(smf + fl);
+    double *bvec = A + D * D;
+    __shared__ double s_totw[kIvWarps];
+    __shared__ int s_nlist;
+    const int ch = ln.channel;
+    double *cm_sum = a.st.cmvn_sum + (size_t)ch * F;
+    float *nring = a.st.norm_ring + (size_t)ch * kNormRing * F;
+    double *lin = a.st.lin + (size_t)ch * D;
+    double *quad = a.st.quad + (size_t)ch * D * D;
+    if (ln.first) {  // stream start: prior  (OnlineIvectorEstimationStats ctor)
+        for (int i = tid; i < D * D; i += kIvThreads) quad[i] = (i / D == i % D) ? 1.0 : 0.0;
+        for (int i = tid; i < D; i += kIvThreads) lin[i] = i == 0 ? (double)m.prior_offset : 0.0;
+        if (tid < F) cm_sum[tid] = 0.0;
+        if (tid == 0) a.st.num_frames[ch] = 0.0;
+    }
+    for (int i = tid; i < kIvWarps * G; i += kIvThreads) gamma[i] = 0.f;
+    for (int i = tid; i < kIvWarps * D; i += kIvThreads) linw[i] = 0.f;
+    if (tid < kIvWarps) s_totw[tid] = 0.0;
+    __syncthreads();
+    // ---- A. sliding-window CMN over the new frames (thread per dimension, sequential in time) ----
+    if (tid < F) {
+        double s = cm_sum[tid];
+        for (int t = ln.frames_before; t < ln.frames_after; t++) {
+            float x = ring_row(a.in_node, ch, t)[tid];
+            s += (double)x;
+            if (t >= m.cmn_window) s -= (double)ring_row(a.in_node, ch, t - m.cmn_window)[tid];
+            double n = t + 1 < m.cmn_window ? t + 1 : m.cmn_window;
+            double fg = n < m.cmn_window ? fmin((double)m.cmn_window - n, (double)m.global_frames) : 0.0;
+            double tot = s;
+            if (fg > 0.0) tot += fg / m.gcmvn_count * m.gcmvn_sum[tid];
+            nring[(t & (kNormRing - 1)) * F + tid] = (float)((double)x - tot / (n + fg));
+        }
+        cm_sum[tid] = s;
+    }
+    __syncthreads();
+    // ---- B. per frame: splice, LDA (raw + normalised), UBM posteriors, statistics ----
+    const int last_avail = ln.frames_after - 1;
+    float *xs = splice + warp * 2 * S, *xn = xs + S;
+    float *fu = feat + warp * 2 * F, *fn = fu + F;
+    float lin_acc[kMaxIvecPerLane] = {0.f, 0.f, 0.f, 0.f};
+    double totw = 0.0;
+    for (int t = ln.iv_end_before + warp; t < ln.iv_end_after; t += kIvWarps) {
+        for (int i = lane; i < S; i += 32) {
+            int o = i / F - 3, d = i % F;
+            int tt = min(max(t + o, 0), last_avail);
+            xs[i] = ring_row(a.in_node, ch, tt)[d];
+            xn[i] = nring[(tt & (kNormRing - 1)) * F + d];
+        }
+        __syncwarp();
+        for (int d = lane; d < F; d += 32) {
+            float su = __ldg(m.lda_t + (size_t)S * F + d), sn = su;
+            for (int k = 0; k < S; k++) {
+                float w = __ldg(m.lda_t + (size_t)k * F + d);
+                su = fmaf(w, xs[k], su);
+                sn = fmaf(w, xn[k], sn);
+            }
+            fu[d] = su;
+            fn[d] = sn;
+        }
+        __syncwarp();
+        // diag-UBM log-likelihoods: lane owns gaussians lane, lane+32, ...
+        float best_v[kMaxGselect];
+        int best_g[kMaxGselect];
+        const int per = (G + 31) / 32;
+        // keep this lane's values in a small local array (G <= 1024)
+        float llv[32];
+        for (int j = 0; j < per; j++) {
+            int g = lane + 32 * j;
+            float s = -FLT_MAX;
+            if (g < G) {
+                s = __ldg(m.gconsts + g);
+                for (int d = 0; d < F; d++) {
+                    float x = fn[d];
+                    s += __ldg(m.mi_t + (size_t)d * G + g) * x - 0.5f * __ldg(m.iv_t + (size_t)d * G + g) * x * x;
+                }
+            }
+            llv[j] = s;
+        }
+        const int ng = min(m.num_gselect, G);
+        for (int r = 0; r < ng; r++) {
+            float bv = -FLT_MAX;
+            int bg = 0x7fffffff;
+            for (int j = 0; j < per; j++)
+                if (llv[j] > bv) { bv = llv[j]; bg = lane + 32 * j; }
+            for (int o = 16; o; o >>= 1) {
+                float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                int og = __shfl_xor_sync(0xffffffffu, bg, o);
+                if (ov > bv || (ov == bv && og < bg)) { bv = ov; bg = og; }
+            }
+            best_v[r] = bv;
+            best_g[r] = bg;
+            if ((bg & 31) == lane) llv[bg >> 5] = -FLT_MAX;
+        }
+        float post[kMaxGselect], tot = 0.f;
+        for (int r = 0; r < ng; r++) { post[r] = expf(best_v[r] - best_v[0]); tot += post[r]; }
+        float kept = 0.f;
+        for (int r = 0; r < ng; r++) {
+            post[r] /= tot;
+            if (r > 0 && post[r] < m.min_post) post[r] = 0.f;
+            kept += post[r];
+        }
+        for (int r = 0; r < ng; r++) {
+            float w = post[r] / kept * m.posterior_scale;
+            post[r] = w;
+            if (w != 0.f) {
+                if (lane == 0) gamma[warp * G + best_g[r]] += w;
+                totw += (double)w;
+            }
+        }
+        // linear term: lin[d] += w * sum_a SiM[g][a][d] * fu[a]
+        for (int r = 0; r < ng; r++) {
+            if (post[r] == 0.f) continue;
+            const float *sm_g = m.sim + (size_t)best_g[r] * F * D;
+#pragma unroll
+            for (int j = 0; j < kMaxIvecPerLane; j++) {
+                int d = lane + 32 * j;
+                if (d < D) {
+                    float s = 0.f;
+                    for (int q = 0; q < F; q++) s = fmaf(__ldg(sm_g + (size_t)q * D + d), fu[q], s);
+                    lin_acc[j] += post[r] * s;
+                }
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxIvecPerLane; j++) {
+        int d = lane + 32 * j;
+        if (d < D) linw[warp * D + d] = lin_acc[j];
+    }
+    if (lane == 0) s_totw[warp] = totw;
+    __syncthreads();
+    // ---- C. fold the chunk's statistics into the channel state (fixed summation order) ----
+    if (tid == 0) s_nlist = 0;
+    __syncthreads();
+    for (int g = tid; g < G; g += kIvThreads) {
+        float s = 0.f;
+        for (int w = 0; w < kIvWarps; w++) s += gamma[w * G + g];
+        gamma[g] = s;  // row 0 now holds the per-gaussian occupancy of this chunk
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int n = 0;
+        for (int g = 0; g < G; g++)
+            if (gamma[g] != 0.f) glist[n++] = g;
+        s_nlist = n;
+    }
+    __syncthreads();
+    const int nl = s_nlist;
+    double tw = 0.0;
+    for (int w = 0; w < kIvWarps; w++) tw += s_totw[w];
+    const double nf_old = a.st.num_frames[ch], nf_new = nf_old + tw;
+    double change = 0.0;
+    if (m.max_count > 0.f)
+        change = fmax(nf_new, (double)m.max_count) / m.max_count - fmax(nf_old, (double)m.max_count) / m.max_count;
+    for (int i = tid; i < D * D; i += kIvThreads) {
+        double q = 0.0;
+        for (int k = 0; k < nl; k++) {
+            int g = glist[k];
+            q += (double)gamma[g] * (double)__ldg(m.U + (size_t)g * D * D + i);
+        }
+        if (i / D == i % D) q += change;
+        double v = quad[i] + q;
+        quad[i] = v;
+        A[i] = v;
+    }
+    for (int d = tid; d < D; d += kIvThreads) {
+        double s = 0.0;
+        for (int w = 0; w < kIvWarps; w++) s += (double)linw[w * D + d];
+        if (d == 0) s += (double)m.prior_offset * change;
+        double v = lin[d] + s;
+        lin[d] = v;
+        bvec[d] = v;
+    }
+    __syncthreads();
+    if (tid == 0) a.st.num_frames[ch] = nf_new;
+    // ---- D. solve quad * x = lin by Cholesky (what the reference's batch path does per chunk) ----
+    float *out = a.st.ivec + (size_t)ch * D;
+    if (nf_new <= 0.0) {
+        for (int d = tid; d < D; d += kIvThreads) out[d] = 0.f;
+        return;
+    }
+    for (int j = 0; j < D; j++) {
+        if (tid == 0) {
+            double d = A[j * D + j];
+            for (int k = 0; k < j; k++) d -= A[j * D + k] * A[j * D + k];
+            A[j * D + j] = sqrt(fmax(d, 1e-300));
+        }
+        __syncthreads();
+        for (int i = j + 1 + tid; i < D; i += kIvThreads) {
+            double s = A[i * D + j];
+            for (int k = 0; k < j; k++) s -= A[i * D + k] * A[j * D + k];
+            A[i * D + j] = s / A[j * D + j];
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+        for (int i = 0; i < D; i++) {
+            double s = 0.0;
+            for (int k = lane; k < i; k += 32) s += A[i * D + k] * bvec[k];
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) bvec[i] = (bvec[i] - s) / A[i * D + i];
+            __syncwarp();
+        }
+        for (int i = D - 1; i >= 0; i--) {
+            double s = 0.0;
+            for (int k = i + 1 + lane; k < D; k += 32) s += A[k * D + i] * bvec[k];
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) bvec[i] = (bvec[i] - s) / A[i * D + i];
+            __syncwarp();
+        }
+        for (int d = lane; d < D; d += 32) out[d] = (float)(bvec[d] - (d == 0 ? (double)m.prior_offset : 0.0));
+    }
+}
+
+extern "C" cudaError_t vbk_ivector(const IvecArgs *a, cudaStream_t s) {
+    if (a->num_lanes <= 0) return cudaSuccess;
+    if (a->m.num_gauss > 1024 || a->m.ivec_dim > 32 * kMaxIvecPerLane || a->m.num_gselect > kMaxGselect) return cudaErrorInvalidValue;
+    int smem = ivec_smem_bytes(a->m.num_gauss, a->m.splice_dim, a->m.feat_dim, a->m.ivec_dim);
+    static int configured = 0;
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(ivector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    ivector_kernel<<<a->num_lanes, kIvThreads, smem, s>>>(*a);
+    return cudaGetLastError();
+}
+
+// generic ring-row copy used by the debug capture taps
+__global__ void copy_rows_kernel(NodeDesc node, int ch, int t_begin, int n_rows, float *dst) {
+    int total = n_rows * node.dim;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int r = i / node.dim, c = i % node.dim;
+        dst[i] = ring_row(node, ch, t_begin + r * node.step)[c];
+    }
+}
+extern "C" cudaError_t vbk_copy_rows(NodeDesc node, int ch, int t_begin, int n_rows, float *dst, cudaStream_t s) {
+    if (n_rows <= 0) return cudaSuccess;
+    int total = n_rows * node.dim;
+    copy_rows_kernel<<<(total + 255) / 256, 256, 0, s>>>(node, ch, t_begin, n_rows, dst);
+    return cudaGetLastError();
+}
+
+}  // namespace vb

@@ -1,0 +1,115 @@
+// vb_common.h — shared host/device definitions of the B200 batch recognition engine.
+//
+// The engine replaces everything below the reference's BatchModel/BatchRecognizer
+// [REF src/batch_model.cc], [REF src/batch_recognizer.cc] (Kaldi cudafeat / BatchedStaticNnet3 /
+// CudaDecoder).  One Engine drives one GPU; streams occupy "channels" (persistent per-stream device
+// state) and every engine step processes one chunk for each of up to max_lanes channels ("lanes").
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+#define VB_CUDA_CHECK(expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            char b__[512];                                                                               \
+            snprintf(b__, sizeof b__, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, \
+                     cudaGetErrorString(e__));                                                           \
+            throw std::runtime_error(b__);                                                               \
+        }                                                                                                \
+    } while (0)
+
+namespace vb {
+
+void log_msg(int level, const char *fmt, ...);  // level: -1 error, 0 info, >0 verbose (vosk_set_log_level semantics)
+extern int g_log_level;
+
+constexpr int kFrameLen = 400;    // 25 ms @ 16 kHz   [REF training/conf/mfcc.conf] + Kaldi defaults
+constexpr int kFrameShift = 160;  // 10 ms
+constexpr int kFftSize = 512;
+constexpr int kNumMel = 40;
+constexpr int kNumCeps = 40;
+constexpr int kSubsample = 3;     // [REF src/batch_model.cc:82]
+constexpr int kMaxNodes = 48;
+constexpr int kMaxOffsets = 5;
+
+// ---- engine configuration (defaults follow [REF src/batch_model.cc:69-88] where the reference has one) ----
+struct Config {
+    int frames_per_chunk = 51;  // [REF src/batch_model.cc:88]
+    int max_lanes = 512;        // reference: max_batch_size = 32  [REF :70]; raised — a batch of 32 starves a B200
+    int num_channels = 600;     // [REF :71]
+    float beam = 13.0f;         // [REF :79]
+    float lattice_beam = 6.0f;  // [REF :80]
+    int max_active = 7000;      // [REF :78]
+    int min_active = 200;       // Kaldi LatticeFasterDecoderConfig default
+    float beam_delta = 0.5f;    // Kaldi default
+    float acoustic_scale = 1.0f;  // [REF :81]
+    int tok_cap = 65536;        // tokens per frame per channel
+    int cand_cap = 262144;      // candidate records per frame (per resident CTA)
+    int hash_size = 131072;     // open-addressing slots per resident CTA (power of two, >= 2*tok_cap)
+    int max_seconds = 24;       // token-log capacity per channel (decoder frames = seconds * 100 / 3)
+    int log_tokens_per_frame = 4096;  // average logged tokens per frame the token log is sized for
+    int device = 0;
+    int num_gselect = 5;        // ivector.conf
+    float min_post = 0.025f, posterior_scale = 0.1f, max_count = 100.0f;  // [REF src/model.cc:257]
+    int cmn_window = 600, global_frames = 200;
+    int use_tensor_cores = 1;   // TDNN-F GEMMs on tcgen05 (3xTF32 split, fp32 accumulate); 0 = fp32 FFMA kernel
+    int debug_capture = 0;      // allow per-stream capture of intermediates (tests)
+};
+
+// ---- acoustic model graph description (device-visible, passed by value to kernels) ----
+struct NodeDesc {
+    int dim;        // feature dimension of a row
+    int step;       // time units between consecutive rows (1 or 3)
+    int ring;       // ring size in rows (power of two)
+    int t_start;    // first time index this node ever holds
+    int cum_right;  // input frames (time units) of look-ahead this node needs beyond its own time
+    float *buf;     // [num_channels][ring][dim]
+};
+
+struct OpDesc {
+    int in_node, out_node, byp_node;  // byp_node = -1 if none
+    int n_off;
+    int offs[kMaxOffsets];
+    int uses_ivec;  // append the lane's i-vector to the spliced input (tdnn1)
+    int K, N;       // K = n_off*in_dim (+ ivec_dim)
+    int relu, has_bn;
+    const float *W;     // [N][K] fp32
+    const float *W_hi;  // tf32 split (low 13 mantissa bits cleared), [N][K]
+    const float *W_lo;  // W - W_hi
+    const float *bias;  // [N] or null
+    const float *bn_scale, *bn_offset;
+    float bypass_scale;
+};
+
+// per step, per lane (host -> device)
+struct LaneDesc {
+    int channel;
+    int n_samples;     // new samples in this chunk
+    int carry;         // samples carried from the previous chunk (device-resident)
+    int frames_before; // MFCC frames that existed before this chunk
+    int frames_after;  // ... after (F_k)
+    int first, last;   // first / last chunk of the stream
+    int iv_end_before; // spliced frames already accumulated into the i-vector stats
+    int iv_end_after;
+    int in_end_before; // node-0 timeline end (exclusive) before / after this chunk, incl. edge padding
+    int in_end_after;
+    int dec_frames_before;  // decoder frames consumed before this step
+    int src_row;       // sample source: staging + src_row * src_stride + src_off   (int16 units)
+    int src_off;
+};
+
+// per step, per node, per lane (device, written by the plan kernel)
+struct NodeLane {
+    int t_begin;  // first new time
+    int n_rows;   // new rows this step
+};
+
+inline int num_frames_for(int64_t samples) {
+    return samples < kFrameLen ? 0 : (int)(1 + (samples - kFrameLen) / kFrameShift);
+}
+
+}  // namespace vb

@@ -1,0 +1,633 @@
+// vb_engine.cu — per-GPU batch engine (host side).  See vb_engine.h for the reference objects it replaces.
+#include "vb_engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace vb {
+
+namespace {
+int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+}  // namespace
+
+template <typename T>
+static T *dev_alloc(std::vector<void *> &allocs, size_t n, int fill = -2) {
+    void *p = nullptr;
+    VB_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    if (fill != -2) VB_CUDA_CHECK(cudaMemset(p, fill, std::max<size_t>(n, 1) * sizeof(T)));
+    allocs.push_back(p);
+    return reinterpret_cast<T *>(p);
+}
+template <typename T>
+static T *dev_upload(std::vector<void *> &allocs, const T *src, size_t n) {
+    T *p = dev_alloc<T>(allocs, n);
+    VB_CUDA_CHECK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+template <typename T>
+static T *dev_upload(std::vector<void *> &allocs, const std::vector<T> &v) {
+    return dev_upload(allocs, v.data(), v.size());
+}
+
+Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg) {
+    if (cfg_.frames_per_chunk < 3) throw std::runtime_error("frames-per-chunk must be >= 3");
+    if (cfg_.max_lanes > 1024) cfg_.max_lanes = 1024;
+    if (cfg_.max_lanes > cfg_.num_channels) cfg_.max_lanes = cfg_.num_channels;
+    if (cfg_.hash_size & (cfg_.hash_size - 1)) throw std::runtime_error("hash-size must be a power of two");
+    if (model.graph.has_negative_eps)
+        throw std::runtime_error("HCLG has negative-weight epsilon arcs: not supported by the token log (DESIGN.md)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= cfg_.device)
+        throw std::runtime_error(std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range"));
+    VB_CUDA_CHECK(cudaSetDevice(cfg_.device));
+    VB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto &ev : ev_) VB_CUDA_CHECK(cudaEventCreate(&ev));
+    upload_model();
+    alloc_state();
+    thread_ = std::thread([this] { worker(); });
+}
+
+Engine::~Engine() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_work_.notify_all();
+    if (thread_.joinable()) thread_.join();
+    cudaSetDevice(cfg_.device);
+    cudaStreamSynchronize(stream_);
+    for (void *p : allocs_) cudaFree(p);
+    if (h_staging_) cudaFreeHost(h_staging_);
+    if (h_lanes_) cudaFreeHost(h_lanes_);
+    if (h_cs_) cudaFreeHost(h_cs_);
+    if (h_path_) cudaFreeHost(h_path_);
+    if (h_capture_) cudaFreeHost(h_capture_);
+    for (auto &ev : ev_) cudaEventDestroy(ev);
+    cudaStreamDestroy(stream_);
+}
+
+void Engine::upload_model() {
+    const Model &m = model_;
+    // ---- MFCC tables (double on the host, fp32 on the device) ----
+    {
+        std::vector<float> window(kFrameLen), tw(512), dct_t(1600), lifter(40), mel_w(kNumMel * kMelMaxLen, 0.f);
+        std::vector<int> mel_start(kNumMel), mel_len(kNumMel);
+        for (int i = 0; i < kFrameLen; i++) window[i] = (float)std::pow(0.5 - 0.5 * std::cos(2.0 * M_PI * i / (kFrameLen - 1)), 0.85);
+        for (int k = 0; k < 256; k++) {
+            tw[2 * k] = (float)std::cos(-2.0 * M_PI * k / kFftSize);
+            tw[2 * k + 1] = (float)std::sin(-2.0 * M_PI * k / kFftSize);
+        }
+        auto mel = [](double f) { return 1127.0 * std::log(1.0 + f / 700.0); };
+        const double ml = mel(20.0), mh = mel(8000.0 - 400.0), delta = (mh - ml) / (kNumMel + 1), bw = 16000.0 / kFftSize;
+        for (int j = 0; j < kNumMel; j++) {
+            double l = ml + j * delta, c = ml + (j + 1) * delta, r = ml + (j + 2) * delta;
+            int first = -1, last = -1;
+            std::vector<float> w(256, 0.f);
+            for (int i = 0; i < 256; i++) {
+                double mm = mel(bw * i);
+                if (mm > l && mm < r) {
+                    w[i] = (float)(mm <= c ? (mm - l) / (c - l) : (r - mm) / (r - c));
+                    if (first < 0) first = i;
+                    last = i;
+                }
+            }
+            mel_start[j] = first < 0 ? 0 : first;
+            mel_len[j] = first < 0 ? 0 : last - first + 1;
+            if (mel_len[j] > kMelMaxLen) throw std::runtime_error("mel filter too wide");
+            for (int i = 0; i < mel_len[j]; i++) mel_w[j * kMelMaxLen + i] = w[first + i];
+        }
+        for (int k = 0; k < 40; k++)
+            for (int j = 0; j < 40; j++)
+                dct_t[j * 40 + k] = (float)(k == 0 ? std::sqrt(1.0 / 40) : std::sqrt(2.0 / 40) * std::cos(M_PI / 40 * (j + 0.5) * k));
+        for (int i = 0; i < 40; i++) lifter[i] = (float)(1.0 + 0.5 * 22.0 * std::sin(M_PI * i / 22.0));
+        feat_tab_.window = dev_upload(allocs_, window);
+        feat_tab_.twiddle = dev_upload(allocs_, tw);
+        feat_tab_.mel_start = dev_upload(allocs_, mel_start);
+        feat_tab_.mel_len = dev_upload(allocs_, mel_len);
+        feat_tab_.mel_w = dev_upload(allocs_, mel_w);
+        feat_tab_.dct_t = dev_upload(allocs_, dct_t);
+        feat_tab_.lifter = dev_upload(allocs_, lifter);
+    }
+    // ---- i-vector extractor: derived quantities in double (Kaldi IvectorExtractor::ComputeDerivedVars) ----
+    {
+        const int F = m.feat_dim, D = m.ivec_dim, G = m.num_gauss, S = 7 * F;
+        const Tensor &lda = m.iv_lda.at("lda");
+        if (lda.shape[0] != F || lda.shape[1] != S + 1) throw std::runtime_error("final.mat: unexpected shape");
+        std::vector<float> lda_t((size_t)(S + 1) * F);
+        for (int a = 0; a < F; a++)
+            for (int k = 0; k <= S; k++) lda_t[(size_t)k * F + a] = lda.f32()[(size_t)a * (S + 1) + k];
+        const float *mi = m.iv_dubm.at("means_invvars").f32(), *iv = m.iv_dubm.at("inv_vars").f32();
+        std::vector<float> mi_t((size_t)F * G), iv_t((size_t)F * G);
+        for (int g = 0; g < G; g++)
+            for (int a = 0; a < F; a++) {
+                mi_t[(size_t)a * G + g] = mi[(size_t)g * F + a];
+                iv_t[(size_t)a * G + g] = iv[(size_t)g * F + a];
+            }
+        const float *M = m.iv_ie.at("M").f32(), *Si = m.iv_ie.at("sigma_inv").f32();
+        std::vector<float> sim((size_t)G * F * D), U((size_t)G * D * D);
+        std::vector<double> tmp((size_t)F * D);
+        for (int g = 0; g < G; g++) {
+            const float *Mg = M + (size_t)g * F * D, *Sg = Si + (size_t)g * F * F;
+            for (int a = 0; a < F; a++)
+                for (int d = 0; d < D; d++) {
+                    double s = 0;
+                    for (int b = 0; b < F; b++) s += (double)Sg[a * F + b] * Mg[b * D + d];
+                    tmp[(size_t)a * D + d] = s;
+                    sim[((size_t)g * F + a) * D + d] = (float)s;
+                }
+            for (int d = 0; d < D; d++)
+                for (int e2 = 0; e2 < D; e2++) {
+                    double s = 0;
+                    for (int a = 0; a < F; a++) s += (double)Mg[a * D + d] * tmp[(size_t)a * D + e2];
+                    U[((size_t)g * D + d) * D + e2] = (float)s;
+                }
+        }
+        const double *cm = m.iv_cmvn.at("stats").f64();
+        std::vector<double> gsum(cm, cm + F);
+        iv_model_ = IvecModel{F, D, G, S,
+                              dev_upload(allocs_, lda_t), dev_upload(allocs_, m.iv_dubm.at("gconsts").f32(), (size_t)G),
+                              dev_upload(allocs_, mi_t), dev_upload(allocs_, iv_t), dev_upload(allocs_, sim), dev_upload(allocs_, U),
+                              dev_upload(allocs_, gsum), cm[F], m.prior_offset,
+                              cfg_.num_gselect, cfg_.min_post, cfg_.posterior_scale, cfg_.max_count, cfg_.cmn_window, cfg_.global_frames};
+    }
+    // ---- acoustic model nodes: row grid (every frame / every 3rd), first needed time, look-ahead ----
+    const int ctx = m.context, C = cfg_.num_channels;
+    const int nn = (int)m.node_dim.size();
+    max_in_rows_ = cfg_.frames_per_chunk + 3 + 2 * ctx;
+    std::vector<int> step(nn, kSubsample), t_first(nn, 1 << 30), cum_right(nn, 0);
+    t_first[nn - 1] = 0;
+    for (int o = (int)m.ops.size() - 1; o >= 0; o--) {
+        const AmOp &op = m.ops[o];
+        const int out = o + 1;
+        bool mult3 = true;
+        int mn = 0;
+        for (int off : op.offs) {
+            if (off % kSubsample) mult3 = false;
+            mn = std::min(mn, off);
+        }
+        if (step[out] == 1 || !mult3) step[op.in_node] = 1;
+        t_first[op.in_node] = std::min(t_first[op.in_node], t_first[out] + mn);
+        if (op.byp_node >= 0) {
+            if (step[out] == 1) step[op.byp_node] = 1;
+            t_first[op.byp_node] = std::min(t_first[op.byp_node], t_first[out]);
+        }
+    }
+    if (t_first[0] != -ctx || step[0] != 1) throw std::runtime_error("internal: context computation mismatch");
+    for (size_t o = 0; o < m.ops.size(); o++) {
+        int mx = 0;
+        for (int off : m.ops[o].offs) mx = std::max(mx, off);
+        cum_right[o + 1] = cum_right[m.ops[o].in_node] + mx;
+    }
+    nodes_.resize(nn);
+    for (int n = 0; n < nn; n++) {
+        int rows = step[n] == 1 ? max_in_rows_ + 8 : max_in_rows_ / kSubsample + 8;
+        if (n == 0) rows += cfg_.cmn_window;
+        nodes_[n] = NodeDesc{m.node_dim[n], step[n], next_pow2(rows), t_first[n], cum_right[n], nullptr};
+        nodes_[n].buf = dev_alloc<float>(allocs_, (size_t)C * nodes_[n].ring * nodes_[n].dim, 0);
+    }
+    d_nodes_ = dev_upload(allocs_, nodes_);
+    ops_.resize(m.ops.size());
+    for (size_t o = 0; o < m.ops.size(); o++) {
+        const AmOp &op = m.ops[o];
+        OpDesc d{};
+        d.in_node = op.in_node;
+        d.out_node = (int)o + 1;
+        d.byp_node = op.byp_node;
+        d.n_off = (int)op.offs.size();
+        for (int i = 0; i < d.n_off; i++) d.offs[i] = op.offs[i];
+        d.uses_ivec = op.uses_ivec;
+        d.K = op.K;
+        d.N = op.N;
+        d.relu = op.relu_bn;
+        d.has_bn = op.relu_bn;
+        float *w = dev_upload(allocs_, op.W->f32(), (size_t)op.N * op.K);
+        float *hi = dev_alloc<float>(allocs_, (size_t)op.N * op.K), *lo = dev_alloc<float>(allocs_, (size_t)op.N * op.K);
+        VB_CUDA_CHECK(vbk_split_tf32(w, hi, lo, (long long)op.N * op.K, stream_));
+        d.W = w;
+        d.W_hi = hi;
+        d.W_lo = lo;
+        d.bias = op.b ? dev_upload(allocs_, op.b->f32(), (size_t)op.N) : nullptr;
+        d.bn_scale = op.bn_s ? dev_upload(allocs_, op.bn_s->f32(), (size_t)op.N) : nullptr;
+        d.bn_offset = op.bn_o ? dev_upload(allocs_, op.bn_o->f32(), (size_t)op.N) : nullptr;
+        d.bypass_scale = m.bypass_scale;
+        ops_[o] = d;
+    }
+    // ---- decoding graph: one 16-byte record per arc ----
+    {
+        const Graph &g = m.graph;
+        std::vector<int4> arcs((size_t)g.num_arcs);
+        for (int a = 0; a < g.num_arcs; a++) {
+            int wbits;
+            memcpy(&wbits, &g.arc_w[a], 4);
+            arcs[a] = make_int4(wbits, g.arc_next[a], g.arc_pdf[a], g.arc_olabel[a]);
+        }
+        graph_ = GraphDev{g.num_states, g.num_arcs, g.start, dev_upload(allocs_, g.final_cost), dev_upload(allocs_, g.e_begin),
+                          dev_upload(allocs_, g.eps_begin), dev_upload(allocs_, arcs)};
+    }
+    VB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+void Engine::alloc_state() {
+    const int C = cfg_.num_channels, L = cfg_.max_lanes, F = model_.feat_dim, D = model_.ivec_dim;
+    const int spc = samples_per_chunk();
+    const int nn = (int)nodes_.size();
+    iv_state_.cmvn_sum = dev_alloc<double>(allocs_, (size_t)C * F, 0);
+    iv_state_.norm_ring = dev_alloc<float>(allocs_, (size_t)C * kNormRing * F, 0);
+    iv_state_.lin = dev_alloc<double>(allocs_, (size_t)C * D, 0);
+    iv_state_.quad = dev_alloc<double>(allocs_, (size_t)C * D * D, 0);
+    iv_state_.num_frames = dev_alloc<double>(allocs_, (size_t)C, 0);
+    iv_state_.ivec = dev_alloc<float>(allocs_, (size_t)C * D, 0);
+    d_carry_ = dev_alloc<int16_t>(allocs_, (size_t)C * kCarryMax, 0);
+    d_staging_ = dev_alloc<int16_t>(allocs_, (size_t)L * spc, 0);
+    VB_CUDA_CHECK(cudaMallocHost((void **)&h_staging_, (size_t)L * spc * sizeof(int16_t)));
+    d_lanes_ = dev_alloc<LaneDesc>(allocs_, (size_t)L, 0);
+    VB_CUDA_CHECK(cudaMallocHost((void **)&h_lanes_, (size_t)L * sizeof(LaneDesc)));
+    d_node_end_ = dev_alloc<int>(allocs_, (size_t)C * kMaxNodes, 0);
+    d_table_ = dev_alloc<NodeLane>(allocs_, (size_t)nn * L, 0);
+    d_rowoff_ = dev_alloc<int>(allocs_, (size_t)nn * (L + 1), 0);
+    // decoder
+    max_frames_ = cfg_.max_seconds * 100 / kSubsample + 2;
+    log_cap_ = max_frames_ * std::min(cfg_.max_active + 1, cfg_.log_tokens_per_frame) + cfg_.tok_cap;
+    path_cap_ = 4 * max_frames_ + 64;
+    DecArgs &d = dec_;
+    d.g = graph_;
+    d.beam = cfg_.beam;
+    d.beam_delta = cfg_.beam_delta;
+    d.acoustic_scale = cfg_.acoustic_scale;
+    d.max_active = cfg_.max_active;
+    d.min_active = cfg_.min_active;
+    d.tok_cap = cfg_.tok_cap;
+    d.cand_cap = cfg_.cand_cap;
+    d.hash_size = cfg_.hash_size;
+    d.log_cap = log_cap_;
+    d.max_frames = max_frames_;
+    d.path_cap = path_cap_;
+    d.out_node = nodes_.back();
+    d.out_table = d_table_ + (size_t)(nn - 1) * L;
+    d.cs = dev_alloc<DecChannelState>(allocs_, (size_t)C, 0);
+    d.tok_state = dev_alloc<int>(allocs_, (size_t)C * 2 * cfg_.tok_cap);
+    d.tok_cost = dev_alloc<float>(allocs_, (size_t)C * 2 * cfg_.tok_cap);
+    d.tok_arc = dev_alloc<int>(allocs_, (size_t)C * 2 * cfg_.tok_cap);
+    d.tok_prev = dev_alloc<int>(allocs_, (size_t)C * 2 * cfg_.tok_cap);
+    d.log_prev = dev_alloc<int>(allocs_, (size_t)C * log_cap_);
+    d.log_arc = dev_alloc<int>(allocs_, (size_t)C * log_cap_);
+    d.log_cost = dev_alloc<float>(allocs_, (size_t)C * log_cap_);
+    d.log_state = cfg_.debug_capture ? dev_alloc<int>(allocs_, (size_t)C * log_cap_) : nullptr;
+    d.log_frame_off = dev_alloc<int>(allocs_, (size_t)C * (max_frames_ + 2), 0);
+    d.path = dev_alloc<int>(allocs_, (size_t)C * path_cap_, 0);
+    d.grid = std::min(vbk_decode_max_grid(cfg_.device), L);
+    const size_t G = (size_t)d.grid;
+    d.hash_key = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0xff);
+    d.hash_val = dev_alloc<unsigned long long>(allocs_, G * cfg_.hash_size, 0xff);
+    d.hash_tok = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0);
+    d.cand_packed = dev_alloc<unsigned long long>(allocs_, G * cfg_.cand_cap);
+    d.cand_slot = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
+    d.cand_src = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
+    d.rank = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+    d.counters = dev_alloc<unsigned long long>(allocs_, 8, 0);
+    VB_CUDA_CHECK(cudaMallocHost((void **)&h_cs_, (size_t)L * sizeof(DecChannelState)));
+    VB_CUDA_CHECK(cudaMallocHost((void **)&h_path_, (size_t)L * path_cap_ * sizeof(int)));
+    if (cfg_.debug_capture) {
+        capture_floats_ = (size_t)(max_in_rows_ + 8) * std::max(model_.num_pdfs, F);
+        d_capture_ = dev_alloc<float>(allocs_, capture_floats_);
+        VB_CUDA_CHECK(cudaMallocHost((void **)&h_capture_, capture_floats_ * sizeof(float)));
+    }
+    free_channels_.resize(C);
+    for (int i = 0; i < C; i++) free_channels_[i] = C - 1 - i;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    log_msg(0, "engine on device %d: %d channels, %d lanes/step, chunk %d frames, HBM used %.1f GB of %.1f GB", cfg_.device, C, L,
+            cfg_.frames_per_chunk, (total_b - free_b) / 1e9, total_b / 1e9);
+}
+
+std::shared_ptr<Stream> Engine::open_stream() {
+    auto s = std::make_shared<Stream>();
+    std::lock_guard<std::mutex> lk(mu_);
+    s->id = next_id_++;
+    return s;
+}
+
+void Engine::push(const std::shared_ptr<Stream> &s, const int16_t *samples, int n, bool last) {
+    Stream::Chunk ch;
+    ch.samples.assign(samples, samples + n);
+    ch.last = last;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (s->finished) return;  // chunks after the last one are ignored
+        if (last) s->finished = true;
+        s->pending.push_back(std::move(ch));
+        s->pending_chunks.fetch_add(1);
+        outstanding_++;
+        if (!s->queued) {
+            s->queued = true;
+            ready_.push_back(s);
+        }
+    }
+    cv_work_.notify_one();
+}
+
+void Engine::wait() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [this] { return outstanding_ == 0; });
+}
+
+StepStats Engine::stats() {
+    std::lock_guard<std::mutex> lk(stats_mu_);
+    return stats_;
+}
+void Engine::reset_stats() {
+    std::lock_guard<std::mutex> lk(stats_mu_);
+    stats_ = StepStats{};
+}
+
+void Engine::worker() {
+    cudaSetDevice(cfg_.device);
+    std::vector<Lane> lanes;
+    for (;;) {
+        lanes.clear();
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_work_.wait(lk, [this] { return stop_ || !ready_.empty(); });
+            if (stop_) return;
+            std::deque<std::shared_ptr<Stream>> deferred;
+            while (!ready_.empty() && (int)lanes.size() < cfg_.max_lanes) {
+                std::shared_ptr<Stream> s = ready_.front();
+                ready_.pop_front();
+                if (s->channel < 0) {
+                    if (free_channels_.empty()) {  // all channels busy: the stream waits for one to finish
+                        deferred.push_back(s);
+                        continue;
+                    }
+                    s->channel = free_channels_.back();
+                    free_channels_.pop_back();
+                }
+                Lane ln;
+                ln.s = s;
+                ln.chunk = std::move(s->pending.front());
+                s->pending.pop_front();
+                lanes.push_back(std::move(ln));
+            }
+            for (auto it = deferred.rbegin(); it != deferred.rend(); ++it) ready_.push_front(*it);
+            if (lanes.empty()) {
+                // only channel-less streams are ready; wait for a channel to be released
+                cv_work_.wait_for(lk, std::chrono::milliseconds(1));
+                continue;
+            }
+        }
+        try {
+            step(lanes, nullptr, 0);
+        } catch (const std::exception &ex) {
+            log_msg(-1, "engine step failed: %s", ex.what());
+            for (auto &ln : lanes)
+                if (ln.chunk.last && ln.s->on_result) {
+                    BestPath bp;
+                    bp.error = 100;
+                    ln.s->on_result(bp);
+                }
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (auto &ln : lanes) {
+                ln.s->pending_chunks.fetch_sub(1);
+                if (ln.chunk.last) {
+                    free_channels_.push_back(ln.s->channel);
+                    ln.s->channel = -1;
+                    ln.s->queued = false;
+                } else if (!ln.s->pending.empty()) {
+                    ready_.push_back(ln.s);
+                } else {
+                    ln.s->queued = false;
+                }
+            }
+            outstanding_ -= (long long)lanes.size();
+        }
+        cv_done_.notify_all();
+    }
+}
+
+void Engine::step(std::vector<Lane> &lanes, const int16_t *d_resident, int resident_stride) {
+    const int L = (int)lanes.size();
+    const int ctx = model_.context, spc = samples_per_chunk();
+    const int nn = (int)nodes_.size();
+    double audio = 0;
+    long long in_rows = 0;
+    for (int i = 0; i < L; i++) {
+        Stream &s = *lanes[i].s;
+        const Stream::Chunk &ck = lanes[i].chunk;
+        LaneDesc &d = h_lanes_[i];
+        const int n = d_resident ? (int)ck.samples.size() : (int)ck.samples.size();
+        d.channel = s.channel;
+        d.n_samples = n;
+        d.carry = s.carry;
+        d.first = !s.started;
+        d.last = ck.last;
+        d.frames_before = s.frames;
+        const int64_t total = s.samples + n;
+        d.frames_after = num_frames_for(total);
+        d.iv_end_before = s.iv_end;
+        d.iv_end_after = std::max(s.iv_end, ck.last ? d.frames_after : d.frames_after - 3);
+        d.in_end_before = d.first ? -ctx : s.in_end;
+        d.in_end_after = d.frames_after > 0 ? (ck.last ? d.frames_after + ctx : d.frames_after) : d.in_end_before;
+        d.dec_frames_before = s.dec_frames;
+        d.src_row = i;
+        d.src_off = 0;
+        if (!d_resident && n) memcpy(h_staging_ + (size_t)i * spc, ck.samples.data(), (size_t)n * sizeof(int16_t));
+        in_rows += d.in_end_after - d.in_end_before + 2;
+        audio += n / 16000.0;
+        // advance the host mirror of the stream state
+        s.started = true;
+        s.samples = total;
+        s.frames = d.frames_after;
+        s.iv_end = d.iv_end_after;
+        s.in_end = d.in_end_after;
+        s.carry = d.frames_after > 0 ? (int)(total - (int64_t)kFrameShift * d.frames_after) : (int)total;
+        s.dec_frames = d.in_end_after > ctx ? (d.in_end_after - ctx + kSubsample - 1) / kSubsample : 0;
+    }
+    if (d_resident) {
+        // resident mode: chunk.samples only carries the length; the source offsets were put in place by the caller
+        for (int i = 0; i < L; i++) {
+            h_lanes_[i].src_row = (int)lanes[i].s->id;
+            h_lanes_[i].src_off = (int)(lanes[i].s->samples - h_lanes_[i].n_samples);
+        }
+    }
+    long long launches = 0, gemms = 0;
+    if (timing_) VB_CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
+    VB_CUDA_CHECK(cudaMemcpyAsync(d_lanes_, h_lanes_, (size_t)L * sizeof(LaneDesc), cudaMemcpyHostToDevice, stream_));
+    if (!d_resident)
+        VB_CUDA_CHECK(cudaMemcpyAsync(d_staging_, h_staging_, (size_t)L * spc * sizeof(int16_t), cudaMemcpyHostToDevice, stream_));
+    FeatArgs fa{d_lanes_, L, d_resident ? d_resident : d_staging_, d_resident ? (long long)resident_stride : (long long)spc, spc,
+                d_carry_, nodes_[0], ctx, feat_tab_};
+    VB_CUDA_CHECK(vbk_mfcc(&fa, stream_));
+    launches++;
+    if (timing_) VB_CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
+    IvecArgs ia{d_lanes_, L, nodes_[0], ctx, iv_model_, iv_state_};
+    VB_CUDA_CHECK(vbk_ivector(&ia, stream_));
+    launches++;
+    if (timing_) VB_CUDA_CHECK(cudaEventRecord(ev_[2], stream_));
+    NnetPlanArgs pa{d_lanes_, L, nn, d_nodes_, d_node_end_, d_table_, d_rowoff_, cfg_.max_lanes};
+    VB_CUDA_CHECK(vbk_nnet_plan(&pa, stream_));
+    launches++;
+    for (size_t o = 0; o < ops_.size(); o++) {
+        const OpDesc &op = ops_[o];
+        GemmArgs ga{};
+        ga.op = op;
+        ga.in = nodes_[op.in_node];
+        ga.out = nodes_[op.out_node];
+        ga.byp = nodes_[op.byp_node >= 0 ? op.byp_node : 0];
+        ga.lanes = d_lanes_;
+        ga.num_lanes = L;
+        ga.table = d_table_ + (size_t)op.out_node * cfg_.max_lanes;
+        ga.rowoff = d_rowoff_ + (size_t)op.out_node * (cfg_.max_lanes + 1);
+        ga.ivec = iv_state_.ivec;
+        ga.ivec_dim = model_.ivec_dim;
+        ga.max_rows = (int)(ga.out.step == 1 ? in_rows : in_rows / kSubsample + 2 * L);
+        VB_CUDA_CHECK(cfg_.use_tensor_cores ? vbk_gemm_tc(&ga, stream_) : vbk_gemm_fp32(&ga, stream_));
+        launches++;
+        gemms++;
+    }
+    if (timing_) VB_CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
+    dec_.lanes = d_lanes_;
+    dec_.num_lanes = L;
+    VB_CUDA_CHECK(vbk_decode(&dec_, stream_));
+    launches++;
+    if (timing_) VB_CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
+    // results of finished lanes
+    int n_last = 0;
+    for (int i = 0; i < L; i++)
+        if (lanes[i].chunk.last) {
+            const int ch = lanes[i].s->channel;
+            VB_CUDA_CHECK(cudaMemcpyAsync(h_cs_ + n_last, dec_.cs + ch, sizeof(DecChannelState), cudaMemcpyDeviceToHost, stream_));
+            VB_CUDA_CHECK(cudaMemcpyAsync(h_path_ + (size_t)n_last * path_cap_, dec_.path + (size_t)ch * path_cap_,
+                                          (size_t)path_cap_ * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+            n_last++;
+        }
+    VB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    // debug capture (tests): copy this step's new rows of the tapped stages
+    for (int i = 0; i < L && cfg_.debug_capture; i++) {
+        Stream &s = *lanes[i].s;
+        if (!s.capture) continue;
+        const LaneDesc &d = h_lanes_[i];
+        Capture &cp = *s.capture;
+        auto grab = [&](const NodeDesc &node, int t0, int rows, std::vector<float> &dst) {
+            if (rows <= 0) return;
+            VB_CUDA_CHECK(vbk_copy_rows(node, d.channel, t0, rows, d_capture_, stream_));
+            VB_CUDA_CHECK(cudaMemcpyAsync(h_capture_, d_capture_, (size_t)rows * node.dim * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+            VB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+            dst.insert(dst.end(), h_capture_, h_capture_ + (size_t)rows * node.dim);
+        };
+        grab(nodes_[0], d.frames_before, d.frames_after - d.frames_before, cp.mfcc);
+        grab(nodes_.back(), d.dec_frames_before * kSubsample, s.dec_frames - d.dec_frames_before, cp.loglikes);
+        std::vector<float> iv(model_.ivec_dim);
+        VB_CUDA_CHECK(cudaMemcpy(iv.data(), iv_state_.ivec + (size_t)d.channel * model_.ivec_dim, iv.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        cp.ivectors.insert(cp.ivectors.end(), iv.begin(), iv.end());
+        if (d.last) {
+            DecChannelState cs;
+            VB_CUDA_CHECK(cudaMemcpy(&cs, dec_.cs + d.channel, sizeof cs, cudaMemcpyDeviceToHost));
+            const int nfr = std::min(cs.frame, max_frames_);
+            cp.error = cs.error;
+            cp.frame_off.resize(nfr + 2);
+            VB_CUDA_CHECK(cudaMemcpy(cp.frame_off.data(), dec_.log_frame_off + (size_t)d.channel * (max_frames_ + 2), (nfr + 2) * sizeof(int), cudaMemcpyDeviceToHost));
+            const size_t nt = (size_t)cs.log_count, base = (size_t)d.channel * log_cap_;
+            cp.tok_state.resize(nt);
+            cp.tok_arc.resize(nt);
+            cp.tok_prev.resize(nt);
+            cp.tok_cost.resize(nt);
+            if (nt) {
+                VB_CUDA_CHECK(cudaMemcpy(cp.tok_state.data(), dec_.log_state + base, nt * 4, cudaMemcpyDeviceToHost));
+                VB_CUDA_CHECK(cudaMemcpy(cp.tok_arc.data(), dec_.log_arc + base, nt * 4, cudaMemcpyDeviceToHost));
+                VB_CUDA_CHECK(cudaMemcpy(cp.tok_prev.data(), dec_.log_prev + base, nt * 4, cudaMemcpyDeviceToHost));
+                VB_CUDA_CHECK(cudaMemcpy(cp.tok_cost.data(), dec_.log_cost + base, nt * 4, cudaMemcpyDeviceToHost));
+            }
+        }
+    }
+    if (timing_) {
+        float ms[4];
+        for (int k = 0; k < 4; k++) cudaEventElapsedTime(&ms[k], ev_[k], ev_[k + 1]);
+        std::lock_guard<std::mutex> lk(stats_mu_);
+        stats_.t_feat += ms[0];
+        stats_.t_ivec += ms[1];
+        stats_.t_nnet += ms[2];
+        stats_.t_dec += ms[3];
+        stats_.t_total += ms[0] + ms[1] + ms[2] + ms[3];
+    }
+    {
+        std::lock_guard<std::mutex> lk(stats_mu_);
+        stats_.audio_seconds += audio;
+        stats_.steps++;
+        stats_.lanes += L;
+        stats_.launches += launches;
+        stats_.gemm_launches += gemms;
+        stats_.dec_launches++;
+    }
+    n_last = 0;
+    for (int i = 0; i < L; i++)
+        if (lanes[i].chunk.last) finish_lane(lanes[i], n_last++);
+}
+
+void Engine::finish_lane(Lane &ln, int k) {
+    const DecChannelState &cs = h_cs_[k];
+    BestPath bp;
+    bp.cost = cs.best_cost;
+    bp.reached_final = cs.reached_final != 0;
+    bp.error = cs.error;
+    bp.frames = cs.frame;
+    const int n = std::min(cs.path_len, path_cap_);
+    bp.arcs.resize(n);
+    const int *p = h_path_ + (size_t)k * path_cap_;
+    for (int i = 0; i < n; i++) bp.arcs[i] = p[n - 1 - i];
+    if (cs.error) log_msg(-1, "stream %llu: decoder capacity error %d (result may be truncated)", (unsigned long long)ln.s->id, cs.error);
+    if (ln.s->on_result) ln.s->on_result(bp);
+}
+
+double Engine::run_resident(const int16_t *d_audio, int num_streams, int samples_per_stream, std::vector<BestPath> *out) {
+    // every stream advances in lockstep, one chunk per step, no host<->device sample traffic
+    if (num_streams > cfg_.num_channels) throw std::runtime_error("run_resident: more streams than channels");
+    wait();
+    const int spc = samples_per_chunk();
+    std::vector<std::shared_ptr<Stream>> ss(num_streams);
+    std::vector<BestPath> res(num_streams);
+    for (int i = 0; i < num_streams; i++) {
+        ss[i] = std::make_shared<Stream>();
+        ss[i]->id = (uint64_t)i;
+        ss[i]->channel = i;
+        BestPath *slot = &res[i];
+        ss[i]->on_result = [slot](const BestPath &bp) { *slot = bp; };
+    }
+    cudaEvent_t e0, e1;
+    VB_CUDA_CHECK(cudaEventCreate(&e0));
+    VB_CUDA_CHECK(cudaEventCreate(&e1));
+    VB_CUDA_CHECK(cudaEventRecord(e0, stream_));
+    const int nfull = samples_per_stream / spc;
+    std::vector<Lane> lanes;
+    for (int k = 0; k <= nfull; k++) {
+        const bool last = k == nfull;
+        const int n = last ? samples_per_stream - nfull * spc : spc;
+        for (int g0 = 0; g0 < num_streams; g0 += cfg_.max_lanes) {
+            lanes.clear();
+            for (int i = g0; i < std::min(num_streams, g0 + cfg_.max_lanes); i++) {
+                Lane ln;
+                ln.s = ss[i];
+                ln.chunk.samples.resize(n);  // length only; the samples are read from d_audio
+                ln.chunk.last = last;
+                lanes.push_back(std::move(ln));
+            }
+            step(lanes, d_audio, samples_per_stream);
+        }
+    }
+    VB_CUDA_CHECK(cudaEventRecord(e1, stream_));
+    VB_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (out) *out = std::move(res);
+    return ms;
+}
+
+}  // namespace vb

@@ -1,0 +1,134 @@
+// vb_engine.h — per-GPU batch engine: channels, chunk batching, pipeline launch, result hand-off.
+//
+// Replaces the objects BatchModel constructs from Kaldi — BatchedThreadedNnet3CudaOnlinePipeline and
+// CudaOnlinePipelineDynamicBatcher [REF src/batch_model.cc:90-96] — and the calls BatchRecognizer makes on
+// them: Push / SetLatticeCallback / GetNumPendingChunks / WaitForCompletion
+// [REF src/batch_recognizer.cc:40,138-149,167,201], [REF src/batch_model.cc:118-121].
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "vb_common.h"
+#include "vb_kernels.h"
+#include "vb_model.h"
+
+namespace vb {
+
+struct BestPath {
+    std::vector<int> arcs;  // csr arc ids in path order
+    float cost = 0.f;
+    bool reached_final = false;
+    int error = 0;
+    int frames = 0;         // decoder frames
+};
+
+// debug capture of one stream's intermediates (tests; enabled per stream before the first chunk)
+struct Capture {
+    std::vector<float> mfcc, ivectors, loglikes;
+    std::vector<int> frame_off, tok_state, tok_arc, tok_prev;
+    std::vector<float> tok_cost;
+    int error = 0;
+};
+
+struct Stream {
+    uint64_t id = 0;
+    int channel = -1;
+    bool started = false, finished = false, queued = false;
+    int64_t samples = 0;     // samples handed to the GPU so far
+    int frames = 0;          // MFCC frames computed so far
+    int iv_end = 0, in_end = 0, dec_frames = 0, carry = 0;
+    struct Chunk {
+        std::vector<int16_t> samples;
+        bool last;
+    };
+    std::deque<Chunk> pending;            // guarded by Engine::mu_
+    std::atomic<int> pending_chunks{0};
+    std::function<void(const BestPath &)> on_result;  // called on the engine worker thread
+    std::unique_ptr<Capture> capture;
+};
+
+struct StepStats {
+    double audio_seconds = 0;
+    long long steps = 0, lanes = 0, launches = 0;
+    unsigned long long tok = 0, arc_e = 0, arc_eps = 0, tok_new = 0;
+    double t_feat = 0, t_ivec = 0, t_nnet = 0, t_dec = 0, t_total = 0;  // device ms (only when timing enabled)
+    long long dec_launches = 0, gemm_launches = 0;
+};
+
+class Engine {
+   public:
+    Engine(const Model &model, const Config &cfg);
+    ~Engine();
+    Engine(const Engine &) = delete;
+
+    int samples_per_chunk() const { return cfg_.frames_per_chunk * kFrameShift; }
+    const Config &config() const { return cfg_; }
+    std::shared_ptr<Stream> open_stream();
+    // copies the samples; n <= samples_per_chunk unless it is the (possibly empty) last chunk
+    void push(const std::shared_ptr<Stream> &s, const int16_t *samples, int n, bool last);
+    void wait();  // until every chunk pushed so far is decoded and its result delivered
+    StepStats stats();
+    void reset_stats();
+    void set_timing(bool on) { timing_ = on; }
+
+    // Device-resident run for kernel-level benchmarking: `audio` holds num_streams x samples int16 already in
+    // HBM; processes every stream chunk by chunk with no host<->device sample traffic.  Returns device ms.
+    double run_resident(const int16_t *d_audio, int num_streams, int samples_per_stream, std::vector<BestPath> *out);
+
+   private:
+    struct Lane {
+        std::shared_ptr<Stream> s;
+        Stream::Chunk chunk;
+    };
+    void worker();
+    void step(std::vector<Lane> &lanes, const int16_t *d_resident, int resident_stride);
+    void upload_model();
+    void alloc_state();
+    void finish_lane(Lane &ln, int lane_idx);
+
+    const Model &model_;
+    Config cfg_;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_[6] = {};
+    bool timing_ = false;
+    // model on device
+    FeatTables feat_tab_{};
+    IvecModel iv_model_{};
+    std::vector<NodeDesc> nodes_;
+    std::vector<OpDesc> ops_;
+    NodeDesc *d_nodes_ = nullptr;
+    GraphDev graph_{};
+    std::vector<void *> allocs_;
+    // per channel / per step state
+    IvecState iv_state_{};
+    int16_t *d_carry_ = nullptr, *d_staging_ = nullptr, *h_staging_ = nullptr;
+    LaneDesc *d_lanes_ = nullptr, *h_lanes_ = nullptr;
+    int *d_node_end_ = nullptr;
+    NodeLane *d_table_ = nullptr;
+    int *d_rowoff_ = nullptr;
+    DecArgs dec_{};
+    DecChannelState *h_cs_ = nullptr;
+    int *h_path_ = nullptr;
+    float *d_capture_ = nullptr, *h_capture_ = nullptr;
+    size_t capture_floats_ = 0;
+    int max_in_rows_ = 0, log_cap_ = 0, max_frames_ = 0, path_cap_ = 0;
+    std::vector<int> free_channels_;
+    // batching
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    std::deque<std::shared_ptr<Stream>> ready_;
+    long long outstanding_ = 0;  // chunks pushed and not yet completed
+    bool stop_ = false;
+    std::thread thread_;
+    uint64_t next_id_ = 0;
+    StepStats stats_;
+    std::mutex stats_mu_;
+};
+
+}  // namespace vb

@@ -1,0 +1,155 @@
+// vb_kernels.h — the C-ABI CUDA layer: plain-pointer launch entry points of the sm_100a kernels.
+// Host code (vb_engine.cc) talks to the GPU only through these functions and the CUDA runtime.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vb_common.h"
+
+namespace vb {
+
+// ---------------- K1: fused framing / FFT / mel / DCT / lifter ----------------
+struct FeatTables {          // device pointers, built once per model
+    const float *window;     // [400]  Povey window
+    const float *twiddle;    // [256][2] cos,sin(-2*pi*k/512)
+    const int *mel_start;    // [40]
+    const int *mel_len;      // [40]
+    const float *mel_w;      // [40][kMelMaxLen]
+    const float *dct_t;      // [40 mel][40 cep]  (transposed DCT-II)
+    const float *lifter;     // [40]
+};
+constexpr int kMelMaxLen = 64;
+constexpr int kCarryMax = 400;
+
+struct FeatArgs {
+    const LaneDesc *lanes;   // device
+    int num_lanes;
+    const int16_t *staging;  // sample source (pinned-copy staging rows, or a device-resident audio matrix)
+    long long src_stride;    // int16 elements between source rows
+    int samples_per_chunk;
+    int16_t *carry;          // [num_channels][kCarryMax]
+    NodeDesc in_node;        // node 0 (MFCC ring, padded timeline)
+    int context;
+    FeatTables tab;
+};
+
+// ---------------- K1c: online CMN + i-vector ----------------
+struct IvecModel {           // device pointers
+    int feat_dim, ivec_dim, num_gauss, splice_dim;
+    const float *lda_t;      // [splice_dim+1][feat_dim]  (transposed; last row = offset)
+    const float *gconsts;    // [G]
+    const float *mi_t;       // [F][G] means*inv_vars, transposed
+    const float *iv_t;       // [F][G] inv_vars, transposed
+    const float *sim;        // [G][F][D]   Sigma_i^{-1} M_i
+    const float *U;          // [G][D*D]    M_i^T Sigma_i^{-1} M_i
+    const double *gcmvn_sum; // [F] global cmvn sums
+    double gcmvn_count;
+    float prior_offset;
+    int num_gselect;
+    float min_post, posterior_scale, max_count;
+    int cmn_window, global_frames;
+};
+struct IvecState {           // per channel, device
+    double *cmvn_sum;        // [C][F]
+    float *norm_ring;        // [C][kNormRing][F]
+    double *lin;             // [C][D]
+    double *quad;            // [C][D*D]
+    double *num_frames;      // [C]
+    float *ivec;             // [C][D]   current i-vector (prior offset removed)
+};
+constexpr int kNormRing = 128;
+
+struct IvecArgs {
+    const LaneDesc *lanes;
+    int num_lanes;
+    NodeDesc in_node;
+    int context;
+    IvecModel m;
+    IvecState st;
+};
+
+// ---------------- K2: TDNN-F ----------------
+struct NnetPlanArgs {
+    const LaneDesc *lanes;
+    int num_lanes;
+    int num_nodes;
+    const NodeDesc *nodes;   // device [num_nodes]
+    int *node_end;           // [num_channels][kMaxNodes] next time to compute per node
+    NodeLane *table;         // [num_nodes][max_lanes]
+    int *rowoff;             // [num_nodes][max_lanes+1]
+    int max_lanes;
+};
+struct GemmArgs {
+    OpDesc op;
+    NodeDesc in, out, byp;
+    const LaneDesc *lanes;
+    int num_lanes;
+    const NodeLane *table;   // out node's table [max_lanes]
+    const int *rowoff;       // out node's prefix [max_lanes+1]
+    const float *ivec;       // [C][ivec_dim]
+    int ivec_dim;
+    int max_rows;            // upper bound of total rows (grid sizing)
+};
+
+// ---------------- K3: beam search ----------------
+struct GraphDev {
+    int num_states, num_arcs, start;
+    const float *final_cost;
+    const int *e_begin;      // [S+1]
+    const int *eps_begin;    // [S]
+    const int4 *arcs;        // {weight bits, nextstate, pdf, olabel}
+};
+struct DecChannelState {     // one per channel
+    int n_cur, parity, frame, error;
+    int log_count, path_len, reached_final;
+    float best_cost;
+};
+struct DecArgs {
+    const LaneDesc *lanes;
+    int num_lanes;
+    GraphDev g;
+    float beam, beam_delta, acoustic_scale;
+    int max_active, min_active;
+    int tok_cap, cand_cap, hash_size, log_cap, max_frames, path_cap;
+    // loglikes
+    NodeDesc out_node;
+    const NodeLane *out_table;
+    // per channel
+    DecChannelState *cs;
+    int *tok_state;          // [C][2][tok_cap]
+    float *tok_cost;
+    int *tok_arc;
+    int *tok_prev;
+    int *log_prev;           // [C][log_cap]
+    int *log_arc;
+    float *log_cost;
+    int *log_state;          // optional (debug capture) or null
+    int *log_frame_off;      // [C][max_frames+2]
+    int *path;               // [C][path_cap]  best-path arcs, last arc first
+    // per resident CTA scratch
+    int *hash_key;           // [G][hash_size]
+    unsigned long long *hash_val;
+    int *hash_tok;
+    unsigned long long *cand_packed;  // [G][cand_cap]
+    int *cand_slot;
+    int *cand_src;
+    int *rank;               // [G][tok_cap]
+    unsigned long long *counters;     // [8] profiling counters (tokens, arcs, ...)
+    int grid;
+};
+
+extern "C" {
+int vbk_feat_smem_bytes(int samples_per_chunk);
+cudaError_t vbk_mfcc(const FeatArgs *a, cudaStream_t s);
+cudaError_t vbk_ivector(const IvecArgs *a, cudaStream_t s);
+cudaError_t vbk_nnet_plan(const NnetPlanArgs *a, cudaStream_t s);
+cudaError_t vbk_gemm_fp32(const GemmArgs *a, cudaStream_t s);
+cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s);
+cudaError_t vbk_decode(const DecArgs *a, cudaStream_t s);
+int vbk_decode_max_grid(int device);
+// copies rows [t_begin, t_begin+n) of a node ring for one channel into dst (debug capture / tests)
+cudaError_t vbk_copy_rows(NodeDesc node, int channel, int t_begin, int n_rows, float *dst, cudaStream_t s);
+cudaError_t vbk_split_tf32(const float *w, float *hi, float *lo, long long n, cudaStream_t s);
+}
+
+}  // namespace vb

@@ -1,0 +1,321 @@
+// vb_model.cc — model directory loader (host).  File set and relative paths as hard-coded by the
+// reference [REF src/batch_model.cc:28-37,75-77]; conf syntax = Kaldi ParseOptions "--key=value"
+// [REF src/batch_model.cc:26-28].  HCLG.fst: OpenFst binary, "vector" or "const", StdArc.
+#include "vb_model.h"
+
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace vb {
+
+static std::vector<uint8_t> slurp(const std::string &path) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    std::streamsize n = f.tellg();
+    f.seekg(0);
+    std::vector<uint8_t> buf((size_t)n);
+    if (n && !f.read(reinterpret_cast<char *>(buf.data()), n)) throw std::runtime_error("cannot read " + path);
+    return buf;
+}
+
+TensorMap read_vbt(const std::string &path) {
+    std::vector<uint8_t> buf = slurp(path);
+    if (buf.size() < 8 || memcmp(buf.data(), "VBT1", 4) != 0) throw std::runtime_error("not a VBT1 container: " + path);
+    size_t p = 4;
+    auto rd32 = [&]() {
+        if (p + 4 > buf.size()) throw std::runtime_error("truncated " + path);
+        uint32_t v;
+        memcpy(&v, &buf[p], 4);
+        p += 4;
+        return v;
+    };
+    auto rd64 = [&]() {
+        if (p + 8 > buf.size()) throw std::runtime_error("truncated " + path);
+        uint64_t v;
+        memcpy(&v, &buf[p], 8);
+        p += 8;
+        return v;
+    };
+    static const int item[4] = {4, 4, 8, 1};
+    TensorMap out;
+    uint32_t n = rd32();
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t ln = rd32();
+        if (p + ln > buf.size()) throw std::runtime_error("truncated " + path);
+        std::string name((const char *)&buf[p], ln);
+        p += ln;
+        Tensor t;
+        t.dtype = (int)rd32();
+        if (t.dtype < 0 || t.dtype > 3) throw std::runtime_error("bad dtype in " + path);
+        uint32_t nd = rd32();
+        for (uint32_t d = 0; d < nd; d++) t.shape.push_back((int64_t)rd64());
+        size_t bytes = (size_t)t.numel() * item[t.dtype];
+        if (p + bytes > buf.size()) throw std::runtime_error("truncated tensor " + name + " in " + path);
+        t.data.assign(buf.begin() + p, buf.begin() + p + bytes);
+        p += bytes;
+        out.emplace(name, std::move(t));
+    }
+    return out;
+}
+
+std::map<std::string, std::string> read_conf(const std::string &path) {
+    std::map<std::string, std::string> out;
+    std::ifstream f(path);
+    std::string line;
+    while (std::getline(f, line)) {
+        size_t h = line.find('#');
+        if (h != std::string::npos) line.resize(h);
+        size_t a = line.find_first_not_of(" \t\r");
+        if (a == std::string::npos || line.compare(a, 2, "--") != 0) continue;
+        size_t e = line.find_last_not_of(" \t\r");
+        line = line.substr(a + 2, e - a - 1);
+        size_t eq = line.find('=');
+        if (eq == std::string::npos) out[line] = "true";
+        else out[line.substr(0, eq)] = line.substr(eq + 1);
+    }
+    return out;
+}
+
+namespace {
+struct FileArc {
+    int32_t ilabel, olabel;
+    float weight;
+    int32_t next;
+};
+}  // namespace
+
+Graph read_graph(const std::string &path, const std::vector<int32_t> &tid2pdf) {
+    std::vector<uint8_t> buf = slurp(path);
+    size_t p = 0;
+    auto need = [&](size_t n) {
+        if (p + n > buf.size()) throw std::runtime_error("truncated FST " + path);
+    };
+    auto rdi32 = [&]() { need(4); int32_t v; memcpy(&v, &buf[p], 4); p += 4; return v; };
+    auto rdi64 = [&]() { need(8); int64_t v; memcpy(&v, &buf[p], 8); p += 8; return v; };
+    auto rdstr = [&]() { int32_t n = rdi32(); need((size_t)n); std::string s((const char *)&buf[p], n); p += n; return s; };
+    if (rdi32() != 2125659606) throw std::runtime_error("bad FST magic in " + path);
+    std::string ftype = rdstr(), atype = rdstr();
+    if (atype != "standard") throw std::runtime_error("unsupported arc type " + atype);
+    int32_t version = rdi32(), flags = rdi32();
+    rdi64();  // properties
+    int64_t start = rdi64(), ns = rdi64(), na = rdi64();
+    if (flags & 3) throw std::runtime_error("FST with embedded symbol tables is not supported: " + path);
+    std::vector<float> fin((size_t)ns);
+    std::vector<int64_t> row((size_t)ns + 1, 0);
+    std::vector<FileArc> arcs;
+    if (ftype == "const") {
+        if (version == 1 && (p % 16)) p += 16 - p % 16;
+        need((size_t)ns * 20);
+        for (int64_t s = 0; s < ns; s++) {
+            uint32_t pos, narcs;
+            memcpy(&fin[s], &buf[p], 4);
+            memcpy(&pos, &buf[p + 4], 4);
+            memcpy(&narcs, &buf[p + 8], 4);
+            row[s] = pos;
+            (void)narcs;
+            p += 20;
+        }
+        row[ns] = na;
+        if (version == 1 && (p % 16)) p += 16 - p % 16;
+        need((size_t)na * 16);
+        arcs.resize((size_t)na);
+        memcpy(arcs.data(), &buf[p], (size_t)na * 16);
+    } else if (ftype == "vector") {
+        arcs.reserve((size_t)na);
+        for (int64_t s = 0; s < ns; s++) {
+            need(12);
+            memcpy(&fin[s], &buf[p], 4);
+            p += 4;
+            int64_t n = rdi64();
+            need((size_t)n * 16);
+            size_t old = arcs.size();
+            arcs.resize(old + (size_t)n);
+            memcpy(&arcs[old], &buf[p], (size_t)n * 16);
+            p += (size_t)n * 16;
+            row[s + 1] = (int64_t)arcs.size();
+        }
+        na = (int64_t)arcs.size();
+    } else {
+        throw std::runtime_error("unsupported FST type " + ftype);
+    }
+    if (na >= (1ll << 31) || ns >= (1ll << 31)) throw std::runtime_error("graph too large for 32-bit arc ids");
+    Graph g;
+    g.num_states = (int)ns;
+    g.num_arcs = (int)na;
+    g.start = (int)start;
+    g.final_cost = fin;
+    g.e_begin.resize(ns + 1);
+    g.eps_begin.resize(ns);
+    g.arc_w.resize(na);
+    g.arc_next.resize(na);
+    g.arc_pdf.resize(na);
+    g.arc_ilabel.resize(na);
+    g.arc_olabel.resize(na);
+    int64_t w = 0;
+    for (int64_t s = 0; s < ns; s++) {
+        g.e_begin[s] = (int32_t)w;
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1) g.eps_begin[s] = (int32_t)w;
+            for (int64_t a = row[s]; a < row[s + 1]; a++) {
+                const FileArc &fa = arcs[a];
+                if ((fa.ilabel == 0) != (pass == 1)) continue;
+                if (fa.ilabel < 0 || fa.ilabel >= (int)tid2pdf.size()) throw std::runtime_error("ilabel out of range in " + path);
+                if (fa.next < 0 || fa.next >= ns) throw std::runtime_error("nextstate out of range in " + path);
+                g.arc_w[w] = fa.weight;
+                g.arc_next[w] = fa.next;
+                g.arc_ilabel[w] = fa.ilabel;
+                g.arc_olabel[w] = fa.olabel;
+                g.arc_pdf[w] = fa.ilabel ? tid2pdf[fa.ilabel] : -1;
+                if (!fa.ilabel && fa.weight < 0) g.has_negative_eps = true;
+                w++;
+            }
+        }
+    }
+    g.e_begin[ns] = (int32_t)na;
+    return g;
+}
+
+static const Tensor *find(const TensorMap &m, const std::string &k, bool required = true) {
+    auto it = m.find(k);
+    if (it == m.end()) {
+        if (required) throw std::runtime_error("model tensor missing: " + k);
+        return nullptr;
+    }
+    return &it->second;
+}
+
+void Model::load(const std::string &d) {
+    dir = d;
+    conf = read_conf(d + "/conf/model.conf");
+    am = read_vbt(d + "/am/final.mdl");
+    const Tensor *cfgt = find(am, "config");
+    std::map<std::string, std::string> c;
+    {
+        std::istringstream ss(std::string((const char *)cfgt->data.data(), cfgt->data.size()));
+        std::string line;
+        while (std::getline(ss, line)) {
+            size_t sp = line.find(' ');
+            if (sp != std::string::npos) c[line.substr(0, sp)] = line.substr(sp + 1);
+        }
+    }
+    if (c["arch"] != "tdnnf") throw std::runtime_error("unsupported acoustic model arch '" + c["arch"] + "'");
+    feat_dim = std::stoi(c["feat-dim"]);
+    ivec_dim = std::stoi(c["ivector-dim"]);
+    hidden = std::stoi(c["hidden-dim"]);
+    bottleneck = std::stoi(c["bottleneck-dim"]);
+    prefinal_small = std::stoi(c["prefinal-small"]);
+    prefinal_big = std::stoi(c["prefinal-big"]);
+    num_pdfs = std::stoi(c["num-pdfs"]);
+    bypass_scale = std::stof(c["bypass-scale"]);
+    if (feat_dim != kNumCeps) throw std::runtime_error("feat-dim must be 40");
+    {
+        std::istringstream ss(c["tdnnf-strides"]);
+        int s;
+        while (ss >> s) strides.push_back(s);
+    }
+    context = 2;
+    for (int s : strides) context += s;
+    // op list of the collapsed network  [REF training/local/chain/run_tdnn.sh:98-129]
+    auto add = [&](const std::string &name, int in_node, std::vector<int> offs, bool relu_bn, int byp, bool iv,
+                   const std::string &bn_name) {
+        AmOp op;
+        op.name = name;
+        op.in_node = in_node;
+        op.byp_node = byp;
+        op.offs = offs;
+        op.uses_ivec = iv;
+        op.relu_bn = relu_bn;
+        op.W = find(am, name + ".w");
+        op.b = find(am, name + ".b", false);
+        op.bn_s = relu_bn ? find(am, bn_name + ".bn_scale") : nullptr;
+        op.bn_o = relu_bn ? find(am, bn_name + ".bn_offset") : nullptr;
+        op.N = (int)op.W->shape[0];
+        op.K = (int)op.W->shape[1];
+        int expectK = node_dim[in_node] * (int)offs.size() + (iv ? ivec_dim : 0);
+        if (op.K != expectK) throw std::runtime_error("weight shape mismatch for " + name);
+        ops.push_back(op);
+        node_dim.push_back(op.N);
+    };
+    node_dim.push_back(feat_dim);
+    add("tdnn1", 0, {-2, -1, 0, 1, 2}, true, -1, true, "tdnn1");
+    int cur = 1;
+    for (size_t k = 0; k < strides.size(); k++) {
+        int s = strides[k];
+        std::string nm = "tdnnf" + std::to_string(k + 2);
+        add(nm + ".linear", cur, s ? std::vector<int>{-s, 0} : std::vector<int>{0}, false, -1, false, "");
+        add(nm + ".affine", cur + 1, s ? std::vector<int>{0, s} : std::vector<int>{0}, true, cur, false, nm);
+        cur += 2;
+    }
+    add("prefinal_l", cur, {0}, false, -1, false, "");
+    add("prefinal.affine", cur + 1, {0}, true, -1, false, "prefinal");
+    add("prefinal.linear", cur + 2, {0}, false, -1, false, "");
+    add("output", cur + 3, {0}, false, -1, false, "");
+    if ((int)node_dim.size() > kMaxNodes) throw std::runtime_error("too many layers");
+    if (node_dim.back() != num_pdfs) throw std::runtime_error("output dim != num-pdfs");
+    const Tensor *t2p = find(am, "tid2pdf"), *t2ph = find(am, "tid2phone");
+    tid2pdf.assign(t2p->i32(), t2p->i32() + t2p->numel());
+    tid2phone.assign(t2ph->i32(), t2ph->i32() + t2ph->numel());
+    graph = read_graph(d + "/graph/HCLG.fst", tid2pdf);
+    for (int32_t pdf : graph.arc_pdf)
+        if (pdf >= num_pdfs) throw std::runtime_error("pdf id out of range in graph");
+    {
+        std::ifstream f(d + "/graph/words.txt");
+        if (!f) throw std::runtime_error("cannot open " + d + "/graph/words.txt");
+        std::string w;
+        long id;
+        while (f >> w >> id) {
+            if (id < 0) continue;
+            if ((size_t)id >= words.size()) words.resize(id + 1);
+            words[id] = w;
+        }
+    }
+    {
+        std::ifstream f(d + "/graph/phones/word_boundary.int");
+        int ph;
+        std::string kind;
+        while (f >> ph >> kind) {
+            if (ph < 0) continue;
+            if ((size_t)ph >= phone_type.size()) phone_type.resize(ph + 1, 0);
+            phone_type[ph] = kind == "nonword" ? 1 : kind == "begin" ? 2 : kind == "end" ? 3 : kind == "internal" ? 4 : kind == "singleton" ? 5 : 0;
+        }
+    }
+    iv_lda = read_vbt(d + "/ivector/final.mat");
+    iv_dubm = read_vbt(d + "/ivector/final.dubm");
+    iv_ie = read_vbt(d + "/ivector/final.ie");
+    iv_cmvn = read_vbt(d + "/ivector/global_cmvn.stats");
+    num_gauss = (int)find(iv_dubm, "gconsts")->numel();
+    prior_offset = find(iv_ie, "prior_offset")->f32()[0];
+    if (find(iv_ie, "M")->shape[2] != ivec_dim) throw std::runtime_error("i-vector dim mismatch");
+}
+
+void Model::apply_conf(Config *cfg) const {
+    auto geti = [&](const std::map<std::string, std::string> &m, const char *k, int *v) {
+        auto it = m.find(k);
+        if (it != m.end() && !it->second.empty()) *v = std::stoi(it->second);
+    };
+    auto getf = [&](const std::map<std::string, std::string> &m, const char *k, float *v) {
+        auto it = m.find(k);
+        if (it != m.end() && !it->second.empty()) *v = std::stof(it->second);
+    };
+    // the reference overrides these after reading model.conf [REF src/batch_model.cc:78-82]; we take the
+    // conf value when present so that oracle and engine are driven by one file (defaults = the overrides)
+    getf(conf, "beam", &cfg->beam);
+    getf(conf, "lattice-beam", &cfg->lattice_beam);
+    geti(conf, "max-active", &cfg->max_active);
+    geti(conf, "min-active", &cfg->min_active);
+    geti(conf, "frames-per-chunk", &cfg->frames_per_chunk);
+    geti(conf, "max-batch-size", &cfg->max_lanes);
+    geti(conf, "num-channels", &cfg->num_channels);
+    auto iv = read_conf(dir + "/conf/ivector.conf");
+    geti(iv, "num-gselect", &cfg->num_gselect);
+    getf(iv, "min-post", &cfg->min_post);
+    getf(iv, "posterior-scale", &cfg->posterior_scale);
+    getf(iv, "max-count", &cfg->max_count);
+    auto cm = read_conf(dir + "/ivector/online_cmvn.conf");
+    geti(cm, "cmn-window", &cfg->cmn_window);
+    geti(cm, "global-frames", &cfg->global_frames);
+}
+
+}  // namespace vb

@@ -1,0 +1,41 @@
+// vb_result.h — result text for one finished segment: what BatchRecognizer::PushLattice produces
+// [REF src/batch_recognizer.cc:43-107] for the best path (a linear lattice): word-aligned spans,
+// MinimumBayesRisk one-best (conf = 1), json.h text layout [REF src/json.h:343-384] or NLSML.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "vb_engine.h"
+#include "vb_model.h"
+
+namespace vb {
+
+struct WordSpan {
+    int word;
+    int begin, end;  // decoder frames (30 ms each)
+    float conf;
+};
+
+std::vector<WordSpan> align_words(const Model &m, const std::vector<int> &arcs);
+std::string result_json(const Model &m, const std::vector<WordSpan> &words, float offset_seconds);
+std::string result_nlsml(const Model &m, const std::vector<WordSpan> &words);
+std::string partial_json(const Model &m, const std::vector<WordSpan> &words);
+
+// Kaldi LinearResample restated; the reference calls it with flush=true on every AcceptWaveform
+// [REF src/batch_recognizer.cc:27-29,157-158], so every call is filtered independently.
+class LinearResampler {
+   public:
+    LinearResampler(float rate_in, float rate_out, float cutoff, int num_zeros);
+    void resample_flush(const std::vector<float> &in, std::vector<float> *out) const;
+    bool identity() const { return identity_; }
+
+   private:
+    int in_rate_, out_rate_, in_unit_, out_unit_;
+    double cutoff_;
+    int num_zeros_;
+    bool identity_;
+    std::vector<int> first_index_;
+    std::vector<std::vector<float>> weights_;
+};
+
+}  // namespace vb

@@ -1,0 +1,222 @@
+// vosk_api.cc — extern "C" surface: the reference's batch ABI [REF src/vosk_api.cc:176-282] plus the
+// additive entry points of include/vosk_b200.h.  Handles are the C++ objects cast through opaque structs,
+// as in the reference [REF src/vosk_api.cc:201,210,224,233]; nothing throws across the boundary.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstring>
+#include <string>
+
+#include "../../include/vosk_b200.h"
+#include "batch_model.h"
+#include "batch_recognizer.h"
+
+namespace vb {
+int g_log_level = 0;
+void log_msg(int level, const char *fmt, ...) {
+    // vosk_set_log_level: 0 info+errors, <0 errors only, >0 verbose [REF src/vosk_api.h:287-294]
+    if (level > 0 && g_log_level < level) return;
+    if (level == 0 && g_log_level < 0) return;
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "%s (VoskAPI:b200) %s\n", level < 0 ? "ERROR" : "LOG", buf);
+}
+}  // namespace vb
+
+static thread_local std::string g_last_error;
+
+extern "C" {
+
+void vosk_set_log_level(int log_level) { vb::g_log_level = log_level; }
+
+void vosk_gpu_init() {
+    // reference: CuDevice::SelectGpuId("yes") + AllowMultithreading [REF src/vosk_api.cc:181-189]
+    int n = 0;
+    if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) cudaFree(nullptr);
+}
+
+void vosk_gpu_thread_init() {}
+
+const char *vosk_b200_last_error(void) { return g_last_error.c_str(); }
+
+VoskBatchModel *vosk_batch_model_new_ex(const char *model_dir, const char *options) {
+    try {
+        g_last_error.clear();
+        return (VoskBatchModel *)new BatchModel(model_dir ? model_dir : "model", options ? options : "");
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        vb::log_msg(-1, "cannot create batch model: %s", e.what());
+        return nullptr;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return nullptr;
+    }
+}
+
+VoskBatchModel *vosk_batch_model_new() {
+    const char *p = getenv("VOSK_BATCH_MODEL_PATH");
+    return vosk_batch_model_new_ex(p ? p : "model", "");
+}
+
+void vosk_batch_model_free(VoskBatchModel *model) {
+    try {
+        delete (BatchModel *)model;
+    } catch (...) {
+    }
+}
+
+void vosk_batch_model_wait(VoskBatchModel *model) {
+    if (!model) return;
+    try {
+        ((BatchModel *)model)->WaitForCompletion();
+    } catch (...) {
+    }
+}
+
+VoskBatchRecognizer *vosk_batch_recognizer_new(VoskBatchModel *model, float sample_rate) {
+    if (!model || !(sample_rate > 0)) return nullptr;
+    try {
+        return (VoskBatchRecognizer *)new BatchRecognizer((BatchModel *)model, sample_rate);
+    } catch (const std::exception &e) {
+        vb::log_msg(-1, "cannot create batch recognizer: %s", e.what());
+        return nullptr;
+    } catch (...) {
+        return nullptr;
+    }
+}
+
+void vosk_batch_recognizer_free(VoskBatchRecognizer *recognizer) {
+    try {
+        delete (BatchRecognizer *)recognizer;
+    } catch (...) {
+    }
+}
+
+void vosk_batch_recognizer_accept_waveform(VoskBatchRecognizer *recognizer, const char *data, int length) {
+    if (!recognizer || !data || length <= 0) return;
+    try {
+        ((BatchRecognizer *)recognizer)->AcceptWaveform(data, length);
+    } catch (const std::exception &e) {
+        vb::log_msg(-1, "accept_waveform: %s", e.what());  // the ABI has no error channel [REF src/vosk_api.h:329]
+    } catch (...) {
+    }
+}
+
+void vosk_batch_recognizer_set_nlsml(VoskBatchRecognizer *recognizer, int nlsml) {
+    if (recognizer) ((BatchRecognizer *)recognizer)->SetNLSML(nlsml != 0);
+}
+
+void vosk_batch_recognizer_finish_stream(VoskBatchRecognizer *recognizer) {
+    if (!recognizer) return;
+    try {
+        ((BatchRecognizer *)recognizer)->FinishStream();
+    } catch (const std::exception &e) {
+        vb::log_msg(-1, "finish_stream: %s", e.what());
+    } catch (...) {
+    }
+}
+
+const char *vosk_batch_recognizer_front_result(VoskBatchRecognizer *recognizer) {
+    if (!recognizer) return "";
+    try {
+        return ((BatchRecognizer *)recognizer)->FrontResult();
+    } catch (...) {
+        return "";
+    }
+}
+
+void vosk_batch_recognizer_pop(VoskBatchRecognizer *recognizer) {
+    if (recognizer) ((BatchRecognizer *)recognizer)->Pop();
+}
+
+int vosk_batch_recognizer_get_pending_chunks(VoskBatchRecognizer *recognizer) {
+    return recognizer ? ((BatchRecognizer *)recognizer)->GetNumPendingChunks() : 0;
+}
+
+// ---------------------------------------------------------------------------------- additive surface
+int vosk_batch_model_samples_per_chunk(VoskBatchModel *model) { return model ? ((BatchModel *)model)->samples_per_chunk() : 0; }
+
+int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
+    if (!model || !out) return 0;
+    BatchModel *bm = (BatchModel *)model;
+    double v[13] = {0};
+    for (size_t i = 0; i < bm->num_engines(); i++) {
+        vb::StepStats s = bm->engine(i).stats();
+        v[0] += s.audio_seconds; v[1] += s.steps; v[2] += s.lanes; v[3] += s.launches;
+        v[4] += s.tok; v[5] += s.arc_e; v[6] += s.arc_eps; v[7] += s.tok_new;
+        v[8] += s.t_feat; v[9] += s.t_ivec; v[10] += s.t_nnet; v[11] += s.t_dec; v[12] += s.gemm_launches;
+    }
+    int k = n < 13 ? n : 13;
+    memcpy(out, v, k * sizeof(double));
+    return k;
+}
+void vosk_batch_model_reset_stats(VoskBatchModel *model) {
+    if (!model) return;
+    BatchModel *bm = (BatchModel *)model;
+    for (size_t i = 0; i < bm->num_engines(); i++) bm->engine(i).reset_stats();
+}
+void vosk_batch_model_set_timing(VoskBatchModel *model, int on) {
+    if (!model) return;
+    BatchModel *bm = (BatchModel *)model;
+    for (size_t i = 0; i < bm->num_engines(); i++) bm->engine(i).set_timing(on != 0);
+}
+
+double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream) {
+    if (!model || !audio || num_streams <= 0 || samples_per_stream <= 0) return -1.0;
+    BatchModel *bm = (BatchModel *)model;
+    int16_t *d_audio = nullptr;
+    try {
+        vb::Engine &eng = bm->engine(0);
+        cudaSetDevice(eng.config().device);
+        const size_t bytes = (size_t)num_streams * samples_per_stream * sizeof(int16_t);
+        if (cudaMalloc((void **)&d_audio, bytes) != cudaSuccess) throw std::runtime_error("cudaMalloc(audio) failed");
+        if (cudaMemcpy(d_audio, audio, bytes, cudaMemcpyHostToDevice) != cudaSuccess) throw std::runtime_error("audio upload failed");
+        std::vector<vb::BestPath> res;
+        double ms = eng.run_resident(d_audio, num_streams, samples_per_stream, &res);
+        cudaFree(d_audio);
+        bm->resident_results.clear();
+        for (auto &bp : res) bm->resident_results.push_back(vb::result_json(bm->model(), vb::align_words(bm->model(), bp.arcs), 0.0f));
+        return ms;
+    } catch (const std::exception &e) {
+        if (d_audio) cudaFree(d_audio);
+        vb::log_msg(-1, "run_resident: %s", e.what());
+        return -1.0;
+    }
+}
+const char *vosk_batch_model_resident_result(VoskBatchModel *model, int stream) {
+    if (!model) return "";
+    BatchModel *bm = (BatchModel *)model;
+    if (stream < 0 || stream >= (int)bm->resident_results.size()) return "";
+    return bm->resident_results[stream].c_str();
+}
+
+void vosk_batch_recognizer_debug_capture(VoskBatchRecognizer *recognizer) {
+    if (recognizer) ((BatchRecognizer *)recognizer)->EnableCapture();
+}
+
+int64_t vosk_batch_recognizer_debug_get(VoskBatchRecognizer *recognizer, const char *what, void *out, int64_t cap) {
+    if (!recognizer || !what) return -1;
+    vb::Capture *c = ((BatchRecognizer *)recognizer)->capture();
+    if (!c) return -1;
+    const void *src = nullptr;
+    int64_t bytes = 0;
+    std::string w = what;
+    auto set = [&](const void *p, size_t n) { src = p; bytes = (int64_t)n; };
+    if (w == "mfcc") set(c->mfcc.data(), c->mfcc.size() * 4);
+    else if (w == "ivectors") set(c->ivectors.data(), c->ivectors.size() * 4);
+    else if (w == "loglikes") set(c->loglikes.data(), c->loglikes.size() * 4);
+    else if (w == "frame_off") set(c->frame_off.data(), c->frame_off.size() * 4);
+    else if (w == "tok_state") set(c->tok_state.data(), c->tok_state.size() * 4);
+    else if (w == "tok_arc") set(c->tok_arc.data(), c->tok_arc.size() * 4);
+    else if (w == "tok_prev") set(c->tok_prev.data(), c->tok_prev.size() * 4);
+    else if (w == "tok_cost") set(c->tok_cost.data(), c->tok_cost.size() * 4);
+    else if (w == "error") set(&c->error, 4);
+    else return -1;
+    if (out && cap > 0 && bytes > 0) memcpy(out, src, (size_t)(bytes < cap ? bytes : cap));
+    return bytes;
+}
+
+}  // extern "C"
