@@ -1,0 +1,302 @@
+#!/usr/bin/env python3
+"""bench.py — aggregate real-time factor (audio-seconds decoded per second) of the batch recognition path.
+
+Workload = BASELINE.json configs[1]: small-en-us architecture (random-init TDNN-F, synthetic ~20 MB HCLG),
+512 concurrent 16 kHz streams of U(8,16) s synthetic speech-like audio per GPU.  One "step" = decoding
+the whole 512-stream batch once.
+  value : device-resident run (samples already in HBM; CUDA events) — whole-job audio-s / s
+  e2e   : the reference-facing C ABI (vosk_batch_recognizer_accept_waveform in 8000-byte calls, round robin
+          as in [REF python/example/test_gpu_batch.py:27-51], vosk_batch_model_wait, front_result/pop) with
+          host buffers, host<->device copies inside the timed region
+  --impl reference : the CPU restatement of the reference's recognizer path (oracle/, "port") on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "vosk-api_b200"), os.path.join(ROOT, "vosk-api_b200", "tools"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "aggregate RTFx (audio-sec/sec)"
+UNIT = "audio-seconds/second"
+STREAMS = 512
+MODEL_CACHE = os.environ.get("VB_MODEL_CACHE", "/tmp/vb_bench_models")
+
+
+def model_dir(arch="small"):
+    import vbmodel
+    root = os.path.join(MODEL_CACHE, arch + "_0")
+    if not os.path.exists(os.path.join(root, "model", "graph", "HCLG.fst")):
+        vbmodel.write_model_dir(root, arch, 0)
+    return os.path.join(root, "model")
+
+
+def make_audio(n_streams, rank, lo=8.0, hi=16.0):
+    """Synthetic speech-like streams, U(lo,hi) seconds, seed 1000+i."""
+    import vbmodel
+    waves = []
+    # synthesising 512 x 12 s is slow in numpy: build 16 distinct voices and vary by circular shift / gain
+    base = [vbmodel.synth_audio(hi, 1000 + k) for k in range(16)]
+    rng = np.random.default_rng(12345 + rank)
+    for i in range(n_streams):
+        n = int(rng.uniform(lo, hi) * 16000)
+        b = base[i % 16]
+        sh = int(rng.integers(0, len(b)))
+        w = np.roll(b, sh)[:n].astype(np.float32) * rng.uniform(0.7, 1.2)
+        waves.append(np.clip(np.round(w), -32768, 32767).astype(np.int16))
+    return waves
+
+
+class ClockSampler:
+    def __init__(self, device):
+        self.rows = []
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def e2e_pass(vosk, model, pieces, wait_each_round=False):
+    """The reference's batch driver loop [REF python/example/test_gpu_batch.py:27-51]: 8000-byte reads fed round
+    robin to one recognizer per stream, FinishStream at EOF, Wait, then drain the results."""
+    recs = [vosk.BatchRecognizer(model, 16000.0) for _ in pieces]
+    texts = [""] * len(pieces)
+    rounds = max(len(p) for p in pieces)
+    for r in range(rounds + 1):
+        for i, rec in enumerate(recs):
+            if r < len(pieces[i]):
+                rec.AcceptWaveform(pieces[i][r])
+            elif r == len(pieces[i]):
+                rec.FinishStream()
+        if wait_each_round:
+            model.Wait()
+    model.Wait()
+    for i, rec in enumerate(recs):
+        texts[i] = rec.Result()
+    return texts
+
+
+def run_oracle_sample(n_streams, threads):
+    """CPU restatement of the reference recognizer path on a bounded sample; returns (audio_s, wall_s)."""
+    import oracle
+    import vbmodel
+    model = vbmodel.load_model_dir(model_dir())
+    waves = make_audio(n_streams, 999)
+    rc = oracle.ResultCtx(model)
+    oracle.recognize(model, waves[0][:16000], rc=rc)  # warm (table construction, page-in)
+    audio = sum(len(w) for w in waves) / 16000.0
+    t0 = time.perf_counter()
+    if threads <= 1:
+        for w in waves:
+            oracle.recognize(model, w, rc=rc)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL inside the oracle calls
+            list(ex.map(lambda w: oracle.recognize(model, w, rc=rc), waves))
+    return audio, time.perf_counter() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine")
+    ap.add_argument("--streams", type=int, default=STREAMS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--options", default="")
+    ap.add_argument("--wait-each-round", action="store_true", help="call Wait() after every feeding round, as the reference example does")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "small-en-us arch (random-init TDNN-F, synthetic HCLG ~1.0M arcs), %d concurrent 16 kHz streams of U(8,16) s per GPU" % a.streams,
+              "streams_per_gpu": a.streams, "frames_per_chunk": 51, "beam": 13.0, "lattice_beam": 6.0, "max_active": 7000,
+              "l2": "inputs+state larger than L2 (audio ~190 MB, token logs GBs)", "sharding": "streams by utterance, no collective"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = os.cpu_count() or 1
+        n = max(cores, 8)
+        vals = []
+        for _ in range(max(1, min(a.steps, 2))):
+            audio, wall = run_oracle_sample(n, cores)
+            vals.append(audio / wall)
+        v = float(np.mean(vals))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": config,
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                           "sample": "%d streams of U(8,16) s, one stream per thread, %d threads" % (n, cores)},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    os.environ["VOSK_BATCH_DEVICES"] = str(local_rank)
+    if rank == 0:
+        model_dir()  # generate once
+    if world > 1:
+        dist.barrier()
+    import vosk
+    mdir = model_dir()
+    vosk.SetLogLevel(-1)
+    opts = "num-channels=%d,max-batch-size=%d,max-seconds=18" % (a.streams, min(a.streams, 1024))
+    if a.options:
+        opts += "," + a.options
+    model = vosk.BatchModel(mdir, options=opts)
+    waves = make_audio(a.streams, rank)
+    lengths = np.array([len(w) for w in waves], dtype=np.int32)
+    stride = int((lengths.max() + 7) // 8 * 8)
+    audio_mat = np.zeros((a.streams, stride), dtype=np.int16)
+    for i, w in enumerate(waves):
+        audio_mat[i, :len(w)] = w
+    audio_s = float(lengths.sum()) / 16000.0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- value: device-resident ----------------
+    texts = None
+    for _ in range(a.warmup):
+        _, texts = model.RunResident(audio_mat, lengths)
+    model.ResetStats()
+    model.SetTiming(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        ms, texts = model.RunResident(audio_mat, lengths)
+        dev_ms += ms
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    clocks = sampler.stop()
+    st = model.Stats()
+    model.SetTiming(False)
+    dev_s = max_over_ranks(dev_ms / 1000.0)
+    value = world * audio_s * a.steps / dev_s
+
+    # ---------------- e2e: through the C ABI with host buffers ----------------
+    pieces = [[w[i:i + 4000].tobytes() for i in range(0, len(w), 4000)] for w in waves]  # 8000-byte reads, as the reference driver
+    for _ in range(min(a.warmup, 1)):
+        e2e_pass(vosk, model, pieces, a.wait_each_round)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_texts = None
+    for _ in range(a.steps):
+        e2e_texts = e2e_pass(vosk, model, pieces, a.wait_each_round)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * audio_s * a.steps / e2e_s
+    same = sum(1 for x, y in zip(texts, e2e_texts) if x == y)
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks = {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops": pk["bf16_tflops_sustained"], "src": "measured"}
+    except Exception:
+        pass
+    kernel_ms = {"mfcc": st["ms_feat"], "ivector": st["ms_ivector"], "tdnnf": st["ms_nnet"], "search": st["ms_search"]}
+    dominant = max(kernel_ms, key=kernel_ms.get)
+    out_frames = sum((int(1 + (n - 400) // 160) + 2) // 3 for n in lengths) * a.steps
+    flop = 7.95e6 * out_frames  # 7.95 MFLOP per output frame, small architecture
+    # SURVEY.md §8(d) beam-search byte model from the in-kernel counters
+    T, Ae, Aeps, N = st["tokens"], st["arcs_emitting"], st["arcs_epsilon"], st["tokens_new"]
+    search_bytes = T * 16 + (Ae + Aeps) * 20 + Ae * 4 + N * 16
+    feat_bytes = 480.0 * sum(int(1 + (n - 400) // 160) for n in lengths) * a.steps
+    if dominant == "tdnnf":
+        ach = flop / (kernel_ms["tdnnf"] / 1000.0) / 1e12
+        roof = {"kernel": "tdnnf gemm chain", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_src": peaks["src"] + " bf16 sustained (tf32 nominal is half)"}
+    elif dominant == "search":
+        ach = search_bytes / (kernel_ms["search"] / 1000.0) / 1e9
+        roof = {"kernel": "decode_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"]}
+    else:
+        ach = feat_bytes / (kernel_ms[dominant] / 1000.0) / 1e9
+        roof = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"]}
+
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        ca, cw = run_oracle_sample(3, 1)
+        cpu = {"value": ca / cw, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "3 streams of U(8,16) s decoded one after another on one core (%.1f s of CPU work)" % cw}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": dev_s * 1000.0 / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(lengths.sum()) * 2 + a.streams * 64,
+                        "d2h_bytes_per_step": a.streams * (4 * (18 * 100 // 3 + 2) * 4 + 64 * 4 + 32),
+                        "transcripts_equal_to_resident_run": "%d/%d" % (same, len(texts))},
+                "gpu_launches": int(st["launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "kernel_ms_per_step": {k: v / a.steps for k, v in kernel_ms.items()},
+                "host_wall_ms_per_step_resident": wall_resident * 1000.0 / a.steps,
+                "search_counters_per_step": {"tokens": T / a.steps, "arcs_emitting": Ae / a.steps, "arcs_epsilon": Aeps / a.steps, "tokens_new": N / a.steps},
+                "audio_seconds_per_step": world * audio_s}
+        print(json.dumps(line))
+    del model
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

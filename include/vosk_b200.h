@@ -36,11 +36,13 @@ int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n);
 void vosk_batch_model_reset_stats(VoskBatchModel *model);
 void vosk_batch_model_set_timing(VoskBatchModel *model, int on);
 
-/* Device-resident run (kernel-level measurement): uploads num_streams x samples_per_stream int16
- * samples to HBM (untimed), then decodes all streams in lockstep with no host<->device sample
- * traffic and returns the elapsed device time in milliseconds (CUDA events), < 0 on error.
+/* Device-resident run (kernel-level measurement): uploads the num_streams x samples_per_stream int16
+ * matrix to HBM (untimed), then decodes all streams in lockstep with no host<->device sample traffic
+ * and returns the elapsed device time in milliseconds (CUDA events), < 0 on error.  lengths (may be
+ * NULL = every stream uses the full row) gives the number of valid samples of each row.
  * Result texts are kept until the next call; fetch with vosk_batch_model_resident_result. */
-double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream);
+double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream,
+                                     const int *lengths);
 const char *vosk_batch_model_resident_result(VoskBatchModel *model, int stream);
 
 /* Test taps.  Enable before the first accept_waveform on a model created with debug-capture=1;

@@ -338,10 +338,20 @@ void Engine::wait() {
 }
 
 StepStats Engine::stats() {
+    unsigned long long c[4] = {0, 0, 0, 0};
+    cudaSetDevice(cfg_.device);
+    cudaMemcpy(c, dec_.counters, sizeof c, cudaMemcpyDeviceToHost);
     std::lock_guard<std::mutex> lk(stats_mu_);
-    return stats_;
+    StepStats s = stats_;
+    s.tok = c[0];
+    s.arc_e = c[1];
+    s.arc_eps = c[2];
+    s.tok_new = c[3];
+    return s;
 }
 void Engine::reset_stats() {
+    cudaSetDevice(cfg_.device);
+    cudaMemset(dec_.counters, 0, 8 * sizeof(unsigned long long));
     std::lock_guard<std::mutex> lk(stats_mu_);
     stats_ = StepStats{};
 }
@@ -585,40 +595,46 @@ void Engine::finish_lane(Lane &ln, int k) {
     if (ln.s->on_result) ln.s->on_result(bp);
 }
 
-double Engine::run_resident(const int16_t *d_audio, int num_streams, int samples_per_stream, std::vector<BestPath> *out) {
-    // every stream advances in lockstep, one chunk per step, no host<->device sample traffic
+double Engine::run_resident(const int16_t *d_audio, int num_streams, int stride, const int *lengths, std::vector<BestPath> *out) {
+    // all streams advance one chunk per step until their own end; no host<->device sample traffic
     if (num_streams > cfg_.num_channels) throw std::runtime_error("run_resident: more streams than channels");
     wait();
     const int spc = samples_per_chunk();
     std::vector<std::shared_ptr<Stream>> ss(num_streams);
     std::vector<BestPath> res(num_streams);
+    int max_chunks = 0;
     for (int i = 0; i < num_streams; i++) {
         ss[i] = std::make_shared<Stream>();
         ss[i]->id = (uint64_t)i;
         ss[i]->channel = i;
         BestPath *slot = &res[i];
         ss[i]->on_result = [slot](const BestPath &bp) { *slot = bp; };
+        const int len = lengths ? lengths[i] : stride;
+        if (len < 0 || len > stride) throw std::runtime_error("run_resident: bad stream length");
+        max_chunks = std::max(max_chunks, len / spc + 1);
     }
     cudaEvent_t e0, e1;
     VB_CUDA_CHECK(cudaEventCreate(&e0));
     VB_CUDA_CHECK(cudaEventCreate(&e1));
     VB_CUDA_CHECK(cudaEventRecord(e0, stream_));
-    const int nfull = samples_per_stream / spc;
     std::vector<Lane> lanes;
-    for (int k = 0; k <= nfull; k++) {
-        const bool last = k == nfull;
-        const int n = last ? samples_per_stream - nfull * spc : spc;
-        for (int g0 = 0; g0 < num_streams; g0 += cfg_.max_lanes) {
-            lanes.clear();
-            for (int i = g0; i < std::min(num_streams, g0 + cfg_.max_lanes); i++) {
-                Lane ln;
-                ln.s = ss[i];
-                ln.chunk.samples.resize(n);  // length only; the samples are read from d_audio
-                ln.chunk.last = last;
-                lanes.push_back(std::move(ln));
+    for (int k = 0; k < max_chunks; k++) {
+        lanes.clear();
+        for (int i = 0; i < num_streams; i++) {
+            const int len = lengths ? lengths[i] : stride;
+            const int nfull = len / spc;
+            if (k > nfull) continue;
+            Lane ln;
+            ln.s = ss[i];
+            ln.chunk.samples.resize(k == nfull ? len - nfull * spc : spc);  // length only; samples are read from d_audio
+            ln.chunk.last = k == nfull;
+            lanes.push_back(std::move(ln));
+            if ((int)lanes.size() == cfg_.max_lanes) {
+                step(lanes, d_audio, stride);
+                lanes.clear();
             }
-            step(lanes, d_audio, samples_per_stream);
         }
+        if (!lanes.empty()) step(lanes, d_audio, stride);
     }
     VB_CUDA_CHECK(cudaEventRecord(e1, stream_));
     VB_CUDA_CHECK(cudaEventSynchronize(e1));

@@ -79,7 +79,7 @@ class Engine {
 
     // Device-resident run for kernel-level benchmarking: `audio` holds num_streams x samples int16 already in
     // HBM; processes every stream chunk by chunk with no host<->device sample traffic.  Returns device ms.
-    double run_resident(const int16_t *d_audio, int num_streams, int samples_per_stream, std::vector<BestPath> *out);
+    double run_resident(const int16_t *d_audio, int num_streams, int stride, const int *lengths, std::vector<BestPath> *out);
 
    private:
     struct Lane {

@@ -164,7 +164,8 @@ void vosk_batch_model_set_timing(VoskBatchModel *model, int on) {
     for (size_t i = 0; i < bm->num_engines(); i++) bm->engine(i).set_timing(on != 0);
 }
 
-double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream) {
+double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream,
+                                     const int *lengths) {
     if (!model || !audio || num_streams <= 0 || samples_per_stream <= 0) return -1.0;
     BatchModel *bm = (BatchModel *)model;
     int16_t *d_audio = nullptr;
@@ -175,7 +176,7 @@ double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio
         if (cudaMalloc((void **)&d_audio, bytes) != cudaSuccess) throw std::runtime_error("cudaMalloc(audio) failed");
         if (cudaMemcpy(d_audio, audio, bytes, cudaMemcpyHostToDevice) != cudaSuccess) throw std::runtime_error("audio upload failed");
         std::vector<vb::BestPath> res;
-        double ms = eng.run_resident(d_audio, num_streams, samples_per_stream, &res);
+        double ms = eng.run_resident(d_audio, num_streams, samples_per_stream, lengths, &res);
         cudaFree(d_audio);
         bm->resident_results.clear();
         for (auto &bp : res) bm->resident_results.push_back(vb::result_json(bm->model(), vb::align_words(bm->model(), bp.arcs), 0.0f));

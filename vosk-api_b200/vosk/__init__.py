@@ -91,11 +91,16 @@ class BatchModel(object):
     def SetTiming(self, on):
         _c.vosk_batch_model_set_timing(self._handle, int(on))
 
-    def RunResident(self, audio):
-        """audio: C-contiguous int16 numpy array [streams, samples]; returns (device_ms, [result text])."""
+    def RunResident(self, audio, lengths=None):
+        """audio: C-contiguous int16 numpy array [streams, samples] (+ optional valid length per row);
+        returns (device_ms, [result text])."""
         import numpy as np
         a = np.ascontiguousarray(audio, dtype=np.int16)
-        ms = _c.vosk_batch_model_run_resident(self._handle, _ffi.cast("int16_t *", a.ctypes.data), a.shape[0], a.shape[1])
+        lp = _ffi.NULL
+        if lengths is not None:
+            ln = np.ascontiguousarray(lengths, dtype=np.int32)
+            lp = _ffi.cast("int *", ln.ctypes.data)
+        ms = _c.vosk_batch_model_run_resident(self._handle, _ffi.cast("int16_t *", a.ctypes.data), a.shape[0], a.shape[1], lp)
         if ms < 0:
             raise RuntimeError("run_resident failed")
         return ms, [_ffi.string(_c.vosk_batch_model_resident_result(self._handle, i)).decode() for i in range(a.shape[0])]
