@@ -12,19 +12,25 @@
 //
 // B200 mapping: lanes are independent, so each CTA owns one lane for all frames of the chunk and the whole
 // frame loop runs inside one launch with block-level barriers only (no grid sync, no per-frame launches,
-// no host round trips).  Arc expansion is warp-cooperative: a warp takes 32 tokens, prefix-sums their
-// out-degrees in shared memory and then walks the concatenated arc list 32 arcs at a time with one 16-byte
-// load per arc; the frame's log-likelihood row is staged in shared memory; per-state recombination is a
-// 64-bit atomicMin on an open-addressing table private to the CTA.
+// no host round trips).  CTAs are small (256 threads, 4 per SM) so that all lanes of a step are resident at
+// once and one lane's barrier/latency bubbles are filled by its neighbours.  Emitting-arc expansion is
+// balanced per ARC, not per token: survivors with out-arcs are compacted with an exclusive prefix sum of
+// their out-degrees, the concatenated arc list is cut into 32-arc windows dealt round-robin to the warps,
+// and a window finds the owners of its arcs from one coalesced load of the prefix array plus a shared-memory
+// marker scan — every lane then issues one 16-byte arc load.  The frame's log-likelihood row is staged in
+// shared memory; per-state recombination is a 64-bit atomicMin on an open-addressing table private to the
+// CTA whose active window is sized per frame so that small frames stay L2-resident.
 #include <cfloat>
+#include <climits>
 
 #include "vb_kernels.h"
 
 namespace vb {
 
 namespace {
-constexpr int kDecThreads = 512;
+constexpr int kDecThreads = 256;
 constexpr int kDecWarps = kDecThreads / 32;
+constexpr int kDecBlocksPerSM = 4;
 constexpr unsigned long long kValMax = ~0ull;
 constexpr int kEmpty = -1;
 
@@ -48,18 +54,13 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 struct Shared {
     unsigned min_ord;  // running minimum of candidate costs (ordered)
     int n_cand, n_next, error;
-    int warp_cnt[kDecWarps];
+    int warp_cnt[kDecWarps], warp_exp[kDecWarps], warp_deg[kDecWarps];
     unsigned hist[256];
     unsigned sel_prefix, sel_mask;
     int sel_k;
     unsigned red_u[kDecWarps];
     unsigned long long red_ull[kDecWarps];
-    // per-warp expansion staging
-    int st_pref[kDecWarps][33];
-    int st_a0[kDecWarps][32];
-    float st_cost[kDecWarps][32];
-    int st_src[kDecWarps][32];
-    unsigned long long cnt_tok, cnt_arc_e, cnt_arc_eps, cnt_new;
+    int own[kDecWarps][32];  // per-warp marker array of the arc-window owner scan
 };
 
 struct Ctx {
@@ -71,7 +72,11 @@ struct Ctx {
     int *htok;
     unsigned long long *cpk;
     int *cslot, *csrc, *rank;
+    int *sv_pref, *sv_a0, *sv_src, *win_owner;
+    float *sv_cost;
     int tid, warp, lane;
+    unsigned hmask;  // this frame's table window (power of two - 1): the table is empty between frames, so any
+                     // power-of-two prefix of it is a valid table; small frames stay L2-resident
 };
 
 __device__ __forceinline__ int agg_inc(int *counter) {
@@ -85,18 +90,14 @@ __device__ __forceinline__ int agg_inc(int *counter) {
 
 // insert (state, packed) ; records a candidate when it improved the state's best word
 __device__ __forceinline__ void relax(Ctx &c, int state, unsigned long long pk, int src) {
-    const unsigned mask = (unsigned)c.a.hash_size - 1;
+    const unsigned mask = c.hmask;
     unsigned h = ((unsigned)state * 2654435761u) >> 7 & mask;
     int probes = 0;
     for (;;) {
-        int cur = __ldcg(c.hkey + h);
-        if (cur == state) break;
-        if (cur == kEmpty) {
-            int prev = atomicCAS(c.hkey + h, kEmpty, state);
-            if (prev == kEmpty || prev == state) break;
-        }
+        int prev = atomicCAS(c.hkey + h, kEmpty, state);
+        if (prev == kEmpty || prev == state) break;
         h = (h + 1) & mask;
-        if (++probes > c.a.hash_size) {
+        if (++probes > (int)mask) {
             c.sh.error = 1;
             return;
         }
@@ -135,7 +136,7 @@ __device__ float block_select(Ctx &c, const float *cost, int n, int k) {
     }
     for (int pass = 3; pass >= 0; pass--) {
         const int shift = pass * 8;
-        if (c.tid < 256) c.sh.hist[c.tid] = 0;
+        c.sh.hist[c.tid] = 0;  // kDecThreads == 256
         __syncthreads();
         const unsigned prefix = c.sh.sel_prefix, mask = c.sh.sel_mask;
         for (int i = c.tid; i < n; i += kDecThreads) {
@@ -181,22 +182,41 @@ __device__ float block_select(Ctx &c, const float *cost, int n, int k) {
     return r;
 }
 
-// GetCutoff of LatticeFasterDecoder (see oracle/orc_decode.cc get_cutoff)
+// GetCutoff of LatticeFasterDecoder (see oracle/orc_decode.cc get_cutoff).  The order statistics only matter
+// when they fall on the right side of best+beam, which a counting pass decides:
+//   kth(max_active) <  beam_cutoff  <=>  #{cost <  beam_cutoff} >  max_active
+//   kth(min_active) >  beam_cutoff  <=>  #{cost <= beam_cutoff} <= min_active
+// so the exact radix select runs only on the frames where it changes the result.
 __device__ float get_cutoff(Ctx &c, const float *cost, int n, float *adaptive_beam, float *best_out) {
     const DecArgs &a = c.a;
     float best = block_min(c, cost, n);
     *best_out = best;
-    float beam_cutoff = best + a.beam, min_active_cutoff = INFINITY, max_active_cutoff = INFINITY;
-    if (n > a.max_active) max_active_cutoff = block_select(c, cost, n, a.max_active);
-    if (max_active_cutoff < beam_cutoff) {
+    const float beam_cutoff = best + a.beam;
+    int lt = 0, le = 0;
+    for (int i = c.tid; i < n; i += kDecThreads) {
+        float v = cost[i];
+        lt += v < beam_cutoff;
+        le += v <= beam_cutoff;
+    }
+    unsigned long long tot = ((unsigned long long)lt << 32) | (unsigned)le;
+    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (c.lane == 0) c.sh.red_ull[c.warp] = tot;
+    __syncthreads();
+    tot = 0;
+    for (int w = 0; w < kDecWarps; w++) tot += c.sh.red_ull[w];
+    __syncthreads();
+    const int n_lt = (int)(tot >> 32), n_le = (int)(unsigned)tot;
+    if (n > a.max_active && n_lt > a.max_active) {
+        float max_active_cutoff = block_select(c, cost, n, a.max_active);
         *adaptive_beam = max_active_cutoff - best + a.beam_delta;
         return max_active_cutoff;
     }
-    if (n > a.min_active) {
-        if (a.min_active == 0) min_active_cutoff = best;
-        else min_active_cutoff = block_select(c, cost, n, a.min_active);
+    if (n <= a.min_active) {  // fewer tokens than min_active: no pruning (Kaldi leaves min_active_cutoff at +inf)
+        *adaptive_beam = INFINITY;
+        return INFINITY;
     }
-    if (min_active_cutoff > beam_cutoff) {
+    if (a.min_active > 0 && n_le <= a.min_active) {
+        float min_active_cutoff = block_select(c, cost, n, a.min_active);
         *adaptive_beam = min_active_cutoff - best + a.beam_delta;
         return min_active_cutoff;
     }
@@ -204,90 +224,31 @@ __device__ float get_cutoff(Ctx &c, const float *cost, int n, float *adaptive_be
     return beam_cutoff;
 }
 
-// Warp-cooperative arc walk.  Each lane contributes one token (a0, deg, cost, src); the warp then visits the
-// concatenated arc list 32 arcs at a time.  EMIT: acoustic cost from the shared log-likelihood row.
-template <bool EMIT>
-__device__ __forceinline__ void warp_expand(Ctx &c, int a0, int deg, float cost, int src, float cost_offset,
-                                            float adaptive_beam, float hard_cutoff) {
-    Shared &sh = c.sh;
-    const int w = c.warp, lane = c.lane;
-    int incl = deg;
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;
-    sh.st_pref[w][lane] = incl - deg;
-    sh.st_a0[w][lane] = a0;
-    sh.st_cost[w][lane] = cost;
-    sh.st_src[w][lane] = src;
-    if (lane == 0) sh.st_pref[w][32] = total;
-    __syncwarp();
-    for (int j0 = 0; j0 < total; j0 += 32) {
-        const int j = j0 + lane;
-        const bool valid = j < total;
-        float tot = INFINITY;
-        int arc = 0, next = 0, q = 0;
-        if (valid) {
-            int lo = 0, hi = 32;  // largest q with pref[q] <= j
-            while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (sh.st_pref[w][mid] <= j) lo = mid; else hi = mid;
-            }
-            q = lo;
-            arc = sh.st_a0[w][q] + (j - sh.st_pref[w][q]);
-            const int4 av = __ldg(c.a.g.arcs + arc);
-            next = av.y;
-            const float wgt = __int_as_float(av.x);
-            if (EMIT) {
-                float ac = cost_offset - c.a.acoustic_scale * c.ll[av.z];
-                tot = sh.st_cost[w][q] + ac + wgt;
-            } else {
-                tot = sh.st_cost[w][q] + wgt;
-            }
-        }
-        float cut = hard_cutoff;
-        if (EMIT) {
-            unsigned m = ford(tot);
-            for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (lane == 0) atomicMin(&sh.min_ord, m);
-            __syncwarp();
-            cut = unord(*(volatile unsigned *)&sh.min_ord) + adaptive_beam;  // loose (>= final) cutoff
-        }
-        if (valid && tot < cut) relax(c, next, pack(tot, arc), sh.st_src[w][q]);
-    }
-    __syncwarp();
-}
-
-// epsilon closure over candidates [lo, hi) until no candidate is added; returns total candidate count
-__device__ int closure(Ctx &c, int lo, int hi, float cutoff) {
+// epsilon closure over candidates [lo, hi) until no candidate is added; returns total candidate count.
+// Epsilon out-degrees are tiny (0-2), so one thread per candidate is balanced.
+__device__ int closure(Ctx &c, int lo, int hi, float cutoff, unsigned long long *arcs_seen) {
     const DecArgs &a = c.a;
-    unsigned long long arcs_seen = 0;
     while (lo < hi) {
-        for (int base = lo + c.warp * 32; base < hi; base += kDecWarps * 32) {
-            const int i = base + c.lane;
-            int a0 = 0, deg = 0, slot = 0;
-            float cost = 0.f;
-            if (i < hi) {
-                unsigned long long pk = c.cpk[i];
-                slot = c.cslot[i];
-                cost = unord((unsigned)(pk >> 32));
-                if (__ldcg(c.hval + slot) == pk && cost < cutoff) {
-                    int s = __ldcg(c.hkey + slot);
-                    a0 = __ldg(a.g.eps_begin + s);
-                    deg = __ldg(a.g.e_begin + s + 1) - a0;
+        for (int i = lo + c.tid; i < hi; i += kDecThreads) {
+            const unsigned long long pk = c.cpk[i];
+            const int slot = c.cslot[i];
+            const float cost = unord((unsigned)(pk >> 32));
+            if (__ldcg(c.hval + slot) == pk && cost < cutoff) {
+                const int s = __ldcg(c.hkey + slot);
+                const int a0 = __ldg(a.g.eps_begin + s), a1 = __ldg(a.g.e_begin + s + 1);
+                *arcs_seen += (unsigned)(a1 - a0);
+                for (int arc = a0; arc < a1; arc++) {
+                    const int4 av = __ldg(a.g.arcs + arc);
+                    const float tot = cost + __int_as_float(av.x);
+                    if (tot < cutoff) relax(c, av.y, pack(tot, arc), slot);
                 }
             }
-            arcs_seen += (unsigned)deg;
-            warp_expand<false>(c, a0, deg, cost, slot, 0.f, 0.f, cutoff);
         }
         __syncthreads();
         lo = hi;
         hi = min(c.sh.n_cand, a.cand_cap);
         __syncthreads();
     }
-    if (arcs_seen) atomicAdd(&c.sh.cnt_arc_eps, arcs_seen);
     return hi;
 }
 
@@ -340,22 +301,26 @@ __device__ void finalize_tokens(Ctx &c, int n_emit, int n_cand, float cutoff, in
 }
 }  // namespace
 
-__global__ void __launch_bounds__(kDecThreads, 2) decode_kernel(DecArgs a) {
+__global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(DecArgs a) {
     extern __shared__ __align__(16) float s_ll[];
     __shared__ Shared sh;
     const int tid = threadIdx.x;
     const size_t g = blockIdx.x;
+    const int nwin_cap = a.cand_cap / 32 + 2;
     Ctx c{a, sh, s_ll,
           a.hash_key + g * a.hash_size, a.hash_val + g * a.hash_size, a.hash_tok + g * a.hash_size,
           a.cand_packed + g * a.cand_cap, a.cand_slot + g * a.cand_cap, a.cand_src + g * a.cand_cap,
-          a.rank + g * a.tok_cap, tid, tid >> 5, tid & 31};
-    if (tid == 0) {
-        sh.cnt_tok = sh.cnt_arc_e = sh.cnt_arc_eps = sh.cnt_new = 0;
-    }
+          a.rank + g * a.tok_cap,
+          a.sv_pref + g * a.tok_cap, a.sv_a0 + g * a.tok_cap, a.sv_src + g * a.tok_cap, a.win_owner + g * nwin_cap,
+          a.sv_cost + g * a.tok_cap,
+          tid, tid >> 5, tid & 31, (unsigned)a.hash_size - 1};
+    unsigned long long cnt_tok = 0, cnt_arc_e = 0, cnt_arc_eps = 0, cnt_new = 0;  // per-thread profiling counters
     const int npdf = a.out_node.dim;
     for (int l = blockIdx.x; l < a.num_lanes; l += gridDim.x) {
         const LaneDesc ln = a.lanes[l];
         const int ch = ln.channel;
+        const long long clk0 = clock64();
+        int max_tok = 0;
         DecChannelState *cs = a.cs + ch;
         const size_t tbase = (size_t)ch * 2 * a.tok_cap;
         int *log_prev = a.log_prev + (size_t)ch * a.log_cap;
@@ -372,10 +337,11 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_kernel(DecArgs a) {
                 sh.n_cand = 0;
                 sh.n_next = 0;
             }
+            c.hmask = (unsigned)a.hash_size - 1;
             __syncthreads();
             if (tid == 0) relax(c, a.g.start, pack(0.f, -1), -1);
             __syncthreads();
-            int nc = closure(c, 0, min(sh.n_cand, a.cand_cap), a.beam);
+            int nc = closure(c, 0, min(sh.n_cand, a.cand_cap), a.beam, &cnt_arc_eps);
             finalize_tokens(c, 1, nc, INFINITY, a.tok_state + tbase, a.tok_cost + tbase, a.tok_arc + tbase, a.tok_prev + tbase);
             n_cur = min(sh.n_next, a.tok_cap);
             parity = 0;
@@ -401,6 +367,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_kernel(DecArgs a) {
             int *n_arc = a.tok_arc + tbase + (size_t)(parity ^ 1) * a.tok_cap;
             int *n_prev = a.tok_prev + tbase + (size_t)(parity ^ 1) * a.tok_cap;
             if (n_cur == 0 && !final_pass) { frame++; continue; }  // search died: nothing to expand
+            max_tok = max(max_tok, n_cur);
             float adaptive_beam = a.beam, best = 0.f, cur_cutoff = INFINITY;
             if (!final_pass) {
                 // stage this frame's log-likelihood row
@@ -414,86 +381,177 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_kernel(DecArgs a) {
                 sh.n_cand = 0;
                 sh.n_next = 0;
             }
-            // ---- survivors: rank (stable), log, expand ----
+            // ---- pass A: per-warp counts of survivors, survivors with out-arcs, and out-arcs ----
             const int span = ((n_cur + kDecWarps - 1) / kDecWarps + 31) & ~31;
             const int wbeg = min(c.warp * span, n_cur), wend = min(wbeg + span, n_cur);
-            int cnt = 0;
-            for (int i = wbeg + c.lane; i < wend + ((32 - (wend - wbeg) % 32) % 32); i += 32) {
-                bool f = i < wend && t_cost[i] <= cur_cutoff;
-                cnt += __popc(__ballot_sync(0xffffffffu, f));
+            {
+                int cnt = 0, cexp = 0, degsum = 0;
+                for (int i0 = wbeg; i0 < wend; i0 += 32) {
+                    const int i = i0 + c.lane;
+                    const bool f = i < wend && t_cost[i] <= cur_cutoff;
+                    int deg = 0;
+                    if (f && !final_pass) {
+                        const int s = t_state[i];
+                        deg = __ldg(a.g.eps_begin + s) - __ldg(a.g.e_begin + s);
+                    }
+                    cnt += __popc(__ballot_sync(0xffffffffu, f));
+                    cexp += __popc(__ballot_sync(0xffffffffu, deg > 0));
+                    degsum += deg;
+                }
+                for (int o = 16; o; o >>= 1) degsum += __shfl_xor_sync(0xffffffffu, degsum, o);
+                if (c.lane == 0) {
+                    sh.warp_cnt[c.warp] = cnt;
+                    sh.warp_exp[c.warp] = cexp;
+                    sh.warp_deg[c.warp] = degsum;
+                }
             }
-            if (c.lane == 0) sh.warp_cnt[c.warp] = cnt;
             __syncthreads();
-            int base = 0, n_surv = 0;
+            int rbase = 0, ebase = 0, abase = 0, n_surv = 0, n_exp = 0, n_arcs = 0;
             for (int w = 0; w < kDecWarps; w++) {
-                if (w < c.warp) base += sh.warp_cnt[w];
+                if (w < c.warp) {
+                    rbase += sh.warp_cnt[w];
+                    ebase += sh.warp_exp[w];
+                    abase += sh.warp_deg[w];
+                }
                 n_surv += sh.warp_cnt[w];
+                n_exp += sh.warp_exp[w];
+                n_arcs += sh.warp_deg[w];
+            }
+            {
+                // table window: room for every emitting arc's target plus closure growth, at load factor <= 1/3
+                unsigned want = 3u * (unsigned)n_arcs + 1024u, win = 4096;
+                while (win < want && win < (unsigned)a.hash_size) win <<= 1;
+                c.hmask = min(win, (unsigned)a.hash_size) - 1;
+            }
+            if (n_arcs > a.cand_cap) {  // more emitting arcs than candidate slots: flag and truncate
+                if (tid == 0) sh.error = 6;
+                n_arcs = a.cand_cap;
             }
             const bool log_ok = frame <= a.max_frames && log_count + n_surv <= a.log_cap;
             if (!log_ok && tid == 0) sh.error = 4;
-            // pass 2a: ranks (needed by every token's epsilon back-reference before logging)
-            {
-                int b = base;
-                for (int i0 = wbeg; i0 < wend; i0 += 32) {
-                    int i = i0 + c.lane;
-                    bool f = i < wend && t_cost[i] <= cur_cutoff;
-                    unsigned bal = __ballot_sync(0xffffffffu, f);
-                    if (i < wend) c.rank[i] = f ? b + __popc(bal & lanemask_lt()) : -1;
-                    b += __popc(bal);
-                }
-            }
-            __syncthreads();
-            const float cost_offset = -best;
-            unsigned long long arcs_seen = 0;
+            // ---- pass B: stable ranks; compact the expandable survivors with their arc prefix; window owners ----
             for (int i0 = wbeg; i0 < wend; i0 += 32) {
-                int i = i0 + c.lane;
-                int a0 = 0, deg = 0, li = -1;
+                const int i = i0 + c.lane;
+                const bool f = i < wend && t_cost[i] <= cur_cutoff;
+                int deg = 0, a0 = 0;
                 float cost = 0.f;
-                if (i < wend) {
-                    int r = c.rank[i];
-                    if (r >= 0) {
-                        cost = t_cost[i];
-                        li = log_count + r;
-                        int s = t_state[i];
-                        if (log_ok) {
-                            int pv = t_prev[i];
-                            if (pv <= -2) {  // epsilon predecessor lives in this frame: it must have survived too
-                                int pr = c.rank[-2 - pv];
-                                if (pr < 0) sh.error = 5;  // only possible with negative epsilon weights
-                                pv = pr < 0 ? -1 : log_count + pr;
-                            }
-                            log_prev[li] = pv;
-                            log_arc[li] = t_arc[i];
-                            log_cost[li] = cost;
-                            if (log_state) log_state[li] = s;
-                        }
-                        if (!final_pass) {
-                            a0 = __ldg(a.g.e_begin + s);
-                            deg = __ldg(a.g.eps_begin + s) - a0;
-                        }
+                if (f) {
+                    cost = t_cost[i];
+                    if (!final_pass) {
+                        const int s = t_state[i];
+                        a0 = __ldg(a.g.e_begin + s);
+                        deg = __ldg(a.g.eps_begin + s) - a0;
                     }
                 }
-                if (!final_pass) {
-                    arcs_seen += (unsigned)deg;
-                    warp_expand<true>(c, a0, deg, cost, li, cost_offset, adaptive_beam, INFINITY);
+                const unsigned bal = __ballot_sync(0xffffffffu, f), bexp = __ballot_sync(0xffffffffu, deg > 0);
+                const int r = rbase + __popc(bal & lanemask_lt());
+                if (i < wend) c.rank[i] = f ? r : -1;
+                int incl = deg;
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (c.lane >= o) incl += v;
+                }
+                if (deg > 0) {
+                    const int e = ebase + __popc(bexp & lanemask_lt());
+                    const int p = abase + incl - deg;
+                    c.sv_pref[e] = p;
+                    c.sv_a0[e] = a0;
+                    c.sv_cost[e] = cost;
+                    c.sv_src[e] = log_count + r;
+                    for (int w = (p + 31) >> 5; w <= (p + deg - 1) >> 5 && w < nwin_cap; w++) c.win_owner[w] = e;
+                }
+                rbase += __popc(bal);
+                ebase += __popc(bexp);
+                abase += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            __syncthreads();
+            // ---- pass C1: token log of the survivors (prev of an epsilon-created token = a survivor of this frame) ----
+            if (log_ok) {
+                for (int i = tid; i < n_cur; i += kDecThreads) {
+                    const int r = c.rank[i];
+                    if (r < 0) continue;
+                    const int li = log_count + r;
+                    int pv = t_prev[i];
+                    if (pv <= -2) {
+                        const int pr = c.rank[-2 - pv];
+                        if (pr < 0) sh.error = 5;  // only possible with negative epsilon weights
+                        pv = pr < 0 ? -1 : log_count + pr;
+                    }
+                    log_prev[li] = pv;
+                    log_arc[li] = t_arc[i];
+                    log_cost[li] = t_cost[i];
+                    if (log_state) log_state[li] = t_state[i];
+                }
+                if (tid == 0) {
+                    frame_off[frame] = log_count;
+                    frame_off[frame + 1] = log_count + n_surv;
                 }
             }
-            if (log_ok && tid == 0) {
-                frame_off[frame] = log_count;
-                frame_off[frame + 1] = log_count + n_surv;
-            }
-            if (arcs_seen) atomicAdd(&sh.cnt_arc_e, arcs_seen);
-            if (tid == 0) sh.cnt_tok += (unsigned)n_surv;
+            cnt_tok += tid == 0 ? (unsigned)n_surv : 0u;
             log_count += log_ok ? n_surv : 0;
+            if (final_pass) {
+                __syncthreads();
+                break;
+            }
+            // ---- pass C2: emitting arcs, one 32-arc window per warp iteration ----
+            cnt_arc_e += tid == 0 ? (unsigned)n_arcs : 0u;
+            {
+                const float cost_offset = -best;
+                const int nwin = (n_arcs + 31) >> 5;
+                int *own = sh.own[c.warp];
+                for (int w = c.warp; w < nwin; w += kDecWarps) {
+                    const int j = (w << 5) + c.lane;
+                    const int q0 = c.win_owner[w];
+                    const int my = q0 + c.lane;
+                    int pref = INT_MAX, a0 = 0, src = 0;
+                    float cost = 0.f;
+                    if (my < n_exp) {
+                        pref = c.sv_pref[my];
+                        a0 = c.sv_a0[my];
+                        cost = c.sv_cost[my];
+                        src = c.sv_src[my];
+                    }
+                    own[c.lane] = 0;
+                    __syncwarp();
+                    const int rel = pref - (w << 5);
+                    if (c.lane > 0 && rel >= 0 && rel < 32) own[rel] = c.lane;  // prefixes are strictly increasing
+                    __syncwarp();
+                    int o = own[c.lane];
+                    for (int d = 1; d < 32; d <<= 1) {
+                        int v = __shfl_up_sync(0xffffffffu, o, d);
+                        if (c.lane >= d) o = max(o, v);
+                    }
+                    const int opref = __shfl_sync(0xffffffffu, pref, o);
+                    const int oa0 = __shfl_sync(0xffffffffu, a0, o);
+                    const float ocost = __shfl_sync(0xffffffffu, cost, o);
+                    const int osrc = __shfl_sync(0xffffffffu, src, o);
+                    const bool valid = j < n_arcs;
+                    float tot = INFINITY;
+                    int arc = 0, next = 0;
+                    if (valid) {
+                        arc = oa0 + (j - opref);
+                        const int4 av = __ldg(a.g.arcs + arc);
+                        next = av.y;
+                        const float ac = cost_offset - a.acoustic_scale * s_ll[av.z];
+                        tot = ocost + ac + __int_as_float(av.x);
+                    }
+                    unsigned m = ford(tot);
+                    for (int d = 16; d; d >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
+                    if (c.lane == 0) atomicMin(&sh.min_ord, m);
+                    __syncwarp();
+                    const float cut = unord(*(volatile unsigned *)&sh.min_ord) + adaptive_beam;  // loose (>= final) cutoff
+                    if (valid && tot < cut) relax(c, next, pack(tot, arc), osrc);
+                    __syncwarp();
+                }
+            }
             __syncthreads();
-            if (final_pass) break;
             const float next_cutoff = unord(sh.min_ord) + adaptive_beam;
             const int n_emit = min(sh.n_cand, a.cand_cap);
             __syncthreads();
-            const int nc = closure(c, 0, n_emit, next_cutoff);
+            const int nc = closure(c, 0, n_emit, next_cutoff, &cnt_arc_eps);
             finalize_tokens(c, n_emit, nc, next_cutoff, n_state, n_cost, n_arc, n_prev);
             n_cur = min(sh.n_next, a.tok_cap);
-            if (tid == 0) sh.cnt_new += (unsigned)n_cur;
+            cnt_new += tid == 0 ? (unsigned)n_cur : 0u;
             parity ^= 1;
             frame++;
         }
@@ -507,7 +565,6 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_kernel(DecArgs a) {
                 int s = t_state[i];
                 float cst = log_cost[lo + i];
                 float fc = __ldg(a.g.final_cost + s);
-                // 64-bit key: ordered(total) , state ; the winner's log index is recovered by a second scan
                 if (fc != INFINITY) bw[0] = min(bw[0], ((unsigned long long)ford(cst + fc) << 32) | (unsigned)s);
                 bw[1] = min(bw[1], ((unsigned long long)ford(cst) << 32) | (unsigned)s);
             }
@@ -554,31 +611,38 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_kernel(DecArgs a) {
             cs->frame = frame;
             cs->log_count = log_count;
             cs->error = sh.error;
+            if (a.counters) {  // lane-level balance: sum and max of the cycles one lane took in this launch
+                const unsigned long long cyc = (unsigned long long)(clock64() - clk0);
+                atomicAdd(a.counters + 4, cyc);
+                atomicMax(a.counters + 5, cyc);
+                atomicMax(a.counters + 6, (unsigned long long)max_tok);
+                atomicAdd(a.counters + 7, 1ull);
+            }
         }
     }
-    __syncthreads();
-    if (tid == 0 && a.counters) {
-        atomicAdd(a.counters + 0, sh.cnt_tok);
-        atomicAdd(a.counters + 1, sh.cnt_arc_e);
-        atomicAdd(a.counters + 2, sh.cnt_arc_eps);
-        atomicAdd(a.counters + 3, sh.cnt_new);
+    if (a.counters) {
+        for (int o = 16; o; o >>= 1) cnt_arc_eps += __shfl_xor_sync(0xffffffffu, cnt_arc_eps, o);
+        if (tid == 0) {
+            atomicAdd(a.counters + 0, cnt_tok);
+            atomicAdd(a.counters + 1, cnt_arc_e);
+            atomicAdd(a.counters + 3, cnt_new);
+        }
+        if ((tid & 31) == 0 && cnt_arc_eps) atomicAdd(a.counters + 2, cnt_arc_eps);
     }
 }
 
 extern "C" int vbk_decode_max_grid(int device) {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    return sms * 2;
+    return sms * kDecBlocksPerSM;
 }
 
 extern "C" cudaError_t vbk_decode(const DecArgs *a, cudaStream_t s) {
     if (a->num_lanes <= 0) return cudaSuccess;
     int smem = (a->out_node.dim * 4 + 15) & ~15;
-    static int configured = 0;
-    if (smem > 40000 && configured < smem) {
+    if (smem > 40000) {
         cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     int grid = a->num_lanes < a->grid ? a->num_lanes : a->grid;
     decode_kernel<<<grid, kDecThreads, smem, s>>>(*a);

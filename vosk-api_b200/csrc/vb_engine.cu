@@ -290,6 +290,11 @@ void Engine::alloc_state() {
     d.cand_slot = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
     d.cand_src = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
     d.rank = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+    d.sv_pref = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+    d.sv_a0 = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+    d.sv_src = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+    d.sv_cost = dev_alloc<float>(allocs_, G * cfg_.tok_cap);
+    d.win_owner = dev_alloc<int>(allocs_, G * (cfg_.cand_cap / 32 + 2), 0);
     d.counters = dev_alloc<unsigned long long>(allocs_, 8, 0);
     VB_CUDA_CHECK(cudaMallocHost((void **)&h_cs_, (size_t)L * sizeof(DecChannelState)));
     VB_CUDA_CHECK(cudaMallocHost((void **)&h_path_, (size_t)L * path_cap_ * sizeof(int)));
@@ -338,7 +343,7 @@ void Engine::wait() {
 }
 
 StepStats Engine::stats() {
-    unsigned long long c[4] = {0, 0, 0, 0};
+    unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaSetDevice(cfg_.device);
     cudaMemcpy(c, dec_.counters, sizeof c, cudaMemcpyDeviceToHost);
     std::lock_guard<std::mutex> lk(stats_mu_);
@@ -347,6 +352,10 @@ StepStats Engine::stats() {
     s.arc_e = c[1];
     s.arc_eps = c[2];
     s.tok_new = c[3];
+    s.lane_cycles_sum = c[4];
+    s.lane_cycles_max = c[5];
+    s.max_tokens = c[6];
+    s.lane_launches = c[7];
     return s;
 }
 void Engine::reset_stats() {

@@ -134,6 +134,9 @@ struct DecArgs {
     int *cand_slot;
     int *cand_src;
     int *rank;               // [G][tok_cap]
+    int *sv_pref, *sv_a0, *sv_src;    // [G][tok_cap] expandable survivors: arc prefix, first arc, log index
+    float *sv_cost;
+    int *win_owner;          // [G][cand_cap/32+2] survivor owning the first arc of each 32-arc window
     unsigned long long *counters;     // [8] profiling counters (tokens, arcs, ...)
     int grid;
 };

@@ -3,6 +3,7 @@
 // as in the reference [REF src/vosk_api.cc:201,210,224,233]; nothing throws across the boundary.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 #include <string>
@@ -142,14 +143,15 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model) { return model ? (
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
     if (!model || !out) return 0;
     BatchModel *bm = (BatchModel *)model;
-    double v[13] = {0};
+    double v[17] = {0};
     for (size_t i = 0; i < bm->num_engines(); i++) {
         vb::StepStats s = bm->engine(i).stats();
         v[0] += s.audio_seconds; v[1] += s.steps; v[2] += s.lanes; v[3] += s.launches;
         v[4] += s.tok; v[5] += s.arc_e; v[6] += s.arc_eps; v[7] += s.tok_new;
         v[8] += s.t_feat; v[9] += s.t_ivec; v[10] += s.t_nnet; v[11] += s.t_dec; v[12] += s.gemm_launches;
+        v[13] += s.lane_cycles_sum; v[14] = std::max(v[14], (double)s.lane_cycles_max); v[15] = std::max(v[15], (double)s.max_tokens); v[16] += s.lane_launches;
     }
-    int k = n < 13 ? n : 13;
+    int k = n < 17 ? n : 17;
     memcpy(out, v, k * sizeof(double));
     return k;
 }

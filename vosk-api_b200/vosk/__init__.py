@@ -79,10 +79,11 @@ class BatchModel(object):
         return _c.vosk_batch_model_samples_per_chunk(self._handle)
 
     def Stats(self):
-        buf = _ffi.new("double[13]")
-        n = _c.vosk_batch_model_stats(self._handle, buf, 13)
+        buf = _ffi.new("double[17]")
+        n = _c.vosk_batch_model_stats(self._handle, buf, 17)
         keys = ["audio_seconds", "steps", "lanes", "launches", "tokens", "arcs_emitting", "arcs_epsilon", "tokens_new",
-                "ms_feat", "ms_ivector", "ms_nnet", "ms_search", "gemm_launches"]
+                "ms_feat", "ms_ivector", "ms_nnet", "ms_search", "gemm_launches",
+                "lane_cycles_sum", "lane_cycles_max", "max_tokens_per_frame", "lane_launches"]
         return {k: buf[i] for i, k in enumerate(keys[:n])}
 
     def ResetStats(self):
