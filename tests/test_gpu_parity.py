@@ -48,13 +48,14 @@ def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3):
     assert got["text"] == ref["text"]
 
 
+@pytest.mark.parametrize("tc", [1, 0])
 @pytest.mark.parametrize("fpc", [51, 9])
-def test_tiny_model_all_stages(model_root, oracle_lib, fpc):
+def test_tiny_model_all_stages(model_root, oracle_lib, fpc, tc):
     import vbmodel
     mdir = model_root("tiny")
     model = vbmodel.load_model_dir(mdir)
     waves = _waves(LENGTHS)
-    got, _ = helpers.run_engine(mdir, waves, options=f"frames-per-chunk={fpc},num-channels=8,max-batch-size=8,max-seconds=8,tensor-cores=0")
+    got, _ = helpers.run_engine(mdir, waves, options=f"frames-per-chunk={fpc},num-channels=8,max-batch-size=8,max-seconds=8,tensor-cores={tc}")
     for w, g in zip(waves, got):
         _check_stream(model, oracle_lib, w, g, fpc)
 
@@ -64,17 +65,18 @@ def test_tiny_more_streams_than_lanes_and_channels(model_root, oracle_lib):
     mdir = model_root("tiny")
     model = vbmodel.load_model_dir(mdir)
     waves = _waves([1.1, 0.7, 2.2, 1.6, 0.9, 1.3, 2.9], seed0=300)
-    got, _ = helpers.run_engine(mdir, waves, options="num-channels=3,max-batch-size=2,max-seconds=8,tensor-cores=0")
+    got, _ = helpers.run_engine(mdir, waves, options="num-channels=3,max-batch-size=2,max-seconds=8")
     for w, g in zip(waves, got):
         _check_stream(model, oracle_lib, w, g, 51)
 
 
-def test_small_model_all_stages(model_root, oracle_lib):
+@pytest.mark.parametrize("tc", [1, 0])
+def test_small_model_all_stages(model_root, oracle_lib, tc):
     import vbmodel
     mdir = model_root("small")
     model = vbmodel.load_model_dir(mdir)
     waves = _waves([2.5, 4.2, 0.9], seed0=500)
-    got, _ = helpers.run_engine(mdir, waves, options="num-channels=4,max-batch-size=4,max-seconds=10,tensor-cores=0")
+    got, _ = helpers.run_engine(mdir, waves, options=f"num-channels=4,max-batch-size=4,max-seconds=10,tensor-cores={tc}")
     for w, g in zip(waves, got):
         _check_stream(model, oracle_lib, w, g, 51)
 
@@ -88,6 +90,6 @@ def test_max_active_binds(model_root, oracle_lib):
     model["conf"]["min-active"] = "50"
     model["conf"]["beam"] = "20"
     waves = _waves([2.0, 3.1], seed0=700)
-    got, _ = helpers.run_engine(mdir, waves, options="num-channels=2,max-batch-size=2,max-seconds=10,max-active=300,min-active=50,beam=20,tensor-cores=0")
+    got, _ = helpers.run_engine(mdir, waves, options="num-channels=2,max-batch-size=2,max-seconds=10,max-active=300,min-active=50,beam=20")
     for w, g in zip(waves, got):
         _check_stream(model, oracle_lib, w, g, 51)

@@ -1,5 +1,359 @@
-// kernels_nnet_tc.cu — placeholder until the tcgen05 kernel lands (next commit): routes to the fp32 kernel.
+// kernels_nnet_tc.cu — K2 product path: TDNN-F layer GEMM on the 5th-generation tensor cores.
+//
+//   C[rows, N] = epilogue( A[rows, K] * W[N, K]^T ),  A gathered from the producer layer's time ring
+//   (the TDNN splice [x(t+o0), x(t+o1), ...] (+ i-vector) is materialised only in shared memory).
+//
+// Precision: the reference runs this stage as fp32 SGEMM (tensor cores off, [REF src/vosk_api.cc:184-185]) and
+// north_star asks for log-likelihoods within 1e-3, which plain TF32/BF16 inputs cannot hold through 30 chained
+// GEMMs.  Each fp32 operand is therefore split x = hi + lo with hi = x & 0xffffe000 (exactly a TF32 value) and
+// lo = x - hi (exact in fp32); the tile is accumulated as  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  in the fp32 TMEM
+// accumulators ("3xTF32"), dropping only the lo*lo term (~2^-22 relative).  Measured on B200: the tensor core
+// adds into the fp32 accumulator with truncation, so the error grows with the NUMBER of MMAs accumulated
+// (~1e-5 relative at K=1024 with all three terms in one accumulator).  The two cross terms are ~2^-11 of the
+// result, so they get their own TMEM accumulator (their truncation error is relative to their own size) and
+// the epilogue adds them in fp32 round-to-nearest; for long K the hi*hi k-steps are additionally dealt
+// round-robin over 2 or 4 accumulators, so at most K/32 truncating adds touch any one accumulator.
+// Tensor-pipe FLOPs are 3x the algorithmic ones; bench.py counts the algorithmic ones.
+//
+// Structure (one 128 x BN output tile per CTA, BN = min(N, 256)):
+//   warps 0-3  A producers: coalesced 16-byte gathers from the ring rows -> hi/lo split in registers -> 128B-
+//              swizzled K-major smem tiles (generic-proxy stores + fence.proxy.async + mbarrier arrive);
+//              afterwards the same warps are the epilogue (tcgen05.ld of their 32 TMEM lanes, bias / ReLU /
+//              batchnorm / bypass fused, 64-byte row-segment stores).
+//   warp 4     TMA: cp.async.bulk.tensor of the W_hi / W_lo [BN x 32] boxes (SWIZZLE_128B) per K-block.
+//   warp 5     allocates TMEM, issues tcgen05.mma.cta_group::1.kind::tf32 (3 per 8-wide k-step), commits the
+//              smem stage back to the producers and finally the accumulator to the epilogue.
+#include <cuda.h>
+
 #include "vb_kernels.h"
+
 namespace vb {
-extern "C" cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s) { return vbk_gemm_fp32(a, s); }
+
+namespace {
+constexpr int TM = 128;       // tile rows (UMMA_M)
+constexpr int TK = 32;        // fp32 elements per K-block = one 128-byte swizzle row
+constexpr int kTcThreads = 192;
+constexpr int kProducerThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1ll << 26)) __trap();  // a protocol bug must fail loudly, never hang the GPU
+    }
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row (1024 B) swizzle atoms
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffff) >> 4);        // start address
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+
+struct TcSmem {
+    uint64_t full[4], empty[4], accum;
+    uint32_t tmem_base;
+    int row_ch[TM], row_t[TM];
+};
+}  // namespace
+
+struct alignas(64) TensorMapBlob {
+    unsigned char b[128];
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const __grid_constant__ TensorMapBlob map_lo, int BN,
+               int stages, int tmem_cols, int terms, int n_main) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // dynamic smem: [stage][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], 1024-byte aligned
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ TcSmem ts;
+    const int total = a.rowoff[a.num_lanes];
+    const int row0 = blockIdx.x * TM;
+    if (row0 >= total) return;
+    const int n0 = blockIdx.y * BN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const OpDesc &op = a.op;
+    const uint32_t stage_bytes = 2u * TM * 128u + 2u * (uint32_t)BN * 128u;
+    const int nkb = (op.K + TK - 1) / TK;
+
+    if (tid < TM) {
+        int r = row0 + tid, ch = -1, t = 0;
+        if (r < total) {
+            int lo = 0, hi = a.num_lanes;
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (a.rowoff[mid] <= r) lo = mid; else hi = mid;
+            }
+            ch = a.lanes[lo].channel;
+            t = a.table[lo].t_begin + (r - a.rowoff[lo]) * a.out.step;
+        }
+        ts.row_ch[tid] = ch;
+        ts.row_t[tid] = t;
+    }
+    if (tid == 128) {
+        for (int s = 0; s < stages; s++) {
+            mbar_init(&ts.full[s], kProducerThreads + 1);
+            mbar_init(&ts.empty[s], 1);
+        }
+        mbar_init(&ts.accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ts.tmem_base)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = ts.tmem_base;
+
+    if (warp < 4) {
+        // =========================== A producers ===========================
+        const int in_dim = a.in.dim, spliced = op.n_off * in_dim;
+        const int c = tid & 7;          // 16-byte chunk within the 128-byte row
+        const int rsub = tid >> 3;      // 0..15: row within a group of 16
+        for (int kb = 0; kb < nkb; kb++) {
+            const int s = kb % stages;
+            const uint32_t par = (uint32_t)((kb / stages) & 1);
+            mbar_wait(&ts.empty[s], par ^ 1);
+            unsigned char *A_hi = smem + (size_t)s * stage_bytes, *A_lo = A_hi + TM * 128;
+            const int k = kb * TK + c * 4;
+            int seg = 0, col = 0;
+            const bool in_k = k < op.K, is_iv = k >= spliced;
+            if (in_k && !is_iv) {
+                seg = k / in_dim;
+                col = k - seg * in_dim;
+            }
+            const int off = in_k && !is_iv ? op.offs[seg] : 0;
+#pragma unroll
+            for (int it = 0; it < TM / 16; it++) {
+                const int r = it * 16 + rsub;
+                const int ch = ts.row_ch[r];
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ch >= 0 && in_k) {
+                    const float *src = is_iv ? a.ivec + (size_t)ch * a.ivec_dim + (k - spliced)
+                                             : a.in.buf + ((size_t)ch * a.in.ring + (((ts.row_t[r] + off - a.in.t_start) / a.in.step) & (a.in.ring - 1))) * in_dim + col;
+                    v = *reinterpret_cast<const float4 *>(src);
+                }
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                const uint32_t o = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+                *reinterpret_cast<float4 *>(A_hi + o) = h;
+                *reinterpret_cast<float4 *>(A_lo + o) = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA (async proxy)
+            mbar_arrive(&ts.full[s]);
+        }
+        // =========================== epilogue ===========================
+        mbar_wait(&ts.accum, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int r = warp * 32 + lane;
+        const int ch = ts.row_ch[r], t = ts.row_t[r];
+        float *orow = nullptr;
+        const float *brow = nullptr;
+        if (ch >= 0) {
+            orow = a.out.buf + ((size_t)ch * a.out.ring + (((t - a.out.t_start) / a.out.step) & (a.out.ring - 1))) * a.out.dim;
+            if (op.byp_node >= 0) brow = a.byp.buf + ((size_t)ch * a.byp.ring + (((t - a.byp.t_start) / a.byp.step) & (a.byp.ring - 1))) * a.byp.dim;
+        }
+        const uint32_t taddr_row = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int cb = 0; cb < BN; cb += 16) {
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc[j] = 0.f;
+            const int nsteps = (nkb * (TK / 8));
+            for (int q = 0; q <= n_main; q++) {
+                if (q < n_main && q >= nsteps) continue;  // accumulator never written (K shorter than n_main k-steps)
+                uint32_t v[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr_row + (uint32_t)(q * BN + cb)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; j++) acc[j] += __uint_as_float(v[j]);  // fp32 round-to-nearest sum of the partial accumulators
+            }
+            const int n = n0 + cb;
+            if (orow && n < op.N) {
+                float z[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    float x = acc[j];
+                    if (op.bias) x += __ldg(op.bias + n + j);
+                    if (op.relu) x = fmaxf(x, 0.f);
+                    if (op.has_bn) x = fmaf(x, __ldg(op.bn_scale + n + j), __ldg(op.bn_offset + n + j));
+                    if (brow) x = fmaf(op.bypass_scale, brow[n + j], x);
+                    z[j] = x;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(orow + n + j) = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else if (warp == 4) {
+        // =========================== TMA: weight boxes ===========================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % stages;
+                const uint32_t par = (uint32_t)((kb / stages) & 1);
+                mbar_wait(&ts.empty[s], par ^ 1);
+                unsigned char *B_hi = smem + (size_t)s * stage_bytes + 2 * TM * 128, *B_lo = B_hi + (size_t)BN * 128;
+                mbar_arrive_expect_tx(&ts.full[s], 2u * (uint32_t)BN * 128u);
+                const int k0 = kb * TK;
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(B_hi)),
+                             "l"(&map_hi), "r"(k0), "r"(n0), "r"(smem_u32(&ts.full[s]))
+                             : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(B_lo)),
+                             "l"(&map_lo), "r"(k0), "r"(n0), "r"(smem_u32(&ts.full[s]))
+                             : "memory");
+            }
+        }
+    } else {
+        // =========================== MMA issuer ===========================
+        // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+        for (int kb = 0; kb < nkb; kb++) {
+            const int s = kb % stages;
+            const uint32_t par = (uint32_t)((kb / stages) & 1);
+            mbar_wait(&ts.full[s], par);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t dAh = umma_desc(sa), dAl = umma_desc(sa + TM * 128);
+                const uint64_t dBh = umma_desc(sa + 2 * TM * 128), dBl = umma_desc(sa + 2 * TM * 128 + BN * 128);
+#pragma unroll
+                for (int k8 = 0; k8 < TK / 8; k8++) {
+                    const uint64_t adv = (uint64_t)((k8 * 32) >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle row
+                    const int step = kb * (TK / 8) + k8;
+                    const uint32_t d_main = tmem + (uint32_t)((step % n_main) * BN);   // hi*hi: round-robin over n_main accumulators
+                    const uint32_t d_cross = tmem + (uint32_t)(n_main * BN);            // cross terms: their own accumulator
+                    const uint32_t acc_main = step >= n_main ? 1u : 0u, acc_cross = step ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_main),
+                        "l"(dAh + adv), "l"(dBh + adv), "r"(idesc), "r"(acc_main)
+                        : "memory");
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_cross),
+                        "l"(dAl + adv), "l"(dBh + adv), "r"(idesc), "r"(acc_cross)
+                        : "memory");
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_cross),
+                        "l"(dAh + adv), "l"(dBl + adv), "r"(idesc), "r"(1u)
+                        : "memory");
+                    if (terms > 3) asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_cross),
+                        "l"(dAl + adv), "l"(dBl + adv), "r"(idesc), "r"(1u)
+                        : "memory");
+                }
+                // tcgen05.commit: arrives on the barrier when the MMAs issued so far have read their operands
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&ts.empty[s])) : "memory");
+                if (kb == nkb - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&ts.accum)) : "memory");
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// Number of hi*hi accumulators (fewer truncating adds per accumulator) and the N tile that fits
+// (n_main + 1) * BN fp32 columns into the 512 TMEM columns.
+static int main_accs(int K) { return K >= 128 ? 4 : K >= 64 ? 2 : 1; }
+static int tile_n(int N, int K) {
+    int limit = (512 / (main_accs(K) + 1)) & ~15;
+    return N < limit ? N : limit;
+}
+
+extern "C" cudaError_t vbk_make_weight_map(const float *w, int N, int K, void *out128) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return cudaErrorNotSupported;
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)tile_n(N, K)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    memcpy(out128, &m, 128);
+    return cudaSuccess;
+}
+
+extern "C" cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s) {
+    if (a->num_lanes <= 0 || a->max_rows <= 0) return cudaSuccess;
+    const OpDesc &op = a->op;
+    if (op.N % 16 || (op.K * 4) % 16 || !a->map_hi || !a->map_lo) return cudaErrorInvalidValue;
+    const int BN = tile_n(op.N, op.K), n_main = main_accs(op.K);
+    const uint32_t stage_bytes = 2u * TM * 128u + 2u * (uint32_t)BN * 128u;
+    int stages = (int)((200u * 1024u) / stage_bytes);
+    if (stages > 4) stages = 4;
+    const int nkb = (op.K + TK - 1) / TK;
+    if (stages > nkb) stages = nkb;
+    if (stages < 1) stages = 1;
+    int tmem_cols = 32;
+    while (tmem_cols < (n_main + 1) * BN) tmem_cols <<= 1;  // n_main hi*hi accumulators + one for the small cross terms
+    const int smem = (int)(stage_bytes * stages + 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((a->max_rows + TM - 1) / TM, (op.N + BN - 1) / BN);
+    TensorMapBlob mh, ml;
+    memcpy(mh.b, a->map_hi, 128);
+    memcpy(ml.b, a->map_lo, 128);
+    static int terms = getenv("VB_TC_TERMS") ? atoi(getenv("VB_TC_TERMS")) : 3;
+    gemm_tc_kernel<<<grid, kTcThreads, smem, s>>>(*a, mh, ml, BN, stages, tmem_cols, terms, n_main);
+    return cudaGetLastError();
+}
+
+}  // namespace vb

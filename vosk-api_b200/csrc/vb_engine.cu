@@ -193,6 +193,7 @@ void Engine::upload_model() {
     }
     d_nodes_ = dev_upload(allocs_, nodes_);
     ops_.resize(m.ops.size());
+    maps_.resize(m.ops.size());
     for (size_t o = 0; o < m.ops.size(); o++) {
         const AmOp &op = m.ops[o];
         OpDesc d{};
@@ -217,6 +218,10 @@ void Engine::upload_model() {
         d.bn_offset = op.bn_o ? dev_upload(allocs_, op.bn_o->f32(), (size_t)op.N) : nullptr;
         d.bypass_scale = m.bypass_scale;
         ops_[o] = d;
+        if (cfg_.use_tensor_cores) {
+            VB_CUDA_CHECK(vbk_make_weight_map(hi, op.N, op.K, maps_[o].hi));
+            VB_CUDA_CHECK(vbk_make_weight_map(lo, op.N, op.K, maps_[o].lo));
+        }
     }
     // ---- decoding graph: one 16-byte record per arc ----
     {
@@ -506,6 +511,8 @@ void Engine::step(std::vector<Lane> &lanes, const int16_t *d_resident, int resid
         ga.ivec = iv_state_.ivec;
         ga.ivec_dim = model_.ivec_dim;
         ga.max_rows = (int)(ga.out.step == 1 ? in_rows : in_rows / kSubsample + 2 * L);
+        ga.map_hi = maps_[o].hi;
+        ga.map_lo = maps_[o].lo;
         VB_CUDA_CHECK(cfg_.use_tensor_cores ? vbk_gemm_tc(&ga, stream_) : vbk_gemm_fp32(&ga, stream_));
         launches++;
         gemms++;

@@ -103,6 +103,8 @@ class Engine {
     IvecModel iv_model_{};
     std::vector<NodeDesc> nodes_;
     std::vector<OpDesc> ops_;
+    struct MapPair { alignas(64) unsigned char hi[128]; alignas(64) unsigned char lo[128]; };
+    std::vector<MapPair> maps_;
     NodeDesc *d_nodes_ = nullptr;
     GraphDev graph_{};
     std::vector<void *> allocs_;

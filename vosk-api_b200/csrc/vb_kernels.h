@@ -89,6 +89,8 @@ struct GemmArgs {
     const float *ivec;       // [C][ivec_dim]
     int ivec_dim;
     int max_rows;            // upper bound of total rows (grid sizing)
+    const void *map_hi;      // HOST pointers to the 128-byte TMA descriptors of W_hi / W_lo (tensor-core path)
+    const void *map_lo;
 };
 
 // ---------------- K3: beam search ----------------
@@ -148,6 +150,8 @@ cudaError_t vbk_ivector(const IvecArgs *a, cudaStream_t s);
 cudaError_t vbk_nnet_plan(const NnetPlanArgs *a, cudaStream_t s);
 cudaError_t vbk_gemm_fp32(const GemmArgs *a, cudaStream_t s);
 cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s);
+// encodes the TMA descriptor ([N][K] fp32, box 32 x min(N,256), SWIZZLE_128B) of a weight matrix into out128
+cudaError_t vbk_make_weight_map(const float *w, int N, int K, void *out128);
 cudaError_t vbk_decode(const DecArgs *a, cudaStream_t s);
 int vbk_decode_max_grid(int device);
 // copies rows [t_begin, t_begin+n) of a node ring for one channel into dst (debug capture / tests)
