@@ -132,41 +132,60 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
 
     if (warp < 4) {
         // =========================== A producers ===========================
+        // Thread (c, rsub) owns 16-byte chunk c of rows rsub, rsub+16, ... of the tile.  Row slots are resolved once;
+        // per K-block all 8 gathers are issued back to back into registers (8 independent L2 requests in flight per
+        // thread) and only then split and stored, so the loop is bandwidth- rather than latency-paced.
         const int in_dim = a.in.dim, spliced = op.n_off * in_dim;
         const int c = tid & 7;          // 16-byte chunk within the 128-byte row
         const int rsub = tid >> 3;      // 0..15: row within a group of 16
+        constexpr int RPT = TM / 16;    // rows per thread
+        const float *row_base[RPT];     // ring base of the row's channel (nullptr = padding row)
+        const float *iv_base[RPT];
+        int row_slot[RPT];              // (t - t_start) / step of the row in the input ring
+#pragma unroll
+        for (int it = 0; it < RPT; it++) {
+            const int r = it * 16 + rsub;
+            const int ch = ts.row_ch[r];
+            row_base[it] = ch >= 0 ? a.in.buf + (size_t)ch * a.in.ring * in_dim : nullptr;
+            iv_base[it] = ch >= 0 ? a.ivec + (size_t)ch * a.ivec_dim : nullptr;
+            row_slot[it] = (ts.row_t[r] - a.in.t_start) / a.in.step;
+        }
+        const int ring_mask = a.in.ring - 1;
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % stages;
             const uint32_t par = (uint32_t)((kb / stages) & 1);
-            mbar_wait(&ts.empty[s], par ^ 1);
-            unsigned char *A_hi = smem + (size_t)s * stage_bytes, *A_lo = A_hi + TM * 128;
             const int k = kb * TK + c * 4;
-            int seg = 0, col = 0;
             const bool in_k = k < op.K, is_iv = k >= spliced;
+            int seg = 0, col = 0;
             if (in_k && !is_iv) {
                 seg = k / in_dim;
                 col = k - seg * in_dim;
             }
-            const int off = in_k && !is_iv ? op.offs[seg] : 0;
+            const int off_rows = in_k && !is_iv ? op.offs[seg] / a.in.step : 0;  // offsets are multiples of the input step
+            float4 v[RPT];
 #pragma unroll
-            for (int it = 0; it < TM / 16; it++) {
-                const int r = it * 16 + rsub;
-                const int ch = ts.row_ch[r];
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ch >= 0 && in_k) {
-                    const float *src = is_iv ? a.ivec + (size_t)ch * a.ivec_dim + (k - spliced)
-                                             : a.in.buf + ((size_t)ch * a.in.ring + (((ts.row_t[r] + off - a.in.t_start) / a.in.step) & (a.in.ring - 1))) * in_dim + col;
-                    v = *reinterpret_cast<const float4 *>(src);
+            for (int it = 0; it < RPT; it++) {
+                v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row_base[it] && in_k) {
+                    const float *src = is_iv ? iv_base[it] + (k - spliced)
+                                             : row_base[it] + (size_t)((row_slot[it] + off_rows) & ring_mask) * in_dim + col;
+                    v[it] = __ldg(reinterpret_cast<const float4 *>(src));
                 }
+            }
+            mbar_wait(&ts.empty[s], par ^ 1);
+            const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + TM * 128;
+#pragma unroll
+            for (int it = 0; it < RPT; it++) {
+                const int r = it * 16 + rsub;
                 float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-                h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-                h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                h.x = __uint_as_float(__float_as_uint(v[it].x) & 0xffffe000u);
+                h.y = __uint_as_float(__float_as_uint(v[it].y) & 0xffffe000u);
+                h.z = __uint_as_float(__float_as_uint(v[it].z) & 0xffffe000u);
+                h.w = __uint_as_float(__float_as_uint(v[it].w) & 0xffffe000u);
+                l.x = v[it].x - h.x; l.y = v[it].y - h.y; l.z = v[it].z - h.z; l.w = v[it].w - h.w;
                 const uint32_t o = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-                *reinterpret_cast<float4 *>(A_hi + o) = h;
-                *reinterpret_cast<float4 *>(A_lo + o) = l;
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + o), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA (async proxy)
             mbar_arrive(&ts.full[s]);

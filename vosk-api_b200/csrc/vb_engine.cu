@@ -38,6 +38,8 @@ Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg)
     if (cfg_.frames_per_chunk < 3) throw std::runtime_error("frames-per-chunk must be >= 3");
     if (cfg_.max_lanes > 1024) cfg_.max_lanes = 1024;
     if (cfg_.max_lanes > cfg_.num_channels) cfg_.max_lanes = cfg_.num_channels;
+    if (cfg_.pipeline_slots < 1) cfg_.pipeline_slots = 1;
+    if (cfg_.pipeline_slots > 8) cfg_.pipeline_slots = 8;
     if (cfg_.hash_size & (cfg_.hash_size - 1)) throw std::runtime_error("hash-size must be a power of two");
     if (model.graph.has_negative_eps)
         throw std::runtime_error("HCLG has negative-weight epsilon arcs: not supported by the token log (DESIGN.md)");
@@ -47,7 +49,6 @@ Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg)
         throw std::runtime_error(std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range"));
     VB_CUDA_CHECK(cudaSetDevice(cfg_.device));
     VB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    for (auto &ev : ev_) VB_CUDA_CHECK(cudaEventCreate(&ev));
     upload_model();
     alloc_state();
     thread_ = std::thread([this] { worker(); });
@@ -63,12 +64,17 @@ Engine::~Engine() {
     cudaSetDevice(cfg_.device);
     cudaStreamSynchronize(stream_);
     for (void *p : allocs_) cudaFree(p);
-    if (h_staging_) cudaFreeHost(h_staging_);
-    if (h_lanes_) cudaFreeHost(h_lanes_);
-    if (h_cs_) cudaFreeHost(h_cs_);
-    if (h_path_) cudaFreeHost(h_path_);
+    for (Slot &sl : slots_) {
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        if (sl.h_staging) cudaFreeHost(sl.h_staging);
+        if (sl.h_lanes) cudaFreeHost(sl.h_lanes);
+        if (sl.h_cs) cudaFreeHost(sl.h_cs);
+        if (sl.h_path) cudaFreeHost(sl.h_path);
+        for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     if (h_capture_) cudaFreeHost(h_capture_);
-    for (auto &ev : ev_) cudaEventDestroy(ev);
     cudaStreamDestroy(stream_);
 }
 
@@ -239,9 +245,11 @@ void Engine::upload_model() {
 }
 
 void Engine::alloc_state() {
-    const int C = cfg_.num_channels, L = cfg_.max_lanes, F = model_.feat_dim, D = model_.ivec_dim;
+    const int C = cfg_.num_channels, F = model_.feat_dim, D = model_.ivec_dim;
     const int spc = samples_per_chunk();
     const int nn = (int)nodes_.size();
+    slot_lanes_ = std::max(1, (cfg_.max_lanes + cfg_.pipeline_slots - 1) / cfg_.pipeline_slots);
+    const int L = slot_lanes_;
     iv_state_.cmvn_sum = dev_alloc<double>(allocs_, (size_t)C * F, 0);
     iv_state_.norm_ring = dev_alloc<float>(allocs_, (size_t)C * kNormRing * F, 0);
     iv_state_.lin = dev_alloc<double>(allocs_, (size_t)C * D, 0);
@@ -249,14 +257,8 @@ void Engine::alloc_state() {
     iv_state_.num_frames = dev_alloc<double>(allocs_, (size_t)C, 0);
     iv_state_.ivec = dev_alloc<float>(allocs_, (size_t)C * D, 0);
     d_carry_ = dev_alloc<int16_t>(allocs_, (size_t)C * kCarryMax, 0);
-    d_staging_ = dev_alloc<int16_t>(allocs_, (size_t)L * spc, 0);
-    VB_CUDA_CHECK(cudaMallocHost((void **)&h_staging_, (size_t)L * spc * sizeof(int16_t)));
-    d_lanes_ = dev_alloc<LaneDesc>(allocs_, (size_t)L, 0);
-    VB_CUDA_CHECK(cudaMallocHost((void **)&h_lanes_, (size_t)L * sizeof(LaneDesc)));
     d_node_end_ = dev_alloc<int>(allocs_, (size_t)C * kMaxNodes, 0);
-    d_table_ = dev_alloc<NodeLane>(allocs_, (size_t)nn * L, 0);
-    d_rowoff_ = dev_alloc<int>(allocs_, (size_t)nn * (L + 1), 0);
-    // decoder
+    // decoder: per-channel state shared by all slots
     max_frames_ = cfg_.max_seconds * 100 / kSubsample + 2;
     log_cap_ = max_frames_ * std::min(cfg_.max_active + 1, cfg_.log_tokens_per_frame) + cfg_.tok_cap;
     path_cap_ = 4 * max_frames_ + 64;
@@ -274,7 +276,6 @@ void Engine::alloc_state() {
     d.max_frames = max_frames_;
     d.path_cap = path_cap_;
     d.out_node = nodes_.back();
-    d.out_table = d_table_ + (size_t)(nn - 1) * L;
     d.cs = dev_alloc<DecChannelState>(allocs_, (size_t)C, 0);
     d.tok_state = dev_alloc<int>(allocs_, (size_t)C * 2 * cfg_.tok_cap);
     d.tok_cost = dev_alloc<float>(allocs_, (size_t)C * 2 * cfg_.tok_cap);
@@ -286,23 +287,39 @@ void Engine::alloc_state() {
     d.log_state = cfg_.debug_capture ? dev_alloc<int>(allocs_, (size_t)C * log_cap_) : nullptr;
     d.log_frame_off = dev_alloc<int>(allocs_, (size_t)C * (max_frames_ + 2), 0);
     d.path = dev_alloc<int>(allocs_, (size_t)C * path_cap_, 0);
-    d.grid = std::min(vbk_decode_max_grid(cfg_.device), L);
-    const size_t G = (size_t)d.grid;
-    d.hash_key = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0xff);
-    d.hash_val = dev_alloc<unsigned long long>(allocs_, G * cfg_.hash_size, 0xff);
-    d.hash_tok = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0);
-    d.cand_packed = dev_alloc<unsigned long long>(allocs_, G * cfg_.cand_cap);
-    d.cand_slot = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
-    d.cand_src = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
-    d.rank = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
-    d.sv_pref = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
-    d.sv_a0 = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
-    d.sv_src = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
-    d.sv_cost = dev_alloc<float>(allocs_, G * cfg_.tok_cap);
-    d.win_owner = dev_alloc<int>(allocs_, G * (cfg_.cand_cap / 32 + 2), 0);
     d.counters = dev_alloc<unsigned long long>(allocs_, 8, 0);
-    VB_CUDA_CHECK(cudaMallocHost((void **)&h_cs_, (size_t)L * sizeof(DecChannelState)));
-    VB_CUDA_CHECK(cudaMallocHost((void **)&h_path_, (size_t)L * path_cap_ * sizeof(int)));
+    d.grid = std::min(vbk_decode_max_grid(cfg_.device), L);
+    // pipeline slots: stream, staging, per-step tables, search scratch
+    slots_.resize(cfg_.pipeline_slots);
+    for (Slot &sl : slots_) {
+        VB_CUDA_CHECK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        for (auto &ev : sl.ev) VB_CUDA_CHECK(cudaEventCreate(&ev));
+        VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        sl.d_staging = dev_alloc<int16_t>(allocs_, (size_t)L * spc, 0);
+        VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_staging, (size_t)L * spc * sizeof(int16_t)));
+        sl.d_lanes = dev_alloc<LaneDesc>(allocs_, (size_t)L, 0);
+        VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lanes, (size_t)L * sizeof(LaneDesc)));
+        sl.d_table = dev_alloc<NodeLane>(allocs_, (size_t)nn * L, 0);
+        sl.d_rowoff = dev_alloc<int>(allocs_, (size_t)nn * (L + 1), 0);
+        VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_cs, (size_t)L * sizeof(DecChannelState)));
+        VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_path, (size_t)L * path_cap_ * sizeof(int)));
+        DecArgs &sd = sl.dec;
+        sd = dec_;
+        sd.out_table = sl.d_table + (size_t)(nn - 1) * L;
+        const size_t G = (size_t)sd.grid;
+        sd.hash_key = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0xff);
+        sd.hash_val = dev_alloc<unsigned long long>(allocs_, G * cfg_.hash_size, 0xff);
+        sd.hash_tok = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0);
+        sd.cand_packed = dev_alloc<unsigned long long>(allocs_, G * cfg_.cand_cap);
+        sd.cand_slot = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
+        sd.cand_src = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
+        sd.rank = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+        sd.sv_pref = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+        sd.sv_a0 = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+        sd.sv_src = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+        sd.sv_cost = dev_alloc<float>(allocs_, G * cfg_.tok_cap);
+        sd.win_owner = dev_alloc<int>(allocs_, G * (cfg_.cand_cap / 32 + 2), 0);
+    }
     if (cfg_.debug_capture) {
         capture_floats_ = (size_t)(max_in_rows_ + 8) * std::max(model_.num_pdfs, F);
         d_capture_ = dev_alloc<float>(allocs_, capture_floats_);
@@ -312,8 +329,8 @@ void Engine::alloc_state() {
     for (int i = 0; i < C; i++) free_channels_[i] = C - 1 - i;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    log_msg(0, "engine on device %d: %d channels, %d lanes/step, chunk %d frames, HBM used %.1f GB of %.1f GB", cfg_.device, C, L,
-            cfg_.frames_per_chunk, (total_b - free_b) / 1e9, total_b / 1e9);
+    log_msg(0, "engine on device %d: %d channels, %d slots x %d lanes, chunk %d frames, HBM used %.1f GB of %.1f GB", cfg_.device, C,
+            cfg_.pipeline_slots, L, cfg_.frames_per_chunk, (total_b - free_b) / 1e9, total_b / 1e9);
 }
 
 std::shared_ptr<Stream> Engine::open_stream() {
@@ -370,17 +387,56 @@ void Engine::reset_stats() {
     stats_ = StepStats{};
 }
 
+// The batcher: keeps up to pipeline_slots lane groups in flight.  A stream has at most one chunk in flight
+// (it re-enters the ready queue when its step completes), so per-stream order is preserved across slots.
 void Engine::worker() {
     cudaSetDevice(cfg_.device);
-    std::vector<Lane> lanes;
+    int cur = 0, n_busy = 0;
     for (;;) {
-        lanes.clear();
         {
             std::unique_lock<std::mutex> lk(mu_);
-            cv_work_.wait(lk, [this] { return stop_ || !ready_.empty(); });
-            if (stop_) return;
+            cv_work_.wait(lk, [&] { return stop_ || !ready_.empty() || n_busy > 0; });
+            if (stop_ && n_busy == 0) return;
+        }
+        Slot &sl = slots_[cur];
+        if (sl.busy) {
+            try {
+                complete_step(sl);
+            } catch (const std::exception &ex) {
+                log_msg(-1, "engine step failed: %s", ex.what());
+                for (auto &ln : sl.lanes)
+                    if (ln.chunk.last && ln.s->on_result) {
+                        BestPath bp;
+                        bp.error = 100;
+                        ln.s->on_result(bp);
+                    }
+            }
+            sl.busy = false;
+            n_busy--;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                for (auto &ln : sl.lanes) {
+                    ln.s->pending_chunks.fetch_sub(1);
+                    if (ln.chunk.last) {
+                        free_channels_.push_back(ln.s->channel);
+                        ln.s->channel = -1;
+                        ln.s->queued = false;
+                    } else if (!ln.s->pending.empty()) {
+                        ready_.push_back(ln.s);
+                    } else {
+                        ln.s->queued = false;
+                    }
+                }
+                outstanding_ -= (long long)sl.lanes.size();
+            }
+            sl.lanes.clear();
+            cv_done_.notify_all();
+        }
+        bool starved = false;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
             std::deque<std::shared_ptr<Stream>> deferred;
-            while (!ready_.empty() && (int)lanes.size() < cfg_.max_lanes) {
+            while (!ready_.empty() && (int)sl.lanes.size() < slot_lanes_) {
                 std::shared_ptr<Stream> s = ready_.front();
                 ready_.pop_front();
                 if (s->channel < 0) {
@@ -395,57 +451,41 @@ void Engine::worker() {
                 ln.s = s;
                 ln.chunk = std::move(s->pending.front());
                 s->pending.pop_front();
-                lanes.push_back(std::move(ln));
+                sl.lanes.push_back(std::move(ln));
             }
+            starved = sl.lanes.empty() && !deferred.empty() && n_busy == 0;
             for (auto it = deferred.rbegin(); it != deferred.rend(); ++it) ready_.push_front(*it);
-            if (lanes.empty()) {
-                // only channel-less streams are ready; wait for a channel to be released
-                cv_work_.wait_for(lk, std::chrono::milliseconds(1));
-                continue;
+            if (starved) cv_work_.wait_for(lk, std::chrono::milliseconds(1));
+        }
+        if (!sl.lanes.empty()) {
+            try {
+                launch_step(sl, nullptr, 0);
+                sl.busy = true;
+                n_busy++;
+            } catch (const std::exception &ex) {
+                log_msg(-1, "engine launch failed: %s", ex.what());
+                sl.busy = true;  // let the completion path release the lanes
+                n_busy++;
             }
         }
-        try {
-            step(lanes, nullptr, 0);
-        } catch (const std::exception &ex) {
-            log_msg(-1, "engine step failed: %s", ex.what());
-            for (auto &ln : lanes)
-                if (ln.chunk.last && ln.s->on_result) {
-                    BestPath bp;
-                    bp.error = 100;
-                    ln.s->on_result(bp);
-                }
-        }
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            for (auto &ln : lanes) {
-                ln.s->pending_chunks.fetch_sub(1);
-                if (ln.chunk.last) {
-                    free_channels_.push_back(ln.s->channel);
-                    ln.s->channel = -1;
-                    ln.s->queued = false;
-                } else if (!ln.s->pending.empty()) {
-                    ready_.push_back(ln.s);
-                } else {
-                    ln.s->queued = false;
-                }
-            }
-            outstanding_ -= (long long)lanes.size();
-        }
-        cv_done_.notify_all();
+        cur = (cur + 1) % (int)slots_.size();
     }
 }
 
-void Engine::step(std::vector<Lane> &lanes, const int16_t *d_resident, int resident_stride) {
+void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_stride) {
+    std::vector<Lane> &lanes = sl.lanes;
     const int L = (int)lanes.size();
     const int ctx = model_.context, spc = samples_per_chunk();
     const int nn = (int)nodes_.size();
-    double audio = 0;
+    const int SL = slot_lanes_;
+    cudaStream_t st = sl.stream;
+    sl.audio = 0;
     long long in_rows = 0;
     for (int i = 0; i < L; i++) {
         Stream &s = *lanes[i].s;
         const Stream::Chunk &ck = lanes[i].chunk;
-        LaneDesc &d = h_lanes_[i];
-        const int n = d_resident ? (int)ck.samples.size() : (int)ck.samples.size();
+        LaneDesc &d = sl.h_lanes[i];
+        const int n = (int)ck.samples.size();
         d.channel = s.channel;
         d.n_samples = n;
         d.carry = s.carry;
@@ -459,12 +499,12 @@ void Engine::step(std::vector<Lane> &lanes, const int16_t *d_resident, int resid
         d.in_end_before = d.first ? -ctx : s.in_end;
         d.in_end_after = d.frames_after > 0 ? (ck.last ? d.frames_after + ctx : d.frames_after) : d.in_end_before;
         d.dec_frames_before = s.dec_frames;
-        d.src_row = i;
-        d.src_off = 0;
-        if (!d_resident && n) memcpy(h_staging_ + (size_t)i * spc, ck.samples.data(), (size_t)n * sizeof(int16_t));
+        d.src_row = d_resident ? (int)s.id : i;
+        d.src_off = d_resident ? (int)s.samples : 0;
+        if (!d_resident && n) memcpy(sl.h_staging + (size_t)i * spc, ck.samples.data(), (size_t)n * sizeof(int16_t));
         in_rows += d.in_end_after - d.in_end_before + 2;
-        audio += n / 16000.0;
-        // advance the host mirror of the stream state
+        sl.audio += n / 16000.0;
+        // advance the host mirror of the stream state (a stream has at most one chunk in flight)
         s.started = true;
         s.samples = total;
         s.frames = d.frames_after;
@@ -472,31 +512,27 @@ void Engine::step(std::vector<Lane> &lanes, const int16_t *d_resident, int resid
         s.in_end = d.in_end_after;
         s.carry = d.frames_after > 0 ? (int)(total - (int64_t)kFrameShift * d.frames_after) : (int)total;
         s.dec_frames = d.in_end_after > ctx ? (d.in_end_after - ctx + kSubsample - 1) / kSubsample : 0;
+        lanes[i].dec_frames_after = s.dec_frames;
     }
-    if (d_resident) {
-        // resident mode: chunk.samples only carries the length; the source offsets were put in place by the caller
-        for (int i = 0; i < L; i++) {
-            h_lanes_[i].src_row = (int)lanes[i].s->id;
-            h_lanes_[i].src_off = (int)(lanes[i].s->samples - h_lanes_[i].n_samples);
-        }
-    }
-    long long launches = 0, gemms = 0;
-    if (timing_) VB_CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
-    VB_CUDA_CHECK(cudaMemcpyAsync(d_lanes_, h_lanes_, (size_t)L * sizeof(LaneDesc), cudaMemcpyHostToDevice, stream_));
+    sl.launches = 0;
+    sl.gemms = 0;
+    sl.timed = timing_;
+    if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[0], st));
+    VB_CUDA_CHECK(cudaMemcpyAsync(sl.d_lanes, sl.h_lanes, (size_t)L * sizeof(LaneDesc), cudaMemcpyHostToDevice, st));
     if (!d_resident)
-        VB_CUDA_CHECK(cudaMemcpyAsync(d_staging_, h_staging_, (size_t)L * spc * sizeof(int16_t), cudaMemcpyHostToDevice, stream_));
-    FeatArgs fa{d_lanes_, L, d_resident ? d_resident : d_staging_, d_resident ? (long long)resident_stride : (long long)spc, spc,
+        VB_CUDA_CHECK(cudaMemcpyAsync(sl.d_staging, sl.h_staging, (size_t)L * spc * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    FeatArgs fa{sl.d_lanes, L, d_resident ? d_resident : sl.d_staging, d_resident ? (long long)resident_stride : (long long)spc, spc,
                 d_carry_, nodes_[0], ctx, feat_tab_};
-    VB_CUDA_CHECK(vbk_mfcc(&fa, stream_));
-    launches++;
-    if (timing_) VB_CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
-    IvecArgs ia{d_lanes_, L, nodes_[0], ctx, iv_model_, iv_state_};
-    VB_CUDA_CHECK(vbk_ivector(&ia, stream_));
-    launches++;
-    if (timing_) VB_CUDA_CHECK(cudaEventRecord(ev_[2], stream_));
-    NnetPlanArgs pa{d_lanes_, L, nn, d_nodes_, d_node_end_, d_table_, d_rowoff_, cfg_.max_lanes};
-    VB_CUDA_CHECK(vbk_nnet_plan(&pa, stream_));
-    launches++;
+    VB_CUDA_CHECK(vbk_mfcc(&fa, st));
+    sl.launches++;
+    if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[1], st));
+    IvecArgs ia{sl.d_lanes, L, nodes_[0], ctx, iv_model_, iv_state_};
+    VB_CUDA_CHECK(vbk_ivector(&ia, st));
+    sl.launches++;
+    if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[2], st));
+    NnetPlanArgs pa{sl.d_lanes, L, nn, d_nodes_, d_node_end_, sl.d_table, sl.d_rowoff, SL};
+    VB_CUDA_CHECK(vbk_nnet_plan(&pa, st));
+    sl.launches++;
     for (size_t o = 0; o < ops_.size(); o++) {
         const OpDesc &op = ops_[o];
         GemmArgs ga{};
@@ -504,51 +540,58 @@ void Engine::step(std::vector<Lane> &lanes, const int16_t *d_resident, int resid
         ga.in = nodes_[op.in_node];
         ga.out = nodes_[op.out_node];
         ga.byp = nodes_[op.byp_node >= 0 ? op.byp_node : 0];
-        ga.lanes = d_lanes_;
+        ga.lanes = sl.d_lanes;
         ga.num_lanes = L;
-        ga.table = d_table_ + (size_t)op.out_node * cfg_.max_lanes;
-        ga.rowoff = d_rowoff_ + (size_t)op.out_node * (cfg_.max_lanes + 1);
+        ga.table = sl.d_table + (size_t)op.out_node * SL;
+        ga.rowoff = sl.d_rowoff + (size_t)op.out_node * (SL + 1);
         ga.ivec = iv_state_.ivec;
         ga.ivec_dim = model_.ivec_dim;
         ga.max_rows = (int)(ga.out.step == 1 ? in_rows : in_rows / kSubsample + 2 * L);
         ga.map_hi = maps_[o].hi;
         ga.map_lo = maps_[o].lo;
-        VB_CUDA_CHECK(cfg_.use_tensor_cores ? vbk_gemm_tc(&ga, stream_) : vbk_gemm_fp32(&ga, stream_));
-        launches++;
-        gemms++;
+        VB_CUDA_CHECK(cfg_.use_tensor_cores ? vbk_gemm_tc(&ga, st) : vbk_gemm_fp32(&ga, st));
+        sl.launches++;
+        sl.gemms++;
     }
-    if (timing_) VB_CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
-    dec_.lanes = d_lanes_;
-    dec_.num_lanes = L;
-    VB_CUDA_CHECK(vbk_decode(&dec_, stream_));
-    launches++;
-    if (timing_) VB_CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
+    if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[3], st));
+    sl.dec.lanes = sl.d_lanes;
+    sl.dec.num_lanes = L;
+    VB_CUDA_CHECK(vbk_decode(&sl.dec, st));
+    sl.launches++;
+    if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[4], st));
     // results of finished lanes
     int n_last = 0;
     for (int i = 0; i < L; i++)
         if (lanes[i].chunk.last) {
             const int ch = lanes[i].s->channel;
-            VB_CUDA_CHECK(cudaMemcpyAsync(h_cs_ + n_last, dec_.cs + ch, sizeof(DecChannelState), cudaMemcpyDeviceToHost, stream_));
-            VB_CUDA_CHECK(cudaMemcpyAsync(h_path_ + (size_t)n_last * path_cap_, dec_.path + (size_t)ch * path_cap_,
-                                          (size_t)path_cap_ * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+            VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_cs + n_last, dec_.cs + ch, sizeof(DecChannelState), cudaMemcpyDeviceToHost, st));
+            VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_path + (size_t)n_last * path_cap_, dec_.path + (size_t)ch * path_cap_,
+                                          (size_t)path_cap_ * sizeof(int), cudaMemcpyDeviceToHost, st));
             n_last++;
         }
-    VB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    VB_CUDA_CHECK(cudaEventRecord(sl.done, st));
+}
+
+void Engine::complete_step(Slot &sl) {
+    std::vector<Lane> &lanes = sl.lanes;
+    const int L = (int)lanes.size();
+    cudaStream_t st = sl.stream;
+    VB_CUDA_CHECK(cudaEventSynchronize(sl.done));
     // debug capture (tests): copy this step's new rows of the tapped stages
     for (int i = 0; i < L && cfg_.debug_capture; i++) {
         Stream &s = *lanes[i].s;
         if (!s.capture) continue;
-        const LaneDesc &d = h_lanes_[i];
+        const LaneDesc &d = sl.h_lanes[i];
         Capture &cp = *s.capture;
         auto grab = [&](const NodeDesc &node, int t0, int rows, std::vector<float> &dst) {
             if (rows <= 0) return;
-            VB_CUDA_CHECK(vbk_copy_rows(node, d.channel, t0, rows, d_capture_, stream_));
-            VB_CUDA_CHECK(cudaMemcpyAsync(h_capture_, d_capture_, (size_t)rows * node.dim * sizeof(float), cudaMemcpyDeviceToHost, stream_));
-            VB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+            VB_CUDA_CHECK(vbk_copy_rows(node, d.channel, t0, rows, d_capture_, st));
+            VB_CUDA_CHECK(cudaMemcpyAsync(h_capture_, d_capture_, (size_t)rows * node.dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+            VB_CUDA_CHECK(cudaStreamSynchronize(st));
             dst.insert(dst.end(), h_capture_, h_capture_ + (size_t)rows * node.dim);
         };
         grab(nodes_[0], d.frames_before, d.frames_after - d.frames_before, cp.mfcc);
-        grab(nodes_.back(), d.dec_frames_before * kSubsample, s.dec_frames - d.dec_frames_before, cp.loglikes);
+        grab(nodes_.back(), d.dec_frames_before * kSubsample, lanes[i].dec_frames_after - d.dec_frames_before, cp.loglikes);
         std::vector<float> iv(model_.ivec_dim);
         VB_CUDA_CHECK(cudaMemcpy(iv.data(), iv_state_.ivec + (size_t)d.channel * model_.ivec_dim, iv.size() * sizeof(float), cudaMemcpyDeviceToHost));
         cp.ivectors.insert(cp.ivectors.end(), iv.begin(), iv.end());
@@ -572,32 +615,30 @@ void Engine::step(std::vector<Lane> &lanes, const int16_t *d_resident, int resid
             }
         }
     }
-    if (timing_) {
-        float ms[4];
-        for (int k = 0; k < 4; k++) cudaEventElapsedTime(&ms[k], ev_[k], ev_[k + 1]);
+    {
+        float ms[4] = {0, 0, 0, 0};
+        if (sl.timed)
+            for (int k = 0; k < 4; k++) cudaEventElapsedTime(&ms[k], sl.ev[k], sl.ev[k + 1]);
         std::lock_guard<std::mutex> lk(stats_mu_);
         stats_.t_feat += ms[0];
         stats_.t_ivec += ms[1];
         stats_.t_nnet += ms[2];
         stats_.t_dec += ms[3];
         stats_.t_total += ms[0] + ms[1] + ms[2] + ms[3];
-    }
-    {
-        std::lock_guard<std::mutex> lk(stats_mu_);
-        stats_.audio_seconds += audio;
+        stats_.audio_seconds += sl.audio;
         stats_.steps++;
         stats_.lanes += L;
-        stats_.launches += launches;
-        stats_.gemm_launches += gemms;
+        stats_.launches += sl.launches;
+        stats_.gemm_launches += sl.gemms;
         stats_.dec_launches++;
     }
-    n_last = 0;
+    int n_last = 0;
     for (int i = 0; i < L; i++)
-        if (lanes[i].chunk.last) finish_lane(lanes[i], n_last++);
+        if (lanes[i].chunk.last) finish_lane(sl, lanes[i], n_last++);
 }
 
-void Engine::finish_lane(Lane &ln, int k) {
-    const DecChannelState &cs = h_cs_[k];
+void Engine::finish_lane(Slot &sl, Lane &ln, int k) {
+    const DecChannelState &cs = sl.h_cs[k];
     BestPath bp;
     bp.cost = cs.best_cost;
     bp.reached_final = cs.reached_final != 0;
@@ -605,17 +646,19 @@ void Engine::finish_lane(Lane &ln, int k) {
     bp.frames = cs.frame;
     const int n = std::min(cs.path_len, path_cap_);
     bp.arcs.resize(n);
-    const int *p = h_path_ + (size_t)k * path_cap_;
+    const int *p = sl.h_path + (size_t)k * path_cap_;
     for (int i = 0; i < n; i++) bp.arcs[i] = p[n - 1 - i];
     if (cs.error) log_msg(-1, "stream %llu: decoder capacity error %d (result may be truncated)", (unsigned long long)ln.s->id, cs.error);
     if (ln.s->on_result) ln.s->on_result(bp);
 }
 
 double Engine::run_resident(const int16_t *d_audio, int num_streams, int stride, const int *lengths, std::vector<BestPath> *out) {
-    // all streams advance one chunk per step until their own end; no host<->device sample traffic
+    // Streams are dealt to the pipeline slots in contiguous groups; every group advances one chunk per step until
+    // its streams end; no host<->device sample traffic.  Groups run on their own CUDA streams and overlap.
     if (num_streams > cfg_.num_channels) throw std::runtime_error("run_resident: more streams than channels");
     wait();
     const int spc = samples_per_chunk();
+    const int G = (int)slots_.size();
     std::vector<std::shared_ptr<Stream>> ss(num_streams);
     std::vector<BestPath> res(num_streams);
     int max_chunks = 0;
@@ -629,28 +672,45 @@ double Engine::run_resident(const int16_t *d_audio, int num_streams, int stride,
         if (len < 0 || len > stride) throw std::runtime_error("run_resident: bad stream length");
         max_chunks = std::max(max_chunks, len / spc + 1);
     }
+    const int per_group = (num_streams + G - 1) / G;
+    if (per_group > slot_lanes_) throw std::runtime_error("run_resident: more streams than lanes (raise max-batch-size)");
     cudaEvent_t e0, e1;
     VB_CUDA_CHECK(cudaEventCreate(&e0));
     VB_CUDA_CHECK(cudaEventCreate(&e1));
     VB_CUDA_CHECK(cudaEventRecord(e0, stream_));
-    std::vector<Lane> lanes;
+    for (Slot &sl : slots_) VB_CUDA_CHECK(cudaStreamWaitEvent(sl.stream, e0, 0));
     for (int k = 0; k < max_chunks; k++) {
-        lanes.clear();
-        for (int i = 0; i < num_streams; i++) {
-            const int len = lengths ? lengths[i] : stride;
-            const int nfull = len / spc;
-            if (k > nfull) continue;
-            Lane ln;
-            ln.s = ss[i];
-            ln.chunk.samples.resize(k == nfull ? len - nfull * spc : spc);  // length only; samples are read from d_audio
-            ln.chunk.last = k == nfull;
-            lanes.push_back(std::move(ln));
-            if ((int)lanes.size() == cfg_.max_lanes) {
-                step(lanes, d_audio, stride);
-                lanes.clear();
+        for (int g = 0; g < G; g++) {
+            Slot &sl = slots_[g];
+            if (sl.busy) {
+                complete_step(sl);
+                sl.busy = false;
+                sl.lanes.clear();
+            }
+            for (int i = g * per_group; i < std::min(num_streams, (g + 1) * per_group); i++) {
+                const int len = lengths ? lengths[i] : stride;
+                const int nfull = len / spc;
+                if (k > nfull) continue;
+                Lane ln;
+                ln.s = ss[i];
+                ln.chunk.samples.resize(k == nfull ? len - nfull * spc : spc);  // length only; samples are read from d_audio
+                ln.chunk.last = k == nfull;
+                sl.lanes.push_back(std::move(ln));
+            }
+            if (!sl.lanes.empty()) {
+                launch_step(sl, d_audio, stride);
+                sl.busy = true;
             }
         }
-        if (!lanes.empty()) step(lanes, d_audio, stride);
+    }
+    for (Slot &sl : slots_) {
+        if (sl.busy) {
+            complete_step(sl);
+            sl.busy = false;
+            sl.lanes.clear();
+        }
+        VB_CUDA_CHECK(cudaEventRecord(e1, sl.stream));
+        VB_CUDA_CHECK(cudaStreamWaitEvent(stream_, e1, 0));
     }
     VB_CUDA_CHECK(cudaEventRecord(e1, stream_));
     VB_CUDA_CHECK(cudaEventSynchronize(e1));

@@ -86,17 +86,38 @@ class Engine {
     struct Lane {
         std::shared_ptr<Stream> s;
         Stream::Chunk chunk;
+        int dec_frames_after = 0;
+    };
+    // One pipeline slot = one lane group in flight on its own CUDA stream.  Slots only share read-only model
+    // data and the per-channel state of disjoint streams, so kernels of different slots overlap on the GPU
+    // (a latency-bound search launch of one group runs under the GEMMs / feature kernels of another).
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev[5] = {};
+        cudaEvent_t done = nullptr;
+        int16_t *d_staging = nullptr, *h_staging = nullptr;
+        LaneDesc *d_lanes = nullptr, *h_lanes = nullptr;
+        NodeLane *d_table = nullptr;
+        int *d_rowoff = nullptr;
+        DecArgs dec{};
+        DecChannelState *h_cs = nullptr;
+        int *h_path = nullptr;
+        std::vector<Lane> lanes;
+        bool busy = false, timed = false;
+        double audio = 0;
+        long long launches = 0, gemms = 0;
     };
     void worker();
-    void step(std::vector<Lane> &lanes, const int16_t *d_resident, int resident_stride);
+    void launch_step(Slot &sl, const int16_t *d_resident, int resident_stride);
+    void complete_step(Slot &sl);
     void upload_model();
     void alloc_state();
-    void finish_lane(Lane &ln, int lane_idx);
+    void finish_lane(Slot &sl, Lane &ln, int lane_idx);
 
     const Model &model_;
     Config cfg_;
-    cudaStream_t stream_ = nullptr;
-    cudaEvent_t ev_[6] = {};
+    cudaStream_t stream_ = nullptr;  // setup / utility stream
+    std::vector<Slot> slots_;
     bool timing_ = false;
     // model on device
     FeatTables feat_tab_{};
@@ -110,17 +131,12 @@ class Engine {
     std::vector<void *> allocs_;
     // per channel / per step state
     IvecState iv_state_{};
-    int16_t *d_carry_ = nullptr, *d_staging_ = nullptr, *h_staging_ = nullptr;
-    LaneDesc *d_lanes_ = nullptr, *h_lanes_ = nullptr;
+    int16_t *d_carry_ = nullptr;
     int *d_node_end_ = nullptr;
-    NodeLane *d_table_ = nullptr;
-    int *d_rowoff_ = nullptr;
-    DecArgs dec_{};
-    DecChannelState *h_cs_ = nullptr;
-    int *h_path_ = nullptr;
+    DecArgs dec_{};  // template: graph, options and per-channel arrays; each slot adds its own scratch
     float *d_capture_ = nullptr, *h_capture_ = nullptr;
     size_t capture_floats_ = 0;
-    int max_in_rows_ = 0, log_cap_ = 0, max_frames_ = 0, path_cap_ = 0;
+    int max_in_rows_ = 0, log_cap_ = 0, max_frames_ = 0, path_cap_ = 0, slot_lanes_ = 0;
     std::vector<int> free_channels_;
     // batching
     std::mutex mu_;
