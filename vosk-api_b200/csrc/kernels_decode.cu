@@ -28,9 +28,8 @@
 namespace vb {
 
 namespace {
-constexpr int kDecThreads = 256;
-constexpr int kDecWarps = kDecThreads / 32;
-constexpr int kDecBlocksPerSM = 4;
+constexpr int kDecBlocksPerSM = 3;   // 256-thread variant; the 1024-thread variant (heavy lanes) runs 1 per SM
+constexpr int kSmemSlots = 4096;  // level-1 (shared memory) table entries per CTA
 constexpr unsigned long long kValMax = ~0ull;
 constexpr int kEmpty = -1;
 
@@ -51,30 +50,35 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
+template <int NT>
 struct Shared {
     unsigned min_ord;  // running minimum of candidate costs (ordered)
     int n_cand, n_next, error;
-    int warp_cnt[kDecWarps], warp_exp[kDecWarps], warp_deg[kDecWarps];
+    int warp_cnt[(NT / 32)], warp_exp[(NT / 32)], warp_deg[(NT / 32)];
     unsigned hist[256];
     unsigned sel_prefix, sel_mask;
     int sel_k;
-    unsigned red_u[kDecWarps];
-    unsigned long long red_ull[kDecWarps];
-    int own[kDecWarps][32];  // per-warp marker array of the arc-window owner scan
+    unsigned red_u[(NT / 32)];
+    unsigned long long red_ull[(NT / 32)];
+    int own[(NT / 32)][32];  // per-warp marker array of the arc-window owner scan
 };
 
+template <int NT>
 struct Ctx {
     const DecArgs &a;
-    Shared &sh;
+    Shared<NT> &sh;
     float *ll;  // shared log-likelihood row
-    int *hkey;
+    int *skey;                 // level-1 table in shared memory: keys / 64-bit best words
+    unsigned long long *sval;
+    int *hkey;                 // level-2 table in global memory (overflow of the bounded level-1 probe)
     unsigned long long *hval;
     int *htok;
-    unsigned long long *cpk;
-    int *cslot, *csrc, *rank;
+    int4 *cand;                // {packed lo, packed hi, slot, src}
+    int *rank;
     int *sv_pref, *sv_a0, *sv_src, *win_owner;
     float *sv_cost;
     int tid, warp, lane;
+    bool use_l1;     // level-1 (shared) table enabled for this frame
     unsigned hmask;  // this frame's table window (power of two - 1): the table is empty between frames, so any
                      // power-of-two prefix of it is a valid table; small frames stay L2-resident
 };
@@ -88,47 +92,87 @@ __device__ __forceinline__ int agg_inc(int *counter) {
     return base + __popc(m & lanemask_lt());
 }
 
+// Table slots: [0, kSmemSlots) = shared-memory level, kSmemSlots + g = global level.  A state lives in level 1 iff
+// a free or matching slot existed within kProbe1 probes at its first insertion; slots are never freed inside a
+// frame, so every later lookup of the same state takes the same decision.
+constexpr int kProbe1 = 16;
+template <int NT>
+__device__ __forceinline__ unsigned long long tab_val(const Ctx<NT> &c, int slot) {
+    return slot < kSmemSlots ? *(volatile unsigned long long *)(c.sval + slot) : __ldcg(c.hval + (slot - kSmemSlots));
+}
+template <int NT>
+__device__ __forceinline__ int tab_key(const Ctx<NT> &c, int slot) {
+    return slot < kSmemSlots ? *(volatile int *)(c.skey + slot) : __ldcg(c.hkey + (slot - kSmemSlots));
+}
+// after the winners are known the key field of a level-1 slot is reused for the token index
+template <int NT>
+__device__ __forceinline__ void tab_set_tok(const Ctx<NT> &c, int slot, int idx) {
+    if (slot < kSmemSlots) c.skey[slot] = idx; else c.htok[slot - kSmemSlots] = idx;
+}
+template <int NT>
+__device__ __forceinline__ int tab_tok(const Ctx<NT> &c, int slot) {
+    return slot < kSmemSlots ? *(volatile int *)(c.skey + slot) : __ldcg(c.htok + (slot - kSmemSlots));
+}
+
 // insert (state, packed) ; records a candidate when it improved the state's best word
-__device__ __forceinline__ void relax(Ctx &c, int state, unsigned long long pk, int src) {
-    const unsigned mask = c.hmask;
-    unsigned h = ((unsigned)state * 2654435761u) >> 7 & mask;
-    int probes = 0;
-    for (;;) {
-        int prev = atomicCAS(c.hkey + h, kEmpty, state);
-        if (prev == kEmpty || prev == state) break;
-        h = (h + 1) & mask;
-        if (++probes > (int)mask) {
-            c.sh.error = 1;
-            return;
+template <int NT>
+__device__ __forceinline__ void relax(Ctx<NT> &c, int state, unsigned long long pk, int src) {
+    const unsigned hash = ((unsigned)state * 2654435761u) >> 7;
+    int slot = -1;
+    unsigned h = hash & (kSmemSlots - 1);
+#pragma unroll 1
+    for (int p = 0; p < kProbe1 && c.use_l1; p++) {
+        int prev = atomicCAS(c.skey + h, kEmpty, state);
+        if (prev == kEmpty || prev == state) {
+            slot = (int)h;
+            break;
         }
+        h = (h + 1) & (kSmemSlots - 1);
     }
-    unsigned long long old = atomicMin(c.hval + h, pk);
+    unsigned long long old;
+    if (slot >= 0) {
+        old = atomicMin(c.sval + slot, pk);
+    } else {
+        const unsigned mask = c.hmask;
+        unsigned g = hash & mask;
+        int probes = 0;
+        for (;;) {
+            int prev = atomicCAS(c.hkey + g, kEmpty, state);
+            if (prev == kEmpty || prev == state) break;
+            g = (g + 1) & mask;
+            if (++probes > (int)mask) {
+                c.sh.error = 1;
+                return;
+            }
+        }
+        old = atomicMin(c.hval + g, pk);
+        slot = kSmemSlots + (int)g;
+    }
     if (pk < old) {
         int idx = agg_inc(&c.sh.n_cand);
-        if (idx < c.a.cand_cap) {
-            c.cpk[idx] = pk;
-            c.cslot[idx] = (int)h;
-            c.csrc[idx] = src;
-        } else {
-            c.sh.error = 2;
-        }
+        if (idx < c.a.cand_cap) c.cand[idx] = make_int4((int)(unsigned)pk, (int)(unsigned)(pk >> 32), slot, src);
+        else c.sh.error = 2;
     }
 }
 
-__device__ float block_min(Ctx &c, const float *cost, int n) {
-    unsigned m = 0xffffffffu;
-    for (int i = c.tid; i < n; i += kDecThreads) m = min(m, ford(cost[i]));
+// minimum cost and the index of one token attaining it
+template <int NT>
+__device__ float block_min(Ctx<NT> &c, const float *cost, int n, int *arg) {
+    unsigned long long m = kValMax;
+    for (int i = c.tid; i < n; i += NT) m = min(m, ((unsigned long long)ford(cost[i]) << 32) | (unsigned)i);
     for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (c.lane == 0) c.sh.red_u[c.warp] = m;
+    if (c.lane == 0) c.sh.red_ull[c.warp] = m;
     __syncthreads();
-    m = c.sh.red_u[0];
-    for (int w = 1; w < kDecWarps; w++) m = min(m, c.sh.red_u[w]);
+    m = c.sh.red_ull[0];
+    for (int w = 1; w < (NT / 32); w++) m = min(m, c.sh.red_ull[w]);
     __syncthreads();
-    return unord(m);
+    *arg = (int)(unsigned)m;
+    return unord((unsigned)(m >> 32));
 }
 
 // exact k-th smallest (0-based) of cost[0..n) by 4-pass radix select on the ordered key
-__device__ float block_select(Ctx &c, const float *cost, int n, int k) {
+template <int NT>
+__device__ float block_select(Ctx<NT> &c, const float *cost, int n, int k) {
     if (c.tid == 0) {
         c.sh.sel_prefix = 0;
         c.sh.sel_mask = 0;
@@ -136,10 +180,10 @@ __device__ float block_select(Ctx &c, const float *cost, int n, int k) {
     }
     for (int pass = 3; pass >= 0; pass--) {
         const int shift = pass * 8;
-        c.sh.hist[c.tid] = 0;  // kDecThreads == 256
+        if (c.tid < 256) c.sh.hist[c.tid] = 0;
         __syncthreads();
         const unsigned prefix = c.sh.sel_prefix, mask = c.sh.sel_mask;
-        for (int i = c.tid; i < n; i += kDecThreads) {
+        for (int i = c.tid; i < n; i += NT) {
             unsigned key = ford(cost[i]);
             if ((key & mask) == prefix) {
                 unsigned bin = (key >> shift) & 255u;
@@ -187,13 +231,14 @@ __device__ float block_select(Ctx &c, const float *cost, int n, int k) {
 //   kth(max_active) <  beam_cutoff  <=>  #{cost <  beam_cutoff} >  max_active
 //   kth(min_active) >  beam_cutoff  <=>  #{cost <= beam_cutoff} <= min_active
 // so the exact radix select runs only on the frames where it changes the result.
-__device__ float get_cutoff(Ctx &c, const float *cost, int n, float *adaptive_beam, float *best_out) {
+template <int NT>
+__device__ float get_cutoff(Ctx<NT> &c, const float *cost, int n, float *adaptive_beam, float *best_out, int *best_idx) {
     const DecArgs &a = c.a;
-    float best = block_min(c, cost, n);
+    float best = block_min(c, cost, n, best_idx);
     *best_out = best;
     const float beam_cutoff = best + a.beam;
     int lt = 0, le = 0;
-    for (int i = c.tid; i < n; i += kDecThreads) {
+    for (int i = c.tid; i < n; i += NT) {
         float v = cost[i];
         lt += v < beam_cutoff;
         le += v <= beam_cutoff;
@@ -203,7 +248,7 @@ __device__ float get_cutoff(Ctx &c, const float *cost, int n, float *adaptive_be
     if (c.lane == 0) c.sh.red_ull[c.warp] = tot;
     __syncthreads();
     tot = 0;
-    for (int w = 0; w < kDecWarps; w++) tot += c.sh.red_ull[w];
+    for (int w = 0; w < (NT / 32); w++) tot += c.sh.red_ull[w];
     __syncthreads();
     const int n_lt = (int)(tot >> 32), n_le = (int)(unsigned)tot;
     if (n > a.max_active && n_lt > a.max_active) {
@@ -226,16 +271,18 @@ __device__ float get_cutoff(Ctx &c, const float *cost, int n, float *adaptive_be
 
 // epsilon closure over candidates [lo, hi) until no candidate is added; returns total candidate count.
 // Epsilon out-degrees are tiny (0-2), so one thread per candidate is balanced.
-__device__ int closure(Ctx &c, int lo, int hi, float cutoff, unsigned long long *arcs_seen) {
+template <int NT>
+__device__ int closure(Ctx<NT> &c, int lo, int hi, float cutoff, unsigned long long *arcs_seen) {
     const DecArgs &a = c.a;
     while (lo < hi) {
-        for (int i = lo + c.tid; i < hi; i += kDecThreads) {
-            const unsigned long long pk = c.cpk[i];
-            const int slot = c.cslot[i];
-            const float cost = unord((unsigned)(pk >> 32));
-            if (__ldcg(c.hval + slot) == pk && cost < cutoff) {
-                const int s = __ldcg(c.hkey + slot);
-                const int a0 = __ldg(a.g.eps_begin + s), a1 = __ldg(a.g.e_begin + s + 1);
+        for (int i = lo + c.tid; i < hi; i += NT) {
+            const int4 cd = c.cand[i];
+            const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
+            const int slot = cd.z;
+            const float cost = unord((unsigned)cd.y);
+            if (cost < cutoff && tab_val(c, slot) == pk) {
+                const int s = tab_key(c, slot);
+                const int a0 = __ldg(&a.g.state_arcs[s].y), a1 = __ldg(&a.g.state_arcs[s + 1].x);
                 *arcs_seen += (unsigned)(a1 - a0);
                 for (int arc = a0; arc < a1; arc++) {
                     const int4 av = __ldg(a.g.arcs + arc);
@@ -252,68 +299,83 @@ __device__ int closure(Ctx &c, int lo, int hi, float cutoff, unsigned long long 
     return hi;
 }
 
-// turn the winning candidates into the next frame's token list; clears the hash table
-__device__ void finalize_tokens(Ctx &c, int n_emit, int n_cand, float cutoff, int *t_state, float *t_cost, int *t_arc,
+// turn the winning candidates into the next frame's token list; clears both table levels
+template <int NT>
+__device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff, int *t_state, float *t_cost, int *t_arc,
                                 int *t_prev) {
     const DecArgs &a = c.a;
-    for (int i = c.tid; i < n_cand; i += kDecThreads) {
-        unsigned long long pk = c.cpk[i];
-        int slot = c.cslot[i];
-        float cost = unord((unsigned)(pk >> 32));
-        if (__ldcg(c.hval + slot) == pk && cost < cutoff) {
+    for (int i = c.tid; i < n_cand; i += NT) {
+        const int4 cd = c.cand[i];
+        const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
+        const float cost = unord((unsigned)cd.y);
+        if (cost < cutoff && tab_val(c, cd.z) == pk) {
             int idx = agg_inc(&c.sh.n_next);
             if (idx < a.tok_cap) {
-                t_state[idx] = __ldcg(c.hkey + slot);
+                t_state[idx] = tab_key(c, cd.z);
                 t_cost[idx] = cost;
-                t_arc[idx] = (int)(unsigned)pk;
-                c.htok[slot] = idx;
-                if (i < n_emit) t_prev[idx] = c.csrc[i];
+                t_arc[idx] = cd.x;
+                tab_set_tok(c, cd.z, idx);  // one winner per slot: nobody else reads this slot's key any more
+                if (i < n_emit) t_prev[idx] = cd.w;
             } else {
                 c.sh.error = 3;
+                tab_set_tok(c, cd.z, 0);
             }
         }
     }
     __syncthreads();
-    for (int i = n_emit + c.tid; i < n_cand; i += kDecThreads) {
-        unsigned long long pk = c.cpk[i];
-        int slot = c.cslot[i];
-        float cost = unord((unsigned)(pk >> 32));
-        if (__ldcg(c.hval + slot) == pk && cost < cutoff) {
-            int idx = __ldcg(c.htok + slot);
-            if (idx < a.tok_cap) t_prev[idx] = -2 - __ldcg(c.htok + c.csrc[i]);
+    for (int i = n_emit + c.tid; i < n_cand; i += NT) {
+        const int4 cd = c.cand[i];
+        const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
+        const float cost = unord((unsigned)cd.y);
+        if (cost < cutoff && tab_val(c, cd.z) == pk) {
+            int idx = tab_tok(c, cd.z);
+            if (idx < a.tok_cap) t_prev[idx] = -2 - tab_tok(c, cd.w);
         }
     }
     __syncthreads();
     if (c.sh.error == 1 || c.sh.error == 2) {
         // a candidate was dropped (table/candidate overflow): entries may exist that no candidate points at
-        for (int i = c.tid; i < a.hash_size; i += kDecThreads) {
+        for (int i = c.tid; i < a.hash_size; i += NT) {
             c.hkey[i] = kEmpty;
             c.hval[i] = kValMax;
         }
     } else {
-        for (int i = c.tid; i < n_cand; i += kDecThreads) {
-            int slot = c.cslot[i];
-            c.hkey[slot] = kEmpty;
-            c.hval[slot] = kValMax;
+        for (int i = c.tid; i < n_cand; i += NT) {
+            const int slot = c.cand[i].z;
+            if (slot >= kSmemSlots) {
+                c.hkey[slot - kSmemSlots] = kEmpty;
+                c.hval[slot - kSmemSlots] = kValMax;
+            }
         }
+    }
+    for (int i = c.tid; i < kSmemSlots; i += NT) {
+        c.skey[i] = kEmpty;
+        c.sval[i] = kValMax;
     }
     __syncthreads();
 }
 }  // namespace
 
-__global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(DecArgs a) {
-    extern __shared__ __align__(16) float s_ll[];
-    __shared__ Shared sh;
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : 1) decode_kernel(DecArgs a) {
+    extern __shared__ __align__(16) float s_ll[];  // [npdf floats | level-1 values u64[kSmemSlots] | level-1 keys int[kSmemSlots]]
+    __shared__ Shared<NT> sh;
     const int tid = threadIdx.x;
     const size_t g = blockIdx.x;
     const int nwin_cap = a.cand_cap / 32 + 2;
-    Ctx c{a, sh, s_ll,
+    unsigned long long *s_val = reinterpret_cast<unsigned long long *>(s_ll + ((a.out_node.dim + 3) & ~3));
+    int *s_key = reinterpret_cast<int *>(s_val + kSmemSlots);
+    for (int i = tid; i < kSmemSlots; i += NT) {
+        s_key[i] = kEmpty;
+        s_val[i] = kValMax;
+    }
+    Ctx<NT> c{a, sh, s_ll, s_key, s_val,
           a.hash_key + g * a.hash_size, a.hash_val + g * a.hash_size, a.hash_tok + g * a.hash_size,
-          a.cand_packed + g * a.cand_cap, a.cand_slot + g * a.cand_cap, a.cand_src + g * a.cand_cap,
+          a.cand + g * a.cand_cap,
           a.rank + g * a.tok_cap,
           a.sv_pref + g * a.tok_cap, a.sv_a0 + g * a.tok_cap, a.sv_src + g * a.tok_cap, a.win_owner + g * nwin_cap,
           a.sv_cost + g * a.tok_cap,
-          tid, tid >> 5, tid & 31, (unsigned)a.hash_size - 1};
+          tid, tid >> 5, tid & 31, true, (unsigned)a.hash_size - 1};
     unsigned long long cnt_tok = 0, cnt_arc_e = 0, cnt_arc_eps = 0, cnt_new = 0;  // per-thread profiling counters
     const int npdf = a.out_node.dim;
     for (int l = blockIdx.x; l < a.num_lanes; l += gridDim.x) {
@@ -338,6 +400,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
                 sh.n_next = 0;
             }
             c.hmask = (unsigned)a.hash_size - 1;
+            c.use_l1 = true;
             __syncthreads();
             if (tid == 0) relax(c, a.g.start, pack(0.f, -1), -1);
             __syncthreads();
@@ -373,16 +436,33 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
                 // stage this frame's log-likelihood row
                 const float *row = a.out_node.buf + ((size_t)ch * a.out_node.ring +
                                                      (((t_first + fi * a.out_node.step) - a.out_node.t_start) / a.out_node.step & (a.out_node.ring - 1))) * npdf;
-                for (int i = tid * 4; i < npdf; i += kDecThreads * 4) *reinterpret_cast<float4 *>(s_ll + i) = *reinterpret_cast<const float4 *>(row + i);
-                cur_cutoff = get_cutoff(c, t_cost, n_cur, &adaptive_beam, &best);
-            }
-            if (tid == 0) {
+                for (int i = tid * 4; i < npdf; i += NT * 4) *reinterpret_cast<float4 *>(s_ll + i) = *reinterpret_cast<const float4 *>(row + i);
+                int best_idx = 0;
+                cur_cutoff = get_cutoff(c, t_cost, n_cur, &adaptive_beam, &best, &best_idx);
+                // seed the running minimum with the best token's own arcs (as LatticeFasterDecoder does), so the
+                // loose cutoff used while expanding is already close to the final one and few arcs touch the table
+                if (c.warp == 0) {
+                    const int2 sa = __ldg(&a.g.state_arcs[t_state[best_idx]]);
+                    unsigned m = 0xffffffffu;
+                    for (int arc = sa.x + c.lane; arc < sa.y; arc += 32) {
+                        const int4 av = __ldg(a.g.arcs + arc);
+                        const float ac = -best - a.acoustic_scale * s_ll[av.z];
+                        m = min(m, ford(best + ac + __int_as_float(av.x)));
+                    }
+                    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    if (c.lane == 0) {
+                        sh.min_ord = m;
+                        sh.n_cand = 0;
+                        sh.n_next = 0;
+                    }
+                }
+            } else if (tid == 0) {
                 sh.min_ord = 0xffffffffu;
                 sh.n_cand = 0;
                 sh.n_next = 0;
             }
             // ---- pass A: per-warp counts of survivors, survivors with out-arcs, and out-arcs ----
-            const int span = ((n_cur + kDecWarps - 1) / kDecWarps + 31) & ~31;
+            const int span = ((n_cur + (NT / 32) - 1) / (NT / 32) + 31) & ~31;
             const int wbeg = min(c.warp * span, n_cur), wend = min(wbeg + span, n_cur);
             {
                 int cnt = 0, cexp = 0, degsum = 0;
@@ -391,8 +471,8 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
                     const bool f = i < wend && t_cost[i] <= cur_cutoff;
                     int deg = 0;
                     if (f && !final_pass) {
-                        const int s = t_state[i];
-                        deg = __ldg(a.g.eps_begin + s) - __ldg(a.g.e_begin + s);
+                        const int2 sa = __ldg(&a.g.state_arcs[t_state[i]]);
+                        deg = sa.y - sa.x;
                     }
                     cnt += __popc(__ballot_sync(0xffffffffu, f));
                     cexp += __popc(__ballot_sync(0xffffffffu, deg > 0));
@@ -407,7 +487,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
             }
             __syncthreads();
             int rbase = 0, ebase = 0, abase = 0, n_surv = 0, n_exp = 0, n_arcs = 0;
-            for (int w = 0; w < kDecWarps; w++) {
+            for (int w = 0; w < (NT / 32); w++) {
                 if (w < c.warp) {
                     rbase += sh.warp_cnt[w];
                     ebase += sh.warp_exp[w];
@@ -422,6 +502,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
                 unsigned want = 3u * (unsigned)n_arcs + 1024u, win = 4096;
                 while (win < want && win < (unsigned)a.hash_size) win <<= 1;
                 c.hmask = min(win, (unsigned)a.hash_size) - 1;
+                c.use_l1 = n_arcs <= kSmemSlots + kSmemSlots / 2;  // heavy frames would only collide in level 1
             }
             if (n_arcs > a.cand_cap) {  // more emitting arcs than candidate slots: flag and truncate
                 if (tid == 0) sh.error = 6;
@@ -438,9 +519,9 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
                 if (f) {
                     cost = t_cost[i];
                     if (!final_pass) {
-                        const int s = t_state[i];
-                        a0 = __ldg(a.g.e_begin + s);
-                        deg = __ldg(a.g.eps_begin + s) - a0;
+                        const int2 sa = __ldg(&a.g.state_arcs[t_state[i]]);
+                        a0 = sa.x;
+                        deg = sa.y - a0;
                     }
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, f), bexp = __ballot_sync(0xffffffffu, deg > 0);
@@ -467,7 +548,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
             __syncthreads();
             // ---- pass C1: token log of the survivors (prev of an epsilon-created token = a survivor of this frame) ----
             if (log_ok) {
-                for (int i = tid; i < n_cur; i += kDecThreads) {
+                for (int i = tid; i < n_cur; i += NT) {
                     const int r = c.rank[i];
                     if (r < 0) continue;
                     const int li = log_count + r;
@@ -499,7 +580,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
                 const float cost_offset = -best;
                 const int nwin = (n_arcs + 31) >> 5;
                 int *own = sh.own[c.warp];
-                for (int w = c.warp; w < nwin; w += kDecWarps) {
+                for (int w = c.warp; w < nwin; w += (NT / 32)) {
                     const int j = (w << 5) + c.lane;
                     const int q0 = c.win_owner[w];
                     const int my = q0 + c.lane;
@@ -561,7 +642,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
             const int *t_state = a.tok_state + tbase + (size_t)parity * a.tok_cap;
             // survivors of the final pass are all tokens, logged in list order: log index = lo + i
             unsigned long long bw[2] = {kValMax, kValMax};
-            for (int i = tid; i < n_cur && lo + i < hi; i += kDecThreads) {
+            for (int i = tid; i < n_cur && lo + i < hi; i += NT) {
                 int s = t_state[i];
                 float cst = log_cost[lo + i];
                 float fc = __ldg(a.g.final_cost + s);
@@ -575,7 +656,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
                 if (c.lane == 0) sh.red_ull[c.warp] = v;
                 __syncthreads();
                 v = sh.red_ull[0];
-                for (int w = 1; w < kDecWarps; w++) v = min(v, sh.red_ull[w]);
+                for (int w = 1; w < (NT / 32); w++) v = min(v, sh.red_ull[w]);
                 win[p] = v;
                 __syncthreads();
             }
@@ -589,7 +670,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
             __syncthreads();
             if (target != kValMax) {
                 const int want_state = (int)(unsigned)target;
-                for (int i = tid; i < n_cur && lo + i < hi; i += kDecThreads) {
+                for (int i = tid; i < n_cur && lo + i < hi; i += NT) {
                     if (t_state[i] == want_state) {
                         // single winner thread walks the back pointers (stream end only)
                         int *path = a.path + (size_t)ch * a.path_cap;
@@ -618,6 +699,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecBlocksPerSM) decode_kernel(De
                 atomicMax(a.counters + 6, (unsigned long long)max_tok);
                 atomicAdd(a.counters + 7, 1ull);
             }
+            if (a.lane_load) a.lane_load[l] = max_tok;  // fed back to the batcher: heavy streams are grouped together
         }
     }
     if (a.counters) {
@@ -637,15 +719,21 @@ extern "C" int vbk_decode_max_grid(int device) {
     return sms * kDecBlocksPerSM;
 }
 
-extern "C" cudaError_t vbk_decode(const DecArgs *a, cudaStream_t s) {
+// heavy != 0: 1024-thread CTAs (one per SM) for batches whose lanes carry thousands of tokens per frame — the
+// per-frame critical path of such a lane is what bounds the step, so it gets 4x the threads.
+extern "C" cudaError_t vbk_decode(const DecArgs *a, int heavy, cudaStream_t s) {
     if (a->num_lanes <= 0) return cudaSuccess;
-    int smem = (a->out_node.dim * 4 + 15) & ~15;
-    if (smem > 40000) {
-        cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-    }
+    int smem = ((a->out_node.dim + 3) & ~3) * 4 + kSmemSlots * 12;
     int grid = a->num_lanes < a->grid ? a->num_lanes : a->grid;
-    decode_kernel<<<grid, kDecThreads, smem, s>>>(*a);
+    if (heavy) {
+        cudaError_t e = cudaFuncSetAttribute(decode_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        decode_kernel<1024><<<grid, 1024, smem, s>>>(*a);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(decode_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        decode_kernel<256><<<grid, 256, smem, s>>>(*a);
+    }
     return cudaGetLastError();
 }
 

@@ -70,6 +70,7 @@ Engine::~Engine() {
         if (sl.h_lanes) cudaFreeHost(sl.h_lanes);
         if (sl.h_cs) cudaFreeHost(sl.h_cs);
         if (sl.h_path) cudaFreeHost(sl.h_path);
+        if (sl.h_load) cudaFreeHost(sl.h_load);
         for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -238,8 +239,11 @@ void Engine::upload_model() {
             memcpy(&wbits, &g.arc_w[a], 4);
             arcs[a] = make_int4(wbits, g.arc_next[a], g.arc_pdf[a], g.arc_olabel[a]);
         }
+        std::vector<int2> sa((size_t)g.num_states + 1);
+        for (int s2 = 0; s2 < g.num_states; s2++) sa[s2] = make_int2(g.e_begin[s2], g.eps_begin[s2]);
+        sa[g.num_states] = make_int2(g.num_arcs, g.num_arcs);
         graph_ = GraphDev{g.num_states, g.num_arcs, g.start, dev_upload(allocs_, g.final_cost), dev_upload(allocs_, g.e_begin),
-                          dev_upload(allocs_, g.eps_begin), dev_upload(allocs_, arcs)};
+                          dev_upload(allocs_, g.eps_begin), dev_upload(allocs_, arcs), dev_upload(allocs_, sa)};
     }
     VB_CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
@@ -303,16 +307,17 @@ void Engine::alloc_state() {
         sl.d_rowoff = dev_alloc<int>(allocs_, (size_t)nn * (L + 1), 0);
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_cs, (size_t)L * sizeof(DecChannelState)));
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_path, (size_t)L * path_cap_ * sizeof(int)));
+        sl.d_load = dev_alloc<int>(allocs_, (size_t)L, 0);
+        VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_load, (size_t)L * sizeof(int)));
         DecArgs &sd = sl.dec;
         sd = dec_;
         sd.out_table = sl.d_table + (size_t)(nn - 1) * L;
+        sd.lane_load = sl.d_load;
         const size_t G = (size_t)sd.grid;
         sd.hash_key = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0xff);
         sd.hash_val = dev_alloc<unsigned long long>(allocs_, G * cfg_.hash_size, 0xff);
         sd.hash_tok = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0);
-        sd.cand_packed = dev_alloc<unsigned long long>(allocs_, G * cfg_.cand_cap);
-        sd.cand_slot = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
-        sd.cand_src = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
+        sd.cand = dev_alloc<int4>(allocs_, G * cfg_.cand_cap);
         sd.rank = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
         sd.sv_pref = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
         sd.sv_a0 = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
@@ -398,6 +403,30 @@ void Engine::worker() {
             cv_work_.wait(lk, [&] { return stop_ || !ready_.empty() || n_busy > 0; });
             if (stop_ && n_busy == 0) return;
         }
+        // pick the slot to service: a finished one if any (slots complete out of order: light batches overtake
+        // heavy ones), else a free one when streams are ready, else poll
+        int pick = -1;
+        for (int k = 0; k < (int)slots_.size() && pick < 0; k++) {
+            int i = (cur + k) % (int)slots_.size();
+            if (slots_[i].busy && cudaEventQuery(slots_[i].done) == cudaSuccess) pick = i;
+        }
+        if (pick < 0) {
+            bool have_ready;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                have_ready = !ready_.empty();
+            }
+            if (have_ready)
+                for (int k = 0; k < (int)slots_.size() && pick < 0; k++) {
+                    int i = (cur + k) % (int)slots_.size();
+                    if (!slots_[i].busy) pick = i;
+                }
+        }
+        if (pick < 0) {
+            std::this_thread::yield();
+            continue;
+        }
+        cur = pick;
         Slot &sl = slots_[cur];
         if (sl.busy) {
             try {
@@ -436,6 +465,11 @@ void Engine::worker() {
         {
             std::unique_lock<std::mutex> lk(mu_);
             std::deque<std::shared_ptr<Stream>> deferred;
+            // group streams of similar load: a step lasts as long as its heaviest lane, so mixing a few heavy
+            // streams into every batch would stall all the light ones (stable sort keeps FIFO among equals)
+            if ((int)ready_.size() > slot_lanes_)
+                std::stable_sort(ready_.begin(), ready_.end(),
+                                 [](const std::shared_ptr<Stream> &x, const std::shared_ptr<Stream> &y) { return x->load > y->load; });
             while (!ready_.empty() && (int)sl.lanes.size() < slot_lanes_) {
                 std::shared_ptr<Stream> s = ready_.front();
                 ready_.pop_front();
@@ -459,7 +493,7 @@ void Engine::worker() {
         }
         if (!sl.lanes.empty()) {
             try {
-                launch_step(sl, nullptr, 0);
+                launch_step(sl, resident_audio_, resident_stride_);
                 sl.busy = true;
                 n_busy++;
             } catch (const std::exception &ex) {
@@ -485,7 +519,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         Stream &s = *lanes[i].s;
         const Stream::Chunk &ck = lanes[i].chunk;
         LaneDesc &d = sl.h_lanes[i];
-        const int n = (int)ck.samples.size();
+        const int n = s.resident ? ck.n_resident : (int)ck.samples.size();
         d.channel = s.channel;
         d.n_samples = n;
         d.carry = s.carry;
@@ -499,9 +533,9 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         d.in_end_before = d.first ? -ctx : s.in_end;
         d.in_end_after = d.frames_after > 0 ? (ck.last ? d.frames_after + ctx : d.frames_after) : d.in_end_before;
         d.dec_frames_before = s.dec_frames;
-        d.src_row = d_resident ? (int)s.id : i;
-        d.src_off = d_resident ? (int)s.samples : 0;
-        if (!d_resident && n) memcpy(sl.h_staging + (size_t)i * spc, ck.samples.data(), (size_t)n * sizeof(int16_t));
+        d.src_row = s.resident ? (int)s.id : i;
+        d.src_off = s.resident ? (int)s.samples : 0;
+        if (!s.resident && n) memcpy(sl.h_staging + (size_t)i * spc, ck.samples.data(), (size_t)n * sizeof(int16_t));
         in_rows += d.in_end_after - d.in_end_before + 2;
         sl.audio += n / 16000.0;
         // advance the host mirror of the stream state (a stream has at most one chunk in flight)
@@ -556,7 +590,9 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[3], st));
     sl.dec.lanes = sl.d_lanes;
     sl.dec.num_lanes = L;
-    VB_CUDA_CHECK(vbk_decode(&sl.dec, st));
+    int max_load = 0;
+    for (int i = 0; i < L; i++) max_load = std::max(max_load, lanes[i].s->load);
+    VB_CUDA_CHECK(vbk_decode(&sl.dec, max_load > cfg_.heavy_tokens ? 1 : 0, st));
     sl.launches++;
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[4], st));
     // results of finished lanes
@@ -569,6 +605,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
                                           (size_t)path_cap_ * sizeof(int), cudaMemcpyDeviceToHost, st));
             n_last++;
         }
+    VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_load, sl.d_load, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_CUDA_CHECK(cudaEventRecord(sl.done, st));
 }
 
@@ -577,6 +614,7 @@ void Engine::complete_step(Slot &sl) {
     const int L = (int)lanes.size();
     cudaStream_t st = sl.stream;
     VB_CUDA_CHECK(cudaEventSynchronize(sl.done));
+    for (int i = 0; i < L; i++) lanes[i].s->load = sl.h_load[i];
     // debug capture (tests): copy this step's new rows of the tapped stages
     for (int i = 0; i < L && cfg_.debug_capture; i++) {
         Stream &s = *lanes[i].s;
@@ -653,67 +691,57 @@ void Engine::finish_lane(Slot &sl, Lane &ln, int k) {
 }
 
 double Engine::run_resident(const int16_t *d_audio, int num_streams, int stride, const int *lengths, std::vector<BestPath> *out) {
-    // Streams are dealt to the pipeline slots in contiguous groups; every group advances one chunk per step until
-    // its streams end; no host<->device sample traffic.  Groups run on their own CUDA streams and overlap.
+    // Device-resident run: the streams' chunk descriptors (lengths only) go through the normal batcher, which reads
+    // the samples straight from the resident matrix; no host<->device sample traffic.
     if (num_streams > cfg_.num_channels) throw std::runtime_error("run_resident: more streams than channels");
     wait();
     const int spc = samples_per_chunk();
-    const int G = (int)slots_.size();
     std::vector<std::shared_ptr<Stream>> ss(num_streams);
     std::vector<BestPath> res(num_streams);
-    int max_chunks = 0;
     for (int i = 0; i < num_streams; i++) {
-        ss[i] = std::make_shared<Stream>();
-        ss[i]->id = (uint64_t)i;
-        ss[i]->channel = i;
-        BestPath *slot = &res[i];
-        ss[i]->on_result = [slot](const BestPath &bp) { *slot = bp; };
         const int len = lengths ? lengths[i] : stride;
         if (len < 0 || len > stride) throw std::runtime_error("run_resident: bad stream length");
-        max_chunks = std::max(max_chunks, len / spc + 1);
+        ss[i] = std::make_shared<Stream>();
+        ss[i]->id = (uint64_t)i;
+        ss[i]->resident = true;
+        BestPath *slot = &res[i];
+        ss[i]->on_result = [slot](const BestPath &bp) { *slot = bp; };
     }
-    const int per_group = (num_streams + G - 1) / G;
-    if (per_group > slot_lanes_) throw std::runtime_error("run_resident: more streams than lanes (raise max-batch-size)");
     cudaEvent_t e0, e1;
     VB_CUDA_CHECK(cudaEventCreate(&e0));
     VB_CUDA_CHECK(cudaEventCreate(&e1));
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        resident_audio_ = d_audio;
+        resident_stride_ = stride;
+    }
     VB_CUDA_CHECK(cudaEventRecord(e0, stream_));
-    for (Slot &sl : slots_) VB_CUDA_CHECK(cudaStreamWaitEvent(sl.stream, e0, 0));
-    for (int k = 0; k < max_chunks; k++) {
-        for (int g = 0; g < G; g++) {
-            Slot &sl = slots_[g];
-            if (sl.busy) {
-                complete_step(sl);
-                sl.busy = false;
-                sl.lanes.clear();
-            }
-            for (int i = g * per_group; i < std::min(num_streams, (g + 1) * per_group); i++) {
-                const int len = lengths ? lengths[i] : stride;
-                const int nfull = len / spc;
-                if (k > nfull) continue;
-                Lane ln;
-                ln.s = ss[i];
-                ln.chunk.samples.resize(k == nfull ? len - nfull * spc : spc);  // length only; samples are read from d_audio
-                ln.chunk.last = k == nfull;
-                sl.lanes.push_back(std::move(ln));
-            }
-            if (!sl.lanes.empty()) {
-                launch_step(sl, d_audio, stride);
-                sl.busy = true;
-            }
+    for (int i = 0; i < num_streams; i++) {
+        const int len = lengths ? lengths[i] : stride;
+        const int nfull = len / spc;
+        std::lock_guard<std::mutex> lk(mu_);
+        for (int k = 0; k <= nfull; k++) {
+            Stream::Chunk ck;
+            ck.samples.resize(0);
+            ck.n_resident = k == nfull ? len - nfull * spc : spc;
+            ck.last = k == nfull;
+            ss[i]->pending.push_back(std::move(ck));
+            ss[i]->pending_chunks.fetch_add(1);
+            outstanding_++;
         }
+        ss[i]->finished = true;
+        ss[i]->queued = true;
+        ready_.push_back(ss[i]);
     }
-    for (Slot &sl : slots_) {
-        if (sl.busy) {
-            complete_step(sl);
-            sl.busy = false;
-            sl.lanes.clear();
-        }
-        VB_CUDA_CHECK(cudaEventRecord(e1, sl.stream));
-        VB_CUDA_CHECK(cudaStreamWaitEvent(stream_, e1, 0));
-    }
+    cv_work_.notify_all();
+    wait();
     VB_CUDA_CHECK(cudaEventRecord(e1, stream_));
     VB_CUDA_CHECK(cudaEventSynchronize(e1));
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        resident_audio_ = nullptr;
+        resident_stride_ = 0;
+    }
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);

@@ -43,8 +43,11 @@ struct Stream {
     int64_t samples = 0;     // samples handed to the GPU so far
     int frames = 0;          // MFCC frames computed so far
     int iv_end = 0, in_end = 0, dec_frames = 0, carry = 0;
+    int load = 0;            // tokens per frame seen in the stream's last step (batching key)
+    bool resident = false;   // samples are read from a device-resident matrix (row = id)
     struct Chunk {
         std::vector<int16_t> samples;
+        int n_resident = 0;  // chunk length when the samples live in a device-resident matrix
         bool last;
     };
     std::deque<Chunk> pending;            // guarded by Engine::mu_
@@ -102,6 +105,7 @@ class Engine {
         DecArgs dec{};
         DecChannelState *h_cs = nullptr;
         int *h_path = nullptr;
+        int *d_load = nullptr, *h_load = nullptr;
         std::vector<Lane> lanes;
         bool busy = false, timed = false;
         double audio = 0;
@@ -142,6 +146,8 @@ class Engine {
     std::mutex mu_;
     std::condition_variable cv_work_, cv_done_;
     std::deque<std::shared_ptr<Stream>> ready_;
+    const int16_t *resident_audio_ = nullptr;  // set for the duration of run_resident
+    int resident_stride_ = 0;
     long long outstanding_ = 0;  // chunks pushed and not yet completed
     bool stop_ = false;
     std::thread thread_;

@@ -100,6 +100,7 @@ struct GraphDev {
     const int *e_begin;      // [S+1]
     const int *eps_begin;    // [S]
     const int4 *arcs;        // {weight bits, nextstate, pdf, olabel}
+    const int2 *state_arcs;  // [S+1] {first emitting arc, first epsilon arc}; epsilon arcs of s end at state_arcs[s+1].x
 };
 struct DecChannelState {     // one per channel
     int n_cur, parity, frame, error;
@@ -132,14 +133,13 @@ struct DecArgs {
     int *hash_key;           // [G][hash_size]
     unsigned long long *hash_val;
     int *hash_tok;
-    unsigned long long *cand_packed;  // [G][cand_cap]
-    int *cand_slot;
-    int *cand_src;
+    int4 *cand;              // [G][cand_cap] {packed lo, packed hi, table slot, source}
     int *rank;               // [G][tok_cap]
     int *sv_pref, *sv_a0, *sv_src;    // [G][tok_cap] expandable survivors: arc prefix, first arc, log index
     float *sv_cost;
     int *win_owner;          // [G][cand_cap/32+2] survivor owning the first arc of each 32-arc window
     unsigned long long *counters;     // [8] profiling counters (tokens, arcs, ...)
+    int *lane_load;          // [lanes] largest token count a lane saw in this launch (load feedback)
     int grid;
 };
 
@@ -152,7 +152,7 @@ cudaError_t vbk_gemm_fp32(const GemmArgs *a, cudaStream_t s);
 cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s);
 // encodes the TMA descriptor ([N][K] fp32, box 32 x min(N,256), SWIZZLE_128B) of a weight matrix into out128
 cudaError_t vbk_make_weight_map(const float *w, int N, int K, void *out128);
-cudaError_t vbk_decode(const DecArgs *a, cudaStream_t s);
+cudaError_t vbk_decode(const DecArgs *a, int heavy, cudaStream_t s);
 int vbk_decode_max_grid(int device);
 // copies rows [t_begin, t_begin+n) of a node ring for one channel into dst (debug capture / tests)
 cudaError_t vbk_copy_rows(NodeDesc node, int channel, int t_begin, int n_rows, float *dst, cudaStream_t s);
