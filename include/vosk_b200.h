@@ -37,6 +37,9 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model);
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n);
 void vosk_batch_model_reset_stats(VoskBatchModel *model);
 void vosk_batch_model_set_timing(VoskBatchModel *model, int on);
+/* Number of pipeline slots (lane groups in flight) to use, 1..pipeline-slots; 1 serializes the steps so that
+ * the per-stage device times of vosk_batch_model_stats are free of overlap. */
+void vosk_batch_model_set_slots(VoskBatchModel *model, int n);
 
 /* Device-resident run (kernel-level measurement): uploads the num_streams x samples_per_stream int16
  * matrix to HBM (untimed), then decodes all streams in lockstep with no host<->device sample traffic

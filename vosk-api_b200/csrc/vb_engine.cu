@@ -295,6 +295,7 @@ void Engine::alloc_state() {
     d.grid = std::min(vbk_decode_max_grid(cfg_.device), L);
     // pipeline slots: stream, staging, per-step tables, search scratch
     slots_.resize(cfg_.pipeline_slots);
+    active_slots_ = cfg_.pipeline_slots;
     for (Slot &sl : slots_) {
         VB_CUDA_CHECK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         for (auto &ev : sl.ev) VB_CUDA_CHECK(cudaEventCreate(&ev));
@@ -417,10 +418,8 @@ void Engine::worker() {
                 have_ready = !ready_.empty();
             }
             if (have_ready)
-                for (int k = 0; k < (int)slots_.size() && pick < 0; k++) {
-                    int i = (cur + k) % (int)slots_.size();
+                for (int i = 0; i < active_slots_.load() && pick < 0; i++)
                     if (!slots_[i].busy) pick = i;
-                }
         }
         if (pick < 0) {
             std::this_thread::yield();

@@ -80,6 +80,8 @@ class Engine {
     StepStats stats();
     void reset_stats();
     void set_timing(bool on) { timing_ = on; }
+    // limits the number of pipeline slots in use (1 = fully serialized steps: per-kernel timings without overlap)
+    void set_active_slots(int n) { active_slots_ = std::max(1, std::min(n, (int)slots_.size())); }
 
     // Device-resident run for kernel-level benchmarking: `audio` holds num_streams x samples int16 already in
     // HBM; processes every stream chunk by chunk with no host<->device sample traffic.  Returns device ms.
@@ -123,6 +125,7 @@ class Engine {
     cudaStream_t stream_ = nullptr;  // setup / utility stream
     std::vector<Slot> slots_;
     bool timing_ = false;
+    std::atomic<int> active_slots_{1};
     // model on device
     FeatTables feat_tab_{};
     IvecModel iv_model_{};

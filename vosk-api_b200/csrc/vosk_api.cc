@@ -166,6 +166,12 @@ void vosk_batch_model_set_timing(VoskBatchModel *model, int on) {
     for (size_t i = 0; i < bm->num_engines(); i++) bm->engine(i).set_timing(on != 0);
 }
 
+void vosk_batch_model_set_slots(VoskBatchModel *model, int n) {
+    if (!model) return;
+    BatchModel *bm = (BatchModel *)model;
+    for (size_t i = 0; i < bm->num_engines(); i++) bm->engine(i).set_active_slots(n);
+}
+
 double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream,
                                      const int *lengths) {
     if (!model || !audio || num_streams <= 0 || samples_per_stream <= 0) return -1.0;

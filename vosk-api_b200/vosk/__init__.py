@@ -92,6 +92,9 @@ class BatchModel(object):
     def SetTiming(self, on):
         _c.vosk_batch_model_set_timing(self._handle, int(on))
 
+    def SetSlots(self, n):
+        _c.vosk_batch_model_set_slots(self._handle, int(n))
+
     def RunResident(self, audio, lengths=None):
         """audio: C-contiguous int16 numpy array [streams, samples] (+ optional valid length per row);
         returns (device_ms, [result text])."""
