@@ -115,6 +115,23 @@ def e2e_pass(vosk, model, pieces, wait_each_round=False):
     return texts
 
 
+def reduce_over_ranks(x, op="max", device="cpu"):
+    """Max / sum of a python float over the ranks of the default process group (identity when not distributed)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(x)
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def job_throughput(audio_seconds_local, seconds_local, device="cpu"):
+    """Whole-job metric: streams are sharded by utterance with no exchange, so the job decodes the SUM of the ranks'
+    audio in the MAX of the ranks' times."""
+    return reduce_over_ranks(audio_seconds_local, "sum", device) / reduce_over_ranks(seconds_local, "max", device)
+
+
 def run_oracle_sample(n_streams, threads):
     """CPU restatement of the reference recognizer path on a bounded sample; returns (audio_s, wall_s)."""
     import oracle
@@ -204,11 +221,7 @@ def main():
             torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return reduce_over_ranks(x, "max", "cuda")
 
     # ---------------- value: device-resident ----------------
     texts = None
@@ -237,7 +250,7 @@ def main():
     model.SetSlots(64)
     model.SetTiming(False)
     dev_s = max_over_ranks(dev_ms / 1000.0)
-    value = world * audio_s * a.steps / dev_s
+    value = reduce_over_ranks(audio_s, "sum", "cuda") * a.steps / dev_s
 
     # ---------------- e2e: through the C ABI with host buffers ----------------
     pieces = [[w[i:i + 4000].tobytes() for i in range(0, len(w), 4000)] for w in waves]  # 8000-byte reads, as the reference driver
@@ -250,7 +263,7 @@ def main():
         e2e_texts = e2e_pass(vosk, model, pieces, a.wait_each_round)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * audio_s * a.steps / e2e_s
+    e2e_value = reduce_over_ranks(audio_s, "sum", "cuda") * a.steps / e2e_s
     same = sum(1 for x, y in zip(texts, e2e_texts) if x == y)
 
     # ---------------- roofline of the dominant kernel ----------------
@@ -302,7 +315,7 @@ def main():
                 "roofline_note": "stage durations from one extra pass with the pipeline slots serialized (no overlap); CUDA events on the launching stream",
                 "host_wall_ms_per_step_resident": wall_resident * 1000.0 / a.steps,
                 "search_counters_per_step": {"tokens": T, "arcs_emitting": Ae, "arcs_epsilon": Aeps, "tokens_new": N},
-                "audio_seconds_per_step": world * audio_s}
+                "audio_seconds_per_step": reduce_over_ranks(audio_s, "sum", "cuda")}
         print(json.dumps(line))
     del model
     if world > 1:

@@ -57,6 +57,16 @@ const char *vosk_batch_model_resident_result(VoskBatchModel *model, int stream);
 void vosk_batch_recognizer_debug_capture(VoskBatchRecognizer *recognizer);
 int64_t vosk_batch_recognizer_debug_get(VoskBatchRecognizer *recognizer, const char *what, void *out, int64_t cap_bytes);
 
+/* Host-only hooks (no GPU needed; used by the CPU test suite).
+ * device_for_stream: the utterance -> GPU sharding rule (stream id modulo the number of engines).
+ * format_result: the engine's result-text writer on explicit words (frames are 30 ms decoder frames).
+ * resample: the per-call resampler of accept_waveform (Kaldi LinearResample, flush=true) to 16 kHz.
+ * model_check: loads a model directory with the engine's loaders and prints a one-line summary. */
+int vosk_b200_device_for_stream(unsigned long long stream_id, int num_devices);
+int vosk_b200_format_result(const char *const *words, const int *begin, const int *end, const float *conf, int n, float offset, char *out, int cap);
+int vosk_b200_resample(const float *in, int n, float rate_in, float *out, int cap);
+int vosk_b200_model_check(const char *model_dir, char *out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

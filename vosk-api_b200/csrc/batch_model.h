@@ -21,6 +21,7 @@ class BatchModel {
     uint64_t GetID(BatchRecognizer *recognizer);  // [REF src/batch_model.cc:102-104] (atomic here)
     void WaitForCompletion();                     // [REF src/batch_model.cc:118-121]
 
+    // utterance sharding: streams are independent, so a stream lives on engine (id mod #GPUs); no collective
     vb::Engine &engine_for(uint64_t id) { return *engines_[id % engines_.size()]; }
     const vb::Model &model() const { return model_; }
     int samples_per_chunk() const { return samples_per_chunk_; }

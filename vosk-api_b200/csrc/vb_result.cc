@@ -72,9 +72,9 @@ static std::string joined(const Model &m, const std::vector<WordSpan> &w) {
     return text;
 }
 
-std::string result_json(const Model &m, const std::vector<WordSpan> &w, float offset) {
+std::string result_json_words(const std::vector<std::string> &ws, const std::vector<WordSpan> &w, float offset) {
     // keys come out alphabetically (std::map in json.h), floats as "%f", arrays inline, 2-space pad per depth
-    std::string s = "{\n";
+    std::string s = "{\n", text;
     if (!w.empty()) {
         s += "  \"result\" : [";
         for (size_t i = 0; i < w.size(); i++) {
@@ -85,12 +85,20 @@ std::string result_json(const Model &m, const std::vector<WordSpan> &w, float of
             s += "{\n      \"conf\" : " + std::to_string((double)w[i].conf);
             s += ",\n      \"end\" : " + std::to_string(en);
             s += ",\n      \"start\" : " + std::to_string(st);
-            s += ",\n      \"word\" : \"" + escape(word_str(m, w[i].word)) + "\"\n    }";
+            s += ",\n      \"word\" : \"" + escape(ws[i]) + "\"\n    }";
+            if (i) text += ' ';
+            text += ws[i];
         }
         s += "],\n";
     }
-    s += "  \"text\" : \"" + escape(joined(m, w)) + "\"\n}";
+    s += "  \"text\" : \"" + escape(text) + "\"\n}";
     return s;
+}
+
+std::string result_json(const Model &m, const std::vector<WordSpan> &w, float offset) {
+    std::vector<std::string> ws;
+    for (auto &x : w) ws.push_back(word_str(m, x.word));
+    return result_json_words(ws, w, offset);
 }
 
 std::string partial_json(const Model &m, const std::vector<WordSpan> &w) {

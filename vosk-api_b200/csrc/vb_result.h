@@ -18,6 +18,8 @@ struct WordSpan {
 
 std::vector<WordSpan> align_words(const Model &m, const std::vector<int> &arcs);
 std::string result_json(const Model &m, const std::vector<WordSpan> &words, float offset_seconds);
+// same text from explicit word strings (host-only test hook of include/vosk_b200.h)
+std::string result_json_words(const std::vector<std::string> &words, const std::vector<WordSpan> &spans, float offset_seconds);
 std::string result_nlsml(const Model &m, const std::vector<WordSpan> &words);
 std::string partial_json(const Model &m, const std::vector<WordSpan> &words);
 

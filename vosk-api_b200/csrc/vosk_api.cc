@@ -228,4 +228,53 @@ int64_t vosk_batch_recognizer_debug_get(VoskBatchRecognizer *recognizer, const c
     return bytes;
 }
 
+// ---------------------------------------------------------------------------------- host-only hooks (no GPU)
+int vosk_b200_device_for_stream(unsigned long long stream_id, int num_devices) {
+    return num_devices > 0 ? (int)(stream_id % (unsigned long long)num_devices) : 0;
+}
+
+int vosk_b200_format_result(const char *const *words, const int *begin, const int *end, const float *conf, int n, float offset, char *out, int cap) {
+    std::vector<std::string> ws;
+    std::vector<vb::WordSpan> sp;
+    for (int i = 0; i < n; i++) {
+        ws.push_back(words[i]);
+        sp.push_back(vb::WordSpan{i, begin[i], end[i], conf[i]});
+    }
+    std::string s = vb::result_json_words(ws, sp, offset);
+    if (out && cap > 0) {
+        size_t k = s.size() < (size_t)cap - 1 ? s.size() : (size_t)cap - 1;
+        memcpy(out, s.data(), k);
+        out[k] = 0;
+    }
+    return (int)s.size();
+}
+
+int vosk_b200_resample(const float *in, int n, float rate_in, float *out, int cap) {
+    vb::LinearResampler rs(rate_in, 16000.0f, std::min(rate_in / 2, 8000.0f), 6);
+    std::vector<float> vin(in, in + n), vout;
+    rs.resample_flush(vin, &vout);
+    for (size_t i = 0; i < vout.size() && (int)i < cap; i++) out[i] = vout[i];
+    return (int)vout.size();
+}
+
+int vosk_b200_model_check(const char *model_dir, char *out, int cap) {
+    try {
+        vb::Model m;
+        m.load(model_dir ? model_dir : "model");
+        vb::Config cfg;
+        m.apply_conf(&cfg);
+        double wsum = 0;
+        for (float w : m.graph.arc_w) wsum += w;
+        int n_eps = 0;
+        for (int p : m.graph.arc_pdf) n_eps += p < 0;
+        snprintf(out, cap, "states=%d arcs=%d eps=%d start=%d wsum=%.3f ops=%zu context=%d pdfs=%d words=%zu beam=%g max_active=%d fpc=%d gauss=%d",
+                 m.graph.num_states, m.graph.num_arcs, n_eps, m.graph.start, wsum, m.ops.size(), m.context, m.num_pdfs, m.words.size(),
+                 cfg.beam, cfg.max_active, cfg.frames_per_chunk, m.num_gauss);
+        return 0;
+    } catch (const std::exception &e) {
+        snprintf(out, cap, "error: %s", e.what());
+        return -1;
+    }
+}
+
 }  // extern "C"
