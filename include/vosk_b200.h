@@ -32,7 +32,7 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model);
  * [0] audio seconds, [1] steps, [2] lanes, [3] kernel launches, [4] tokens expanded,
  * [5] emitting arcs, [6] epsilon arcs, [7] tokens created, [8..11] device ms features / i-vector /
  * network / search (only when timing is on), [12] GEMM launches, [13] sum and [14] max of the SM cycles
- * one lane spent in a search launch, [15] largest token count of a frame, [16] lane-launches.
+ * one lane spent in a search launch, [15] largest token count of a frame, [16] lane-launches, [17] host ms spent enqueueing steps.
  * Returns the number written. */
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n);
 void vosk_batch_model_reset_stats(VoskBatchModel *model);

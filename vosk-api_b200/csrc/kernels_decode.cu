@@ -357,7 +357,7 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
 }  // namespace
 
 template <int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : 1) decode_kernel(DecArgs a) {
+__global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 2 : 1) decode_kernel(DecArgs a) {
     extern __shared__ __align__(16) float s_ll[];  // [npdf floats | level-1 values u64[kSmemSlots] | level-1 keys int[kSmemSlots]]
     __shared__ Shared<NT> sh;
     const int tid = threadIdx.x;
@@ -719,21 +719,27 @@ extern "C" int vbk_decode_max_grid(int device) {
     return sms * kDecBlocksPerSM;
 }
 
-// heavy != 0: 1024-thread CTAs (one per SM) for batches whose lanes carry thousands of tokens per frame — the
+// heavy = threads per CTA (256 / 512 / 1024): 1024-thread CTAs (one per SM) for batches whose lanes carry thousands of tokens per frame — the
 // per-frame critical path of such a lane is what bounds the step, so it gets 4x the threads.
 extern "C" cudaError_t vbk_decode(const DecArgs *a, int heavy, cudaStream_t s) {
     if (a->num_lanes <= 0) return cudaSuccess;
     int smem = ((a->out_node.dim + 3) & ~3) * 4 + kSmemSlots * 12;
     int grid = a->num_lanes < a->grid ? a->num_lanes : a->grid;
-    if (heavy) {
-        cudaError_t e = cudaFuncSetAttribute(decode_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    // the opt-in shared-memory size is a per-device function attribute: set it once per (variant, device, size)
+    static int done[3][16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int v = heavy >= 1024 ? 2 : heavy >= 512 ? 1 : 0;
+    if (dev < 16 && done[v][dev] < smem) {
+        cudaError_t e = v == 2   ? cudaFuncSetAttribute(decode_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                        : v == 1 ? cudaFuncSetAttribute(decode_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                 : cudaFuncSetAttribute(decode_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        decode_kernel<1024><<<grid, 1024, smem, s>>>(*a);
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(decode_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        decode_kernel<256><<<grid, 256, smem, s>>>(*a);
+        done[v][dev] = smem;
     }
+    if (v == 2) decode_kernel<1024><<<grid, 1024, smem, s>>>(*a);
+    else if (v == 1) decode_kernel<512><<<grid, 512, smem, s>>>(*a);
+    else decode_kernel<256><<<grid, 256, smem, s>>>(*a);
     return cudaGetLastError();
 }
 

@@ -144,12 +144,14 @@ __global__ void __launch_bounds__(kFeatThreads) mfcc_kernel(FeatArgs a) {
 
 extern "C" cudaError_t vbk_mfcc(const FeatArgs *a, cudaStream_t s) {
     if (a->num_lanes <= 0) return cudaSuccess;
-    static int configured = 0;
+    static int configured[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
     int smem = vbk_feat_smem_bytes(a->samples_per_chunk);
-    if (configured < smem) {
+    if (dev < 16 && configured[dev] < smem) {
         cudaError_t e = cudaFuncSetAttribute(mfcc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[dev] = smem;
     }
     mfcc_kernel<<<a->num_lanes, kFeatThreads, smem, s>>>(*a);
     return cudaGetLastError();
@@ -404,11 +406,13 @@ extern "C" cudaError_t vbk_ivector(const IvecArgs *a, cudaStream_t s) {
     if (a->num_lanes <= 0) return cudaSuccess;
     if (a->m.num_gauss > 1024 || a->m.ivec_dim > 32 * kMaxIvecPerLane || a->m.num_gselect > kMaxGselect) return cudaErrorInvalidValue;
     int smem = ivec_smem_bytes(a->m.num_gauss, a->m.splice_dim, a->m.feat_dim, a->m.ivec_dim);
-    static int configured = 0;
-    if (configured < smem) {
+    static int configured[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && configured[dev] < smem) {
         cudaError_t e = cudaFuncSetAttribute(ivector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[dev] = smem;
     }
     ivector_kernel<<<a->num_lanes, kIvThreads, smem, s>>>(*a);
     return cudaGetLastError();

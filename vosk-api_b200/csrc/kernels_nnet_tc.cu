@@ -364,8 +364,14 @@ extern "C" cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s) {
     int tmem_cols = 32;
     while (tmem_cols < (n_main + 1) * BN) tmem_cols <<= 1;  // n_main hi*hi accumulators + one for the small cross terms
     const int smem = (int)(stage_bytes * stages + 1024);
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
+    static int done[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && done[dev] < smem) {  // per-device function attribute: raise it only when a larger tile set is needed
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        done[dev] = smem;
+    }
     dim3 grid((a->max_rows + TM - 1) / TM, (op.N + BN - 1) / BN);
     TensorMapBlob mh, ml;
     memcpy(mh.b, a->map_hi, 128);

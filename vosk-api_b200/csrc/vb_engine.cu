@@ -2,6 +2,7 @@
 #include "vb_engine.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 
@@ -506,6 +507,7 @@ void Engine::worker() {
 }
 
 void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_stride) {
+    const auto host_t0 = std::chrono::steady_clock::now();
     std::vector<Lane> &lanes = sl.lanes;
     const int L = (int)lanes.size();
     const int ctx = model_.context, spc = samples_per_chunk();
@@ -591,7 +593,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     sl.dec.num_lanes = L;
     int max_load = 0;
     for (int i = 0; i < L; i++) max_load = std::max(max_load, lanes[i].s->load);
-    VB_CUDA_CHECK(vbk_decode(&sl.dec, max_load > cfg_.heavy_tokens ? 1 : 0, st));
+    VB_CUDA_CHECK(vbk_decode(&sl.dec, max_load > cfg_.heavy_tokens ? cfg_.heavy_threads : cfg_.light_threads, st));
     sl.launches++;
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[4], st));
     // results of finished lanes
@@ -606,6 +608,10 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         }
     VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_load, sl.d_load, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_CUDA_CHECK(cudaEventRecord(sl.done, st));
+    {
+        std::lock_guard<std::mutex> lk(stats_mu_);
+        stats_.host_launch_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+    }
 }
 
 void Engine::complete_step(Slot &sl) {

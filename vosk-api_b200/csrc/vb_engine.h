@@ -63,6 +63,7 @@ struct StepStats {
     unsigned long long lane_cycles_sum = 0, lane_cycles_max = 0, max_tokens = 0, lane_launches = 0;
     double t_feat = 0, t_ivec = 0, t_nnet = 0, t_dec = 0, t_total = 0;  // device ms (only when timing enabled)
     long long dec_launches = 0, gemm_launches = 0;
+    double host_launch_ms = 0;  // host time spent enqueueing steps
 };
 
 class Engine {

@@ -143,15 +143,15 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model) { return model ? (
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
     if (!model || !out) return 0;
     BatchModel *bm = (BatchModel *)model;
-    double v[17] = {0};
+    double v[18] = {0};
     for (size_t i = 0; i < bm->num_engines(); i++) {
         vb::StepStats s = bm->engine(i).stats();
         v[0] += s.audio_seconds; v[1] += s.steps; v[2] += s.lanes; v[3] += s.launches;
         v[4] += s.tok; v[5] += s.arc_e; v[6] += s.arc_eps; v[7] += s.tok_new;
         v[8] += s.t_feat; v[9] += s.t_ivec; v[10] += s.t_nnet; v[11] += s.t_dec; v[12] += s.gemm_launches;
-        v[13] += s.lane_cycles_sum; v[14] = std::max(v[14], (double)s.lane_cycles_max); v[15] = std::max(v[15], (double)s.max_tokens); v[16] += s.lane_launches;
+        v[13] += s.lane_cycles_sum; v[14] = std::max(v[14], (double)s.lane_cycles_max); v[15] = std::max(v[15], (double)s.max_tokens); v[16] += s.lane_launches; v[17] += s.host_launch_ms;
     }
-    int k = n < 17 ? n : 17;
+    int k = n < 18 ? n : 18;
     memcpy(out, v, k * sizeof(double));
     return k;
 }
