@@ -151,9 +151,8 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
             row_slot[it] = (ts.row_t[r] - a.in.t_start) / a.in.step;
         }
         const int ring_mask = a.in.ring - 1;
-        for (int kb = 0; kb < nkb; kb++) {
-            const int s = kb % stages;
-            const uint32_t par = (uint32_t)((kb / stages) & 1);
+        // gather of one K-block into registers (8 independent 16-byte requests per thread)
+        auto gather = [&](int kb, float4 *v) {
             const int k = kb * TK + c * 4;
             const bool in_k = k < op.K, is_iv = k >= spliced;
             int seg = 0, col = 0;
@@ -162,7 +161,6 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
                 col = k - seg * in_dim;
             }
             const int off_rows = in_k && !is_iv ? op.offs[seg] / a.in.step : 0;  // offsets are multiples of the input step
-            float4 v[RPT];
 #pragma unroll
             for (int it = 0; it < RPT; it++) {
                 v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -172,6 +170,13 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
                     v[it] = __ldg(reinterpret_cast<const float4 *>(src));
                 }
             }
+        };
+        float4 v[RPT], vn[RPT];
+        gather(0, v);
+        for (int kb = 0; kb < nkb; kb++) {
+            const int s = kb % stages;
+            const uint32_t par = (uint32_t)((kb / stages) & 1);
+            if (kb + 1 < nkb) gather(kb + 1, vn);  // software pipelining: the next block's loads fly while this one is split and stored
             mbar_wait(&ts.empty[s], par ^ 1);
             const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + TM * 128;
 #pragma unroll
@@ -189,6 +194,8 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA (async proxy)
             mbar_arrive(&ts.full[s]);
+#pragma unroll
+            for (int it = 0; it < RPT; it++) v[it] = vn[it];
         }
         // =========================== epilogue ===========================
         mbar_wait(&ts.accum, 0);
