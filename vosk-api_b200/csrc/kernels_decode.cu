@@ -360,8 +360,9 @@ template <int NT>
 __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 2 : 1) decode_kernel(DecArgs a) {
     extern __shared__ __align__(16) float s_ll[];  // [npdf floats | level-1 values u64[kSmemSlots] | level-1 keys int[kSmemSlots]]
     __shared__ Shared<NT> sh;
+    __shared__ int s_lane;
     const int tid = threadIdx.x;
-    const size_t g = blockIdx.x;
+    const size_t g = (size_t)a.scratch_base + blockIdx.x;
     const int nwin_cap = a.cand_cap / 32 + 2;
     unsigned long long *s_val = reinterpret_cast<unsigned long long *>(s_ll + ((a.out_node.dim + 3) & ~3));
     int *s_key = reinterpret_cast<int *>(s_val + kSmemSlots);
@@ -378,7 +379,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
           tid, tid >> 5, tid & 31, true, (unsigned)a.hash_size - 1};
     unsigned long long cnt_tok = 0, cnt_arc_e = 0, cnt_arc_eps = 0, cnt_new = 0;  // per-thread profiling counters
     const int npdf = a.out_node.dim;
-    for (int l = blockIdx.x; l < a.num_lanes; l += gridDim.x) {
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_lane = a.lane_begin + atomicAdd(a.queue, 1);
+        __syncthreads();
+        const int l = s_lane;
+        if (l >= a.lane_end) break;
         const LaneDesc ln = a.lanes[l];
         const int ch = ln.channel;
         const long long clk0 = clock64();
@@ -722,15 +728,22 @@ extern "C" int vbk_decode_max_grid(int device) {
 // heavy = threads per CTA (256 / 512 / 1024): 1024-thread CTAs (one per SM) for batches whose lanes carry thousands of tokens per frame — the
 // per-frame critical path of such a lane is what bounds the step, so it gets 4x the threads.
 extern "C" cudaError_t vbk_decode(const DecArgs *a, int heavy, cudaStream_t s) {
-    if (a->num_lanes <= 0) return cudaSuccess;
+    const int n = a->lane_end - a->lane_begin;
+    if (n <= 0) return cudaSuccess;
     int smem = ((a->out_node.dim + 3) & ~3) * 4 + kSmemSlots * 12;
-    int grid = a->num_lanes < a->grid ? a->num_lanes : a->grid;
+    static int sms[16] = {};
     // the opt-in shared-memory size is a per-device function attribute: set it once per (variant, device, size)
     static int done[3][16] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     const int v = heavy >= 1024 ? 2 : heavy >= 512 ? 1 : 0;
-    if (dev < 16 && done[v][dev] < smem) {
+    if (dev >= 16) return cudaErrorInvalidDevice;
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    int grid = sms[dev] * (v == 2 ? 1 : v == 1 ? 2 : kDecBlocksPerSM);
+    if (grid > n) grid = n;
+    if (grid > a->grid - a->scratch_base) grid = a->grid - a->scratch_base;
+    if (grid <= 0) return cudaErrorInvalidValue;
+    if (done[v][dev] < smem) {
         cudaError_t e = v == 2   ? cudaFuncSetAttribute(decode_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
                         : v == 1 ? cudaFuncSetAttribute(decode_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
                                  : cudaFuncSetAttribute(decode_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

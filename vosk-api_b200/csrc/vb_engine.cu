@@ -74,6 +74,9 @@ Engine::~Engine() {
         if (sl.h_load) cudaFreeHost(sl.h_load);
         for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
         if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.fork) cudaEventDestroy(sl.fork);
+        if (sl.join) cudaEventDestroy(sl.join);
+        if (sl.stream2) cudaStreamDestroy(sl.stream2);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (h_capture_) cudaFreeHost(h_capture_);
@@ -301,6 +304,10 @@ void Engine::alloc_state() {
         VB_CUDA_CHECK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         for (auto &ev : sl.ev) VB_CUDA_CHECK(cudaEventCreate(&ev));
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        VB_CUDA_CHECK(cudaStreamCreateWithFlags(&sl.stream2, cudaStreamNonBlocking));
+        VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.fork, cudaEventDisableTiming));
+        VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.join, cudaEventDisableTiming));
+        sl.d_queue = dev_alloc<int>(allocs_, 2, 0);
         sl.d_staging = dev_alloc<int16_t>(allocs_, (size_t)L * spc, 0);
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_staging, (size_t)L * spc * sizeof(int16_t)));
         sl.d_lanes = dev_alloc<LaneDesc>(allocs_, (size_t)L, 0);
@@ -514,6 +521,9 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     const int nn = (int)nodes_.size();
     const int SL = slot_lanes_;
     cudaStream_t st = sl.stream;
+    // heaviest lanes first: the search kernels pull lanes from a queue in this order (longest first), and the lanes
+    // above heavy_tokens form a prefix that gets the 1024-thread CTAs
+    std::stable_sort(lanes.begin(), lanes.end(), [](const Lane &x, const Lane &y) { return x.s->load > y.s->load; });
     sl.audio = 0;
     long long in_rows = 0;
     for (int i = 0; i < L; i++) {
@@ -591,10 +601,35 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[3], st));
     sl.dec.lanes = sl.d_lanes;
     sl.dec.num_lanes = L;
-    int max_load = 0;
-    for (int i = 0; i < L; i++) max_load = std::max(max_load, lanes[i].s->load);
-    VB_CUDA_CHECK(vbk_decode(&sl.dec, max_load > cfg_.heavy_tokens ? cfg_.heavy_threads : cfg_.light_threads, st));
-    sl.launches++;
+    int n_heavy = 0;
+    while (n_heavy < L && lanes[n_heavy].s->load > cfg_.heavy_tokens) n_heavy++;
+    VB_CUDA_CHECK(cudaMemsetAsync(sl.d_queue, 0, 2 * sizeof(int), st));
+    sl.dec.queue = sl.d_queue;
+    sl.dec.lane_begin = 0;
+    sl.dec.lane_end = n_heavy;
+    sl.dec.scratch_base = 0;
+    const bool split = n_heavy > 0 && n_heavy < L;
+    if (split) {  // the light lanes run beside the heavy ones on the slot's second stream
+        VB_CUDA_CHECK(cudaEventRecord(sl.fork, st));
+        VB_CUDA_CHECK(cudaStreamWaitEvent(sl.stream2, sl.fork, 0));
+    }
+    if (n_heavy > 0) {
+        VB_CUDA_CHECK(vbk_decode(&sl.dec, cfg_.heavy_threads, st));
+        sl.launches++;
+    }
+    if (n_heavy < L) {
+        DecArgs light = sl.dec;
+        light.queue = sl.d_queue + 1;
+        light.lane_begin = n_heavy;
+        light.lane_end = L;
+        light.scratch_base = std::min(n_heavy, vbk_decode_max_grid(cfg_.device) / (cfg_.heavy_threads >= 1024 ? 3 : 1));  // CTAs the heavy launch can have
+        VB_CUDA_CHECK(vbk_decode(&light, cfg_.light_threads, split ? sl.stream2 : st));
+        sl.launches++;
+        if (split) {
+            VB_CUDA_CHECK(cudaEventRecord(sl.join, sl.stream2));
+            VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.join, 0));
+        }
+    }
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[4], st));
     // results of finished lanes
     int n_last = 0;

@@ -98,7 +98,9 @@ class Engine {
     // data and the per-channel state of disjoint streams, so kernels of different slots overlap on the GPU
     // (a latency-bound search launch of one group runs under the GEMMs / feature kernels of another).
     struct Slot {
-        cudaStream_t stream = nullptr;
+        cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: the light-lane search launch of a step (forked/joined by events)
+        cudaEvent_t fork = nullptr, join = nullptr;
+        int *d_queue = nullptr;  // [2] lane queues of the two search launches
         cudaEvent_t ev[5] = {};
         cudaEvent_t done = nullptr;
         int16_t *d_staging = nullptr, *h_staging = nullptr;

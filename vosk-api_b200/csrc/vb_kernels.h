@@ -140,7 +140,12 @@ struct DecArgs {
     int *win_owner;          // [G][cand_cap/32+2] survivor owning the first arc of each 32-arc window
     unsigned long long *counters;     // [8] profiling counters (tokens, arcs, ...)
     int *lane_load;          // [lanes] largest token count a lane saw in this launch (load feedback)
-    int grid;
+    int grid;                // CTAs' worth of scratch allocated per slot
+    // one launch serves lanes [lane_begin, lane_end): CTAs pull the next lane from *queue (zeroed before the launch; lanes
+    // are sorted by descending load, so this is longest-processing-time-first list scheduling) and use scratch
+    // [scratch_base + blockIdx.x]; a step issues up to two launches (1024-thread CTAs for its heavy lanes, 256 for the rest)
+    int lane_begin, lane_end, scratch_base;
+    int *queue;
 };
 
 extern "C" {
