@@ -17,7 +17,8 @@ extern "C" {
 
 /* Like vosk_batch_model_new but with an explicit model directory and "key=value,key=value"
  * options: frames-per-chunk, max-batch-size, num-channels, beam, lattice-beam, max-active,
- * min-active, tok-cap, cand-cap, hash-size, max-seconds, log-tokens-per-frame, tensor-cores,
+ * min-active, tok-cap, cand-cap, hash-size, max-seconds, log-tokens-per-frame, tensor-cores, lattice,
+ * log-links-per-frame, lat-tok-cap, lat-link-cap, pipeline-slots, heavy-tokens,
  * debug-capture, devices (GPU indices separated by ':' or "all").
  * Env VOSK_BATCH_OPTIONS / VOSK_BATCH_DEVICES are applied first.  NULL on failure. */
 VoskBatchModel *vosk_batch_model_new_ex(const char *model_dir, const char *options);
@@ -32,7 +33,8 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model);
  * [0] audio seconds, [1] steps, [2] lanes, [3] kernel launches, [4] tokens expanded,
  * [5] emitting arcs, [6] epsilon arcs, [7] tokens created, [8..11] device ms features / i-vector /
  * network / search (only when timing is on), [12] GEMM launches, [13] sum and [14] max of the SM cycles
- * one lane spent in a search launch, [15] largest token count of a frame, [16] lane-launches, [17] host ms spent enqueueing steps.
+ * one lane spent in a search launch, [15] largest token count of a frame, [16] lane-launches, [17] host ms spent enqueueing steps,
+ * [18] arcs parked below the running cutoff, [19] lattice links logged, [20] lattice arcs kept after pruning.
  * Returns the number written. */
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n);
 void vosk_batch_model_reset_stats(VoskBatchModel *model);
@@ -52,7 +54,9 @@ const char *vosk_batch_model_resident_result(VoskBatchModel *model, int stream);
 
 /* Test taps.  Enable before the first accept_waveform on a model created with debug-capture=1;
  * after finish_stream + wait, fetch "mfcc" [T][40], "ivectors" [chunks][D], "loglikes" [N][pdfs] (f32),
- * "frame_off" [N+2], "tok_state", "tok_arc", "tok_prev" (i32), "tok_cost" (f32), "error" (i32).
+ * "frame_off" [N+2], "tok_state", "tok_arc", "tok_prev" (i32), "tok_cost" (f32), "error" (i32);
+ * with lattice=1 also "lat_hdr" {states, links, finals, start, error, frames}, "lat_links" [n][4] {src, dst, arc, acoustic
+ * cost bits}, "lat_final" [n][2] {state, final cost bits}, "lat_tok_frame", "lat_tok_state" (i32).
  * Returns the size in bytes (copies min(size, cap_bytes)), or -1 for an unknown name. */
 void vosk_batch_recognizer_debug_capture(VoskBatchRecognizer *recognizer);
 int64_t vosk_batch_recognizer_debug_get(VoskBatchRecognizer *recognizer, const char *what, void *out, int64_t cap_bytes);

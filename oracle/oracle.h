@@ -83,6 +83,13 @@ int64_t orc_decoder_num_tokens(const OrcDecoder *d);
 /* offsets[f] .. offsets[f+1] = tokens logged for frame f (f = 0..num_frames), sorted by state id */
 void orc_decoder_tokens(const OrcDecoder *d, int64_t *offsets, int *state, float *cost, int *arc, int64_t *prev);
 int orc_decoder_best_path(const OrcDecoder *d, int *arcs, int cap, float *total_cost, int *reached_final);
+/* raw lattice after FinalizeDecoding's lattice_beam pruning (GetRawLattice): lattice states = surviving tokens in log
+ * order (tok_index maps them to token indices of orc_decoder_tokens), links {src, dst, csr arc, acoustic cost}, final
+ * states with their final costs.  Returns the number of links (writes at most cap_links). */
+int64_t orc_decoder_num_links(const OrcDecoder *d);
+int64_t orc_decoder_lattice(const OrcDecoder *d, const OrcGraph *g, float lattice_beam, int64_t *n_states, int64_t *tok_index,
+                            int64_t *lsrc, int64_t *ldst, int *larc, float *lac, int64_t cap_links,
+                            int64_t *fin_state, float *fin_cost, int64_t *n_final);
 
 /* ---- result text (PushLattice for a linear lattice [REF src/batch_recognizer.cc:43-107]) ---- */
 typedef struct {

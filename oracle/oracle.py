@@ -208,8 +208,30 @@ def decode(model, loglikes, **over):
         tot = C.c_float()
         rf = C.c_int()
         n = L.orc_decoder_best_path(h, _p(arcs), cap, C.byref(tot), C.byref(rf))
-        return dict(frames=nf, offsets=offsets, state=state, cost=cost, arc=arc, prev=prev,
-                    best_arcs=arcs[:n].copy(), best_cost=tot.value, reached_final=bool(rf.value))
+        out = dict(frames=nf, offsets=offsets, state=state, cost=cost, arc=arc, prev=prev,
+                   best_arcs=arcs[:n].copy(), best_cost=tot.value, reached_final=bool(rf.value))
+        if "lattice_beam" in over or "lattice-beam" in model["conf"]:
+            lb = float(over.get("lattice_beam", model["conf"].get("lattice-beam", 6.0)))
+            L.orc_decoder_num_links.restype = C.c_int64
+            L.orc_decoder_lattice.restype = C.c_int64
+            cap = int(L.orc_decoder_num_links(h))
+            tok_index = np.zeros(max(nt, 1), dtype=np.int64)
+            lsrc = np.zeros(max(cap, 1), dtype=np.int64)
+            ldst = np.zeros(max(cap, 1), dtype=np.int64)
+            larc = np.zeros(max(cap, 1), dtype=np.int32)
+            lac = np.zeros(max(cap, 1), dtype=np.float32)
+            fst = np.zeros(max(nt, 1), dtype=np.int64)
+            fco = np.zeros(max(nt, 1), dtype=np.float32)
+            ns = C.c_int64()
+            nfin = C.c_int64()
+            nl = L.orc_decoder_lattice(h, C.byref(G), C.c_float(lb), C.byref(ns), _p(tok_index), _p(lsrc), _p(ldst), _p(larc), _p(lac),
+                                       C.c_int64(cap), _p(fst), _p(fco), C.byref(nfin))
+            frame_of = np.searchsorted(offsets, tok_index[:ns.value], side="right") - 1
+            out["lattice"] = dict(tok_index=tok_index[:ns.value].copy(), frame=frame_of.astype(np.int32),
+                                  state=state[tok_index[:ns.value]].copy(), src=lsrc[:nl].copy(), dst=ldst[:nl].copy(),
+                                  arc=larc[:nl].copy(), ac=lac[:nl].copy(), final_state=fst[:nfin.value].copy(),
+                                  final_cost=fco[:nfin.value].copy(), num_links_unpruned=cap)
+        return out
     finally:
         L.orc_decoder_free(h)
 

@@ -53,6 +53,10 @@ struct OrcDecoder {
     std::vector<int> best_arcs;
     float best_cost = kInf;
     int reached_final = 0;
+    // ForwardLinks of LatticeFasterDecoder: every arc taken below the frame's cutoff, endpoints as log indices
+    struct Link { int64_t src, dst; int arc; float ac; };
+    std::vector<Link> links;
+    std::vector<int64_t> link_off;  // segment f = links whose destination token is in frame f
 };
 
 namespace {
@@ -130,6 +134,17 @@ extern "C" OrcDecoder *orc_decode(const OrcGraph *g, const OrcDecodeOpts *o, con
     cur.relax(g->start, pack(0.f, -1));
     closure(g, cur, o->beam);
     d->offsets.push_back(0);
+    struct Pending { int64_t src_log; int src_state; int dst_state; int arc; float ac; };
+    std::vector<Pending> pending;  // links into the frontier that is logged next (src_state >= 0: epsilon link inside it)
+    auto eps_links = [&](Frontier &fr, float cutoff) {
+        // ProcessNonemitting: every token below the cutoff links to the target of each of its epsilon arcs below the cutoff
+        for (int s : fr.touched) {
+            float c = unord((uint32_t)(fr.best[s] >> 32));
+            if (c >= cutoff) continue;
+            for (int a = g->eps_begin[s]; a < g->e_begin[s + 1]; a++)
+                if (c + g->arc_w[a] < cutoff) pending.push_back({-1, s, g->arc_next[a], a, 0.f});
+        }
+    };
     auto log_frame = [&](Frontier &fr, float cutoff, bool all) {
         // survivors sorted by state id; resolves prev via the previous/current frame's maps
         std::vector<int> sv;
@@ -159,8 +174,17 @@ extern "C" OrcDecoder *orc_decode(const OrcGraph *g, const OrcDecodeOpts *o, con
             d->prev.push_back(pv);
         }
         d->offsets.push_back((int64_t)d->state.size());
+        // links into this frame: tokens that were not logged (they fail this frame's cutoff) take their links with them
+        d->link_off.push_back((int64_t)d->links.size());
+        for (const Pending &p : pending) {
+            int64_t src = p.src_state >= 0 ? log_index_cur[p.src_state] : p.src_log;
+            int64_t dst = log_index_cur[p.dst_state];
+            if (src >= 0 && dst >= 0) d->links.push_back({src, dst, p.arc, p.ac});
+        }
+        pending.clear();
         return sv;
     };
+    eps_links(cur, o->beam);
     int f = 0;
     for (; f < N; f++) {
         if (cur.touched.empty()) break;
@@ -188,14 +212,19 @@ extern "C" OrcDecoder *orc_decode(const OrcGraph *g, const OrcDecodeOpts *o, con
             for (int a = g->e_begin[s]; a < g->eps_begin[s]; a++) {
                 float ac = cost_offset - ll[g->arc_pdf[a]];
                 float tot = c + ac + g->arc_w[a];
-                if (tot < next_cutoff) nxt.relax(g->arc_next[a], pack(tot, a));
+                if (tot < next_cutoff) {
+                    nxt.relax(g->arc_next[a], pack(tot, a));
+                    pending.push_back({log_index_cur[s], -1, g->arc_next[a], a, ac});
+                }
             }
         }
         closure(g, nxt, next_cutoff);
+        eps_links(nxt, next_cutoff);
         std::swap(cur, nxt);
     }
     d->frames_decoded = f;
     log_frame(cur, kInf, true);
+    d->link_off.push_back((int64_t)d->links.size());
     // best path: minimum of (cost + final, state); if no final state is active, minimum of (cost, state)
     int64_t lo = d->offsets[d->offsets.size() - 2], hi = d->offsets.back();
     int64_t bi = -1;
@@ -239,6 +268,87 @@ extern "C" int orc_decoder_best_path(const OrcDecoder *d, int *arcs, int cap, fl
     if (reached_final) *reached_final = d->reached_final;
     return n;
 }
+
+// --------------------------------------------------------------------------------------------
+// raw lattice: LatticeFasterDecoder::FinalizeDecoding (PruneForwardLinksFinal, then PruneForwardLinks(delta = 0) and
+// PruneTokensForFrame for every earlier frame) + GetRawLattice, on the link log above.  Token extra costs start at 0
+// (Token constructor) and every frame is swept in list order until nothing changes, as Kaldi does; the final frame is
+// iterated to the exact fixed point (Kaldi stops it at a relative change of 1e-5).
+// --------------------------------------------------------------------------------------------
+extern "C" int64_t orc_decoder_lattice(const OrcDecoder *d, const OrcGraph *g, float lattice_beam, int64_t *n_states_out,
+                                       int64_t *tok_index /* [n_tokens] lattice state -> token index */,
+                                       int64_t *lsrc, int64_t *ldst, int *larc, float *lac, int64_t cap_links,
+                                       int64_t *fin_state, float *fin_cost, int64_t *n_final_out) {
+    const int64_t nt = (int64_t)d->state.size();
+    const int F = d->frames_decoded;
+    std::vector<float> extra(nt, 0.f);
+    std::vector<char> alive(d->links.size(), 1);
+    // links grouped by source token
+    std::vector<std::vector<int64_t>> out(nt);
+    for (size_t k = 0; k < d->links.size(); k++) out[d->links[k].src].push_back((int64_t)k);
+    auto link_extra = [&](const OrcDecoder::Link &l) {
+        float graph = g->arc_w[l.arc];
+        return extra[l.dst] + ((d->cost[l.src] + l.ac + graph) - d->cost[l.dst]);
+    };
+    for (int f = F; f >= 0; f--) {
+        bool changed = true;
+        while (changed) {
+            changed = false;
+            for (int64_t i = d->offsets[f]; i < d->offsets[f + 1]; i++) {
+                float tok_extra = kInf;
+                if (f == F) {
+                    float fc = d->reached_final ? g->final_cost[d->state[i]] : 0.f;
+                    tok_extra = d->cost[i] + fc - d->best_cost;
+                }
+                for (int64_t k : out[i]) {
+                    if (!alive[k]) continue;
+                    float le = link_extra(d->links[k]);
+                    if (le > lattice_beam) {
+                        alive[k] = 0;
+                    } else {
+                        if (le < 0.f) le = 0.f;
+                        if (le < tok_extra) tok_extra = le;
+                    }
+                }
+                if (f == F && tok_extra > lattice_beam) tok_extra = kInf;
+                if (tok_extra != extra[i]) changed = true;
+                extra[i] = tok_extra;
+            }
+        }
+    }
+    std::vector<int64_t> newidx(nt, -1);
+    int64_t ns = 0;
+    for (int64_t i = 0; i < nt; i++)
+        if (extra[i] != kInf) {
+            tok_index[ns] = i;
+            newidx[i] = ns++;
+        }
+    *n_states_out = ns;
+    int64_t nl = 0;
+    for (size_t k = 0; k < d->links.size(); k++) {
+        const OrcDecoder::Link &l = d->links[k];
+        if (!alive[k] || newidx[l.src] < 0 || newidx[l.dst] < 0) continue;
+        if (nl < cap_links) {
+            lsrc[nl] = newidx[l.src];
+            ldst[nl] = newidx[l.dst];
+            larc[nl] = l.arc;
+            lac[nl] = l.ac;
+        }
+        nl++;
+    }
+    int64_t nf = 0;
+    for (int64_t i = d->offsets[F]; i < d->offsets[F + 1]; i++) {
+        if (newidx[i] < 0) continue;
+        float fc = d->reached_final ? g->final_cost[d->state[i]] : 0.f;
+        if (fc == kInf) continue;
+        fin_state[nf] = newidx[i];
+        fin_cost[nf] = fc;
+        nf++;
+    }
+    *n_final_out = nf;
+    return nl;
+}
+extern "C" int64_t orc_decoder_num_links(const OrcDecoder *d) { return (int64_t)d->links.size(); }
 
 // --------------------------------------------------------------------------------------------
 // word alignment of a linear path and result text

@@ -42,6 +42,12 @@ def run_engine(model_dir, waves, options="", capture=True, bytes_per_call=8000):
                 d[k] = r.DebugGet(k, np.int32)
             d["tok_cost"] = r.DebugGet("tok_cost", np.float32)
             d["error"] = int(r.DebugGet("error", np.int32)[0])
+            if "lattice=1" in options:
+                d["lat_hdr"] = r.DebugGet("lat_hdr", np.int32)
+                d["lat_links"] = r.DebugGet("lat_links", np.int32).reshape(-1, 4)
+                d["lat_final"] = r.DebugGet("lat_final", np.int32).reshape(-1, 2)
+                d["lat_tok_frame"] = r.DebugGet("lat_tok_frame", np.int32)
+                d["lat_tok_state"] = r.DebugGet("lat_tok_state", np.int32)
         out.append(d)
     stats = model.Stats()
     del recs
@@ -62,6 +68,18 @@ def canonical_tokens(frame_off, state, cost, arc, prev):
     p = prev[order_all].astype(np.int64)
     p = np.where(p >= 0, new_index[np.maximum(p, 0)], p)
     return state[order_all], cost[order_all], arc[order_all], p
+
+
+def canonical_lattice(frame, state, src, dst, arc, ac_bits, final_state, final_bits):
+    """Order-free form of a raw lattice: states as sorted (frame, graph state), links as sorted
+    (src frame, src state, dst frame, dst state, arc, acoustic-cost bits), finals as sorted (frame, state, cost bits)."""
+    states = np.stack([frame, state], 1).astype(np.int64)
+    states = states[np.lexsort(states.T[::-1])]
+    links = np.stack([frame[src], state[src], frame[dst], state[dst], arc, ac_bits], 1).astype(np.int64)
+    links = links[np.lexsort(links.T[::-1])]
+    fin = np.stack([frame[final_state], state[final_state], final_bits], 1).astype(np.int64)
+    fin = fin[np.lexsort(fin.T[::-1])]
+    return states, links, fin
 
 
 def words_of(text):

@@ -15,7 +15,7 @@ def _waves(lengths, seed0=100):
     return [vbmodel.synth_audio(s, seed0 + i) for i, s in enumerate(lengths)]
 
 
-def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3):
+def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3, lattice_beam=6.0):
     ref = oracle.recognize(model, wave, frames_per_chunk=fpc, stages=True)
     D = int(model["cfg"]["ivector-dim"])
     P = int(model["cfg"]["num-pdfs"])
@@ -44,6 +44,20 @@ def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3):
         np.testing.assert_array_equal(co.view(np.uint32), dec["cost"].view(np.uint32))
         np.testing.assert_array_equal(pv, dec["prev"])
         assert got["text"] == oracle.result_json(model, dec["best_arcs"])
+        if "lat_hdr" in got:
+            # raw lattice (links within lattice_beam, FinalizeDecoding pruning): bit-exact in canonical order
+            lat = oracle.decode(model, ll, lattice_beam=lattice_beam)["lattice"]
+            hdr = got["lat_hdr"]
+            assert hdr[4] == 0, "lattice error %d" % hdr[4]
+            assert hdr[0] == len(lat["tok_index"]) and hdr[1] == len(lat["src"])
+            gl = got["lat_links"]
+            a = helpers.canonical_lattice(got["lat_tok_frame"], got["lat_tok_state"], gl[:, 0], gl[:, 1], gl[:, 2], gl[:, 3],
+                                          got["lat_final"][:, 0], got["lat_final"][:, 1])
+            b = helpers.canonical_lattice(lat["frame"], lat["state"], lat["src"], lat["dst"], lat["arc"], lat["ac"].view(np.int32),
+                                          lat["final_state"], lat["final_cost"].view(np.int32))
+            for x, y in zip(a, b):
+                np.testing.assert_array_equal(x, y)
+            assert got["lat_tok_frame"][hdr[3]] == 0 and got["lat_tok_state"][hdr[3]] == model["graph"]["start"]
     # end to end: identical transcript and word timings against the pure-oracle pipeline
     assert got["text"] == ref["text"]
 
@@ -93,3 +107,16 @@ def test_max_active_binds(model_root, oracle_lib):
     got, _ = helpers.run_engine(mdir, waves, options="num-channels=2,max-batch-size=2,max-seconds=10,max-active=300,min-active=50,beam=20")
     for w, g in zip(waves, got):
         _check_stream(model, oracle_lib, w, g, 51)
+
+
+@pytest.mark.parametrize("arch,lb", [("tiny", 6.0), ("tiny", 1.5), ("small", 6.0)])
+def test_lattice_generation(model_root, oracle_lib, arch, lb):
+    """lattice=1: the link log pruned on the device equals LatticeFasterDecoder's raw lattice (oracle), bit for bit."""
+    import vbmodel
+    mdir = model_root(arch)
+    model = vbmodel.load_model_dir(mdir)
+    waves = _waves([0.3, 1.3, 2.04, 3.7] if arch == "tiny" else [2.5, 0.9], seed0=900)
+    got, stats = helpers.run_engine(mdir, waves, options=f"lattice=1,lattice-beam={lb},num-channels=4,max-batch-size=4,max-seconds=10")
+    assert stats["links"] > 0 and stats["lattice_arcs"] > 0
+    for w, g in zip(waves, got):
+        _check_stream(model, oracle_lib, w, g, 51, lattice_beam=lb)

@@ -167,6 +167,53 @@ def test_decoder_pruned_path_is_a_valid_path(model_root, oracle_lib):
     assert np.all(frame_of[d["prev"][has_prev & eps]] == frame_of[has_prev & eps])
 
 
+def test_lattice_pruning_matches_forward_backward(model_root, oracle_lib):
+    """Independent pin of FinalizeDecoding's pruning: a link survives iff alpha(src) + link + beta(dst) is within
+    lattice_beam of the best complete path, where alpha = the logged forward costs and beta = a dense backward
+    Viterbi over the UNPRUNED link log (fp64)."""
+    import vbmodel
+    m = vbmodel.load_model_dir(model_root("tiny"))
+    g = m["graph"]
+    r = oracle_lib.recognize(m, vbmodel.synth_audio(1.6, 21), stages=True)
+    lb = 2.5
+    full = oracle_lib.decode(m, r["loglikes"], lattice_beam=1e30)["lattice"]
+    pruned = oracle_lib.decode(m, r["loglikes"], lattice_beam=lb)
+    d, lat = pruned, pruned["lattice"]
+    assert len(lat["src"]) < len(full["src"]) and len(lat["src"]) > d["frames"]
+    # backward costs over the unpruned lattice (states of `full` are in topological order except epsilon links inside a
+    # frame, so relax to the fixed point)
+    cost = d["cost"][full["tok_index"]].astype(np.float64)
+    w = (g["arc_w"][full["arc"]].astype(np.float64) + full["ac"].astype(np.float64))
+    beta = np.full(len(cost), np.inf)
+    beta[full["final_state"]] = full["final_cost"]
+    for _ in range(10000):
+        new = beta.copy()
+        np.minimum.at(new, full["src"], w + beta[full["dst"]])
+        if np.array_equal(new, beta):
+            break
+        beta = new
+    best = (cost + beta).min()
+    assert abs(best - d["best_cost"]) < 1e-3
+    link_total = cost[full["src"]] + w + beta[full["dst"]] - best
+    key_full = list(zip(full["tok_index"][full["src"]], full["arc"]))
+    want = {k for k, t in zip(key_full, link_total) if t <= lb - 1e-3}
+    maybe = {k for k, t in zip(key_full, link_total) if t <= lb + 1e-3}
+    got = set(zip(lat["tok_index"][lat["src"]], lat["arc"]))
+    assert want <= got <= maybe
+    # every surviving state lies on a surviving path from the start to a final state
+    reach = np.zeros(len(lat["tok_index"]), bool)
+    reach[lat["final_state"]] = True
+    for _ in range(10000):
+        n = reach.copy()
+        n[lat["src"][reach[lat["dst"]]]] = True
+        if np.array_equal(n, reach):
+            break
+        reach = n
+    assert reach.all()
+    # the best path is inside the lattice
+    assert set(int(a) for a in d["best_arcs"]) <= set(int(x) for x in lat["arc"])
+
+
 def test_result_text_matches_reference_json_h(model_root, oracle_lib):
     """Oracle result text == the reference's own json.h output (golden fixture from oracle/_ref) for the same words/times."""
     import vbmodel

@@ -20,6 +20,17 @@
 // marker scan — every lane then issues one 16-byte arc load.  The frame's log-likelihood row is staged in
 // shared memory; per-state recombination is a 64-bit atomicMin on an open-addressing table private to the
 // CTA whose active window is sized per frame so that small frames stay L2-resident.
+//
+// Expansion is staged: the gather pass only loads (two 32-arc windows in flight per warp) and parks every arc below
+// the running cutoff as a candidate record; once the frame's minimum is known the insertion pass touches the table
+// only with arcs below the FINAL cutoff (thread per record, independent iterations).
+//
+// Lattice generation (lattice=1; CudaDecoder's per-state extra_prev_tokens / LatticeFasterDecoder's ForwardLinks):
+// every arc below the final cutoff whose cost is within lattice_beam of its destination state's best cost is logged as
+// a link {src token, dst token, arc, acoustic cost}.  At stream end lattice_prune_kernel restates
+// PruneForwardLinksFinal / PruneForwardLinks / PruneTokensForFrame: backward extra-cost propagation (epsilon links of
+// a frame to their fixed point, then the emitting links into it), links and tokens above lattice_beam dropped, the
+// survivors renumbered and compacted into the raw lattice the host reads.
 #include <cfloat>
 #include <climits>
 
@@ -32,6 +43,8 @@ constexpr int kDecBlocksPerSM = 3;   // 256-thread variant; the 1024-thread vari
 constexpr int kSmemSlots = 4096;  // level-1 (shared memory) table entries per CTA
 constexpr unsigned long long kValMax = ~0ull;
 constexpr int kEmpty = -1;
+constexpr int kAltFlag = 0x40000000;  // candidate did not improve its state's best word; kept as a lattice link only
+constexpr unsigned kInfBits = 0x7f800000u;
 
 __device__ __forceinline__ unsigned ford(float f) {
     unsigned u = __float_as_uint(f);
@@ -53,14 +66,14 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 template <int NT>
 struct Shared {
     unsigned min_ord;  // running minimum of candidate costs (ordered)
-    int n_cand, n_next, error;
+    int n_cand, n_next, n_links, error;
     int warp_cnt[(NT / 32)], warp_exp[(NT / 32)], warp_deg[(NT / 32)];
     unsigned hist[256];
     unsigned sel_prefix, sel_mask;
     int sel_k;
     unsigned red_u[(NT / 32)];
     unsigned long long red_ull[(NT / 32)];
-    int own[(NT / 32)][32];  // per-warp marker array of the arc-window owner scan
+    int own[(NT / 32)][2][32];  // per-warp marker arrays of the arc-window owner scan (two windows in flight)
 };
 
 template <int NT>
@@ -73,7 +86,8 @@ struct Ctx {
     int *hkey;                 // level-2 table in global memory (overflow of the bounded level-1 probe)
     unsigned long long *hval;
     int *htok;
-    int4 *cand;                // {packed lo, packed hi, slot, src}
+    int4 *cand;                // {arc (packed lo), ordered cost (packed hi), slot | kAltFlag (-1 = dead; state before insertion), src}
+    int *cand_next;            // destination state of a candidate
     int *rank;
     int *sv_pref, *sv_a0, *sv_src, *win_owner;
     float *sv_cost;
@@ -114,44 +128,61 @@ __device__ __forceinline__ int tab_tok(const Ctx<NT> &c, int slot) {
     return slot < kSmemSlots ? *(volatile int *)(c.skey + slot) : __ldcg(c.htok + (slot - kSmemSlots));
 }
 
-// insert (state, packed) ; records a candidate when it improved the state's best word
+// claims / finds the table slot of a state and folds pk into its best word; returns the slot (-1: table full)
+template <int NT>
+__device__ __forceinline__ int table_insert(Ctx<NT> &c, int state, unsigned long long pk, unsigned long long *old_out) {
+    const unsigned hash = ((unsigned)state * 2654435761u) >> 7;
+    if (c.use_l1) {
+        unsigned h = hash & (kSmemSlots - 1);
+#pragma unroll 1
+        for (int p = 0; p < kProbe1; p++) {
+            int prev = atomicCAS(c.skey + h, kEmpty, state);
+            if (prev == kEmpty || prev == state) {
+                *old_out = atomicMin(c.sval + h, pk);
+                return (int)h;
+            }
+            h = (h + 1) & (kSmemSlots - 1);
+        }
+    }
+    const unsigned mask = c.hmask;
+    unsigned g = hash & mask;
+    int probes = 0;
+    for (;;) {
+        int prev = atomicCAS(c.hkey + g, kEmpty, state);
+        if (prev == kEmpty || prev == state) break;
+        g = (g + 1) & mask;
+        if (++probes > (int)mask) {
+            c.sh.error = 1;
+            return -1;
+        }
+    }
+    *old_out = atomicMin(c.hval + g, pk);
+    return kSmemSlots + (int)g;
+}
+
+// 0: pk became the state's best word (a token candidate); kAltFlag: not the best, but within lattice_beam of the best
+// seen so far (the best only decreases, so nothing the final test keeps is lost here); -1: drop
+template <int NT>
+__device__ __forceinline__ int keep_flags(const Ctx<NT> &c, unsigned long long pk, unsigned long long old, float cost) {
+    if (pk < old) return 0;
+    if (c.a.lattice && cost - unord((unsigned)(old >> 32)) <= c.a.lattice_beam) return kAltFlag;
+    return -1;
+}
+
+// epsilon-closure insertion: appends a candidate record (src = index of the generating candidate)
 template <int NT>
 __device__ __forceinline__ void relax(Ctx<NT> &c, int state, unsigned long long pk, int src) {
-    const unsigned hash = ((unsigned)state * 2654435761u) >> 7;
-    int slot = -1;
-    unsigned h = hash & (kSmemSlots - 1);
-#pragma unroll 1
-    for (int p = 0; p < kProbe1 && c.use_l1; p++) {
-        int prev = atomicCAS(c.skey + h, kEmpty, state);
-        if (prev == kEmpty || prev == state) {
-            slot = (int)h;
-            break;
-        }
-        h = (h + 1) & (kSmemSlots - 1);
-    }
     unsigned long long old;
-    if (slot >= 0) {
-        old = atomicMin(c.sval + slot, pk);
+    const int slot = table_insert(c, state, pk, &old);
+    if (slot < 0) return;
+    const int fl = keep_flags(c, pk, old, unord((unsigned)(pk >> 32)));
+    if (fl < 0) return;
+    int idx = agg_inc(&c.sh.n_cand);
+    if (idx < c.a.cand_cap) {
+        c.cand[idx] = make_int4((int)(unsigned)pk, (int)(unsigned)(pk >> 32), slot | fl, src);
+        c.cand_next[idx] = state;
     } else {
-        const unsigned mask = c.hmask;
-        unsigned g = hash & mask;
-        int probes = 0;
-        for (;;) {
-            int prev = atomicCAS(c.hkey + g, kEmpty, state);
-            if (prev == kEmpty || prev == state) break;
-            g = (g + 1) & mask;
-            if (++probes > (int)mask) {
-                c.sh.error = 1;
-                return;
-            }
-        }
-        old = atomicMin(c.hval + g, pk);
-        slot = kSmemSlots + (int)g;
-    }
-    if (pk < old) {
-        int idx = agg_inc(&c.sh.n_cand);
-        if (idx < c.a.cand_cap) c.cand[idx] = make_int4((int)(unsigned)pk, (int)(unsigned)(pk >> 32), slot, src);
-        else c.sh.error = 2;
+        c.sh.error = 2;
     }
 }
 
@@ -270,24 +301,25 @@ __device__ float get_cutoff(Ctx<NT> &c, const float *cost, int n, float *adaptiv
 }
 
 // epsilon closure over candidates [lo, hi) until no candidate is added; returns total candidate count.
-// Epsilon out-degrees are tiny (0-2), so one thread per candidate is balanced.
+// Epsilon out-degrees are tiny (0-2), so one thread per candidate is balanced.  Only a candidate that currently is
+// its state's best word is expanded; if it is superseded later, the better one is expanded in a later round.
 template <int NT>
 __device__ int closure(Ctx<NT> &c, int lo, int hi, float cutoff, unsigned long long *arcs_seen) {
     const DecArgs &a = c.a;
     while (lo < hi) {
         for (int i = lo + c.tid; i < hi; i += NT) {
             const int4 cd = c.cand[i];
+            if (cd.z < 0 || (cd.z & kAltFlag)) continue;
             const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
-            const int slot = cd.z;
             const float cost = unord((unsigned)cd.y);
-            if (cost < cutoff && tab_val(c, slot) == pk) {
-                const int s = tab_key(c, slot);
+            if (cost < cutoff && tab_val(c, cd.z) == pk) {
+                const int s = c.cand_next[i];
                 const int a0 = __ldg(&a.g.state_arcs[s].y), a1 = __ldg(&a.g.state_arcs[s + 1].x);
                 *arcs_seen += (unsigned)(a1 - a0);
                 for (int arc = a0; arc < a1; arc++) {
                     const int4 av = __ldg(a.g.arcs + arc);
                     const float tot = cost + __int_as_float(av.x);
-                    if (tot < cutoff) relax(c, av.y, pack(tot, arc), slot);
+                    if (tot < cutoff) relax(c, av.y, pack(tot, arc), i);
                 }
             }
         }
@@ -299,19 +331,22 @@ __device__ int closure(Ctx<NT> &c, int lo, int hi, float cutoff, unsigned long l
     return hi;
 }
 
-// turn the winning candidates into the next frame's token list; clears both table levels
+// turn the winning candidates into the next frame's token list, log the lattice links, clear both table levels.
+// Links are appended at links[link_base ...] with token-LIST indices of the new frame in the destination (and, for
+// epsilon links, source) field; the next frame's pass translates them to log indices once the survivors are ranked.
 template <int NT>
-__device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff, int *t_state, float *t_cost, int *t_arc,
-                                int *t_prev) {
+__device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff, float cost_offset, int4 *links, int link_base,
+                                int *t_state, float *t_cost, int *t_arc, int *t_prev) {
     const DecArgs &a = c.a;
     for (int i = c.tid; i < n_cand; i += NT) {
         const int4 cd = c.cand[i];
+        if (cd.z < 0 || (cd.z & kAltFlag)) continue;
         const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
         const float cost = unord((unsigned)cd.y);
         if (cost < cutoff && tab_val(c, cd.z) == pk) {
             int idx = agg_inc(&c.sh.n_next);
             if (idx < a.tok_cap) {
-                t_state[idx] = tab_key(c, cd.z);
+                t_state[idx] = c.cand_next[i];
                 t_cost[idx] = cost;
                 t_arc[idx] = cd.x;
                 tab_set_tok(c, cd.z, idx);  // one winner per slot: nobody else reads this slot's key any more
@@ -323,13 +358,33 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
         }
     }
     __syncthreads();
-    for (int i = n_emit + c.tid; i < n_cand; i += NT) {
+    const int first = a.lattice ? 0 : n_emit;  // without lattice generation only the epsilon winners need this pass
+    for (int i = first + c.tid; i < n_cand; i += NT) {
         const int4 cd = c.cand[i];
+        if (cd.z < 0) continue;
+        const int slot = cd.z & ~kAltFlag;
         const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
         const float cost = unord((unsigned)cd.y);
-        if (cost < cutoff && tab_val(c, cd.z) == pk) {
-            int idx = tab_tok(c, cd.z);
-            if (idx < a.tok_cap) t_prev[idx] = -2 - tab_tok(c, cd.w);
+        if (!(cost < cutoff)) continue;
+        const unsigned long long best = tab_val(c, slot);
+        const bool winner = !(cd.z & kAltFlag) && best == pk;
+        const bool is_eps = i >= n_emit;
+        int src_tok = 0;
+        bool src_ok = true;
+        if (is_eps) {  // the generating candidate must still be its state's best word (else this record is stale)
+            const int4 sc = c.cand[cd.w];
+            const unsigned long long spk = ((unsigned long long)(unsigned)sc.y << 32) | (unsigned)sc.x;
+            src_ok = sc.z >= 0 && !(sc.z & kAltFlag) && tab_val(c, sc.z) == spk;
+            if (src_ok) src_tok = tab_tok(c, sc.z);
+        }
+        const int dst_tok = tab_tok(c, slot);
+        if (winner && is_eps && dst_tok < a.tok_cap) t_prev[dst_tok] = -2 - src_tok;
+        if (a.lattice && src_ok && cd.x >= 0 && cost - unord((unsigned)(best >> 32)) <= a.lattice_beam) {
+            float ac = 0.f;
+            if (!is_eps) ac = cost_offset - a.acoustic_scale * c.ll[__ldg(a.g.arcs + cd.x).z];
+            const int k = link_base + agg_inc(&c.sh.n_links);
+            if (k < a.link_cap) links[k] = make_int4(is_eps ? -2 - src_tok : cd.w, dst_tok | (is_eps ? kEpsLinkFlag : 0), cd.x, __float_as_int(ac));
+            else c.sh.error = 7;
         }
     }
     __syncthreads();
@@ -341,8 +396,9 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
         }
     } else {
         for (int i = c.tid; i < n_cand; i += NT) {
-            const int slot = c.cand[i].z;
-            if (slot >= kSmemSlots) {
+            const int z = c.cand[i].z;
+            const int slot = z & ~kAltFlag;
+            if (z >= 0 && slot >= kSmemSlots) {
                 c.hkey[slot - kSmemSlots] = kEmpty;
                 c.hval[slot - kSmemSlots] = kValMax;
             }
@@ -372,12 +428,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
     }
     Ctx<NT> c{a, sh, s_ll, s_key, s_val,
           a.hash_key + g * a.hash_size, a.hash_val + g * a.hash_size, a.hash_tok + g * a.hash_size,
-          a.cand + g * a.cand_cap,
+          a.cand + g * a.cand_cap, a.cand_next + g * a.cand_cap,
           a.rank + g * a.tok_cap,
           a.sv_pref + g * a.tok_cap, a.sv_a0 + g * a.tok_cap, a.sv_src + g * a.tok_cap, a.win_owner + g * nwin_cap,
           a.sv_cost + g * a.tok_cap,
           tid, tid >> 5, tid & 31, true, (unsigned)a.hash_size - 1};
-    unsigned long long cnt_tok = 0, cnt_arc_e = 0, cnt_arc_eps = 0, cnt_new = 0;  // per-thread profiling counters
+    unsigned long long cnt_tok = 0, cnt_arc_e = 0, cnt_arc_eps = 0, cnt_new = 0, cnt_stage = 0, cnt_links = 0;  // per-thread profiling counters
     const int npdf = a.out_node.dim;
     for (;;) {
         __syncthreads();
@@ -396,14 +452,18 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
         float *log_cost = a.log_cost + (size_t)ch * a.log_cap;
         int *log_state = a.log_state ? a.log_state + (size_t)ch * a.log_cap : nullptr;
         int *frame_off = a.log_frame_off + (size_t)ch * (a.max_frames + 2);
+        int4 *links = a.lattice ? a.links + (size_t)ch * a.link_cap : nullptr;
+        int *link_off = a.lattice ? a.link_off + (size_t)ch * (a.max_frames + 3) : nullptr;
         __syncthreads();
         if (tid == 0) sh.error = ln.first ? 0 : cs->error;
-        int n_cur, parity, frame, log_count;
+        int n_cur, parity, frame, log_count, link_count = 0, seg_begin = 0;
         if (ln.first) {
             // InitDecoding: start token + epsilon closure with cutoff = beam
             if (tid == 0) {
                 sh.n_cand = 0;
                 sh.n_next = 0;
+                sh.n_links = 0;
+                if (link_off) link_off[0] = 0;
             }
             c.hmask = (unsigned)a.hash_size - 1;
             c.use_l1 = true;
@@ -411,8 +471,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             if (tid == 0) relax(c, a.g.start, pack(0.f, -1), -1);
             __syncthreads();
             int nc = closure(c, 0, min(sh.n_cand, a.cand_cap), a.beam, &cnt_arc_eps);
-            finalize_tokens(c, 1, nc, INFINITY, a.tok_state + tbase, a.tok_cost + tbase, a.tok_arc + tbase, a.tok_prev + tbase);
+            finalize_tokens(c, 1, nc, INFINITY, 0.f, links, 0, a.tok_state + tbase, a.tok_cost + tbase, a.tok_arc + tbase, a.tok_prev + tbase);
             n_cur = min(sh.n_next, a.tok_cap);
+            link_count = a.lattice ? min(sh.n_links, a.link_cap) : 0;
             parity = 0;
             frame = 0;
             log_count = 0;
@@ -421,6 +482,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             parity = cs->parity;
             frame = cs->frame;
             log_count = cs->log_count;
+            link_count = cs->link_count;
+            if (link_off) seg_begin = link_off[min(frame, a.max_frames + 1)];
         }
         const int nf = a.out_table[l].n_rows;
         const int t_first = a.out_table[l].t_begin;
@@ -460,12 +523,14 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                         sh.min_ord = m;
                         sh.n_cand = 0;
                         sh.n_next = 0;
+                        sh.n_links = 0;
                     }
                 }
             } else if (tid == 0) {
                 sh.min_ord = 0xffffffffu;
                 sh.n_cand = 0;
                 sh.n_next = 0;
+                sh.n_links = 0;
             }
             // ---- pass A: per-warp counts of survivors, survivors with out-arcs, and out-arcs ----
             const int span = ((n_cur + (NT / 32) - 1) / (NT / 32) + 31) & ~31;
@@ -574,69 +639,131 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                     frame_off[frame + 1] = log_count + n_surv;
                 }
             }
+            if (links) {
+                // links created by the previous frame point at this frame's tokens by LIST index: now that the survivors
+                // are ranked, rewrite them to log indices (a link into a token that was not logged is dropped)
+                for (int k = seg_begin + tid; k < link_count; k += NT) {
+                    int4 l = links[k];
+                    const int r = log_ok ? c.rank[l.y & ~kEpsLinkFlag] : -1;
+                    int y = r < 0 ? -1 : ((log_count + r) | (l.y & kEpsLinkFlag));
+                    if (l.x <= -2) {
+                        const int rs = log_ok ? c.rank[-2 - l.x] : -1;
+                        if (rs < 0) y = -1;
+                        l.x = log_count + max(rs, 0);
+                    }
+                    l.y = y;
+                    links[k] = l;
+                }
+                if (tid == 0 && frame <= a.max_frames) link_off[frame + 1] = link_count;
+                seg_begin = link_count;
+            }
             cnt_tok += tid == 0 ? (unsigned)n_surv : 0u;
             log_count += log_ok ? n_surv : 0;
             if (final_pass) {
                 __syncthreads();
                 break;
             }
-            // ---- pass C2: emitting arcs, one 32-arc window per warp iteration ----
+            // ---- pass C2a: gather.  Two 32-arc windows per warp iteration, all loads of a stage issued before their
+            // first use; arcs below the running cutoff are parked as candidate records {arc, cost, next state, src} ----
             cnt_arc_e += tid == 0 ? (unsigned)n_arcs : 0u;
+            const float cost_offset = -best;
             {
-                const float cost_offset = -best;
+                constexpr int NW = NT / 32;
                 const int nwin = (n_arcs + 31) >> 5;
-                int *own = sh.own[c.warp];
-                for (int w = c.warp; w < nwin; w += (NT / 32)) {
-                    const int j = (w << 5) + c.lane;
-                    const int q0 = c.win_owner[w];
-                    const int my = q0 + c.lane;
-                    int pref = INT_MAX, a0 = 0, src = 0;
-                    float cost = 0.f;
-                    if (my < n_exp) {
-                        pref = c.sv_pref[my];
-                        a0 = c.sv_a0[my];
-                        cost = c.sv_cost[my];
-                        src = c.sv_src[my];
+                int *ownA = sh.own[c.warp][0], *ownB = sh.own[c.warp][1];
+                for (int w0 = c.warp; w0 < nwin; w0 += 2 * NW) {
+                    const int w1 = w0 + NW;
+                    const bool h1 = w1 < nwin;  // warp-uniform
+                    const int qA = c.win_owner[w0], qB = h1 ? c.win_owner[w1] : 0;
+                    const int myA = qA + c.lane, myB = qB + c.lane;
+                    int prefA = INT_MAX, a0A = 0, srcA = 0, prefB = INT_MAX, a0B = 0, srcB = 0;
+                    float costA = 0.f, costB = 0.f;
+                    if (myA < n_exp) {
+                        prefA = c.sv_pref[myA];
+                        a0A = c.sv_a0[myA];
+                        costA = c.sv_cost[myA];
+                        srcA = c.sv_src[myA];
                     }
-                    own[c.lane] = 0;
+                    if (h1 && myB < n_exp) {
+                        prefB = c.sv_pref[myB];
+                        a0B = c.sv_a0[myB];
+                        costB = c.sv_cost[myB];
+                        srcB = c.sv_src[myB];
+                    }
+                    ownA[c.lane] = 0;
+                    ownB[c.lane] = 0;
                     __syncwarp();
-                    const int rel = pref - (w << 5);
-                    if (c.lane > 0 && rel >= 0 && rel < 32) own[rel] = c.lane;  // prefixes are strictly increasing
+                    const int relA = prefA - (w0 << 5), relB = prefB - (w1 << 5);
+                    if (c.lane > 0 && relA >= 0 && relA < 32) ownA[relA] = c.lane;  // prefixes are strictly increasing
+                    if (c.lane > 0 && relB >= 0 && relB < 32) ownB[relB] = c.lane;
                     __syncwarp();
-                    int o = own[c.lane];
+                    int oA = ownA[c.lane], oB = ownB[c.lane];
                     for (int d = 1; d < 32; d <<= 1) {
-                        int v = __shfl_up_sync(0xffffffffu, o, d);
-                        if (c.lane >= d) o = max(o, v);
+                        const int vA = __shfl_up_sync(0xffffffffu, oA, d), vB = __shfl_up_sync(0xffffffffu, oB, d);
+                        if (c.lane >= d) {
+                            oA = max(oA, vA);
+                            oB = max(oB, vB);
+                        }
                     }
-                    const int opref = __shfl_sync(0xffffffffu, pref, o);
-                    const int oa0 = __shfl_sync(0xffffffffu, a0, o);
-                    const float ocost = __shfl_sync(0xffffffffu, cost, o);
-                    const int osrc = __shfl_sync(0xffffffffu, src, o);
-                    const bool valid = j < n_arcs;
-                    float tot = INFINITY;
-                    int arc = 0, next = 0;
-                    if (valid) {
-                        arc = oa0 + (j - opref);
-                        const int4 av = __ldg(a.g.arcs + arc);
-                        next = av.y;
-                        const float ac = cost_offset - a.acoustic_scale * s_ll[av.z];
-                        tot = ocost + ac + __int_as_float(av.x);
-                    }
-                    unsigned m = ford(tot);
+                    const int jA = (w0 << 5) + c.lane, jB = (w1 << 5) + c.lane;
+                    const bool validA = jA < n_arcs, validB = h1 && jB < n_arcs;
+                    const int arcA = __shfl_sync(0xffffffffu, a0A, oA) + (jA - __shfl_sync(0xffffffffu, prefA, oA));
+                    const int arcB = __shfl_sync(0xffffffffu, a0B, oB) + (jB - __shfl_sync(0xffffffffu, prefB, oB));
+                    const float ocostA = __shfl_sync(0xffffffffu, costA, oA), ocostB = __shfl_sync(0xffffffffu, costB, oB);
+                    const int osrcA = __shfl_sync(0xffffffffu, srcA, oA), osrcB = __shfl_sync(0xffffffffu, srcB, oB);
+                    int4 avA = make_int4(0, 0, 0, 0), avB = make_int4(0, 0, 0, 0);
+                    if (validA) avA = __ldg(a.g.arcs + arcA);
+                    if (validB) avB = __ldg(a.g.arcs + arcB);
+                    float totA = INFINITY, totB = INFINITY;
+                    if (validA) totA = ocostA + (cost_offset - a.acoustic_scale * s_ll[avA.z]) + __int_as_float(avA.x);
+                    if (validB) totB = ocostB + (cost_offset - a.acoustic_scale * s_ll[avB.z]) + __int_as_float(avB.x);
+                    unsigned m = min(ford(totA), ford(totB));
                     for (int d = 16; d; d >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
                     if (c.lane == 0) atomicMin(&sh.min_ord, m);
                     __syncwarp();
                     const float cut = unord(*(volatile unsigned *)&sh.min_ord) + adaptive_beam;  // loose (>= final) cutoff
-                    if (valid && tot < cut) relax(c, next, pack(tot, arc), osrc);
+                    if (validA && totA < cut) {
+                        const int idx = agg_inc(&sh.n_cand);
+                        if (idx < a.cand_cap) c.cand[idx] = make_int4(arcA, (int)ford(totA), avA.y, osrcA);
+                    }
+                    if (validB && totB < cut) {
+                        const int idx = agg_inc(&sh.n_cand);
+                        if (idx < a.cand_cap) c.cand[idx] = make_int4(arcB, (int)ford(totB), avB.y, osrcB);
+                    }
                     __syncwarp();
                 }
             }
             __syncthreads();
             const float next_cutoff = unord(sh.min_ord) + adaptive_beam;
+            if (tid == 0 && sh.n_cand > a.cand_cap) sh.error = 2;
             const int n_emit = min(sh.n_cand, a.cand_cap);
+            cnt_stage += tid == 0 ? (unsigned)n_emit : 0u;
+            // ---- pass C2b: insertion of the records below the FINAL cutoff (thread per record) ----
+            for (int i = tid; i < n_emit; i += NT) {
+                const int4 cd = c.cand[i];
+                const float cost = unord((unsigned)cd.y);
+                int z = -1;
+                if (cost < next_cutoff) {
+                    const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
+                    unsigned long long old;
+                    const int slot = table_insert(c, cd.z, pk, &old);
+                    if (slot >= 0) {
+                        const int fl = keep_flags(c, pk, old, cost);
+                        if (fl >= 0) {
+                            z = slot | fl;
+                            c.cand_next[i] = cd.z;
+                        }
+                    }
+                }
+                reinterpret_cast<int *>(c.cand + i)[2] = z;
+            }
             __syncthreads();
             const int nc = closure(c, 0, n_emit, next_cutoff, &cnt_arc_eps);
-            finalize_tokens(c, n_emit, nc, next_cutoff, n_state, n_cost, n_arc, n_prev);
+            finalize_tokens(c, n_emit, nc, next_cutoff, cost_offset, links, link_count, n_state, n_cost, n_arc, n_prev);
+            if (a.lattice) {
+                cnt_links += tid == 0 ? (unsigned)sh.n_links : 0u;
+                link_count = min(link_count + sh.n_links, a.link_cap);
+            }
             n_cur = min(sh.n_next, a.tok_cap);
             cnt_new += tid == 0 ? (unsigned)n_cur : 0u;
             parity ^= 1;
@@ -697,6 +824,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             cs->parity = parity;
             cs->frame = frame;
             cs->log_count = log_count;
+            cs->link_count = link_count;
             cs->error = sh.error;
             if (a.counters) {  // lane-level balance: sum and max of the cycles one lane took in this launch
                 const unsigned long long cyc = (unsigned long long)(clock64() - clk0);
@@ -714,9 +842,187 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             atomicAdd(a.counters + 0, cnt_tok);
             atomicAdd(a.counters + 1, cnt_arc_e);
             atomicAdd(a.counters + 3, cnt_new);
+            atomicAdd(a.counters + 8, cnt_stage);
+            atomicAdd(a.counters + 9, cnt_links);
         }
         if ((tid & 31) == 0 && cnt_arc_eps) atomicAdd(a.counters + 2, cnt_arc_eps);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Lattice pruning + compaction at stream end (one CTA per finished lane).
+// Restates LatticeFasterDecoder::PruneForwardLinksFinal / PruneForwardLinks(delta = 0) / PruneTokensForFrame:
+//   extra(tok of the last frame) = (cost + final) - best_final            (final = 0 if no final state was reached)
+//   link_extra = extra(dst) + ((cost(src) + acoustic + graph) - cost(dst)), clamped at 0
+//   a link survives iff link_extra <= lattice_beam; extra(tok) = min over its surviving links (inf: token dropped)
+// Frames are visited last to first; within a frame the epsilon links are iterated to their fixed point (monotone
+// atomicMin on the ordered-float bits of non-negative costs) before the emitting links push into the previous frame.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kPruneThreads = 256;
+
+__device__ __forceinline__ float link_extra(const DecArgs &a, const int4 l, const float *cost, const unsigned *extra) {
+    const int dst = l.y & ~kEpsLinkFlag;
+    const float ed = __uint_as_float(__ldcg(extra + dst));
+    if (ed == INFINITY) return INFINITY;
+    const float w = __int_as_float(__ldg(a.g.arcs + l.z).x);
+    float le = ed + (((cost[l.x] + __int_as_float(l.w)) + w) - cost[dst]);
+    if (le < 0.f) le = 0.f;
+    return le;
+}
+
+__global__ void __launch_bounds__(kPruneThreads) lattice_prune_kernel(DecArgs a) {
+    const int l = blockIdx.x;
+    const LaneDesc ln = a.lanes[l];
+    if (!ln.last) return;
+    constexpr int NT = kPruneThreads;
+    __shared__ int s_changed, s_count, s_warp[NT / 32], s_nlinks, s_nfinal, s_start;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ch = ln.channel;
+    const DecChannelState cs = a.cs[ch];
+    const float *cost = a.log_cost + (size_t)ch * a.log_cap;
+    const int *log_arc = a.log_arc + (size_t)ch * a.log_cap;
+    unsigned *extra = a.lat_extra ? a.lat_extra + (size_t)ch * a.log_cap : reinterpret_cast<unsigned *>(a.log_prev + (size_t)ch * a.log_cap);
+    int *remap = reinterpret_cast<int *>(extra);  // the new state numbers overwrite the extra costs once the links are filtered
+    const int *frame_off = a.log_frame_off + (size_t)ch * (a.max_frames + 2);
+    int4 *links = a.links + (size_t)ch * a.link_cap;
+    const int *link_off = a.link_off + (size_t)ch * (a.max_frames + 3);
+    const int F = min(cs.frame, a.max_frames);
+    const int n_tok = cs.log_count;
+    const float lb = a.lattice_beam;
+    LatHeader *hdr = a.lat_hdr + l;
+    int4 *out_links = a.lat_links + (size_t)l * a.lat_link_cap;
+    int2 *out_final = a.lat_final + (size_t)l * a.lat_final_cap;
+    int *out_frame = a.lat_tok_frame + (size_t)l * a.lat_tok_cap;
+    int *out_state = a.lat_tok_state ? a.lat_tok_state + (size_t)l * a.lat_tok_cap : nullptr;
+    const int *log_state = a.log_state ? a.log_state + (size_t)ch * a.log_cap : nullptr;
+    int error = cs.error;
+    if (cs.n_cur == 0 || n_tok == 0 || cs.frame > a.max_frames) {  // search died / log overflow: no lattice
+        if (tid == 0) *hdr = LatHeader{0, 0, 0, -1, error ? error : 11, F, 0, 0};
+        return;
+    }
+    for (int i = tid; i < n_tok; i += NT) extra[i] = kInfBits;
+    if (tid == 0) {
+        s_nlinks = 0;
+        s_nfinal = 0;
+        s_start = -1;
+    }
+    __syncthreads();
+    // last frame: all its tokens were logged in list order, so the token list still gives their states
+    const int lo_last = frame_off[F], hi_last = frame_off[F + 1];
+    const int *t_state = a.tok_state + (size_t)ch * 2 * a.tok_cap + (size_t)cs.parity * a.tok_cap;
+    for (int i = lo_last + tid; i < hi_last; i += NT) {
+        const float fc = cs.reached_final ? __ldg(a.g.final_cost + t_state[i - lo_last]) : 0.f;
+        const float e = (cost[i] + fc) - cs.best_cost;
+        extra[i] = e <= lb ? __float_as_uint(fmaxf(e, 0.f)) : kInfBits;
+    }
+    __syncthreads();
+    for (int f = F; f >= 0; f--) {
+        const int k0 = link_off[f], k1 = link_off[f + 1];
+        // epsilon links inside frame f: iterate to the fixed point
+        for (;;) {
+            if (tid == 0) s_changed = 0;
+            __syncthreads();
+            bool ch_any = false;
+            for (int k = k0 + tid; k < k1; k += NT) {
+                const int4 lk = links[k];
+                if (lk.y < 0 || !(lk.y & kEpsLinkFlag)) continue;
+                const float le = link_extra(a, lk, cost, extra);
+                if (le <= lb) {
+                    const unsigned b = __float_as_uint(le);
+                    if (b < atomicMin(extra + lk.x, b)) ch_any = true;
+                }
+            }
+            if (ch_any) s_changed = 1;
+            __syncthreads();
+            const int again = s_changed;
+            __syncthreads();
+            if (!again) break;
+        }
+        // emitting links into frame f: push to their sources in frame f-1
+        for (int k = k0 + tid; k < k1; k += NT) {
+            const int4 lk = links[k];
+            if (lk.y < 0 || (lk.y & kEpsLinkFlag)) continue;
+            const float le = link_extra(a, lk, cost, extra);
+            if (le <= lb) atomicMin(extra + lk.x, __float_as_uint(le));
+        }
+        __syncthreads();
+    }
+    // surviving links -> output (old token indices for now)
+    const int n_links_all = min(cs.link_count, a.link_cap);
+    for (int k = tid; k < n_links_all; k += NT) {
+        const int4 lk = links[k];
+        if (lk.y < 0) continue;
+        const float le = link_extra(a, lk, cost, extra);
+        if (le <= lb) {
+            const int o = agg_inc(&s_nlinks);
+            if (o < a.lat_link_cap) out_links[o] = make_int4(lk.x, lk.y & ~kEpsLinkFlag, lk.z, lk.w);
+        }
+    }
+    __syncthreads();
+    // surviving tokens, renumbered in log order (frame by frame); remap[] replaces the extra costs when they share storage,
+    // so the keep flags are taken before the barrier and written after it
+    int base = 0;
+    for (int f = 0; f <= F; f++) {
+        const int lo = frame_off[f], hi = frame_off[f + 1];
+        for (int i0 = lo; i0 < hi; i0 += NT) {
+            const int i = i0 + tid;
+            const bool keep = i < hi && __ldcg(extra + i) != kInfBits;
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_warp[warp] = __popc(bal);
+            __syncthreads();
+            int off = 0, tot = 0;
+            for (int w = 0; w < NT / 32; w++) {
+                if (w < warp) off += s_warp[w];
+                tot += s_warp[w];
+            }
+            if (i < hi) {
+                int ni = -1;
+                if (keep) {
+                    ni = base + off + __popc(bal & lanemask_lt());
+                    if (ni < a.lat_tok_cap) {
+                        out_frame[ni] = f;
+                        if (out_state) out_state[ni] = log_state ? log_state[i] : -1;
+                        if (log_arc[i] < 0 && f == 0) s_start = ni;
+                        if (f == F) {  // a token kept only through epsilon links into final tokens is not final itself
+                            const float fc = cs.reached_final ? __ldg(a.g.final_cost + t_state[i - lo_last]) : 0.f;
+                            if (fc != INFINITY) {
+                                const int o = atomicAdd(&s_nfinal, 1);
+                                if (o < a.lat_final_cap) out_final[o] = make_int2(ni, __float_as_int(fc));
+                            }
+                        }
+                    }
+                }
+                remap[i] = ni;
+            }
+            base += tot;
+            __syncthreads();
+        }
+    }
+    if (base > a.lat_tok_cap) error = error ? error : 8;
+    if (s_nlinks > a.lat_link_cap) error = error ? error : 9;
+    if (s_nfinal > a.lat_final_cap) error = error ? error : 10;
+    const int n_out = min(s_nlinks, a.lat_link_cap);
+    for (int k = tid; k < n_out; k += NT) {
+        int4 lk = out_links[k];
+        lk.x = remap[lk.x];
+        lk.y = remap[lk.y];
+        out_links[k] = lk;
+    }
+    if (tid == 0) {
+        hdr->n_tok = min(base, a.lat_tok_cap);
+        hdr->n_links = n_out;
+        hdr->n_final = min(s_nfinal, a.lat_final_cap);
+        hdr->start = s_start;
+        hdr->error = error;
+        hdr->frames = F;
+        if (a.counters) atomicAdd(a.counters + 10, (unsigned long long)n_out);
+    }
+}
+
+extern "C" cudaError_t vbk_lattice_prune(const DecArgs *a, cudaStream_t s) {
+    if (!a->lattice || a->num_lanes <= 0) return cudaSuccess;
+    lattice_prune_kernel<<<a->num_lanes, kPruneThreads, 0, s>>>(*a);
+    return cudaGetLastError();
 }
 
 extern "C" int vbk_decode_max_grid(int device) {

@@ -61,6 +61,9 @@ struct Config {
     int cmn_window = 600, global_frames = 200;
     int use_tensor_cores = 1;   // TDNN-F GEMMs on tcgen05 (3xTF32 split, fp32 accumulate); 0 = fp32 FFMA kernel
     int debug_capture = 0;      // allow per-stream capture of intermediates (tests)
+    int lattice = 0;            // lattice generation: link log + lattice_beam pruning on the device, raw lattice to the host
+    int log_links_per_frame = 6144;   // average links per frame the link log is sized for
+    int lat_tok_cap = 131072, lat_link_cap = 262144;  // pruned raw lattice of one stream (states / arcs)
 };
 
 // ---- acoustic model graph description (device-visible, passed by value to kernels) ----

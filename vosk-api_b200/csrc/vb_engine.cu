@@ -72,6 +72,10 @@ Engine::~Engine() {
         if (sl.h_cs) cudaFreeHost(sl.h_cs);
         if (sl.h_path) cudaFreeHost(sl.h_path);
         if (sl.h_load) cudaFreeHost(sl.h_load);
+        if (sl.h_lat_hdr) cudaFreeHost(sl.h_lat_hdr);
+        if (sl.h_lat_links) cudaFreeHost(sl.h_lat_links);
+        if (sl.h_lat_final) cudaFreeHost(sl.h_lat_final);
+        if (sl.h_lat_tok) cudaFreeHost(sl.h_lat_tok);
         for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.fork) cudaEventDestroy(sl.fork);
@@ -295,7 +299,19 @@ void Engine::alloc_state() {
     d.log_state = cfg_.debug_capture ? dev_alloc<int>(allocs_, (size_t)C * log_cap_) : nullptr;
     d.log_frame_off = dev_alloc<int>(allocs_, (size_t)C * (max_frames_ + 2), 0);
     d.path = dev_alloc<int>(allocs_, (size_t)C * path_cap_, 0);
-    d.counters = dev_alloc<unsigned long long>(allocs_, 8, 0);
+    d.counters = dev_alloc<unsigned long long>(allocs_, 16, 0);
+    d.lattice = cfg_.lattice;
+    d.lattice_beam = cfg_.lattice_beam;
+    if (cfg_.lattice) {
+        link_cap_ = max_frames_ * cfg_.log_links_per_frame + cfg_.cand_cap;
+        d.link_cap = link_cap_;
+        d.links = dev_alloc<int4>(allocs_, (size_t)C * link_cap_);
+        d.link_off = dev_alloc<int>(allocs_, (size_t)C * (max_frames_ + 3), 0);
+        d.lat_extra = cfg_.debug_capture ? dev_alloc<unsigned>(allocs_, (size_t)C * log_cap_) : nullptr;
+        d.lat_link_cap = cfg_.lat_link_cap;
+        d.lat_tok_cap = cfg_.lat_tok_cap;
+        d.lat_final_cap = cfg_.tok_cap;
+    }
     d.grid = std::min(vbk_decode_max_grid(cfg_.device), L);
     // pipeline slots: stream, staging, per-step tables, search scratch
     slots_.resize(cfg_.pipeline_slots);
@@ -327,6 +343,18 @@ void Engine::alloc_state() {
         sd.hash_val = dev_alloc<unsigned long long>(allocs_, G * cfg_.hash_size, 0xff);
         sd.hash_tok = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0);
         sd.cand = dev_alloc<int4>(allocs_, G * cfg_.cand_cap);
+        sd.cand_next = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
+        if (cfg_.lattice) {
+            sd.lat_hdr = dev_alloc<LatHeader>(allocs_, (size_t)L, 0);
+            sd.lat_links = dev_alloc<int4>(allocs_, (size_t)L * cfg_.lat_link_cap);
+            sd.lat_final = dev_alloc<int2>(allocs_, (size_t)L * cfg_.tok_cap);
+            sd.lat_tok_frame = dev_alloc<int>(allocs_, (size_t)L * cfg_.lat_tok_cap);
+            sd.lat_tok_state = cfg_.debug_capture ? dev_alloc<int>(allocs_, (size_t)L * cfg_.lat_tok_cap) : nullptr;
+            VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lat_hdr, (size_t)L * sizeof(LatHeader)));
+            VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lat_links, (size_t)cfg_.lat_link_cap * sizeof(int4)));
+            VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lat_final, (size_t)cfg_.tok_cap * sizeof(int2)));
+            VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lat_tok, (size_t)2 * cfg_.lat_tok_cap * sizeof(int)));
+        }
         sd.rank = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
         sd.sv_pref = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
         sd.sv_a0 = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
@@ -379,7 +407,7 @@ void Engine::wait() {
 }
 
 StepStats Engine::stats() {
-    unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long c[16] = {};
     cudaSetDevice(cfg_.device);
     cudaMemcpy(c, dec_.counters, sizeof c, cudaMemcpyDeviceToHost);
     std::lock_guard<std::mutex> lk(stats_mu_);
@@ -392,11 +420,14 @@ StepStats Engine::stats() {
     s.lane_cycles_max = c[5];
     s.max_tokens = c[6];
     s.lane_launches = c[7];
+    s.arcs_staged = c[8];
+    s.links = c[9];
+    s.lat_arcs = c[10];
     return s;
 }
 void Engine::reset_stats() {
     cudaSetDevice(cfg_.device);
-    cudaMemset(dec_.counters, 0, 8 * sizeof(unsigned long long));
+    cudaMemset(dec_.counters, 0, 16 * sizeof(unsigned long long));
     std::lock_guard<std::mutex> lk(stats_mu_);
     stats_ = StepStats{};
 }
@@ -630,9 +661,18 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
             VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.join, 0));
         }
     }
+    int n_last = 0;
+    for (int i = 0; i < L; i++) n_last += lanes[i].chunk.last ? 1 : 0;
+    if (cfg_.lattice && n_last > 0) {
+        sl.dec.lane_begin = 0;
+        sl.dec.lane_end = L;
+        VB_CUDA_CHECK(vbk_lattice_prune(&sl.dec, st));
+        sl.launches++;
+        VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_hdr, sl.dec.lat_hdr, (size_t)L * sizeof(LatHeader), cudaMemcpyDeviceToHost, st));
+    }
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[4], st));
     // results of finished lanes
-    int n_last = 0;
+    n_last = 0;
     for (int i = 0; i < L; i++)
         if (lanes[i].chunk.last) {
             const int ch = lanes[i].s->channel;
@@ -712,12 +752,57 @@ void Engine::complete_step(Slot &sl) {
     }
     int n_last = 0;
     for (int i = 0; i < L; i++)
-        if (lanes[i].chunk.last) finish_lane(sl, lanes[i], n_last++);
+        if (lanes[i].chunk.last) finish_lane(sl, lanes[i], n_last++, i);
 }
 
-void Engine::finish_lane(Slot &sl, Lane &ln, int k) {
+// copies one finished lane's pruned lattice to the host (sizes come from the header that arrived with the step)
+std::shared_ptr<RawLattice> Engine::fetch_lattice(Slot &sl, int i) {
+    auto lat = std::make_shared<RawLattice>();
+    const LatHeader h = sl.h_lat_hdr[i];
+    cudaStream_t st = sl.stream;
+    lat->n_states = h.n_tok;
+    lat->start = h.start;
+    lat->frames = h.frames;
+    lat->error = h.error;
+    if (h.n_tok <= 0) return lat;
+    const bool with_state = sl.dec.lat_tok_state != nullptr;
+    VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_links, sl.dec.lat_links + (size_t)i * cfg_.lat_link_cap, (size_t)h.n_links * sizeof(int4), cudaMemcpyDeviceToHost, st));
+    VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_final, sl.dec.lat_final + (size_t)i * cfg_.tok_cap, (size_t)h.n_final * sizeof(int2), cudaMemcpyDeviceToHost, st));
+    VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_tok, sl.dec.lat_tok_frame + (size_t)i * cfg_.lat_tok_cap, (size_t)h.n_tok * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (with_state)
+        VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_tok + cfg_.lat_tok_cap, sl.dec.lat_tok_state + (size_t)i * cfg_.lat_tok_cap, (size_t)h.n_tok * sizeof(int), cudaMemcpyDeviceToHost, st));
+    VB_CUDA_CHECK(cudaStreamSynchronize(st));
+    lat->src.resize(h.n_links);
+    lat->dst.resize(h.n_links);
+    lat->arc.resize(h.n_links);
+    lat->acoustic.resize(h.n_links);
+    for (int k = 0; k < h.n_links; k++) {
+        const int4 l = sl.h_lat_links[k];
+        lat->src[k] = l.x;
+        lat->dst[k] = l.y;
+        lat->arc[k] = l.z;
+        memcpy(&lat->acoustic[k], &l.w, 4);
+    }
+    lat->final_state.resize(h.n_final);
+    lat->final_cost.resize(h.n_final);
+    for (int k = 0; k < h.n_final; k++) {
+        lat->final_state[k] = sl.h_lat_final[k].x;
+        memcpy(&lat->final_cost[k], &sl.h_lat_final[k].y, 4);
+    }
+    lat->state_frame.assign(sl.h_lat_tok, sl.h_lat_tok + h.n_tok);
+    if (with_state) lat->state_graph.assign(sl.h_lat_tok + cfg_.lat_tok_cap, sl.h_lat_tok + cfg_.lat_tok_cap + h.n_tok);
+    return lat;
+}
+
+void Engine::finish_lane(Slot &sl, Lane &ln, int k, int lane_pos) {
     const DecChannelState &cs = sl.h_cs[k];
     BestPath bp;
+    if (cfg_.lattice) {
+        bp.lattice = fetch_lattice(sl, lane_pos);
+        if (bp.lattice->error && !cs.error)
+            log_msg(-1, "stream %llu: lattice capacity error %d", (unsigned long long)ln.s->id, bp.lattice->error);
+        if (ln.s->capture) ln.s->capture->lattice = bp.lattice;
+    }
     bp.cost = cs.best_cost;
     bp.reached_final = cs.reached_final != 0;
     bp.error = cs.error;

@@ -20,7 +20,19 @@
 
 namespace vb {
 
+// pruned raw lattice of one stream as the device hands it over (lattice=1): states are the surviving tokens in
+// (frame, log) order, arcs refer to the decoding graph by csr arc id
+struct RawLattice {
+    int n_states = 0, start = -1, frames = 0, error = 0;
+    std::vector<int> src, dst, arc;
+    std::vector<float> acoustic;
+    std::vector<int> final_state;
+    std::vector<float> final_cost;
+    std::vector<int> state_frame, state_graph;  // per lattice state: frame, graph state (graph state only with debug-capture)
+};
+
 struct BestPath {
+    std::shared_ptr<RawLattice> lattice;  // set when lattice generation is on
     std::vector<int> arcs;  // csr arc ids in path order
     float cost = 0.f;
     bool reached_final = false;
@@ -34,6 +46,10 @@ struct Capture {
     std::vector<int> frame_off, tok_state, tok_arc, tok_prev;
     std::vector<float> tok_cost;
     int error = 0;
+    std::shared_ptr<RawLattice> lattice;
+    std::vector<int> lat_links;  // flattened [n][4] {src, dst, arc, acoustic bits}
+    std::vector<int> lat_final;  // flattened [n][2] {state, final cost bits}
+    std::vector<int> lat_hdr;    // {n_states, n_links, n_final, start, error, frames}
 };
 
 struct Stream {
@@ -61,6 +77,7 @@ struct StepStats {
     long long steps = 0, lanes = 0, launches = 0;
     unsigned long long tok = 0, arc_e = 0, arc_eps = 0, tok_new = 0;
     unsigned long long lane_cycles_sum = 0, lane_cycles_max = 0, max_tokens = 0, lane_launches = 0;
+    unsigned long long arcs_staged = 0, links = 0, lat_arcs = 0;  // arcs parked below the running cutoff, links logged, lattice arcs kept
     double t_feat = 0, t_ivec = 0, t_nnet = 0, t_dec = 0, t_total = 0;  // device ms (only when timing enabled)
     long long dec_launches = 0, gemm_launches = 0;
     double host_launch_ms = 0;  // host time spent enqueueing steps
@@ -111,6 +128,10 @@ class Engine {
         DecChannelState *h_cs = nullptr;
         int *h_path = nullptr;
         int *d_load = nullptr, *h_load = nullptr;
+        LatHeader *h_lat_hdr = nullptr;
+        int4 *h_lat_links = nullptr;  // pinned bounce buffers for one finished lane's lattice
+        int2 *h_lat_final = nullptr;
+        int *h_lat_tok = nullptr;
         std::vector<Lane> lanes;
         bool busy = false, timed = false;
         double audio = 0;
@@ -121,7 +142,8 @@ class Engine {
     void complete_step(Slot &sl);
     void upload_model();
     void alloc_state();
-    void finish_lane(Slot &sl, Lane &ln, int lane_idx);
+    void finish_lane(Slot &sl, Lane &ln, int lane_idx, int lane_pos);
+    std::shared_ptr<RawLattice> fetch_lattice(Slot &sl, int lane_pos);
 
     const Model &model_;
     Config cfg_;
@@ -146,7 +168,7 @@ class Engine {
     DecArgs dec_{};  // template: graph, options and per-channel arrays; each slot adds its own scratch
     float *d_capture_ = nullptr, *h_capture_ = nullptr;
     size_t capture_floats_ = 0;
-    int max_in_rows_ = 0, log_cap_ = 0, max_frames_ = 0, path_cap_ = 0, slot_lanes_ = 0;
+    int max_in_rows_ = 0, log_cap_ = 0, max_frames_ = 0, path_cap_ = 0, slot_lanes_ = 0, link_cap_ = 0;
     std::vector<int> free_channels_;
     // batching
     std::mutex mu_;

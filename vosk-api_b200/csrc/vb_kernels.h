@@ -106,7 +106,14 @@ struct DecChannelState {     // one per channel
     int n_cur, parity, frame, error;
     int log_count, path_len, reached_final;
     float best_cost;
+    int link_count, pad0, pad1, pad2;
 };
+// pruned raw lattice of one finished stream (lattice=1): written by lattice_prune_kernel, read by the host
+struct LatHeader {
+    int n_tok, n_links, n_final, start;  // start = lattice state of the initial token (-1: empty lattice)
+    int error, frames, pad0, pad1;
+};
+constexpr int kEpsLinkFlag = 0x40000000;  // set in the destination field of an epsilon link
 struct DecArgs {
     const LaneDesc *lanes;
     int num_lanes;
@@ -138,7 +145,24 @@ struct DecArgs {
     int *sv_pref, *sv_a0, *sv_src;    // [G][tok_cap] expandable survivors: arc prefix, first arc, log index
     float *sv_cost;
     int *win_owner;          // [G][cand_cap/32+2] survivor owning the first arc of each 32-arc window
-    unsigned long long *counters;     // [8] profiling counters (tokens, arcs, ...)
+    // lattice generation (lattice != 0): every arc below the frame's final cutoff whose cost is within lattice_beam
+    // of the best cost of its destination state becomes a link {src token, dst token, arc, acoustic cost}
+    int lattice;
+    float lattice_beam;
+    int4 *links;             // [C][link_cap] {src log index, dst log index | kEpsLinkFlag (-1 = dropped), arc, acoustic cost bits}
+    int *link_off;           // [C][max_frames+3] segment s = links whose destination token belongs to frame s
+    int link_cap;
+    int *cand_next;          // [G][cand_cap] destination state of a candidate
+    unsigned *lat_extra;     // [C][log_cap] extra-cost scratch of the lattice pruning, or null: the pruning then
+                             // reuses log_prev (whose content is dead once the best path has been traced)
+    // per slot: outputs of the pruning for the lanes that finished in this step (index = lane)
+    LatHeader *lat_hdr;      // [L]
+    int4 *lat_links;         // [L][lat_link_cap] {src state, dst state, arc, acoustic cost bits}
+    int2 *lat_final;         // [L][lat_final_cap] {state, final cost bits}
+    int *lat_tok_frame;      // [L][lat_tok_cap] frame of each lattice state
+    int *lat_tok_state;      // [L][lat_tok_cap] graph state (only when log_state is kept), else null
+    int lat_link_cap, lat_final_cap, lat_tok_cap;
+    unsigned long long *counters;     // [16] profiling counters (tokens, arcs, ...)
     int *lane_load;          // [lanes] largest token count a lane saw in this launch (load feedback)
     int grid;                // CTAs' worth of scratch allocated per slot
     // one launch serves lanes [lane_begin, lane_end): CTAs pull the next lane from *queue (zeroed before the launch; lanes
@@ -158,6 +182,8 @@ cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s);
 // encodes the TMA descriptor ([N][K] fp32, box 32 x min(N,256), SWIZZLE_128B) of a weight matrix into out128
 cudaError_t vbk_make_weight_map(const float *w, int N, int K, void *out128);
 cudaError_t vbk_decode(const DecArgs *a, int heavy, cudaStream_t s);
+// backward extra-cost pruning (lattice_beam) + compaction of the link log of the lanes whose stream ended in this step
+cudaError_t vbk_lattice_prune(const DecArgs *a, cudaStream_t s);
 int vbk_decode_max_grid(int device);
 // copies rows [t_begin, t_begin+n) of a node ring for one channel into dst (debug capture / tests)
 cudaError_t vbk_copy_rows(NodeDesc node, int channel, int t_begin, int n_rows, float *dst, cudaStream_t s);

@@ -143,15 +143,16 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model) { return model ? (
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
     if (!model || !out) return 0;
     BatchModel *bm = (BatchModel *)model;
-    double v[18] = {0};
+    double v[21] = {0};
     for (size_t i = 0; i < bm->num_engines(); i++) {
         vb::StepStats s = bm->engine(i).stats();
         v[0] += s.audio_seconds; v[1] += s.steps; v[2] += s.lanes; v[3] += s.launches;
         v[4] += s.tok; v[5] += s.arc_e; v[6] += s.arc_eps; v[7] += s.tok_new;
         v[8] += s.t_feat; v[9] += s.t_ivec; v[10] += s.t_nnet; v[11] += s.t_dec; v[12] += s.gemm_launches;
         v[13] += s.lane_cycles_sum; v[14] = std::max(v[14], (double)s.lane_cycles_max); v[15] = std::max(v[15], (double)s.max_tokens); v[16] += s.lane_launches; v[17] += s.host_launch_ms;
+        v[18] += s.arcs_staged; v[19] += s.links; v[20] += s.lat_arcs;
     }
-    int k = n < 18 ? n : 18;
+    int k = n < 21 ? n : 21;
     memcpy(out, v, k * sizeof(double));
     return k;
 }
@@ -223,6 +224,28 @@ int64_t vosk_batch_recognizer_debug_get(VoskBatchRecognizer *recognizer, const c
     else if (w == "tok_prev") set(c->tok_prev.data(), c->tok_prev.size() * 4);
     else if (w == "tok_cost") set(c->tok_cost.data(), c->tok_cost.size() * 4);
     else if (w == "error") set(&c->error, 4);
+    else if (w == "lat_hdr" || w == "lat_links" || w == "lat_final" || w == "lat_tok_frame" || w == "lat_tok_state") {
+        if (!c->lattice) return 0;
+        const vb::RawLattice &L = *c->lattice;
+        if (c->lat_hdr.empty()) {
+            c->lat_hdr = {L.n_states, (int)L.src.size(), (int)L.final_state.size(), L.start, L.error, L.frames};
+            for (size_t k = 0; k < L.src.size(); k++) {
+                int ab;
+                memcpy(&ab, &L.acoustic[k], 4);
+                c->lat_links.insert(c->lat_links.end(), {L.src[k], L.dst[k], L.arc[k], ab});
+            }
+            for (size_t k = 0; k < L.final_state.size(); k++) {
+                int fb;
+                memcpy(&fb, &L.final_cost[k], 4);
+                c->lat_final.insert(c->lat_final.end(), {L.final_state[k], fb});
+            }
+        }
+        if (w == "lat_hdr") set(c->lat_hdr.data(), c->lat_hdr.size() * 4);
+        else if (w == "lat_links") set(c->lat_links.data(), c->lat_links.size() * 4);
+        else if (w == "lat_final") set(c->lat_final.data(), c->lat_final.size() * 4);
+        else if (w == "lat_tok_frame") set(L.state_frame.data(), L.state_frame.size() * 4);
+        else set(L.state_graph.data(), L.state_graph.size() * 4);
+    }
     else return -1;
     if (out && cap > 0 && bytes > 0) memcpy(out, src, (size_t)(bytes < cap ? bytes : cap));
     return bytes;
