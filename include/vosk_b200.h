@@ -34,7 +34,9 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model);
  * [5] emitting arcs, [6] epsilon arcs, [7] tokens created, [8..11] device ms features / i-vector /
  * network / search (only when timing is on), [12] GEMM launches, [13] sum and [14] max of the SM cycles
  * one lane spent in a search launch, [15] largest token count of a frame, [16] lane-launches, [17] host ms spent enqueueing steps,
- * [18] arcs parked below the running cutoff, [19] lattice links logged, [20] lattice arcs kept after pruning.
+ * [18] arcs parked below the running cutoff, [19] lattice links logged, [20] lattice arcs kept after pruning,
+ * [21..28] / [29..36] SM cycles the 1024-thread / smaller search CTAs spent per phase (cutoff, rank, log, gather,
+ * insert, closure, finalize, unused).
  * Returns the number written. */
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n);
 void vosk_batch_model_reset_stats(VoskBatchModel *model);

@@ -38,6 +38,11 @@ def lib():
         _LIB.orc_decoder_num_tokens.restype = C.c_int64
         _LIB.orc_decoder_tokens.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         _LIB.orc_decoder_best_path.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _LIB.orc_decoder_num_links.argtypes = [C.c_void_p]
+        _LIB.orc_decoder_num_links.restype = C.c_int64
+        _LIB.orc_decoder_lattice.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        _LIB.orc_decoder_lattice.restype = C.c_int64
         _LIB.orc_align_words.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _LIB.orc_result_json.restype = C.c_void_p
         _LIB.orc_result_json.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
@@ -212,8 +217,6 @@ def decode(model, loglikes, **over):
                    best_arcs=arcs[:n].copy(), best_cost=tot.value, reached_final=bool(rf.value))
         if "lattice_beam" in over or "lattice-beam" in model["conf"]:
             lb = float(over.get("lattice_beam", model["conf"].get("lattice-beam", 6.0)))
-            L.orc_decoder_num_links.restype = C.c_int64
-            L.orc_decoder_lattice.restype = C.c_int64
             cap = int(L.orc_decoder_num_links(h))
             tok_index = np.zeros(max(nt, 1), dtype=np.int64)
             lsrc = np.zeros(max(cap, 1), dtype=np.int64)
@@ -224,8 +227,8 @@ def decode(model, loglikes, **over):
             fco = np.zeros(max(nt, 1), dtype=np.float32)
             ns = C.c_int64()
             nfin = C.c_int64()
-            nl = L.orc_decoder_lattice(h, C.byref(G), C.c_float(lb), C.byref(ns), _p(tok_index), _p(lsrc), _p(ldst), _p(larc), _p(lac),
-                                       C.c_int64(cap), _p(fst), _p(fco), C.byref(nfin))
+            nl = L.orc_decoder_lattice(h, C.byref(G), lb, C.byref(ns), _p(tok_index), _p(lsrc), _p(ldst), _p(larc), _p(lac),
+                                       cap, _p(fst), _p(fco), C.byref(nfin))
             frame_of = np.searchsorted(offsets, tok_index[:ns.value], side="right") - 1
             out["lattice"] = dict(tok_index=tok_index[:ns.value].copy(), frame=frame_of.astype(np.int32),
                                   state=state[tok_index[:ns.value]].copy(), src=lsrc[:nl].copy(), dst=ldst[:nl].copy(),

@@ -120,3 +120,16 @@ def test_lattice_generation(model_root, oracle_lib, arch, lb):
     assert stats["links"] > 0 and stats["lattice_arcs"] > 0
     for w, g in zip(waves, got):
         _check_stream(model, oracle_lib, w, g, 51, lattice_beam=lb)
+
+
+def test_pipelined_steps_give_the_oracle_transcripts(model_root, oracle_lib):
+    """No test taps: steps overlap (front end of step s+1 beside the search of step s, several chunks of a stream in
+    flight); more streams than lanes and channels.  Transcripts and word timings must equal the oracle pipeline's."""
+    import vbmodel
+    mdir = model_root("small")
+    model = vbmodel.load_model_dir(mdir)
+    waves = _waves([3.3, 1.2, 4.1, 2.6, 0.4, 3.9, 2.2, 1.7, 3.0], seed0=1100)
+    for opts in ("num-channels=6,max-batch-size=4,max-seconds=10,pipeline-slots=3", "num-channels=16,max-batch-size=16,max-seconds=10,lattice=1"):
+        got, stats = helpers.run_engine(mdir, waves, options=opts, capture=False, bytes_per_call=32000)
+        for w, g in zip(waves, got):
+            assert g["text"] == oracle_lib.recognize(model, w, stages=True)["text"]

@@ -73,6 +73,7 @@ struct Shared {
     int sel_k;
     unsigned red_u[(NT / 32)];
     unsigned long long red_ull[(NT / 32)];
+    long long phase[8];  // cycles per phase of this CTA (tid 0), flushed to counters[16..23] of the heavy / [24..31] of the light variants
     int own[(NT / 32)][2][32];  // per-warp marker arrays of the arc-window owner scan (two windows in flight)
 };
 
@@ -433,6 +434,15 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
           a.sv_pref + g * a.tok_cap, a.sv_a0 + g * a.tok_cap, a.sv_src + g * a.tok_cap, a.win_owner + g * nwin_cap,
           a.sv_cost + g * a.tok_cap,
           tid, tid >> 5, tid & 31, true, (unsigned)a.hash_size - 1};
+    long long tph = 0;
+    if (tid == 0)
+        for (int k = 0; k < 8; k++) sh.phase[k] = 0;
+#define VB_PHASE(k)                                   \
+    if (tid == 0 && a.counters) {                     \
+        const long long t_ = clock64();               \
+        sh.phase[k] += t_ - tph;                      \
+        tph = t_;                                     \
+    }
     unsigned long long cnt_tok = 0, cnt_arc_e = 0, cnt_arc_eps = 0, cnt_new = 0, cnt_stage = 0, cnt_links = 0;  // per-thread profiling counters
     const int npdf = a.out_node.dim;
     for (;;) {
@@ -500,6 +510,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             int *n_prev = a.tok_prev + tbase + (size_t)(parity ^ 1) * a.tok_cap;
             if (n_cur == 0 && !final_pass) { frame++; continue; }  // search died: nothing to expand
             max_tok = max(max_tok, n_cur);
+            if (tid == 0) tph = clock64();
             float adaptive_beam = a.beam, best = 0.f, cur_cutoff = INFINITY;
             if (!final_pass) {
                 // stage this frame's log-likelihood row
@@ -532,6 +543,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 sh.n_next = 0;
                 sh.n_links = 0;
             }
+            VB_PHASE(0)
             // ---- pass A: per-warp counts of survivors, survivors with out-arcs, and out-arcs ----
             const int span = ((n_cur + (NT / 32) - 1) / (NT / 32) + 31) & ~31;
             const int wbeg = min(c.warp * span, n_cur), wend = min(wbeg + span, n_cur);
@@ -617,6 +629,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 abase += __shfl_sync(0xffffffffu, incl, 31);
             }
             __syncthreads();
+            VB_PHASE(1)
             // ---- pass C1: token log of the survivors (prev of an epsilon-created token = a survivor of this frame) ----
             if (log_ok) {
                 for (int i = tid; i < n_cur; i += NT) {
@@ -663,6 +676,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 __syncthreads();
                 break;
             }
+            VB_PHASE(2)
             // ---- pass C2a: gather.  Two 32-arc windows per warp iteration, all loads of a stage issued before their
             // first use; arcs below the running cutoff are parked as candidate records {arc, cost, next state, src} ----
             cnt_arc_e += tid == 0 ? (unsigned)n_arcs : 0u;
@@ -738,6 +752,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             if (tid == 0 && sh.n_cand > a.cand_cap) sh.error = 2;
             const int n_emit = min(sh.n_cand, a.cand_cap);
             cnt_stage += tid == 0 ? (unsigned)n_emit : 0u;
+            VB_PHASE(3)
             // ---- pass C2b: insertion of the records below the FINAL cutoff (thread per record) ----
             for (int i = tid; i < n_emit; i += NT) {
                 const int4 cd = c.cand[i];
@@ -758,8 +773,11 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 reinterpret_cast<int *>(c.cand + i)[2] = z;
             }
             __syncthreads();
+            VB_PHASE(4)
             const int nc = closure(c, 0, n_emit, next_cutoff, &cnt_arc_eps);
+            VB_PHASE(5)
             finalize_tokens(c, n_emit, nc, next_cutoff, cost_offset, links, link_count, n_state, n_cost, n_arc, n_prev);
+            VB_PHASE(6)
             if (a.lattice) {
                 cnt_links += tid == 0 ? (unsigned)sh.n_links : 0u;
                 link_count = min(link_count + sh.n_links, a.link_cap);
@@ -844,6 +862,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             atomicAdd(a.counters + 3, cnt_new);
             atomicAdd(a.counters + 8, cnt_stage);
             atomicAdd(a.counters + 9, cnt_links);
+            for (int k = 0; k < 8; k++) atomicAdd(a.counters + (NT >= 1024 ? 16 : 24) + k, (unsigned long long)sh.phase[k]);
         }
         if ((tid & 31) == 0 && cnt_arc_eps) atomicAdd(a.counters + 2, cnt_arc_eps);
     }

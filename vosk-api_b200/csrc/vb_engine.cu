@@ -40,6 +40,7 @@ Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg)
     if (cfg_.max_lanes > 1024) cfg_.max_lanes = 1024;
     if (cfg_.max_lanes > cfg_.num_channels) cfg_.max_lanes = cfg_.num_channels;
     if (cfg_.pipeline_slots < 1) cfg_.pipeline_slots = 1;
+    if (cfg_.debug_capture) cfg_.pipeline_slots = 1;  // the test taps read per-channel state right after each step
     if (cfg_.pipeline_slots > 8) cfg_.pipeline_slots = 8;
     if (cfg_.hash_size & (cfg_.hash_size - 1)) throw std::runtime_error("hash-size must be a power of two");
     if (model.graph.has_negative_eps)
@@ -50,6 +51,9 @@ Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg)
         throw std::runtime_error(std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range"));
     VB_CUDA_CHECK(cudaSetDevice(cfg_.device));
     VB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    VB_CUDA_CHECK(cudaStreamCreateWithFlags(&fe_stream_, cudaStreamNonBlocking));
+    VB_CUDA_CHECK(cudaStreamCreateWithFlags(&dec_stream_, cudaStreamNonBlocking));
+    VB_CUDA_CHECK(cudaStreamCreateWithFlags(&dec_stream2_, cudaStreamNonBlocking));
     upload_model();
     alloc_state();
     thread_ = std::thread([this] { worker(); });
@@ -64,6 +68,8 @@ Engine::~Engine() {
     if (thread_.joinable()) thread_.join();
     cudaSetDevice(cfg_.device);
     cudaStreamSynchronize(stream_);
+    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_})
+        if (q) cudaStreamSynchronize(q);
     for (void *p : allocs_) cudaFree(p);
     for (Slot &sl : slots_) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
@@ -80,10 +86,12 @@ Engine::~Engine() {
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.fork) cudaEventDestroy(sl.fork);
         if (sl.join) cudaEventDestroy(sl.join);
-        if (sl.stream2) cudaStreamDestroy(sl.stream2);
+        if (sl.fe_done) cudaEventDestroy(sl.fe_done);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (h_capture_) cudaFreeHost(h_capture_);
+    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_})
+        if (q) cudaStreamDestroy(q);
     cudaStreamDestroy(stream_);
 }
 
@@ -260,7 +268,7 @@ void Engine::alloc_state() {
     const int C = cfg_.num_channels, F = model_.feat_dim, D = model_.ivec_dim;
     const int spc = samples_per_chunk();
     const int nn = (int)nodes_.size();
-    slot_lanes_ = std::max(1, (cfg_.max_lanes + cfg_.pipeline_slots - 1) / cfg_.pipeline_slots);
+    slot_lanes_ = std::max(1, cfg_.max_lanes);
     const int L = slot_lanes_;
     iv_state_.cmvn_sum = dev_alloc<double>(allocs_, (size_t)C * F, 0);
     iv_state_.norm_ring = dev_alloc<float>(allocs_, (size_t)C * kNormRing * F, 0);
@@ -299,7 +307,7 @@ void Engine::alloc_state() {
     d.log_state = cfg_.debug_capture ? dev_alloc<int>(allocs_, (size_t)C * log_cap_) : nullptr;
     d.log_frame_off = dev_alloc<int>(allocs_, (size_t)C * (max_frames_ + 2), 0);
     d.path = dev_alloc<int>(allocs_, (size_t)C * path_cap_, 0);
-    d.counters = dev_alloc<unsigned long long>(allocs_, 16, 0);
+    d.counters = dev_alloc<unsigned long long>(allocs_, 32, 0);
     d.lattice = cfg_.lattice;
     d.lattice_beam = cfg_.lattice_beam;
     if (cfg_.lattice) {
@@ -313,14 +321,35 @@ void Engine::alloc_state() {
         d.lat_final_cap = cfg_.tok_cap;
     }
     d.grid = std::min(vbk_decode_max_grid(cfg_.device), L);
-    // pipeline slots: stream, staging, per-step tables, search scratch
+    {   // search scratch, one copy: the searches of all steps run in order on dec_stream_
+        const size_t G = (size_t)d.grid;
+        d.hash_key = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0xff);
+        d.hash_val = dev_alloc<unsigned long long>(allocs_, G * cfg_.hash_size, 0xff);
+        d.hash_tok = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0);
+        d.cand = dev_alloc<int4>(allocs_, G * cfg_.cand_cap);
+        d.cand_next = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
+        d.rank = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+        d.sv_pref = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+        d.sv_a0 = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+        d.sv_src = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
+        d.sv_cost = dev_alloc<float>(allocs_, G * cfg_.tok_cap);
+        d.win_owner = dev_alloc<int>(allocs_, G * (cfg_.cand_cap / 32 + 2), 0);
+    }
+    // a slot is reused only after its step completed, so the front end runs at most (slots - 1) steps ahead of the
+    // search: the log-likelihood ring must hold that many chunks beside the one being searched
+    {
+        const int rows_per_chunk = cfg_.frames_per_chunk / kSubsample + 2;
+        const int depth = std::max(1, nodes_.back().ring / rows_per_chunk);
+        if (cfg_.pipeline_slots > depth) cfg_.pipeline_slots = depth;
+    }
+    // pipeline slots: staging, per-step tables, result buffers
     slots_.resize(cfg_.pipeline_slots);
     active_slots_ = cfg_.pipeline_slots;
     for (Slot &sl : slots_) {
         VB_CUDA_CHECK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         for (auto &ev : sl.ev) VB_CUDA_CHECK(cudaEventCreate(&ev));
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
-        VB_CUDA_CHECK(cudaStreamCreateWithFlags(&sl.stream2, cudaStreamNonBlocking));
+        VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.fe_done, cudaEventDisableTiming));
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.fork, cudaEventDisableTiming));
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.join, cudaEventDisableTiming));
         sl.d_queue = dev_alloc<int>(allocs_, 2, 0);
@@ -338,12 +367,6 @@ void Engine::alloc_state() {
         sd = dec_;
         sd.out_table = sl.d_table + (size_t)(nn - 1) * L;
         sd.lane_load = sl.d_load;
-        const size_t G = (size_t)sd.grid;
-        sd.hash_key = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0xff);
-        sd.hash_val = dev_alloc<unsigned long long>(allocs_, G * cfg_.hash_size, 0xff);
-        sd.hash_tok = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0);
-        sd.cand = dev_alloc<int4>(allocs_, G * cfg_.cand_cap);
-        sd.cand_next = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
         if (cfg_.lattice) {
             sd.lat_hdr = dev_alloc<LatHeader>(allocs_, (size_t)L, 0);
             sd.lat_links = dev_alloc<int4>(allocs_, (size_t)L * cfg_.lat_link_cap);
@@ -355,12 +378,6 @@ void Engine::alloc_state() {
             VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lat_final, (size_t)cfg_.tok_cap * sizeof(int2)));
             VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lat_tok, (size_t)2 * cfg_.lat_tok_cap * sizeof(int)));
         }
-        sd.rank = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
-        sd.sv_pref = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
-        sd.sv_a0 = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
-        sd.sv_src = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
-        sd.sv_cost = dev_alloc<float>(allocs_, G * cfg_.tok_cap);
-        sd.win_owner = dev_alloc<int>(allocs_, G * (cfg_.cand_cap / 32 + 2), 0);
     }
     if (cfg_.debug_capture) {
         capture_floats_ = (size_t)(max_in_rows_ + 8) * std::max(model_.num_pdfs, F);
@@ -407,7 +424,7 @@ void Engine::wait() {
 }
 
 StepStats Engine::stats() {
-    unsigned long long c[16] = {};
+    unsigned long long c[32] = {};
     cudaSetDevice(cfg_.device);
     cudaMemcpy(c, dec_.counters, sizeof c, cudaMemcpyDeviceToHost);
     std::lock_guard<std::mutex> lk(stats_mu_);
@@ -423,91 +440,78 @@ StepStats Engine::stats() {
     s.arcs_staged = c[8];
     s.links = c[9];
     s.lat_arcs = c[10];
+    for (int k = 0; k < 16; k++) s.phase[k] = c[16 + k];
     return s;
 }
 void Engine::reset_stats() {
     cudaSetDevice(cfg_.device);
-    cudaMemset(dec_.counters, 0, 16 * sizeof(unsigned long long));
+    cudaMemset(dec_.counters, 0, 32 * sizeof(unsigned long long));
     std::lock_guard<std::mutex> lk(stats_mu_);
     stats_ = StepStats{};
 }
 
-// The batcher: keeps up to pipeline_slots lane groups in flight.  A stream has at most one chunk in flight
-// (it re-enters the ready queue when its step completes), so per-stream order is preserved across slots.
+// The batcher: keeps up to pipeline_slots steps in flight.  Steps complete in launch order (both pipes are in order),
+// so the slots form a ring: `head` is the oldest step in flight, `tail` the next free slot.  A stream goes back to the
+// ready queue as soon as its chunk has been launched — per-stream order is guaranteed by the pipes, not by waiting.
 void Engine::worker() {
     cudaSetDevice(cfg_.device);
-    int cur = 0, n_busy = 0;
+    int head = 0, tail = 0, n_busy = 0;
     for (;;) {
         {
             std::unique_lock<std::mutex> lk(mu_);
             cv_work_.wait(lk, [&] { return stop_ || !ready_.empty() || n_busy > 0; });
             if (stop_ && n_busy == 0) return;
         }
-        // pick the slot to service: a finished one if any (slots complete out of order: light batches overtake
-        // heavy ones), else a free one when streams are ready, else poll
-        int pick = -1;
-        for (int k = 0; k < (int)slots_.size() && pick < 0; k++) {
-            int i = (cur + k) % (int)slots_.size();
-            if (slots_[i].busy && cudaEventQuery(slots_[i].done) == cudaSuccess) pick = i;
+        const int nslots = std::min((int)slots_.size(), active_slots_.load());
+        bool have_ready;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            have_ready = !ready_.empty();
         }
-        if (pick < 0) {
-            bool have_ready;
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                have_ready = !ready_.empty();
+        // complete the oldest step when it is done, or when nothing else can be started
+        if (n_busy > 0) {
+            Slot &old = slots_[head];
+            const bool must = n_busy >= nslots || !have_ready;
+            if (must || cudaEventQuery(old.done) == cudaSuccess) {
+                try {
+                    complete_step(old);
+                } catch (const std::exception &ex) {
+                    log_msg(-1, "engine step failed: %s", ex.what());
+                    for (auto &ln : old.lanes)
+                        if (ln.chunk.last && ln.s->on_result) {
+                            BestPath bp;
+                            bp.error = 100;
+                            ln.s->on_result(bp);
+                        }
+                }
+                old.busy = false;
+                n_busy--;
+                head = (head + 1) % (int)slots_.size();
+                {
+                    std::lock_guard<std::mutex> lk(mu_);
+                    for (auto &ln : old.lanes) {
+                        ln.s->pending_chunks.fetch_sub(1);
+                        if (ln.chunk.last) {
+                            free_channels_.push_back(ln.s->channel);
+                            ln.s->channel = -1;
+                        }
+                    }
+                    outstanding_ -= (long long)old.lanes.size();
+                }
+                old.lanes.clear();
+                cv_done_.notify_all();
+                continue;
             }
-            if (have_ready)
-                for (int i = 0; i < active_slots_.load() && pick < 0; i++)
-                    if (!slots_[i].busy) pick = i;
         }
-        if (pick < 0) {
+        if (!have_ready || n_busy >= nslots) {
             std::this_thread::yield();
             continue;
         }
-        cur = pick;
-        Slot &sl = slots_[cur];
-        if (sl.busy) {
-            try {
-                complete_step(sl);
-            } catch (const std::exception &ex) {
-                log_msg(-1, "engine step failed: %s", ex.what());
-                for (auto &ln : sl.lanes)
-                    if (ln.chunk.last && ln.s->on_result) {
-                        BestPath bp;
-                        bp.error = 100;
-                        ln.s->on_result(bp);
-                    }
-            }
-            sl.busy = false;
-            n_busy--;
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                for (auto &ln : sl.lanes) {
-                    ln.s->pending_chunks.fetch_sub(1);
-                    if (ln.chunk.last) {
-                        free_channels_.push_back(ln.s->channel);
-                        ln.s->channel = -1;
-                        ln.s->queued = false;
-                    } else if (!ln.s->pending.empty()) {
-                        ready_.push_back(ln.s);
-                    } else {
-                        ln.s->queued = false;
-                    }
-                }
-                outstanding_ -= (long long)sl.lanes.size();
-            }
-            sl.lanes.clear();
-            cv_done_.notify_all();
-        }
+        Slot &sl = slots_[tail];
         bool starved = false;
         {
             std::unique_lock<std::mutex> lk(mu_);
-            std::deque<std::shared_ptr<Stream>> deferred;
-            // group streams of similar load: a step lasts as long as its heaviest lane, so mixing a few heavy
-            // streams into every batch would stall all the light ones (stable sort keeps FIFO among equals)
-            if ((int)ready_.size() > slot_lanes_)
-                std::stable_sort(ready_.begin(), ready_.end(),
-                                 [](const std::shared_ptr<Stream> &x, const std::shared_ptr<Stream> &y) { return x->load > y->load; });
+            std::deque<std::shared_ptr<Stream>> deferred, again;
             while (!ready_.empty() && (int)sl.lanes.size() < slot_lanes_) {
                 std::shared_ptr<Stream> s = ready_.front();
                 ready_.pop_front();
@@ -523,24 +527,28 @@ void Engine::worker() {
                 ln.s = s;
                 ln.chunk = std::move(s->pending.front());
                 s->pending.pop_front();
+                if (!s->pending.empty()) again.push_back(s);  // next chunk: a later step (one chunk per stream per step)
+                else s->queued = false;
                 sl.lanes.push_back(std::move(ln));
             }
             starved = sl.lanes.empty() && !deferred.empty() && n_busy == 0;
             for (auto it = deferred.rbegin(); it != deferred.rend(); ++it) ready_.push_front(*it);
+            for (auto &s : again) ready_.push_back(s);
             if (starved) cv_work_.wait_for(lk, std::chrono::milliseconds(1));
         }
-        if (!sl.lanes.empty()) {
-            try {
-                launch_step(sl, resident_audio_, resident_stride_);
-                sl.busy = true;
-                n_busy++;
-            } catch (const std::exception &ex) {
-                log_msg(-1, "engine launch failed: %s", ex.what());
-                sl.busy = true;  // let the completion path release the lanes
-                n_busy++;
-            }
+        if (sl.lanes.empty()) {
+            if (!starved) std::this_thread::yield();
+            continue;
         }
-        cur = (cur + 1) % (int)slots_.size();
+        try {
+            launch_step(sl, resident_audio_, resident_stride_);
+        } catch (const std::exception &ex) {
+            log_msg(-1, "engine launch failed: %s", ex.what());
+            cudaEventRecord(sl.done, dec_stream_);  // let the completion path release the lanes
+        }
+        sl.busy = true;
+        n_busy++;
+        tail = (tail + 1) % (int)slots_.size();
     }
 }
 
@@ -551,7 +559,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     const int ctx = model_.context, spc = samples_per_chunk();
     const int nn = (int)nodes_.size();
     const int SL = slot_lanes_;
-    cudaStream_t st = sl.stream;
+    cudaStream_t st = fe_stream_;
     // heaviest lanes first: the search kernels pull lanes from a queue in this order (longest first), and the lanes
     // above heavy_tokens form a prefix that gets the 1024-thread CTAs
     std::stable_sort(lanes.begin(), lanes.end(), [](const Lane &x, const Lane &y) { return x.s->load > y.s->load; });
@@ -630,6 +638,11 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         sl.gemms++;
     }
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[3], st));
+    VB_CUDA_CHECK(cudaEventRecord(sl.fe_done, st));
+    // ---- search pipe ----
+    st = dec_stream_;
+    VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.fe_done, 0));
+    if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[5], st));
     sl.dec.lanes = sl.d_lanes;
     sl.dec.num_lanes = L;
     int n_heavy = 0;
@@ -642,7 +655,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     const bool split = n_heavy > 0 && n_heavy < L;
     if (split) {  // the light lanes run beside the heavy ones on the slot's second stream
         VB_CUDA_CHECK(cudaEventRecord(sl.fork, st));
-        VB_CUDA_CHECK(cudaStreamWaitEvent(sl.stream2, sl.fork, 0));
+        VB_CUDA_CHECK(cudaStreamWaitEvent(dec_stream2_, sl.fork, 0));
     }
     if (n_heavy > 0) {
         VB_CUDA_CHECK(vbk_decode(&sl.dec, cfg_.heavy_threads, st));
@@ -654,10 +667,10 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         light.lane_begin = n_heavy;
         light.lane_end = L;
         light.scratch_base = std::min(n_heavy, vbk_decode_max_grid(cfg_.device) / (cfg_.heavy_threads >= 1024 ? 3 : 1));  // CTAs the heavy launch can have
-        VB_CUDA_CHECK(vbk_decode(&light, cfg_.light_threads, split ? sl.stream2 : st));
+        VB_CUDA_CHECK(vbk_decode(&light, cfg_.light_threads, split ? dec_stream2_ : st));
         sl.launches++;
         if (split) {
-            VB_CUDA_CHECK(cudaEventRecord(sl.join, sl.stream2));
+            VB_CUDA_CHECK(cudaEventRecord(sl.join, dec_stream2_));
             VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.join, 0));
         }
     }
@@ -735,8 +748,10 @@ void Engine::complete_step(Slot &sl) {
     }
     {
         float ms[4] = {0, 0, 0, 0};
-        if (sl.timed)
-            for (int k = 0; k < 4; k++) cudaEventElapsedTime(&ms[k], sl.ev[k], sl.ev[k + 1]);
+        if (sl.timed) {
+            for (int k = 0; k < 3; k++) cudaEventElapsedTime(&ms[k], sl.ev[k], sl.ev[k + 1]);
+            cudaEventElapsedTime(&ms[3], sl.ev[5], sl.ev[4]);
+        }
         std::lock_guard<std::mutex> lk(stats_mu_);
         stats_.t_feat += ms[0];
         stats_.t_ivec += ms[1];

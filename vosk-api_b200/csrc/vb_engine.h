@@ -77,7 +77,8 @@ struct StepStats {
     long long steps = 0, lanes = 0, launches = 0;
     unsigned long long tok = 0, arc_e = 0, arc_eps = 0, tok_new = 0;
     unsigned long long lane_cycles_sum = 0, lane_cycles_max = 0, max_tokens = 0, lane_launches = 0;
-    unsigned long long arcs_staged = 0, links = 0, lat_arcs = 0;  // arcs parked below the running cutoff, links logged, lattice arcs kept
+    unsigned long long arcs_staged = 0, links = 0, lat_arcs = 0;
+    unsigned long long phase[16] = {};  // search cycles per phase (cutoff, rank, log, gather, insert, closure, finalize, -) of the heavy / light CTAs  // arcs parked below the running cutoff, links logged, lattice arcs kept
     double t_feat = 0, t_ivec = 0, t_nnet = 0, t_dec = 0, t_total = 0;  // device ms (only when timing enabled)
     long long dec_launches = 0, gemm_launches = 0;
     double host_launch_ms = 0;  // host time spent enqueueing steps
@@ -111,14 +112,17 @@ class Engine {
         Stream::Chunk chunk;
         int dec_frames_after = 0;
     };
-    // One pipeline slot = one lane group in flight on its own CUDA stream.  Slots only share read-only model
-    // data and the per-channel state of disjoint streams, so kernels of different slots overlap on the GPU
-    // (a latency-bound search launch of one group runs under the GEMMs / feature kernels of another).
+    // One pipeline slot = the buffers of one engine step (one chunk for each of up to max_lanes streams).  Steps flow
+    // through two in-order pipes: the front end (H2D, features, i-vector, TDNN-F) on fe_stream_ and the search
+    // (beam search, lattice pruning, D2H of results) on dec_stream_.  The search of step s only waits for the front end
+    // of step s, so the front end of step s+1 runs beside it; a stream may have one chunk in every slot, and a slot is
+    // reused only after its step has completed, which also bounds how far the front end runs ahead of the search in
+    // the log-likelihood rings.
     struct Slot {
-        cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: the light-lane search launch of a step (forked/joined by events)
-        cudaEvent_t fork = nullptr, join = nullptr;
+        cudaStream_t stream = nullptr;  // utility stream (debug taps, lattice fetch) of the slot
+        cudaEvent_t fe_done = nullptr, fork = nullptr, join = nullptr;
         int *d_queue = nullptr;  // [2] lane queues of the two search launches
-        cudaEvent_t ev[5] = {};
+        cudaEvent_t ev[6] = {};
         cudaEvent_t done = nullptr;
         int16_t *d_staging = nullptr, *h_staging = nullptr;
         LaneDesc *d_lanes = nullptr, *h_lanes = nullptr;
@@ -148,6 +152,7 @@ class Engine {
     const Model &model_;
     Config cfg_;
     cudaStream_t stream_ = nullptr;  // setup / utility stream
+    cudaStream_t fe_stream_ = nullptr, dec_stream_ = nullptr, dec_stream2_ = nullptr;  // the two pipes (+ the light-lane search launch)
     std::vector<Slot> slots_;
     bool timing_ = false;
     std::atomic<int> active_slots_{1};
