@@ -159,35 +159,57 @@ extern "C" cudaError_t vbk_mfcc(const FeatArgs *a, cudaStream_t s) {
 
 // =====================================================================================================
 // K1c — online CMN (600-frame window, global-stats smoothing), splice +-3, LDA, diag-UBM top-N posteriors,
-// i-vector statistics (double accumulation), per-chunk Cholesky solve.  One CTA per lane, one warp per frame.
+// i-vector statistics (double accumulation), per-chunk Cholesky solve.  One CTA per lane.  The frames of the chunk
+// are processed in tiles of kIvTB frames by block-wide passes whose operands live in shared memory / registers:
+//   LDA    : thread = (output dim, frame group); the 7-frame input window of the tile is staged once
+//   UBM    : thread = 2 Gaussians x all frames of the tile (32 register accumulators); every (mean, inv-var) pair is
+//            loaded once per tile and the normalised features are broadcast from shared memory as float4
+//   select : warp per frame (top-N by repeated warp arg-max), posteriors, occupancies
+//   linear : thread = (i-vector dim, (frame, Gaussian) group)
 // =====================================================================================================
 constexpr int kIvThreads = 256;
 constexpr int kIvWarps = kIvThreads / 32;
+constexpr int kIvTB = 16;           // frames per tile
 constexpr int kMaxGselect = 8;
-constexpr int kMaxIvecPerLane = 4;  // ivec_dim <= 128
 
-// dynamic smem: gamma[kIvWarps][G] floats | splice[kIvWarps][2][splice_dim] | feat[kIvWarps][2][F] |
-//               linw[kIvWarps][D] | glist[G] ints | doubles: A[D*D] b[D]
-static int ivec_smem_bytes(int G, int S, int F, int D) {
-    size_t fl = (size_t)kIvWarps * G + (size_t)kIvWarps * 2 * S + (size_t)kIvWarps * 2 * F + (size_t)kIvWarps * D + G + 8;
-    fl = (fl + 1) & ~(size_t)1;
-    return (int)(fl * 4 + ((size_t)D * D + D) * 8);
+struct IvLayout {  // shared-memory carve-up, in floats (doubles at the end)
+    int win_raw, win_nrm, fu, fnT, fn2T, ll, gamma, sel_g, sel_w, lin_part, glist, total_floats;
+    int cmn_tile;  // frames per CMN staging tile (aliases ll)
+};
+__host__ __device__ inline IvLayout iv_layout(int G, int F, int D) {
+    IvLayout L;
+    int o = 0;
+    L.win_raw = o; o += (kIvTB + 6) * F;
+    L.win_nrm = o; o += (kIvTB + 6) * F;
+    L.fu = o; o += kIvTB * F;
+    o = (o + 3) & ~3;
+    L.fnT = o; o += F * kIvTB;
+    L.fn2T = o; o += F * kIvTB;
+    L.ll = o; o += kIvTB * G;
+    L.gamma = o; o += kIvWarps * G;
+    L.sel_g = o; o += kIvTB * kMaxGselect;
+    L.sel_w = o; o += kIvTB * kMaxGselect;
+    L.lin_part = o; o += kIvThreads;
+    L.glist = o; o += G + 8;
+    L.total_floats = (o + 1) & ~1;
+    L.cmn_tile = (kIvTB * G) / (2 * F);
+    return L;
+}
+static int ivec_smem_bytes(int G, int F, int D) {
+    return iv_layout(G, F, D).total_floats * 4 + (D * D + D) * 8;
 }
 
-__global__ void __launch_bounds__(kIvThreads) ivector_kernel(IvecArgs a) {
+__global__ void __launch_bounds__(kIvThreads, 2) ivector_kernel(IvecArgs a) {
     extern __shared__ __align__(16) float smf[];
     const LaneDesc ln = a.lanes[blockIdx.x];
     const IvecModel &m = a.m;
     const int F = m.feat_dim, D = m.ivec_dim, G = m.num_gauss, S = m.splice_dim;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float *gamma = smf;
-    float *splice = gamma + kIvWarps * G;
-    float *feat = splice + kIvWarps * 2 * S;
-    float *linw = feat + kIvWarps * 2 * F;
-    int *glist = reinterpret_cast<int *>(linw + kIvWarps * D);
-    size_t fl = (size_t)kIvWarps * G + (size_t)kIvWarps * 2 * S + (size_t)kIvWarps * 2 * F + (size_t)kIvWarps * D + G + 8;
-    fl = (fl + 1) & ~(size_t)1;
-    double *A = reinterpret_cast<double *>(smf + fl);
+    const IvLayout L = iv_layout(G, F, D);
+    float *win_raw = smf + L.win_raw, *win_nrm = smf + L.win_nrm, *fu = smf + L.fu, *fnT = smf + L.fnT, *fn2T = smf + L.fn2T;
+    float *ll = smf + L.ll, *gamma = smf + L.gamma, *sel_w = smf + L.sel_w, *lin_part = smf + L.lin_part;
+    int *sel_g = reinterpret_cast<int *>(smf + L.sel_g), *glist = reinterpret_cast<int *>(smf + L.glist);
+    double *A = reinterpret_cast<double *>(smf + L.total_floats);
     double *bvec = A + D * D;
     __shared__ double s_totw[kIvWarps];
     __shared__ int s_nlist;
@@ -203,120 +225,204 @@ __global__ void __launch_bounds__(kIvThreads) ivector_kernel(IvecArgs a) {
         if (tid == 0) a.st.num_frames[ch] = 0.0;
     }
     for (int i = tid; i < kIvWarps * G; i += kIvThreads) gamma[i] = 0.f;
-    for (int i = tid; i < kIvWarps * D; i += kIvThreads) linw[i] = 0.f;
     if (tid < kIvWarps) s_totw[tid] = 0.0;
     __syncthreads();
-    // ---- A. sliding-window CMN over the new frames (thread per dimension, sequential in time) ----
-    if (tid < F) {
-        double s = cm_sum[tid];
-        for (int t = ln.frames_before; t < ln.frames_after; t++) {
-            float x = ring_row(a.in_node, ch, t)[tid];
-            s += (double)x;
-            if (t >= m.cmn_window) s -= (double)ring_row(a.in_node, ch, t - m.cmn_window)[tid];
-            double n = t + 1 < m.cmn_window ? t + 1 : m.cmn_window;
-            double fg = n < m.cmn_window ? fmin((double)m.cmn_window - n, (double)m.global_frames) : 0.0;
-            double tot = s;
-            if (fg > 0.0) tot += fg / m.gcmvn_count * m.gcmvn_sum[tid];
-            nring[(t & (kNormRing - 1)) * F + tid] = (float)((double)x - tot / (n + fg));
+    // ---- A. sliding-window CMN over the new frames: rows staged with coalesced loads, then thread per dimension ----
+    {
+        float *xin = ll, *xold = ll + L.cmn_tile * F;
+        for (int t0 = ln.frames_before; t0 < ln.frames_after; t0 += L.cmn_tile) {
+            const int n = min(L.cmn_tile, ln.frames_after - t0);
+            for (int i = tid; i < n * F; i += kIvThreads) {
+                const int t = t0 + i / F, d = i % F;
+                xin[i] = ring_row(a.in_node, ch, t)[d];
+                xold[i] = t >= m.cmn_window ? ring_row(a.in_node, ch, t - m.cmn_window)[d] : 0.f;
+            }
+            __syncthreads();
+            if (tid < F) {
+                double s = t0 == ln.frames_before ? cm_sum[tid] : cm_sum[tid];
+                for (int j = 0; j < n; j++) {
+                    const int t = t0 + j;
+                    const float x = xin[j * F + tid];
+                    s += (double)x;
+                    if (t >= m.cmn_window) s -= (double)xold[j * F + tid];
+                    const double nn = t + 1 < m.cmn_window ? t + 1 : m.cmn_window;
+                    const double fg = nn < m.cmn_window ? fmin((double)m.cmn_window - nn, (double)m.global_frames) : 0.0;
+                    double tot = s;
+                    if (fg > 0.0) tot += fg / m.gcmvn_count * m.gcmvn_sum[tid];
+                    nring[(t & (kNormRing - 1)) * F + tid] = (float)((double)x - tot / (nn + fg));
+                }
+                cm_sum[tid] = s;
+            }
+            __syncthreads();
         }
-        cm_sum[tid] = s;
     }
-    __syncthreads();
-    // ---- B. per frame: splice, LDA (raw + normalised), UBM posteriors, statistics ----
+    // ---- B. tiles of frames: splice, LDA (raw + normalised), UBM posteriors, statistics ----
     const int last_avail = ln.frames_after - 1;
-    float *xs = splice + warp * 2 * S, *xn = xs + S;
-    float *fu = feat + warp * 2 * F, *fn = fu + F;
-    float lin_acc[kMaxIvecPerLane] = {0.f, 0.f, 0.f, 0.f};
+    const int ng = min(m.num_gselect, G);
+    const int ngF = kIvThreads / F, ngD = kIvThreads / D;
+    float lin_acc = 0.f;
     double totw = 0.0;
-    for (int t = ln.iv_end_before + warp; t < ln.iv_end_after; t += kIvWarps) {
-        for (int i = lane; i < S; i += 32) {
-            int o = i / F - 3, d = i % F;
-            int tt = min(max(t + o, 0), last_avail);
-            xs[i] = ring_row(a.in_node, ch, tt)[d];
-            xn[i] = nring[(tt & (kNormRing - 1)) * F + d];
+    for (int tb = ln.iv_end_before; tb < ln.iv_end_after; tb += kIvTB) {
+        const int nb = min(kIvTB, ln.iv_end_after - tb);
+        for (int i = tid; i < (nb + 6) * F; i += kIvThreads) {
+            const int r = i / F, d = i % F;
+            const int tt = min(max(tb + r - 3, 0), last_avail);
+            win_raw[i] = ring_row(a.in_node, ch, tt)[d];
+            win_nrm[i] = nring[(tt & (kNormRing - 1)) * F + d];
         }
-        __syncwarp();
-        for (int d = lane; d < F; d += 32) {
-            float su = __ldg(m.lda_t + (size_t)S * F + d), sn = su;
-            for (int k = 0; k < S; k++) {
-                float w = __ldg(m.lda_t + (size_t)k * F + d);
-                su = fmaf(w, xs[k], su);
-                sn = fmaf(w, xn[k], sn);
-            }
-            fu[d] = su;
-            fn[d] = sn;
-        }
-        __syncwarp();
-        // diag-UBM log-likelihoods: lane owns gaussians lane, lane+32, ...
-        float best_v[kMaxGselect];
-        int best_g[kMaxGselect];
-        const int per = (G + 31) / 32;
-        // keep this lane's values in a small local array (G <= 1024)
-        float llv[32];
-        for (int j = 0; j < per; j++) {
-            int g = lane + 32 * j;
-            float s = -FLT_MAX;
-            if (g < G) {
-                s = __ldg(m.gconsts + g);
-                for (int d = 0; d < F; d++) {
-                    float x = fn[d];
-                    s += __ldg(m.mi_t + (size_t)d * G + g) * x - 0.5f * __ldg(m.iv_t + (size_t)d * G + g) * x * x;
+        __syncthreads();
+        // B1. LDA: out[t][d] = offset[d] + sum_k lda[k][d] * splice(t)[k]; splice(t)[o*F + kd] = win[t + o][kd]
+        if (tid < ngF * F) {
+            const int d = tid % F, tg = tid / F;
+            for (int t0 = tg; t0 < nb; t0 += 3 * ngF) {
+                const int t1 = t0 + ngF, t2 = t0 + 2 * ngF;
+                const int r0 = t0, r1 = min(t1, nb - 1), r2 = min(t2, nb - 1);  // rows beyond the tile repeat the last one (discarded)
+                const float off = __ldg(m.lda_t + (size_t)S * F + d);
+                float u0 = off, u1 = off, u2 = off, n0 = off, n1 = off, n2 = off;
+                for (int o = 0; o < 7; o++) {
+                    const float *w = m.lda_t + (size_t)o * F * F + d;
+                    const float *xr0 = win_raw + (r0 + o) * F, *xr1 = win_raw + (r1 + o) * F, *xr2 = win_raw + (r2 + o) * F;
+                    const float *xn0 = win_nrm + (r0 + o) * F, *xn1 = win_nrm + (r1 + o) * F, *xn2 = win_nrm + (r2 + o) * F;
+#pragma unroll 4
+                    for (int kd = 0; kd < F; kd++) {
+                        const float wv = __ldg(w + (size_t)kd * F);
+                        u0 = fmaf(wv, xr0[kd], u0);
+                        u1 = fmaf(wv, xr1[kd], u1);
+                        u2 = fmaf(wv, xr2[kd], u2);
+                        n0 = fmaf(wv, xn0[kd], n0);
+                        n1 = fmaf(wv, xn1[kd], n1);
+                        n2 = fmaf(wv, xn2[kd], n2);
+                    }
                 }
-            }
-            llv[j] = s;
-        }
-        const int ng = min(m.num_gselect, G);
-        for (int r = 0; r < ng; r++) {
-            float bv = -FLT_MAX;
-            int bg = 0x7fffffff;
-            for (int j = 0; j < per; j++)
-                if (llv[j] > bv) { bv = llv[j]; bg = lane + 32 * j; }
-            for (int o = 16; o; o >>= 1) {
-                float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                int og = __shfl_xor_sync(0xffffffffu, bg, o);
-                if (ov > bv || (ov == bv && og < bg)) { bv = ov; bg = og; }
-            }
-            best_v[r] = bv;
-            best_g[r] = bg;
-            if ((bg & 31) == lane) llv[bg >> 5] = -FLT_MAX;
-        }
-        float post[kMaxGselect], tot = 0.f;
-        for (int r = 0; r < ng; r++) { post[r] = expf(best_v[r] - best_v[0]); tot += post[r]; }
-        float kept = 0.f;
-        for (int r = 0; r < ng; r++) {
-            post[r] /= tot;
-            if (r > 0 && post[r] < m.min_post) post[r] = 0.f;
-            kept += post[r];
-        }
-        for (int r = 0; r < ng; r++) {
-            float w = post[r] / kept * m.posterior_scale;
-            post[r] = w;
-            if (w != 0.f) {
-                if (lane == 0) gamma[warp * G + best_g[r]] += w;
-                totw += (double)w;
-            }
-        }
-        // linear term: lin[d] += w * sum_a SiM[g][a][d] * fu[a]
-        for (int r = 0; r < ng; r++) {
-            if (post[r] == 0.f) continue;
-            const float *sm_g = m.sim + (size_t)best_g[r] * F * D;
-#pragma unroll
-            for (int j = 0; j < kMaxIvecPerLane; j++) {
-                int d = lane + 32 * j;
-                if (d < D) {
-                    float s = 0.f;
-                    for (int q = 0; q < F; q++) s = fmaf(__ldg(sm_g + (size_t)q * D + d), fu[q], s);
-                    lin_acc[j] += post[r] * s;
+                fu[t0 * F + d] = u0;
+                fnT[d * kIvTB + t0] = n0;
+                fn2T[d * kIvTB + t0] = n0 * n0;
+                if (t1 < nb) {
+                    fu[t1 * F + d] = u1;
+                    fnT[d * kIvTB + t1] = n1;
+                    fn2T[d * kIvTB + t1] = n1 * n1;
+                }
+                if (t2 < nb) {
+                    fu[t2 * F + d] = u2;
+                    fnT[d * kIvTB + t2] = n2;
+                    fn2T[d * kIvTB + t2] = n2 * n2;
                 }
             }
         }
-        __syncwarp();
-    }
+        __syncthreads();
+        // B2. diag-UBM log-likelihoods of the tile: ll[t][g] = gconst[g] + sum_d (mi[d][g] x - 0.5 iv[d][g] x^2)
+        for (int g0 = tid; g0 < G; g0 += 2 * kIvThreads) {
+            const int g1 = g0 + kIvThreads;
+            const bool h1 = g1 < G;
+            const int g1c = h1 ? g1 : g0;
+            float acc0[kIvTB], acc1[kIvTB];
+            const float c0 = __ldg(m.gconsts + g0), c1 = __ldg(m.gconsts + g1c);
 #pragma unroll
-    for (int j = 0; j < kMaxIvecPerLane; j++) {
-        int d = lane + 32 * j;
-        if (d < D) linw[warp * D + d] = lin_acc[j];
+            for (int t = 0; t < kIvTB; t++) {
+                acc0[t] = c0;
+                acc1[t] = c1;
+            }
+            for (int d = 0; d < F; d++) {
+                const float mi0 = __ldg(m.mi_t + (size_t)d * G + g0), mi1 = __ldg(m.mi_t + (size_t)d * G + g1c);
+                const float iv0 = -0.5f * __ldg(m.iv_t + (size_t)d * G + g0), iv1 = -0.5f * __ldg(m.iv_t + (size_t)d * G + g1c);
+                const float4 *x4 = reinterpret_cast<const float4 *>(fnT + d * kIvTB), *q4 = reinterpret_cast<const float4 *>(fn2T + d * kIvTB);
+#pragma unroll
+                for (int q = 0; q < kIvTB / 4; q++) {
+                    const float4 x = x4[q], xx = q4[q];
+                    acc0[4 * q + 0] = fmaf(iv0, xx.x, fmaf(mi0, x.x, acc0[4 * q + 0]));
+                    acc0[4 * q + 1] = fmaf(iv0, xx.y, fmaf(mi0, x.y, acc0[4 * q + 1]));
+                    acc0[4 * q + 2] = fmaf(iv0, xx.z, fmaf(mi0, x.z, acc0[4 * q + 2]));
+                    acc0[4 * q + 3] = fmaf(iv0, xx.w, fmaf(mi0, x.w, acc0[4 * q + 3]));
+                    acc1[4 * q + 0] = fmaf(iv1, xx.x, fmaf(mi1, x.x, acc1[4 * q + 0]));
+                    acc1[4 * q + 1] = fmaf(iv1, xx.y, fmaf(mi1, x.y, acc1[4 * q + 1]));
+                    acc1[4 * q + 2] = fmaf(iv1, xx.z, fmaf(mi1, x.z, acc1[4 * q + 2]));
+                    acc1[4 * q + 3] = fmaf(iv1, xx.w, fmaf(mi1, x.w, acc1[4 * q + 3]));
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < kIvTB; t++) {
+                ll[t * G + g0] = acc0[t];
+                if (h1) ll[t * G + g1] = acc1[t];
+            }
+        }
+        __syncthreads();
+        // B3. per frame (warp): top-N Gaussians, posteriors (min_post pruning, posterior_scale), occupancies
+        for (int t = warp; t < nb; t += kIvWarps) {
+            const int per = (G + 31) / 32;  // G <= 1024
+            float llv[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int g = lane + 32 * j;
+                llv[j] = (j < per && g < G) ? ll[t * G + g] : -FLT_MAX;
+            }
+            float best_v[kMaxGselect];
+            int best_g[kMaxGselect];
+#pragma unroll
+            for (int r = 0; r < kMaxGselect; r++) {
+                best_v[r] = -FLT_MAX;
+                best_g[r] = 0;
+                if (r >= ng) continue;
+                float bv = -FLT_MAX;
+                int bg = 0x7fffffff;
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (llv[j] > bv) { bv = llv[j]; bg = lane + 32 * j; }
+                for (int o = 16; o; o >>= 1) {
+                    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    int og = __shfl_xor_sync(0xffffffffu, bg, o);
+                    if (ov > bv || (ov == bv && og < bg)) { bv = ov; bg = og; }
+                }
+                best_v[r] = bv;
+                best_g[r] = bg;
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if ((bg & 31) == lane && (bg >> 5) == j) llv[j] = -FLT_MAX;
+            }
+            float post[kMaxGselect], tot = 0.f;
+#pragma unroll
+            for (int r = 0; r < kMaxGselect; r++) {
+                post[r] = r < ng ? expf(best_v[r] - best_v[0]) : 0.f;
+                tot += post[r];
+            }
+            float kept = 0.f;
+#pragma unroll
+            for (int r = 0; r < kMaxGselect; r++) {
+                if (r >= ng) continue;
+                post[r] /= tot;
+                if (r > 0 && post[r] < m.min_post) post[r] = 0.f;
+                kept += post[r];
+            }
+#pragma unroll
+            for (int r = 0; r < kMaxGselect; r++) {
+                if (r >= ng) continue;
+                const float w = post[r] / kept * m.posterior_scale;
+                if (lane == 0) {
+                    sel_g[t * kMaxGselect + r] = best_g[r];
+                    sel_w[t * kMaxGselect + r] = w;
+                    if (w != 0.f) gamma[warp * G + best_g[r]] += w;
+                }
+                if (w != 0.f) totw += (double)w;
+            }
+        }
+        __syncthreads();
+        // B4. linear term: lin[d] += w * sum_a SiM[g][a][d] * fu[t][a]   (thread = dim x (frame, Gaussian) group)
+        if (tid < ngD * D) {
+            const int d = tid % D, pg = tid / D;
+            for (int p = pg; p < nb * ng; p += ngD) {
+                const int t = p / ng, r = p % ng;
+                const float w = sel_w[t * kMaxGselect + r];
+                if (w == 0.f) continue;
+                const float *sm_g = m.sim + (size_t)sel_g[t * kMaxGselect + r] * F * D + d;
+                const float *f = fu + t * F;
+                float s0 = 0.f;
+#pragma unroll 8
+                for (int q = 0; q < F; q++) s0 = fmaf(__ldg(sm_g + (size_t)q * D), f[q], s0);
+                lin_acc += w * s0;
+            }
+        }
+        __syncthreads();
     }
+    lin_part[tid] = tid < ngD * D ? lin_acc : 0.f;
     if (lane == 0) s_totw[warp] = totw;
     __syncthreads();
     // ---- C. fold the chunk's statistics into the channel state (fixed summation order) ----
@@ -355,7 +461,7 @@ __global__ void __launch_bounds__(kIvThreads) ivector_kernel(IvecArgs a) {
     }
     for (int d = tid; d < D; d += kIvThreads) {
         double s = 0.0;
-        for (int w = 0; w < kIvWarps; w++) s += (double)linw[w * D + d];
+        for (int pg = 0; pg < ngD; pg++) s += (double)lin_part[pg * D + d];
         if (d == 0) s += (double)m.prior_offset * change;
         double v = lin[d] + s;
         lin[d] = v;
@@ -404,8 +510,10 @@ __global__ void __launch_bounds__(kIvThreads) ivector_kernel(IvecArgs a) {
 
 extern "C" cudaError_t vbk_ivector(const IvecArgs *a, cudaStream_t s) {
     if (a->num_lanes <= 0) return cudaSuccess;
-    if (a->m.num_gauss > 1024 || a->m.ivec_dim > 32 * kMaxIvecPerLane || a->m.num_gselect > kMaxGselect) return cudaErrorInvalidValue;
-    int smem = ivec_smem_bytes(a->m.num_gauss, a->m.splice_dim, a->m.feat_dim, a->m.ivec_dim);
+    if (a->m.num_gauss > 1024 || a->m.ivec_dim > kIvThreads || a->m.feat_dim > kIvThreads || a->m.num_gselect > kMaxGselect ||
+        a->m.splice_dim != 7 * a->m.feat_dim)
+        return cudaErrorInvalidValue;
+    int smem = ivec_smem_bytes(a->m.num_gauss, a->m.feat_dim, a->m.ivec_dim);
     static int configured[16] = {};
     int dev = 0;
     cudaGetDevice(&dev);
