@@ -72,6 +72,13 @@ int vosk_b200_device_for_stream(unsigned long long stream_id, int num_devices);
 int vosk_b200_format_result(const char *const *words, const int *begin, const int *end, const float *conf, int n, float offset, char *out, int cap);
 int vosk_b200_resample(const float *in, int n, float rate_in, float *out, int cap);
 int vosk_b200_model_check(const char *model_dir, char *out, int cap);
+/* lattice_result: the host lattice chain (pruned word determinization, graph scale 0.9, word alignment, MBR) on an
+ * explicit raw lattice {states, start, links {src, dst, csr arc, acoustic cost}, finals}; stage 0 = result text,
+ * 1 = determinized lattice, 2 = word-aligned lattice as text lines ("S start", "A src dst word graph acoustic tids",
+ * "F state graph acoustic tids").  Returns the text length (copies at most cap-1 bytes), -1 on error. */
+int vosk_b200_lattice_result(const char *model_dir, int n_states, int start, int n_links, const int *src, const int *dst, const int *arc,
+                             const float *acoustic, int n_final, const int *final_state, const float *final_cost, float lattice_beam,
+                             int stage, char *out, int cap);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,7 @@ int orc_decoder_best_path(const OrcDecoder *d, int *arcs, int cap, float *total_
  * order (tok_index maps them to token indices of orc_decoder_tokens), links {src, dst, csr arc, acoustic cost}, final
  * states with their final costs.  Returns the number of links (writes at most cap_links). */
 int64_t orc_decoder_num_links(const OrcDecoder *d);
+void orc_decoder_cost_offsets(const OrcDecoder *d, float *out /* [frames decoded] -best token cost of each frame */);
 int64_t orc_decoder_lattice(const OrcDecoder *d, const OrcGraph *g, float lattice_beam, int64_t *n_states, int64_t *tok_index,
                             int64_t *lsrc, int64_t *ldst, int *larc, float *lac, int64_t cap_links,
                             int64_t *fin_state, float *fin_cost, int64_t *n_final);

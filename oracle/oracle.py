@@ -38,6 +38,7 @@ def lib():
         _LIB.orc_decoder_num_tokens.restype = C.c_int64
         _LIB.orc_decoder_tokens.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         _LIB.orc_decoder_best_path.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _LIB.orc_decoder_cost_offsets.argtypes = [C.c_void_p, C.c_void_p]
         _LIB.orc_decoder_num_links.argtypes = [C.c_void_p]
         _LIB.orc_decoder_num_links.restype = C.c_int64
         _LIB.orc_decoder_lattice.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -229,6 +230,9 @@ def decode(model, loglikes, **over):
             nfin = C.c_int64()
             nl = L.orc_decoder_lattice(h, C.byref(G), lb, C.byref(ns), _p(tok_index), _p(lsrc), _p(ldst), _p(larc), _p(lac),
                                        cap, _p(fst), _p(fco), C.byref(nfin))
+            coff = np.zeros(max(nf, 1), dtype=np.float32)
+            L.orc_decoder_cost_offsets(h, _p(coff))
+            out["cost_offset"] = coff[:nf].copy()
             frame_of = np.searchsorted(offsets, tok_index[:ns.value], side="right") - 1
             out["lattice"] = dict(tok_index=tok_index[:ns.value].copy(), frame=frame_of.astype(np.int32),
                                   state=state[tok_index[:ns.value]].copy(), src=lsrc[:nl].copy(), dst=ldst[:nl].copy(),

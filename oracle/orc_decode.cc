@@ -57,6 +57,7 @@ struct OrcDecoder {
     struct Link { int64_t src, dst; int arc; float ac; };
     std::vector<Link> links;
     std::vector<int64_t> link_off;  // segment f = links whose destination token is in frame f
+    std::vector<float> cost_offset; // per decoded frame
 };
 
 namespace {
@@ -195,6 +196,7 @@ extern "C" OrcDecoder *orc_decode(const OrcGraph *g, const OrcDecodeOpts *o, con
         float cur_cutoff = get_cutoff(costs, o, &adaptive_beam, &best);
         std::vector<int> sv = log_frame(cur, cur_cutoff, false);
         const float cost_offset = -best;
+        d->cost_offset.push_back(cost_offset);
         const float *ll = loglikes + (size_t)f * P;
         float min_tot = kInf;
         for (int s : sv) {
@@ -332,7 +334,10 @@ extern "C" int64_t orc_decoder_lattice(const OrcDecoder *d, const OrcGraph *g, f
             lsrc[nl] = newidx[l.src];
             ldst[nl] = newidx[l.dst];
             larc[nl] = l.arc;
-            lac[nl] = l.ac;
+            // GetRawLattice: Weight(graph_cost, acoustic_cost - cost_offsets_[frame]) for emitting arcs
+            bool eps = g->arc_pdf[l.arc] < 0;
+            int64_t fsrc = std::upper_bound(d->offsets.begin(), d->offsets.end(), l.src) - d->offsets.begin() - 1;
+            lac[nl] = eps ? 0.f : l.ac - d->cost_offset[fsrc];
         }
         nl++;
     }
@@ -349,6 +354,7 @@ extern "C" int64_t orc_decoder_lattice(const OrcDecoder *d, const OrcGraph *g, f
     return nl;
 }
 extern "C" int64_t orc_decoder_num_links(const OrcDecoder *d) { return (int64_t)d->links.size(); }
+extern "C" void orc_decoder_cost_offsets(const OrcDecoder *d, float *out) { memcpy(out, d->cost_offset.data(), d->cost_offset.size() * sizeof(float)); }
 
 // --------------------------------------------------------------------------------------------
 // word alignment of a linear path and result text

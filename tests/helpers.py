@@ -84,3 +84,50 @@ def canonical_lattice(frame, state, src, dst, arc, ac_bits, final_state, final_b
 
 def words_of(text):
     return json.loads(text).get("text", "")
+
+
+_LAT_HOOK = None
+
+
+def lattice_text(model_dir, oracle_lattice, start, lattice_beam, stage=0):
+    """Host lattice chain (vosk_b200_lattice_result, no GPU involved) on a raw lattice given as oracle.decode()["lattice"]."""
+    import ctypes
+    import os
+    global _LAT_HOOK
+    if _LAT_HOOK is None:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        lib = ctypes.CDLL(os.path.join(root, "vosk-api_b200", "lib", "libvosk.so"))
+        f = lib.vosk_b200_lattice_result
+        f.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                      ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+        f.restype = ctypes.c_int
+        _LAT_HOOK = f
+    lat = oracle_lattice
+    src = np.ascontiguousarray(lat["src"], dtype=np.int32)
+    dst = np.ascontiguousarray(lat["dst"], dtype=np.int32)
+    arc = np.ascontiguousarray(lat["arc"], dtype=np.int32)
+    ac = np.ascontiguousarray(lat["ac"], dtype=np.float32)
+    fs = np.ascontiguousarray(lat["final_state"], dtype=np.int32)
+    fc = np.ascontiguousarray(lat["final_cost"], dtype=np.float32)
+    cap = 1 << 22
+    buf = ctypes.create_string_buffer(cap)
+    n = _LAT_HOOK(model_dir.encode(), len(lat["tok_index"]), int(start), len(src), src.ctypes.data, dst.ctypes.data, arc.ctypes.data,
+                  ac.ctypes.data, len(fs), fs.ctypes.data, fc.ctypes.data, lattice_beam, stage, buf, cap)
+    assert 0 <= n < cap, buf.value
+    return buf.value.decode()
+
+
+def oracle_lattice_start(dec):
+    lat = dec["lattice"]
+    return int(np.flatnonzero((lat["frame"] == 0) & (dec["arc"][lat["tok_index"]] < 0))[0])
+
+
+def results_close(a, b, conf_tol=2e-2):
+    """Two result texts: same words and word times, confidences within conf_tol."""
+    ja, jb = json.loads(a), json.loads(b)
+    if ja.get("text") != jb.get("text"):
+        return False
+    for x, y in zip(ja.get("result", []), jb.get("result", [])):
+        if x["word"] != y["word"] or abs(x["start"] - y["start"]) > 1e-6 or abs(x["end"] - y["end"]) > 1e-6 or abs(x["conf"] - y["conf"]) > conf_tol:
+            return False
+    return True

@@ -15,7 +15,7 @@ def _waves(lengths, seed0=100):
     return [vbmodel.synth_audio(s, seed0 + i) for i, s in enumerate(lengths)]
 
 
-def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3, lattice_beam=6.0):
+def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3, lattice_beam=6.0, mdir=None):
     ref = oracle.recognize(model, wave, frames_per_chunk=fpc, stages=True)
     D = int(model["cfg"]["ivector-dim"])
     P = int(model["cfg"]["num-pdfs"])
@@ -43,7 +43,8 @@ def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3, lattice_beam=6.0):
         np.testing.assert_array_equal(ar, dec["arc"])
         np.testing.assert_array_equal(co.view(np.uint32), dec["cost"].view(np.uint32))
         np.testing.assert_array_equal(pv, dec["prev"])
-        assert got["text"] == oracle.result_json(model, dec["best_arcs"])
+        if "lat_hdr" not in got:
+            assert got["text"] == oracle.result_json(model, dec["best_arcs"])
         if "lat_hdr" in got:
             # raw lattice (links within lattice_beam, FinalizeDecoding pruning): bit-exact in canonical order
             lat = oracle.decode(model, ll, lattice_beam=lattice_beam)["lattice"]
@@ -58,6 +59,11 @@ def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3, lattice_beam=6.0):
             for x, y in zip(a, b):
                 np.testing.assert_array_equal(x, y)
             assert got["lat_tok_frame"][hdr[3]] == 0 and got["lat_tok_state"][hdr[3]] == model["graph"]["start"]
+            # result text: the host chain (determinize, scale, align, MBR) on the oracle's lattice, run without the GPU
+            ldec = oracle.decode(model, ll, lattice_beam=lattice_beam)
+            want = helpers.lattice_text(mdir, ldec["lattice"], helpers.oracle_lattice_start(ldec), lattice_beam)
+            assert helpers.results_close(got["text"], want, conf_tol=1e-4), (got["text"], want)
+            return
     # end to end: identical transcript and word timings against the pure-oracle pipeline
     assert got["text"] == ref["text"]
 
@@ -122,7 +128,7 @@ def test_lattice_generation(model_root, oracle_lib, arch, lb):
     got, stats = helpers.run_engine(mdir, waves, options=f"lattice=1,lattice-beam={lb},num-channels=4,max-batch-size=4,max-seconds=10")
     assert stats["links"] > 0 and stats["lattice_arcs"] > 0
     for w, g in zip(waves, got):
-        _check_stream(model, oracle_lib, w, g, 51, lattice_beam=lb)
+        _check_stream(model, oracle_lib, w, g, 51, lattice_beam=lb, mdir=mdir)
 
 
 def test_pipelined_steps_give_the_oracle_transcripts(model_root, oracle_lib):
@@ -135,4 +141,12 @@ def test_pipelined_steps_give_the_oracle_transcripts(model_root, oracle_lib):
     for opts in ("num-channels=6,max-batch-size=4,max-seconds=10,pipeline-slots=3", "num-channels=16,max-batch-size=16,max-seconds=10,lattice=1"):
         got, stats = helpers.run_engine(mdir, waves, options=opts, capture=False, bytes_per_call=32000)
         for w, g in zip(waves, got):
-            assert g["text"] == oracle_lib.recognize(model, w, stages=True)["text"]
+            ref = oracle_lib.recognize(model, w, stages=True)
+            if "lattice=1" in opts:
+                # the engine's log-likelihoods differ from the oracle's by < 1e-3, which can move a lattice arc across the
+                # beam: words and times must agree, confidences closely
+                ldec = oracle_lib.decode(model, ref["loglikes"], lattice_beam=6.0)
+                want = helpers.lattice_text(mdir, ldec["lattice"], helpers.oracle_lattice_start(ldec), 6.0)
+                assert helpers.results_close(g["text"], want, conf_tol=5e-2), (g["text"], want)
+            else:
+                assert g["text"] == ref["text"]

@@ -1,0 +1,241 @@
+"""CPU tests of the host lattice chain (vb_lattice.cc: pruned word determinization, graph scale, word alignment, MBR),
+driven through the host-only hook vosk_b200_lattice_result on raw lattices produced by the oracle decoder.
+
+The checks are brute force (pure-Python path enumeration on small lattices), independent of the C++ under test:
+  * a linear lattice gives exactly the best-path result text of the oracle (conf 1, word spans of the alignment);
+  * the determinized lattice holds every word sequence of the raw lattice within the beam exactly once, at the cost of
+    its best raw path, with a transition-id string of the right length;
+  * word alignment keeps the weighted language and cuts it at word boundaries;
+  * the MBR one-best has an expected edit distance no worse than the best path, confidences are posteriors.
+"""
+import ctypes
+import json
+import os
+from collections import defaultdict
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "vosk-api_b200", "lib", "libvosk.so")
+
+
+@pytest.fixture(scope="module")
+def hook():
+    lib = ctypes.CDLL(LIB)
+    f = lib.vosk_b200_lattice_result
+    f.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                  ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    f.restype = ctypes.c_int
+
+    def call(mdir, lat, beam, stage):
+        src = np.ascontiguousarray(lat["src"], dtype=np.int32)
+        dst = np.ascontiguousarray(lat["dst"], dtype=np.int32)
+        arc = np.ascontiguousarray(lat["arc"], dtype=np.int32)
+        ac = np.ascontiguousarray(lat["ac"], dtype=np.float32)
+        fs = np.ascontiguousarray(lat["final_state"], dtype=np.int32)
+        fc = np.ascontiguousarray(lat["final_cost"], dtype=np.float32)
+        cap = 1 << 24
+        buf = ctypes.create_string_buffer(cap)
+        n = f(mdir.encode(), int(lat["n_states"]), int(lat["start"]), len(src), src.ctypes.data, dst.ctypes.data, arc.ctypes.data,
+              ac.ctypes.data, len(fs), fs.ctypes.data, fc.ctypes.data, beam, stage, buf, cap)
+        assert n >= 0, buf.value
+        assert n < cap
+        return buf.value.decode()
+
+    return call
+
+
+def _oracle_lattice(oracle_lib, model, seconds, seed, lattice_beam, **over):
+    import vbmodel
+    r = oracle_lib.recognize(model, vbmodel.synth_audio(seconds, seed), stages=True)
+    d = oracle_lib.decode(model, r["loglikes"], lattice_beam=lattice_beam, **over)
+    lat = dict(d["lattice"])
+    lat["n_states"] = len(lat["tok_index"])
+    start = np.flatnonzero((lat["frame"] == 0) & (d["arc"][lat["tok_index"]] < 0))
+    lat["start"] = int(start[0])
+    return d, lat
+
+
+def _parse(text):
+    arcs = defaultdict(list)
+    finals = {}
+    start = -1
+    for line in text.splitlines():
+        p = line.split()
+        if p[0] == "S":
+            start = int(p[1])
+        elif p[0] == "A":
+            tids = [] if p[6] == "-" else [int(x) for x in p[6].split(",")]
+            arcs[int(p[1])].append((int(p[2]), int(p[3]), float(p[4]), float(p[5]), tids))
+        elif p[0] == "F":
+            tids = [] if p[4] == "-" else [int(x) for x in p[4].split(",")]
+            finals[int(p[1])] = (float(p[2]), float(p[3]), tids)
+    return start, arcs, finals
+
+
+def _paths(start, arcs, finals, limit=300000):
+    """All complete paths as (words tuple, graph, acoustic, tids list, [(word, n_tids)...])."""
+    out = []
+    stack = [(start, (), 0.0, 0.0, [], [])]
+    while stack:
+        s, words, g, a, tids, segs = stack.pop()
+        if s in finals:
+            fg, fa, ft = finals[s]
+            out.append((words, g + fg, a + fa, tids + ft, segs))
+            assert len(out) < limit
+        for d, w, ag, aa, t in arcs.get(s, ()):
+            stack.append((d, words + ((w,) if w else ()), g + ag, a + aa, tids + t, segs + [(w, len(t))]))
+    return out
+
+
+def _raw_paths(model, lat, graph_scale=1.0):
+    g = model["graph"]
+    arcs = defaultdict(list)
+    for s, d, a, ac in zip(lat["src"], lat["dst"], lat["arc"], lat["ac"]):
+        tid = int(g["arc_ilabel"][a])
+        arcs[int(s)].append((int(d), int(g["arc_olabel"][a]), float(g["arc_w"][a]) * graph_scale, float(ac), [tid] if tid else []))
+    finals = {int(s): (float(c) * graph_scale, 0.0, []) for s, c in zip(lat["final_state"], lat["final_cost"])}
+    return _paths(lat["start"], arcs, finals)
+
+
+def _edit(a, b):
+    d = list(range(len(b) + 1))
+    for i, x in enumerate(a, 1):
+        prev, d[0] = d[0], i
+        for j, y in enumerate(b, 1):
+            prev, d[j] = d[j], min(d[j] + 1, d[j - 1] + 1, prev + (x != y))
+    return d[-1]
+
+
+def test_linear_lattice_gives_the_best_path_result(model_root, oracle_lib, hook):
+    import vbmodel
+    mdir = model_root("tiny")
+    model = vbmodel.load_model_dir(mdir)
+    for seed, secs in ((31, 1.9), (32, 0.7), (33, 3.1)):
+        r = oracle_lib.recognize(model, vbmodel.synth_audio(secs, seed), stages=True)
+        arcs = r["decode"]["best_arcs"]
+        n = len(arcs)
+        final_cost = float(model["graph"]["final"][model["graph"]["arc_next"][arcs[-1]]])
+        lat = dict(n_states=n + 1, start=0, src=np.arange(n), dst=np.arange(1, n + 1), arc=arcs, ac=np.linspace(0.5, 1.5, n, dtype=np.float32),
+                   final_state=[n], final_cost=[final_cost if np.isfinite(final_cost) else 0.0])
+        assert hook(mdir, lat, 6.0, 0) == r["text"]
+
+
+@pytest.mark.parametrize("seed,secs,beam", [(41, 1.2, 2.0), (42, 0.8, 3.0), (43, 1.6, 1.5)])
+def test_determinize_align_mbr_against_path_enumeration(model_root, oracle_lib, hook, seed, secs, beam):
+    import vbmodel
+    mdir = model_root("tiny")
+    model = vbmodel.load_model_dir(mdir)
+    d, lat = _oracle_lattice(oracle_lib, model, secs, seed, beam)
+    frames = d["frames"]
+    raw = _raw_paths(model, lat)
+    assert len(raw) >= 2
+    best_by_words = {}
+    for words, g, a, tids, _ in raw:
+        assert len(tids) == frames
+        if words not in best_by_words or g + a < best_by_words[words][0] + best_by_words[words][1]:
+            best_by_words[words] = (g, a)
+    best_total = min(g + a for g, a in best_by_words.values())
+
+    # ---- determinized lattice (graph costs already scaled by 0.9) ----
+    start, arcs, finals = _parse(hook(mdir, lat, beam, 1))
+    det = _paths(start, arcs, finals)
+    det_words = [p[0] for p in det]
+    assert len(set(det_words)) == len(det_words), "word sequences must be unique in a deterministic lattice"
+    for s in arcs:  # deterministic: at most one arc per word label out of a state
+        labels = [w for _, w, _, _, _ in arcs[s] if w]
+        assert len(labels) == len(set(labels))
+    within = {w for w, (g, a) in best_by_words.items() if g + a <= best_total + beam - 1e-3}
+    assert within <= set(det_words) <= set(best_by_words)
+    for words, g, a, tids, _ in det:
+        rg, ra = best_by_words[words]
+        assert abs(g - 0.9 * rg) < 2e-3 and abs(a - ra) < 2e-3, (words, g, a, rg, ra)
+        assert len(tids) == frames
+
+    # ---- word-aligned lattice: same weighted language, arcs cut at word boundaries ----
+    astart, aarcs, afinals = _parse(hook(mdir, lat, beam, 2))
+    ali = _paths(astart, aarcs, afinals)
+    cost_det = {p[0]: p[1] + p[2] for p in det}
+    cost_ali = defaultdict(lambda: np.inf)
+    for words, g, a, tids, segs in ali:
+        cost_ali[words] = min(cost_ali[words], g + a)
+        assert len(tids) == frames
+        assert all(nt > 0 for w, nt in segs if w), "a word arc carries the transition ids of its phones"
+    assert set(cost_ali) == set(cost_det)
+    for w in cost_det:
+        assert abs(cost_det[w] - cost_ali[w]) < 2e-3
+    tid2phone, kind = model["nnet"]["tid2phone"], model["word_boundary"]
+    for s in aarcs:
+        for _, w, _, _, tids in aarcs[s]:
+            if w and tids:
+                assert kind[int(tid2phone[tids[0]])] in ("begin", "singleton"), "a word arc starts with a word-begin (or singleton) phone"
+                assert kind[int(tid2phone[tids[-1]])] in ("end", "singleton"), "... and ends with a word-end phone"
+            elif tids:
+                assert all(kind[int(tid2phone[t])] == "nonword" for t in tids), "label-0 arcs with transition ids are silence"
+
+    # ---- MBR ----
+    res = json.loads(hook(mdir, lat, beam, 0))
+    word_id = {w: i for i, w in model["words"].items()}
+    hyp = tuple(word_id[w] for w in res["text"].split())
+    post = np.array([np.exp(-(cost_det[w] - min(cost_det.values()))) for w in det_words])
+    post /= post.sum()
+    risk = lambda h: float(sum(p * _edit(h, w) for p, w in zip(post, det_words)))
+    best_path_words = min(cost_det, key=cost_det.get)
+    assert risk(hyp) <= risk(best_path_words) + 1e-6
+    if res.get("result"):
+        confs = [x["conf"] for x in res["result"]]
+        assert all(0.0 < c <= 1.0 + 1e-5 for c in confs)
+        # a word present in every hypothesis at that position has posterior 1
+        if len(det_words) == 1:
+            assert all(abs(c - 1.0) < 1e-5 for c in confs)
+        ends = [x["end"] for x in res["result"]]
+        starts = [x["start"] for x in res["result"]]
+        assert all(s <= e for s, e in zip(starts, ends)) and all(e <= s2 + 1e-9 for e, s2 in zip(ends, starts[1:]))
+        assert ends[-1] <= frames * 0.03 + 1e-6
+
+
+def test_two_way_ambiguity_confidence_is_the_path_posterior(model_root, hook):
+    """Hand-made lattice: two parallel single-word hypotheses of known cost; conf = posterior of the winner."""
+    import vbmodel
+    mdir = model_root("tiny")
+    model = vbmodel.load_model_dir(mdir)
+    g = model["graph"]
+    # find two different complete one-word paths start -> ... -> final through brute force over the oracle's best paths
+    import oracle
+    paths = []
+    for seed in range(60, 90):
+        r = oracle.recognize(model, vbmodel.synth_audio(0.5, seed), stages=True)
+        words = [w for w in json.loads(r["text"])["text"].split()]
+        arcs = list(r["decode"]["best_arcs"])
+        if len(words) == 1 and r["decode"]["reached_final"]:
+            key = (words[0], len([a for a in arcs if g["arc_pdf"][a] >= 0]))
+            if all(k[0] != key[0] for k, _ in paths) and (not paths or paths[0][0][1] == key[1]):
+                paths.append((key, arcs))
+        if len(paths) == 2:
+            break
+    if len(paths) < 2:
+        pytest.skip("no two single-word utterances of equal length among the probe seeds")
+    src, dst, arc, ac, fin_s, fin_c = [], [], [], [], [], []
+    n = 1
+    delta = 0.7  # the second path is worse by 0.7 (acoustic)
+    for k, (_, arcs) in enumerate(paths):
+        prev = 0
+        for j, a in enumerate(arcs):
+            src.append(prev)
+            dst.append(n)
+            arc.append(a)
+            ac.append((delta if k == 1 and j == 0 else 0.0) - 0.9 * 0 - float(g["arc_w"][a]) * 0.0)
+            prev = n
+            n += 1
+        fin_s.append(prev)
+        fin_c.append(0.0)
+    lat = dict(n_states=n, start=0, src=src, dst=dst, arc=arc, ac=ac, final_state=fin_s, final_cost=fin_c)
+    gcost = [0.9 * sum(float(g["arc_w"][a]) for a in arcs) for _, arcs in paths]
+    c = np.array([gcost[0], gcost[1] + delta])
+    post = np.exp(-(c - c.min()))
+    post /= post.sum()
+    res = json.loads(hook(mdir, lat, 50.0, 0))
+    win = int(np.argmax(post))
+    assert res["text"] == paths[win][0][0]
+    assert abs(res["result"][0]["conf"] - post[win]) < 1e-4

@@ -1,6 +1,8 @@
 // batch_recognizer.cc — see batch_recognizer.h.  Replaces [REF src/batch_recognizer.cc].
 #include "batch_recognizer.h"
 
+#include "vb_lattice.h"
+
 #include <algorithm>
 #include <cmath>
 
@@ -14,8 +16,17 @@ BatchRecognizer::BatchRecognizer(BatchModel *model, float sample_frequency)
     stream_ = model->engine_for(id_).open_stream();
     std::shared_ptr<Sink> sink = sink_;
     const Model *m = &model->model();
-    stream_->on_result = [sink, m](const BestPath &bp) {
-        std::vector<WordSpan> words = align_words(*m, bp.arcs);
+    const float lattice_beam = model->engine_for(id_).config().lattice_beam;
+    stream_->on_result = [sink, m, lattice_beam](const BestPath &bp) {
+        // lattice=1: PushLattice's chain on the pruned raw lattice [REF src/batch_recognizer.cc:43-56]; otherwise (and if the
+        // lattice came back empty or over capacity) the best path, which is the MBR result of a linear lattice
+        std::vector<WordSpan> words;
+        bool done = false;
+        if (bp.lattice && bp.lattice->error == 0 && bp.lattice->n_states > 0) {
+            words = lattice_to_words(*bp.lattice, *m, lattice_beam);
+            done = !words.empty() || bp.arcs.empty();
+        }
+        if (!done) words = align_words(*m, bp.arcs);
         std::lock_guard<std::mutex> lk(sink->mu);
         sink->results.push(sink->nlsml ? result_nlsml(*m, words) : result_json(*m, words, 0.0f));
     };

@@ -681,6 +681,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             // first use; arcs below the running cutoff are parked as candidate records {arc, cost, next state, src} ----
             cnt_arc_e += tid == 0 ? (unsigned)n_arcs : 0u;
             const float cost_offset = -best;
+            if (links && tid == 0 && frame <= a.max_frames) a.frame_offset[(size_t)ch * (a.max_frames + 2) + frame] = cost_offset;
             {
                 constexpr int NW = NT / 32;
                 const int nwin = (n_arcs + 31) >> 5;
@@ -966,15 +967,21 @@ __global__ void __launch_bounds__(kPruneThreads) lattice_prune_kernel(DecArgs a)
         }
         __syncthreads();
     }
-    // surviving links -> output (old token indices for now)
-    const int n_links_all = min(cs.link_count, a.link_cap);
-    for (int k = tid; k < n_links_all; k += NT) {
-        const int4 lk = links[k];
-        if (lk.y < 0) continue;
-        const float le = link_extra(a, lk, cost, extra);
-        if (le <= lb) {
-            const int o = agg_inc(&s_nlinks);
-            if (o < a.lat_link_cap) out_links[o] = make_int4(lk.x, lk.y & ~kEpsLinkFlag, lk.z, lk.w);
+    // surviving links -> output (old token indices for now).  GetRawLattice takes the frame's cost offset back out of
+    // the acoustic cost of an emitting arc (segment f holds the arcs from frame f-1 into frame f).
+    const float *frame_offset = a.frame_offset + (size_t)ch * (a.max_frames + 2);
+    for (int f = 0; f <= F; f++) {
+        const int k1 = min(link_off[f + 1], a.link_cap);
+        const float off = f > 0 ? frame_offset[f - 1] : 0.f;
+        for (int k = link_off[f] + tid; k < k1; k += NT) {
+            const int4 lk = links[k];
+            if (lk.y < 0) continue;
+            const float le = link_extra(a, lk, cost, extra);
+            if (le <= lb) {
+                const int o = agg_inc(&s_nlinks);
+                const float ac = (lk.y & kEpsLinkFlag) ? 0.f : __int_as_float(lk.w) - off;
+                if (o < a.lat_link_cap) out_links[o] = make_int4(lk.x, lk.y & ~kEpsLinkFlag, lk.z, __float_as_int(ac));
+            }
         }
     }
     __syncthreads();

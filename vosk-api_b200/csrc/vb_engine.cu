@@ -57,6 +57,33 @@ Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg)
     upload_model();
     alloc_state();
     thread_ = std::thread([this] { worker(); });
+    if (cfg_.lattice) {
+        int n = cfg_.post_threads > 0 ? cfg_.post_threads : std::max(1, std::min(32, (int)std::thread::hardware_concurrency() / 2));
+        for (int i = 0; i < n; i++) post_threads_.emplace_back([this] { post_worker(); });
+    }
+}
+
+void Engine::post_worker() {
+    for (;;) {
+        std::function<void()> job;
+        {
+            std::unique_lock<std::mutex> lk(post_mu_);
+            post_cv_.wait(lk, [&] { return post_stop_ || !post_queue_.empty(); });
+            if (post_queue_.empty()) return;
+            job = std::move(post_queue_.front());
+            post_queue_.pop_front();
+        }
+        try {
+            job();
+        } catch (const std::exception &ex) {
+            log_msg(-1, "lattice post-processing failed: %s", ex.what());
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            post_outstanding_--;
+        }
+        cv_done_.notify_all();
+    }
 }
 
 Engine::~Engine() {
@@ -66,6 +93,12 @@ Engine::~Engine() {
     }
     cv_work_.notify_all();
     if (thread_.joinable()) thread_.join();
+    {
+        std::lock_guard<std::mutex> lk(post_mu_);
+        post_stop_ = true;
+    }
+    post_cv_.notify_all();
+    for (auto &t : post_threads_) t.join();
     cudaSetDevice(cfg_.device);
     cudaStreamSynchronize(stream_);
     for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_})
@@ -315,6 +348,7 @@ void Engine::alloc_state() {
         d.link_cap = link_cap_;
         d.links = dev_alloc<int4>(allocs_, (size_t)C * link_cap_);
         d.link_off = dev_alloc<int>(allocs_, (size_t)C * (max_frames_ + 3), 0);
+        d.frame_offset = dev_alloc<float>(allocs_, (size_t)C * (max_frames_ + 2), 0);
         d.lat_extra = cfg_.debug_capture ? dev_alloc<unsigned>(allocs_, (size_t)C * log_cap_) : nullptr;
         d.lat_link_cap = cfg_.lat_link_cap;
         d.lat_tok_cap = cfg_.lat_tok_cap;
@@ -420,7 +454,7 @@ void Engine::push(const std::shared_ptr<Stream> &s, const int16_t *samples, int 
 
 void Engine::wait() {
     std::unique_lock<std::mutex> lk(mu_);
-    cv_done_.wait(lk, [this] { return outstanding_ == 0; });
+    cv_done_.wait(lk, [this] { return outstanding_ == 0 && post_outstanding_ == 0; });
 }
 
 StepStats Engine::stats() {
@@ -827,7 +861,20 @@ void Engine::finish_lane(Slot &sl, Lane &ln, int k, int lane_pos) {
     const int *p = sl.h_path + (size_t)k * path_cap_;
     for (int i = 0; i < n; i++) bp.arcs[i] = p[n - 1 - i];
     if (cs.error) log_msg(-1, "stream %llu: decoder capacity error %d (result may be truncated)", (unsigned long long)ln.s->id, cs.error);
-    if (ln.s->on_result) ln.s->on_result(bp);
+    if (!ln.s->on_result) return;
+    if (post_threads_.empty()) {
+        ln.s->on_result(bp);
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        post_outstanding_++;
+    }
+    {
+        std::lock_guard<std::mutex> lk(post_mu_);
+        post_queue_.emplace_back([cb = ln.s->on_result, bp = std::move(bp)] { cb(bp); });
+    }
+    post_cv_.notify_one();
 }
 
 double Engine::run_resident(const int16_t *d_audio, int num_streams, int stride, const int *lengths, std::vector<BestPath> *out) {
@@ -845,7 +892,10 @@ double Engine::run_resident(const int16_t *d_audio, int num_streams, int stride,
         ss[i]->id = (uint64_t)i;
         ss[i]->resident = true;
         BestPath *slot = &res[i];
-        ss[i]->on_result = [slot](const BestPath &bp) { *slot = bp; };
+        ss[i]->on_result = [slot, i, this](const BestPath &bp) {
+            *slot = bp;
+            if (resident_hook) resident_hook(i, bp);
+        };
     }
     cudaEvent_t e0, e1;
     VB_CUDA_CHECK(cudaEventCreate(&e0));

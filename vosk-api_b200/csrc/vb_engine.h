@@ -105,6 +105,8 @@ class Engine {
     // Device-resident run for kernel-level benchmarking: `audio` holds num_streams x samples int16 already in
     // HBM; processes every stream chunk by chunk with no host<->device sample traffic.  Returns device ms.
     double run_resident(const int16_t *d_audio, int num_streams, int stride, const int *lengths, std::vector<BestPath> *out);
+    // called for every finished stream of a resident run, on the thread that delivers results (stream index, result)
+    std::function<void(int, const BestPath &)> resident_hook;
 
    private:
     struct Lane {
@@ -184,6 +186,15 @@ class Engine {
     long long outstanding_ = 0;  // chunks pushed and not yet completed
     bool stop_ = false;
     std::thread thread_;
+    // lattice post-processing pool (lattice=1): determinization / alignment / MBR of finished segments run here, off the
+    // batcher thread, as the reference pipeline does with its lattice thread pool
+    std::vector<std::thread> post_threads_;
+    std::deque<std::function<void()>> post_queue_;
+    std::mutex post_mu_;
+    std::condition_variable post_cv_;
+    long long post_outstanding_ = 0;  // guarded by mu_ (wait() watches it)
+    bool post_stop_ = false;
+    void post_worker();
     uint64_t next_id_ = 0;
     StepStats stats_;
     std::mutex stats_mu_;

@@ -152,6 +152,7 @@ struct DecArgs {
     int4 *links;             // [C][link_cap] {src log index, dst log index | kEpsLinkFlag (-1 = dropped), arc, acoustic cost bits}
     int *link_off;           // [C][max_frames+3] segment s = links whose destination token belongs to frame s
     int link_cap;
+    float *frame_offset;     // [C][max_frames+2] cost offset (-best token cost) of every frame: taken back out of the lattice arcs
     int *cand_next;          // [G][cand_cap] destination state of a candidate
     unsigned *lat_extra;     // [C][log_cap] extra-cost scratch of the lattice pruning, or null: the pruning then
                              // reuses log_prev (whose content is dead once the best path has been traced)

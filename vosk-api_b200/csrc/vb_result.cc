@@ -39,7 +39,7 @@ std::vector<WordSpan> align_words(const Model &m, const std::vector<int> &arcs) 
         const bool last = s + 1 == segs.size();
         if (!emit && last && wb >= 0 && li < labels.size()) emit = true;  // partial word forced out at the end
         if (emit) {
-            if (li < labels.size()) out.push_back({labels[li++], wb, segs[s].e, 1.0f});
+            if (li < labels.size()) out.push_back({labels[li++], (float)wb, (float)segs[s].e, 1.0f});
             wb = -1;
         }
     }
@@ -79,8 +79,8 @@ std::string result_json_words(const std::vector<std::string> &ws, const std::vec
         s += "  \"result\" : [";
         for (size_t i = 0; i < w.size(); i++) {
             // [REF src/batch_recognizer.cc:91-93]: round(frame) * 0.03 + offset, evaluated in double
-            const double st = (double)std::round((float)w[i].begin) * 0.03 + (double)offset;
-            const double en = (double)std::round((float)w[i].end) * 0.03 + (double)offset;
+            const double st = (double)std::round(w[i].begin) * 0.03 + (double)offset;
+            const double en = (double)std::round(w[i].end) * 0.03 + (double)offset;
             if (i) s += ", ";
             s += "{\n      \"conf\" : " + std::to_string((double)w[i].conf);
             s += ",\n      \"end\" : " + std::to_string(en);

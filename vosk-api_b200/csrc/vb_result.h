@@ -12,7 +12,7 @@ namespace vb {
 
 struct WordSpan {
     int word;
-    int begin, end;  // decoder frames (30 ms each)
+    float begin, end;  // decoder frames (30 ms each); fractional for MBR time averages
     float conf;
 };
 

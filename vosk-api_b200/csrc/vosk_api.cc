@@ -11,6 +11,7 @@
 #include "../../include/vosk_b200.h"
 #include "batch_model.h"
 #include "batch_recognizer.h"
+#include "vb_lattice.h"
 
 namespace vb {
 int g_log_level = 0;
@@ -186,10 +187,24 @@ double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio
         if (cudaMalloc((void **)&d_audio, bytes) != cudaSuccess) throw std::runtime_error("cudaMalloc(audio) failed");
         if (cudaMemcpy(d_audio, audio, bytes, cudaMemcpyHostToDevice) != cudaSuccess) throw std::runtime_error("audio upload failed");
         std::vector<vb::BestPath> res;
+        bm->resident_results.assign(num_streams, std::string());
+        const vb::Model *m = &bm->model();
+        const float lattice_beam = eng.config().lattice_beam;
+        std::vector<std::string> *texts = &bm->resident_results;
+        // result text is produced where the engine delivers results (the lattice pool when lattice=1), inside the timed region
+        eng.resident_hook = [m, lattice_beam, texts](int i, const vb::BestPath &bp) {
+            std::vector<vb::WordSpan> words;
+            bool done = false;
+            if (bp.lattice && bp.lattice->error == 0 && bp.lattice->n_states > 0) {
+                words = vb::lattice_to_words(*bp.lattice, *m, lattice_beam);
+                done = !words.empty() || bp.arcs.empty();
+            }
+            if (!done) words = vb::align_words(*m, bp.arcs);
+            (*texts)[i] = vb::result_json(*m, words, 0.0f);
+        };
         double ms = eng.run_resident(d_audio, num_streams, samples_per_stream, lengths, &res);
+        eng.resident_hook = nullptr;
         cudaFree(d_audio);
-        bm->resident_results.clear();
-        for (auto &bp : res) bm->resident_results.push_back(vb::result_json(bm->model(), vb::align_words(bm->model(), bp.arcs), 0.0f));
         return ms;
     } catch (const std::exception &e) {
         if (d_audio) cudaFree(d_audio);
@@ -262,7 +277,7 @@ int vosk_b200_format_result(const char *const *words, const int *begin, const in
     std::vector<vb::WordSpan> sp;
     for (int i = 0; i < n; i++) {
         ws.push_back(words[i]);
-        sp.push_back(vb::WordSpan{i, begin[i], end[i], conf[i]});
+        sp.push_back(vb::WordSpan{i, (float)begin[i], (float)end[i], conf[i]});
     }
     std::string s = vb::result_json_words(ws, sp, offset);
     if (out && cap > 0) {
@@ -297,6 +312,75 @@ int vosk_b200_model_check(const char *model_dir, char *out, int cap) {
         return 0;
     } catch (const std::exception &e) {
         snprintf(out, cap, "error: %s", e.what());
+        return -1;
+    }
+}
+
+// Host-only: the lattice chain of PushLattice on an explicit raw lattice.  stage 0: result text (JSON); 1: determinized
+// lattice; 2: word-aligned lattice, as text lines "A src dst word graph acoustic tid,tid,..", "F state graph acoustic tids",
+// "S start".
+int vosk_b200_lattice_result(const char *model_dir, int n_states, int start, int n_links, const int *src, const int *dst, const int *arc,
+                             const float *acoustic, int n_final, const int *final_state, const float *final_cost, float lattice_beam,
+                             int stage, char *out, int cap) {
+    try {
+        static std::string cached_dir;
+        static std::unique_ptr<vb::Model> cached;
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        const std::string dir = model_dir ? model_dir : "model";
+        if (!cached || cached_dir != dir) {
+            cached.reset(new vb::Model);
+            cached->load(dir);
+            cached_dir = dir;
+        }
+        const vb::Model &m = *cached;
+        vb::RawLattice raw;
+        raw.n_states = n_states;
+        raw.start = start;
+        raw.src.assign(src, src + n_links);
+        raw.dst.assign(dst, dst + n_links);
+        raw.arc.assign(arc, arc + n_links);
+        raw.acoustic.assign(acoustic, acoustic + n_links);
+        raw.final_state.assign(final_state, final_state + n_final);
+        raw.final_cost.assign(final_cost, final_cost + n_final);
+        std::string text;
+        if (stage == 0) {
+            text = vb::result_json(m, vb::lattice_to_words(raw, m, lattice_beam), 0.0f);
+        } else {
+            vb::LatticeCtx ctx{&m.graph, &m.tid2phone, &m.phone_type};
+            vb::CLat det, ali;
+            if (vb::determinize_lattice(raw, ctx, lattice_beam, &det)) {
+                vb::scale_graph_costs(&det, 0.9f);
+                if (stage == 2) vb::word_align_lattice(det, ctx, &ali);
+            }
+            const vb::CLat &L = stage == 2 ? ali : det;
+            char b[128];
+            snprintf(b, sizeof b, "S %d\n", L.start);
+            text += b;
+            auto tids = [&](const std::vector<int> &t) {
+                std::string s2;
+                for (size_t i = 0; i < t.size(); i++) s2 += (i ? "," : "") + std::to_string(t[i]);
+                return s2.empty() ? std::string("-") : s2;
+            };
+            for (size_t s2 = 0; s2 < L.num_states(); s2++) {
+                for (const vb::CLatArc &a : L.arcs[s2]) {
+                    snprintf(b, sizeof b, "A %zu %d %d %.9g %.9g ", s2, a.dst, a.word, a.w.g, a.w.a);
+                    text += b + tids(a.tids) + "\n";
+                }
+                if (L.is_final[s2]) {
+                    snprintf(b, sizeof b, "F %zu %.9g %.9g ", s2, L.final_w[s2].g, L.final_w[s2].a);
+                    text += b + tids(L.final_tids[s2]) + "\n";
+                }
+            }
+        }
+        if (out && cap > 0) {
+            size_t k = text.size() < (size_t)cap - 1 ? text.size() : (size_t)cap - 1;
+            memcpy(out, text.data(), k);
+            out[k] = 0;
+        }
+        return (int)text.size();
+    } catch (const std::exception &e) {
+        if (out && cap > 0) snprintf(out, cap, "error: %s", e.what());
         return -1;
     }
 }
