@@ -18,7 +18,7 @@ extern "C" {
 /* Like vosk_batch_model_new but with an explicit model directory and "key=value,key=value"
  * options: frames-per-chunk, max-batch-size, num-channels, beam, lattice-beam, max-active,
  * min-active, tok-cap, cand-cap, hash-size, max-seconds, log-tokens-per-frame, tensor-cores, lattice,
- * log-links-per-frame, lat-tok-cap, lat-link-cap, pipeline-slots, heavy-tokens,
+ * log-links-per-frame, lat-tok-cap, lat-link-cap, post-threads, partials, pipeline-slots, heavy-tokens,
  * debug-capture, devices (GPU indices separated by ':' or "all").
  * Env VOSK_BATCH_OPTIONS / VOSK_BATCH_DEVICES are applied first.  NULL on failure. */
 VoskBatchModel *vosk_batch_model_new_ex(const char *model_dir, const char *options);
@@ -53,6 +53,16 @@ void vosk_batch_model_set_slots(VoskBatchModel *model, int n);
 double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream,
                                      const int *lengths);
 const char *vosk_batch_model_resident_result(VoskBatchModel *model, int stream);
+
+/* Partial result (model option partials=1): the best path so far, without final costs, in the CPU API's text layout
+ * {"partial" : "..."} [REF src/recognizer.cc:795-802]; the reference's batch path only has a disabled best-path callback
+ * [REF src/batch_recognizer.cc:120-137].  The string is owned by the recognizer and valid until the next call.
+ * partial_frames: decoder frames (30 ms) the latest partial covers. */
+const char *vosk_batch_recognizer_partial_result(VoskBatchRecognizer *recognizer);
+int vosk_batch_recognizer_partial_frames(VoskBatchRecognizer *recognizer);
+/* Latency from the acceptance of a chunk's last sample to the moment its step's partial / final result became
+ * retrievable, over the chunks completed since the last reset: out5 = {p50, p90, p99, mean (ms), count}. */
+int vosk_batch_model_latency(VoskBatchModel *model, double *out5, int reset);
 
 /* Test taps.  Enable before the first accept_waveform on a model created with debug-capture=1;
  * after finish_stream + wait, fetch "mfcc" [T][40], "ivectors" [chunks][D], "loglikes" [N][pdfs] (f32),

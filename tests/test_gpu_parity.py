@@ -150,3 +150,49 @@ def test_pipelined_steps_give_the_oracle_transcripts(model_root, oracle_lib):
                 assert helpers.results_close(g["text"], want, conf_tol=5e-2), (g["text"], want)
             else:
                 assert g["text"] == ref["text"]
+
+
+def test_partial_results_follow_the_best_path(model_root, oracle_lib):
+    """partials=1: after every chunk the partial text is the word sequence of the cheapest token's path (no final costs,
+    as GetBestPath(use_final_probs=false)); checked against the oracle decoder run on the engine's log-likelihoods so far."""
+    import json
+    import vbmodel
+    import vosk
+    mdir = model_root("small")
+    model = vbmodel.load_model_dir(mdir)
+    g = model["graph"]
+    P = int(model["cfg"]["num-pdfs"])
+    wave = vbmodel.synth_audio(4.3, 1300)
+    for fpc in (51, 10):
+        m = vosk.BatchModel(mdir, options=f"partials=1,debug-capture=1,frames-per-chunk={fpc},num-channels=2,max-batch-size=2,max-seconds=8")
+        r = vosk.BatchRecognizer(m, 16000.0)
+        r.DebugCapture()
+        step = fpc * 160
+        seen = 0
+        for i in range(0, len(wave), step):
+            r.AcceptWaveform(wave[i:i + step].tobytes())
+            m.Wait()
+            nf = r.PartialFrames()
+            if nf == 0:
+                continue
+            ll = r.DebugGet("loglikes", np.float32).reshape(-1, P)[:nf]
+            assert len(ll) == nf
+            d = oracle_lib.decode(model, ll)
+            lo, hi = int(d["offsets"][-2]), int(d["offsets"][-1])
+            i_best = lo + int(np.argmin(d["cost"][lo:hi]))
+            words = []
+            while i_best >= 0 and d["arc"][i_best] >= 0:
+                ol = int(g["arc_olabel"][d["arc"][i_best]])
+                if ol:
+                    words.append(model["words"][ol])
+                i_best = int(d["prev"][i_best])
+            want = " ".join(reversed(words))
+            assert json.loads(r.PartialResult())["partial"] == want
+            seen += 1
+        r.FinishStream()
+        m.Wait()
+        assert seen >= 3
+        assert r.Result() == oracle_lib.recognize(model, wave, frames_per_chunk=fpc, stages=True)["text"]
+        lat = m.Latency()
+        assert lat["count"] >= seen and lat["p50"] > 0
+        del r, m

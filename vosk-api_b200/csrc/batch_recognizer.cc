@@ -83,4 +83,19 @@ void BatchRecognizer::Pop() {
     if (!sink_->results.empty()) sink_->results.pop();
 }
 
+const char *BatchRecognizer::PartialResult() {
+    std::vector<WordSpan> words;
+    {
+        std::lock_guard<std::mutex> lk(stream_->partial_mu);
+        for (int w : stream_->partial_words) words.push_back(WordSpan{w, 0.f, 0.f, 1.f});
+    }
+    partial_ = partial_json(model_->model(), words);
+    return partial_.c_str();
+}
+
+int BatchRecognizer::PartialFrames() {
+    std::lock_guard<std::mutex> lk(stream_->partial_mu);
+    return stream_->partial_frames;
+}
+
 int BatchRecognizer::GetNumPendingChunks() { return stream_->pending_chunks.load(); }

@@ -22,6 +22,8 @@ class BatchRecognizer {
     void FinishStream();                             // [REF :37-41]
     void SetNLSML(bool nlsml);                       // [REF :109-112]
 
+    const char *PartialResult();                     // additive: best path so far as {"partial" : "..."} [REF src/recognizer.cc:795-802]
+    int PartialFrames();                             // additive: decoder frames (30 ms) the partial covers
     void EnableCapture();                            // additive: test taps (include/vosk_b200.h)
     vb::Capture *capture() { return stream_->capture.get(); }
 
@@ -42,5 +44,6 @@ class BatchRecognizer {
     vb::LinearResampler resampler_;
     std::vector<int16_t> buffer_;
     std::string front_;  // keeps the string returned by FrontResult alive until Pop
+    std::string partial_;
     bool finished_ = false;
 };

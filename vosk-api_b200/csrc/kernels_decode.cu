@@ -1051,6 +1051,65 @@ extern "C" cudaError_t vbk_lattice_prune(const DecArgs *a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Partial result: argmin over the current tokens (no final costs, as the reference's partial results do
+// [REF src/recognizer.cc:790-793]), then a walk over the back pointers collecting the output labels.  One warp per lane:
+// the walk is a dependent chain, so it runs off the search kernel's critical path in its own small launch.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) partial_kernel(DecArgs a) {
+    const int l = blockIdx.x, lane = threadIdx.x;
+    const LaneDesc ln = a.lanes[l];
+    if (ln.last) return;
+    const int ch = ln.channel;
+    const DecChannelState cs = a.cs[ch];
+    int *out = a.partial_words + (size_t)l * kPartialCap;
+    const size_t tbase = (size_t)ch * 2 * a.tok_cap + (size_t)cs.parity * a.tok_cap;
+    const float *t_cost = a.tok_cost + tbase;
+    const int *t_arc = a.tok_arc + tbase, *t_prev = a.tok_prev + tbase;
+    unsigned long long m = kValMax;
+    for (int i = lane; i < cs.n_cur; i += 32) m = min(m, ((unsigned long long)ford(t_cost[i]) << 32) | (unsigned)i);
+    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane != 0) return;
+    int n = 0;
+    if (m != kValMax) {
+        const int *log_prev = a.log_prev + (size_t)ch * a.log_cap, *log_arc = a.log_arc + (size_t)ch * a.log_cap;
+        int i = (int)(unsigned)m, li = -1;
+        for (int guard = 0; guard < a.tok_cap; guard++) {  // epsilon predecessors live in the same token list
+            const int arc = t_arc[i];
+            if (arc < 0) break;
+            const int ol = __ldg(a.g.arcs + arc).w;
+            if (ol != 0) {
+                if (n < kPartialCap) out[n] = ol;
+                n++;
+            }
+            const int pv = t_prev[i];
+            if (pv <= -2) {
+                i = -2 - pv;
+            } else {
+                li = pv;
+                break;
+            }
+        }
+        while (li >= 0) {
+            const int arc = log_arc[li];
+            if (arc < 0) break;
+            const int ol = __ldg(a.g.arcs + arc).w;
+            if (ol != 0) {
+                if (n < kPartialCap) out[n] = ol;
+                n++;
+            }
+            li = log_prev[li];
+        }
+    }
+    a.partial_count[l] = n;
+}
+
+extern "C" cudaError_t vbk_partial(const DecArgs *a, cudaStream_t s) {
+    if (!a->partial_words || a->num_lanes <= 0) return cudaSuccess;
+    partial_kernel<<<a->num_lanes, 32, 0, s>>>(*a);
+    return cudaGetLastError();
+}
+
 extern "C" int vbk_decode_max_grid(int device) {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

@@ -63,6 +63,7 @@ struct Config {
     int debug_capture = 0;      // allow per-stream capture of intermediates (tests)
     int lattice = 0;            // lattice generation: link log + lattice_beam pruning on the device, raw lattice to the host
     int log_links_per_frame = 6144;   // average links per frame the link log is sized for
+    int partials = 0;           // partial results: best path so far after every chunk (vosk_batch_recognizer_partial_result)
     int post_threads = 0;       // host threads turning lattices into results (0 = hardware threads / 2, at most 32)
     int lat_tok_cap = 131072, lat_link_cap = 262144;  // pruned raw lattice of one stream (states / arcs)
 };

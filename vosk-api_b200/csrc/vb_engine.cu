@@ -111,6 +111,7 @@ Engine::~Engine() {
         if (sl.h_cs) cudaFreeHost(sl.h_cs);
         if (sl.h_path) cudaFreeHost(sl.h_path);
         if (sl.h_load) cudaFreeHost(sl.h_load);
+        if (sl.h_partial) cudaFreeHost(sl.h_partial);
         if (sl.h_lat_hdr) cudaFreeHost(sl.h_lat_hdr);
         if (sl.h_lat_links) cudaFreeHost(sl.h_lat_links);
         if (sl.h_lat_final) cudaFreeHost(sl.h_lat_final);
@@ -401,6 +402,11 @@ void Engine::alloc_state() {
         sd = dec_;
         sd.out_table = sl.d_table + (size_t)(nn - 1) * L;
         sd.lane_load = sl.d_load;
+        if (cfg_.partials) {
+            sd.partial_words = dev_alloc<int>(allocs_, (size_t)L * kPartialCap, 0);
+            sd.partial_count = dev_alloc<int>(allocs_, (size_t)L, 0);
+            VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_partial, (size_t)L * (kPartialCap + 1) * sizeof(int)));
+        }
         if (cfg_.lattice) {
             sd.lat_hdr = dev_alloc<LatHeader>(allocs_, (size_t)L, 0);
             sd.lat_links = dev_alloc<int4>(allocs_, (size_t)L * cfg_.lat_link_cap);
@@ -437,6 +443,7 @@ void Engine::push(const std::shared_ptr<Stream> &s, const int16_t *samples, int 
     Stream::Chunk ch;
     ch.samples.assign(samples, samples + n);
     ch.last = last;
+    ch.t_push = std::chrono::steady_clock::now();
     {
         std::lock_guard<std::mutex> lk(mu_);
         if (s->finished) return;  // chunks after the last one are ignored
@@ -477,6 +484,26 @@ StepStats Engine::stats() {
     for (int k = 0; k < 16; k++) s.phase[k] = c[16 + k];
     return s;
 }
+void Engine::latency(double *out, bool reset) {
+    std::vector<float> v;
+    {
+        std::lock_guard<std::mutex> lk(stats_mu_);
+        v = latencies_ms_;
+        if (reset) latencies_ms_.clear();
+    }
+    for (int k = 0; k < 5; k++) out[k] = 0;
+    if (v.empty()) return;
+    std::sort(v.begin(), v.end());
+    auto pct = [&](double p) { return (double)v[std::min(v.size() - 1, (size_t)(p * v.size()))]; };
+    double sum = 0;
+    for (float x : v) sum += x;
+    out[0] = pct(0.50);
+    out[1] = pct(0.90);
+    out[2] = pct(0.99);
+    out[3] = sum / v.size();
+    out[4] = (double)v.size();
+}
+
 void Engine::reset_stats() {
     cudaSetDevice(cfg_.device);
     cudaMemset(dec_.counters, 0, 32 * sizeof(unsigned long long));
@@ -710,6 +737,14 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     }
     int n_last = 0;
     for (int i = 0; i < L; i++) n_last += lanes[i].chunk.last ? 1 : 0;
+    if (cfg_.partials && n_last < L) {
+        sl.dec.lane_begin = 0;
+        sl.dec.lane_end = L;
+        VB_CUDA_CHECK(vbk_partial(&sl.dec, st));
+        sl.launches++;
+        VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_partial, sl.dec.partial_words, (size_t)L * kPartialCap * sizeof(int), cudaMemcpyDeviceToHost, st));
+        VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_partial + (size_t)L * kPartialCap, sl.dec.partial_count, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     if (cfg_.lattice && n_last > 0) {
         sl.dec.lane_begin = 0;
         sl.dec.lane_end = L;
@@ -742,6 +777,24 @@ void Engine::complete_step(Slot &sl) {
     cudaStream_t st = sl.stream;
     VB_CUDA_CHECK(cudaEventSynchronize(sl.done));
     for (int i = 0; i < L; i++) lanes[i].s->load = sl.h_load[i];
+    {
+        const auto now = std::chrono::steady_clock::now();
+        std::lock_guard<std::mutex> lk(stats_mu_);
+        for (int i = 0; i < L; i++) {
+            if (lanes[i].s->resident) continue;
+            if (latencies_ms_.size() < (1u << 22)) latencies_ms_.push_back(std::chrono::duration<float, std::milli>(now - lanes[i].chunk.t_push).count());
+        }
+    }
+    if (cfg_.partials)
+        for (int i = 0; i < L; i++) {
+            if (lanes[i].chunk.last) continue;
+            const int total = sl.h_partial[(size_t)L * kPartialCap + i], n = std::min(total, kPartialCap);
+            const int *w = sl.h_partial + (size_t)i * kPartialCap;
+            Stream &s = *lanes[i].s;
+            std::lock_guard<std::mutex> lk(s.partial_mu);
+            s.partial_words.assign(std::reverse_iterator<const int *>(w + n), std::reverse_iterator<const int *>(w));
+            s.partial_frames = lanes[i].dec_frames_after;
+        }
     // debug capture (tests): copy this step's new rows of the tapped stages
     for (int i = 0; i < L && cfg_.debug_capture; i++) {
         Stream &s = *lanes[i].s;

@@ -6,6 +6,7 @@
 // [REF src/batch_recognizer.cc:40,138-149,167,201], [REF src/batch_model.cc:118-121].
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -65,7 +66,12 @@ struct Stream {
         std::vector<int16_t> samples;
         int n_resident = 0;  // chunk length when the samples live in a device-resident matrix
         bool last;
+        std::chrono::steady_clock::time_point t_push;  // when the chunk's last sample was accepted
     };
+    // partial result (partials=1): output labels of the best path so far, oldest first
+    std::mutex partial_mu;
+    std::vector<int> partial_words;
+    int partial_frames = 0;  // decoder frames the partial covers
     std::deque<Chunk> pending;            // guarded by Engine::mu_
     std::atomic<int> pending_chunks{0};
     std::function<void(const BestPath &)> on_result;  // called on the engine worker thread
@@ -97,6 +103,8 @@ class Engine {
     void push(const std::shared_ptr<Stream> &s, const int16_t *samples, int n, bool last);
     void wait();  // until every chunk pushed so far is decoded and its result delivered
     StepStats stats();
+    // latency from a chunk's acceptance to its step's results (partial / final) being available: {p50, p90, p99, mean, count} in ms
+    void latency(double *out5, bool reset);
     void reset_stats();
     void set_timing(bool on) { timing_ = on; }
     // limits the number of pipeline slots in use (1 = fully serialized steps: per-kernel timings without overlap)
@@ -134,6 +142,7 @@ class Engine {
         DecChannelState *h_cs = nullptr;
         int *h_path = nullptr;
         int *d_load = nullptr, *h_load = nullptr;
+        int *h_partial = nullptr;  // [L][kPartialCap] words + [L] counts
         LatHeader *h_lat_hdr = nullptr;
         int4 *h_lat_links = nullptr;  // pinned bounce buffers for one finished lane's lattice
         int2 *h_lat_final = nullptr;
@@ -197,6 +206,7 @@ class Engine {
     void post_worker();
     uint64_t next_id_ = 0;
     StepStats stats_;
+    std::vector<float> latencies_ms_;  // guarded by stats_mu_
     std::mutex stats_mu_;
 };
 

@@ -113,6 +113,7 @@ struct LatHeader {
     int n_tok, n_links, n_final, start;  // start = lattice state of the initial token (-1: empty lattice)
     int error, frames, pad0, pad1;
 };
+constexpr int kPartialCap = 256;
 constexpr int kEpsLinkFlag = 0x40000000;  // set in the destination field of an epsilon link
 struct DecArgs {
     const LaneDesc *lanes;
@@ -163,7 +164,10 @@ struct DecArgs {
     int *lat_tok_frame;      // [L][lat_tok_cap] frame of each lattice state
     int *lat_tok_state;      // [L][lat_tok_cap] graph state (only when log_state is kept), else null
     int lat_link_cap, lat_final_cap, lat_tok_cap;
-    unsigned long long *counters;     // [16] profiling counters (tokens, arcs, ...)
+    // partial results (partials != 0): output labels of the current best path of every unfinished lane, newest first
+    int *partial_words;      // [L][kPartialCap]
+    int *partial_count;      // [L] words on the path (may exceed kPartialCap: the oldest are cut)
+    unsigned long long *counters;     // [32] profiling counters (tokens, arcs, ...)
     int *lane_load;          // [lanes] largest token count a lane saw in this launch (load feedback)
     int grid;                // CTAs' worth of scratch allocated per slot
     // one launch serves lanes [lane_begin, lane_end): CTAs pull the next lane from *queue (zeroed before the launch; lanes
@@ -185,6 +189,8 @@ cudaError_t vbk_make_weight_map(const float *w, int N, int K, void *out128);
 cudaError_t vbk_decode(const DecArgs *a, int heavy, cudaStream_t s);
 // backward extra-cost pruning (lattice_beam) + compaction of the link log of the lanes whose stream ended in this step
 cudaError_t vbk_lattice_prune(const DecArgs *a, cudaStream_t s);
+// best path so far (no final costs) of every unfinished lane -> its output labels (GetBestPath(use_final_probs = false))
+cudaError_t vbk_partial(const DecArgs *a, cudaStream_t s);
 int vbk_decode_max_grid(int device);
 // copies rows [t_begin, t_begin+n) of a node ring for one channel into dst (debug capture / tests)
 cudaError_t vbk_copy_rows(NodeDesc node, int channel, int t_begin, int n_rows, float *dst, cudaStream_t s);

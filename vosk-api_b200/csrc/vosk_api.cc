@@ -219,6 +219,24 @@ const char *vosk_batch_model_resident_result(VoskBatchModel *model, int stream) 
     return bm->resident_results[stream].c_str();
 }
 
+const char *vosk_batch_recognizer_partial_result(VoskBatchRecognizer *recognizer) {
+    if (!recognizer) return "";
+    try {
+        return ((BatchRecognizer *)recognizer)->PartialResult();
+    } catch (...) {
+        return "";
+    }
+}
+int vosk_batch_recognizer_partial_frames(VoskBatchRecognizer *recognizer) {
+    return recognizer ? ((BatchRecognizer *)recognizer)->PartialFrames() : 0;
+}
+int vosk_batch_model_latency(VoskBatchModel *model, double *out5, int reset) {
+    if (!model || !out5) return 0;
+    BatchModel *bm = (BatchModel *)model;
+    bm->engine(0).latency(out5, reset != 0);  // per engine; engine 0 reported (streams are sharded evenly)
+    return 5;
+}
+
 void vosk_batch_recognizer_debug_capture(VoskBatchRecognizer *recognizer) {
     if (recognizer) ((BatchRecognizer *)recognizer)->EnableCapture();
 }

@@ -88,6 +88,11 @@ class BatchModel(object):
         keys += ["cyc_%s_%s" % (v, ph) for v in ("heavy", "light") for ph in ("cutoff", "rank", "log", "gather", "insert", "closure", "finalize", "x")]
         return {k: buf[i] for i, k in enumerate(keys[:n])}
 
+    def Latency(self, reset=False):
+        buf = _ffi.new("double[5]")
+        _c.vosk_batch_model_latency(self._handle, buf, int(reset))
+        return dict(p50=buf[0], p90=buf[1], p99=buf[2], mean=buf[3], count=int(buf[4]))
+
     def ResetStats(self):
         _c.vosk_batch_model_reset_stats(self._handle)
 
@@ -141,6 +146,13 @@ class BatchRecognizer(object):
 
     def SetNLSML(self, on):
         _c.vosk_batch_recognizer_set_nlsml(self._handle, int(on))
+
+    # ---- additive surface: partial results (model option partials=1) ----
+    def PartialResult(self):
+        return _ffi.string(_c.vosk_batch_recognizer_partial_result(self._handle)).decode()
+
+    def PartialFrames(self):
+        return _c.vosk_batch_recognizer_partial_frames(self._handle)
 
     # ---- additive surface: test taps ----
     def DebugCapture(self):
