@@ -115,6 +115,49 @@ def e2e_pass(vosk, model, pieces, wait_each_round=False):
     return texts
 
 
+def latency_pass(vosk, mdir, n_streams, seconds, packet_ms=100, fpc=10):
+    """BASELINE.json configs[3]: low-latency streaming with partial results.  n_streams recognizers are fed packet_ms
+    packets in real time (one packet per stream per tick); the engine records, for every chunk, the time from the
+    acceptance of its last sample to the moment the partial covering it is retrievable."""
+    model = vosk.BatchModel(mdir, options="partials=1,frames-per-chunk=%d,num-channels=%d,max-batch-size=%d,max-seconds=%d"
+                            % (fpc, n_streams, min(n_streams, 1024), int(seconds) + 4))
+    waves = make_audio(64, 77, seconds, seconds + 0.01)
+    step = packet_ms * 16
+    recs = [vosk.BatchRecognizer(model, 16000.0) for _ in range(n_streams)]
+    pk = [[w[i:i + step].tobytes() for i in range(0, len(w) - step + 1, step)] for w in waves]
+    n_ticks = min(len(p) for p in pk)
+    # warm-up tick (first launches, allocator) is not counted
+    for i, r in enumerate(recs):
+        r.AcceptWaveform(pk[i % 64][0])
+    model.Wait()
+    model.Latency(reset=True)
+    t0 = time.perf_counter()
+    late = 0
+    for k in range(1, n_ticks):
+        target = t0 + (k - 1) * packet_ms / 1000.0
+        now = time.perf_counter()
+        if now < target:
+            time.sleep(target - now)
+        elif now - target > packet_ms / 1000.0:
+            late += 1
+        for i, r in enumerate(recs):
+            r.AcceptWaveform(pk[i % 64][k])
+    model.Wait()
+    wall = time.perf_counter() - t0
+    lat = model.Latency()
+    sample = recs[0].PartialResult()
+    for r in recs:
+        r.FinishStream()
+    model.Wait()
+    del recs
+    del model
+    return {"p50_ms": lat["p50"], "p90_ms": lat["p90"], "p99_ms": lat["p99"], "mean_ms": lat["mean"], "chunks": lat["count"],
+            "streams": n_streams, "frames_per_chunk": fpc, "packet_ms": packet_ms, "feed": "real-time paced, one packet per stream per tick",
+            "ticks": n_ticks - 1, "late_ticks": late, "wall_s": wall, "audio_s_per_stream": (n_ticks - 1) * packet_ms / 1000.0,
+            "definition": "acceptance of a chunk's last sample -> partial result covering it retrievable (host clock, engine-side)",
+            "sample_partial": sample[:80]}
+
+
 def reduce_over_ranks(x, op="max", device="cpu"):
     """Max / sum of a python float over the ranks of the default process group (identity when not distributed)."""
     import torch
@@ -162,6 +205,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--options", default="")
     ap.add_argument("--wait-each-round", action="store_true", help="call Wait() after every feeding round, as the reference example does")
+    ap.add_argument("--no-extras", action="store_true", help="skip the lattice-mode and partial-latency legs")
+    ap.add_argument("--latency-streams", type=int, default=2048)
+    ap.add_argument("--latency-seconds", type=float, default=4.0)
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -300,6 +346,42 @@ def main():
         roof = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"]}
 
+    # ---------------- extras (rank 0): lattice generation on, and the low-latency / partial-result configuration ----------------
+    del model
+    lattice_mode = None
+    partial_latency = None
+    if rank == 0 and not a.no_extras:
+        try:
+            res = {}
+            for mode, name in ((2, "device_lattice"), (1, "device_lattice_plus_host_mbr")):
+                lm = vosk.BatchModel(mdir, options=opts + ",lattice=%d" % mode)
+                lm.RunResident(audio_mat, lengths)
+                lm.ResetStats()
+                lm.SetTiming(True)
+                ms, ltexts = lm.RunResident(audio_mat, lengths)
+                lst = lm.Stats()
+                res[name] = {"value": audio_s / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms, "links_logged": lst["links"],
+                             "lattice_arcs_after_pruning": lst["lattice_arcs"], "search_ms_overlapped": lst["ms_search"]}
+                if mode == 1:
+                    res[name]["results_with_confidence_below_1"] = sum(1 for t in ltexts if '"conf" : 0.' in t)
+                    res[name]["host_threads"] = "hardware threads / 2 (lattice pool)"
+                del lm
+            lattice_mode = res
+        except Exception as e:  # the extras never take the headline line down
+            lattice_mode = {"error": str(e)[:200]}
+        try:
+            partial_latency = latency_pass(vosk, mdir, a.latency_streams, a.latency_seconds)
+        except Exception as e:
+            partial_latency = {"error": str(e)[:200]}
+
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get({"search": "decode_kernel", "tdnnf": "gemm_tc_kernel", "ivector": "ivector_kernel", "mfcc": "mfcc_kernel"}[dominant])
+    except Exception:
+        pass
+    roof["traffic"] = traffic
+
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
         ca, cw = run_oracle_sample(12, 1)
@@ -317,9 +399,9 @@ def main():
                 "roofline_note": "stage durations from one extra pass with the pipeline slots serialized (no overlap); CUDA events on the launching stream",
                 "host_wall_ms_per_step_resident": wall_resident * 1000.0 / a.steps,
                 "search_counters_per_step": {"tokens": T, "arcs_emitting": Ae, "arcs_epsilon": Aeps, "tokens_new": N},
-                "audio_seconds_per_step": audio_total}
+                "audio_seconds_per_step": audio_total,
+                "lattice_mode": lattice_mode, "partial_latency": partial_latency}
         print(json.dumps(line))
-    del model
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -115,8 +115,9 @@ def test_max_active_binds(model_root, oracle_lib):
         _check_stream(model, oracle_lib, w, g, 51)
 
 
+@pytest.mark.parametrize("heavy", [2500, 0])
 @pytest.mark.parametrize("arch,lb", [("tiny", 6.0), ("tiny", 1.5), ("small", 6.0)])
-def test_lattice_generation(model_root, oracle_lib, arch, lb):
+def test_lattice_generation(model_root, oracle_lib, arch, lb, heavy):
     """lattice=1: the link log pruned on the device equals LatticeFasterDecoder's raw lattice (oracle), bit for bit."""
     import vbmodel
     mdir = model_root(arch)
@@ -125,7 +126,7 @@ def test_lattice_generation(model_root, oracle_lib, arch, lb):
     # within fp32 rounding of such a threshold flips that one decision against the fp64 oracle — seed 901 does — and is
     # not a usable parity case, exactly as it would not be between Kaldi's own CPU and GPU feature code)
     waves = _waves([0.3, 1.3, 2.04, 3.7] if arch == "tiny" else [2.5, 0.9], seed0=900 if arch == "tiny" else 920)
-    got, stats = helpers.run_engine(mdir, waves, options=f"lattice=1,lattice-beam={lb},num-channels=4,max-batch-size=4,max-seconds=10")
+    got, stats = helpers.run_engine(mdir, waves, options=f"lattice=1,lattice-beam={lb},num-channels=4,max-batch-size=4,max-seconds=10,heavy-tokens={heavy}")
     assert stats["links"] > 0 and stats["lattice_arcs"] > 0
     for w, g in zip(waves, got):
         _check_stream(model, oracle_lib, w, g, 51, lattice_beam=lb, mdir=mdir)
@@ -196,3 +197,27 @@ def test_partial_results_follow_the_best_path(model_root, oracle_lib):
         lat = m.Latency()
         assert lat["count"] >= seen and lat["p50"] > 0
         del r, m
+
+
+def test_lattice_mode_is_deterministic(model_root):
+    """Same input, three runs: identical counters and lattices (guards the shared-counter race at the final pass)."""
+    import vbmodel
+    import vosk
+    mdir = model_root("small")
+    waves = _waves([2.2 + 0.05 * i for i in range(48)], seed0=1500)
+    lengths = np.array([len(w) for w in waves], dtype=np.int32)
+    mat = np.zeros((len(waves), int(lengths.max() + 7) // 8 * 8), dtype=np.int16)
+    for i, w in enumerate(waves):
+        mat[i, :len(w)] = w
+    m = vosk.BatchModel(mdir, options="lattice=1,num-channels=48,max-batch-size=48,max-seconds=6,heavy-tokens=600")
+    seen = set()
+    texts0 = None
+    for rep in range(3):
+        m.ResetStats()
+        _, texts = m.RunResident(mat, lengths)
+        st = m.Stats()
+        seen.add((st["tokens"], st["tokens_new"], st["links"], st["lattice_arcs"]))
+        texts0 = texts0 or texts
+        assert texts == texts0
+    assert len(seen) == 1 and next(iter(seen))[3] > 0
+    del m

@@ -17,12 +17,13 @@ BatchRecognizer::BatchRecognizer(BatchModel *model, float sample_frequency)
     std::shared_ptr<Sink> sink = sink_;
     const Model *m = &model->model();
     const float lattice_beam = model->engine_for(id_).config().lattice_beam;
-    stream_->on_result = [sink, m, lattice_beam](const BestPath &bp) {
+    const bool host_chain = model->engine_for(id_).config().lattice == 1;  // lattice=2: device lattice only, text from the best path
+    stream_->on_result = [sink, m, lattice_beam, host_chain](const BestPath &bp) {
         // lattice=1: PushLattice's chain on the pruned raw lattice [REF src/batch_recognizer.cc:43-56]; otherwise (and if the
         // lattice came back empty or over capacity) the best path, which is the MBR result of a linear lattice
         std::vector<WordSpan> words;
         bool done = false;
-        if (bp.lattice && bp.lattice->error == 0 && bp.lattice->n_states > 0) {
+        if (host_chain && bp.lattice && bp.lattice->error == 0 && bp.lattice->n_states > 0) {
             words = lattice_to_words(*bp.lattice, *m, lattice_beam);
             done = !words.empty() || bp.arcs.empty();
         }

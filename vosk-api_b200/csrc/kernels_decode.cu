@@ -376,7 +376,8 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
             const int4 sc = c.cand[cd.w];
             const unsigned long long spk = ((unsigned long long)(unsigned)sc.y << 32) | (unsigned)sc.x;
             src_ok = sc.z >= 0 && !(sc.z & kAltFlag) && tab_val(c, sc.z) == spk;
-            if (src_ok) src_tok = tab_tok(c, sc.z);
+            // the source STATE's token (a superseded twin of equal cost still names the right predecessor token)
+            if (sc.z >= 0) src_tok = tab_tok(c, sc.z & ~kAltFlag);
         }
         const int dst_tok = tab_tok(c, slot);
         if (winner && is_eps && dst_tok < a.tok_cap) t_prev[dst_tok] = -2 - src_tok;
@@ -510,6 +511,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             int *n_prev = a.tok_prev + tbase + (size_t)(parity ^ 1) * a.tok_cap;
             if (n_cur == 0 && !final_pass) { frame++; continue; }  // search died: nothing to expand
             max_tok = max(max_tok, n_cur);
+            __syncthreads();  // every thread has read the previous frame's shared counters (n_next, n_links) before they are reset
             if (tid == 0) tph = clock64();
             float adaptive_beam = a.beam, best = 0.f, cur_cutoff = INFINITY;
             if (!final_pass) {
@@ -1035,6 +1037,8 @@ __global__ void __launch_bounds__(kPruneThreads) lattice_prune_kernel(DecArgs a)
         out_links[k] = lk;
     }
     if (tid == 0) {
+        if (hdr->pad1 == 12345 && (hdr->n_links != n_out || hdr->n_tok != min(base, a.lat_tok_cap)) && a.counters) atomicAdd(a.counters + 11, 1ull);
+        hdr->pad1 = 12345;
         hdr->n_tok = min(base, a.lat_tok_cap);
         hdr->n_links = n_out;
         hdr->n_final = min(s_nfinal, a.lat_final_cap);

@@ -54,6 +54,7 @@ Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg)
     VB_CUDA_CHECK(cudaStreamCreateWithFlags(&fe_stream_, cudaStreamNonBlocking));
     VB_CUDA_CHECK(cudaStreamCreateWithFlags(&dec_stream_, cudaStreamNonBlocking));
     VB_CUDA_CHECK(cudaStreamCreateWithFlags(&dec_stream2_, cudaStreamNonBlocking));
+    VB_CUDA_CHECK(cudaStreamCreateWithFlags(&post_stream_, cudaStreamNonBlocking));
     upload_model();
     alloc_state();
     thread_ = std::thread([this] { worker(); });
@@ -101,7 +102,7 @@ Engine::~Engine() {
     for (auto &t : post_threads_) t.join();
     cudaSetDevice(cfg_.device);
     cudaStreamSynchronize(stream_);
-    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_})
+    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_, post_stream_})
         if (q) cudaStreamSynchronize(q);
     for (void *p : allocs_) cudaFree(p);
     for (Slot &sl : slots_) {
@@ -121,10 +122,11 @@ Engine::~Engine() {
         if (sl.fork) cudaEventDestroy(sl.fork);
         if (sl.join) cudaEventDestroy(sl.join);
         if (sl.fe_done) cudaEventDestroy(sl.fe_done);
+        if (sl.dec_done) cudaEventDestroy(sl.dec_done);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (h_capture_) cudaFreeHost(h_capture_);
-    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_})
+    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_, post_stream_})
         if (q) cudaStreamDestroy(q);
     cudaStreamDestroy(stream_);
 }
@@ -385,6 +387,7 @@ void Engine::alloc_state() {
         for (auto &ev : sl.ev) VB_CUDA_CHECK(cudaEventCreate(&ev));
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.fe_done, cudaEventDisableTiming));
+        VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.dec_done, cudaEventDisableTiming));
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.fork, cudaEventDisableTiming));
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.join, cudaEventDisableTiming));
         sl.d_queue = dev_alloc<int>(allocs_, 2, 0);
@@ -481,6 +484,7 @@ StepStats Engine::stats() {
     s.arcs_staged = c[8];
     s.links = c[9];
     s.lat_arcs = c[10];
+    s.prune_mismatch = c[11];
     for (int k = 0; k < 16; k++) s.phase[k] = c[16 + k];
     return s;
 }
@@ -745,25 +749,35 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_partial, sl.dec.partial_words, (size_t)L * kPartialCap * sizeof(int), cudaMemcpyDeviceToHost, st));
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_partial + (size_t)L * kPartialCap, sl.dec.partial_count, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
+    if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[4], st));
+    // results of finished lanes
+    int k_last = 0;
+    for (int i = 0; i < L; i++)
+        if (lanes[i].chunk.last) {
+            const int ch = lanes[i].s->channel;
+            VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_cs + k_last, dec_.cs + ch, sizeof(DecChannelState), cudaMemcpyDeviceToHost, st));
+            VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_path + (size_t)k_last * path_cap_, dec_.path + (size_t)ch * path_cap_,
+                                          (size_t)path_cap_ * sizeof(int), cudaMemcpyDeviceToHost, st));
+            k_last++;
+        }
+    VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_load, sl.d_load, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (cfg_.lattice && n_last > 0) {
+        // lattice pruning only touches finished channels (nothing else does until they are reused after completion), so
+        // it leaves the search pipe and runs beside the next steps on its own stream
+        VB_CUDA_CHECK(cudaEventRecord(sl.dec_done, st));
+        st = post_stream_;
+        VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.dec_done, 0));
         sl.dec.lane_begin = 0;
         sl.dec.lane_end = L;
+        static const bool twice = getenv("VB_PRUNE_TWICE") != nullptr;  // determinism probe: same inputs, two launches
+        if (twice) {
+            VB_CUDA_CHECK(cudaMemsetAsync(sl.dec.lat_hdr, 0, (size_t)L * sizeof(LatHeader), st));
+            VB_CUDA_CHECK(vbk_lattice_prune(&sl.dec, st));
+        }
         VB_CUDA_CHECK(vbk_lattice_prune(&sl.dec, st));
         sl.launches++;
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_hdr, sl.dec.lat_hdr, (size_t)L * sizeof(LatHeader), cudaMemcpyDeviceToHost, st));
     }
-    if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[4], st));
-    // results of finished lanes
-    n_last = 0;
-    for (int i = 0; i < L; i++)
-        if (lanes[i].chunk.last) {
-            const int ch = lanes[i].s->channel;
-            VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_cs + n_last, dec_.cs + ch, sizeof(DecChannelState), cudaMemcpyDeviceToHost, st));
-            VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_path + (size_t)n_last * path_cap_, dec_.path + (size_t)ch * path_cap_,
-                                          (size_t)path_cap_ * sizeof(int), cudaMemcpyDeviceToHost, st));
-            n_last++;
-        }
-    VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_load, sl.d_load, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_CUDA_CHECK(cudaEventRecord(sl.done, st));
     {
         std::lock_guard<std::mutex> lk(stats_mu_);

@@ -83,7 +83,7 @@ struct StepStats {
     long long steps = 0, lanes = 0, launches = 0;
     unsigned long long tok = 0, arc_e = 0, arc_eps = 0, tok_new = 0;
     unsigned long long lane_cycles_sum = 0, lane_cycles_max = 0, max_tokens = 0, lane_launches = 0;
-    unsigned long long arcs_staged = 0, links = 0, lat_arcs = 0;
+    unsigned long long arcs_staged = 0, links = 0, lat_arcs = 0, prune_mismatch = 0;
     unsigned long long phase[16] = {};  // search cycles per phase (cutoff, rank, log, gather, insert, closure, finalize, -) of the heavy / light CTAs  // arcs parked below the running cutoff, links logged, lattice arcs kept
     double t_feat = 0, t_ivec = 0, t_nnet = 0, t_dec = 0, t_total = 0;  // device ms (only when timing enabled)
     long long dec_launches = 0, gemm_launches = 0;
@@ -130,7 +130,7 @@ class Engine {
     // the log-likelihood rings.
     struct Slot {
         cudaStream_t stream = nullptr;  // utility stream (debug taps, lattice fetch) of the slot
-        cudaEvent_t fe_done = nullptr, fork = nullptr, join = nullptr;
+        cudaEvent_t fe_done = nullptr, dec_done = nullptr, fork = nullptr, join = nullptr;
         int *d_queue = nullptr;  // [2] lane queues of the two search launches
         cudaEvent_t ev[6] = {};
         cudaEvent_t done = nullptr;
@@ -163,7 +163,7 @@ class Engine {
     const Model &model_;
     Config cfg_;
     cudaStream_t stream_ = nullptr;  // setup / utility stream
-    cudaStream_t fe_stream_ = nullptr, dec_stream_ = nullptr, dec_stream2_ = nullptr;  // the two pipes (+ the light-lane search launch)
+    cudaStream_t fe_stream_ = nullptr, dec_stream_ = nullptr, dec_stream2_ = nullptr, post_stream_ = nullptr;  // the two pipes (+ the light-lane search launch)
     std::vector<Slot> slots_;
     bool timing_ = false;
     std::atomic<int> active_slots_{1};

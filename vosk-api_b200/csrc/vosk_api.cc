@@ -153,6 +153,7 @@ int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
         v[13] += s.lane_cycles_sum; v[14] = std::max(v[14], (double)s.lane_cycles_max); v[15] = std::max(v[15], (double)s.max_tokens); v[16] += s.lane_launches; v[17] += s.host_launch_ms;
         v[18] += s.arcs_staged; v[19] += s.links; v[20] += s.lat_arcs;
         for (int k = 0; k < 16; k++) v[21 + k] += s.phase[k];
+        v[36] = (double)s.prune_mismatch;  // probe (VB_PRUNE_TWICE): replaces the unused last phase slot
     }
     int k = n < 37 ? n : 37;
     memcpy(out, v, k * sizeof(double));
@@ -190,12 +191,13 @@ double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio
         bm->resident_results.assign(num_streams, std::string());
         const vb::Model *m = &bm->model();
         const float lattice_beam = eng.config().lattice_beam;
+        const bool host_chain = eng.config().lattice == 1;
         std::vector<std::string> *texts = &bm->resident_results;
         // result text is produced where the engine delivers results (the lattice pool when lattice=1), inside the timed region
-        eng.resident_hook = [m, lattice_beam, texts](int i, const vb::BestPath &bp) {
+        eng.resident_hook = [m, lattice_beam, texts, host_chain](int i, const vb::BestPath &bp) {
             std::vector<vb::WordSpan> words;
             bool done = false;
-            if (bp.lattice && bp.lattice->error == 0 && bp.lattice->n_states > 0) {
+            if (host_chain && bp.lattice && bp.lattice->error == 0 && bp.lattice->n_states > 0) {
                 words = vb::lattice_to_words(*bp.lattice, *m, lattice_beam);
                 done = !words.empty() || bp.arcs.empty();
             }
