@@ -20,12 +20,12 @@ def model_root(tmp_path_factory):
     base = os.environ.get("VB_MODEL_CACHE") or str(tmp_path_factory.mktemp("models"))
     made = {}
 
-    def get(arch="tiny", seed=0):
-        key = f"{arch}_{seed}"
+    def get(arch="tiny", seed=0, overrides=None, tag=""):
+        key = f"{arch}_{seed}{tag}"
         if key not in made:
             root = os.path.join(base, key)
             if not os.path.exists(os.path.join(root, "model", "graph", "HCLG.fst")):
-                vbmodel.write_model_dir(root, arch, seed)
+                vbmodel.write_model_dir(root, arch, seed, overrides=overrides)
             made[key] = os.path.join(root, "model")
         return made[key]
 
