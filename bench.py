@@ -377,7 +377,13 @@ def main():
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get({"search": "decode_kernel", "tdnnf": "gemm_tc_kernel", "ivector": "ivector_kernel", "mfcc": "mfcc_kernel"}[dominant])
+        ent = tj.get({"search": "decode_kernel", "tdnnf": "gemm_tc_kernel", "ivector": "ivector_kernel", "mfcc": "mfcc_kernel"}[dominant])
+        if ent:
+            traffic = ent["value"]
+            roof["traffic_note"] = ent["unit"] + "; from " + tj["_source"]
+            if dominant == "search":  # the same unit for the algorithmic side: bytes of one search step (512 lanes x 17 frames)
+                steps_run = max(1.0, st["steps"])
+                roof["algorithmic_bytes_per_search_step"] = search_bytes / steps_run
     except Exception:
         pass
     roof["traffic"] = traffic

@@ -26,6 +26,8 @@ static void apply_option(Config *c, const std::string &k, const std::string &v) 
     else if (k == "tensor-cores") I(&c->use_tensor_cores);
     else if (k == "pipeline-slots") I(&c->pipeline_slots);
     else if (k == "heavy-tokens") I(&c->heavy_tokens);
+    else if (k == "mid-tokens") I(&c->mid_tokens);
+    else if (k == "mid-threads") I(&c->mid_threads);
     else if (k == "heavy-threads") I(&c->heavy_threads);
     else if (k == "light-threads") I(&c->light_threads);
     else if (k == "debug-capture") I(&c->debug_capture);

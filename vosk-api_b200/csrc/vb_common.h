@@ -53,8 +53,9 @@ struct Config {
     int max_seconds = 24;       // token-log capacity per channel (decoder frames = seconds * 100 / 3)
     int log_tokens_per_frame = 4096;  // average logged tokens per frame the token log is sized for
     int device = 0;
-    int heavy_tokens = 2500;    // batches whose lanes exceed this many tokens per frame use the 1024-thread search CTAs
-    int heavy_threads = 1024, light_threads = 256;  // search CTA sizes for heavy / light batches
+    int heavy_tokens = 2500;    // lanes above this many tokens per frame get the 1024-thread search CTAs,
+    int mid_tokens = 900;       // ... lanes above this the 512-thread ones, the rest 256
+    int heavy_threads = 1024, mid_threads = 512, light_threads = 256;
     int pipeline_slots = 4;     // lane groups in flight on separate CUDA streams
     int num_gselect = 5;        // ivector.conf
     float min_post = 0.025f, posterior_scale = 0.1f, max_count = 100.0f;  // [REF src/model.cc:257]

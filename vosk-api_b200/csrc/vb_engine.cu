@@ -54,6 +54,7 @@ Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg)
     VB_CUDA_CHECK(cudaStreamCreateWithFlags(&fe_stream_, cudaStreamNonBlocking));
     VB_CUDA_CHECK(cudaStreamCreateWithFlags(&dec_stream_, cudaStreamNonBlocking));
     VB_CUDA_CHECK(cudaStreamCreateWithFlags(&dec_stream2_, cudaStreamNonBlocking));
+    VB_CUDA_CHECK(cudaStreamCreateWithFlags(&dec_stream3_, cudaStreamNonBlocking));
     VB_CUDA_CHECK(cudaStreamCreateWithFlags(&post_stream_, cudaStreamNonBlocking));
     upload_model();
     alloc_state();
@@ -102,7 +103,7 @@ Engine::~Engine() {
     for (auto &t : post_threads_) t.join();
     cudaSetDevice(cfg_.device);
     cudaStreamSynchronize(stream_);
-    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_, post_stream_})
+    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_, dec_stream3_, post_stream_})
         if (q) cudaStreamSynchronize(q);
     for (void *p : allocs_) cudaFree(p);
     for (Slot &sl : slots_) {
@@ -120,13 +121,13 @@ Engine::~Engine() {
         for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.fork) cudaEventDestroy(sl.fork);
-        if (sl.join) cudaEventDestroy(sl.join);
+        for (auto &j : sl.join) if (j) cudaEventDestroy(j);
         if (sl.fe_done) cudaEventDestroy(sl.fe_done);
         if (sl.dec_done) cudaEventDestroy(sl.dec_done);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (h_capture_) cudaFreeHost(h_capture_);
-    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_, post_stream_})
+    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_, dec_stream3_, post_stream_})
         if (q) cudaStreamDestroy(q);
     cudaStreamDestroy(stream_);
 }
@@ -357,7 +358,7 @@ void Engine::alloc_state() {
         d.lat_tok_cap = cfg_.lat_tok_cap;
         d.lat_final_cap = cfg_.tok_cap;
     }
-    d.grid = std::min(vbk_decode_max_grid(cfg_.device), L);
+    d.grid = L;  // scratch for one CTA per lane: the tiers' launches together never have more CTAs than lanes
     {   // search scratch, one copy: the searches of all steps run in order on dec_stream_
         const size_t G = (size_t)d.grid;
         d.hash_key = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0xff);
@@ -389,8 +390,8 @@ void Engine::alloc_state() {
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.fe_done, cudaEventDisableTiming));
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.dec_done, cudaEventDisableTiming));
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.fork, cudaEventDisableTiming));
-        VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.join, cudaEventDisableTiming));
-        sl.d_queue = dev_alloc<int>(allocs_, 2, 0);
+        for (auto &j : sl.join) VB_CUDA_CHECK(cudaEventCreateWithFlags(&j, cudaEventDisableTiming));
+        sl.d_queue = dev_alloc<int>(allocs_, 4, 0);
         sl.d_staging = dev_alloc<int16_t>(allocs_, (size_t)L * spc, 0);
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_staging, (size_t)L * spc * sizeof(int16_t)));
         sl.d_lanes = dev_alloc<LaneDesc>(allocs_, (size_t)L, 0);
@@ -710,35 +711,40 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[5], st));
     sl.dec.lanes = sl.d_lanes;
     sl.dec.num_lanes = L;
-    int n_heavy = 0;
+    // three tiers by the token load of the lane's previous step (lanes are sorted by it): 1024-, 512- and 256-thread CTAs.
+    // Each tier is one launch with its own lane queue and scratch range; the launches run side by side.
+    int n_heavy = 0, n_mid = 0;
     while (n_heavy < L && lanes[n_heavy].s->load > cfg_.heavy_tokens) n_heavy++;
-    VB_CUDA_CHECK(cudaMemsetAsync(sl.d_queue, 0, 2 * sizeof(int), st));
-    sl.dec.queue = sl.d_queue;
-    sl.dec.lane_begin = 0;
-    sl.dec.lane_end = n_heavy;
-    sl.dec.scratch_base = 0;
-    const bool split = n_heavy > 0 && n_heavy < L;
-    if (split) {  // the light lanes run beside the heavy ones on the slot's second stream
-        VB_CUDA_CHECK(cudaEventRecord(sl.fork, st));
-        VB_CUDA_CHECK(cudaStreamWaitEvent(dec_stream2_, sl.fork, 0));
-    }
-    if (n_heavy > 0) {
-        VB_CUDA_CHECK(vbk_decode(&sl.dec, cfg_.heavy_threads, st));
+    n_mid = n_heavy;
+    while (n_mid < L && lanes[n_mid].s->load > cfg_.mid_tokens) n_mid++;
+    VB_CUDA_CHECK(cudaMemsetAsync(sl.d_queue, 0, 4 * sizeof(int), st));
+    const int tier_begin[3] = {0, n_heavy, n_mid}, tier_end[3] = {n_heavy, n_mid, L};
+    const int tier_threads[3] = {cfg_.heavy_threads, cfg_.mid_threads, cfg_.light_threads};
+    cudaStream_t tier_stream[3] = {st, dec_stream2_, dec_stream3_};
+    int n_tiers = 0, scratch = 0;
+    for (int t = 0; t < 3; t++) n_tiers += tier_end[t] > tier_begin[t];
+    if (n_tiers > 1) VB_CUDA_CHECK(cudaEventRecord(sl.fork, st));
+    bool first = true;
+    for (int t = 0; t < 3; t++) {
+        const int n = tier_end[t] - tier_begin[t];
+        if (n <= 0) continue;
+        cudaStream_t ts = first ? st : tier_stream[t];
+        if (!first) VB_CUDA_CHECK(cudaStreamWaitEvent(ts, sl.fork, 0));
+        DecArgs da = sl.dec;
+        da.queue = sl.d_queue + t;
+        da.lane_begin = tier_begin[t];
+        da.lane_end = tier_end[t];
+        da.scratch_base = scratch;
+        scratch += n;  // a launch never has more CTAs than lanes
+        VB_CUDA_CHECK(vbk_decode(&da, tier_threads[t], ts));
         sl.launches++;
-    }
-    if (n_heavy < L) {
-        DecArgs light = sl.dec;
-        light.queue = sl.d_queue + 1;
-        light.lane_begin = n_heavy;
-        light.lane_end = L;
-        light.scratch_base = std::min(n_heavy, vbk_decode_max_grid(cfg_.device) / (cfg_.heavy_threads >= 1024 ? 3 : 1));  // CTAs the heavy launch can have
-        VB_CUDA_CHECK(vbk_decode(&light, cfg_.light_threads, split ? dec_stream2_ : st));
-        sl.launches++;
-        if (split) {
-            VB_CUDA_CHECK(cudaEventRecord(sl.join, dec_stream2_));
-            VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.join, 0));
+        if (!first) {
+            VB_CUDA_CHECK(cudaEventRecord(sl.join[t - 1], ts));
+            VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.join[t - 1], 0));
         }
+        first = false;
     }
+    sl.dec.queue = sl.d_queue;
     int n_last = 0;
     for (int i = 0; i < L; i++) n_last += lanes[i].chunk.last ? 1 : 0;
     if (cfg_.partials && n_last < L) {

@@ -130,7 +130,7 @@ class Engine {
     // the log-likelihood rings.
     struct Slot {
         cudaStream_t stream = nullptr;  // utility stream (debug taps, lattice fetch) of the slot
-        cudaEvent_t fe_done = nullptr, dec_done = nullptr, fork = nullptr, join = nullptr;
+        cudaEvent_t fe_done = nullptr, dec_done = nullptr, fork = nullptr, join[2] = {};
         int *d_queue = nullptr;  // [2] lane queues of the two search launches
         cudaEvent_t ev[6] = {};
         cudaEvent_t done = nullptr;
@@ -163,7 +163,7 @@ class Engine {
     const Model &model_;
     Config cfg_;
     cudaStream_t stream_ = nullptr;  // setup / utility stream
-    cudaStream_t fe_stream_ = nullptr, dec_stream_ = nullptr, dec_stream2_ = nullptr, post_stream_ = nullptr;  // the two pipes (+ the light-lane search launch)
+    cudaStream_t fe_stream_ = nullptr, dec_stream_ = nullptr, dec_stream2_ = nullptr, dec_stream3_ = nullptr, post_stream_ = nullptr;  // the two pipes (+ the light-lane search launch)
     std::vector<Slot> slots_;
     bool timing_ = false;
     std::atomic<int> active_slots_{1};

@@ -808,7 +808,19 @@ std::vector<WordSpan> mbr_one_best(const CLat &aligned) {
         std::vector<std::vector<double>> alpha_dash(N + 1, std::vector<double>(Q + 1, 0.0)), beta_dash(N + 1, std::vector<double>(Q + 1, 0.0));
         std::vector<double> alpha_dash_arc(Q + 1), beta_dash_arc(Q + 1);
         std::vector<char> b_arc(Q + 1);
-        std::vector<std::map<int, double>> gamma(Q + 1), tau_b(Q + 1), tau_e(Q + 1);
+        // per position q: (word, gamma, tau_b, tau_e) of the few words aligned there; linear search beats a tree here
+        struct Acc { int word; double g, tb, te; };
+        std::vector<std::vector<Acc>> acc(Q + 1);
+        auto add = [&](int q, int word, double g, double tb, double te) {
+            for (Acc &x : acc[q])
+                if (x.word == word) {
+                    x.g += g;
+                    x.tb += tb;
+                    x.te += te;
+                    return;
+                }
+            acc[q].push_back(Acc{word, g, tb, te});
+        };
         alpha[1] = 0.0;
         alpha_dash[1][0] = 0.0;
         for (int q = 1; q <= Q; q++) alpha_dash[1][q] = alpha_dash[1][q - 1] + edit_l(0, r(q));
@@ -820,6 +832,7 @@ std::vector<WordSpan> mbr_one_best(const CLat &aligned) {
                 const MbrArc &arc = arcs[ai];
                 const int s_a = arc.start, w_a = arc.word;
                 const double p_a = arc.loglike;
+                const double arc_post_f = std::exp(alpha[s_a] + p_a - alpha[nn]);
                 for (int q = 0; q <= Q; q++) {
                     if (q == 0) {
                         alpha_dash_arc[q] = alpha_dash[s_a][q] + edit_l(w_a, 0, true);
@@ -828,7 +841,7 @@ std::vector<WordSpan> mbr_one_best(const CLat &aligned) {
                                      a3 = alpha_dash_arc[q - 1] + edit_l(0, r(q));
                         alpha_dash_arc[q] = std::min(a1, std::min(a2, a3));
                     }
-                    alpha_dash[nn][q] += std::exp(alpha[s_a] + p_a - alpha[nn]) * alpha_dash_arc[q];
+                    alpha_dash[nn][q] += arc_post_f * alpha_dash_arc[q];
                 }
             }
         }
@@ -856,18 +869,14 @@ std::vector<WordSpan> mbr_one_best(const CLat &aligned) {
                     switch (b_arc[q]) {
                         case 1:
                             beta_dash[s_a][q - 1] += beta_dash_arc[q];
-                            gamma[q][w_a] += beta_dash_arc[q];
-                            tau_b[q][w_a] += state_times[s_a] * beta_dash_arc[q];
-                            tau_e[q][w_a] += state_times[nn] * beta_dash_arc[q];
+                            add(q, w_a, beta_dash_arc[q], state_times[s_a] * beta_dash_arc[q], state_times[nn] * beta_dash_arc[q]);
                             break;
                         case 2:
                             beta_dash[s_a][q] += beta_dash_arc[q];
                             break;
                         case 3:
                             beta_dash_arc[q - 1] += beta_dash_arc[q];
-                            gamma[q][0] += beta_dash_arc[q];
-                            tau_b[q][0] += state_times[s_a] * beta_dash_arc[q];
-                            tau_e[q][0] += state_times[s_a] * beta_dash_arc[q];
+                            add(q, 0, beta_dash_arc[q], state_times[s_a] * beta_dash_arc[q], state_times[s_a] * beta_dash_arc[q]);
                             break;
                     }
                 }
@@ -879,22 +888,24 @@ std::vector<WordSpan> mbr_one_best(const CLat &aligned) {
         for (int q = Q; q >= 1; q--) {
             beta_dash_arc[q] += beta_dash[1][q];
             beta_dash_arc[q - 1] += beta_dash_arc[q];
-            gamma[q][0] += beta_dash_arc[q];
-            tau_b[q][0] += state_times[1] * beta_dash_arc[q];
-            tau_e[q][0] += state_times[1] * beta_dash_arc[q];
+            add(q, 0, beta_dash_arc[q], state_times[1] * beta_dash_arc[q], state_times[1] * beta_dash_arc[q]);
         }
         gamma_out.assign(Q, {});
         times_out.assign(Q, {});
         for (int q = 1; q <= Q; q++) {
             auto &gq = gamma_out[q - 1];
-            for (auto &kv : gamma[q]) gq.emplace_back(kv.first, (float)kv.second);
-            std::sort(gq.begin(), gq.end(), [](const std::pair<int, float> &x, const std::pair<int, float> &y) {
-                if (x.second > y.second) return true;
-                if (x.second < y.second) return false;
-                return x.first > y.first;
+            std::vector<Acc> &aq = acc[q];
+            std::sort(aq.begin(), aq.end(), [](const Acc &x, const Acc &y) {  // GammaCompare on the float posteriors
+                const float gx = (float)x.g, gy = (float)y.g;
+                if (gx > gy) return true;
+                if (gx < gy) return false;
+                return x.word > y.word;
             });
-            for (auto &pr : gq)
-                times_out[q - 1].emplace_back((float)(tau_b[q][pr.first] / pr.second), (float)(tau_e[q][pr.first] / pr.second));
+            for (const Acc &x : aq) {
+                const float g = (float)x.g;
+                gq.emplace_back(x.word, g);
+                times_out[q - 1].emplace_back((float)(x.tb / g), (float)(x.te / g));
+            }
         }
         // ---- MbrDecode step ----
         double delta_Q = 0.0;
