@@ -335,10 +335,17 @@ static EncodeTiledFn encode_fn() {
 
 // Number of hi*hi accumulators (fewer truncating adds per accumulator) and the N tile that fits
 // (n_main + 1) * BN fp32 columns into the 512 TMEM columns.
+// Measured on the small architecture (end-to-end log-likelihood error against the oracle, tolerance 1e-3): 4 main accumulators
+// at K = 192 (6 truncating adds each, 96-column tiles) 7e-4; 3 (8 adds, 128-column tiles, TDNN-F chain 12 % faster) 1.05e-3;
+// 1 (24 adds, 256-column tiles, 22 % faster) 1.3e-3.  The tolerance decides: 4.  Wider tiles need the accumulators drained
+// into fp32 registers every few k-steps.
 static int main_accs(int K) { return K >= 128 ? 4 : K >= 64 ? 2 : 1; }
 static int tile_n(int N, int K) {
     int limit = (512 / (main_accs(K) + 1)) & ~15;
-    return N < limit ? N : limit;
+    if (N <= limit) return N;
+    for (int bn = limit; bn >= 64; bn -= 16)  // whole tiles only: the largest multiple of 16 that divides N
+        if (N % bn == 0) return bn;
+    return limit;
 }
 
 extern "C" cudaError_t vbk_make_weight_map(const float *w, int N, int K, void *out128) {
