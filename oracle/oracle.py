@@ -289,3 +289,27 @@ def recognize(model, wave, frames_per_chunk=51, stages=False, rc=None, **over):
     if stages:
         return dict(mfcc=feats, ivectors=ivecs, loglikes=ll, decode=dec, text=text, iv_index=iv_index)
     return text
+
+
+def recognize_segments(model, wave, frames_per_chunk=51, rule5_seconds=20.0, rc=None, **over):
+    """The batch path with reset_on_endpoint [REF src/batch_model.cc:72]: Kaldi's default endpoint rules with the reference's
+    empty silence-phone list leave rule 5 (decoded length >= 20 s), tested after every chunk; a segment is finalized there,
+    the search starts over on the next chunk while features and i-vector carry on, and result times are offset by the
+    segment start (GetTimeOffsetSeconds [REF src/batch_recognizer.cc:146-147]).  Returns the list of result texts."""
+    ctx = model_context(model)
+    feats = mfcc(wave)
+    ends, avail, iv_index = chunk_plan(len(wave), frames_per_chunk, ctx)
+    ivecs = ivectors(model, feats, ends, avail)
+    ll = nnet_forward(model, feats, ivecs, iv_index)
+    rc = rc or ResultCtx(model)
+    rule5 = int(np.ceil(rule5_seconds / 0.03 - 1e-6)) if rule5_seconds > 0 else 0
+    texts, seg_start = [], 0
+    for k, a in enumerate(avail):
+        last = k == len(avail) - 1
+        dec = len(ll) if last else ((int(a) - ctx + 2) // 3 if a > ctx else 0)
+        if last or (rule5 and dec - seg_start >= rule5):
+            seg = ll[seg_start:dec]
+            d = decode(model, seg, **over) if len(seg) else dict(best_arcs=np.zeros(0, dtype=np.int32))
+            texts.append(result_json(model, d["best_arcs"], offset=float(np.float32(seg_start * 0.03)), rc=rc))
+            seg_start = dec
+    return texts

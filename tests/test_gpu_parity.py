@@ -239,3 +239,29 @@ def test_large_architecture_all_stages(model_root, oracle_lib, tc):
     tol = 2.5e-3 if tc else 1e-3
     for w, g in zip(waves, got):
         _check_stream(model, oracle_lib, w, g, 51, mdir=mdir, tol_ll=tol)
+
+
+def test_rule5_endpoint_segments(model_root, oracle_lib):
+    """reset_on_endpoint: streams longer than 20 s are cut at the first chunk boundary past 20 s of decoded audio; every
+    segment gives its own result, in order, with times offset by the segment start."""
+    import vbmodel
+    import vosk
+    mdir = model_root("tiny")
+    model = vbmodel.load_model_dir(mdir)
+    waves = [vbmodel.synth_audio(s, 1900 + i) for i, s in enumerate([25.0, 41.3, 7.0])]
+    for opts in ("", "lattice=2"):
+        m = vosk.BatchModel(mdir, options="num-channels=4,max-batch-size=4,max-seconds=24," + opts)
+        recs = [vosk.BatchRecognizer(m, 16000.0) for _ in waves]
+        helpers.feed_round_robin(recs, waves, 32000)
+        m.Wait()
+        for r, w in zip(recs, waves):
+            got = []
+            while True:
+                t = r.Result()
+                if not t:
+                    break
+                got.append(t)
+            want = oracle_lib.recognize_segments(model, w)
+            assert len(want) == (2 if len(w) < 40 * 16000 and len(w) > 20 * 16000 else 3 if len(w) > 40 * 16000 else 1)
+            assert got == want
+        del recs, m

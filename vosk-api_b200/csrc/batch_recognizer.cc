@@ -29,7 +29,12 @@ BatchRecognizer::BatchRecognizer(BatchModel *model, float sample_frequency)
         }
         if (!done) words = align_words(*m, bp.arcs);
         std::lock_guard<std::mutex> lk(sink->mu);
-        sink->results.push(sink->nlsml ? result_nlsml(*m, words) : result_json(*m, words, 0.0f));
+        sink->early[bp.seq] = sink->nlsml ? result_nlsml(*m, words) : result_json(*m, words, bp.offset);
+        for (auto it = sink->early.find(sink->next_seq); it != sink->early.end(); it = sink->early.find(sink->next_seq)) {
+            sink->results.push(std::move(it->second));  // results of a stream come out in segment order
+            sink->early.erase(it);
+            sink->next_seq++;
+        }
     };
 }
 

@@ -1,6 +1,7 @@
 // batch_recognizer.h — BatchRecognizer: same public surface as the reference class
 // [REF src/batch_recognizer.h:28-53], rebuilt over vb::Engine streams.
 #pragma once
+#include <map>
 #include <memory>
 #include <mutex>
 #include <queue>
@@ -34,6 +35,8 @@ class BatchRecognizer {
     struct Sink {
         std::mutex mu;
         std::queue<std::string> results;
+        std::map<int, std::string> early;  // segments finished out of order by the lattice pool wait here for their turn
+        int next_seq = 0;
         bool nlsml = false;
     };
     BatchModel *model_;

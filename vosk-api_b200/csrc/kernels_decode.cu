@@ -466,9 +466,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
         int4 *links = a.lattice ? a.links + (size_t)ch * a.link_cap : nullptr;
         int *link_off = a.lattice ? a.link_off + (size_t)ch * (a.max_frames + 3) : nullptr;
         __syncthreads();
-        if (tid == 0) sh.error = ln.first ? 0 : cs->error;
+        if (tid == 0) sh.error = ln.dec_first ? 0 : cs->error;
         int n_cur, parity, frame, log_count, link_count = 0, seg_begin = 0;
-        if (ln.first) {
+        if (ln.dec_first) {
             // InitDecoding: start token + epsilon closure with cutoff = beam
             if (tid == 0) {
                 sh.n_cand = 0;
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
         }
         const int nf = a.out_table[l].n_rows;
         const int t_first = a.out_table[l].t_begin;
-        const int total_frames = nf + (ln.last ? 1 : 0);  // the extra pass logs the final frame's tokens
+        const int total_frames = nf + (ln.dec_last ? 1 : 0);  // the extra pass logs the final frame's tokens
         for (int fi = 0; fi < total_frames; fi++) {
             const bool final_pass = fi == nf;
             const int *t_state = a.tok_state + tbase + (size_t)parity * a.tok_cap;
@@ -791,7 +791,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             frame++;
         }
         // ---- stream end: best token (cost + final, ties by state id) and on-device traceback ----
-        if (ln.last) {
+        if (ln.dec_last) {
             const int lo = frame <= a.max_frames ? frame_off[frame] : 0, hi = log_count;
             const int *t_state = a.tok_state + tbase + (size_t)parity * a.tok_cap;
             // survivors of the final pass are all tokens, logged in list order: log index = lo + i
@@ -895,7 +895,7 @@ __device__ __forceinline__ float link_extra(const DecArgs &a, const int4 l, cons
 __global__ void __launch_bounds__(kPruneThreads) lattice_prune_kernel(DecArgs a) {
     const int l = blockIdx.x;
     const LaneDesc ln = a.lanes[l];
-    if (!ln.last) return;
+    if (!ln.dec_last) return;
     constexpr int NT = kPruneThreads;
     __shared__ int s_changed, s_count, s_warp[NT / 32], s_nlinks, s_nfinal, s_start;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1063,7 +1063,7 @@ extern "C" cudaError_t vbk_lattice_prune(const DecArgs *a, cudaStream_t s) {
 __global__ void __launch_bounds__(32) partial_kernel(DecArgs a) {
     const int l = blockIdx.x, lane = threadIdx.x;
     const LaneDesc ln = a.lanes[l];
-    if (ln.last) return;
+    if (ln.dec_last) return;
     const int ch = ln.channel;
     const DecChannelState cs = a.cs[ch];
     int *out = a.partial_words + (size_t)l * kPartialCap;

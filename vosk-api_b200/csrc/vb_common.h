@@ -56,6 +56,9 @@ struct Config {
     int heavy_tokens = 2500;    // lanes above this many tokens per frame get the 1024-thread search CTAs,
     int mid_tokens = 900;       // ... lanes above this the 512-thread ones, the rest 256
     int heavy_threads = 1024, mid_threads = 512, light_threads = 256;
+    float endpoint_rule5_seconds = 20.0f;  // reset_on_endpoint [REF src/batch_model.cc:72] with Kaldi's default endpoint rules and the
+                                // reference's empty silence-phone list: only rule 5 (utterance length) can fire; 0 = never
+    int fe_priority = 0;        // CUDA stream priority of the front-end pipe relative to the search pipe (1 / 0 / -1)
     int pipeline_slots = 4;     // lane groups in flight on separate CUDA streams
     int num_gselect = 5;        // ivector.conf
     float min_post = 0.025f, posterior_scale = 0.1f, max_count = 100.0f;  // [REF src/model.cc:257]
@@ -109,6 +112,8 @@ struct LaneDesc {
     int dec_frames_before;  // decoder frames consumed before this step
     int src_row;       // sample source: staging + src_row * src_stride + src_off   (int16 units)
     int src_off;
+    int dec_first;     // first chunk of a SEGMENT: the search starts over (InitDecoding); features / i-vector carry on
+    int dec_last;      // last chunk of a segment (endpoint or stream end): final pass, traceback, lattice, result
 };
 
 // per step, per node, per lane (device, written by the plan kernel)

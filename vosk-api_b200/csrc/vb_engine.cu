@@ -51,10 +51,17 @@ Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg)
         throw std::runtime_error(std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range"));
     VB_CUDA_CHECK(cudaSetDevice(cfg_.device));
     VB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    VB_CUDA_CHECK(cudaStreamCreateWithFlags(&fe_stream_, cudaStreamNonBlocking));
-    VB_CUDA_CHECK(cudaStreamCreateWithFlags(&dec_stream_, cudaStreamNonBlocking));
-    VB_CUDA_CHECK(cudaStreamCreateWithFlags(&dec_stream2_, cudaStreamNonBlocking));
-    VB_CUDA_CHECK(cudaStreamCreateWithFlags(&dec_stream3_, cudaStreamNonBlocking));
+    {
+        // stream priorities decide who gets an SM when a search CTA retires: the short front-end CTAs of the next step or the
+        // queued search CTAs of this one (fe-priority: 1 = front end first, -1 = search first, 0 = none)
+        int lo = 0, hi = 0;
+        VB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const int pfe = cfg_.fe_priority > 0 ? hi : cfg_.fe_priority < 0 ? lo : 0, pdec = cfg_.fe_priority > 0 ? lo : cfg_.fe_priority < 0 ? hi : 0;
+        VB_CUDA_CHECK(cudaStreamCreateWithPriority(&fe_stream_, cudaStreamNonBlocking, pfe));
+        VB_CUDA_CHECK(cudaStreamCreateWithPriority(&dec_stream_, cudaStreamNonBlocking, pdec));
+        VB_CUDA_CHECK(cudaStreamCreateWithPriority(&dec_stream2_, cudaStreamNonBlocking, pdec));
+        VB_CUDA_CHECK(cudaStreamCreateWithPriority(&dec_stream3_, cudaStreamNonBlocking, pdec));
+    }
     VB_CUDA_CHECK(cudaStreamCreateWithFlags(&post_stream_, cudaStreamNonBlocking));
     upload_model();
     alloc_state();
@@ -663,6 +670,19 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         s.carry = d.frames_after > 0 ? (int)(total - (int64_t)kFrameShift * d.frames_after) : (int)total;
         s.dec_frames = d.in_end_after > ctx ? (d.in_end_after - ctx + kSubsample - 1) / kSubsample : 0;
         lanes[i].dec_frames_after = s.dec_frames;
+        // segmentation: a segment ends with the stream, or at the first chunk boundary where the decoded length reaches rule 5
+        const int rule5 = cfg_.endpoint_rule5_seconds > 0 ? (int)std::ceil(cfg_.endpoint_rule5_seconds / 0.03 - 1e-6) : 0;
+        const bool seg_end = ck.last || (rule5 > 0 && s.dec_frames - s.seg_start >= rule5);
+        d.dec_first = !s.seg_open;
+        d.dec_last = seg_end;
+        lanes[i].seg_end = seg_end;
+        lanes[i].seg_offset = (float)(s.seg_start * 0.03);
+        lanes[i].seg_index = s.seg_index;
+        s.seg_open = !seg_end;
+        if (seg_end) {
+            s.seg_start = s.dec_frames;
+            s.seg_index++;
+        }
     }
     sl.launches = 0;
     sl.gemms = 0;
@@ -746,7 +766,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     }
     sl.dec.queue = sl.d_queue;
     int n_last = 0;
-    for (int i = 0; i < L; i++) n_last += lanes[i].chunk.last ? 1 : 0;
+    for (int i = 0; i < L; i++) n_last += lanes[i].seg_end ? 1 : 0;
     if (cfg_.partials && n_last < L) {
         sl.dec.lane_begin = 0;
         sl.dec.lane_end = L;
@@ -759,7 +779,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     // results of finished lanes
     int k_last = 0;
     for (int i = 0; i < L; i++)
-        if (lanes[i].chunk.last) {
+        if (lanes[i].seg_end) {
             const int ch = lanes[i].s->channel;
             VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_cs + k_last, dec_.cs + ch, sizeof(DecChannelState), cudaMemcpyDeviceToHost, st));
             VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_path + (size_t)k_last * path_cap_, dec_.path + (size_t)ch * path_cap_,
@@ -807,7 +827,7 @@ void Engine::complete_step(Slot &sl) {
     }
     if (cfg_.partials)
         for (int i = 0; i < L; i++) {
-            if (lanes[i].chunk.last) continue;
+            if (lanes[i].seg_end) continue;
             const int total = sl.h_partial[(size_t)L * kPartialCap + i], n = std::min(total, kPartialCap);
             const int *w = sl.h_partial + (size_t)i * kPartialCap;
             Stream &s = *lanes[i].s;
@@ -874,7 +894,7 @@ void Engine::complete_step(Slot &sl) {
     }
     int n_last = 0;
     for (int i = 0; i < L; i++)
-        if (lanes[i].chunk.last) finish_lane(sl, lanes[i], n_last++, i);
+        if (lanes[i].seg_end) finish_lane(sl, lanes[i], n_last++, i);
 }
 
 // copies one finished lane's pruned lattice to the host (sizes come from the header that arrived with the step)
@@ -929,6 +949,8 @@ void Engine::finish_lane(Slot &sl, Lane &ln, int k, int lane_pos) {
     bp.reached_final = cs.reached_final != 0;
     bp.error = cs.error;
     bp.frames = cs.frame;
+    bp.offset = ln.seg_offset;
+    bp.seq = ln.seg_index;
     const int n = std::min(cs.path_len, path_cap_);
     bp.arcs.resize(n);
     const int *p = sl.h_path + (size_t)k * path_cap_;

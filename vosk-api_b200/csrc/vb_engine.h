@@ -39,6 +39,8 @@ struct BestPath {
     bool reached_final = false;
     int error = 0;
     int frames = 0;         // decoder frames
+    float offset = 0.f;     // start of the segment in the stream, seconds (GetTimeOffsetSeconds)
+    int seq = 0;            // index of the segment in its stream
 };
 
 // debug capture of one stream's intermediates (tests; enabled per stream before the first chunk)
@@ -61,6 +63,9 @@ struct Stream {
     int frames = 0;          // MFCC frames computed so far
     int iv_end = 0, in_end = 0, dec_frames = 0, carry = 0;
     int load = 0;            // tokens per frame seen in the stream's last step (batching key)
+    int seg_start = 0;       // decoder frames before the current segment
+    int seg_index = 0;       // segments closed so far
+    bool seg_open = false;   // the search of the current segment has been initialised
     bool resident = false;   // samples are read from a device-resident matrix (row = id)
     struct Chunk {
         std::vector<int16_t> samples;
@@ -121,6 +126,9 @@ class Engine {
         std::shared_ptr<Stream> s;
         Stream::Chunk chunk;
         int dec_frames_after = 0;
+        bool seg_end = false;    // this chunk closes a segment: a result is due
+        float seg_offset = 0.f;
+        int seg_index = 0;
     };
     // One pipeline slot = the buffers of one engine step (one chunk for each of up to max_lanes streams).  Steps flow
     // through two in-order pipes: the front end (H2D, features, i-vector, TDNN-F) on fe_stream_ and the search

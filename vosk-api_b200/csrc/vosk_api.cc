@@ -6,6 +6,9 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 
 #include "../../include/vosk_b200.h"
@@ -193,8 +196,10 @@ double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio
         const float lattice_beam = eng.config().lattice_beam;
         const bool host_chain = eng.config().lattice == 1;
         std::vector<std::string> *texts = &bm->resident_results;
+        auto parts = std::make_shared<std::vector<std::map<int, std::string>>>(num_streams);  // segment index -> text, per stream
+        auto parts_mu = std::make_shared<std::mutex>();
         // result text is produced where the engine delivers results (the lattice pool when lattice=1), inside the timed region
-        eng.resident_hook = [m, lattice_beam, texts, host_chain](int i, const vb::BestPath &bp) {
+        eng.resident_hook = [m, lattice_beam, parts, parts_mu, host_chain](int i, const vb::BestPath &bp) {
             std::vector<vb::WordSpan> words;
             bool done = false;
             if (host_chain && bp.lattice && bp.lattice->error == 0 && bp.lattice->n_states > 0) {
@@ -202,10 +207,14 @@ double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio
                 done = !words.empty() || bp.arcs.empty();
             }
             if (!done) words = vb::align_words(*m, bp.arcs);
-            (*texts)[i] = vb::result_json(*m, words, 0.0f);
+            std::string t = vb::result_json(*m, words, bp.offset);
+            std::lock_guard<std::mutex> lk(*parts_mu);
+            (*parts)[i][bp.seq] = std::move(t);
         };
         double ms = eng.run_resident(d_audio, num_streams, samples_per_stream, lengths, &res);
         eng.resident_hook = nullptr;
+        for (int i = 0; i < num_streams; i++)  // segments of one stream (rule-5 endpoints) are concatenated in order
+            for (auto &kv : (*parts)[i]) (*texts)[i] += kv.second;
         cudaFree(d_audio);
         return ms;
     } catch (const std::exception &e) {
