@@ -66,7 +66,7 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 template <int NT>
 struct Shared {
     unsigned min_ord;  // running minimum of candidate costs (ordered)
-    int n_cand, n_next, n_links, error;
+    int n_cand, n_next, n_links, n_work, error;
     int warp_cnt[(NT / 32)], warp_exp[(NT / 32)], warp_deg[(NT / 32)];
     unsigned hist[256];
     unsigned sel_prefix, sel_mask;
@@ -89,6 +89,7 @@ struct Ctx {
     int *htok;
     int4 *cand;                // {arc (packed lo), ordered cost (packed hi), slot | kAltFlag (-1 = dead; state before insertion), src}
     int *cand_next;            // destination state of a candidate
+    int *work;                 // epsilon-closure work list (candidate indices)
     int *rank;
     int *sv_pref, *sv_a0, *sv_src, *win_owner;
     float *sv_cost;
@@ -172,7 +173,7 @@ __device__ __forceinline__ int keep_flags(const Ctx<NT> &c, unsigned long long p
 
 // epsilon-closure insertion: appends a candidate record (src = index of the generating candidate)
 template <int NT>
-__device__ __forceinline__ void relax(Ctx<NT> &c, int state, unsigned long long pk, int src) {
+__device__ __forceinline__ void relax(Ctx<NT> &c, int state, unsigned long long pk, int src, bool has_eps) {
     unsigned long long old;
     const int slot = table_insert(c, state, pk, &old);
     if (slot < 0) return;
@@ -182,6 +183,7 @@ __device__ __forceinline__ void relax(Ctx<NT> &c, int state, unsigned long long 
     if (idx < c.a.cand_cap) {
         c.cand[idx] = make_int4((int)(unsigned)pk, (int)(unsigned)(pk >> 32), slot | fl, src);
         c.cand_next[idx] = state;
+        if (fl == 0 && has_eps) c.work[agg_inc(&c.sh.n_work)] = idx;  // at most one entry per candidate: never beyond cand_cap
     } else {
         c.sh.error = 2;
     }
@@ -301,16 +303,19 @@ __device__ float get_cutoff(Ctx<NT> &c, const float *cost, int n, float *adaptiv
     return beam_cutoff;
 }
 
-// epsilon closure over candidates [lo, hi) until no candidate is added; returns total candidate count.
-// Epsilon out-degrees are tiny (0-2), so one thread per candidate is balanced.  Only a candidate that currently is
-// its state's best word is expanded; if it is superseded later, the better one is expanded in a later round.
+// Epsilon closure to the fixed point; returns the total candidate count.  The work list holds the candidates that became
+// their state's best word AND whose state has epsilon arcs (a static property flagged in the arc records), so a round
+// costs what it expands, not a scan of all candidates.  Only an entry that still is its state's best word is expanded; if
+// it was superseded, the better candidate sits further down the list.  Epsilon out-degrees are tiny: thread per entry.
 template <int NT>
-__device__ int closure(Ctx<NT> &c, int lo, int hi, float cutoff, unsigned long long *arcs_seen) {
+__device__ int closure(Ctx<NT> &c, float cutoff, unsigned long long *arcs_seen) {
     const DecArgs &a = c.a;
+    int lo = 0, hi = min(c.sh.n_work, a.cand_cap);
+    __syncthreads();
     while (lo < hi) {
-        for (int i = lo + c.tid; i < hi; i += NT) {
+        for (int w = lo + c.tid; w < hi; w += NT) {
+            const int i = c.work[w];
             const int4 cd = c.cand[i];
-            if (cd.z < 0 || (cd.z & kAltFlag)) continue;
             const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
             const float cost = unord((unsigned)cd.y);
             if (cost < cutoff && tab_val(c, cd.z) == pk) {
@@ -320,16 +325,16 @@ __device__ int closure(Ctx<NT> &c, int lo, int hi, float cutoff, unsigned long l
                 for (int arc = a0; arc < a1; arc++) {
                     const int4 av = __ldg(a.g.arcs + arc);
                     const float tot = cost + __int_as_float(av.x);
-                    if (tot < cutoff) relax(c, av.y, pack(tot, arc), i);
+                    if (tot < cutoff) relax(c, av.y, pack(tot, arc), i, (av.w & kNextHasEps) != 0);
                 }
             }
         }
         __syncthreads();
         lo = hi;
-        hi = min(c.sh.n_cand, a.cand_cap);
+        hi = min(c.sh.n_work, a.cand_cap);
         __syncthreads();
     }
-    return hi;
+    return min(c.sh.n_cand, a.cand_cap);
 }
 
 // turn the winning candidates into the next frame's token list, log the lattice links, clear both table levels.
@@ -430,7 +435,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
     }
     Ctx<NT> c{a, sh, s_ll, s_key, s_val,
           a.hash_key + g * a.hash_size, a.hash_val + g * a.hash_size, a.hash_tok + g * a.hash_size,
-          a.cand + g * a.cand_cap, a.cand_next + g * a.cand_cap,
+          a.cand + g * a.cand_cap, a.cand_next + g * a.cand_cap, a.eps_work + g * a.cand_cap,
           a.rank + g * a.tok_cap,
           a.sv_pref + g * a.tok_cap, a.sv_a0 + g * a.tok_cap, a.sv_src + g * a.tok_cap, a.win_owner + g * nwin_cap,
           a.sv_cost + g * a.tok_cap,
@@ -474,14 +479,15 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 sh.n_cand = 0;
                 sh.n_next = 0;
                 sh.n_links = 0;
+                sh.n_work = 0;
                 if (link_off) link_off[0] = 0;
             }
             c.hmask = (unsigned)a.hash_size - 1;
             c.use_l1 = true;
             __syncthreads();
-            if (tid == 0) relax(c, a.g.start, pack(0.f, -1), -1);
+            if (tid == 0) relax(c, a.g.start, pack(0.f, -1), -1, true);
             __syncthreads();
-            int nc = closure(c, 0, min(sh.n_cand, a.cand_cap), a.beam, &cnt_arc_eps);
+            int nc = closure(c, a.beam, &cnt_arc_eps);
             finalize_tokens(c, 1, nc, INFINITY, 0.f, links, 0, a.tok_state + tbase, a.tok_cost + tbase, a.tok_arc + tbase, a.tok_prev + tbase);
             n_cur = min(sh.n_next, a.tok_cap);
             link_count = a.lattice ? min(sh.n_links, a.link_cap) : 0;
@@ -537,6 +543,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                         sh.n_cand = 0;
                         sh.n_next = 0;
                         sh.n_links = 0;
+                        sh.n_work = 0;
                     }
                 }
             } else if (tid == 0) {
@@ -544,6 +551,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 sh.n_cand = 0;
                 sh.n_next = 0;
                 sh.n_links = 0;
+                sh.n_work = 0;
             }
             VB_PHASE(0)
             // ---- pass A: per-warp counts of survivors, survivors with out-arcs, and out-arcs ----
@@ -741,11 +749,11 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                     const float cut = unord(*(volatile unsigned *)&sh.min_ord) + adaptive_beam;  // loose (>= final) cutoff
                     if (validA && totA < cut) {
                         const int idx = agg_inc(&sh.n_cand);
-                        if (idx < a.cand_cap) c.cand[idx] = make_int4(arcA, (int)ford(totA), avA.y, osrcA);
+                        if (idx < a.cand_cap) c.cand[idx] = make_int4(arcA, (int)ford(totA), avA.y | (avA.w & kNextHasEps), osrcA);
                     }
                     if (validB && totB < cut) {
                         const int idx = agg_inc(&sh.n_cand);
-                        if (idx < a.cand_cap) c.cand[idx] = make_int4(arcB, (int)ford(totB), avB.y, osrcB);
+                        if (idx < a.cand_cap) c.cand[idx] = make_int4(arcB, (int)ford(totB), avB.y | (avB.w & kNextHasEps), osrcB);
                     }
                     __syncwarp();
                 }
@@ -763,13 +771,15 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 int z = -1;
                 if (cost < next_cutoff) {
                     const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
+                    const int state = cd.z & ~kNextHasEps;
                     unsigned long long old;
-                    const int slot = table_insert(c, cd.z, pk, &old);
+                    const int slot = table_insert(c, state, pk, &old);
                     if (slot >= 0) {
                         const int fl = keep_flags(c, pk, old, cost);
                         if (fl >= 0) {
                             z = slot | fl;
-                            c.cand_next[i] = cd.z;
+                            c.cand_next[i] = state;
+                            if (fl == 0 && (cd.z & kNextHasEps)) c.work[agg_inc(&sh.n_work)] = i;
                         }
                     }
                 }
@@ -777,7 +787,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             }
             __syncthreads();
             VB_PHASE(4)
-            const int nc = closure(c, 0, n_emit, next_cutoff, &cnt_arc_eps);
+            const int nc = closure(c, next_cutoff, &cnt_arc_eps);
             VB_PHASE(5)
             finalize_tokens(c, n_emit, nc, next_cutoff, cost_offset, links, link_count, n_state, n_cost, n_arc, n_prev);
             VB_PHASE(6)
@@ -1081,7 +1091,7 @@ __global__ void __launch_bounds__(32) partial_kernel(DecArgs a) {
         for (int guard = 0; guard < a.tok_cap; guard++) {  // epsilon predecessors live in the same token list
             const int arc = t_arc[i];
             if (arc < 0) break;
-            const int ol = __ldg(a.g.arcs + arc).w;
+            const int ol = __ldg(a.g.arcs + arc).w & ~kNextHasEps;
             if (ol != 0) {
                 if (n < kPartialCap) out[n] = ol;
                 n++;
@@ -1097,7 +1107,7 @@ __global__ void __launch_bounds__(32) partial_kernel(DecArgs a) {
         while (li >= 0) {
             const int arc = log_arc[li];
             if (arc < 0) break;
-            const int ol = __ldg(a.g.arcs + arc).w;
+            const int ol = __ldg(a.g.arcs + arc).w & ~kNextHasEps;
             if (ol != 0) {
                 if (n < kPartialCap) out[n] = ol;
                 n++;

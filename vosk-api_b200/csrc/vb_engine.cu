@@ -297,7 +297,10 @@ void Engine::upload_model() {
         for (int a = 0; a < g.num_arcs; a++) {
             int wbits;
             memcpy(&wbits, &g.arc_w[a], 4);
-            arcs[a] = make_int4(wbits, g.arc_next[a], g.arc_pdf[a], g.arc_olabel[a]);
+            const int nx = g.arc_next[a];
+            const bool next_has_eps = g.eps_begin[nx] < g.e_begin[nx + 1];
+            if (g.arc_olabel[a] >= kNextHasEps || nx >= kNextHasEps) throw std::runtime_error("graph too large for the packed arc record");
+            arcs[a] = make_int4(wbits, nx, g.arc_pdf[a], g.arc_olabel[a] | (next_has_eps ? kNextHasEps : 0));
         }
         std::vector<int2> sa((size_t)g.num_states + 1);
         for (int s2 = 0; s2 < g.num_states; s2++) sa[s2] = make_int2(g.e_begin[s2], g.eps_begin[s2]);
@@ -373,6 +376,7 @@ void Engine::alloc_state() {
         d.hash_tok = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0);
         d.cand = dev_alloc<int4>(allocs_, G * cfg_.cand_cap);
         d.cand_next = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
+        d.eps_work = dev_alloc<int>(allocs_, G * cfg_.cand_cap);
         d.rank = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
         d.sv_pref = dev_alloc<int>(allocs_, G * cfg_.tok_cap);
         d.sv_a0 = dev_alloc<int>(allocs_, G * cfg_.tok_cap);

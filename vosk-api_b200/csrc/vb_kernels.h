@@ -99,7 +99,7 @@ struct GraphDev {
     const float *final_cost;
     const int *e_begin;      // [S+1]
     const int *eps_begin;    // [S]
-    const int4 *arcs;        // {weight bits, nextstate, pdf, olabel}
+    const int4 *arcs;        // {weight bits, nextstate, pdf, olabel | kNextHasEps if the next state has epsilon arcs}
     const int2 *state_arcs;  // [S+1] {first emitting arc, first epsilon arc}; epsilon arcs of s end at state_arcs[s+1].x
 };
 struct DecChannelState {     // one per channel
@@ -114,6 +114,7 @@ struct LatHeader {
     int error, frames, pad0, pad1;
 };
 constexpr int kPartialCap = 256;
+constexpr int kNextHasEps = 0x40000000;  // flag in the olabel field of a device arc record (labels and state ids stay below 2^30)
 constexpr int kEpsLinkFlag = 0x40000000;  // set in the destination field of an epsilon link
 struct DecArgs {
     const LaneDesc *lanes;
@@ -155,6 +156,8 @@ struct DecArgs {
     int link_cap;
     float *frame_offset;     // [C][max_frames+2] cost offset (-best token cost) of every frame: taken back out of the lattice arcs
     int *cand_next;          // [G][cand_cap] destination state of a candidate
+    int *eps_work;           // [G][cand_cap] work list of the epsilon closure: candidates that became a state's best word and whose
+                             // state has epsilon arcs
     unsigned *lat_extra;     // [C][log_cap] extra-cost scratch of the lattice pruning, or null: the pruning then
                              // reuses log_prev (whose content is dead once the best path has been traced)
     // per slot: outputs of the pruning for the lanes that finished in this step (index = lane)
