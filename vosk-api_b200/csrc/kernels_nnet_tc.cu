@@ -32,8 +32,9 @@ namespace vb {
 namespace {
 constexpr int TM = 128;       // tile rows (UMMA_M)
 constexpr int TK = 32;        // fp32 elements per K-block = one 128-byte swizzle row
-constexpr int kTcThreads = 192;
-constexpr int kProducerThreads = 128;
+constexpr int kTcThreads = 320;        // 8 producer warps (the first 4 are also the epilogue), 1 TMA warp, 1 MMA warp
+constexpr int kProducerThreads = 256;
+constexpr int kTmaWarp = kProducerThreads / 32, kMmaWarp = kTmaWarp + 1;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -76,6 +77,7 @@ struct TcSmem {
     uint64_t full[4], empty[4], accum;
     uint32_t tmem_base;
     int row_ch[TM], row_t[TM];
+    float bias[256], bn_scale[256], bn_offset[256];  // the tile's columns of the epilogue constants (BN <= 256)
 };
 }  // namespace
 
@@ -113,7 +115,14 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
         ts.row_ch[tid] = ch;
         ts.row_t[tid] = t;
     }
-    if (tid == 128) {
+    for (int j = tid; j < BN; j += kTcThreads) {
+        const int n = n0 + j;
+        const bool in_n = n < op.N;
+        ts.bias[j] = op.bias && in_n ? __ldg(op.bias + n) : 0.f;
+        ts.bn_scale[j] = op.has_bn && in_n ? __ldg(op.bn_scale + n) : 1.f;
+        ts.bn_offset[j] = op.has_bn && in_n ? __ldg(op.bn_offset + n) : 0.f;
+    }
+    if (tid == kProducerThreads) {
         for (int s = 0; s < stages; s++) {
             mbar_init(&ts.full[s], kProducerThreads + 1);
             mbar_init(&ts.empty[s], 1);
@@ -121,7 +130,7 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
         mbar_init(&ts.accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ts.tmem_base)), "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -130,21 +139,22 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = ts.tmem_base;
 
-    if (warp < 4) {
+    if (warp < kTmaWarp) {
         // =========================== A producers ===========================
-        // Thread (c, rsub) owns 16-byte chunk c of rows rsub, rsub+16, ... of the tile.  Row slots are resolved once;
-        // per K-block all 8 gathers are issued back to back into registers (8 independent L2 requests in flight per
-        // thread) and only then split and stored, so the loop is bandwidth- rather than latency-paced.
+        // Thread (c, rsub) owns 16-byte chunk c of rows rsub, rsub+32, ... of the tile.  Row slots are resolved once; the
+        // gathers of a K-block are issued back to back into registers and three K-blocks are kept in flight per thread
+        // (48 KB of independent L2 requests per SM), so the loop is bandwidth- rather than latency-paced.
         const int in_dim = a.in.dim, spliced = op.n_off * in_dim;
         const int c = tid & 7;          // 16-byte chunk within the 128-byte row
-        const int rsub = tid >> 3;      // 0..15: row within a group of 16
-        constexpr int RPT = TM / 16;    // rows per thread
+        const int rsub = tid >> 3;      // 0..31: row within a group of 32
+        constexpr int RG = kProducerThreads / 8;  // rows per group
+        constexpr int RPT = TM / RG;    // rows per thread
         const float *row_base[RPT];     // ring base of the row's channel (nullptr = padding row)
         const float *iv_base[RPT];
         int row_slot[RPT];              // (t - t_start) / step of the row in the input ring
 #pragma unroll
         for (int it = 0; it < RPT; it++) {
-            const int r = it * 16 + rsub;
+            const int r = it * RG + rsub;
             const int ch = ts.row_ch[r];
             row_base[it] = ch >= 0 ? a.in.buf + (size_t)ch * a.in.ring * in_dim : nullptr;
             iv_base[it] = ch >= 0 ? a.ivec + (size_t)ch * a.ivec_dim : nullptr;
@@ -171,17 +181,18 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
                 }
             }
         };
-        float4 v[RPT], vn[RPT];
+        float4 v[RPT], vn[RPT], vnn[RPT];
         gather(0, v);
+        if (nkb > 1) gather(1, vn);
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % stages;
             const uint32_t par = (uint32_t)((kb / stages) & 1);
-            if (kb + 1 < nkb) gather(kb + 1, vn);  // software pipelining: the next block's loads fly while this one is split and stored
+            if (kb + 2 < nkb) gather(kb + 2, vnn);  // software pipelining: two more blocks' loads fly while this one is split and stored
             mbar_wait(&ts.empty[s], par ^ 1);
             const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + TM * 128;
 #pragma unroll
             for (int it = 0; it < RPT; it++) {
-                const int r = it * 16 + rsub;
+                const int r = it * RG + rsub;
                 float4 h, l;
                 h.x = __uint_as_float(__float_as_uint(v[it].x) & 0xffffe000u);
                 h.y = __uint_as_float(__float_as_uint(v[it].y) & 0xffffe000u);
@@ -195,8 +206,12 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA (async proxy)
             mbar_arrive(&ts.full[s]);
 #pragma unroll
-            for (int it = 0; it < RPT; it++) v[it] = vn[it];
+            for (int it = 0; it < RPT; it++) {
+                v[it] = vn[it];
+                vn[it] = vnn[it];
+            }
         }
+      if (warp < 4) {  // (a warp reads the 32 TMEM lanes of its quarter: the first four producer warps)
         // =========================== epilogue ===========================
         mbar_wait(&ts.accum, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -210,32 +225,52 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
         }
         const uint32_t taddr_row = tmem + ((uint32_t)(warp * 32) << 16);
         for (int cb = 0; cb < BN; cb += 16) {
+            // the bypass row segment (4 independent 16-byte loads) is requested first, so it arrives under the TMEM loads
+            const int n = n0 + cb;
+            float4 byp[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) byp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (brow && n < op.N) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) byp[j] = *reinterpret_cast<const float4 *>(brow + n + 4 * j);
+            }
+            // all partial accumulators of this 16-column chunk are requested before the single wait (the loads pipeline);
+            // they are summed in fp32 round-to-nearest in a fixed order
+            const int nsteps = (nkb * (TK / 8));
+            uint32_t v[5][16];
+#pragma unroll
+            for (int q = 0; q < 5; q++) {
+                const bool live = q <= n_main && !(q < n_main && q >= nsteps);  // (an accumulator K never reached stays out)
+                if (live) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(v[q][0]), "=r"(v[q][1]), "=r"(v[q][2]), "=r"(v[q][3]), "=r"(v[q][4]), "=r"(v[q][5]), "=r"(v[q][6]), "=r"(v[q][7]),
+                          "=r"(v[q][8]), "=r"(v[q][9]), "=r"(v[q][10]), "=r"(v[q][11]), "=r"(v[q][12]), "=r"(v[q][13]), "=r"(v[q][14]), "=r"(v[q][15])
+                        : "r"(taddr_row + (uint32_t)(q * BN + cb)));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) v[q][j] = 0u;
+                }
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             float acc[16];
 #pragma unroll
-            for (int j = 0; j < 16; j++) acc[j] = 0.f;
-            const int nsteps = (nkb * (TK / 8));
-            for (int q = 0; q <= n_main; q++) {
-                if (q < n_main && q >= nsteps) continue;  // accumulator never written (K shorter than n_main k-steps)
-                uint32_t v[16];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(taddr_row + (uint32_t)(q * BN + cb)));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int j = 0; j < 16; j++) {
+                float x = 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; j++) acc[j] += __uint_as_float(v[j]);  // fp32 round-to-nearest sum of the partial accumulators
+                for (int q = 0; q < 5; q++) x += __uint_as_float(v[q][j]);
+                acc[j] = x;
             }
-            const int n = n0 + cb;
             if (orow && n < op.N) {
                 float z[16];
+                const float *bv = reinterpret_cast<const float *>(byp);
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     float x = acc[j];
-                    if (op.bias) x += __ldg(op.bias + n + j);
+                    if (op.bias) x += ts.bias[cb + j];
                     if (op.relu) x = fmaxf(x, 0.f);
-                    if (op.has_bn) x = fmaf(x, __ldg(op.bn_scale + n + j), __ldg(op.bn_offset + n + j));
-                    if (brow) x = fmaf(op.bypass_scale, brow[n + j], x);
+                    if (op.has_bn) x = fmaf(x, ts.bn_scale[cb + j], ts.bn_offset[cb + j]);
+                    if (brow) x = fmaf(op.bypass_scale, bv[j], x);
                     z[j] = x;
                 }
 #pragma unroll
@@ -243,7 +278,8 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    } else if (warp == 4) {
+      }
+    } else if (warp == kTmaWarp) {
         // =========================== TMA: weight boxes ===========================
         if (lane == 0) {
             for (int kb = 0; kb < nkb; kb++) {
@@ -311,7 +347,7 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
         }
     }
     __syncthreads();
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
     }
