@@ -43,6 +43,11 @@ __global__ void __launch_bounds__(1024) nnet_plan_kernel(NnetPlanArgs a) {
     }
     if (l < a.num_lanes) a.rowoff[(size_t)n * (a.max_lanes + 1) + l + 1] = s_scan[l];
     if (l == 0) a.rowoff[(size_t)n * (a.max_lanes + 1)] = 0;
+    if (l < a.num_lanes && a.rows) {
+        const int ch = a.lanes[l].channel, base = s_scan[l] - rows;
+        int2 *dst = a.rows + (size_t)n * a.rows_cap;
+        for (int i = 0; i < rows && base + i < a.rows_cap; i++) dst[base + i] = make_int2(ch, t0 + i * nd.step);
+    }
 }
 
 extern "C" cudaError_t vbk_nnet_plan(const NnetPlanArgs *a, cudaStream_t s) {

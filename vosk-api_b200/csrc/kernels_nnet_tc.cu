@@ -104,13 +104,9 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
     if (tid < TM) {
         int r = row0 + tid, ch = -1, t = 0;
         if (r < total) {
-            int lo = 0, hi = a.num_lanes;
-            while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (a.rowoff[mid] <= r) lo = mid; else hi = mid;
-            }
-            ch = a.lanes[lo].channel;
-            t = a.table[lo].t_begin + (r - a.rowoff[lo]) * a.out.step;
+            const int2 rc = a.rows[r];  // written by the plan kernel
+            ch = rc.x;
+            t = rc.y;
         }
         ts.row_ch[tid] = ch;
         ts.row_t[tid] = t;

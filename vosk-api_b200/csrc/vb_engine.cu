@@ -409,6 +409,8 @@ void Engine::alloc_state() {
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lanes, (size_t)L * sizeof(LaneDesc)));
         sl.d_table = dev_alloc<NodeLane>(allocs_, (size_t)nn * L, 0);
         sl.d_rowoff = dev_alloc<int>(allocs_, (size_t)nn * (L + 1), 0);
+        rows_cap_ = L * (max_in_rows_ + 8);
+        sl.d_rows = dev_alloc<int2>(allocs_, (size_t)nn * rows_cap_, 0);
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_cs, (size_t)L * sizeof(DecChannelState)));
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_path, (size_t)L * path_cap_ * sizeof(int)));
         sl.d_load = dev_alloc<int>(allocs_, (size_t)L, 0);
@@ -704,7 +706,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     VB_CUDA_CHECK(vbk_ivector(&ia, st));
     sl.launches++;
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[2], st));
-    NnetPlanArgs pa{sl.d_lanes, L, nn, d_nodes_, d_node_end_, sl.d_table, sl.d_rowoff, SL};
+    NnetPlanArgs pa{sl.d_lanes, L, nn, d_nodes_, d_node_end_, sl.d_table, sl.d_rowoff, SL, sl.d_rows, rows_cap_};
     VB_CUDA_CHECK(vbk_nnet_plan(&pa, st));
     sl.launches++;
     for (size_t o = 0; o < ops_.size(); o++) {
@@ -718,6 +720,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         ga.num_lanes = L;
         ga.table = sl.d_table + (size_t)op.out_node * SL;
         ga.rowoff = sl.d_rowoff + (size_t)op.out_node * (SL + 1);
+        ga.rows = sl.d_rows + (size_t)op.out_node * rows_cap_;
         ga.ivec = iv_state_.ivec;
         ga.ivec_dim = model_.ivec_dim;
         ga.max_rows = (int)(ga.out.step == 1 ? in_rows : in_rows / kSubsample + 2 * L);

@@ -146,6 +146,7 @@ class Engine {
         LaneDesc *d_lanes = nullptr, *h_lanes = nullptr;
         NodeLane *d_table = nullptr;
         int *d_rowoff = nullptr;
+        int2 *d_rows = nullptr;  // [nodes][rows_cap_] packed row table of the step
         DecArgs dec{};
         DecChannelState *h_cs = nullptr;
         int *h_path = nullptr;
@@ -192,7 +193,7 @@ class Engine {
     DecArgs dec_{};  // template: graph, options and per-channel arrays; each slot adds its own scratch
     float *d_capture_ = nullptr, *h_capture_ = nullptr;
     size_t capture_floats_ = 0;
-    int max_in_rows_ = 0, log_cap_ = 0, max_frames_ = 0, path_cap_ = 0, slot_lanes_ = 0, link_cap_ = 0;
+    int max_in_rows_ = 0, log_cap_ = 0, max_frames_ = 0, path_cap_ = 0, slot_lanes_ = 0, link_cap_ = 0, rows_cap_ = 0;
     std::vector<int> free_channels_;
     // batching
     std::mutex mu_;

@@ -78,6 +78,8 @@ struct NnetPlanArgs {
     NodeLane *table;         // [num_nodes][max_lanes]
     int *rowoff;             // [num_nodes][max_lanes+1]
     int max_lanes;
+    int2 *rows;              // [num_nodes][rows_cap] {channel, time} of every packed row (saves the GEMM tiles a search)
+    int rows_cap;
 };
 struct GemmArgs {
     OpDesc op;
@@ -86,6 +88,7 @@ struct GemmArgs {
     int num_lanes;
     const NodeLane *table;   // out node's table [max_lanes]
     const int *rowoff;       // out node's prefix [max_lanes+1]
+    const int2 *rows;        // out node's packed rows {channel, time}
     const float *ivec;       // [C][ivec_dim]
     int ivec_dim;
     int max_rows;            // upper bound of total rows (grid sizing)

@@ -49,6 +49,11 @@ extern "C" int vosk_b200_gemm_selftest(int M, int N, int K, int bits, double *ou
     cudaMemcpy(dL, &ln, sizeof ln, cudaMemcpyHostToDevice);
     cudaMemcpy(dT, &nl, sizeof nl, cudaMemcpyHostToDevice);
     cudaMemcpy(dR, rowoff, sizeof rowoff, cudaMemcpyHostToDevice);
+    std::vector<int2> rows(M);
+    for (int m = 0; m < M; m++) rows[m] = make_int2(0, m);
+    int2 *dRows;
+    cudaMalloc(&dRows, (size_t)M * sizeof(int2));
+    cudaMemcpy(dRows, rows.data(), (size_t)M * sizeof(int2), cudaMemcpyHostToDevice);
     alignas(64) unsigned char mh[128], ml[128];
     if (vbk_make_weight_map(dHi, N, K, mh) != cudaSuccess || vbk_make_weight_map(dLo, N, K, ml) != cudaSuccess) return -1;
     GemmArgs g{};
@@ -57,7 +62,7 @@ extern "C" int vosk_b200_gemm_selftest(int M, int N, int K, int bits, double *ou
     g.in = NodeDesc{K, 1, ring, 0, 0, dA};
     g.out = NodeDesc{N, 1, ring, 0, 0, dC0};
     g.byp = g.in;
-    g.lanes = dL; g.num_lanes = 1; g.table = dT; g.rowoff = dR; g.ivec = dA; g.ivec_dim = 4; g.max_rows = M;
+    g.lanes = dL; g.num_lanes = 1; g.table = dT; g.rowoff = dR; g.rows = dRows; g.ivec = dA; g.ivec_dim = 4; g.max_rows = M;
     g.map_hi = mh; g.map_lo = ml;
     if (vbk_gemm_fp32(&g, 0) != cudaSuccess) return -2;
     g.out.buf = dC1;
@@ -78,6 +83,6 @@ extern "C" int vosk_b200_gemm_selftest(int M, int N, int K, int bits, double *ou
             sr += r * r;
         }
     out[0] = e0; out[1] = e1; out[2] = std::sqrt(s1 / ((double)M * N)); out[3] = std::sqrt(sr / ((double)M * N));
-    cudaFree(dA); cudaFree(dW); cudaFree(dHi); cudaFree(dLo); cudaFree(dC0); cudaFree(dC1); cudaFree(dL); cudaFree(dT); cudaFree(dR);
+    cudaFree(dA); cudaFree(dW); cudaFree(dHi); cudaFree(dLo); cudaFree(dC0); cudaFree(dC1); cudaFree(dL); cudaFree(dT); cudaFree(dR); cudaFree(dRows);
     return 0;
 }
