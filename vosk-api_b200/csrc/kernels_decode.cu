@@ -1071,7 +1071,7 @@ extern "C" cudaError_t vbk_lattice_prune(const DecArgs *a, cudaStream_t s) {
 // the walk is a dependent chain, so it runs off the search kernel's critical path in its own small launch.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) partial_kernel(DecArgs a) {
-    const int l = blockIdx.x, lane = threadIdx.x;
+    const int l = a.lane_begin + blockIdx.x, lane = threadIdx.x;
     const LaneDesc ln = a.lanes[l];
     if (ln.dec_last) return;
     const int ch = ln.channel;
@@ -1119,8 +1119,8 @@ __global__ void __launch_bounds__(32) partial_kernel(DecArgs a) {
 }
 
 extern "C" cudaError_t vbk_partial(const DecArgs *a, cudaStream_t s) {
-    if (!a->partial_words || a->num_lanes <= 0) return cudaSuccess;
-    partial_kernel<<<a->num_lanes, 32, 0, s>>>(*a);
+    if (!a->partial_words || a->lane_end <= a->lane_begin) return cudaSuccess;
+    partial_kernel<<<a->lane_end - a->lane_begin, 32, 0, s>>>(*a);
     return cudaGetLastError();
 }
 

@@ -129,6 +129,7 @@ Engine::~Engine() {
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.fork) cudaEventDestroy(sl.fork);
         for (auto &j : sl.join) if (j) cudaEventDestroy(j);
+        for (auto &j : sl.tier_done) if (j) cudaEventDestroy(j);
         if (sl.fe_done) cudaEventDestroy(sl.fe_done);
         if (sl.dec_done) cudaEventDestroy(sl.dec_done);
         if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -368,7 +369,14 @@ void Engine::alloc_state() {
         d.lat_tok_cap = cfg_.lat_tok_cap;
         d.lat_final_cap = cfg_.tok_cap;
     }
-    d.grid = L;  // scratch for one CTA per lane: the tiers' launches together never have more CTAs than lanes
+    {   // fixed scratch partition per tier (tiers of different steps overlap in time): as many CTAs as the tier can have resident
+        const int sms = vbk_decode_max_grid(cfg_.device) / 3;
+        auto cap = [&](int threads) { return sms * (threads >= 1024 ? 1 : threads >= 512 ? 2 : 3); };
+        tier_scratch_[0] = 0;
+        tier_scratch_[1] = cap(cfg_.heavy_threads);
+        tier_scratch_[2] = tier_scratch_[1] + cap(cfg_.mid_threads);
+        d.grid = tier_scratch_[2] + cap(cfg_.light_threads);
+    }
     {   // search scratch, one copy: the searches of all steps run in order on dec_stream_
         const size_t G = (size_t)d.grid;
         d.hash_key = dev_alloc<int>(allocs_, G * cfg_.hash_size, 0xff);
@@ -402,6 +410,7 @@ void Engine::alloc_state() {
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.dec_done, cudaEventDisableTiming));
         VB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.fork, cudaEventDisableTiming));
         for (auto &j : sl.join) VB_CUDA_CHECK(cudaEventCreateWithFlags(&j, cudaEventDisableTiming));
+        for (auto &j : sl.tier_done) VB_CUDA_CHECK(cudaEventCreateWithFlags(&j, cudaEventDisableTiming));
         sl.d_queue = dev_alloc<int>(allocs_, 4, 0);
         sl.d_staging = dev_alloc<int16_t>(allocs_, (size_t)L * spc, 0);
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_staging, (size_t)L * spc * sizeof(int16_t)));
@@ -731,54 +740,66 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         sl.gemms++;
     }
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[3], st));
+    VB_CUDA_CHECK(cudaMemsetAsync(sl.d_queue, 0, 4 * sizeof(int), st));
     VB_CUDA_CHECK(cudaEventRecord(sl.fe_done, st));
-    // ---- search pipe ----
-    st = dec_stream_;
-    VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.fe_done, 0));
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[5], st));
+    // ---- search: three in-order tier pipes ----
+    // Lanes are split by the token load of their previous step (they are sorted by it) into 1024-, 512- and 256-thread CTA
+    // tiers.  Each tier is an in-order pipe of its own across steps (own stream, own scratch range, own lane queue), so the
+    // light lanes of step s+1 start as soon as their front end and their own previous search are done, while the few heavy
+    // lanes of step s — the critical path of a full-width step — are still running.  A lane that changes tier waits for
+    // the pipe it comes from.
     sl.dec.lanes = sl.d_lanes;
     sl.dec.num_lanes = L;
-    // three tiers by the token load of the lane's previous step (lanes are sorted by it): 1024-, 512- and 256-thread CTAs.
-    // Each tier is one launch with its own lane queue and scratch range; the launches run side by side.
+    sl.dec.queue = sl.d_queue;
     int n_heavy = 0, n_mid = 0;
     while (n_heavy < L && lanes[n_heavy].s->load > cfg_.heavy_tokens) n_heavy++;
     n_mid = n_heavy;
     while (n_mid < L && lanes[n_mid].s->load > cfg_.mid_tokens) n_mid++;
-    VB_CUDA_CHECK(cudaMemsetAsync(sl.d_queue, 0, 4 * sizeof(int), st));
     const int tier_begin[3] = {0, n_heavy, n_mid}, tier_end[3] = {n_heavy, n_mid, L};
     const int tier_threads[3] = {cfg_.heavy_threads, cfg_.mid_threads, cfg_.light_threads};
-    cudaStream_t tier_stream[3] = {st, dec_stream2_, dec_stream3_};
-    int n_tiers = 0, scratch = 0;
-    for (int t = 0; t < 3; t++) n_tiers += tier_end[t] > tier_begin[t];
-    if (n_tiers > 1) VB_CUDA_CHECK(cudaEventRecord(sl.fork, st));
-    bool first = true;
+    cudaStream_t tier_stream[3] = {dec_stream_, dec_stream2_, dec_stream3_};
+    int n_last = 0;
+    for (int i = 0; i < L; i++) n_last += lanes[i].seg_end ? 1 : 0;
+    bool tier_used[3] = {false, false, false};
+    // all waits are issued before any of this step's tier events is (re-)recorded: with few slots the event a lane has to
+    // wait for can be the very event object this step records next
     for (int t = 0; t < 3; t++) {
-        const int n = tier_end[t] - tier_begin[t];
-        if (n <= 0) continue;
-        cudaStream_t ts = first ? st : tier_stream[t];
-        if (!first) VB_CUDA_CHECK(cudaStreamWaitEvent(ts, sl.fork, 0));
+        if (tier_end[t] <= tier_begin[t]) continue;
+        tier_used[t] = true;
+        cudaStream_t ts = tier_stream[t];
+        VB_CUDA_CHECK(cudaStreamWaitEvent(ts, sl.fe_done, 0));
+        bool from[3] = {false, false, false};
+        for (int i = tier_begin[t]; i < tier_end[t]; i++) {
+            Stream &s = *lanes[i].s;
+            if (s.last_tier >= 0 && s.last_tier != t) from[s.last_tier] = true;
+            s.last_tier = t;
+        }
+        for (int u = 0; u < 3; u++)
+            if (from[u] && last_tier_done_[u]) VB_CUDA_CHECK(cudaStreamWaitEvent(ts, last_tier_done_[u], 0));
+    }
+    for (int t = 0; t < 3; t++) {
+        if (!tier_used[t]) continue;
+        cudaStream_t ts = tier_stream[t];
         DecArgs da = sl.dec;
         da.queue = sl.d_queue + t;
         da.lane_begin = tier_begin[t];
         da.lane_end = tier_end[t];
-        da.scratch_base = scratch;
-        scratch += n;  // a launch never has more CTAs than lanes
+        da.scratch_base = tier_scratch_[t];
         VB_CUDA_CHECK(vbk_decode(&da, tier_threads[t], ts));
         sl.launches++;
-        if (!first) {
-            VB_CUDA_CHECK(cudaEventRecord(sl.join[t - 1], ts));
-            VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.join[t - 1], 0));
+        if (cfg_.partials) {  // the partial walk reads the lane's tokens: it must precede the lane's next search, so it rides the tier pipe
+            VB_CUDA_CHECK(vbk_partial(&da, ts));
+            sl.launches++;
         }
-        first = false;
+        VB_CUDA_CHECK(cudaEventRecord(sl.tier_done[t], ts));
+        last_tier_done_[t] = sl.tier_done[t];
     }
-    sl.dec.queue = sl.d_queue;
-    int n_last = 0;
-    for (int i = 0; i < L; i++) n_last += lanes[i].seg_end ? 1 : 0;
+    // ---- finish: results of the step, after all its tiers ----
+    st = post_stream_;
+    for (int t = 0; t < 3; t++)
+        if (tier_used[t]) VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.tier_done[t], 0));
     if (cfg_.partials && n_last < L) {
-        sl.dec.lane_begin = 0;
-        sl.dec.lane_end = L;
-        VB_CUDA_CHECK(vbk_partial(&sl.dec, st));
-        sl.launches++;
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_partial, sl.dec.partial_words, (size_t)L * kPartialCap * sizeof(int), cudaMemcpyDeviceToHost, st));
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_partial + (size_t)L * kPartialCap, sl.dec.partial_count, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
@@ -795,11 +816,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         }
     VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_load, sl.d_load, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (cfg_.lattice && n_last > 0) {
-        // lattice pruning only touches finished channels (nothing else does until they are reused after completion), so
-        // it leaves the search pipe and runs beside the next steps on its own stream
-        VB_CUDA_CHECK(cudaEventRecord(sl.dec_done, st));
-        st = post_stream_;
-        VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.dec_done, 0));
+        // lattice pruning only touches finished channels (nothing else does until they are reused after completion)
         sl.dec.lane_begin = 0;
         sl.dec.lane_end = L;
         static const bool twice = getenv("VB_PRUNE_TWICE") != nullptr;  // determinism probe: same inputs, two launches

@@ -66,6 +66,7 @@ struct Stream {
     int seg_start = 0;       // decoder frames before the current segment
     int seg_index = 0;       // segments closed so far
     bool seg_open = false;   // the search of the current segment has been initialised
+    int last_tier = -1;      // search tier (pipe) that ran the stream's previous chunk
     bool resident = false;   // samples are read from a device-resident matrix (row = id)
     struct Chunk {
         std::vector<int16_t> samples;
@@ -138,7 +139,7 @@ class Engine {
     // the log-likelihood rings.
     struct Slot {
         cudaStream_t stream = nullptr;  // utility stream (debug taps, lattice fetch) of the slot
-        cudaEvent_t fe_done = nullptr, dec_done = nullptr, fork = nullptr, join[2] = {};
+        cudaEvent_t fe_done = nullptr, dec_done = nullptr, fork = nullptr, join[2] = {}, tier_done[3] = {};
         int *d_queue = nullptr;  // [2] lane queues of the two search launches
         cudaEvent_t ev[6] = {};
         cudaEvent_t done = nullptr;
@@ -193,6 +194,8 @@ class Engine {
     DecArgs dec_{};  // template: graph, options and per-channel arrays; each slot adds its own scratch
     float *d_capture_ = nullptr, *h_capture_ = nullptr;
     size_t capture_floats_ = 0;
+    int tier_scratch_[3] = {0, 0, 0};            // first scratch index of each search tier
+    cudaEvent_t last_tier_done_[3] = {};         // most recent completion event recorded on each tier pipe
     int max_in_rows_ = 0, log_cap_ = 0, max_frames_ = 0, path_cap_ = 0, slot_lanes_ = 0, link_cap_ = 0, rows_cap_ = 0;
     std::vector<int> free_channels_;
     // batching
