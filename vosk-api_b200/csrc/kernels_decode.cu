@@ -39,8 +39,14 @@
 namespace vb {
 
 namespace {
-constexpr int kDecBlocksPerSM = 3;   // 256-thread variant; the 1024-thread variant (heavy lanes) runs 1 per SM
-constexpr int kSmemSlots = 4096;  // level-1 (shared memory) table entries per CTA
+#ifndef VB_DEC_LIGHT_PER_SM
+#define VB_DEC_LIGHT_PER_SM 3
+#endif
+#ifndef VB_DEC_SMEM_SLOTS
+#define VB_DEC_SMEM_SLOTS 4096
+#endif
+constexpr int kDecBlocksPerSM = VB_DEC_LIGHT_PER_SM;   // 256-thread variant; the 1024-thread variant (heavy lanes) runs 1 per SM
+constexpr int kSmemSlots = VB_DEC_SMEM_SLOTS;  // level-1 (shared memory) table entries per CTA
 constexpr unsigned long long kValMax = ~0ull;
 constexpr int kEmpty = -1;
 constexpr int kAltFlag = 0x40000000;  // candidate did not improve its state's best word; kept as a lattice link only
@@ -405,16 +411,21 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
         for (int i = c.tid; i < n_cand; i += NT) {
             const int z = c.cand[i].z;
             const int slot = z & ~kAltFlag;
-            if (z >= 0 && slot >= kSmemSlots) {
+            if (z < 0) continue;
+            if (slot >= kSmemSlots) {
                 c.hkey[slot - kSmemSlots] = kEmpty;
                 c.hval[slot - kSmemSlots] = kValMax;
+            } else {  // level 1 is cleared slot by slot too: a full sweep per frame costs more than the frame's few entries
+                c.skey[slot] = kEmpty;
+                c.sval[slot] = kValMax;
             }
         }
     }
-    for (int i = c.tid; i < kSmemSlots; i += NT) {
-        c.skey[i] = kEmpty;
-        c.sval[i] = kValMax;
-    }
+    if (c.sh.error == 1 || c.sh.error == 2)
+        for (int i = c.tid; i < kSmemSlots; i += NT) {
+            c.skey[i] = kEmpty;
+            c.sval[i] = kValMax;
+        }
     __syncthreads();
 }
 }  // namespace
@@ -1123,6 +1134,8 @@ extern "C" cudaError_t vbk_partial(const DecArgs *a, cudaStream_t s) {
     partial_kernel<<<a->lane_end - a->lane_begin, 32, 0, s>>>(*a);
     return cudaGetLastError();
 }
+
+extern "C" int vbk_decode_blocks_per_sm(int threads) { return threads >= 1024 ? 1 : threads >= 512 ? 2 : kDecBlocksPerSM; }
 
 extern "C" int vbk_decode_max_grid(int device) {
     int sms = 0;

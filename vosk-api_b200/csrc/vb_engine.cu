@@ -370,8 +370,9 @@ void Engine::alloc_state() {
         d.lat_final_cap = cfg_.tok_cap;
     }
     {   // fixed scratch partition per tier (tiers of different steps overlap in time): as many CTAs as the tier can have resident
-        const int sms = vbk_decode_max_grid(cfg_.device) / 3;
-        auto cap = [&](int threads) { return sms * (threads >= 1024 ? 1 : threads >= 512 ? 2 : 3); };
+        int sms = 0;
+        VB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device));
+        auto cap = [&](int threads) { return sms * vbk_decode_blocks_per_sm(threads); };
         tier_scratch_[0] = 0;
         tier_scratch_[1] = cap(cfg_.heavy_threads);
         tier_scratch_[2] = tier_scratch_[1] + cap(cfg_.mid_threads);

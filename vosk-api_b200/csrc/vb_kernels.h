@@ -198,6 +198,7 @@ cudaError_t vbk_lattice_prune(const DecArgs *a, cudaStream_t s);
 // best path so far (no final costs) of every unfinished lane -> its output labels (GetBestPath(use_final_probs = false))
 cudaError_t vbk_partial(const DecArgs *a, cudaStream_t s);
 int vbk_decode_max_grid(int device);
+int vbk_decode_blocks_per_sm(int threads);  // resident search CTAs per SM of a tier's CTA size
 // copies rows [t_begin, t_begin+n) of a node ring for one channel into dst (debug capture / tests)
 cudaError_t vbk_copy_rows(NodeDesc node, int channel, int t_begin, int n_rows, float *dst, cudaStream_t s);
 cudaError_t vbk_split_tf32(const float *w, float *hi, float *lo, long long n, cudaStream_t s);
