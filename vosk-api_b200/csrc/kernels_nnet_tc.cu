@@ -374,10 +374,7 @@ static EncodeTiledFn encode_fn() {
 static int main_accs(int K) { return K >= 128 ? 4 : K >= 64 ? 2 : 1; }
 static int tile_n(int N, int K) {
     int limit = (512 / (main_accs(K) + 1)) & ~15;
-    if (N <= limit) return N;
-    for (int bn = limit; bn >= 64; bn -= 16)  // whole tiles only: the largest multiple of 16 that divides N
-        if (N % bn == 0) return bn;
-    return limit;
+    return N < limit ? N : limit;  // (a partial last tile is fine: TMA zero-fills beyond N and the epilogue guards its stores)
 }
 
 extern "C" cudaError_t vbk_make_weight_map(const float *w, int N, int K, void *out128) {
