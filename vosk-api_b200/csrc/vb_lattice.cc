@@ -174,6 +174,16 @@ class Determinizer {
             for (const RArc &a : in_.arcs[s]) f(a.dst);
         };
         std::vector<int> order = topo_order(n, in_.start, arcs_of);
+        topo_.assign(n, n);
+        for (size_t i = 0; i < order.size(); i++) topo_[order[i]] = (int)i;
+        stamp_.assign(n, 0);
+        slot_.assign(n, 0);
+        keepable_.assign(n, 0);
+        for (int s2 = 0; s2 < n; s2++) {
+            bool k = in_.final_cost[s2] != kInfF;
+            for (const RArc &a : in_.arcs[s2]) k = k || a.word != 0;
+            keepable_[s2] = k;
+        }
         for (auto it = order.rbegin(); it != order.rend(); ++it) {
             const int s = *it;
             double b = in_.final_cost[s] == kInfF ? kInfD : (double)in_.final_cost[s];
@@ -183,65 +193,69 @@ class Determinizer {
         }
     }
 
-    // follow arcs without a word label; per state keep the best (weight, then string) element
-    void closure(std::vector<Elem> *sub) {
-        bool any = false;
-        for (const Elem &e : *sub)
-            for (const RArc &a : in_.arcs[e.state])
-                if (a.word == 0) any = true;
-        if (!any) return;
-        std::unordered_map<int, int> pos;
-        std::vector<Elem> cur(*sub);
-        std::vector<int> queue;
-        std::vector<char> queued;
-        for (size_t i = 0; i < cur.size(); i++) {
-            pos[cur[i].state] = (int)i;
-            queue.push_back((int)i);
-            queued.push_back(1);
+    // Follow arcs without a word label; per state keep the best (weight, then string) element; then drop the elements
+    // whose state neither is final nor has an arc with a word label (ConvertToMinimal).  The raw lattice is acyclic, so
+    // states are expanded in topological order (each once, after all its predecessors inside the closure); strings grow
+    // as parent-linked nodes in an arena and are materialised only for the elements that survive.
+    struct SNode { int parent, tid; };
+    struct Work { int state; LatWeight w; int base, node; };  // string = input element `base`'s string + arena path `node`
+    std::vector<int> materialize(const std::vector<Elem> &in, const Work &x, const std::vector<SNode> &arena) const {
+        std::vector<int> tail;
+        for (int n = x.node; n >= 0; n = arena[n].parent) tail.push_back(arena[n].tid);
+        std::vector<int> out(in[x.base].str);
+        out.insert(out.end(), tail.rbegin(), tail.rend());
+        return out;
+    }
+    void closure_minimal(std::vector<Elem> *sub) {
+        const std::vector<Elem> &in = *sub;
+        std::vector<Work> cur;
+        std::vector<SNode> arena;
+        epoch_++;
+        typedef std::pair<int, int> QE;  // (topological index, work index)
+        std::priority_queue<QE, std::vector<QE>, std::greater<QE>> heap;
+        for (size_t i = 0; i < in.size(); i++) {
+            cur.push_back(Work{in[i].state, in[i].w, (int)i, -1});
+            stamp_[in[i].state] = epoch_;
+            slot_[in[i].state] = (int)i;
+            heap.push(QE(topo_[in[i].state], (int)i));
         }
-        size_t guard = 0;
-        while (!queue.empty() && guard++ < 10000000) {
-            const int i = queue.back();
-            queue.pop_back();
-            queued[i] = 0;
-            const Elem e = cur[i];
+        std::vector<char> done;
+        while (!heap.empty()) {
+            const int i = heap.top().second;
+            heap.pop();
+            if ((int)done.size() < (int)cur.size()) done.resize(cur.size(), 0);
+            if (done[i]) continue;
+            done[i] = 1;
+            const Work e = cur[i];
             for (const RArc &a : in_.arcs[e.state]) {
                 if (a.word != 0) continue;
-                Elem nx{a.dst, times_w(e.w, a.w), e.str};
-                if (a.tid != 0) nx.str.push_back(a.tid);
-                auto it = pos.find(a.dst);
-                if (it == pos.end()) {
-                    pos[a.dst] = (int)cur.size();
-                    cur.push_back(std::move(nx));
-                    queue.push_back((int)cur.size() - 1);
-                    queued.push_back(1);
-                } else if (compare_elem(nx.w, nx.str, cur[it->second].w, cur[it->second].str) == 1) {
-                    cur[it->second] = std::move(nx);
-                    if (!queued[it->second]) {
-                        queued[it->second] = 1;
-                        queue.push_back(it->second);
-                    }
+                int node = e.node;
+                if (a.tid != 0) {
+                    arena.push_back(SNode{e.node, a.tid});
+                    node = (int)arena.size() - 1;
+                }
+                Work nx{a.dst, times_w(e.w, a.w), e.base, node};
+                if (stamp_[a.dst] != epoch_) {
+                    stamp_[a.dst] = epoch_;
+                    slot_[a.dst] = (int)cur.size();
+                    cur.push_back(nx);
+                    heap.push(QE(topo_[a.dst], (int)cur.size() - 1));
+                } else {
+                    Work &old = cur[slot_[a.dst]];
+                    int c = compare_w(nx.w, old.w);
+                    if (c == 0) c = compare_str(materialize(in, nx, arena), materialize(in, old, arena));
+                    if (c == 1) old = nx;  // (its successors have not been expanded yet: topological order)
                 }
             }
         }
-        std::sort(cur.begin(), cur.end(), [](const Elem &x, const Elem &y) { return x.state < y.state; });
-        sub->swap(cur);
-    }
-
-    // drop elements whose state neither is final nor has an arc with a word label
-    void to_minimal(std::vector<Elem> *sub) {
         std::vector<Elem> keep;
-        for (Elem &e : *sub) {
-            bool k = in_.final_cost[e.state] != kInfF;
-            for (const RArc &a : in_.arcs[e.state])
-                if (a.word != 0) {
-                    k = true;
-                    break;
-                }
-            if (k) keep.push_back(std::move(e));
-        }
+        for (const Work &x : cur)
+            if (keepable_[x.state]) keep.push_back(Elem{x.state, x.w, materialize(in, x, arena)});
+        std::sort(keep.begin(), keep.end(), [](const Elem &x, const Elem &y) { return x.state < y.state; });
         sub->swap(keep);
     }
+    void closure(std::vector<Elem> *sub) { closure_minimal(sub); }
+    void to_minimal(std::vector<Elem> *) {}  // (folded into closure_minimal)
 
     // take the best weight and the longest common string prefix out of the subset
     void normalize(std::vector<Elem> *sub, LatWeight *tot, std::vector<int> *common) {
@@ -357,6 +371,9 @@ class Determinizer {
     float beam_;
     CLat *out_ = nullptr;
     std::vector<double> beta_;
+    std::vector<int> topo_, stamp_, slot_;
+    std::vector<char> keepable_;
+    int epoch_ = 0;
     double cutoff_ = 0;
     std::vector<OutState> states_;  // index = output state id of the subset states (the optional extra start state is added last)
     std::unordered_map<std::string, std::vector<int>> index_;
