@@ -270,7 +270,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     config = {"workload": "small-en-us arch (random-init TDNN-F, synthetic HCLG ~1.0M arcs), %d concurrent 16 kHz streams of U(8,16) s per GPU" % a.streams,
               "streams_per_gpu": a.streams, "frames_per_chunk": 51, "beam": 13.0, "lattice_beam": 6.0, "max_active": 7000,
-              "l2": "inputs+state larger than L2 (audio ~190 MB, token logs GBs)", "sharding": "streams by utterance, no collective"}
+              "l2": "inputs+state larger than L2 (audio ~190 MB, token logs GBs)", "sharding": "streams by utterance, no collective",
+              "result_mode": "best path (lattice=0: word-aligned best path, conf 1); lattice generation and the host MBR chain are the separate lattice_mode legs"}
 
     if a.workload == "large-lattice":
         return large_lattice(a)

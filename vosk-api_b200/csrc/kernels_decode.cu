@@ -1058,8 +1058,6 @@ __global__ void __launch_bounds__(kPruneThreads) lattice_prune_kernel(DecArgs a)
         out_links[k] = lk;
     }
     if (tid == 0) {
-        if (hdr->pad1 == 12345 && (hdr->n_links != n_out || hdr->n_tok != min(base, a.lat_tok_cap)) && a.counters) atomicAdd(a.counters + 11, 1ull);
-        hdr->pad1 = 12345;
         hdr->n_tok = min(base, a.lat_tok_cap);
         hdr->n_links = n_out;
         hdr->n_final = min(s_nfinal, a.lat_final_cap);

@@ -372,7 +372,7 @@ void Engine::alloc_state() {
     {   // fixed scratch partition per tier (tiers of different steps overlap in time): as many CTAs as the tier can have resident
         int sms = 0;
         VB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device));
-        auto cap = [&](int threads) { return sms * vbk_decode_blocks_per_sm(threads); };
+        auto cap = [&](int threads) { return std::min(sms * vbk_decode_blocks_per_sm(threads), L); };  // never more CTAs than lanes
         tier_scratch_[0] = 0;
         tier_scratch_[1] = cap(cfg_.heavy_threads);
         tier_scratch_[2] = tier_scratch_[1] + cap(cfg_.mid_threads);
@@ -508,7 +508,6 @@ StepStats Engine::stats() {
     s.arcs_staged = c[8];
     s.links = c[9];
     s.lat_arcs = c[10];
-    s.prune_mismatch = c[11];
     for (int k = 0; k < 16; k++) s.phase[k] = c[16 + k];
     return s;
 }
@@ -820,11 +819,6 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         // lattice pruning only touches finished channels (nothing else does until they are reused after completion)
         sl.dec.lane_begin = 0;
         sl.dec.lane_end = L;
-        static const bool twice = getenv("VB_PRUNE_TWICE") != nullptr;  // determinism probe: same inputs, two launches
-        if (twice) {
-            VB_CUDA_CHECK(cudaMemsetAsync(sl.dec.lat_hdr, 0, (size_t)L * sizeof(LatHeader), st));
-            VB_CUDA_CHECK(vbk_lattice_prune(&sl.dec, st));
-        }
         VB_CUDA_CHECK(vbk_lattice_prune(&sl.dec, st));
         sl.launches++;
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_hdr, sl.dec.lat_hdr, (size_t)L * sizeof(LatHeader), cudaMemcpyDeviceToHost, st));

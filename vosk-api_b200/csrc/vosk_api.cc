@@ -156,7 +156,6 @@ int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
         v[13] += s.lane_cycles_sum; v[14] = std::max(v[14], (double)s.lane_cycles_max); v[15] = std::max(v[15], (double)s.max_tokens); v[16] += s.lane_launches; v[17] += s.host_launch_ms;
         v[18] += s.arcs_staged; v[19] += s.links; v[20] += s.lat_arcs;
         for (int k = 0; k < 16; k++) v[21 + k] += s.phase[k];
-        v[36] = (double)s.prune_mismatch;  // probe (VB_PRUNE_TWICE): replaces the unused last phase slot
     }
     int k = n < 37 ? n : 37;
     memcpy(out, v, k * sizeof(double));
