@@ -82,6 +82,13 @@ int vosk_b200_device_for_stream(unsigned long long stream_id, int num_devices);
 int vosk_b200_format_result(const char *const *words, const int *begin, const int *end, const float *conf, int n, float offset, char *out, int cap);
 int vosk_b200_resample(const float *in, int n, float rate_in, float *out, int cap);
 int vosk_b200_model_check(const char *model_dir, char *out, int cap);
+/* model_tensor: loads a model directory (Kaldi formats or the generator's container, file by file) with the engine's
+ * loaders and returns one loaded object as doubles: "meta" {ops, context, pdfs, ivector dim, bypass scale, prior offset,
+ * gaussians}, "op<i>.meta" {in node, bypass node, uses ivector, relu+batchnorm, K, N, number of offsets, offsets...},
+ * "op<i>.w" [N][K], "op<i>.b", "op<i>.bn_scale", "op<i>.bn_offset", "tid2pdf", "tid2phone", "iv.lda", "iv.gconsts",
+ * "iv.weights", "iv.means_invvars", "iv.inv_vars", "iv.M", "iv.sigma_inv", "iv.cmvn".  Returns the element count (copies
+ * min(count, cap)), 0 for an absent optional object, -1 on error (text in vosk_b200_last_error). */
+int64_t vosk_b200_model_tensor(const char *model_dir, const char *name, double *out, int64_t cap);
 /* lattice_result: the host lattice chain (pruned word determinization, graph scale 0.9, word alignment, MBR) on an
  * explicit raw lattice {states, start, links {src, dst, csr arc, acoustic cost}, finals}; stage 0 = result text,
  * 1 = determinized lattice, 2 = word-aligned lattice as text lines ("S start", "A src dst word graph acoustic tids",

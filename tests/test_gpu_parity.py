@@ -265,3 +265,18 @@ def test_rule5_endpoint_segments(model_root, oracle_lib):
             assert len(want) == (2 if len(w) < 40 * 16000 and len(w) > 20 * 16000 else 3 if len(w) > 40 * 16000 else 1)
             assert got == want
         del recs, m
+
+
+def test_kaldi_format_model_dir_decodes_like_the_container(model_root, oracle_lib, tmp_path):
+    """the model written in Kaldi's own formats (un-collapsed nnet3 final.mdl, DiagGMM, IvectorExtractor,
+    text CMVN stats) goes through the real-format loader and every stage still matches the oracle, which reads the
+    generator's collapsed container of the same parameters."""
+    import kaldi_io
+    import vbmodel
+    src = model_root("tiny")
+    kdir = kaldi_io.convert_model_dir(src, str(tmp_path))
+    model = vbmodel.load_model_dir(src)
+    waves = _waves([0.52, 2.04, 3.7], seed0=300)
+    got, _ = helpers.run_engine(kdir, waves, options="num-channels=4,max-batch-size=4,max-seconds=8")
+    for w, g in zip(waves, got):
+        _check_stream(model, oracle_lib, w, g, 51)

@@ -3,6 +3,8 @@
 // [REF src/batch_model.cc:26-28].  HCLG.fst: OpenFst binary, "vector" or "const", StdArc.
 #include "vb_model.h"
 
+#include "vb_kaldi.h"
+
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -186,10 +188,61 @@ static const Tensor *find(const TensorMap &m, const std::string &k, bool require
     return &it->second;
 }
 
-void Model::load(const std::string &d) {
-    dir = d;
-    conf = read_conf(d + "/conf/model.conf");
-    am = read_vbt(d + "/am/final.mdl");
+static Tensor make_f32(const std::vector<float> &v, std::vector<int64_t> shape) {
+    Tensor t;
+    t.dtype = 0;
+    t.shape = std::move(shape);
+    t.data.resize(v.size() * 4);
+    if (!v.empty()) memcpy(t.data.data(), v.data(), v.size() * 4);
+    return t;
+}
+
+// final.mdl in Kaldi's own format (TransitionModel + nnet3): compiled into the same op chain (vb_kaldi.cc)
+void Model::load_kaldi_am(const std::string &mdl) {
+    KaldiAm k = read_kaldi_final_mdl(mdl);
+    feat_dim = k.feat_dim;
+    ivec_dim = k.ivec_dim;
+    num_pdfs = k.num_pdfs;
+    if (feat_dim != kNumCeps) throw std::runtime_error("feat-dim must be 40");
+    if (k.left_context != k.right_context)
+        throw std::runtime_error("asymmetric model context (" + std::to_string(k.left_context) + ", " + std::to_string(k.right_context) + ") is not supported");
+    context = k.left_context;
+    if ((int)k.ops.size() + 1 > kMaxNodes) throw std::runtime_error("too many layers");
+    node_dim.push_back(feat_dim);
+    bool have_scale = false;
+    for (size_t i = 0; i < k.ops.size(); i++) {
+        KaldiOp &o = k.ops[i];
+        const std::string base = "op" + std::to_string(i);
+        AmOp op;
+        op.name = o.name;
+        op.in_node = o.in_node;
+        op.byp_node = o.byp_node;
+        op.offs = o.offs;
+        op.uses_ivec = o.uses_ivec;
+        op.relu_bn = o.relu;
+        op.K = o.K;
+        op.N = o.N;
+        if ((int)op.offs.size() > kMaxOffsets) throw std::runtime_error("too many time offsets in " + o.name);
+        if (op.N % 16 || op.K % 4) throw std::runtime_error("layer " + o.name + ": dimensions must be multiples of 16 (outputs) / 4 (inputs)");
+        op.W = &(am[base + ".w"] = make_f32(o.W, {o.N, o.K}));
+        op.b = o.b.empty() ? nullptr : &(am[base + ".b"] = make_f32(o.b, {o.N}));
+        op.bn_s = o.relu ? &(am[base + ".bn_scale"] = make_f32(o.bn_s, {o.N})) : nullptr;
+        op.bn_o = o.relu ? &(am[base + ".bn_offset"] = make_f32(o.bn_o, {o.N})) : nullptr;
+        if (o.byp_node >= 0) {
+            if (have_scale && o.byp_scale != bypass_scale) throw std::runtime_error("layers with different bypass scales are not supported");
+            bypass_scale = o.byp_scale;
+            have_scale = true;
+            if (node_dim[o.byp_node] != o.N) throw std::runtime_error("bypass dimension mismatch in " + o.name);
+        }
+        ops.push_back(op);
+        node_dim.push_back(o.N);
+    }
+    tid2pdf = std::move(k.tid2pdf);
+    tid2phone = std::move(k.tid2phone);
+}
+
+void Model::load_vbt_am(const std::string &mdl) {
+    am = read_vbt(mdl);
     const Tensor *cfgt = find(am, "config");
     std::map<std::string, std::string> c;
     {
@@ -257,6 +310,16 @@ void Model::load(const std::string &d) {
     const Tensor *t2p = find(am, "tid2pdf"), *t2ph = find(am, "tid2phone");
     tid2pdf.assign(t2p->i32(), t2p->i32() + t2p->numel());
     tid2phone.assign(t2ph->i32(), t2ph->i32() + t2ph->numel());
+}
+
+void Model::load(const std::string &d) {
+    dir = d;
+    conf = read_conf(d + "/conf/model.conf");
+    // am/final.mdl: Kaldi's TransitionModel + nnet3 file, or the generator's tensor container
+    const std::string mdl = d + "/am/final.mdl";
+    if (file_is_vbt(mdl)) load_vbt_am(mdl);
+    else if (kaldi_is_binary(mdl)) load_kaldi_am(mdl);
+    else throw std::runtime_error("unrecognised acoustic model file (neither Kaldi binary nor VBT1): " + mdl);
     graph = read_graph(d + "/graph/HCLG.fst", tid2pdf);
     for (int32_t pdf : graph.arc_pdf)
         if (pdf >= num_pdfs) throw std::runtime_error("pdf id out of range in graph");
@@ -281,10 +344,29 @@ void Model::load(const std::string &d) {
             phone_type[ph] = kind == "nonword" ? 1 : kind == "begin" ? 2 : kind == "end" ? 3 : kind == "internal" ? 4 : kind == "singleton" ? 5 : 0;
         }
     }
-    iv_lda = read_vbt(d + "/ivector/final.mat");
-    iv_dubm = read_vbt(d + "/ivector/final.dubm");
-    iv_ie = read_vbt(d + "/ivector/final.ie");
-    iv_cmvn = read_vbt(d + "/ivector/global_cmvn.stats");
+    // i-vector extractor files [REF src/model.cc:251-256]: Kaldi formats or the generator's container, file by file
+    auto matrix_tensor = [](const KaldiMatrix &km, bool f64) {
+        Tensor t;
+        t.dtype = f64 ? 2 : 0;
+        t.shape = {km.rows, km.cols};
+        t.data.resize(km.v.size() * (f64 ? 8 : 4));
+        if (f64) memcpy(t.data.data(), km.v.data(), km.v.size() * 8);
+        else
+            for (size_t i = 0; i < km.v.size(); i++) reinterpret_cast<float *>(t.data.data())[i] = (float)km.v[i];
+        return t;
+    };
+    const std::string ivd = d + "/ivector/";
+    if (file_is_vbt(ivd + "final.mat")) iv_lda = read_vbt(ivd + "final.mat");
+    else iv_lda["lda"] = matrix_tensor(read_kaldi_matrix_file(ivd + "final.mat"), false);
+    iv_dubm = file_is_vbt(ivd + "final.dubm") ? read_vbt(ivd + "final.dubm") : read_kaldi_dubm(ivd + "final.dubm");
+    iv_ie = file_is_vbt(ivd + "final.ie") ? read_vbt(ivd + "final.ie") : read_kaldi_ie(ivd + "final.ie");
+    if (file_is_vbt(ivd + "global_cmvn.stats")) iv_cmvn = read_vbt(ivd + "global_cmvn.stats");
+    else iv_cmvn["stats"] = matrix_tensor(read_kaldi_matrix_file(ivd + "global_cmvn.stats"), true);
+    {
+        const Tensor *lda = find(iv_lda, "lda"), *st = find(iv_cmvn, "stats");
+        if (lda->shape.size() != 2 || lda->shape[0] != feat_dim) throw std::runtime_error("final.mat: unexpected shape");
+        if (st->shape.size() != 2 || st->shape[0] != 2 || st->shape[1] != feat_dim + 1) throw std::runtime_error("global_cmvn.stats: unexpected shape");
+    }
     num_gauss = (int)find(iv_dubm, "gconsts")->numel();
     prior_offset = find(iv_ie, "prior_offset")->f32()[0];
     if (find(iv_ie, "M")->shape[2] != ivec_dim) throw std::runtime_error("i-vector dim mismatch");

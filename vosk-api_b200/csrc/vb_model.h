@@ -68,6 +68,8 @@ struct Model {
     float prior_offset = 0.f;
 
     void load(const std::string &model_dir);  // throws std::runtime_error on a missing/corrupt file
+    void load_vbt_am(const std::string &mdl);    // am/final.mdl as the generator's tensor container (collapsed network)
+    void load_kaldi_am(const std::string &mdl);  // am/final.mdl as Kaldi's TransitionModel + nnet3 file (vb_kaldi.cc)
     void apply_conf(Config *cfg) const;
 };
 

@@ -344,6 +344,73 @@ int vosk_b200_model_check(const char *model_dir, char *out, int cap) {
     }
 }
 
+// Host-only: one object of a loaded model directory as doubles (format-independent view used by the loader tests).
+int64_t vosk_b200_model_tensor(const char *model_dir, const char *name, double *out, int64_t cap) {
+    try {
+        static std::string cached_dir;
+        static std::unique_ptr<vb::Model> cached;
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        const std::string dir = model_dir ? model_dir : "model";
+        if (!cached || cached_dir != dir) {
+            cached.reset();
+            std::unique_ptr<vb::Model> m(new vb::Model);
+            m->load(dir);
+            cached = std::move(m);
+            cached_dir = dir;
+        }
+        const vb::Model &m = *cached;
+        std::vector<double> v;
+        auto from_tensor = [&](const vb::Tensor *t) {
+            if (!t) return;
+            const int64_t n = t->numel();
+            v.resize((size_t)n);
+            for (int64_t i = 0; i < n; i++)
+                v[(size_t)i] = t->dtype == 0 ? (double)t->f32()[i] : t->dtype == 1 ? (double)t->i32()[i] : t->dtype == 2 ? t->f64()[i] : (double)t->data[(size_t)i];
+        };
+        auto opt = [](const vb::TensorMap &tm, const char *k) -> const vb::Tensor * {
+            auto it = tm.find(k);
+            return it == tm.end() ? nullptr : &it->second;
+        };
+        const std::string nm = name ? name : "";
+        if (nm == "meta") {
+            v = {(double)m.ops.size(), (double)m.context, (double)m.num_pdfs, (double)m.ivec_dim, (double)m.bypass_scale, (double)m.prior_offset,
+                 (double)m.num_gauss};
+        } else if (nm == "tid2pdf") {
+            v.assign(m.tid2pdf.begin(), m.tid2pdf.end());
+        } else if (nm == "tid2phone") {
+            v.assign(m.tid2phone.begin(), m.tid2phone.end());
+        } else if (nm.compare(0, 3, "iv.") == 0) {
+            const std::string k = nm.substr(3);
+            if (k == "lda") from_tensor(opt(m.iv_lda, "lda"));
+            else if (k == "cmvn") from_tensor(opt(m.iv_cmvn, "stats"));
+            else if (k == "M" || k == "sigma_inv") from_tensor(opt(m.iv_ie, k.c_str()));
+            else from_tensor(opt(m.iv_dubm, k.c_str()));
+        } else if (nm.compare(0, 2, "op") == 0 && nm.find('.') != std::string::npos) {
+            const size_t dot = nm.find('.');
+            const int i = std::stoi(nm.substr(2, dot - 2));
+            if (i < 0 || i >= (int)m.ops.size()) throw std::runtime_error("no such op: " + nm);
+            const vb::AmOp &op = m.ops[(size_t)i];
+            const std::string k = nm.substr(dot + 1);
+            if (k == "meta") {
+                v = {(double)op.in_node, (double)op.byp_node, (double)op.uses_ivec, (double)op.relu_bn, (double)op.K, (double)op.N, (double)op.offs.size()};
+                for (int o : op.offs) v.push_back(o);
+            } else if (k == "w") from_tensor(op.W);
+            else if (k == "b") from_tensor(op.b);
+            else if (k == "bn_scale") from_tensor(op.bn_s);
+            else if (k == "bn_offset") from_tensor(op.bn_o);
+            else throw std::runtime_error("unknown object: " + nm);
+        } else {
+            throw std::runtime_error("unknown object: " + nm);
+        }
+        for (int64_t i = 0; i < (int64_t)v.size() && i < cap; i++) out[i] = v[(size_t)i];
+        return (int64_t)v.size();
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return -1;
+    }
+}
+
 // Host-only: the lattice chain of PushLattice on an explicit raw lattice.  stage 0: result text (JSON); 1: determinized
 // lattice; 2: word-aligned lattice, as text lines "A src dst word graph acoustic tid,tid,..", "F state graph acoustic tids",
 // "S start".
