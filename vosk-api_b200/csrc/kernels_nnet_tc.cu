@@ -81,13 +81,19 @@ struct TcSmem {
 };
 }  // namespace
 
+// per-phase cycle counters of the tile pipeline (profiling aid, VB_TC_PROF=1 all layers / 2 the K=192 N=512 affines /
+// 3 the K>=1024 linears): tiles, prologue, producer loop, wait for the accumulator, epilogue, MMA warp: first operands
+// ready, MMA warp: last commit (both counted from the end of the prologue)
+__device__ unsigned long long g_tc_prof[8];
+
 struct alignas(64) TensorMapBlob {
     unsigned char b[128];
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const __grid_constant__ TensorMapBlob map_lo, int BN,
-               int stages, int tmem_cols, int terms, int n_main) {
+               int stages, int tmem_cols, int terms, int n_main, int prof) {
+    const long long pt0 = prof ? clock64() : 0;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // dynamic smem: [stage][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], 1024-byte aligned
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -134,6 +140,7 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = ts.tmem_base;
+    const long long pt1 = prof ? clock64() : 0;
 
     if (warp < kTmaWarp) {
         // =========================== A producers ===========================
@@ -177,13 +184,10 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
                 }
             }
         };
-        float4 v[RPT], vn[RPT], vnn[RPT];
-        gather(0, v);
-        if (nkb > 1) gather(1, vn);
-        for (int kb = 0; kb < nkb; kb++) {
+        // split one gathered K-block into hi/lo and publish it to the MMA warp
+        auto publish = [&](int kb, const float4 *v) {
             const int s = kb % stages;
             const uint32_t par = (uint32_t)((kb / stages) & 1);
-            if (kb + 2 < nkb) gather(kb + 2, vnn);  // software pipelining: two more blocks' loads fly while this one is split and stored
             mbar_wait(&ts.empty[s], par ^ 1);
             const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + TM * 128;
 #pragma unroll
@@ -201,15 +205,29 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA (async proxy)
             mbar_arrive(&ts.full[s]);
-#pragma unroll
-            for (int it = 0; it < RPT; it++) {
-                v[it] = vn[it];
-                vn[it] = vnn[it];
+        };
+        // software pipeline, unrolled by three so that the buffers rotate by name (no register moves that would wait for the
+        // loads just issued): while block kb is split and stored, the loads of kb + 1 and kb + 2 are in flight
+        float4 v0[RPT], v1[RPT], v2[RPT];
+        gather(0, v0);
+        if (nkb > 1) gather(1, v1);
+        for (int kb = 0; kb < nkb; kb += 3) {
+            if (kb + 2 < nkb) gather(kb + 2, v2);
+            publish(kb, v0);
+            if (kb + 1 < nkb) {
+                if (kb + 3 < nkb) gather(kb + 3, v0);
+                publish(kb + 1, v1);
+            }
+            if (kb + 2 < nkb) {
+                if (kb + 4 < nkb) gather(kb + 4, v1);
+                publish(kb + 2, v2);
             }
         }
       if (warp < 4) {  // (a warp reads the 32 TMEM lanes of its quarter: the first four producer warps)
         // =========================== epilogue ===========================
+        const long long pt2 = prof ? clock64() : 0;
         mbar_wait(&ts.accum, 0);
+        const long long pt3 = prof ? clock64() : 0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int r = warp * 32 + lane;
         const int ch = ts.row_ch[r], t = ts.row_t[r];
@@ -274,6 +292,14 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (prof && tid == 0) {
+            const long long pt4 = clock64();
+            atomicAdd(&g_tc_prof[0], 1ull);
+            atomicAdd(&g_tc_prof[1], (unsigned long long)(pt1 - pt0));
+            atomicAdd(&g_tc_prof[2], (unsigned long long)(pt2 - pt1));
+            atomicAdd(&g_tc_prof[3], (unsigned long long)(pt3 - pt2));
+            atomicAdd(&g_tc_prof[4], (unsigned long long)(pt4 - pt3));
+        }
       }
     } else if (warp == kTmaWarp) {
         // =========================== TMA: weight boxes ===========================
@@ -302,6 +328,7 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
             const uint32_t par = (uint32_t)((kb / stages) & 1);
             mbar_wait(&ts.full[s], par);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (prof && kb == 0 && lane == 0) atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - pt1));
             if (lane == 0) {
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t dAh = umma_desc(sa), dAl = umma_desc(sa + TM * 128);
@@ -336,8 +363,10 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
                 }
                 // tcgen05.commit: arrives on the barrier when the MMAs issued so far have read their operands
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&ts.empty[s])) : "memory");
-                if (kb == nkb - 1)
+                if (kb == nkb - 1) {
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&ts.accum)) : "memory");
+                    if (prof) atomicAdd(&g_tc_prof[6], (unsigned long long)(clock64() - pt1));
+                }
             }
             __syncwarp();
         }
@@ -420,7 +449,22 @@ extern "C" cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s) {
     memcpy(mh.b, a->map_hi, 128);
     memcpy(ml.b, a->map_lo, 128);
     static int terms = getenv("VB_TC_TERMS") ? atoi(getenv("VB_TC_TERMS")) : 3;
-    gemm_tc_kernel<<<grid, kTcThreads, smem, s>>>(*a, mh, ml, BN, stages, tmem_cols, terms, n_main);
+    static int prof = getenv("VB_TC_PROF") ? atoi(getenv("VB_TC_PROF")) : 0;
+    const bool prof_this = prof == 1 || (prof == 2 && op.K == 192 && op.N == 512) || (prof == 3 && op.K >= 1024);
+    if (prof_this) {
+        static bool hooked = false;
+        if (!hooked) {
+            hooked = true;
+            atexit([] {
+                unsigned long long h[8] = {};
+                if (cudaMemcpyFromSymbol(h, g_tc_prof, sizeof h) != cudaSuccess || !h[0]) return;
+                const double n = (double)h[0];
+                fprintf(stderr, "[gemm_tc prof] tiles %.0f; cycles per tile: prologue %.0f, producer loop %.0f, wait accumulator %.0f, epilogue %.0f; MMA warp: first operands after %.0f, last commit after %.0f\n",
+                        n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n);
+            });
+        }
+    }
+    gemm_tc_kernel<<<grid, kTcThreads, smem, s>>>(*a, mh, ml, BN, stages, tmem_cols, terms, n_main, prof_this ? 1 : 0);
     return cudaGetLastError();
 }
 

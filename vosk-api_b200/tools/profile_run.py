@@ -24,6 +24,8 @@ mat = np.zeros((streams, stride), dtype=np.int16)
 for i, w in enumerate(waves):
     mat[i, :len(w)] = w
 model.SetTiming(True)
+if os.environ.get("VB_SLOTS"):  # 1 = serialize the steps: per-stage device times free of overlap
+    model.SetSlots(int(os.environ["VB_SLOTS"]))
 for _ in range(reps):
     ms, texts = model.RunResident(mat, lengths)
 st = model.Stats()
