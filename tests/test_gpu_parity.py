@@ -280,3 +280,38 @@ def test_kaldi_format_model_dir_decodes_like_the_container(model_root, oracle_li
     got, _ = helpers.run_engine(kdir, waves, options="num-channels=4,max-batch-size=4,max-seconds=8")
     for w, g in zip(waves, got):
         _check_stream(model, oracle_lib, w, g, 51)
+
+
+def test_full_size_batch_is_invariant_to_batch_composition(model_root, oracle_lib):
+    """BASELINE.json configs[1] size: 512 concurrent streams on the small architecture (shortened audio so the test runs
+    in seconds).  Size-independent properties: (1) a stream's result does not depend on which streams share its batch —
+    the 512-lane run, a 64-lane / 96-channel run of the same streams (different batching, channel reuse, tier mix) and
+    the device-resident run give identical texts; (2) a sample of the streams equals the oracle pipeline's transcript and
+    word times; (3) the search counters of the two runs are identical (same tokens, same arcs: bit-exact search)."""
+    import vosk
+    import vbmodel
+    mdir = model_root("small")
+    model = vbmodel.load_model_dir(mdir)
+    rng = np.random.default_rng(77)
+    base = [vbmodel.synth_audio(3.2, 2000 + k) for k in range(12)]
+    waves = []
+    for i in range(512):
+        n = int(rng.uniform(1.0, 3.2) * 16000)
+        waves.append(np.roll(base[i % 12], int(rng.integers(0, 16000)))[:n].copy())
+    big, st_big = helpers.run_engine(mdir, waves, options="num-channels=512,max-batch-size=512,max-seconds=6", capture=False, bytes_per_call=16000)
+    small, st_small = helpers.run_engine(mdir, waves, options="num-channels=96,max-batch-size=64,max-seconds=6", capture=False, bytes_per_call=6400)
+    assert [g["text"] for g in big] == [g["text"] for g in small]
+    for k in ("tokens", "arcs_emitting", "arcs_epsilon", "tokens_new"):
+        assert st_big[k] == st_small[k], k
+    assert sum(1 for g in big if helpers.words_of(g["text"])) > 400  # the streams do decode to words
+    # device-resident path (bench.py's `value` leg) on the same streams
+    m = vosk.BatchModel(mdir, options="num-channels=512,max-batch-size=512,max-seconds=6")
+    lengths = np.array([len(w) for w in waves], dtype=np.int32)
+    mat = np.zeros((512, int((lengths.max() + 7) // 8 * 8)), dtype=np.int16)
+    for i, w in enumerate(waves):
+        mat[i, :len(w)] = w
+    _, texts = m.RunResident(mat, lengths)
+    assert list(texts) == [g["text"] for g in big]
+    del m
+    for i in (0, 101, 255, 388, 511):
+        assert big[i]["text"] == oracle_lib.recognize(model, waves[i], stages=True)["text"], i
