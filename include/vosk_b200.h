@@ -18,7 +18,7 @@ extern "C" {
 /* Like vosk_batch_model_new but with an explicit model directory and "key=value,key=value"
  * options: frames-per-chunk, max-batch-size, num-channels, beam, lattice-beam, max-active,
  * min-active, tok-cap, cand-cap, hash-size, max-seconds, log-tokens-per-frame, tensor-cores, lattice,
- * log-links-per-frame, lat-tok-cap, lat-link-cap, post-threads, partials, pipeline-slots, heavy-tokens,
+ * log-links-per-frame, lat-tok-cap, lat-link-cap, post-threads, partials, pipeline-slots, heavy-tokens, device-resample,
  * debug-capture, devices (GPU indices separated by ':' or "all").
  * Env VOSK_BATCH_OPTIONS / VOSK_BATCH_DEVICES are applied first.  NULL on failure. */
 VoskBatchModel *vosk_batch_model_new_ex(const char *model_dir, const char *options);
@@ -36,7 +36,7 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model);
  * one lane spent in a search launch, [15] largest token count of a frame, [16] lane-launches, [17] host ms spent enqueueing steps,
  * [18] arcs parked below the running cutoff, [19] lattice links logged, [20] lattice arcs kept after pruning,
  * [21..28] / [29..36] SM cycles the 1024-thread / smaller search CTAs spent per phase (cutoff, rank, log, gather,
- * insert, closure, finalize, unused).
+ * insert, closure, finalize, unused), [37] per-call segments resampled on the device.
  * Returns the number written. */
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n);
 void vosk_batch_model_reset_stats(VoskBatchModel *model);

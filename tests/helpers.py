@@ -21,11 +21,11 @@ def feed_round_robin(recs, waves, bytes_per_call=8000):
             r.AcceptWaveform(data)
 
 
-def run_engine(model_dir, waves, options="", capture=True, bytes_per_call=8000):
+def run_engine(model_dir, waves, options="", capture=True, bytes_per_call=8000, rate=16000.0):
     import vosk
     opts = "debug-capture=1," + options if capture else options
     model = vosk.BatchModel(model_dir, options=opts)
-    recs = [vosk.BatchRecognizer(model, 16000.0) for _ in waves]
+    recs = [vosk.BatchRecognizer(model, float(rate)) for _ in waves]
     if capture:
         for r in recs:
             r.DebugCapture()

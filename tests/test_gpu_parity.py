@@ -315,3 +315,41 @@ def test_full_size_batch_is_invariant_to_batch_composition(model_root, oracle_li
     del m
     for i in (0, 101, 255, 388, 511):
         assert big[i]["text"] == oracle_lib.recognize(model, waves[i], stages=True)["text"], i
+
+
+@pytest.mark.parametrize("rate,bytes_per_call", [(8000, 8000), (44100, 3000), (22050, 17000), (8000, 60)])
+def test_device_resampling_equals_the_host_resampler(model_root, oracle_lib, rate, bytes_per_call):
+    """streams opened at another rate.  The reference resamples every accept_waveform call on its own
+    (LinearResample, flush=true) [REF src/batch_recognizer.cc:27-29,157-158].  The GPU resampling kernel (device-resample=1:
+    raw samples and per-call segments staged, chunks cut in 16 kHz samples) must give the very samples the host resampler
+    gives (device-resample=0), so MFCCs are bit-identical and everything after them too; the host resampler itself is pinned
+    in tests/test_host_logic.py.  Call sizes: straddling chunk boundaries, large, and tiny (60 bytes: more than 64 calls per
+    chunk, which the recognizer resamples on the host instead)."""
+    import vbmodel
+    mdir = model_root("tiny")
+    waves = [vbmodel.synth_audio(s, 400 + i, sr=rate) for i, s in enumerate([0.31, 1.3, 2.6])]
+    opts = "num-channels=4,max-batch-size=4,max-seconds=8"
+    dev, st_dev = helpers.run_engine(mdir, waves, options=opts + ",device-resample=1", bytes_per_call=bytes_per_call, rate=rate)
+    host, st_host = helpers.run_engine(mdir, waves, options=opts + ",device-resample=0", bytes_per_call=bytes_per_call, rate=rate)
+    assert st_host["resample_segments"] == 0
+    if bytes_per_call >= 1000:
+        assert st_dev["resample_segments"] >= sum(-(-len(w) * 2 // bytes_per_call) for w in waves)  # every call went through the kernel
+    for a, b in zip(dev, host):
+        assert a["error"] == 0 and b["error"] == 0
+        assert a["mfcc"].shape == b["mfcc"].shape and a["mfcc"].shape[0] > 0
+        np.testing.assert_array_equal(a["mfcc"].view(np.uint32), b["mfcc"].view(np.uint32))
+        np.testing.assert_array_equal(a["loglikes"].view(np.uint32), b["loglikes"].view(np.uint32))
+        assert a["text"] == b["text"]
+    # and the whole chain against the oracle fed with the host-resampled samples
+    import ctypes, os
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vosk-api_b200", "lib", "libvosk.so"))
+    lib.vosk_b200_resample.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_int]
+    model = vbmodel.load_model_dir(mdir)
+    w = waves[1]
+    pieces = []
+    for off in range(0, len(w), bytes_per_call // 2):
+        x = np.ascontiguousarray(w[off:off + bytes_per_call // 2], dtype=np.float32)
+        out = np.zeros(len(x) * 3 + 16, dtype=np.float32)
+        n = lib.vosk_b200_resample(x.ctypes.data, len(x), float(rate), out.ctypes.data, len(out))
+        pieces.append(np.clip(np.rint(out[:n]), -32768, 32767).astype(np.int16))
+    _check_stream(model, oracle_lib, np.concatenate(pieces), dev[1], 51)

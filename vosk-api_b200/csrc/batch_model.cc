@@ -25,6 +25,7 @@ static void apply_option(Config *c, const std::string &k, const std::string &v) 
     else if (k == "log-tokens-per-frame") I(&c->log_tokens_per_frame);
     else if (k == "tensor-cores") I(&c->use_tensor_cores);
     else if (k == "pipeline-slots") I(&c->pipeline_slots);
+    else if (k == "device-resample") I(&c->device_resample);
     else if (k == "heavy-tokens") I(&c->heavy_tokens);
     else if (k == "mid-tokens") I(&c->mid_tokens);
     else if (k == "mid-threads") I(&c->mid_threads);

@@ -14,6 +14,8 @@ BatchRecognizer::BatchRecognizer(BatchModel *model, float sample_frequency)
       resampler_(sample_frequency, 16000.0f, std::min(sample_frequency / 2, 16000.0f / 2), 6) {
     id_ = model->GetID(this);
     stream_ = model->engine_for(id_).open_stream();
+    // non-16 kHz input is resampled on the GPU (option device-resample, default on) for rates up to 48 kHz
+    device_resample_ = !resampler_.identity() && model->engine_for(id_).config().device_resample && sample_frequency <= 48000.f;
     std::shared_ptr<Sink> sink = sink_;
     const Model *m = &model->model();
     const float lattice_beam = model->engine_for(id_).config().lattice_beam;
@@ -53,6 +55,16 @@ void BatchRecognizer::AcceptWaveform(const char *data, int len) {
     const int16_t *pcm = reinterpret_cast<const int16_t *>(data);
     if (resampler_.identity()) {
         buffer_.insert(buffer_.end(), pcm, pcm + n);
+    } else if (device_resample_) {
+        // keep the call as it came; hand over chunks of samples_per_chunk OUTPUT samples with the raw samples their taps reach
+        Call c;
+        c.in.assign(pcm, pcm + n);
+        c.n_out = resampler_.num_output(n);
+        avail_ += c.n_out;
+        if (c.n_out > 0) calls_.push_back(std::move(c));
+        const int spc = model_->samples_per_chunk();
+        while (avail_ >= spc) push_resampled_chunk(spc, false);
+        return;
     } else {
         std::vector<float> in(n), out;
         for (int i = 0; i < n; i++) in[i] = pcm[i];
@@ -72,6 +84,10 @@ void BatchRecognizer::AcceptWaveform(const char *data, int len) {
 void BatchRecognizer::FinishStream() {
     if (finished_) return;
     finished_ = true;
+    if (device_resample_) {
+        push_resampled_chunk((int)avail_, true);
+        return;
+    }
     // whatever is buffered (possibly nothing) goes out flagged last [REF src/batch_recognizer.cc:37-41]
     model_->engine_for(id_).push(stream_, buffer_.data(), (int)buffer_.size(), true);
     buffer_.clear();
@@ -105,3 +121,60 @@ int BatchRecognizer::PartialFrames() {
 }
 
 int BatchRecognizer::GetNumPendingChunks() { return stream_->pending_chunks.load(); }
+
+// One chunk of n_out 16 kHz samples, described by the calls it spans: per call the output range taken and the raw
+// samples those outputs' filter taps can reach (the reference resamples every call on its own with flush=true
+// [REF src/batch_recognizer.cc:157-158], so taps never cross a call boundary).  A chunk made of too many small calls
+// is resampled here instead (same arithmetic, vb_result.cc) and handed over as plain 16 kHz samples.
+void BatchRecognizer::push_resampled_chunk(int n_out, bool last) {
+    Engine &eng = model_->engine_for(id_);
+    Stream::Chunk ck;
+    ck.last = last;
+    ck.rate = resampler_.in_rate();
+    ck.n_out = n_out;
+    int pos = 0;
+    size_t k = 0;
+    bool fits = true;
+    for (; pos < n_out; k++) {
+        Call &c = calls_[k];
+        const long long take = std::min<long long>(c.n_out - c.taken, n_out - pos);
+        long long lo, hi;
+        resampler_.input_range(c.taken, c.taken + take - 1, &lo, &hi);
+        lo = std::max<long long>(lo, 0);
+        hi = std::min<long long>(hi, (long long)c.in.size() - 1);
+        Stream::Chunk::Seg g{(int)ck.raw.size(), (int)lo, (int)c.in.size(), (int)c.taken, pos, (int)take};
+        if (hi >= lo) ck.raw.insert(ck.raw.end(), c.in.begin() + lo, c.in.begin() + hi + 1);
+        ck.segs.push_back(g);
+        pos += (int)take;
+        if ((int)ck.segs.size() > Engine::kMaxResampleSegs || (int)ck.raw.size() > eng.max_resample_raw()) fits = false;
+    }
+    if (n_out == 0) ck.rate = 0;  // an empty last chunk needs no device pass
+    if (!fits) {  // host path for this chunk
+        ck.samples.resize(n_out);
+        int p2 = 0;
+        for (size_t j = 0; p2 < n_out; j++) {
+            Call &c = calls_[j];
+            const long long take = std::min<long long>(c.n_out - c.taken, n_out - p2);
+            std::vector<float> in(c.in.begin(), c.in.end()), out;
+            resampler_.resample_flush(in, &out);
+            for (long long t = 0; t < take; t++)
+                ck.samples[p2 + t] = (int16_t)std::lrintf(std::max(-32768.f, std::min(32767.f, out[(size_t)(c.taken + t)])));
+            p2 += (int)take;
+        }
+        ck.rate = 0;
+        ck.n_out = 0;
+        ck.raw.clear();
+        ck.segs.clear();
+    }
+    // consume
+    int left = n_out;
+    while (left > 0) {
+        Call &c = calls_.front();
+        const long long take = std::min<long long>(c.n_out - c.taken, left);
+        c.taken += take;
+        left -= (int)take;
+        if (c.taken == c.n_out) calls_.pop_front();
+    }
+    avail_ -= n_out;
+    eng.push_chunk(stream_, std::move(ck));
+}

@@ -1,6 +1,7 @@
 // batch_recognizer.h — BatchRecognizer: same public surface as the reference class
 // [REF src/batch_recognizer.h:28-53], rebuilt over vb::Engine streams.
 #pragma once
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -46,6 +47,15 @@ class BatchRecognizer {
     std::shared_ptr<vb::Stream> stream_;
     vb::LinearResampler resampler_;
     std::vector<int16_t> buffer_;
+    // device-side resampling: the calls whose 16 kHz output has not been handed over yet (raw input-rate samples)
+    struct Call {
+        std::vector<int16_t> in;
+        long long n_out = 0, taken = 0;
+    };
+    std::deque<Call> calls_;
+    long long avail_ = 0;  // 16 kHz samples the queued calls still hold
+    bool device_resample_ = false;
+    void push_resampled_chunk(int n_out, bool last);
     std::string front_;  // keeps the string returned by FrontResult alive until Pop
     std::string partial_;
     bool finished_ = false;

@@ -142,6 +142,42 @@ __global__ void __launch_bounds__(kFeatThreads) mfcc_kernel(FeatArgs a) {
     }
 }
 
+// K0: resampling of one step's non-16 kHz segments.  One CTA per (segment, 1024-output tile); the segment's phase table
+// (first tap index, tap count, weights) is read through the read-only path, the raw samples are staged by the host.  The
+// arithmetic is the host resampler's, operation for operation (vb_result.cc LinearResampler::resample_flush: products and
+// sums in fp32, taps in order, taps outside the call skipped, no fused multiply-add), so the int16 samples the feature
+// kernel sees are bit-identical to the host path's.
+constexpr int kResampleTile = 1024;
+__global__ void __launch_bounds__(256) resample_kernel(ResampleArgs a) {
+    const ResampleSeg sg = a.segs[blockIdx.x];
+    const ResampleTable tb = a.tables[sg.table];
+    const int16_t *raw = a.raw + sg.raw_off;
+    int16_t *dst = a.staging + (size_t)sg.lane * a.samples_per_chunk + sg.out_pos;
+    const int j0 = blockIdx.y * kResampleTile;
+    for (int j = j0 + threadIdx.x; j < sg.n_out && j < j0 + kResampleTile; j += blockDim.x) {
+        const long long so = (long long)sg.out_first + j;
+        const long long unit = so / tb.out_unit;
+        const int wrapped = (int)(so - unit * tb.out_unit);
+        const long long first = (long long)__ldg(tb.first_index + wrapped) + unit * tb.in_unit;
+        const int nt = __ldg(tb.n_taps + wrapped);
+        const float *w = tb.weights + (size_t)wrapped * tb.max_taps;
+        float acc = 0.f;
+        for (int i = 0; i < nt; i++) {
+            const long long idx = first + i;
+            if (idx >= 0 && idx < sg.n_in) acc = __fadd_rn(acc, __fmul_rn(__ldg(w + i), (float)raw[idx - sg.in_base]));
+        }
+        acc = fmaxf(-32768.f, fminf(32767.f, acc));
+        dst[j] = (int16_t)__float2int_rn(acc);
+    }
+}
+
+extern "C" cudaError_t vbk_resample(const ResampleArgs *a, cudaStream_t s) {
+    if (a->num_segs <= 0) return cudaSuccess;
+    dim3 grid(a->num_segs, (a->samples_per_chunk + kResampleTile - 1) / kResampleTile);
+    resample_kernel<<<grid, 256, 0, s>>>(*a);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t vbk_mfcc(const FeatArgs *a, cudaStream_t s) {
     if (a->num_lanes <= 0) return cudaSuccess;
     static int configured[16] = {};

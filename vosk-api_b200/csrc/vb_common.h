@@ -59,6 +59,7 @@ struct Config {
     float endpoint_rule5_seconds = 20.0f;  // reset_on_endpoint [REF src/batch_model.cc:72] with Kaldi's default endpoint rules and the
                                 // reference's empty silence-phone list: only rule 5 (utterance length) can fire; 0 = never
     int fe_priority = 0;        // CUDA stream priority of the front-end pipe relative to the search pipe (1 / 0 / -1)
+    int device_resample = 1;    // resample non-16 kHz input on the GPU (0: on the host, in accept_waveform)
     int pipeline_slots = 4;     // lane groups in flight on separate CUDA streams
     int num_gselect = 5;        // ivector.conf
     float min_post = 0.025f, posterior_scale = 0.1f, max_count = 100.0f;  // [REF src/model.cc:257]

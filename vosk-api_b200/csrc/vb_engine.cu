@@ -1,6 +1,8 @@
 // vb_engine.cu — per-GPU batch engine (host side).  See vb_engine.h for the reference objects it replaces.
 #include "vb_engine.h"
 
+#include "vb_result.h"
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -116,6 +118,10 @@ Engine::~Engine() {
     for (Slot &sl : slots_) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         if (sl.h_staging) cudaFreeHost(sl.h_staging);
+        if (sl.h_raw) cudaFreeHost(sl.h_raw);
+        if (sl.h_segs) cudaFreeHost(sl.h_segs);
+        if (sl.d_raw) cudaFree(sl.d_raw);
+        if (sl.d_segs) cudaFree(sl.d_segs);
         if (sl.h_lanes) cudaFreeHost(sl.h_lanes);
         if (sl.h_cs) cudaFreeHost(sl.h_cs);
         if (sl.h_path) cudaFreeHost(sl.h_path);
@@ -466,10 +472,42 @@ std::shared_ptr<Stream> Engine::open_stream() {
     return s;
 }
 
+// Phase table of Kaldi's LinearResample for one input rate, with the reference's filter settings
+// [REF src/batch_recognizer.cc:27-29]; called on the worker thread, tables are few and built once.
+int Engine::resample_table(int rate) {
+    auto it = resample_ids_.find(rate);
+    if (it != resample_ids_.end()) return it->second;
+    constexpr int kMaxTables = 16;
+    if ((int)resample_tables_.size() >= kMaxTables) throw std::runtime_error("too many distinct input sample rates");
+    LinearResampler rs((float)rate, 16000.0f, std::min((float)rate / 2, 8000.0f), 6);
+    const int U = rs.out_unit();
+    int max_taps = 0;
+    for (const auto &w : rs.weights()) max_taps = std::max(max_taps, (int)w.size());
+    std::vector<int> ntaps(U);
+    std::vector<float> w((size_t)U * max_taps, 0.f);
+    for (int i = 0; i < U; i++) {
+        ntaps[i] = (int)rs.weights()[i].size();
+        std::copy(rs.weights()[i].begin(), rs.weights()[i].end(), w.begin() + (size_t)i * max_taps);
+    }
+    ResampleTable t{rs.in_unit(), U, max_taps, dev_upload(allocs_, rs.first_index()), dev_upload(allocs_, ntaps), dev_upload(allocs_, w)};
+    if (!d_resample_tables_) d_resample_tables_ = dev_alloc<ResampleTable>(allocs_, kMaxTables);
+    resample_tables_.push_back(t);
+    VB_CUDA_CHECK(cudaMemcpy(d_resample_tables_, resample_tables_.data(), resample_tables_.size() * sizeof(ResampleTable), cudaMemcpyHostToDevice));
+    const int id = (int)resample_tables_.size() - 1;
+    resample_ids_[rate] = id;
+    return id;
+}
+
 void Engine::push(const std::shared_ptr<Stream> &s, const int16_t *samples, int n, bool last) {
     Stream::Chunk ch;
     ch.samples.assign(samples, samples + n);
     ch.last = last;
+    push_chunk(s, std::move(ch));
+}
+
+void Engine::push_chunk(const std::shared_ptr<Stream> &s, Stream::Chunk &&ch_in) {
+    Stream::Chunk ch = std::move(ch_in);
+    const bool last = ch.last;
     ch.t_push = std::chrono::steady_clock::now();
     {
         std::lock_guard<std::mutex> lk(mu_);
@@ -653,11 +691,13 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     std::stable_sort(lanes.begin(), lanes.end(), [](const Lane &x, const Lane &y) { return x.s->load > y.s->load; });
     sl.audio = 0;
     long long in_rows = 0;
+    size_t raw_used = 0;
+    int n_segs = 0;
     for (int i = 0; i < L; i++) {
         Stream &s = *lanes[i].s;
         const Stream::Chunk &ck = lanes[i].chunk;
         LaneDesc &d = sl.h_lanes[i];
-        const int n = s.resident ? ck.n_resident : (int)ck.samples.size();
+        const int n = s.resident ? ck.n_resident : ck.rate ? ck.n_out : (int)ck.samples.size();
         d.channel = s.channel;
         d.n_samples = n;
         d.carry = s.carry;
@@ -673,7 +713,23 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         d.dec_frames_before = s.dec_frames;
         d.src_row = s.resident ? (int)s.id : i;
         d.src_off = s.resident ? (int)s.samples : 0;
-        if (!s.resident && n) memcpy(sl.h_staging + (size_t)i * spc, ck.samples.data(), (size_t)n * sizeof(int16_t));
+        if (ck.rate && !s.resident) {
+            // resampled on the device: stage the raw samples and the segment list of this lane
+            if (!sl.h_raw) {
+                const size_t cap = (size_t)SL * max_resample_raw(), scap = (size_t)SL * kMaxResampleSegs;
+                VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_raw, cap * sizeof(int16_t)));
+                VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_segs, scap * sizeof(ResampleSeg)));
+                VB_CUDA_CHECK(cudaMalloc((void **)&sl.d_raw, cap * sizeof(int16_t)));
+                VB_CUDA_CHECK(cudaMalloc((void **)&sl.d_segs, scap * sizeof(ResampleSeg)));
+            }
+            const int table = resample_table(ck.rate);
+            if (!ck.raw.empty()) memcpy(sl.h_raw + raw_used, ck.raw.data(), ck.raw.size() * sizeof(int16_t));
+            for (const Stream::Chunk::Seg &g : ck.segs)
+                sl.h_segs[n_segs++] = ResampleSeg{i, (int)raw_used + g.raw_off, g.in_base, g.n_in, g.out_first, g.out_pos, g.n_out, table};
+            raw_used += ck.raw.size();
+        } else if (!s.resident && n) {
+            memcpy(sl.h_staging + (size_t)i * spc, ck.samples.data(), (size_t)n * sizeof(int16_t));
+        }
         in_rows += d.in_end_after - d.in_end_before + 2;
         sl.audio += n / 16000.0;
         // advance the host mirror of the stream state (a stream has at most one chunk in flight)
@@ -701,11 +757,20 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     }
     sl.launches = 0;
     sl.gemms = 0;
+    sl.resample_segs = n_segs;
     sl.timed = timing_;
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[0], st));
     VB_CUDA_CHECK(cudaMemcpyAsync(sl.d_lanes, sl.h_lanes, (size_t)L * sizeof(LaneDesc), cudaMemcpyHostToDevice, st));
     if (!d_resident)
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.d_staging, sl.h_staging, (size_t)L * spc * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    if (n_segs) {
+        // K0: the non-16 kHz lanes' chunks are produced on the device (after the staging copy, which they overwrite row-wise)
+        VB_CUDA_CHECK(cudaMemcpyAsync(sl.d_raw, sl.h_raw, raw_used * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        VB_CUDA_CHECK(cudaMemcpyAsync(sl.d_segs, sl.h_segs, (size_t)n_segs * sizeof(ResampleSeg), cudaMemcpyHostToDevice, st));
+        ResampleArgs ra{sl.d_segs, n_segs, sl.d_raw, d_resample_tables_, sl.d_staging, spc};
+        VB_CUDA_CHECK(vbk_resample(&ra, st));
+        sl.launches++;
+    }
     FeatArgs fa{sl.d_lanes, L, d_resident ? d_resident : sl.d_staging, d_resident ? (long long)resident_stride : (long long)spc, spc,
                 d_carry_, nodes_[0], ctx, feat_tab_};
     VB_CUDA_CHECK(vbk_mfcc(&fa, st));
@@ -909,6 +974,7 @@ void Engine::complete_step(Slot &sl) {
         stats_.lanes += L;
         stats_.launches += sl.launches;
         stats_.gemm_launches += sl.gemms;
+        stats_.resample_segments += sl.resample_segs;
         stats_.dec_launches++;
     }
     int n_last = 0;

@@ -10,6 +10,7 @@
 #include <condition_variable>
 #include <deque>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -71,6 +72,13 @@ struct Stream {
     struct Chunk {
         std::vector<int16_t> samples;
         int n_resident = 0;  // chunk length when the samples live in a device-resident matrix
+        // device-side resampling (stream opened at another rate): the chunk's n_out 16 kHz samples are produced on the GPU
+        // from the raw input-rate samples of the accept_waveform calls that overlap it (vb_kernels.h ResampleSeg)
+        struct Seg { int raw_off, in_base, n_in, out_first, out_pos, n_out; };
+        int rate = 0;        // input rate; 0 = samples[] already is 16 kHz
+        int n_out = 0;
+        std::vector<int16_t> raw;
+        std::vector<Seg> segs;
         bool last;
         std::chrono::steady_clock::time_point t_push;  // when the chunk's last sample was accepted
     };
@@ -92,7 +100,7 @@ struct StepStats {
     unsigned long long arcs_staged = 0, links = 0, lat_arcs = 0;
     unsigned long long phase[16] = {};  // search cycles per phase (cutoff, rank, log, gather, insert, closure, finalize, -) of the heavy / light CTAs  // arcs parked below the running cutoff, links logged, lattice arcs kept
     double t_feat = 0, t_ivec = 0, t_nnet = 0, t_dec = 0, t_total = 0;  // device ms (only when timing enabled)
-    long long dec_launches = 0, gemm_launches = 0;
+    long long dec_launches = 0, gemm_launches = 0, resample_segments = 0;
     double host_launch_ms = 0;  // host time spent enqueueing steps
 };
 
@@ -107,6 +115,10 @@ class Engine {
     std::shared_ptr<Stream> open_stream();
     // copies the samples; n <= samples_per_chunk unless it is the (possibly empty) last chunk
     void push(const std::shared_ptr<Stream> &s, const int16_t *samples, int n, bool last);
+    void push_chunk(const std::shared_ptr<Stream> &s, Stream::Chunk &&ch);  // a prepared chunk (16 kHz samples, or raw segments to resample)
+    // limits of one device-resampled chunk (a chunk beyond them is resampled on the host by the recognizer)
+    static constexpr int kMaxResampleSegs = 64;
+    int max_resample_raw() const { return samples_per_chunk() * 3 + 4096; }
     void wait();  // until every chunk pushed so far is decoded and its result delivered
     StepStats stats();
     // latency from a chunk's acceptance to its step's results (partial / final) being available: {p50, p90, p99, mean, count} in ms
@@ -144,6 +156,8 @@ class Engine {
         cudaEvent_t ev[6] = {};
         cudaEvent_t done = nullptr;
         int16_t *d_staging = nullptr, *h_staging = nullptr;
+        int16_t *d_raw = nullptr, *h_raw = nullptr;          // raw input-rate samples of the step's resampled lanes (allocated on first use)
+        ResampleSeg *d_segs = nullptr, *h_segs = nullptr;
         LaneDesc *d_lanes = nullptr, *h_lanes = nullptr;
         NodeLane *d_table = nullptr;
         int *d_rowoff = nullptr;
@@ -160,8 +174,9 @@ class Engine {
         std::vector<Lane> lanes;
         bool busy = false, timed = false;
         double audio = 0;
-        long long launches = 0, gemms = 0;
+        long long launches = 0, gemms = 0, resample_segs = 0;
     };
+    int resample_table(int rate);  // index of the device phase table of an input rate (built on first use)
     void worker();
     void launch_step(Slot &sl, const int16_t *d_resident, int resident_stride);
     void complete_step(Slot &sl);
@@ -187,6 +202,9 @@ class Engine {
     NodeDesc *d_nodes_ = nullptr;
     GraphDev graph_{};
     std::vector<void *> allocs_;
+    std::map<int, int> resample_ids_;
+    std::vector<ResampleTable> resample_tables_;
+    ResampleTable *d_resample_tables_ = nullptr;
     // per channel / per step state
     IvecState iv_state_{};
     int16_t *d_carry_ = nullptr;

@@ -33,6 +33,35 @@ struct FeatArgs {
     FeatTables tab;
 };
 
+// ---------------- K0: input resampling to 16 kHz (streams opened at another rate) ----------------
+// Kaldi LinearResample with flush=true per accept_waveform call [REF src/batch_recognizer.cc:27-29,157-158]: every call is
+// filtered on its own (zeros outside the call).  A chunk of 16 kHz samples is therefore a concatenation of segments, each
+// the share one call contributes; the host stages the raw input-rate samples the segment's taps can reach.
+struct ResampleTable {       // device pointers; one per distinct input rate
+    int in_unit, out_unit, max_taps;
+    const int *first_index;  // [out_unit]
+    const int *n_taps;       // [out_unit]
+    const float *weights;    // [out_unit][max_taps]
+};
+struct ResampleSeg {
+    int lane;       // staging row the samples go to
+    int raw_off;    // first staged raw sample of the segment in the step's raw buffer
+    int in_base;    // call-relative index of that sample
+    int n_in;       // samples of the whole call (taps beyond it read zero)
+    int out_first;  // call-relative index of the segment's first output sample
+    int out_pos;    // position of that sample in the lane's chunk
+    int n_out;
+    int table;
+};
+struct ResampleArgs {
+    const ResampleSeg *segs;  // device
+    int num_segs;
+    const int16_t *raw;       // device: raw input-rate samples of the step
+    const ResampleTable *tables;
+    int16_t *staging;         // [lanes][samples_per_chunk]
+    int samples_per_chunk;
+};
+
 // ---------------- K1c: online CMN + i-vector ----------------
 struct IvecModel {           // device pointers
     int feat_dim, ivec_dim, num_gauss, splice_dim;
@@ -186,6 +215,7 @@ struct DecArgs {
 extern "C" {
 int vbk_feat_smem_bytes(int samples_per_chunk);
 cudaError_t vbk_mfcc(const FeatArgs *a, cudaStream_t s);
+cudaError_t vbk_resample(const ResampleArgs *a, cudaStream_t s);
 cudaError_t vbk_ivector(const IvecArgs *a, cudaStream_t s);
 cudaError_t vbk_nnet_plan(const NnetPlanArgs *a, cudaStream_t s);
 cudaError_t vbk_gemm_fp32(const GemmArgs *a, cudaStream_t s);

@@ -317,6 +317,7 @@ void Model::load(const std::string &d) {
     conf = read_conf(d + "/conf/model.conf");
     // am/final.mdl: Kaldi's TransitionModel + nnet3 file, or the generator's tensor container
     const std::string mdl = d + "/am/final.mdl";
+    if (!std::ifstream(mdl, std::ios::binary)) throw std::runtime_error("cannot open " + mdl);
     if (file_is_vbt(mdl)) load_vbt_am(mdl);
     else if (kaldi_is_binary(mdl)) load_kaldi_am(mdl);
     else throw std::runtime_error("unrecognised acoustic model file (neither Kaldi binary nor VBT1): " + mdl);

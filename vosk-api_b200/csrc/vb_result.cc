@@ -147,20 +147,30 @@ LinearResampler::LinearResampler(float rate_in, float rate_out, float cutoff, in
     }
 }
 
+long long LinearResampler::num_output(long long n_in) const {
+    if (identity_) return n_in;
+    const long long tick = std::lcm((long long)in_rate_, (long long)out_rate_);
+    const long long ticks_in = tick / in_rate_, ticks_out = tick / out_rate_;
+    const long long interval = n_in * ticks_in;
+    if (interval <= 0) return 0;
+    long long last = interval / ticks_out;
+    if (last * ticks_out == interval) last--;
+    return last + 1;
+}
+
+void LinearResampler::input_range(long long t0, long long t1, long long *lo, long long *hi) const {
+    const long long u0 = t0 / out_unit_, u1 = t1 / out_unit_;
+    const int w0 = (int)(t0 - u0 * out_unit_), w1 = (int)(t1 - u1 * out_unit_);
+    *lo = first_index_[w0] + u0 * in_unit_;
+    *hi = first_index_[w1] + u1 * in_unit_ + (long long)weights_[w1].size() - 1;
+}
+
 void LinearResampler::resample_flush(const std::vector<float> &in, std::vector<float> *out) const {
     if (identity_) {
         *out = in;
         return;
     }
-    const long long tick = std::lcm((long long)in_rate_, (long long)out_rate_);
-    const long long ticks_in = tick / in_rate_, ticks_out = tick / out_rate_;
-    const long long interval = (long long)in.size() * ticks_in;
-    long long n_out = 0;
-    if (interval > 0) {
-        long long last = interval / ticks_out;
-        if (last * ticks_out == interval) last--;
-        n_out = last + 1;
-    }
+    const long long n_out = num_output((long long)in.size());
     out->assign((size_t)n_out, 0.f);
     const long long n_in = (long long)in.size();
     for (long long so = 0; so < n_out; so++) {

@@ -30,6 +30,15 @@ class LinearResampler {
     LinearResampler(float rate_in, float rate_out, float cutoff, int num_zeros);
     void resample_flush(const std::vector<float> &in, std::vector<float> *out) const;
     bool identity() const { return identity_; }
+    // number of output samples one flushed call of n_in input samples produces (LinearResample::GetNumOutputSamples)
+    long long num_output(long long n_in) const;
+    // input indices [*lo, *hi] (call coordinates, not yet clipped to the call) that outputs t0..t1 of one call read
+    void input_range(long long t0, long long t1, long long *lo, long long *hi) const;
+    int in_rate() const { return in_rate_; }
+    int in_unit() const { return in_unit_; }
+    int out_unit() const { return out_unit_; }
+    const std::vector<int> &first_index() const { return first_index_; }
+    const std::vector<std::vector<float>> &weights() const { return weights_; }
 
    private:
     int in_rate_, out_rate_, in_unit_, out_unit_;

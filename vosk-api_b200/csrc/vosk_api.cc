@@ -147,7 +147,7 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model) { return model ? (
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
     if (!model || !out) return 0;
     BatchModel *bm = (BatchModel *)model;
-    double v[37] = {0};
+    double v[38] = {0};
     for (size_t i = 0; i < bm->num_engines(); i++) {
         vb::StepStats s = bm->engine(i).stats();
         v[0] += s.audio_seconds; v[1] += s.steps; v[2] += s.lanes; v[3] += s.launches;
@@ -156,8 +156,9 @@ int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
         v[13] += s.lane_cycles_sum; v[14] = std::max(v[14], (double)s.lane_cycles_max); v[15] = std::max(v[15], (double)s.max_tokens); v[16] += s.lane_launches; v[17] += s.host_launch_ms;
         v[18] += s.arcs_staged; v[19] += s.links; v[20] += s.lat_arcs;
         for (int k = 0; k < 16; k++) v[21 + k] += s.phase[k];
+        v[37] += s.resample_segments;
     }
-    int k = n < 37 ? n : 37;
+    int k = n < 38 ? n : 38;
     memcpy(out, v, k * sizeof(double));
     return k;
 }
