@@ -291,11 +291,48 @@ def recognize(model, wave, frames_per_chunk=51, stages=False, rc=None, **over):
     return text
 
 
-def recognize_segments(model, wave, frames_per_chunk=51, rule5_seconds=20.0, rc=None, **over):
-    """The batch path with reset_on_endpoint [REF src/batch_model.cc:72]: Kaldi's default endpoint rules with the reference's
-    empty silence-phone list leave rule 5 (decoded length >= 20 s), tested after every chunk; a segment is finalized there,
-    the search starts over on the next chunk while features and i-vector carry on, and result times are offset by the
-    segment start (GetTimeOffsetSeconds [REF src/batch_recognizer.cc:146-147]).  Returns the list of result texts."""
+# Kaldi OnlineEndpointConfig defaults, rules 1-4: (must_contain_nonsilence, min_trailing_silence, max_relative_cost, min_utterance_length)
+ENDPOINT_RULES = [(False, 5.0, np.inf, 0.0), (True, 0.5, 2.0, 0.0), (True, 1.0, 8.0, 0.0), (True, 2.0, np.inf, 0.0)]
+
+
+def endpoint_detected(model, dec, rules, silence_phones):
+    """kaldi::EndpointDetected(config, tmodel, frame_shift, decoder) on a decoder that has consumed the log-likelihoods `dec`
+    was run on [REF src/recognizer.cc:318]: TrailingSilenceLength (best path without final costs, emitting arcs of silence
+    phones counted back from the newest frame), FinalRelativeCost, then rules 1-4 in single precision."""
+    g = model["graph"]
+    lo, hi = int(dec["offsets"][-2]), int(dec["offsets"][-1])
+    if hi <= lo:
+        return False
+    cost = dec["cost"][lo:hi]
+    i = lo + int(np.argmin(cost))
+    fin = g["final"][dec["state"][lo:hi]].astype(np.float32)
+    with_final = (cost + fin)[np.isfinite(fin)]
+    relative = np.float32(with_final.min() - cost.min()) if len(with_final) else np.float32(np.inf)
+    tid2phone = model["nnet"]["tid2phone"]
+    sil = 0
+    while i >= 0 and dec["arc"][i] >= 0:
+        il = int(g["arc_ilabel"][dec["arc"][i]])
+        if il != 0:
+            if int(tid2phone[il]) in silence_phones:
+                sil += 1
+            else:
+                break
+        i = int(dec["prev"][i])
+    shift = np.float32(0.03)
+    utt, trail = np.float32(dec["frames"]) * shift, np.float32(sil) * shift
+    nonsil = utt > trail
+    for must, min_trail, max_rel, min_utt in rules:
+        if (nonsil or not must) and trail >= np.float32(min_trail) and relative <= np.float32(min(max_rel, 1e30)) and utt >= np.float32(min_utt):
+            return True
+    return False
+
+
+def recognize_segments(model, wave, frames_per_chunk=51, rule5_seconds=20.0, rc=None, silence_phones=None, rules=None, **over):
+    """The batch path with reset_on_endpoint [REF src/batch_model.cc:72]: Kaldi's endpoint rules tested after every chunk; a
+    segment is finalized there, the search starts over on the next chunk while features and i-vector carry on, and result
+    times are offset by the segment start (GetTimeOffsetSeconds [REF src/batch_recognizer.cc:146-147]).  With an empty
+    silence-phone list only rule 5 (decoded length >= 20 s) can fire; with silence_phones (a set of phone ids) rules 1-4 run
+    too (`rules` defaults to Kaldi's).  Returns the list of result texts."""
     ctx = model_context(model)
     feats = mfcc(wave)
     ends, avail, iv_index = chunk_plan(len(wave), frames_per_chunk, ctx)
@@ -307,9 +344,15 @@ def recognize_segments(model, wave, frames_per_chunk=51, rule5_seconds=20.0, rc=
     for k, a in enumerate(avail):
         last = k == len(avail) - 1
         dec = len(ll) if last else ((int(a) - ctx + 2) // 3 if a > ctx else 0)
-        if last or (rule5 and dec - seg_start >= rule5):
+        close = last or (rule5 and dec - seg_start >= rule5)
+        d = None
+        if not close and silence_phones and dec > seg_start:
+            d = decode(model, ll[seg_start:dec], **over)
+            close = endpoint_detected(model, d, rules or ENDPOINT_RULES, silence_phones)
+        if close:
             seg = ll[seg_start:dec]
-            d = decode(model, seg, **over) if len(seg) else dict(best_arcs=np.zeros(0, dtype=np.int32))
+            if d is None:
+                d = decode(model, seg, **over) if len(seg) else dict(best_arcs=np.zeros(0, dtype=np.int32))
             texts.append(result_json(model, d["best_arcs"], offset=float(np.float32(seg_start * 0.03)), rc=rc))
             seg_start = dec
     return texts

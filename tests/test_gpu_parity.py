@@ -353,3 +353,44 @@ def test_device_resampling_equals_the_host_resampler(model_root, oracle_lib, rat
         n = lib.vosk_b200_resample(x.ctypes.data, len(x), float(rate), out.ctypes.data, len(out))
         pieces.append(np.clip(np.rint(out[:n]), -32768, 32767).astype(np.int16))
     _check_stream(model, oracle_lib, np.concatenate(pieces), dev[1], 51)
+
+
+def test_silence_endpoint_rules_segment_like_the_oracle(model_root, oracle_lib, tmp_path):
+    """with --endpoint.silence-phones in model.conf (as real Vosk models have) Kaldi's endpoint rules 1-4 run
+    after every chunk: trailing silence of the best path + final relative cost, kaldi::EndpointDetected [REF src/recognizer.cc:318].
+    The device computes both per chunk (partial kernel), the host applies the rules and closes the segment before the stream's
+    next chunk; every segment gives its own result with its time offset.  A random-init model has no real silence, so twenty
+    phones are declared silent and the thresholds are shortened: on these streams some chunks end a segment and others do not."""
+    import shutil
+    import vbmodel
+    import vosk
+    src = model_root("tiny")
+    mdir = str(tmp_path / "model")
+    shutil.copytree(src, mdir)
+    silence = set(range(1, 21))
+    rules = [(False, 1.2, np.inf, 0.0), (True, 0.3, 4.0, 0.0), (True, 0.45, 10.0, 1.5), (True, 0.6, np.inf, 0.0)]
+    with open(mdir + "/conf/model.conf", "a") as f:
+        f.write("--endpoint.silence-phones=" + ":".join(str(p) for p in sorted(silence)) + "\n")
+        for r, (must, trail, rel, utt) in enumerate(rules, start=1):
+            f.write(f"--endpoint.rule{r}.must-contain-nonsilence={'true' if must else 'false'}\n")
+            f.write(f"--endpoint.rule{r}.min-trailing-silence={trail}\n")
+            f.write(f"--endpoint.rule{r}.max-relative-cost={'inf' if np.isinf(rel) else rel}\n")
+            f.write(f"--endpoint.rule{r}.min-utterance-length={utt}\n")
+    model = vbmodel.load_model_dir(mdir)
+    waves = [vbmodel.synth_audio(s, 2300 + i) for i, s in enumerate([6.3, 3.1, 9.0, 0.4])]
+    want = [oracle_lib.recognize_segments(model, w, silence_phones=silence, rules=rules) for w in waves]
+    assert max(len(x) for x in want) >= 3 and sum(len(x) for x in want) < 25, [len(x) for x in want]  # the rules fire, but not at every chunk
+    for opts in ("num-channels=4,max-batch-size=4,max-seconds=12", "num-channels=2,max-batch-size=2,max-seconds=12,partials=1"):
+        m = vosk.BatchModel(mdir, options=opts)
+        recs = [vosk.BatchRecognizer(m, 16000.0) for _ in waves]
+        helpers.feed_round_robin(recs, waves, 8000)
+        m.Wait()
+        for r, x in zip(recs, want):
+            got = []
+            while True:
+                t = r.Result()
+                if not t:
+                    break
+                got.append(t)
+            assert got == x
+        del recs, m

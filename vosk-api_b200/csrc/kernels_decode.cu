@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 int z = -1;
                 if (cost < next_cutoff) {
                     const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
-                    const int state = cd.z & ~kNextHasEps;
+                    const int state = cd.z & ~kArcFlagMask;
                     unsigned long long old;
                     const int slot = table_insert(c, state, pk, &old);
                     if (slot >= 0) {
@@ -1085,25 +1085,43 @@ __global__ void __launch_bounds__(32) partial_kernel(DecArgs a) {
     if (ln.dec_last) return;
     const int ch = ln.channel;
     const DecChannelState cs = a.cs[ch];
-    int *out = a.partial_words + (size_t)l * kPartialCap;
+    int *out = a.partial_words ? a.partial_words + (size_t)l * kPartialCap : nullptr;
     const size_t tbase = (size_t)ch * 2 * a.tok_cap + (size_t)cs.parity * a.tok_cap;
     const float *t_cost = a.tok_cost + tbase;
     const int *t_arc = a.tok_arc + tbase, *t_prev = a.tok_prev + tbase;
+    const int *t_state = a.tok_state + tbase;
     unsigned long long m = kValMax;
-    for (int i = lane; i < cs.n_cur; i += 32) m = min(m, ((unsigned long long)ford(t_cost[i]) << 32) | (unsigned)i);
-    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    unsigned mf = 0xffffffffu;  // best cost + final cost (ordered)
+    for (int i = lane; i < cs.n_cur; i += 32) {
+        const float c = t_cost[i];
+        m = min(m, ((unsigned long long)ford(c) << 32) | (unsigned)i);
+        if (a.endp_silence) {
+            const float fc = __ldg(a.g.final_cost + t_state[i]);
+            if (fc != INFINITY) mf = min(mf, ford(c + fc));
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+        mf = min(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+    }
     if (lane != 0) return;
-    int n = 0;
+    int n = 0, n_sil = 0;
+    bool counting = true;  // trailing silence: emitting arcs of silence phones, back from the newest frame to the first other phone
     if (m != kValMax) {
         const int *log_prev = a.log_prev + (size_t)ch * a.log_cap, *log_arc = a.log_arc + (size_t)ch * a.log_cap;
         int i = (int)(unsigned)m, li = -1;
         for (int guard = 0; guard < a.tok_cap; guard++) {  // epsilon predecessors live in the same token list
             const int arc = t_arc[i];
             if (arc < 0) break;
-            const int ol = __ldg(a.g.arcs + arc).w & ~kNextHasEps;
-            if (ol != 0) {
+            const int4 av = __ldg(a.g.arcs + arc);
+            const int ol = av.w & ~kArcFlagMask;
+            if (ol != 0 && out) {
                 if (n < kPartialCap) out[n] = ol;
                 n++;
+            }
+            if (counting && av.z >= 0) {
+                if (av.w & kArcSilence) n_sil++;
+                else counting = false;
             }
             const int pv = t_prev[i];
             if (pv <= -2) {
@@ -1113,22 +1131,32 @@ __global__ void __launch_bounds__(32) partial_kernel(DecArgs a) {
                 break;
             }
         }
-        while (li >= 0) {
+        while (li >= 0 && (out || counting)) {
             const int arc = log_arc[li];
             if (arc < 0) break;
-            const int ol = __ldg(a.g.arcs + arc).w & ~kNextHasEps;
-            if (ol != 0) {
+            const int4 av = __ldg(a.g.arcs + arc);
+            const int ol = av.w & ~kArcFlagMask;
+            if (ol != 0 && out) {
                 if (n < kPartialCap) out[n] = ol;
                 n++;
+            }
+            if (counting && av.z >= 0) {
+                if (av.w & kArcSilence) n_sil++;
+                else counting = false;
             }
             li = log_prev[li];
         }
     }
-    a.partial_count[l] = n;
+    if (out) a.partial_count[l] = n;
+    if (a.endp_silence) {
+        a.endp_silence[l] = n_sil;
+        // FinalRelativeCost of LatticeFasterDecoder: best (cost + final) - best cost; infinity without a final token
+        a.endp_relcost[l] = (m == kValMax || mf == 0xffffffffu) ? INFINITY : unord(mf) - unord((unsigned)(m >> 32));
+    }
 }
 
 extern "C" cudaError_t vbk_partial(const DecArgs *a, cudaStream_t s) {
-    if (!a->partial_words || a->lane_end <= a->lane_begin) return cudaSuccess;
+    if ((!a->partial_words && !a->endp_silence) || a->lane_end <= a->lane_begin) return cudaSuccess;
     partial_kernel<<<a->lane_end - a->lane_begin, 32, 0, s>>>(*a);
     return cudaGetLastError();
 }

@@ -58,6 +58,14 @@ struct Config {
     int heavy_threads = 1024, mid_threads = 512, light_threads = 256;
     float endpoint_rule5_seconds = 20.0f;  // reset_on_endpoint [REF src/batch_model.cc:72] with Kaldi's default endpoint rules and the
                                 // reference's empty silence-phone list: only rule 5 (utterance length) can fire; 0 = never
+    // Silence endpointing (Kaldi OnlineEndpointConfig rules 1-4), active when model.conf names --endpoint.silence-phones:
+    // after every chunk the best path's trailing silence and the final relative cost are tested as kaldi::EndpointDetected does
+    // [REF src/recognizer.cc:318], [REF src/model.cc:142-145]; defaults are Kaldi's.
+    char endpoint_silence_phones[512] = "";
+    int ep_must_contain_nonsilence[4] = {0, 1, 1, 1};
+    float ep_min_trailing_silence[4] = {5.0f, 0.5f, 1.0f, 2.0f};
+    float ep_max_relative_cost[4] = {1e30f, 2.0f, 8.0f, 1e30f};
+    float ep_min_utterance_length[4] = {0.f, 0.f, 0.f, 0.f};
     int fe_priority = 0;        // CUDA stream priority of the front-end pipe relative to the search pipe (1 / 0 / -1)
     int device_resample = 1;    // resample non-16 kHz input on the GPU (0: on the host, in accept_waveform)
     int pipeline_slots = 4;     // lane groups in flight on separate CUDA streams

@@ -127,6 +127,7 @@ Engine::~Engine() {
         if (sl.h_path) cudaFreeHost(sl.h_path);
         if (sl.h_load) cudaFreeHost(sl.h_load);
         if (sl.h_partial) cudaFreeHost(sl.h_partial);
+        if (sl.h_endp) cudaFreeHost(sl.h_endp);
         if (sl.h_lat_hdr) cudaFreeHost(sl.h_lat_hdr);
         if (sl.h_lat_links) cudaFreeHost(sl.h_lat_links);
         if (sl.h_lat_final) cudaFreeHost(sl.h_lat_final);
@@ -298,6 +299,26 @@ void Engine::upload_model() {
         }
     }
     // ---- decoding graph: one 16-byte record per arc ----
+    std::vector<char> silence;  // endpointing silence phones ("1:2:3") -> flag per phone id
+    {
+        int v = 0;
+        bool have = false;
+        for (const char *c = cfg_.endpoint_silence_phones;; c++) {
+            if (*c >= '0' && *c <= '9') {
+                v = v * 10 + (*c - '0');
+                have = true;
+            } else {
+                if (have) {
+                    if ((size_t)v >= silence.size()) silence.resize((size_t)v + 1, 0);
+                    silence[(size_t)v] = 1;
+                    endpointing_ = true;
+                }
+                v = 0;
+                have = false;
+                if (!*c) break;
+            }
+        }
+    }
     {
         const Graph &g = m.graph;
         std::vector<int4> arcs((size_t)g.num_arcs);
@@ -306,8 +327,10 @@ void Engine::upload_model() {
             memcpy(&wbits, &g.arc_w[a], 4);
             const int nx = g.arc_next[a];
             const bool next_has_eps = g.eps_begin[nx] < g.e_begin[nx + 1];
-            if (g.arc_olabel[a] >= kNextHasEps || nx >= kNextHasEps) throw std::runtime_error("graph too large for the packed arc record");
-            arcs[a] = make_int4(wbits, nx, g.arc_pdf[a], g.arc_olabel[a] | (next_has_eps ? kNextHasEps : 0));
+            if (g.arc_olabel[a] >= kArcSilence || nx >= kArcSilence) throw std::runtime_error("graph too large for the packed arc record");
+            const int il = g.arc_ilabel[a];
+            const bool sil = il > 0 && il < (int)m.tid2phone.size() && m.tid2phone[il] >= 0 && m.tid2phone[il] < (int)silence.size() && silence[m.tid2phone[il]];
+            arcs[a] = make_int4(wbits, nx, g.arc_pdf[a], g.arc_olabel[a] | (next_has_eps ? kNextHasEps : 0) | (sil ? kArcSilence : 0));
         }
         std::vector<int2> sa((size_t)g.num_states + 1);
         for (int s2 = 0; s2 < g.num_states; s2++) sa[s2] = make_int2(g.e_begin[s2], g.eps_begin[s2]);
@@ -435,6 +458,11 @@ void Engine::alloc_state() {
         sd = dec_;
         sd.out_table = sl.d_table + (size_t)(nn - 1) * L;
         sd.lane_load = sl.d_load;
+        if (endpointing_) {
+            sd.endp_silence = dev_alloc<int>(allocs_, (size_t)L, 0);
+            sd.endp_relcost = dev_alloc<float>(allocs_, (size_t)L, 0);
+            VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_endp, (size_t)L * 2 * sizeof(int)));
+        }
         if (cfg_.partials) {
             sd.partial_words = dev_alloc<int>(allocs_, (size_t)L * kPartialCap, 0);
             sd.partial_count = dev_alloc<int>(allocs_, (size_t)L, 0);
@@ -516,7 +544,7 @@ void Engine::push_chunk(const std::shared_ptr<Stream> &s, Stream::Chunk &&ch_in)
         s->pending.push_back(std::move(ch));
         s->pending_chunks.fetch_add(1);
         outstanding_++;
-        if (!s->queued) {
+        if (!s->queued && !s->in_flight) {
             s->queued = true;
             ready_.push_back(s);
         }
@@ -621,6 +649,24 @@ void Engine::worker() {
                             free_channels_.push_back(ln.s->channel);
                             ln.s->channel = -1;
                         }
+                        if (endpointing_ && !ln.s->resident) {
+                            // the stream was held back until the endpoint decision of this chunk: a detected endpoint first
+                            // closes the segment with an empty chunk, then the stream goes on (a new segment) with what is queued
+                            if (ln.endpoint && !ln.chunk.last) {
+                                Stream::Chunk fin;
+                                fin.last = false;
+                                fin.close_segment = true;
+                                fin.t_push = std::chrono::steady_clock::now();
+                                ln.s->pending.push_front(std::move(fin));
+                                ln.s->pending_chunks.fetch_add(1);
+                                outstanding_++;
+                            }
+                            ln.s->in_flight = false;
+                            if (!ln.s->pending.empty() && !ln.s->queued) {
+                                ln.s->queued = true;
+                                ready_.push_back(ln.s);
+                            }
+                        }
                     }
                     outstanding_ -= (long long)old.lanes.size();
                 }
@@ -653,7 +699,10 @@ void Engine::worker() {
                 ln.s = s;
                 ln.chunk = std::move(s->pending.front());
                 s->pending.pop_front();
-                if (!s->pending.empty()) again.push_back(s);  // next chunk: a later step (one chunk per stream per step)
+                if (endpointing_ && !s->resident) {
+                    s->in_flight = true;  // the next chunk is queued when this one has completed (endpoint decision)
+                    s->queued = false;
+                } else if (!s->pending.empty()) again.push_back(s);  // next chunk: a later step (one chunk per stream per step)
                 else s->queued = false;
                 sl.lanes.push_back(std::move(ln));
             }
@@ -743,7 +792,8 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         lanes[i].dec_frames_after = s.dec_frames;
         // segmentation: a segment ends with the stream, or at the first chunk boundary where the decoded length reaches rule 5
         const int rule5 = cfg_.endpoint_rule5_seconds > 0 ? (int)std::ceil(cfg_.endpoint_rule5_seconds / 0.03 - 1e-6) : 0;
-        const bool seg_end = ck.last || (rule5 > 0 && s.dec_frames - s.seg_start >= rule5);
+        const bool seg_end = ck.last || ck.close_segment || (rule5 > 0 && s.dec_frames - s.seg_start >= rule5);
+        lanes[i].seg_start = s.seg_start;
         d.dec_first = !s.seg_open;
         d.dec_last = seg_end;
         lanes[i].seg_end = seg_end;
@@ -853,7 +903,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         da.scratch_base = tier_scratch_[t];
         VB_CUDA_CHECK(vbk_decode(&da, tier_threads[t], ts));
         sl.launches++;
-        if (cfg_.partials) {  // the partial walk reads the lane's tokens: it must precede the lane's next search, so it rides the tier pipe
+        if (cfg_.partials || endpointing_) {  // the partial walk reads the lane's tokens: it must precede the lane's next search, so it rides the tier pipe
             VB_CUDA_CHECK(vbk_partial(&da, ts));
             sl.launches++;
         }
@@ -867,6 +917,10 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     if (cfg_.partials && n_last < L) {
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_partial, sl.dec.partial_words, (size_t)L * kPartialCap * sizeof(int), cudaMemcpyDeviceToHost, st));
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_partial + (size_t)L * kPartialCap, sl.dec.partial_count, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    if (endpointing_ && n_last < L) {
+        VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_endp, sl.dec.endp_silence, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
+        VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_endp + L, sl.dec.endp_relcost, (size_t)L * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[4], st));
     // results of finished lanes
@@ -909,6 +963,21 @@ void Engine::complete_step(Slot &sl) {
             if (latencies_ms_.size() < (1u << 22)) latencies_ms_.push_back(std::chrono::duration<float, std::milli>(now - lanes[i].chunk.t_push).count());
         }
     }
+    if (endpointing_)
+        for (int i = 0; i < L; i++) {
+            // kaldi::EndpointDetected on the state after this chunk: rules 1-4 (rule 5 is applied when a chunk is launched)
+            lanes[i].endpoint = false;
+            const int frames = lanes[i].dec_frames_after - lanes[i].seg_start;
+            if (lanes[i].seg_end || frames <= 0 || lanes[i].s->resident) continue;
+            const float frame_shift = 0.03f;
+            const float utterance_length = frames * frame_shift, trailing_silence = sl.h_endp[i] * frame_shift;
+            float relative_cost;
+            memcpy(&relative_cost, &sl.h_endp[L + i], 4);
+            const bool contains_nonsilence = utterance_length > trailing_silence;
+            for (int r = 0; r < 4 && !lanes[i].endpoint; r++)
+                lanes[i].endpoint = (contains_nonsilence || !cfg_.ep_must_contain_nonsilence[r]) && trailing_silence >= cfg_.ep_min_trailing_silence[r] &&
+                                    relative_cost <= cfg_.ep_max_relative_cost[r] && utterance_length >= cfg_.ep_min_utterance_length[r];
+        }
     if (cfg_.partials)
         for (int i = 0; i < L; i++) {
             if (lanes[i].seg_end) continue;

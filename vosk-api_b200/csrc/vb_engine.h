@@ -60,6 +60,7 @@ struct Stream {
     uint64_t id = 0;
     int channel = -1;
     bool started = false, finished = false, queued = false;
+    bool in_flight = false;  // silence endpointing: the stream's next chunk waits for the decision taken when this one completes
     int64_t samples = 0;     // samples handed to the GPU so far
     int frames = 0;          // MFCC frames computed so far
     int iv_end = 0, in_end = 0, dec_frames = 0, carry = 0;
@@ -80,6 +81,7 @@ struct Stream {
         std::vector<int16_t> raw;
         std::vector<Seg> segs;
         bool last;
+        bool close_segment = false;  // an empty chunk injected after a silence endpoint: final pass, traceback and result of the segment
         std::chrono::steady_clock::time_point t_push;  // when the chunk's last sample was accepted
     };
     // partial result (partials=1): output labels of the best path so far, oldest first
@@ -140,6 +142,8 @@ class Engine {
         Stream::Chunk chunk;
         int dec_frames_after = 0;
         bool seg_end = false;    // this chunk closes a segment: a result is due
+        int seg_start = 0;       // decoder frames before the segment this chunk belongs to
+        bool endpoint = false;   // set on completion: a silence endpoint was detected after this chunk
         float seg_offset = 0.f;
         int seg_index = 0;
     };
@@ -167,6 +171,7 @@ class Engine {
         int *h_path = nullptr;
         int *d_load = nullptr, *h_load = nullptr;
         int *h_partial = nullptr;  // [L][kPartialCap] words + [L] counts
+        int *h_endp = nullptr;     // [L] trailing silence frames + [L] final relative cost (float bits)
         LatHeader *h_lat_hdr = nullptr;
         int4 *h_lat_links = nullptr;  // pinned bounce buffers for one finished lane's lattice
         int2 *h_lat_final = nullptr;
@@ -202,6 +207,7 @@ class Engine {
     NodeDesc *d_nodes_ = nullptr;
     GraphDev graph_{};
     std::vector<void *> allocs_;
+    bool endpointing_ = false;  // silence rules 1-4 active (model.conf names silence phones)
     std::map<int, int> resample_ids_;
     std::vector<ResampleTable> resample_tables_;
     ResampleTable *d_resample_tables_ = nullptr;

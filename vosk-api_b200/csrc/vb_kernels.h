@@ -146,7 +146,9 @@ struct LatHeader {
     int error, frames, pad0, pad1;
 };
 constexpr int kPartialCap = 256;
-constexpr int kNextHasEps = 0x40000000;  // flag in the olabel field of a device arc record (labels and state ids stay below 2^30)
+constexpr int kNextHasEps = 0x40000000;  // flag in the olabel field of a device arc record (labels and state ids stay below 2^29)
+constexpr int kArcSilence = 0x20000000;  // same field: the arc's transition-id belongs to an endpointing silence phone
+constexpr int kArcFlagMask = kNextHasEps | kArcSilence;
 constexpr int kEpsLinkFlag = 0x40000000;  // set in the destination field of an epsilon link
 struct DecArgs {
     const LaneDesc *lanes;
@@ -202,6 +204,8 @@ struct DecArgs {
     // partial results (partials != 0): output labels of the current best path of every unfinished lane, newest first
     int *partial_words;      // [L][kPartialCap]
     int *partial_count;      // [L] words on the path (may exceed kPartialCap: the oldest are cut)
+    int *endp_silence;       // [L] endpointing: trailing silence frames of the best path so far (TrailingSilenceLength) ...
+    float *endp_relcost;     // [L] ... and FinalRelativeCost of the current frame (inf: no final token); null = off
     unsigned long long *counters;     // [32] profiling counters (tokens, arcs, ...)
     int *lane_load;          // [lanes] largest token count a lane saw in this launch (load feedback)
     int grid;                // CTAs' worth of scratch allocated per slot

@@ -391,6 +391,21 @@ void Model::apply_conf(Config *cfg) const {
     geti(conf, "frames-per-chunk", &cfg->frames_per_chunk);
     geti(conf, "max-batch-size", &cfg->max_lanes);
     geti(conf, "num-channels", &cfg->num_channels);
+    // endpointing [REF src/model.cc:142-145]: Kaldi's OnlineEndpointConfig keys
+    {
+        auto it = conf.find("endpoint.silence-phones");
+        if (it != conf.end()) snprintf(cfg->endpoint_silence_phones, sizeof cfg->endpoint_silence_phones, "%s", it->second.c_str());
+        for (int r = 0; r < 4; r++) {
+            const std::string pre = "endpoint.rule" + std::to_string(r + 1) + ".";
+            auto b = conf.find(pre + "must-contain-nonsilence");
+            if (b != conf.end()) cfg->ep_must_contain_nonsilence[r] = b->second == "true" || b->second == "1";
+            getf(conf, (pre + "min-trailing-silence").c_str(), &cfg->ep_min_trailing_silence[r]);
+            getf(conf, (pre + "min-utterance-length").c_str(), &cfg->ep_min_utterance_length[r]);
+            auto m = conf.find(pre + "max-relative-cost");
+            if (m != conf.end() && !m->second.empty()) cfg->ep_max_relative_cost[r] = m->second == "inf" ? 1e30f : std::stof(m->second);
+        }
+        getf(conf, "endpoint.rule5.min-utterance-length", &cfg->endpoint_rule5_seconds);
+    }
     auto iv = read_conf(dir + "/conf/ivector.conf");
     geti(iv, "num-gselect", &cfg->num_gselect);
     getf(iv, "min-post", &cfg->min_post);
