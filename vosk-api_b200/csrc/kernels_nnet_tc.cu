@@ -83,8 +83,8 @@ struct TcSmem {
 
 // per-phase cycle counters of the tile pipeline (profiling aid, VB_TC_PROF=1 all layers / 2 the K=192 N=512 affines /
 // 3 the K>=1024 linears): tiles, prologue, producer loop, wait for the accumulator, epilogue, MMA warp: first operands
-// ready, MMA warp: last commit (both counted from the end of the prologue)
-__device__ unsigned long long g_tc_prof[8];
+// ready, MMA warp: last commit (both counted from the end of the prologue), MMA warp: cycles waiting for operands / issuing MMAs
+__device__ unsigned long long g_tc_prof[16];
 
 struct alignas(64) TensorMapBlob {
     unsigned char b[128];
@@ -326,9 +326,12 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % stages;
             const uint32_t par = (uint32_t)((kb / stages) & 1);
+            const long long q0 = prof ? clock64() : 0;
             mbar_wait(&ts.full[s], par);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (prof && kb == 0 && lane == 0) atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - pt1));
+            const long long q1 = prof ? clock64() : 0;
+            if (prof && lane == 0) atomicAdd(&g_tc_prof[8], (unsigned long long)(q1 - q0));
             if (lane == 0) {
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t dAh = umma_desc(sa), dAl = umma_desc(sa + TM * 128);
@@ -361,6 +364,7 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
                         "l"(dAl + adv), "l"(dBl + adv), "r"(idesc), "r"(1u)
                         : "memory");
                 }
+                if (prof) atomicAdd(&g_tc_prof[9], (unsigned long long)(clock64() - q1));  // issuing the K-block's MMAs (the issue blocks while the pipe is busy)
                 // tcgen05.commit: arrives on the barrier when the MMAs issued so far have read their operands
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&ts.empty[s])) : "memory");
                 if (kb == nkb - 1) {
@@ -456,11 +460,12 @@ extern "C" cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s) {
         if (!hooked) {
             hooked = true;
             atexit([] {
-                unsigned long long h[8] = {};
+                unsigned long long h[16] = {};
                 if (cudaMemcpyFromSymbol(h, g_tc_prof, sizeof h) != cudaSuccess || !h[0]) return;
                 const double n = (double)h[0];
                 fprintf(stderr, "[gemm_tc prof] tiles %.0f; cycles per tile: prologue %.0f, producer loop %.0f, wait accumulator %.0f, epilogue %.0f; MMA warp: first operands after %.0f, last commit after %.0f\n",
                         n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n);
+                fprintf(stderr, "[gemm_tc prof] MMA warp per tile: waiting for operands %.0f, issuing the MMAs %.0f\n", h[8] / n, h[9] / n);
             });
         }
     }
