@@ -16,12 +16,14 @@
 // Tensor-pipe FLOPs are 3x the algorithmic ones; bench.py counts the algorithmic ones.
 //
 // Structure (one 128 x BN output tile per CTA, BN = min(N, 256)):
-//   warps 0-3  A producers: coalesced 16-byte gathers from the ring rows -> hi/lo split in registers -> 128B-
+//   warps 0-7  A producers: coalesced 16-byte gathers from the ring rows -> hi/lo split in registers -> 128B-
 //              swizzled K-major smem tiles (generic-proxy stores + fence.proxy.async + mbarrier arrive);
-//              afterwards the same warps are the epilogue (tcgen05.ld of their 32 TMEM lanes, bias / ReLU /
-//              batchnorm / bypass fused, 64-byte row-segment stores).
-//   warp 4     TMA: cp.async.bulk.tensor of the W_hi / W_lo [BN x 32] boxes (SWIZZLE_128B) per K-block.
-//   warp 5     allocates TMEM, issues tcgen05.mma.cta_group::1.kind::tf32 (3 per 8-wide k-step), commits the
+//              afterwards the same warps are the epilogue (warps w and w + 4 share the 32 TMEM lanes of quarter w % 4 and
+//              take alternate 16-column chunks: tcgen05.ld, bias / ReLU / batchnorm / bypass fused, 64-byte row-segment
+//              stores; measured bound: the TMEM read path, a per-warp shared-memory transpose for coalesced stores
+//              changed nothing).
+//   warp 8     TMA: cp.async.bulk.tensor of the W_hi / W_lo [BN x 32] boxes (SWIZZLE_128B) per K-block.
+//   warp 9     allocates TMEM, issues tcgen05.mma.cta_group::1.kind::tf32 (3 per 8-wide k-step), commits the
 //              smem stage back to the producers and finally the accumulator to the epilogue.
 #include <cuda.h>
 
@@ -32,7 +34,7 @@ namespace vb {
 namespace {
 constexpr int TM = 128;       // tile rows (UMMA_M)
 constexpr int TK = 32;        // fp32 elements per K-block = one 128-byte swizzle row
-constexpr int kTcThreads = 320;        // 8 producer warps (the first 4 are also the epilogue), 1 TMA warp, 1 MMA warp
+constexpr int kTcThreads = 320;        // 8 producer warps (also the epilogue), 1 TMA warp, 1 MMA warp
 constexpr int kProducerThreads = 256;
 constexpr int kTmaWarp = kProducerThreads / 32, kMmaWarp = kTmaWarp + 1;
 
@@ -223,13 +225,14 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
                 publish(kb + 2, v2);
             }
         }
-      if (warp < 4) {  // (a warp reads the 32 TMEM lanes of its quarter: the first four producer warps)
+      {  // all eight producer warps: warps w and w + 4 share the 32 TMEM lanes of quarter w % 4 and take alternate 16-column chunks
         // =========================== epilogue ===========================
         const long long pt2 = prof ? clock64() : 0;
         mbar_wait(&ts.accum, 0);
         const long long pt3 = prof ? clock64() : 0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int r = warp * 32 + lane;
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
         const int ch = ts.row_ch[r], t = ts.row_t[r];
         float *orow = nullptr;
         const float *brow = nullptr;
@@ -237,8 +240,8 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
             orow = a.out.buf + ((size_t)ch * a.out.ring + (((t - a.out.t_start) / a.out.step) & (a.out.ring - 1))) * a.out.dim;
             if (op.byp_node >= 0) brow = a.byp.buf + ((size_t)ch * a.byp.ring + (((t - a.byp.t_start) / a.byp.step) & (a.byp.ring - 1))) * a.byp.dim;
         }
-        const uint32_t taddr_row = tmem + ((uint32_t)(warp * 32) << 16);
-        for (int cb = 0; cb < BN; cb += 16) {
+        const uint32_t taddr_row = tmem + ((uint32_t)(quarter * 32) << 16);
+        for (int cb = (warp >> 2) * 16; cb < BN; cb += 32) {
             // the bypass row segment (4 independent 16-byte loads) is requested first, so it arrives under the TMEM loads
             const int n = n0 + cb;
             float4 byp[4];
