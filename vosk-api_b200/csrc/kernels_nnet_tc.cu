@@ -4,16 +4,20 @@
 //   (the TDNN splice [x(t+o0), x(t+o1), ...] (+ i-vector) is materialised only in shared memory).
 //
 // Precision: the reference runs this stage as fp32 SGEMM (tensor cores off, [REF src/vosk_api.cc:184-185]) and
-// north_star asks for log-likelihoods within 1e-3, which plain TF32/BF16 inputs cannot hold through 30 chained
-// GEMMs.  Each fp32 operand is therefore split x = hi + lo with hi = x & 0xffffe000 (exactly a TF32 value) and
-// lo = x - hi (exact in fp32); the tile is accumulated as  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  in the fp32 TMEM
-// accumulators ("3xTF32"), dropping only the lo*lo term (~2^-22 relative).  Measured on B200: the tensor core
-// adds into the fp32 accumulator with truncation, so the error grows with the NUMBER of MMAs accumulated
-// (~1e-5 relative at K=1024 with all three terms in one accumulator).  The two cross terms are ~2^-11 of the
-// result, so they get their own TMEM accumulator (their truncation error is relative to their own size) and
-// the epilogue adds them in fp32 round-to-nearest; for long K the hi*hi k-steps are additionally dealt
-// round-robin over 2 or 4 accumulators, so at most K/32 truncating adds touch any one accumulator.
-// Tensor-pipe FLOPs are 3x the algorithmic ones; bench.py counts the algorithmic ones.
+// north_star asks for log-likelihoods within 1e-3, which plain TF32/BF16/FP16 inputs cannot hold through 30 chained
+// GEMMs.  Each fp32 operand is therefore split x = hi + lo and the tile is accumulated as
+// A_hi*W_hi + A_lo*W_hi + A_hi*W_lo in fp32 TMEM accumulators, dropping only the lo*lo term (~2^-22 relative):
+//   tensor-cores=1 (default): hi = fp16(x), lo = fp16((x - hi) * 2^11) — x - hi is exact in fp32, the scaling keeps lo a
+//     normal fp16 number and is undone (exactly) in the epilogue; kind::f16, K = 16 per MMA, 64 K-elements per 128-byte
+//     operand row.  |x| is clamped to the fp16 range (65504), far above what batch-normalised activations reach.
+//   tensor-cores=2: hi = x & 0xffffe000 (a TF32 value), lo = x - hi; kind::tf32, K = 8 per MMA, 32 K-elements per row.
+// Measured on B200: the tensor core adds into the fp32 accumulator with truncation, so the error grows with the NUMBER
+// of MMAs accumulated.  The two cross terms are ~2^-11 of the result, so they get their own TMEM accumulator (their
+// truncation error is relative to their own size) and the epilogue adds them in fp32 round-to-nearest; the hi*hi k-steps
+// are dealt round-robin over several accumulators.  The fp16 split needs half as many MMAs per K: with two accumulators it
+// measures 4.4e-4 end to end on the small architecture (TF32 split with four: 7.1e-4) and, with four from K = 2048,
+// 7.9e-4 on the large one (TF32 split: 1.6e-3), while the tile grows from 96 to 128-160 columns and the TDNN-F chain runs
+// 26 % faster.  Tensor-pipe FLOPs are 3x the algorithmic ones; bench.py counts the algorithmic ones.
 //
 // Structure (one 128 x BN output tile per CTA, BN = min(N, 256)):
 //   warps 0-7  A producers: coalesced 16-byte gathers from the ring rows -> hi/lo split in registers -> 128B-
@@ -26,6 +30,7 @@
 //   warp 9     allocates TMEM, issues tcgen05.mma.cta_group::1.kind::tf32 (3 per 8-wide k-step), commits the
 //              smem stage back to the producers and finally the accumulator to the epilogue.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "vb_kernels.h"
 
@@ -92,6 +97,10 @@ struct alignas(64) TensorMapBlob {
     unsigned char b[128];
 };
 
+// F16 = false: operands split into TF32 hi/lo (32 K-elements per 128-byte row);  F16 = true: operands split into fp16 hi and
+// 2^11-scaled fp16 lo (64 K-elements per 128-byte row, kind::f16, K = 16 per MMA) — half the shared-memory operand bytes
+// per multiply-add, which is what paces the main loop.
+template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const __grid_constant__ TensorMapBlob map_lo, int BN,
                int stages, int tmem_cols, int terms, int n_main, int prof) {
@@ -107,7 +116,8 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const OpDesc &op = a.op;
     const uint32_t stage_bytes = 2u * TM * 128u + 2u * (uint32_t)BN * 128u;
-    const int nkb = (op.K + TK - 1) / TK;
+    constexpr int TKE = F16 ? 64 : TK;  // K-elements per K-block (one 128-byte swizzle row)
+    const int nkb = (op.K + TKE - 1) / TKE;
 
     if (tid < TM) {
         int r = row0 + tid, ch = -1, t = 0;
@@ -166,63 +176,127 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
             row_slot[it] = (ts.row_t[r] - a.in.t_start) / a.in.step;
         }
         const int ring_mask = a.in.ring - 1;
-        // gather of one K-block into registers (8 independent 16-byte requests per thread)
-        auto gather = [&](int kb, float4 *v) {
-            const int k = kb * TK + c * 4;
-            const bool in_k = k < op.K, is_iv = k >= spliced;
-            int seg = 0, col = 0;
-            if (in_k && !is_iv) {
-                seg = k / in_dim;
-                col = k - seg * in_dim;
-            }
-            const int off_rows = in_k && !is_iv ? op.offs[seg] / a.in.step : 0;  // offsets are multiples of the input step
+        if constexpr (F16) {
+            // chunk c of a row = 8 K-elements = two 16-byte fp32 pieces -> one 16-byte piece of 8 halves in each operand tile
+            auto gather16 = [&](int kb, float4 *v) {
 #pragma unroll
-            for (int it = 0; it < RPT; it++) {
-                v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row_base[it] && in_k) {
-                    const float *src = is_iv ? iv_base[it] + (k - spliced)
-                                             : row_base[it] + (size_t)((row_slot[it] + off_rows) & ring_mask) * in_dim + col;
-                    v[it] = __ldg(reinterpret_cast<const float4 *>(src));
+                for (int pc = 0; pc < 2; pc++) {
+                    const int k = kb * TKE + c * 8 + pc * 4;
+                    const bool in_k = k < op.K, is_iv = k >= spliced;
+                    int seg = 0, col = 0;
+                    if (in_k && !is_iv) {
+                        seg = k / in_dim;
+                        col = k - seg * in_dim;
+                    }
+                    const int off_rows = in_k && !is_iv ? op.offs[seg] / a.in.step : 0;
+#pragma unroll
+                    for (int it = 0; it < RPT; it++) {
+                        v[it * 2 + pc] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row_base[it] && in_k) {
+                            const float *src = is_iv ? iv_base[it] + (k - spliced)
+                                                     : row_base[it] + (size_t)((row_slot[it] + off_rows) & ring_mask) * in_dim + col;
+                            v[it * 2 + pc] = __ldg(reinterpret_cast<const float4 *>(src));
+                        }
+                    }
+                }
+            };
+            auto publish16 = [&](int kb, const float4 *v) {
+                const int s = kb % stages;
+                const uint32_t par = (uint32_t)((kb / stages) & 1);
+                mbar_wait(&ts.empty[s], par ^ 1);
+                const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + TM * 128;
+#pragma unroll
+                for (int it = 0; it < RPT; it++) {
+                    const int r = it * RG + rsub;
+                    const float x[8] = {v[it * 2].x, v[it * 2].y, v[it * 2].z, v[it * 2].w, v[it * 2 + 1].x, v[it * 2 + 1].y, v[it * 2 + 1].z, v[it * 2 + 1].w};
+                    uint32_t hp[4], lp[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        // hi = fp16(x) (|x| clamped to the fp16 range), lo = fp16((x - hi) * 2^11): x - hi is exact in fp32
+                        const float x0 = fminf(fmaxf(x[2 * j], -65504.f), 65504.f), x1 = fminf(fmaxf(x[2 * j + 1], -65504.f), 65504.f);
+                        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                        const __half l0 = __float2half_rn((x0 - __half2float(h0)) * 2048.f), l1 = __float2half_rn((x1 - __half2float(h1)) * 2048.f);
+                        hp[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                        lp[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                    }
+                    const uint32_t o = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "r"(hp[0]), "r"(hp[1]), "r"(hp[2]), "r"(hp[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + o), "r"(lp[0]), "r"(lp[1]), "r"(lp[2]), "r"(lp[3]) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&ts.full[s]);
+            };
+            // two K-blocks (2 x 64 K-elements) in flight per thread, buffers rotating by name
+            float4 v0[RPT * 2], v1[RPT * 2];
+            gather16(0, v0);
+            if (nkb > 1) gather16(1, v1);
+            for (int kb = 0; kb < nkb; kb += 2) {
+                publish16(kb, v0);
+                if (kb + 2 < nkb) gather16(kb + 2, v0);
+                if (kb + 1 < nkb) {
+                    publish16(kb + 1, v1);
+                    if (kb + 3 < nkb) gather16(kb + 3, v1);
                 }
             }
-        };
-        // split one gathered K-block into hi/lo and publish it to the MMA warp
-        auto publish = [&](int kb, const float4 *v) {
-            const int s = kb % stages;
-            const uint32_t par = (uint32_t)((kb / stages) & 1);
-            mbar_wait(&ts.empty[s], par ^ 1);
-            const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + TM * 128;
-#pragma unroll
-            for (int it = 0; it < RPT; it++) {
-                const int r = it * RG + rsub;
-                float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(v[it].x) & 0xffffe000u);
-                h.y = __uint_as_float(__float_as_uint(v[it].y) & 0xffffe000u);
-                h.z = __uint_as_float(__float_as_uint(v[it].z) & 0xffffe000u);
-                h.w = __uint_as_float(__float_as_uint(v[it].w) & 0xffffe000u);
-                l.x = v[it].x - h.x; l.y = v[it].y - h.y; l.z = v[it].z - h.z; l.w = v[it].w - h.w;
-                const uint32_t o = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + o), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA (async proxy)
-            mbar_arrive(&ts.full[s]);
-        };
-        // software pipeline, unrolled by three so that the buffers rotate by name (no register moves that would wait for the
-        // loads just issued): while block kb is split and stored, the loads of kb + 1 and kb + 2 are in flight
-        float4 v0[RPT], v1[RPT], v2[RPT];
-        gather(0, v0);
-        if (nkb > 1) gather(1, v1);
-        for (int kb = 0; kb < nkb; kb += 3) {
-            if (kb + 2 < nkb) gather(kb + 2, v2);
-            publish(kb, v0);
-            if (kb + 1 < nkb) {
-                if (kb + 3 < nkb) gather(kb + 3, v0);
-                publish(kb + 1, v1);
-            }
-            if (kb + 2 < nkb) {
-                if (kb + 4 < nkb) gather(kb + 4, v1);
-                publish(kb + 2, v2);
+        } else {
+            // gather of one K-block into registers (8 independent 16-byte requests per thread)
+            auto gather = [&](int kb, float4 *v) {
+                const int k = kb * TK + c * 4;
+                const bool in_k = k < op.K, is_iv = k >= spliced;
+                int seg = 0, col = 0;
+                if (in_k && !is_iv) {
+                    seg = k / in_dim;
+                    col = k - seg * in_dim;
+                }
+                const int off_rows = in_k && !is_iv ? op.offs[seg] / a.in.step : 0;  // offsets are multiples of the input step
+    #pragma unroll
+                for (int it = 0; it < RPT; it++) {
+                    v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row_base[it] && in_k) {
+                        const float *src = is_iv ? iv_base[it] + (k - spliced)
+                                                 : row_base[it] + (size_t)((row_slot[it] + off_rows) & ring_mask) * in_dim + col;
+                        v[it] = __ldg(reinterpret_cast<const float4 *>(src));
+                    }
+                }
+            };
+            // split one gathered K-block into hi/lo and publish it to the MMA warp
+            auto publish = [&](int kb, const float4 *v) {
+                const int s = kb % stages;
+                const uint32_t par = (uint32_t)((kb / stages) & 1);
+                mbar_wait(&ts.empty[s], par ^ 1);
+                const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + TM * 128;
+    #pragma unroll
+                for (int it = 0; it < RPT; it++) {
+                    const int r = it * RG + rsub;
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v[it].x) & 0xffffe000u);
+                    h.y = __uint_as_float(__float_as_uint(v[it].y) & 0xffffe000u);
+                    h.z = __uint_as_float(__float_as_uint(v[it].z) & 0xffffe000u);
+                    h.w = __uint_as_float(__float_as_uint(v[it].w) & 0xffffe000u);
+                    l.x = v[it].x - h.x; l.y = v[it].y - h.y; l.z = v[it].z - h.z; l.w = v[it].w - h.w;
+                    const uint32_t o = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + o), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA (async proxy)
+                mbar_arrive(&ts.full[s]);
+            };
+            // software pipeline, unrolled by three so that the buffers rotate by name (no register moves that would wait for the
+            // loads just issued): while block kb is split and stored, the loads of kb + 1 and kb + 2 are in flight
+            float4 v0[RPT], v1[RPT], v2[RPT];
+            gather(0, v0);
+            if (nkb > 1) gather(1, v1);
+            for (int kb = 0; kb < nkb; kb += 3) {
+                if (kb + 2 < nkb) gather(kb + 2, v2);
+                publish(kb, v0);
+                if (kb + 1 < nkb) {
+                    if (kb + 3 < nkb) gather(kb + 3, v0);
+                    publish(kb + 1, v1);
+                }
+                if (kb + 2 < nkb) {
+                    if (kb + 4 < nkb) gather(kb + 4, v1);
+                    publish(kb + 2, v2);
+                }
             }
         }
       {  // all eight producer warps: warps w and w + 4 share the 32 TMEM lanes of quarter w % 4 and take alternate 16-column chunks
@@ -253,7 +327,7 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
             }
             // all partial accumulators of this 16-column chunk are requested before the single wait (the loads pipeline);
             // they are summed in fp32 round-to-nearest in a fixed order
-            const int nsteps = (nkb * (TK / 8));
+            const int nsteps = nkb * 4;
             uint32_t v[5][16];
 #pragma unroll
             for (int q = 0; q < 5; q++) {
@@ -274,8 +348,19 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 float x = 0.f;
+                if constexpr (F16) {  // accumulator n_main holds 2^11 x the cross terms: the lo operands are scaled to stay normal in fp16
+                    float cr = 0.f;
 #pragma unroll
-                for (int q = 0; q < 5; q++) x += __uint_as_float(v[q][j]);
+                    for (int q = 0; q < 5; q++) {
+                        const float t = __uint_as_float(v[q][j]);
+                        x += q < n_main ? t : 0.f;
+                        cr = q == n_main ? t : cr;
+                    }
+                    x = fmaf(cr, 1.f / 2048.f, x);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 5; q++) x += __uint_as_float(v[q][j]);
+                }
                 acc[j] = x;
             }
             if (orow && n < op.N) {
@@ -313,7 +398,7 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
                 mbar_wait(&ts.empty[s], par ^ 1);
                 unsigned char *B_hi = smem + (size_t)s * stage_bytes + 2 * TM * 128, *B_lo = B_hi + (size_t)BN * 128;
                 mbar_arrive_expect_tx(&ts.full[s], 2u * (uint32_t)BN * 128u);
-                const int k0 = kb * TK;
+                const int k0 = kb * TKE;
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(B_hi)),
                              "l"(&map_hi), "r"(k0), "r"(n0), "r"(smem_u32(&ts.full[s]))
                              : "memory");
@@ -325,7 +410,8 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
     } else {
         // =========================== MMA issuer ===========================
         // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+        // (A/B format field: 2 = TF32 for kind::tf32, 0 = F16 for kind::f16)
+        const uint32_t idesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % stages;
             const uint32_t par = (uint32_t)((kb / stages) & 1);
@@ -339,33 +425,30 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t dAh = umma_desc(sa), dAl = umma_desc(sa + TM * 128);
                 const uint64_t dBh = umma_desc(sa + 2 * TM * 128), dBl = umma_desc(sa + 2 * TM * 128 + BN * 128);
+                auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+                    if constexpr (F16)
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                            "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                            : "memory");
+                    else
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                            "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                            : "memory");
+                };
 #pragma unroll
-                for (int k8 = 0; k8 < TK / 8; k8++) {
-                    const uint64_t adv = (uint64_t)((k8 * 32) >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle row
-                    const int step = kb * (TK / 8) + k8;
+                for (int k8 = 0; k8 < 4; k8++) {
+                    const uint64_t adv = (uint64_t)((k8 * 32) >> 4);  // one MMA = 32 bytes along K inside the swizzle row (8 tf32 / 16 f16)
+                    const int step = kb * 4 + k8;
                     const uint32_t d_main = tmem + (uint32_t)((step % n_main) * BN);   // hi*hi: round-robin over n_main accumulators
                     const uint32_t d_cross = tmem + (uint32_t)(n_main * BN);            // cross terms: their own accumulator
-                    const uint32_t acc_main = step >= n_main ? 1u : 0u, acc_cross = step ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_main),
-                        "l"(dAh + adv), "l"(dBh + adv), "r"(idesc), "r"(acc_main)
-                        : "memory");
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_cross),
-                        "l"(dAl + adv), "l"(dBh + adv), "r"(idesc), "r"(acc_cross)
-                        : "memory");
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_cross),
-                        "l"(dAh + adv), "l"(dBl + adv), "r"(idesc), "r"(1u)
-                        : "memory");
-                    if (terms > 3) asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_cross),
-                        "l"(dAl + adv), "l"(dBl + adv), "r"(idesc), "r"(1u)
-                        : "memory");
+                    mma(d_main, dAh + adv, dBh + adv, step >= n_main ? 1u : 0u);
+                    mma(d_cross, dAl + adv, dBh + adv, step ? 1u : 0u);
+                    mma(d_cross, dAh + adv, dBl + adv, 1u);
+                    if (terms > 3) mma(d_cross, dAl + adv, dBl + adv, 1u);
                 }
                 if (prof) atomicAdd(&g_tc_prof[9], (unsigned long long)(clock64() - q1));  // issuing the K-block's MMAs (the issue blocks while the pipe is busy)
                 // tcgen05.commit: arrives on the barrier when the MMAs issued so far have read their operands
@@ -403,26 +486,59 @@ static EncodeTiledFn encode_fn() {
 
 // Number of hi*hi accumulators (fewer truncating adds per accumulator) and the N tile that fits
 // (n_main + 1) * BN fp32 columns into the 512 TMEM columns.
-// Measured on the small architecture (end-to-end log-likelihood error against the oracle, tolerance 1e-3): 4 main accumulators
-// at K = 192 (6 truncating adds each, 96-column tiles) 7e-4; 3 (8 adds, 128-column tiles, TDNN-F chain 12 % faster) 1.05e-3;
-// 1 (24 adds, 256-column tiles, 22 % faster) 1.3e-3.  The tolerance decides: 4.  Wider tiles need the accumulators drained
-// into fp32 registers every few k-steps.
-static int main_accs(int K) { return K >= 128 ? 4 : K >= 64 ? 2 : 1; }
-static int tile_n(int N, int K) {
-    int limit = (512 / (main_accs(K) + 1)) & ~15;
-    return N < limit ? N : limit;  // (a partial last tile is fine: TMA zero-fills beyond N and the epilogue guards its stores)
+// TF32 split, measured on the small architecture (end-to-end log-likelihood error against the oracle, tolerance 1e-3): 4 main
+// accumulators at K = 192 (6 truncating adds each, 96-column tiles) 7e-4; 3 (8 adds, 128-column tiles) 1.05e-3; 1 (24 adds,
+// 256-column tiles) 1.3e-3.  The tolerance decides: 4.  The fp16 split issues half as many MMAs per K (K = 16 each), so two
+// main accumulators give the same number of adds per accumulator, and the tile can be up to 160 columns wide.
+static int main_accs(int K, bool f16) {
+    static int force = getenv("VB_TC_NMAIN") ? atoi(getenv("VB_TC_NMAIN")) : 0;  // experiments
+    if (force > 0 && f16) return force;
+    return f16 ? (K >= 2048 ? 4 : K >= 128 ? 2 : 1) : (K >= 128 ? 4 : K >= 64 ? 2 : 1);
+}
+static int tile_n(int N, int K, bool f16) {
+    const int limit = (512 / (main_accs(K, f16) + 1)) & ~15;
+    if (!f16) return N < limit ? N : limit;  // (a partial last tile is fine: TMA zero-fills beyond N and the epilogue guards its stores)
+    const int ntiles = (N + limit - 1) / limit;  // equal tiles: 512 columns -> 4 x 128 rather than 3 x 160 + 32
+    return (((N + ntiles - 1) / ntiles) + 15) & ~15;
+}
+static bool tc_f16(int mode) { return mode != 2; }
+
+__global__ void split_f16_kernel(const float *w, __half *hi, __half *lo, int N, int K, int Kp) {
+    const long long n = (long long)N * Kp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / Kp), k = (int)(i - (long long)r * Kp);
+        float v = k < K ? w[(size_t)r * K + k] : 0.f;
+        v = fminf(fmaxf(v, -65504.f), 65504.f);
+        const __half h = __float2half_rn(v);
+        hi[i] = h;
+        lo[i] = __float2half_rn((v - __half2float(h)) * 2048.f);
+    }
 }
 
-extern "C" cudaError_t vbk_make_weight_map(const float *w, int N, int K, void *out128) {
+// Weight operands of the tensor-core path.  mode 2: W_hi = W & 0xffffe000, W_lo = W - W_hi as fp32 [N][K];
+// otherwise fp16 hi and 2^11-scaled fp16 lo as [N][Kp], Kp = K rounded up to 8 (zero columns).  hi / lo need N * K * 4 bytes each.
+extern "C" cudaError_t vbk_split_weights(const float *w, int N, int K, int mode, void *hi, void *lo, cudaStream_t s) {
+    if (N <= 0 || K <= 0) return cudaSuccess;
+    if (!tc_f16(mode)) return vbk_split_tf32(w, (float *)hi, (float *)lo, (long long)N * K, s);
+    if (K < 8) return cudaErrorInvalidValue;
+    const int Kp = (K + 7) & ~7;
+    const long long n = (long long)N * Kp;
+    split_f16_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(w, (__half *)hi, (__half *)lo, N, K, Kp);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t vbk_make_weight_map(const void *w, int N, int K, int mode, void *out128) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return cudaErrorNotSupported;
+    const bool f16 = tc_f16(mode);
     CUtensorMap m;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)tile_n(N, K)};
+    const int Kp = f16 ? (K + 7) & ~7 : K;
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * (f16 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)(f16 ? 64 : TK), (cuuint32_t)tile_n(N, K, f16)};  // one 128-byte swizzle row per weight row
     cuuint32_t es[2] = {1, 1};
-    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(&m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
     memcpy(out128, &m, 128);
@@ -433,23 +549,25 @@ extern "C" cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s) {
     if (a->num_lanes <= 0 || a->max_rows <= 0) return cudaSuccess;
     const OpDesc &op = a->op;
     if (op.N % 16 || (op.K * 4) % 16 || !a->map_hi || !a->map_lo) return cudaErrorInvalidValue;
-    const int BN = tile_n(op.N, op.K), n_main = main_accs(op.K);
+    const bool f16 = tc_f16(a->tc_mode);
+    const int BN = tile_n(op.N, op.K, f16), n_main = main_accs(op.K, f16);
     const uint32_t stage_bytes = 2u * TM * 128u + 2u * (uint32_t)BN * 128u;
     int stages = (int)((200u * 1024u) / stage_bytes);
     if (stages > 4) stages = 4;
-    const int nkb = (op.K + TK - 1) / TK;
+    const int nkb = (op.K + (f16 ? 64 : TK) - 1) / (f16 ? 64 : TK);
     if (stages > nkb) stages = nkb;
     if (stages < 1) stages = 1;
     int tmem_cols = 32;
     while (tmem_cols < (n_main + 1) * BN) tmem_cols <<= 1;  // n_main hi*hi accumulators + one for the small cross terms
     const int smem = (int)(stage_bytes * stages + 1024);
-    static int done[16] = {};
+    static int done[2][16] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 16 && done[dev] < smem) {  // per-device function attribute: raise it only when a larger tile set is needed
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (dev < 16 && done[f16][dev] < smem) {  // per-device function attribute: raise it only when a larger tile set is needed
+        cudaError_t e = f16 ? cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                            : cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        done[dev] = smem;
+        done[f16][dev] = smem;
     }
     dim3 grid((a->max_rows + TM - 1) / TM, (op.N + BN - 1) / BN);
     TensorMapBlob mh, ml;
@@ -472,7 +590,8 @@ extern "C" cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s) {
             });
         }
     }
-    gemm_tc_kernel<<<grid, kTcThreads, smem, s>>>(*a, mh, ml, BN, stages, tmem_cols, terms, n_main, prof_this ? 1 : 0);
+    if (f16) gemm_tc_kernel<true><<<grid, kTcThreads, smem, s>>>(*a, mh, ml, BN, stages, tmem_cols, terms, n_main, prof_this ? 1 : 0);
+    else gemm_tc_kernel<false><<<grid, kTcThreads, smem, s>>>(*a, mh, ml, BN, stages, tmem_cols, terms, n_main, prof_this ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -72,7 +72,7 @@ struct Config {
     int num_gselect = 5;        // ivector.conf
     float min_post = 0.025f, posterior_scale = 0.1f, max_count = 100.0f;  // [REF src/model.cc:257]
     int cmn_window = 600, global_frames = 200;
-    int use_tensor_cores = 1;   // TDNN-F GEMMs on tcgen05 (3xTF32 split, fp32 accumulate); 0 = fp32 FFMA kernel
+    int use_tensor_cores = 1;   // TDNN-F GEMMs on tcgen05, fp32 accumulate: 1 = fp16 hi/lo split (3 x f16 MMAs), 2 = TF32 hi/lo split; 0 = fp32 FFMA kernel
     int debug_capture = 0;      // allow per-stream capture of intermediates (tests)
     int lattice = 0;            // lattice generation: link log + lattice_beam pruning on the device, raw lattice to the host
     int log_links_per_frame = 6144;   // average links per frame the link log is sized for
@@ -99,8 +99,8 @@ struct OpDesc {
     int K, N;       // K = n_off*in_dim (+ ivec_dim)
     int relu, has_bn;
     const float *W;     // [N][K] fp32
-    const float *W_hi;  // tf32 split (low 13 mantissa bits cleared), [N][K]
-    const float *W_lo;  // W - W_hi
+    const void *W_hi;   // tensor-core operand split of W (vbk_split_weights): fp16 hi / TF32 hi
+    const void *W_lo;   // fp16 (W - hi) * 2^11 / fp32 W - hi
     const float *bias;  // [N] or null
     const float *bn_scale, *bn_offset;
     float bypass_scale;

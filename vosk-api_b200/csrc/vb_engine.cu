@@ -284,7 +284,7 @@ void Engine::upload_model() {
         d.has_bn = op.relu_bn;
         float *w = dev_upload(allocs_, op.W->f32(), (size_t)op.N * op.K);
         float *hi = dev_alloc<float>(allocs_, (size_t)op.N * op.K), *lo = dev_alloc<float>(allocs_, (size_t)op.N * op.K);
-        VB_CUDA_CHECK(vbk_split_tf32(w, hi, lo, (long long)op.N * op.K, stream_));
+        if (cfg_.use_tensor_cores) VB_CUDA_CHECK(vbk_split_weights(w, op.N, op.K, cfg_.use_tensor_cores, hi, lo, stream_));
         d.W = w;
         d.W_hi = hi;
         d.W_lo = lo;
@@ -294,8 +294,8 @@ void Engine::upload_model() {
         d.bypass_scale = m.bypass_scale;
         ops_[o] = d;
         if (cfg_.use_tensor_cores) {
-            VB_CUDA_CHECK(vbk_make_weight_map(hi, op.N, op.K, maps_[o].hi));
-            VB_CUDA_CHECK(vbk_make_weight_map(lo, op.N, op.K, maps_[o].lo));
+            VB_CUDA_CHECK(vbk_make_weight_map(hi, op.N, op.K, cfg_.use_tensor_cores, maps_[o].hi));
+            VB_CUDA_CHECK(vbk_make_weight_map(lo, op.N, op.K, cfg_.use_tensor_cores, maps_[o].lo));
         }
     }
     // ---- decoding graph: one 16-byte record per arc ----
@@ -848,6 +848,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         ga.ivec = iv_state_.ivec;
         ga.ivec_dim = model_.ivec_dim;
         ga.max_rows = (int)(ga.out.step == 1 ? in_rows : in_rows / kSubsample + 2 * L);
+        ga.tc_mode = cfg_.use_tensor_cores;
         ga.map_hi = maps_[o].hi;
         ga.map_lo = maps_[o].lo;
         VB_CUDA_CHECK(cfg_.use_tensor_cores ? vbk_gemm_tc(&ga, st) : vbk_gemm_fp32(&ga, st));

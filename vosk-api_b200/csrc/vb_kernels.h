@@ -121,6 +121,7 @@ struct GemmArgs {
     const float *ivec;       // [C][ivec_dim]
     int ivec_dim;
     int max_rows;            // upper bound of total rows (grid sizing)
+    int tc_mode;             // tensor-core operand split: 1 = fp16 hi/lo (kind::f16), 2 = TF32 hi/lo (kind::tf32)
     const void *map_hi;      // HOST pointers to the 128-byte TMA descriptors of W_hi / W_lo (tensor-core path)
     const void *map_lo;
 };
@@ -224,8 +225,11 @@ cudaError_t vbk_ivector(const IvecArgs *a, cudaStream_t s);
 cudaError_t vbk_nnet_plan(const NnetPlanArgs *a, cudaStream_t s);
 cudaError_t vbk_gemm_fp32(const GemmArgs *a, cudaStream_t s);
 cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s);
-// encodes the TMA descriptor ([N][K] fp32, box 32 x min(N,256), SWIZZLE_128B) of a weight matrix into out128
-cudaError_t vbk_make_weight_map(const float *w, int N, int K, void *out128);
+// tensor-core operand form of a weight matrix (tc_mode 1: fp16 hi + 2^11-scaled fp16 lo, [N][K rounded up to 8]; 2: TF32 hi / lo,
+// fp32 [N][K]); hi and lo must hold N * K * 4 bytes each
+cudaError_t vbk_split_weights(const float *w, int N, int K, int tc_mode, void *hi, void *lo, cudaStream_t s);
+// encodes the TMA descriptor (box = one 128-byte swizzle row x the N tile) of such an operand into out128
+cudaError_t vbk_make_weight_map(const void *w, int N, int K, int tc_mode, void *out128);
 cudaError_t vbk_decode(const DecArgs *a, int heavy, cudaStream_t s);
 // backward extra-cost pruning (lattice_beam) + compaction of the link log of the lanes whose stream ended in this step
 cudaError_t vbk_lattice_prune(const DecArgs *a, cudaStream_t s);

@@ -33,7 +33,8 @@ extern "C" int vosk_b200_gemm_selftest(int M, int N, int K, int bits, double *ou
     cudaMalloc(&dHi, W.size() * 4);
     cudaMalloc(&dLo, W.size() * 4);
     cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice);
-    vbk_split_tf32(dW, dHi, dLo, (long long)W.size(), 0);
+    const int tc_mode = getenv("VB_TC_MODE") ? atoi(getenv("VB_TC_MODE")) : 1;
+    vbk_split_weights(dW, N, K, tc_mode, dHi, dLo, 0);
     cudaMalloc(&dC0, (size_t)ring * N * 4);
     cudaMalloc(&dC1, (size_t)ring * N * 4);
     LaneDesc ln{};
@@ -55,7 +56,7 @@ extern "C" int vosk_b200_gemm_selftest(int M, int N, int K, int bits, double *ou
     cudaMalloc(&dRows, (size_t)M * sizeof(int2));
     cudaMemcpy(dRows, rows.data(), (size_t)M * sizeof(int2), cudaMemcpyHostToDevice);
     alignas(64) unsigned char mh[128], ml[128];
-    if (vbk_make_weight_map(dHi, N, K, mh) != cudaSuccess || vbk_make_weight_map(dLo, N, K, ml) != cudaSuccess) return -1;
+    if (vbk_make_weight_map(dHi, N, K, tc_mode, mh) != cudaSuccess || vbk_make_weight_map(dLo, N, K, tc_mode, ml) != cudaSuccess) return -1;
     GemmArgs g{};
     g.op.in_node = 0; g.op.out_node = 1; g.op.byp_node = -1; g.op.n_off = 1; g.op.offs[0] = 0; g.op.K = K; g.op.N = N;
     g.op.W = dW; g.op.W_hi = dHi; g.op.W_lo = dLo;
@@ -63,7 +64,7 @@ extern "C" int vosk_b200_gemm_selftest(int M, int N, int K, int bits, double *ou
     g.out = NodeDesc{N, 1, ring, 0, 0, dC0};
     g.byp = g.in;
     g.lanes = dL; g.num_lanes = 1; g.table = dT; g.rowoff = dR; g.rows = dRows; g.ivec = dA; g.ivec_dim = 4; g.max_rows = M;
-    g.map_hi = mh; g.map_lo = ml;
+    g.map_hi = mh; g.map_lo = ml; g.tc_mode = tc_mode;
     if (vbk_gemm_fp32(&g, 0) != cudaSuccess) return -2;
     g.out.buf = dC1;
     if (vbk_gemm_tc(&g, 0) != cudaSuccess) return -3;

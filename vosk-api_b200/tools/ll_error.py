@@ -17,12 +17,13 @@ for arch in sys.argv[1:] or ["tiny", "small"]:
     P = int(model["cfg"]["num-pdfs"])
     refs = [oracle.recognize(model, w, stages=True) for w in waves]
     res = {}
-    for tc in (0, 1):
+    for tc in (0, 1, 2):
         got, _ = helpers.run_engine(mdir, waves, options="num-channels=4,max-batch-size=4,max-seconds=8,tensor-cores=%d" % tc)
         res[tc] = got
         errs = [np.abs(g["loglikes"].reshape(-1, P) - r["loglikes"]).max() for g, r in zip(got, refs)]
         rms = [np.sqrt(np.mean((g["loglikes"].reshape(-1, P) - r["loglikes"]) ** 2)) for g, r in zip(got, refs)]
         same = [g["text"] == r["text"] for g, r in zip(got, refs)]
         print(arch, "tc=%d" % tc, "max abs err", ["%.2e" % e for e in errs], "rms", ["%.2e" % e for e in rms], "text equal", same)
-    d = [np.abs(a["loglikes"] - b["loglikes"]).max() for a, b in zip(res[0], res[1])]
-    print(arch, "tc1 vs tc0 max abs diff", ["%.2e" % e for e in d])
+    for tc in (1, 2):
+        d = [np.abs(a["loglikes"] - b["loglikes"]).max() for a, b in zip(res[0], res[tc])]
+        print(arch, "tc%d vs tc0 max abs diff" % tc, ["%.2e" % e for e in d])
