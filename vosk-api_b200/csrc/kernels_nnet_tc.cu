@@ -475,8 +475,9 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
 // 80 columns or fewer, VB_TC_BN_CAP=80 — even the MMAs of tile i + 1 overlap the epilogue).  Bit-identical results
 // (tools/gemm_selftest.py incl. multi-tile shapes), but measured SLOWER than the one-tile-per-CTA kernel on the small
 // architecture: TDNN-F chain 25.7 ms vs 22.0 ms per 4.2 k audio-seconds (28 ms with two accumulator sets): with one
-// accumulator set the next tile's MMAs still wait for an epilogue that now runs on four warps instead of eight.  Kept as
-// the starting point for a version with eight epilogue warps (needs setmaxnreg to fit 18 warps).
+// accumulator set the next tile's MMAs still wait for an epilogue that now runs on four warps instead of eight; with eight
+// epilogue warps (576 threads, 96 registers, 344 bytes of spills) it measured 32.5 ms.  Kept as the starting point for a
+// version that redistributes registers between the roles (setmaxnreg).
 //   warps 0-7   A producers (gather -> fp16 hi / lo split -> swizzled tiles)
 //   warp  8     TMA weight boxes            warp 9   TMEM allocation + MMA issue
 //   warps 10-13 epilogue (warp w owns the TMEM lanes of quarter w % 4)
