@@ -139,3 +139,129 @@ def test_loader_reports_what_it_cannot_express(lib, pair, tmp_path):
     assert "unsupported descriptor function Const" in msg
     # neither format
     assert "unrecognised" in broken(lambda b: b"XXXX" + b[4:])
+
+
+def _write_custom_mdl(path, cfg_lines, comps, n_pdfs, hmm_triples=False):
+    """A final.mdl with an arbitrary nnet3 graph; hmm_triples: plain-HMM topology (no self-loop pdf class) and <Triples>."""
+    import kaldi_io
+    with open(path, "wb") as f:
+        w = kaldi_io._W(f)
+        w.raw(b"\0B")
+        n_ts = n_pdfs // 2
+        tid2pdf = np.zeros(2 * n_ts + 1, dtype=np.int32)
+        tid2phone = np.zeros(2 * n_ts + 1, dtype=np.int32)
+        for ts in range(n_ts):
+            tid2pdf[2 * ts + 1], tid2pdf[2 * ts + 2] = 2 * ts + 1, 2 * ts
+            tid2phone[2 * ts + 1] = tid2phone[2 * ts + 2] = 1 + ts % 7
+        if not hmm_triples:
+            kaldi_io._write_transition_model(w, tid2pdf, tid2phone)
+        else:
+            w.tok("<TransitionModel>")
+            w.tok("<Topology>")
+            w.intvec(list(range(1, 8)))
+            w.intvec([-1] + [0] * 7)
+            w.i32(1); w.i32(2)
+            w.i32(0); w.i32(2); w.i32(0); w.f32(0.5); w.i32(1); w.f32(0.5)   # state 0: pdf class 0, self loop + forward
+            w.i32(-1); w.i32(0)
+            w.tok("</Topology>")
+            w.tok("<Triples>")
+            w.i32(n_ts)
+            for ts in range(n_ts):
+                w.i32(1 + ts % 7); w.i32(0); w.i32(ts)
+            w.tok("</Triples>")
+            w.tok("<LogProbs>"); w.vec(np.zeros(2 * n_ts + 1)); w.tok("</LogProbs>")
+            w.tok("</TransitionModel>")
+        w.tok("<Nnet3>")
+        w.raw(b"\n")
+        for line in cfg_lines:
+            w.raw(line.encode() + b"\n")
+        w.raw(b"\n")
+        w.tok("<NumComponents>"); w.i32(len(comps))
+        for name, fn in comps:
+            w.tok("<ComponentName>"); w.tok(name)
+            fn(w)
+        w.tok("</Nnet3>")
+        w.tok("<LeftContext>"); w.i32(0)
+        w.tok("<RightContext>"); w.i32(0)
+        w.tok("<Priors>"); w.vec(np.zeros(0))
+
+
+def test_compiler_on_an_lda_style_network_against_direct_evaluation(lib, model_root, tmp_path):
+    """A graph the TDNN-F recipe does not produce: spliced fixed 'lda' affine over Append(Offset...) + a scaled i-vector, plain
+    AffineComponent, ReLU + batchnorm, a dim-range-node, a bypass over a no-op, <Triples> + HMM topology.  The compiled op chain,
+    evaluated in numpy, must equal the direct evaluation of the graph as written."""
+    import kaldi_io
+    rng = np.random.default_rng(11)
+    F, I, P = 40, 16, 96
+    Wl, bl = rng.standard_normal((64, 3 * F + I)) * 0.1, rng.standard_normal(64) * 0.1
+    W1, b1 = rng.standard_normal((48, 64)) * 0.2, rng.standard_normal(48) * 0.1
+    s1, o1 = rng.uniform(0.5, 1.5, 48), rng.standard_normal(48) * 0.1
+    W2, b2 = rng.standard_normal((48, 2 * 32)) * 0.2, rng.standard_normal(48) * 0.1     # TdnnComponent over the dim-range, offsets -3, 3
+    s2, o2 = rng.uniform(0.5, 1.5, 48), rng.standard_normal(48) * 0.1
+    Wo, bo = rng.standard_normal((P, 48)) * 0.2, rng.standard_normal(P) * 0.1
+    cfg = [f"input-node name=ivector dim={I}", f"input-node name=input dim={F}",
+           "component-node name=lda component=lda input=Append(Offset(input, -1), input, Offset(input, 1), Scale(0.5, ReplaceIndex(ivector, t, 0)))",
+           "component-node name=l1.affine component=l1.affine input=lda",
+           "component-node name=l1.relu component=l1.relu input=l1.affine",
+           "component-node name=l1.bn component=l1.bn input=l1.relu",
+           "dim-range-node name=l1.part input-node=l1.bn dim-offset=8 dim=32",
+           "component-node name=l2.affine component=l2.affine input=l1.part",
+           "component-node name=l2.relu component=l2.relu input=l2.affine",
+           "component-node name=l2.bn component=l2.bn input=l2.relu",
+           "component-node name=l2.noop component=l2.noop input=Sum(l2.bn, Scale(0.66, l1.bn))",
+           "component-node name=out.affine component=out.affine input=l2.noop",
+           "output-node name=output input=out.affine objective=linear"]
+
+    def affine(W, b):
+        def fn(w):
+            w.tok("<AffineComponent>")
+            w.tok("<LearningRate>"); w.f32(0.001)
+            w.tok("<LinearParams>"); w.mat(W)
+            w.tok("<BiasParams>"); w.vec(b)
+            w.tok("<IsGradient>"); w.boolean(False)
+            w.tok("</AffineComponent>")
+        return fn
+    comps = [("lda", lambda w: kaldi_io._c_fixed_affine(w, Wl, bl)), ("l1.affine", affine(W1, b1)),
+             ("l1.relu", lambda w: kaldi_io._c_relu(w, 48)), ("l1.bn", lambda w: kaldi_io._c_batchnorm(w, s1, o1)),
+             ("l2.affine", lambda w: kaldi_io._c_tdnn(w, W2, b2, [-3, 3])), ("l2.relu", lambda w: kaldi_io._c_relu(w, 48)),
+             ("l2.bn", lambda w: kaldi_io._c_batchnorm(w, s2, o2)), ("l2.noop", lambda w: kaldi_io._c_noop(w, 48)),
+             ("out.affine", affine(Wo, bo))]
+    dst = str(tmp_path / "model")
+    shutil.copytree(model_root("tiny"), dst)
+    _write_custom_mdl(os.path.join(dst, "am/final.mdl"), cfg, comps, P, hmm_triples=True)
+    meta = tensor(lib, dst, "meta")
+    n_ops, ctx = int(meta[0]), int(meta[1])
+    assert n_ops == 3 and ctx == 4 and abs(meta[4] - 0.66) < 1e-6
+    # <Triples> with a plain HMM topology: both transitions of a state emit the state's single pdf
+    t2p = tensor(lib, dst, "tid2pdf")
+    np.testing.assert_array_equal(t2p[1:], np.repeat(np.arange(P // 2), 2))
+    # evaluate the compiled chain and the graph as written on random input (interior frames only)
+    T = 40
+    x = rng.standard_normal((T, F)).astype(np.float32).astype(np.float64)
+    iv = rng.standard_normal(I).astype(np.float32).astype(np.float64)
+    nodes = [x]
+    for i in range(n_ops):
+        m = tensor(lib, dst, f"op{i}.meta")
+        in_node, byp, uses_iv, relu, K, N, noff = (int(v) for v in m[:7])
+        offs = [int(v) for v in m[7:7 + noff]]
+        W = tensor(lib, dst, f"op{i}.w").reshape(N, K)
+        b = tensor(lib, dst, f"op{i}.b", True)
+        src = nodes[in_node]
+        ar = np.arange(T)
+        cols = [src[np.clip(ar + o, 0, T - 1)] for o in offs]
+        if uses_iv:
+            cols.append(np.tile(iv, (T, 1)))
+        z = np.concatenate(cols, 1) @ W.T + (b if b is not None else 0.0)
+        if relu:
+            z = np.maximum(z, 0.0) * tensor(lib, dst, f"op{i}.bn_scale") + tensor(lib, dst, f"op{i}.bn_offset")
+        if byp >= 0:
+            z = z + meta[4] * nodes[byp]
+        nodes.append(z)
+    ar = np.arange(T)
+    sp = lambda a, o: a[np.clip(ar + o, 0, T - 1)]
+    lda = np.concatenate([sp(x, -1), x, sp(x, 1), np.tile(0.5 * iv, (T, 1))], 1) @ Wl.T + bl
+    h1 = np.maximum(lda @ W1.T + b1, 0.0) * s1 + o1
+    part = h1[:, 8:40]
+    h2 = np.maximum(np.concatenate([sp(part, -3), sp(part, 3)], 1) @ W2.T + b2, 0.0) * s2 + o2
+    want = (h2 + 0.66 * h1) @ Wo.T + bo
+    np.testing.assert_allclose(nodes[-1][ctx:T - ctx], want[ctx:T - ctx], rtol=0, atol=2e-5)
