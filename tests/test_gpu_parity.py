@@ -394,3 +394,28 @@ def test_silence_endpoint_rules_segment_like_the_oracle(model_root, oracle_lib, 
                 got.append(t)
             assert got == x
         del recs, m
+
+
+def test_odd_model_dimensions_decode_like_the_oracle(model_root, oracle_lib):
+    """i-vector dimension 14 and 90 pdfs (not multiples of 4 / 16, as real models often are): the loader pads exactly
+    (tests/test_kaldi_formats.py), so log-likelihoods of the real pdfs, the i-vector and the transcript still match the oracle."""
+    import vbmodel
+    import vosk
+    mdir = model_root("tiny", overrides=dict(ivector_dim=14, num_pdfs=90), tag="_odd")
+    model = vbmodel.load_model_dir(mdir)
+    waves = _waves([1.3, 2.9], seed0=2500)
+    m = vosk.BatchModel(mdir, options="debug-capture=1,num-channels=2,max-batch-size=2,max-seconds=8")
+    recs = [vosk.BatchRecognizer(m, 16000.0) for _ in waves]
+    for r in recs:
+        r.DebugCapture()
+    helpers.feed_round_robin(recs, waves)
+    m.Wait()
+    for r, w in zip(recs, waves):
+        ref = oracle_lib.recognize(model, w, stages=True)
+        ll = r.DebugGet("loglikes", np.float32).reshape(-1, 96)
+        assert ll.shape[0] == ref["loglikes"].shape[0]
+        assert np.abs(ll[:, :90] - ref["loglikes"]).max() < 1e-3
+        iv = r.DebugGet("ivectors", np.float32).reshape(-1, 16)
+        assert np.abs(iv[:, :14] - ref["ivectors"]).max() < 2e-3 and not iv[:, 14:].any()
+        assert r.Result() == ref["text"]
+    del recs, m

@@ -265,3 +265,33 @@ def test_compiler_on_an_lda_style_network_against_direct_evaluation(lib, model_r
     h2 = np.maximum(np.concatenate([sp(part, -3), sp(part, 3)], 1) @ W2.T + b2, 0.0) * s2 + o2
     want = (h2 + 0.66 * h1) @ Wo.T + bo
     np.testing.assert_allclose(nodes[-1][ctx:T - ctx], want[ctx:T - ctx], rtol=0, atol=2e-5)
+
+
+def test_odd_ivector_and_output_dimensions_are_padded_exactly(lib, model_root):
+    """Real models have i-vector dimensions such as 30 and arbitrary pdf counts; the kernels want multiples of 4 / 16.  The
+    loader pads with zero extractor columns, zero weight columns and zero output rows (both file formats)."""
+    import kaldi_io
+    import vbmodel
+    import tempfile
+    src = model_root("tiny", overrides=dict(ivector_dim=14, num_pdfs=90), tag="_odd")
+    T = vbmodel.read_vbt(os.path.join(src, "am/final.mdl"))
+    ie = vbmodel.read_vbt(os.path.join(src, "ivector/final.ie"))
+    with tempfile.TemporaryDirectory() as td:
+        for mdir in (src, kaldi_io.convert_model_dir(src, td)):
+            meta = tensor(lib, mdir, "meta")
+            assert int(meta[2]) == 90 and int(meta[3]) == 16          # pdfs stay 90, the i-vector is carried as 16
+            m0 = tensor(lib, mdir, "op0.meta")
+            K, N = int(m0[4]), int(m0[5])
+            assert K == 5 * 40 + 16
+            w0 = tensor(lib, mdir, "op0.w").reshape(N, K)
+            np.testing.assert_allclose(w0[:, :214], T["tdnn1.w"], rtol=0, atol=3e-6 * np.abs(T["tdnn1.w"]).max())
+            assert not w0[:, 214:].any()
+            last = int(meta[0]) - 1
+            ml = tensor(lib, mdir, f"op{last}.meta")
+            assert int(ml[5]) == 96
+            wl = tensor(lib, mdir, f"op{last}.w").reshape(96, int(ml[4]))
+            np.testing.assert_allclose(wl[:90], T["output.w"], rtol=0, atol=3e-6 * np.abs(T["output.w"]).max())
+            assert not wl[90:].any() and not tensor(lib, mdir, f"op{last}.b")[90:].any()
+            M = tensor(lib, mdir, "iv.M").reshape(ie["M"].shape[0], ie["M"].shape[1], 16)
+            np.testing.assert_array_equal(M[:, :, :14], ie["M"].astype(np.float64))
+            assert not M[:, :, 14:].any()

@@ -481,7 +481,7 @@ void Engine::alloc_state() {
         }
     }
     if (cfg_.debug_capture) {
-        capture_floats_ = (size_t)(max_in_rows_ + 8) * std::max(model_.num_pdfs, F);
+        capture_floats_ = (size_t)(max_in_rows_ + 8) * std::max(model_.node_dim.back(), F);
         d_capture_ = dev_alloc<float>(allocs_, capture_floats_);
         VB_CUDA_CHECK(cudaMallocHost((void **)&h_capture_, capture_floats_ * sizeof(float)));
     }

@@ -223,7 +223,6 @@ void Model::load_kaldi_am(const std::string &mdl) {
         op.K = o.K;
         op.N = o.N;
         if ((int)op.offs.size() > kMaxOffsets) throw std::runtime_error("too many time offsets in " + o.name);
-        if (op.N % 16 || op.K % 4) throw std::runtime_error("layer " + o.name + ": dimensions must be multiples of 16 (outputs) / 4 (inputs)");
         op.W = &(am[base + ".w"] = make_f32(o.W, {o.N, o.K}));
         op.b = o.b.empty() ? nullptr : &(am[base + ".b"] = make_f32(o.b, {o.N}));
         op.bn_s = o.relu ? &(am[base + ".bn_scale"] = make_f32(o.bn_s, {o.N})) : nullptr;
@@ -371,6 +370,57 @@ void Model::load(const std::string &d) {
     num_gauss = (int)find(iv_dubm, "gconsts")->numel();
     prior_offset = find(iv_ie, "prior_offset")->f32()[0];
     if (find(iv_ie, "M")->shape[2] != ivec_dim) throw std::runtime_error("i-vector dim mismatch");
+    pad_dimensions();
+}
+
+// The kernels move rows in 16-byte pieces and tile outputs by 16: an i-vector dimension that is not a multiple of 4 (30 is
+// common) and an output layer that is not a multiple of 16 wide are padded here, exactly: extra i-vector dimensions get zero
+// columns in the extractor (their prior keeps them at 0) and zero columns in the weights that read them; extra outputs get
+// zero rows (no pdf id refers to them).  Any other odd layer size is rejected.
+void Model::pad_dimensions() {
+    auto padded_rows = [&](const Tensor &w, int n_new) {
+        Tensor t = w;
+        t.shape[0] = n_new;
+        t.data.resize((size_t)n_new * (size_t)(w.numel() / w.shape[0]) * 4, 0);
+        return t;
+    };
+    const int D = ivec_dim, Dp = (D + 3) & ~3;
+    if (Dp != D && D > 0) {
+        const Tensor &M = *find(iv_ie, "M");
+        const int64_t G = M.shape[0], F = M.shape[1];
+        Tensor t;
+        t.dtype = 0;
+        t.shape = {G, F, Dp};
+        t.data.assign((size_t)(G * F * Dp) * 4, 0);
+        for (int64_t r = 0; r < G * F; r++) memcpy(t.data.data() + (size_t)r * Dp * 4, M.data.data() + (size_t)r * D * 4, (size_t)D * 4);
+        iv_ie["M"] = std::move(t);
+        for (AmOp &op : ops) {
+            if (!op.uses_ivec) continue;
+            const int Kn = op.K + (Dp - D);  // the i-vector block is the tail of the spliced input
+            Tensor w;
+            w.dtype = 0;
+            w.shape = {op.N, Kn};
+            w.data.assign((size_t)op.N * Kn * 4, 0);
+            for (int n = 0; n < op.N; n++) memcpy(w.data.data() + (size_t)n * Kn * 4, op.W->data.data() + (size_t)n * op.K * 4, (size_t)op.K * 4);
+            op.W = &(am[op.name + ".w(padded)"] = std::move(w));
+            op.K = Kn;
+        }
+        ivec_dim = Dp;
+    }
+    if (!ops.empty() && ops.back().N % 16) {
+        AmOp &op = ops.back();
+        const int Nn = (op.N + 15) & ~15;
+        op.W = &(am[op.name + ".w(rows padded)"] = padded_rows(*op.W, Nn));
+        if (op.b) op.b = &(am[op.name + ".b(padded)"] = padded_rows(*op.b, Nn));
+        if (op.bn_s) {
+            op.bn_s = &(am[op.name + ".bn_scale(padded)"] = padded_rows(*op.bn_s, Nn));
+            op.bn_o = &(am[op.name + ".bn_offset(padded)"] = padded_rows(*op.bn_o, Nn));
+        }
+        op.N = Nn;
+        node_dim.back() = Nn;
+    }
+    for (const AmOp &op : ops)
+        if (op.N % 16 || op.K % 4) throw std::runtime_error("layer " + op.name + ": dimensions must be multiples of 16 (outputs) / 4 (inputs)");
 }
 
 void Model::apply_conf(Config *cfg) const {

@@ -70,6 +70,7 @@ struct Model {
     void load(const std::string &model_dir);  // throws std::runtime_error on a missing/corrupt file
     void load_vbt_am(const std::string &mdl);    // am/final.mdl as the generator's tensor container (collapsed network)
     void load_kaldi_am(const std::string &mdl);  // am/final.mdl as Kaldi's TransitionModel + nnet3 file (vb_kaldi.cc)
+    void pad_dimensions();  // i-vector dim -> multiple of 4, output width -> multiple of 16 (exact: zero columns / rows)
     void apply_conf(Config *cfg) const;
 };
 
