@@ -175,3 +175,20 @@ def test_world_size_2_aggregation_gloo():
         p.join(60)
     for rank, val, tmax, asum in res:
         assert tmax == 3.0 and asum == 300.0 and abs(val - 100.0) < 1e-9
+
+
+def test_mfcc_conf_is_read_and_checked(lib, model_root, tmp_path):
+    """conf/mfcc.conf [REF src/batch_model.cc:75-76]: band edges are taken from it (7600 Hz = Nyquist - 400), a feature geometry
+    the kernels are not built for is refused at load time instead of silently decoding with other features."""
+    import shutil
+    dst = str(tmp_path / "model")
+    shutil.copytree(model_root("tiny"), dst)
+    buf = ctypes.create_string_buffer(1024)
+    conf = os.path.join(dst, "conf", "mfcc.conf")
+    base = open(conf).read()
+    open(conf, "w").write(base.replace("--high-freq=-400", "--high-freq=7600") + "--sample-frequency=16000\n")
+    assert lib.vosk_b200_model_check(dst.encode(), buf, 1024) == 0, buf.value
+    open(conf, "w").write(base.replace("--num-mel-bins=40", "--num-mel-bins=23"))
+    assert lib.vosk_b200_model_check(dst.encode(), buf, 1024) == -1 and b"num-mel-bins" in buf.value
+    open(conf, "w").write(base.replace("--low-freq=20", "--low-freq=9000"))
+    assert lib.vosk_b200_model_check(dst.encode(), buf, 1024) == -1 and b"low-freq" in buf.value

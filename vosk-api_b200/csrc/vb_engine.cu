@@ -159,7 +159,8 @@ void Engine::upload_model() {
             tw[2 * k + 1] = (float)std::sin(-2.0 * M_PI * k / kFftSize);
         }
         auto mel = [](double f) { return 1127.0 * std::log(1.0 + f / 700.0); };
-        const double ml = mel(20.0), mh = mel(8000.0 - 400.0), delta = (mh - ml) / (kNumMel + 1), bw = 16000.0 / kFftSize;
+        const double f_lo = cfg_.mfcc_low_freq, f_hi = cfg_.mfcc_high_freq > 0 ? cfg_.mfcc_high_freq : 8000.0 + cfg_.mfcc_high_freq;
+        const double ml = mel(f_lo), mh = mel(f_hi), delta = (mh - ml) / (kNumMel + 1), bw = 16000.0 / kFftSize;
         for (int j = 0; j < kNumMel; j++) {
             double l = ml + j * delta, c = ml + (j + 1) * delta, r = ml + (j + 2) * delta;
             int first = -1, last = -1;

@@ -456,11 +456,41 @@ void Model::apply_conf(Config *cfg) const {
         }
         getf(conf, "endpoint.rule5.min-utterance-length", &cfg->endpoint_rule5_seconds);
     }
+    // conf/mfcc.conf [REF src/batch_model.cc:75-76]: the mel band edges are configurable, the feature geometry the kernels are
+    // built for (40 mel bins, 40 cepstra, no energy, 16 kHz, 25 ms / 10 ms frames, lifter 22) is checked
+    {
+        auto mf = read_conf(dir + "/conf/mfcc.conf");
+        getf(mf, "low-freq", &cfg->mfcc_low_freq);
+        getf(mf, "high-freq", &cfg->mfcc_high_freq);
+        auto expect = [&](const char *k, double want) {
+            auto it = mf.find(k);
+            if (it == mf.end() || it->second.empty()) return;
+            const double v = it->second == "true" ? 1 : it->second == "false" ? 0 : std::stod(it->second);
+            if (std::fabs(v - want) > 1e-9) throw std::runtime_error(std::string("conf/mfcc.conf: --") + k + "=" + it->second + " is not supported (expected " + std::to_string(want) + ")");
+        };
+        expect("num-mel-bins", 40);
+        expect("num-ceps", 40);
+        expect("use-energy", 0);
+        expect("sample-frequency", 16000);
+        expect("frame-length", 25);
+        expect("frame-shift", 10);
+        expect("cepstral-lifter", 22);
+        expect("dither", 0);
+        const double hi = cfg->mfcc_high_freq > 0 ? cfg->mfcc_high_freq : 8000.0 + cfg->mfcc_high_freq;
+        if (cfg->mfcc_low_freq < 0 || hi <= cfg->mfcc_low_freq || hi > 8000.0) throw std::runtime_error("conf/mfcc.conf: bad --low-freq / --high-freq");
+    }
     auto iv = read_conf(dir + "/conf/ivector.conf");
     geti(iv, "num-gselect", &cfg->num_gselect);
     getf(iv, "min-post", &cfg->min_post);
     getf(iv, "posterior-scale", &cfg->posterior_scale);
     getf(iv, "max-count", &cfg->max_count);
+    {  // the i-vector front end splices +-3 frames (the LDA matrix has 7 x 40 + 1 columns): splice.conf must say the same
+        auto sp = read_conf(dir + "/ivector/splice.conf");
+        int l = 3, r = 3;
+        geti(sp, "left-context", &l);
+        geti(sp, "right-context", &r);
+        if (l != 3 || r != 3) throw std::runtime_error("ivector/splice.conf: only --left-context=3 --right-context=3 is supported");
+    }
     auto cm = read_conf(dir + "/ivector/online_cmvn.conf");
     geti(cm, "cmn-window", &cfg->cmn_window);
     geti(cm, "global-frames", &cfg->global_frames);
