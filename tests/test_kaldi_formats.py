@@ -295,3 +295,35 @@ def test_odd_ivector_and_output_dimensions_are_padded_exactly(lib, model_root):
             M = tensor(lib, mdir, "iv.M").reshape(ie["M"].shape[0], ie["M"].shape[1], 16)
             np.testing.assert_array_equal(M[:, :, :14], ie["M"].astype(np.float64))
             assert not M[:, :, 14:].any()
+
+
+def test_reader_on_hand_assembled_bytes(lib, model_root, tmp_path):
+    """Byte strings put together by hand from Kaldi's I/O rules (not through tools/kaldi_io.py): binary marker, token + space,
+    size-prefixed basic types, FM / FV / DM headers — so reader and writer cannot agree on a private dialect."""
+    import struct
+    dst = str(tmp_path / "model")
+    shutil.copytree(model_root("tiny"), dst)
+    F = 40
+    lda = (np.arange(F * (7 * F + 1), dtype=np.float32).reshape(F, 7 * F + 1) % 17 - 8) / 16.0
+    with open(os.path.join(dst, "ivector/final.mat"), "wb") as f:
+        f.write(b"\x00B" + b"FM " + b"\x04" + struct.pack("<i", F) + b"\x04" + struct.pack("<i", 7 * F + 1) + lda.astype("<f4").tobytes())
+    G = 16
+    w = np.full(G, 1.0 / G, dtype=np.float32)
+    iv = (1.0 + (np.arange(G * F, dtype=np.float32).reshape(G, F) % 5) / 4.0)
+    miv = ((np.arange(G * F, dtype=np.float32).reshape(G, F) % 7) - 3.0) / 2.0
+    with open(os.path.join(dst, "ivector/final.dubm"), "wb") as f:
+        f.write(b"\x00B<DiagGMM> ")
+        f.write(b"<WEIGHTS> FV \x04" + struct.pack("<i", G) + w.astype("<f4").tobytes())
+        f.write(b"<MEANS_INVVARS> FM \x04" + struct.pack("<i", G) + b"\x04" + struct.pack("<i", F) + miv.astype("<f4").tobytes())
+        f.write(b"<INV_VARS> FM \x04" + struct.pack("<i", G) + b"\x04" + struct.pack("<i", F) + iv.astype("<f4").tobytes())
+        f.write(b"</DiagGMM> ")
+    stats = np.arange(2 * (F + 1), dtype=np.float64).reshape(2, F + 1)
+    with open(os.path.join(dst, "ivector/global_cmvn.stats"), "wb") as f:
+        f.write(b"\x00B" + b"DM " + b"\x04" + struct.pack("<i", 2) + b"\x04" + struct.pack("<i", F + 1) + stats.astype("<f8").tobytes())
+    np.testing.assert_array_equal(tensor(lib, dst, "iv.lda").reshape(F, -1), lda.astype(np.float64))
+    np.testing.assert_array_equal(tensor(lib, dst, "iv.inv_vars").reshape(G, F), iv.astype(np.float64))
+    np.testing.assert_array_equal(tensor(lib, dst, "iv.means_invvars").reshape(G, F), miv.astype(np.float64))
+    np.testing.assert_array_equal(tensor(lib, dst, "iv.cmvn").reshape(2, F + 1), stats)
+    # gconsts were absent: log w - 0.5 (F log 2pi - sum log inv_var + sum mean_invvar^2 / inv_var)
+    want = np.log(w.astype(np.float64)) - 0.5 * (F * np.log(2 * np.pi) - np.log(iv).sum(1) + (miv.astype(np.float64) ** 2 / iv).sum(1))
+    np.testing.assert_allclose(tensor(lib, dst, "iv.gconsts"), want, rtol=0, atol=1e-4)
