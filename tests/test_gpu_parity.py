@@ -419,3 +419,33 @@ def test_odd_model_dimensions_decode_like_the_oracle(model_root, oracle_lib):
         assert np.abs(iv[:, :14] - ref["ivectors"]).max() < 2e-3 and not iv[:, 14:].any()
         assert r.Result() == ref["text"]
     del recs, m
+
+
+@pytest.mark.parametrize("env", [{}, {"VB_TC_MODE": "2"}, {"VB_TC_PERSIST": "1"}, {"VB_TC_PERSIST": "1", "VB_TC_BN_CAP": "80"}])
+def test_gemm_kernels_against_fp64(env):
+    """K2 in isolation (vosk_b200_gemm_selftest: random A / W, one lane, fp64 reference on the host): the default fp16 hi/lo
+    operand split, the TF32 split (tensor-cores=2), and the experimental persistent kernel with one and with two accumulator
+    sets — shapes of the small architecture plus one with more tiles than SMs.  The switches are read once per process, hence
+    the subprocess."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import ctypes, json\n"
+        "lib = ctypes.CDLL(%r)\n"
+        "out = (ctypes.c_double * 4)()\n"
+        "res = []\n"
+        "for M, N, K in [(256, 512, 192), (300, 2496, 192), (256, 96, 1024), (200, 64, 216), (20000, 96, 192)]:\n"
+        "    rc = lib.vosk_b200_gemm_selftest(M, N, K, 0, out)\n"
+        "    res.append([M, N, K, rc, out[0], out[1], out[2], out[3]])\n"
+        "print(json.dumps(res))\n" % os.path.join(root, "vosk-api_b200", "lib", "libvosk.so"))
+    e = dict(os.environ)
+    e.update(env)
+    p = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    for M, N, K, rc, err_fp32, err_tc, rms_tc, rms_ref in json.loads(p.stdout.strip().splitlines()[-1]):
+        assert rc == 0, (M, N, K, rc)
+        # relative to the output's rms (about 1): the split GEMM must be as good as the fp32 FFMA kernel, far from fp16 / tf32 inputs (1e-3)
+        assert err_tc < 1.5e-5 * max(1.0, rms_ref) and rms_tc < 2e-6 * max(1.0, rms_ref), (env, M, N, K, err_tc, rms_tc)
