@@ -447,6 +447,17 @@ def main():
     except Exception:
         pass
     roof["traffic"] = traffic
+    # the same figures for every stage: algorithmic bytes or flops of one serialized step / its device time
+    roof_all = {
+        "mfcc": {"bound": "hbm", "achieved": feat_bytes / (kernel_ms["mfcc"] / 1000.0) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "algorithmic": "480 B per frame"},
+        "tdnnf": {"bound": "tensor", "achieved": flop / (kernel_ms["tdnnf"] / 1000.0) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                  "algorithmic": "7.95 MFLOP per output frame (the fp16 hi/lo split issues 3x that on the tensor pipe)"},
+        "search": {"bound": "hbm", "achieved": search_bytes / (kernel_ms["search"] / 1000.0) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                   "algorithmic": "T*16 + (Ae+Aeps)*20 + Ae*4 + N*16 bytes from the in-kernel counters"},
+    }
+    for v in roof_all.values():
+        v["frac"] = v["achieved"] / v["peak"]
 
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
@@ -460,7 +471,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(lengths.sum()) * 2 + a.streams * 64,
                         "d2h_bytes_per_step": a.streams * (4 * (18 * 100 // 3 + 2) * 4 + 64 * 4 + 32),
                         "transcripts_equal_to_resident_run": "%d/%d" % (same, len(texts))},
-                "gpu_launches": launches_timed, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "gpu_launches": launches_timed, "clocks": clocks, "roofline": roof, "roofline_all_stages": roof_all, "cpu_baseline": cpu,
                 "kernel_ms_per_step": kernel_ms, "kernel_ms_per_step_overlapped": kernel_ms_overlapped,
                 "roofline_note": "stage durations from one extra pass with the pipeline slots serialized (no overlap); CUDA events on the launching stream",
                 "host_wall_ms_per_step_resident": wall_resident * 1000.0 / a.steps,
