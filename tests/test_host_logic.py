@@ -192,3 +192,19 @@ def test_mfcc_conf_is_read_and_checked(lib, model_root, tmp_path):
     assert lib.vosk_b200_model_check(dst.encode(), buf, 1024) == -1 and b"num-mel-bins" in buf.value
     open(conf, "w").write(base.replace("--low-freq=20", "--low-freq=9000"))
     assert lib.vosk_b200_model_check(dst.encode(), buf, 1024) == -1 and b"low-freq" in buf.value
+
+
+@pytest.mark.parametrize("rate,n", [(8000, 4000), (44100, 4410), (22050, 3000), (48000, 4800), (11025, 2000)])
+def test_resampler_matches_torchaudio(lib, rate, n):
+    """Independent pin of the LinearResample restatement (filter design, phase tables, zero-padded edges of a flushed call,
+    output count): torchaudio's sinc_interp_hann resampler is derived from Kaldi's LinearResample; with rolloff 1.0 and filter
+    width 6 it is the filter the reference asks for — cutoff min(rate, 16000) / 2, num_zeros 6 [REF src/batch_recognizer.cc:27-29]."""
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    lib.vosk_b200_resample.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_int]
+    x = (np.random.default_rng(rate).standard_normal(n) * 1000).astype(np.float32)
+    out = np.zeros(3 * n + 64, dtype=np.float32)
+    m = lib.vosk_b200_resample(x.ctypes.data, n, float(rate), out.ctypes.data, len(out))
+    ref = torchaudio.functional.resample(torch.from_numpy(x)[None].double(), rate, 16000, lowpass_filter_width=6, rolloff=1.0)[0].numpy()
+    assert m == len(ref)
+    assert np.abs(out[:m] - ref).max() < 2e-6 * np.abs(ref).max() + 1e-3   # fp32 products / sums against fp64
