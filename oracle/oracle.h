@@ -107,6 +107,18 @@ int orc_align_words(const OrcResultCtx *c, const int *arcs, int n_arcs, int *wor
 char *orc_result_json(const OrcResultCtx *c, const int *arcs, int n_arcs, float offset_seconds, int nlsml);
 void orc_free(void *p);
 
+/* ---- lattice result chain (orc_lattice.cc): DeterminizeLatticePhonePrunedWrapper -> ScaleLattice(GraphLatticeScale(lm_scale)) ->
+ *      WordAlignLattice -> MinimumBayesRisk -> text, as the pipeline + PushLattice do [REF src/batch_recognizer.cc:43-107,138-149].
+ *      Input = the raw lattice of orc_decoder_lattice.  tid_flags (may be NULL = the generator's chain topology): bit 0 self-loop,
+ *      bit 1 final transition, bit 2 leaves HMM state 0.  stage 0 = result text (JSON / NLSML), 1 = determinized + scaled
+ *      CompactLattice, 2 = word-aligned CompactLattice as text lines ("S start", "A src dst word graph acoustic tids",
+ *      "F state graph acoustic tids").  phone_pass 0 skips the phone-level first determinization pass.
+ *      Returns a malloc'd string (orc_free). ---- */
+char *orc_lattice_result(const OrcResultCtx *c, const float *arc_w, const unsigned char *tid_flags, int num_tids, int n_states, int start,
+                         int64_t n_links, const int64_t *src, const int64_t *dst, const int *arc, const float *acoustic, int64_t n_final,
+                         const int64_t *final_state, const float *final_cost, float lattice_beam, double lm_scale, float offset_seconds,
+                         int nlsml, int stage, int phone_pass);
+
 #ifdef __cplusplus
 }
 #endif

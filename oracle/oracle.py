@@ -22,7 +22,7 @@ def build():
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(_HERE, "liboracle.so")
+        so = os.environ.get("ORC_SO") or os.path.join(_HERE, "liboracle.so")
         if not os.path.exists(so):
             build()
         _LIB = C.CDLL(so)
@@ -48,6 +48,10 @@ def lib():
         _LIB.orc_result_json.restype = C.c_void_p
         _LIB.orc_result_json.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
         _LIB.orc_free.argtypes = [C.c_void_p]
+        _LIB.orc_lattice_result.restype = C.c_void_p
+        _LIB.orc_lattice_result.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_double, C.c_float,
+                                            C.c_int, C.c_int, C.c_int]
     return _LIB
 
 
@@ -272,6 +276,33 @@ def result_json(model, arcs, offset=0.0, nlsml=False, rc=None):
     rc = rc or ResultCtx(model)
     arcs = _i32(arcs)
     ptr = lib().orc_result_json(C.byref(rc.ctx), _p(arcs), len(arcs), offset, int(nlsml))
+    s = C.string_at(ptr).decode()
+    lib().orc_free(ptr)
+    return s
+
+
+def lattice_start(dec):
+    """Lattice state of the start token (frame 0, no incoming arc)."""
+    lat = dec["lattice"]
+    return int(np.flatnonzero((lat["frame"] == 0) & (dec["arc"][lat["tok_index"]] < 0))[0])
+
+
+def lattice_result(model, dec, lattice_beam=None, lm_scale=0.9, offset=0.0, nlsml=False, stage=0, phone_pass=True, rc=None):
+    """The reference's result chain on the raw lattice of decode(..., lattice_beam=...): phone-pruned determinization, graph
+    scale 0.9, word alignment, MBR, text [REF src/batch_recognizer.cc:43-107,138-149]."""
+    rc = rc or ResultCtx(model)
+    lat = dec["lattice"]
+    lb = float(lattice_beam if lattice_beam is not None else model["conf"].get("lattice-beam", 6.0))
+    g = model["graph"]
+    src, dst = np.ascontiguousarray(lat["src"], dtype=np.int64), np.ascontiguousarray(lat["dst"], dtype=np.int64)
+    arc, ac = _i32(lat["arc"]), _f32(lat["ac"])
+    fs, fc = np.ascontiguousarray(lat["final_state"], dtype=np.int64), _f32(lat["final_cost"])
+    arc_w = _f32(g["arc_w"])
+    flags = model["nnet"].get("tid_flags")
+    flags = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+    ptr = lib().orc_lattice_result(C.byref(rc.ctx), _p(arc_w), None if flags is None else _p(flags), len(model["nnet"]["tid2phone"]),
+                                   len(lat["tok_index"]), lattice_start(dec), len(src), _p(src), _p(dst), _p(arc), _p(ac), len(fs), _p(fs),
+                                   _p(fc), lb, lm_scale, offset, int(nlsml), stage, int(phone_pass))
     s = C.string_at(ptr).decode()
     lib().orc_free(ptr)
     return s

@@ -431,7 +431,9 @@ extern "C" char *orc_result_json(const OrcResultCtx *c, const int *arcs, int n, 
         for (int i = 0; i < nw; i++) conf += 1.0f;
         conf /= nw;
         ss << "<?xml version=\"1.0\"?>\n<result grammar=\"default\">\n";
-        ss << "<interpretation grammar=\"default\" confidence=\"" << conf << "\">\n";
+        char cbuf[64];
+        snprintf(cbuf, sizeof cbuf, "%g", (double)conf);  // = ostream << float (see orc_lattice.cc)
+        ss << "<interpretation grammar=\"default\" confidence=\"" << cbuf << "\">\n";
         ss << "<input mode=\"speech\">" << text << "</input>\n";
         ss << "<instance>" << text << "</instance>\n</interpretation>\n</result>\n";
         out = ss.str();

@@ -89,8 +89,14 @@ def words_of(text):
 _LAT_HOOK = None
 
 
+def oracle_lattice_text(model, dec, lattice_beam, offset=0.0, nlsml=False, rc=None):
+    """Expected lattice-mode result text: the ORACLE's chain (oracle/orc_lattice.cc) on the oracle's raw lattice."""
+    import oracle
+    return oracle.lattice_result(model, dec, lattice_beam, offset=offset, nlsml=nlsml, rc=rc)
+
+
 def lattice_text(model_dir, oracle_lattice, start, lattice_beam, stage=0):
-    """Host lattice chain (vosk_b200_lattice_result, no GPU involved) on a raw lattice given as oracle.decode()["lattice"]."""
+    """ENGINE host lattice chain (vosk_b200_lattice_result, no GPU involved) on a raw lattice given as oracle.decode()["lattice"]."""
     import ctypes
     import os
     global _LAT_HOOK

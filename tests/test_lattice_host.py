@@ -1,5 +1,8 @@
-"""CPU tests of the host lattice chain (vb_lattice.cc: pruned word determinization, graph scale, word alignment, MBR),
+"""CPU tests of the host lattice chain (vb_lattice.cc: phone-pruned determinization, graph scale, word alignment, MBR),
 driven through the host-only hook vosk_b200_lattice_result on raw lattices produced by the oracle decoder.
+
+The expected value is the oracle's own restatement of the chain (oracle/orc_lattice.cc, written in Kaldi's object structure,
+independently of the engine's flat-array code): result text, determinized and word-aligned lattices must be identical.
 
 The checks are brute force (pure-Python path enumeration on small lattices), independent of the C++ under test:
   * a linear lattice gives exactly the best-path result text of the oracle (conf 1, word spans of the alignment);
@@ -239,3 +242,60 @@ def test_two_way_ambiguity_confidence_is_the_path_posterior(model_root, hook):
     win = int(np.argmax(post))
     assert res["text"] == paths[win][0][0]
     assert abs(res["result"][0]["conf"] - post[win]) < 1e-4
+
+
+def _same_lattice_text(a, b):
+    """Two "S/A/F" dumps describe the same lattice up to state numbering and arc order: compared through a canonical
+    relabelling (breadth-first from the start over arcs sorted by their content)."""
+    def canon(text):
+        start, arcs, finals = _parse(text)
+        if start < 0:
+            return []
+        order, queue, out = {start: 0}, [start], []
+        while queue:
+            s = queue.pop(0)
+            for d, w, g, a, t in sorted(arcs.get(s, ()), key=lambda x: (x[1], x[4], x[2], x[3])):
+                if d not in order:
+                    order[d] = len(order)
+                    queue.append(d)
+                out.append((order[s], w, order[d], np.float32(g), np.float32(a), tuple(t)))
+            if s in finals:
+                out.append((order[s], -1, -1, np.float32(finals[s][0]), np.float32(finals[s][1]), tuple(finals[s][2])))
+        return sorted(out, key=lambda x: (x[0], x[1], x[2], x[5], float(x[3]), float(x[4])))
+    return canon(a) == canon(b)
+
+
+@pytest.mark.parametrize("seed,secs,beam", [(41, 1.2, 2.0), (42, 0.8, 3.0), (43, 1.6, 1.5), (44, 3.5, 6.0), (45, 2.2, 6.0), (46, 4.0, 4.0)])
+def test_chain_equals_the_oracle_restatement(model_root, oracle_lib, hook, seed, secs, beam):
+    """Engine chain == oracle chain [REF src/batch_recognizer.cc:43-107,138-149]: identical result text (words, times,
+    confidences as printed), identical determinized and word-aligned lattices; also with the phone pass switched off in both."""
+    import vbmodel
+    mdir = model_root("tiny")
+    model = vbmodel.load_model_dir(mdir)
+    d, lat = _oracle_lattice(oracle_lib, model, secs, seed, beam)
+    rc = oracle_lib.ResultCtx(model)
+    want = oracle_lib.lattice_result(model, d, beam, rc=rc)
+    assert hook(mdir, lat, beam, 0) == want
+    assert json.loads(want)["text"] != "" or d["frames"] < 10
+    assert hook(mdir, lat, beam, 3) == oracle_lib.lattice_result(model, d, beam, rc=rc, nlsml=True)
+    for stage in (1, 2):
+        assert _same_lattice_text(hook(mdir, lat, beam, stage), oracle_lib.lattice_result(model, d, beam, rc=rc, stage=stage)), stage
+        # stage + 10: single (word) determinization pass in both
+        assert _same_lattice_text(hook(mdir, lat, beam, stage + 10), oracle_lib.lattice_result(model, d, beam, rc=rc, stage=stage, phone_pass=False)), stage
+
+
+def test_phone_pass_matters_beyond_the_beam(model_root, oracle_lib, hook):
+    """The two-pass (phone, then word) determinization and a single word pass keep the same word sequences inside the beam;
+    they may differ in the sequences beyond it (the pruning acts on different subset structures) — which is why the engine
+    runs both passes, as DeterminizeLatticePhonePrunedWrapper does."""
+    import vbmodel
+    mdir = model_root("tiny")
+    model = vbmodel.load_model_dir(mdir)
+    d, lat = _oracle_lattice(oracle_lib, model, 3.5, 44, 6.0)
+    one = {p[0]: p[1] + p[2] for p in _paths(*_parse(hook(mdir, lat, 6.0, 11)))}
+    two = {p[0]: p[1] + p[2] for p in _paths(*_parse(hook(mdir, lat, 6.0, 1)))}
+    best = min(two.values())
+    inside = lambda m: {w for w, c in m.items() if c <= best + 6.0 - 1e-3}
+    assert inside(one) == inside(two)
+    for w in inside(two):
+        assert abs(one[w] - two[w]) < 2e-3

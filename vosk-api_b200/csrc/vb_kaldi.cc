@@ -1058,6 +1058,7 @@ KaldiAm read_kaldi_final_mdl(const std::string &path) {
     if (n_tuples < 0) r.fail("bad tuple count");
     am.tid2pdf.assign(1, -1);
     am.tid2phone.assign(1, 0);
+    am.tid_flags.assign(1, 0);
     int max_pdf = -1;
     for (int32_t i = 0; i < n_tuples; i++) {
         const int32_t phone = r.i32(), hs = r.i32(), fwd = r.i32();
@@ -1068,6 +1069,8 @@ KaldiAm read_kaldi_final_mdl(const std::string &path) {
         for (int32_t d : e[(size_t)hs].dst) {
             am.tid2phone.push_back(phone);
             am.tid2pdf.push_back(d == hs ? self : fwd);
+            // TransitionModel::IsSelfLoop / IsFinal (the transition enters the topology's last, non-emitting state) / HMM state 0
+            am.tid_flags.push_back((uint8_t)((d == hs ? 1 : 0) | (d + 1 == (int32_t)e.size() ? 2 : 0) | (hs == 0 ? 4 : 0)));
         }
         max_pdf = std::max(max_pdf, std::max(fwd, self));
     }

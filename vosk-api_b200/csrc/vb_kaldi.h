@@ -41,6 +41,7 @@ struct KaldiAm {
     int feat_dim = 0, ivec_dim = 0, num_pdfs = 0, left_context = 0, right_context = 0;
     std::vector<KaldiOp> ops;            // op i produces node i + 1; node 0 is the "input" node
     std::vector<int32_t> tid2pdf, tid2phone;  // index = transition-id (entry 0 unused: -1 / 0)
+    std::vector<uint8_t> tid_flags;           // bit 0 self-loop, bit 1 enters the final HMM state, bit 2 leaves HMM state 0
 };
 // Reads final.mdl and compiles the nnet3 graph feeding output-node "output" into the collapsed op chain: every linear,
 // test-mode batchnorm, identity (dropout / no-op / spec-augment) component and every Append / Offset / Sum / Scale

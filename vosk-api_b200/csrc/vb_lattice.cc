@@ -1,460 +1,1027 @@
 // vb_lattice.cc — see vb_lattice.h.
 //
-// Everything here restates published Kaldi algorithms whose sources are NOT in /root/reference (they live in
-// alphacep/kaldi); the reference only names them at its call sites
-// [REF src/batch_recognizer.cc:45-54].  Stated differences:
-//   * determinization runs once on the word labels (Kaldi's wrapper first determinizes with phone boundaries
-//     inserted, then on words; both yield a word-deterministic lattice holding the best alignment per word sequence);
-//     tasks are expanded best-first on (forward cost + arc + exact backward cost), arcs beyond best + beam are dropped;
-//   * subsets are matched on exact states and strings and on weights within 1/1024 (Kaldi's kDelta);
-//   * there is no max_mem retry loop: if a lattice grows beyond kMaxDetStates the beam is halved and the
-//     determinization redone.
+// Everything here implements published Kaldi algorithms whose sources are NOT in /root/reference (they live in
+// alphacep/kaldi); the reference only names them at its call sites [REF src/batch_recognizer.cc:45-54]
+// and receives the determinized lattice from the cudadecoder pipeline [REF src/batch_recognizer.cc:138-149]:
+//   * DeterminizeLatticePhonePrunedWrapper, default options: Invert, phone labels inserted where a phone begins (not on
+//     the arcs leaving the start state), pruned determinization on phone + word labels, phone labels deleted, pruned
+//     determinization on the word labels, Connect.  Pruning: a transition is expanded only while forward cost + best
+//     completion stays within best + lattice_beam; subsets are matched on states, strings and total weight within 1/1024;
+//   * fst::ScaleLattice(GraphLatticeScale(0.9)) (evaluated in double);
+//   * WordAlignLattice (reorder = true, silence / partial-word label 0) with RemoveEpsLocal;
+//   * MinimumBayesRisk (Xu, Povey, Mangu, Zhu; decode_mbr = true, print_silence = false).
+// Layout: lattices are CSR arrays, strings live in a hash-consed trie, subsets / tuples in arenas with open-addressing
+// lookup; all of it in one per-thread workspace that is reused from segment to segment.
+// Stated differences: no max_mem / max_arcs retry loop (a lattice beyond kMaxDetStates output states fails and the caller
+// falls back to the best path, logged and counted); RemoveEpsLocal's stochasticity re-weighting is omitted (it moves weight
+// along a path without changing any path weight, and never triggers on a word-aligned lattice: the oracle, which has it,
+// counts zero non-trivial re-weights).
 #include "vb_lattice.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstring>
 #include <limits>
-#include <map>
 #include <queue>
-#include <unordered_map>
 
 namespace vb {
 
 namespace {
 constexpr float kInfF = std::numeric_limits<float>::infinity();
 constexpr double kInfD = std::numeric_limits<double>::infinity();
-constexpr int kMaxDetStates = 200000;
+constexpr int kMaxDetStates = 400000;
 constexpr float kDelta = 1.0f / 1024.0f;
+constexpr int kPhoneBase = 1 << 28;         // labels of the phone pass: kPhoneBase + phone
+constexpr int kSilTmp = -1, kPartialTmp = -2;  // temporary labels so that epsilon removal leaves these arcs alone
+constexpr int kDead = -7;                   // nextstate of an arc deleted by RemoveEpsLocal
 
-// fst::Compare(LatticeWeight): 1 if a is better (lower total cost, then lower graph cost)
-inline int compare_w(const LatWeight &a, const LatWeight &b) {
-    const float fa = a.g + a.a, fb = b.g + b.a;
-    if (fa < fb) return 1;
-    if (fa > fb) return -1;
-    if (a.g < b.g) return 1;
-    if (a.g > b.g) return -1;
+// fst::Compare(LatticeWeight): 1 if (g1, a1) is better (lower total cost, then lower graph cost)
+inline int compare_w(float g1, float a1, float g2, float a2) {
+    const float f1 = g1 + a1, f2 = g2 + a2;
+    if (f1 < f2) return 1;
+    if (f1 > f2) return -1;
+    if (g1 < g2) return 1;
+    if (g1 > g2) return -1;
     return 0;
 }
-inline LatWeight times_w(const LatWeight &a, const LatWeight &b) { return LatWeight{a.g + b.g, a.a + b.a}; }
-inline LatWeight divide_w(const LatWeight &a, const LatWeight &b) { return LatWeight{a.g - b.g, a.a - b.a}; }
-// LatticeDeterminizerPruned::Compare on strings: the shorter one is better, then the lexicographically larger (sic)
-inline int compare_str(const std::vector<int> &a, const std::vector<int> &b) {
-    if (a.size() > b.size()) return -1;
-    if (a.size() < b.size()) return 1;
-    for (size_t i = 0; i < a.size(); i++) {
-        if (a[i] < b[i]) return -1;
-        if (a[i] > b[i]) return 1;
-    }
-    return 0;
-}
+inline double cost_of(float g, float a) { return (double)g + (double)a; }  // ConvertToCost
 
-struct RArc {
-    int dst, word, tid;
-    LatWeight w;
+// ------------------------------------------------------------------------------------------------------------
+// flat lattice: input of a determinization pass (topologically numbered; arcs of a state sorted by il, epsilons first).
+// An arc stands for a chain of arcs of the lattice Kaldi would see (one symbol each): interior states of such a chain —
+// one arc in, one unlabelled arc out, not final — can hold no subset element that survives, so the chain is followed in
+// one step; its weights are still added one by one, in order, so every float sum is the one Kaldi forms.
+// ------------------------------------------------------------------------------------------------------------
+struct Sym {  // one arc of the uncompressed lattice: its string symbol (0 = none) and weight
+    int tid;
+    float g, a;
 };
-struct RLat {
-    int start = -1;
-    std::vector<std::vector<RArc>> arcs;
-    std::vector<float> final_cost;  // inf = not final
+struct FArc {
+    int il;            // label determinized on (0 = epsilon), carried by the first arc of the chain
+    int s_off, s_len;  // the chain, as a span of the pass's Sym pool (s_len >= 1)
+    int next;
+};
+struct Edge {
+    int src;
+    FArc a;
+};
+struct FLat {
+    int start = -1, n = 0;
+    std::vector<int> off;
+    std::vector<FArc> arcs;
+    std::vector<float> fin_g, fin_a;  // fin_g = +inf: not final
+    const std::vector<Sym> *syms = nullptr;
+};
+struct MEdge {  // arc of the word-aligned lattice as MinimumBayesRisk sees it
+    int src, word, len, next;
+    float loglike;
+};
+
+// open-addressing table hash -> id (entries are never removed; equality is the caller's)
+struct IdTable {
+    std::vector<uint64_t> hash;
+    std::vector<int> id;
+    size_t used = 0, mask = 0;
+    void reset(size_t cap_pow2) {
+        if (hash.size() != cap_pow2) {
+            hash.assign(cap_pow2, 0);
+            id.assign(cap_pow2, -1);
+        } else {
+            std::fill(id.begin(), id.end(), -1);
+        }
+        mask = cap_pow2 - 1;
+        used = 0;
+    }
+    template <class Eq>
+    int find(uint64_t h, Eq eq) const {
+        for (size_t i = h & mask;; i = (i + 1) & mask) {
+            if (id[i] < 0) return -1;
+            if (hash[i] == h && eq(id[i])) return id[i];
+        }
+    }
+    void insert(uint64_t h, int v) {
+        if ((used + 1) * 2 > hash.size()) grow();
+        size_t i = h & mask;
+        while (id[i] >= 0) i = (i + 1) & mask;
+        hash[i] = h;
+        id[i] = v;
+        used++;
+    }
+    void grow() {
+        std::vector<uint64_t> oh;
+        std::vector<int> oi;
+        oh.swap(hash);
+        oi.swap(id);
+        hash.assign(oh.size() * 2, 0);
+        id.assign(oi.size() * 2, -1);
+        mask = hash.size() - 1;
+        used = 0;
+        for (size_t k = 0; k < oi.size(); k++)
+            if (oi[k] >= 0) insert(oh[k], oi[k]);
+    }
+};
+inline uint64_t mix(uint64_t h, uint64_t v) {
+    h = (h ^ v) * 0x9e3779b97f4a7c15ull;
+    return h ^ (h >> 29);
+}
+
+// LatticeStringRepository: trie of symbol strings; id 0 = the empty string.  Strings that are stored in subsets are canonical
+// (hash-consed from the root: equal content = equal id); the strings built while arcs are followed are plain appended
+// nodes (no lookup), compared by content where it matters.
+struct Repo {
+    std::vector<int> parent, label, depth;
+    std::vector<char> canon;
+    IdTable tab;
+    std::vector<int> tmp;
+    void reset() {
+        parent.assign(1, -1);
+        label.assign(1, 0);
+        depth.assign(1, 0);
+        canon.assign(1, 1);
+        tab.reset(1 << 12);
+    }
+    int append(int id, int lab) {
+        const int k = (int)parent.size();
+        parent.push_back(id);
+        label.push_back(lab);
+        depth.push_back(depth[id] + 1);
+        canon.push_back(0);
+        return k;
+    }
+    int succ(int id, int lab) {  // canonical successor of a canonical string
+        const uint64_t h = mix((uint64_t)(uint32_t)id, (uint64_t)(uint32_t)lab);
+        const int f = tab.find(h, [&](int k) { return parent[k] == id && label[k] == lab; });
+        if (f >= 0) return f;
+        const int k = append(id, lab);
+        canon[k] = 1;
+        tab.insert(h, k);
+        return k;
+    }
+    // a node of x's ancestry that spells the longest common prefix of x and y (by content)
+    int common_prefix(int x, int y) const {
+        while (depth[x] > depth[y]) x = parent[x];
+        while (depth[y] > depth[x]) y = parent[y];
+        int ans = x;
+        while (x != y) {
+            if (label[x] != label[y]) ans = parent[x];
+            x = parent[x];
+            y = parent[y];
+        }
+        return ans;
+    }
+    int remove_prefix(int id, int n) {  // canonical id of the string without its first n symbols
+        if (n == 0 && canon[id]) return id;
+        tmp.clear();
+        for (int k = id; depth[k] > n; k = parent[k]) tmp.push_back(label[k]);
+        int r = 0;
+        for (size_t i = tmp.size(); i-- > 0;) r = succ(r, tmp[i]);
+        return r;
+    }
+    int concat(int x, int y) {  // (not canonical: only the content of an output string matters)
+        if (y == 0) return x;
+        if (x == 0) return y;
+        tmp.clear();
+        for (int k = y; k > 0; k = parent[k]) tmp.push_back(label[k]);
+        for (size_t i = tmp.size(); i-- > 0;) x = append(x, tmp[i]);
+        return x;
+    }
+    void to_vec(int id, std::vector<int> *out) const {
+        const size_t base = out->size();
+        out->resize(base + depth[id]);
+        for (int k = id, i = depth[id]; k > 0; k = parent[k]) (*out)[base + --i] = label[k];
+    }
+    // LatticeDeterminizerPruned::Compare on strings: the shorter one is better, then the lexicographically larger (sic)
+    int compare(int x, int y) const {
+        if (x == y) return 0;
+        if (depth[x] > depth[y]) return -1;
+        if (depth[x] < depth[y]) return 1;
+        int res = 0;  // decided by the first differing symbol = the mismatch closest to the root
+        while (x != y) {
+            if (label[x] != label[y]) res = label[x] < label[y] ? -1 : 1;
+            x = parent[x];
+            y = parent[y];
+        }
+        return res;
+    }
 };
 
 struct Elem {
-    int state;
-    LatWeight w;
-    std::vector<int> str;
+    int state, str;
+    float g, a;
 };
-inline int compare_elem(const LatWeight &aw, const std::vector<int> &as, const LatWeight &bw, const std::vector<int> &bs) {
-    const int c = compare_w(aw, bw);
-    return c ? c : compare_str(as, bs);
-}
+struct TArc {  // output transition of a determinization pass; next = -1: this is the final weight of src
+    int src, label, str, next;
+    float g, a;
+};
 
-RLat build_raw(const RawLattice &raw, const LatticeCtx &ctx) {
-    RLat r;
-    r.start = raw.start;
-    r.arcs.resize(raw.n_states);
-    r.final_cost.assign(raw.n_states, kInfF);
-    const Graph &g = *ctx.graph;
-    for (size_t k = 0; k < raw.src.size(); k++) {
-        const int a = raw.arc[k];
-        if (raw.src[k] < 0 || raw.dst[k] < 0 || a < 0 || a >= g.num_arcs) continue;
-        r.arcs[raw.src[k]].push_back(RArc{raw.dst[k], g.arc_olabel[a], g.arc_ilabel[a], LatWeight{g.arc_w[a], raw.acoustic[k]}});
+// compact lattice in CSR form (output of the word pass; input of the word aligner)
+struct CArcF {
+    int label;
+    float g, a;
+    int t_off, t_len;  // transition-id string in CLatF::tids
+    int next;
+};
+struct CLatF {
+    int start = -1, n = 0;
+    std::vector<int> off;
+    std::vector<CArcF> arcs;
+    std::vector<char> is_final;
+    std::vector<float> fin_g, fin_a;
+    std::vector<int> fin_off, fin_len;
+    std::vector<int> tids;
+};
+
+// word-aligned lattice: arcs of a state form a linked list in insertion order (RemoveEpsLocal appends while it iterates)
+struct AArc {
+    int label;
+    float g, a;
+    int t_off, t_len;  // span in Workspace::seq
+    int next, link;
+};
+struct ALat {
+    int start = -1;
+    std::vector<AArc> arcs;
+    std::vector<int> head, tail;
+    std::vector<char> is_final;
+    std::vector<float> fin_g, fin_a;
+    int add_state() {
+        head.push_back(-1);
+        tail.push_back(-1);
+        is_final.push_back(0);
+        fin_g.push_back(0.f);
+        fin_a.push_back(0.f);
+        return (int)head.size() - 1;
     }
-    for (size_t k = 0; k < raw.final_state.size(); k++)
-        if (raw.final_state[k] >= 0 && raw.final_state[k] < raw.n_states) r.final_cost[raw.final_state[k]] = raw.final_cost[k];
-    return r;
+    void add_arc(int s, const AArc &a) {
+        const int k = (int)arcs.size();
+        arcs.push_back(a);
+        arcs[k].link = -1;
+        if (tail[s] < 0) head[s] = k;
+        else arcs[tail[s]].link = k;
+        tail[s] = k;
+    }
+    void clear() {
+        start = -1;
+        arcs.clear();
+        head.clear();
+        tail.clear();
+        is_final.clear();
+        fin_g.clear();
+        fin_a.clear();
+    }
+    int n() const { return (int)head.size(); }
+};
+
+struct Workspace {
+    // build_flat
+    std::vector<int> csr_off, csr_idx, order, dfs_stack, dfs_pos;
+    std::vector<char> color;
+    std::vector<Edge> edges, edges2;
+    std::vector<MEdge> medges;
+    std::vector<Sym> sym_in, sym1, sym2;
+    std::vector<float> fin_g, fin_a;
+    FLat lat1, lat2;
+    // determinizer
+    Repo repo;
+    std::vector<Elem> pool, cur, sub, allv;
+    std::vector<int> all_label;
+    std::vector<double> all_prio, bw_first;
+    std::vector<int> heap, stamp, done, slot, idx;
+    std::vector<char> keepable;
+    std::vector<double> backward;
+    std::vector<TArc> tarcs;
+    IdTable min_tab, init_tab;
+    std::vector<int> tvec;
+    CLatF clat;
+    // aligner
+    std::vector<int> seq, wseq;
+    ALat ali;
+    IdTable tup_tab;
+    std::vector<int> nin, nout, remap, stack;
+    // mbr
+    std::vector<double> alpha, alpha_dash, beta_dash, post;
+    std::vector<char> b_arc;
+    std::vector<int> lo, hi;
+};
+Workspace &workspace() {
+    static thread_local Workspace w;
+    return w;
 }
 
-// states reachable from the start, in topological order (the lattice is acyclic)
-template <class ArcsOf>
-std::vector<int> topo_order(int n, int start, ArcsOf arcs_of) {
-    std::vector<int> indeg(n, 0), order;
-    std::vector<char> seen(n, 0);
-    std::vector<int> stack{start};
-    seen[start] = 1;
-    while (!stack.empty()) {
-        int s = stack.back();
-        stack.pop_back();
-        arcs_of(s, [&](int d) {
-            indeg[d]++;
-            if (!seen[d]) {
-                seen[d] = 1;
-                stack.push_back(d);
+// Chain compression: an edge absorbs the arcs behind it as long as it ends in an interior state (exactly one arc in, one
+// unlabelled arc out, not final, not the start).  The symbols / weights of the absorbed arcs are appended to its span.
+static int g_comp_pass = 0;
+void compress_chains(Workspace &ws, int n, int start, const std::vector<Edge> &in, const std::vector<float> &fin_g,
+                     const std::vector<Sym> &syms_in, std::vector<Edge> *out, std::vector<Sym> *syms_out) {
+    std::vector<int> &indeg = ws.nin, &outdeg = ws.nout, &out_edge = ws.remap;
+    indeg.assign(n, 0);
+    outdeg.assign(n, 0);
+    out_edge.assign(n, -1);
+    for (size_t k = 0; k < in.size(); k++) {
+        indeg[in[k].a.next]++;
+        outdeg[in[k].src]++;
+        out_edge[in[k].src] = (int)k;
+    }
+    const bool off_ = getenv("VB_NOCOMP") && atoi(getenv("VB_NOCOMP")) == g_comp_pass;
+    auto interior = [&](int x) {
+        return !off_ && x != start && indeg[x] == 1 && outdeg[x] == 1 && fin_g[x] == kInfF && in[out_edge[x]].a.il == 0;
+    };
+    out->clear();
+    syms_out->clear();
+    for (const Edge &e : in) {
+        if (interior(e.src)) continue;  // absorbed by the edge that leads here
+        Edge o = e;
+        o.a.s_off = (int)syms_out->size();
+        syms_out->insert(syms_out->end(), syms_in.begin() + e.a.s_off, syms_in.begin() + e.a.s_off + e.a.s_len);
+        while (interior(o.a.next)) {
+            const FArc &nx = in[out_edge[o.a.next]].a;
+            syms_out->insert(syms_out->end(), syms_in.begin() + nx.s_off, syms_in.begin() + nx.s_off + nx.s_len);
+            o.a.next = nx.next;
+        }
+        o.a.s_len = (int)syms_out->size() - o.a.s_off;
+        out->push_back(o);
+    }
+}
+
+// Topological numbering (reverse DFS finishing order from the start state; unreachable states are dropped) and CSR
+// construction with the arcs of a state ordered by il.  fin_g/fin_a are indexed by the old state ids.
+bool build_flat(Workspace &ws, int n_old, int start_old, const std::vector<Edge> &edges, const std::vector<float> &fin_g,
+                const std::vector<float> &fin_a, const std::vector<Sym> *syms, FLat *out) {
+    out->start = -1;
+    out->n = 0;
+    out->arcs.clear();
+    out->syms = syms;
+    if (start_old < 0 || start_old >= n_old) return false;
+    std::vector<int> &off = ws.csr_off, &idx = ws.csr_idx, &order = ws.order;
+    off.assign(n_old + 1, 0);
+    for (const Edge &e : edges) off[e.src + 1]++;
+    for (int s = 0; s < n_old; s++) off[s + 1] += off[s];
+    idx.resize(edges.size());
+    std::vector<int> &st = ws.dfs_stack, &pos = ws.dfs_pos, &finish = ws.stack;
+    pos.assign(off.begin(), off.end() - 1);
+    for (size_t k = 0; k < edges.size(); k++) idx[pos[edges[k].src]++] = (int)k;
+    order.assign(n_old, -1);
+    ws.color.assign(n_old, 0);
+    st.clear();
+    finish.clear();
+    pos.assign(off.begin(), off.end() - 1);
+    st.push_back(start_old);
+    ws.color[start_old] = 1;
+    while (!st.empty()) {
+        const int s = st.back();
+        if (pos[s] < off[s + 1]) {
+            const int d = edges[idx[pos[s]++]].a.next;
+            if (ws.color[d] == 1) return false;  // a cycle: not a lattice
+            if (!ws.color[d]) {
+                ws.color[d] = 1;
+                st.push_back(d);
             }
-        });
+        } else {
+            ws.color[s] = 2;
+            finish.push_back(s);
+            st.pop_back();
+        }
     }
-    stack.push_back(start);
-    while (!stack.empty()) {
-        int s = stack.back();
-        stack.pop_back();
-        order.push_back(s);
-        arcs_of(s, [&](int d) {
-            if (--indeg[d] == 0) stack.push_back(d);
-        });
+    const int n = (int)finish.size();
+    for (int i = 0; i < n; i++) order[finish[n - 1 - i]] = i;
+    out->n = n;
+    out->start = order[start_old];
+    out->off.assign(n + 1, 0);
+    for (const Edge &e : edges)
+        if (order[e.src] >= 0) out->off[order[e.src] + 1]++;
+    for (int s = 0; s < n; s++) out->off[s + 1] += out->off[s];
+    out->arcs.resize(out->off[n]);
+    pos.assign(out->off.begin(), out->off.end() - 1);
+    for (const Edge &e : edges) {
+        const int s = order[e.src];
+        if (s < 0) continue;
+        FArc a = e.a;
+        a.next = order[a.next];
+        // insertion by il keeps the edge order among equal labels
+        int p = pos[s]++;
+        while (p > out->off[s] && out->arcs[p - 1].il > a.il) {
+            out->arcs[p] = out->arcs[p - 1];
+            p--;
+        }
+        out->arcs[p] = a;
     }
-    return order;
+    out->fin_g.assign(n, kInfF);
+    out->fin_a.assign(n, kInfF);
+    for (int s = 0; s < n_old; s++)
+        if (order[s] >= 0 && s < (int)fin_g.size()) {
+            out->fin_g[order[s]] = fin_g[s];
+            out->fin_a[order[s]] = fin_a[s];
+        }
+    return true;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// LatticeDeterminizerPruned
+// ------------------------------------------------------------------------------------------------------------
 class Determinizer {
    public:
-    Determinizer(const RLat &in, float beam) : in_(in), beam_(beam) {}
+    Determinizer(Workspace &ws, const FLat &in, double beam) : ws_(ws), in_(in), sy_(in.syms->data()), beam_(beam), repo_(ws.repo) {}
 
-    bool run(CLat *out) {
-        out_ = out;
-        *out = CLat();
-        if (in_.start < 0) return false;
-        backward_costs();
-        if (beta_[in_.start] == kInfD) return false;
-        cutoff_ = beta_[in_.start] + beam_;
-        std::vector<Elem> sub{Elem{in_.start, LatWeight{}, {}}};
-        closure(&sub);
-        to_minimal(&sub);
-        LatWeight w0;
-        std::vector<int> s0;
-        normalize(&sub, &w0, &s0);
-        const int first = new_state(sub, (double)w0.cost());
-        if (w0.g != 0.f || w0.a != 0.f || !s0.empty()) {
-            const int st = out_->add_state();  // extra start state carrying the initial weight / string
-            states_.push_back(OutState{{}, 0.0});  // keeps states_ aligned with the output state ids
-            out_->arcs[st].push_back(CLatArc{first, 0, w0, s0});
-            out_->start = st;
-        } else {
-            out_->start = first;
+    bool run() {
+        repo_.reset();
+        ws_.pool.clear();
+        ws_.tarcs.clear();
+        states_.clear();
+        ws_.min_tab.reset(1 << 12);
+        ws_.init_tab.reset(1 << 12);
+        inits_.clear();
+        const int n = in_.n;
+        if (n == 0 || in_.start < 0) return false;
+        // ComputeBackwardWeight (per arc of the uncompressed lattice: the chain is walked from its end)
+        ws_.backward.assign(n, kInfD);
+        ws_.keepable.assign(n, 0);
+        ws_.bw_first.resize(in_.arcs.size());
+        for (int s = n - 1; s >= 0; s--) {
+            double c = in_.fin_g[s] == kInfF ? kInfD : cost_of(in_.fin_g[s], in_.fin_a[s]);
+            bool keep = in_.fin_g[s] != kInfF;
+            for (int k = in_.off[s]; k < in_.off[s + 1]; k++) {
+                const FArc &a = in_.arcs[k];
+                const Sym *sy = sy_ + a.s_off;
+                double b = ws_.backward[a.next];
+                for (int j = a.s_len - 1; j >= 1; j--) b = cost_of(sy[j].g, sy[j].a) + b;
+                ws_.bw_first[k] = b;  // the backward cost of the state behind the chain's first arc
+                c = std::min(c, cost_of(sy[0].g, sy[0].a) + b);
+                keep = keep || a.il != 0;
+            }
+            ws_.backward[s] = c;
+            ws_.keepable[s] = keep;
         }
-        process_state(first);
+        if (ws_.backward[in_.start] == kInfD) return false;
+        cutoff_ = ws_.backward[in_.start] + beam_;
+        ws_.stamp.assign(n, 0);
+        ws_.done.assign(n, 0);
+        ws_.slot.assign(n, 0);
+        epoch_ = 0;
+        // the start subset is not normalized (its weight and string stay inside it)
+        std::vector<Elem> &sub = ws_.sub;
+        sub.clear();
+        sub.push_back(Elem{in_.start, 0, 0.f, 0.f});
+        closure(&sub);
+        for (Elem &e : sub) e.str = repo_.remove_prefix(e.str, 0);  // canonical strings, so that an equal subset can match
+        new_state(sub, 0.0);
         while (!tasks_.empty()) {
-            if ((int)out_->num_states() > kMaxDetStates) return false;
-            Task t = tasks_.top();
+            if ((int)states_.size() > kMaxDetStates) return false;
+            const Task t = tasks_.top();
             tasks_.pop();
-            bool is_new = false;
-            const int dst = find_or_add(*t.subset, states_[t.src].fwd + (double)t.w.cost(), &is_new);
-            out_->arcs[t.src].push_back(CLatArc{dst, t.label, t.w, t.str});
-            if (is_new) process_state(dst);
+            process_transition(t);
         }
         return true;
     }
+    int num_states() const { return (int)states_.size(); }
 
    private:
     struct OutState {
-        std::vector<Elem> subset;
+        int off, len;
         double fwd;
     };
     struct Task {
         double prio;
-        int src, label;
-        std::shared_ptr<std::vector<Elem>> subset;
-        LatWeight w;
-        std::vector<int> str;
-        bool operator<(const Task &o) const { return prio > o.prio; }  // min-heap
+        int src, label, off, len;
+        bool operator<(const Task &o) const { return prio > o.prio; }  // min-heap on the priority cost
+    };
+    struct Init {  // an initial (pre-closure) subset that has been seen, and where it leads
+        int off, len, state, str;
+        float g, a;
     };
 
-    void backward_costs() {
-        const int n = (int)in_.arcs.size();
-        beta_.assign(n, kInfD);
-        auto arcs_of = [&](int s, auto f) {
-            for (const RArc &a : in_.arcs[s]) f(a.dst);
-        };
-        std::vector<int> order = topo_order(n, in_.start, arcs_of);
-        topo_.assign(n, n);
-        for (size_t i = 0; i < order.size(); i++) topo_[order[i]] = (int)i;
-        stamp_.assign(n, 0);
-        slot_.assign(n, 0);
-        keepable_.assign(n, 0);
-        for (int s2 = 0; s2 < n; s2++) {
-            bool k = in_.final_cost[s2] != kInfF;
-            for (const RArc &a : in_.arcs[s2]) k = k || a.word != 0;
-            keepable_[s2] = k;
+    static uint64_t hash_of(const Elem *e, int n) {
+        uint64_t h = (uint64_t)n;
+        for (int i = 0; i < n; i++) h = mix(h, ((uint64_t)(uint32_t)e[i].state << 32) | (uint32_t)e[i].str);
+        return h;
+    }
+    static bool same_subset(const Elem *x, const Elem *y, int n) {
+        for (int i = 0; i < n; i++) {
+            if (x[i].state != y[i].state || x[i].str != y[i].str) return false;
+            const float fx = x[i].g + x[i].a, fy = y[i].g + y[i].a;
+            if (fx != fy && !(std::fabs(fx - fy) <= kDelta)) return false;
         }
-        for (auto it = order.rbegin(); it != order.rend(); ++it) {
-            const int s = *it;
-            double b = in_.final_cost[s] == kInfF ? kInfD : (double)in_.final_cost[s];
-            for (const RArc &a : in_.arcs[s])
-                if (beta_[a.dst] != kInfD) b = std::min(b, (double)a.w.cost() + beta_[a.dst]);
-            beta_[s] = b;
+        return true;
+    }
+    int compare_ws(float g1, float a1, int s1, float g2, float a2, int s2) const {
+        const int c = compare_w(g1, a1, g2, a2);
+        return c ? c : repo_.compare(s1, s2);
+    }
+    // Times(elem.weight, arc.weight) arc by arc along the chain (from its `from`-th arc on); the string is built only when needed
+    inline void walk_weight(const FArc &arc, int from, float *g, float *a) const {
+        const Sym *sy = sy_ + arc.s_off;
+        for (int j = from; j < arc.s_len; j++) {
+            *g += sy[j].g;
+            *a += sy[j].a;
         }
+    }
+    inline int walk_string(const FArc &arc, int from, int str) {
+        const Sym *sy = sy_ + arc.s_off;
+        for (int j = from; j < arc.s_len; j++)
+            if (sy[j].tid) str = repo_.append(str, sy[j].tid);
+        return str;
     }
 
-    // Follow arcs without a word label; per state keep the best (weight, then string) element; then drop the elements
-    // whose state neither is final nor has an arc with a word label (ConvertToMinimal).  The raw lattice is acyclic, so
-    // states are expanded in topological order (each once, after all its predecessors inside the closure); strings grow
-    // as parent-linked nodes in an arena and are materialised only for the elements that survive.
-    struct SNode { int parent, tid; };
-    struct Work { int state; LatWeight w; int base, node; };  // string = input element `base`'s string + arena path `node`
-    std::vector<int> materialize(const std::vector<Elem> &in, const Work &x, const std::vector<SNode> &arena) const {
-        std::vector<int> tail;
-        for (int n = x.node; n >= 0; n = arena[n].parent) tail.push_back(arena[n].tid);
-        std::vector<int> out(in[x.base].str);
-        out.insert(out.end(), tail.rbegin(), tail.rend());
-        return out;
-    }
-    void closure_minimal(std::vector<Elem> *sub) {
-        const std::vector<Elem> &in = *sub;
-        std::vector<Work> cur;
-        std::vector<SNode> arena;
+    // EpsilonClosure + ConvertToMinimal: follow the arcs without a label; per state keep the best (weight, string); drop
+    // the elements whose state neither is final nor has a labelled arc.  States are numbered topologically, so a state
+    // popped from the min-heap has its final element.  An element with state >= n sits inside the chain of arc
+    // (state - n), behind its first (labelled) arc: that is where Kaldi's initial subsets live, and what they are keyed on.
+    // The result is sorted by state.
+    void closure(std::vector<Elem> *sub) {
+        std::vector<Elem> &cur = ws_.cur;
+        std::vector<int> &heap = ws_.heap;
+        cur.clear();
+        heap.clear();
         epoch_++;
-        typedef std::pair<int, int> QE;  // (topological index, work index)
-        std::priority_queue<QE, std::vector<QE>, std::greater<QE>> heap;
-        for (size_t i = 0; i < in.size(); i++) {
-            cur.push_back(Work{in[i].state, in[i].w, (int)i, -1});
-            stamp_[in[i].state] = epoch_;
-            slot_[in[i].state] = (int)i;
-            heap.push(QE(topo_[in[i].state], (int)i));
-        }
-        std::vector<char> done;
-        while (!heap.empty()) {
-            const int i = heap.top().second;
-            heap.pop();
-            if ((int)done.size() < (int)cur.size()) done.resize(cur.size(), 0);
-            if (done[i]) continue;
-            done[i] = 1;
-            const Work e = cur[i];
-            for (const RArc &a : in_.arcs[e.state]) {
-                if (a.word != 0) continue;
-                int node = e.node;
-                if (a.tid != 0) {
-                    arena.push_back(SNode{e.node, a.tid});
-                    node = (int)arena.size() - 1;
+        const int n = in_.n;
+        // one relaxation: the element (weight ng/na, string made by mk()) arrives at state `to`
+        auto relax = [&](int to, float ng, float na, auto mk) {
+            if (ws_.stamp[to] != epoch_) {
+                ws_.stamp[to] = epoch_;
+                ws_.slot[to] = (int)cur.size();
+                cur.push_back(Elem{to, mk(), ng, na});
+                heap.push_back(to);
+                std::push_heap(heap.begin(), heap.end(), std::greater<int>());
+            } else {
+                Elem &old = cur[ws_.slot[to]];
+                int c = compare_w(ng, na, old.g, old.a);
+                int nstr = -1;
+                if (c == 0) {
+                    nstr = mk();
+                    c = repo_.compare(nstr, old.str);
                 }
-                Work nx{a.dst, times_w(e.w, a.w), e.base, node};
-                if (stamp_[a.dst] != epoch_) {
-                    stamp_[a.dst] = epoch_;
-                    slot_[a.dst] = (int)cur.size();
-                    cur.push_back(nx);
-                    heap.push(QE(topo_[a.dst], (int)cur.size() - 1));
-                } else {
-                    Work &old = cur[slot_[a.dst]];
-                    int c = compare_w(nx.w, old.w);
-                    if (c == 0) c = compare_str(materialize(in, nx, arena), materialize(in, old, arena));
-                    if (c == 1) old = nx;  // (its successors have not been expanded yet: topological order)
+                if (c == 1) {
+                    if (nstr < 0) nstr = mk();
+                    old.str = nstr;
+                    old.g = ng;
+                    old.a = na;
                 }
             }
-        }
-        std::vector<Elem> keep;
-        for (const Work &x : cur)
-            if (keepable_[x.state]) keep.push_back(Elem{x.state, x.w, materialize(in, x, arena)});
-        std::sort(keep.begin(), keep.end(), [](const Elem &x, const Elem &y) { return x.state < y.state; });
-        sub->swap(keep);
-    }
-    void closure(std::vector<Elem> *sub) { closure_minimal(sub); }
-    void to_minimal(std::vector<Elem> *) {}  // (folded into closure_minimal)
-
-    // take the best weight and the longest common string prefix out of the subset
-    void normalize(std::vector<Elem> *sub, LatWeight *tot, std::vector<int> *common) {
-        *tot = LatWeight{};
-        common->clear();
-        if (sub->empty()) return;
-        LatWeight best = (*sub)[0].w;
-        size_t pre = (*sub)[0].str.size();
+        };
         for (const Elem &e : *sub) {
-            if (compare_w(e.w, best) == 1) best = e.w;
-            size_t k = 0;
-            while (k < pre && k < e.str.size() && e.str[k] == (*sub)[0].str[k]) k++;
-            pre = k;
+            if (e.state >= n) continue;
+            ws_.stamp[e.state] = epoch_;
+            ws_.slot[e.state] = (int)cur.size();
+            cur.push_back(e);
+            heap.push_back(e.state);
         }
-        common->assign((*sub)[0].str.begin(), (*sub)[0].str.begin() + pre);
-        for (Elem &e : *sub) {
-            e.w = divide_w(e.w, best);
-            e.str.erase(e.str.begin(), e.str.begin() + pre);
+        std::make_heap(heap.begin(), heap.end(), std::greater<int>());
+        for (const Elem &e : *sub) {
+            if (e.state < n) continue;
+            const FArc &arc = in_.arcs[e.state - n];
+            float ng = e.g, na = e.a;
+            walk_weight(arc, 1, &ng, &na);
+            relax(arc.next, ng, na, [&] { return walk_string(arc, 1, e.str); });
         }
-        *tot = best;
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end(), std::greater<int>());
+            const int s = heap.back();
+            heap.pop_back();
+            if (ws_.done[s] == epoch_) continue;
+            ws_.done[s] = epoch_;
+            const Elem e = cur[ws_.slot[s]];
+            for (int k = in_.off[s]; k < in_.off[s + 1]; k++) {
+                const FArc &arc = in_.arcs[k];
+                if (arc.il != 0) break;  // sorted: no more epsilons
+                float ng = e.g, na = e.a;
+                walk_weight(arc, 0, &ng, &na);
+                relax(arc.next, ng, na, [&] { return walk_string(arc, 0, e.str); });
+            }
+        }
+        sub->clear();
+        for (const Elem &e : cur)
+            if (ws_.keepable[e.state]) sub->push_back(e);
+        std::sort(sub->begin(), sub->end(), [](const Elem &x, const Elem &y) { return x.state < y.state; });
     }
 
-    static std::string key_of(const std::vector<Elem> &sub) {
-        std::string k;
-        for (const Elem &e : sub) {
-            k.append(reinterpret_cast<const char *>(&e.state), 4);
-            const int n = (int)e.str.size();
-            k.append(reinterpret_cast<const char *>(&n), 4);
-            k.append(reinterpret_cast<const char *>(e.str.data()), (size_t)n * 4);
+    // NormalizeSubset: take the best weight and the longest common string prefix out of the subset
+    void normalize(Elem *e, int n, float *tg, float *ta, int *common) {
+        if (n == 0) {
+            *tg = *ta = kInfF;
+            *common = 0;
+            return;
         }
-        return k;
+        float bg = e[0].g, ba = e[0].a;
+        int pre = e[0].str;
+        for (int i = 1; i < n; i++) {
+            if (compare_w(bg, ba, e[i].g, e[i].a) < 0) {
+                bg = e[i].g;
+                ba = e[i].a;
+            }
+            pre = repo_.common_prefix(pre, e[i].str);
+        }
+        const int plen = repo_.depth[pre];
+        for (int i = 0; i < n; i++) {
+            e[i].g -= bg;
+            e[i].a -= ba;
+            e[i].str = repo_.remove_prefix(e[i].str, plen);
+        }
+        *tg = bg;
+        *ta = ba;
+        *common = pre;
     }
+
     int new_state(const std::vector<Elem> &sub, double fwd) {
-        const int id = out_->add_state();
-        states_.push_back(OutState{sub, fwd});
-        index_[key_of(sub)].push_back(id);
+        const int id = (int)states_.size();
+        const int off = (int)ws_.pool.size();
+        ws_.pool.insert(ws_.pool.end(), sub.begin(), sub.end());
+        states_.push_back(OutState{off, (int)sub.size(), fwd});
+        ws_.min_tab.insert(hash_of(sub.data(), (int)sub.size()), id);
+        process_final(id);
+        process_transitions(id);
         return id;
     }
-    int find_or_add(const std::vector<Elem> &sub, double fwd, bool *is_new) {
-        auto it = index_.find(key_of(sub));
-        if (it != index_.end())
-            for (int id : it->second) {
-                const std::vector<Elem> &o = states_[id].subset;
-                bool same = true;
-                for (size_t i = 0; i < sub.size() && same; i++)
-                    same = std::fabs(sub[i].w.g - o[i].w.g) <= kDelta && std::fabs(sub[i].w.a - o[i].w.a) <= kDelta;
-                if (same) {
-                    *is_new = false;
-                    return id;
-                }
-            }
-        *is_new = true;
-        return new_state(sub, fwd);
+    int minimal_to_state(const std::vector<Elem> &sub, double fwd) {
+        const int n = (int)sub.size();
+        const int f = ws_.min_tab.find(hash_of(sub.data(), n), [&](int id) {
+            return states_[id].len == n && same_subset(&ws_.pool[states_[id].off], sub.data(), n);
+        });
+        return f >= 0 ? f : new_state(sub, fwd);
     }
 
-    void process_state(int s) {
-        const std::vector<Elem> subset = states_[s].subset;  // copy: states_ may grow
-        const double fwd = states_[s].fwd;
-        // final weight: best of element weight x final weight of its state
-        bool have = false;
-        LatWeight fw;
-        std::vector<int> fs;
-        for (const Elem &e : subset) {
-            if (in_.final_cost[e.state] == kInfF) continue;
-            const LatWeight w = times_w(e.w, LatWeight{in_.final_cost[e.state], 0.f});
-            if (!have || compare_elem(w, e.str, fw, fs) == 1) {
-                fw = w;
+    void process_final(int sid) {
+        const OutState st = states_[sid];
+        bool is_final = false;
+        float fg = kInfF, fa = kInfF;
+        int fs = 0;
+        for (int i = 0; i < st.len; i++) {
+            const Elem e = ws_.pool[st.off + i];
+            if (in_.fin_g[e.state] == kInfF) continue;
+            const float g = e.g + in_.fin_g[e.state], a = e.a + in_.fin_a[e.state];
+            if (!is_final || compare_ws(g, a, e.str, fg, fa, fs) == 1) {
+                is_final = true;
+                fg = g;
+                fa = a;
                 fs = e.str;
-                have = true;
             }
         }
-        if (have) {
-            out_->is_final[s] = 1;
-            out_->final_w[s] = fw;
-            out_->final_tids[s] = fs;
-        }
-        std::map<int, std::vector<Elem>> by_label;
-        for (const Elem &e : subset)
-            for (const RArc &a : in_.arcs[e.state]) {
-                if (a.word == 0) continue;
-                Elem nx{a.dst, times_w(e.w, a.w), e.str};
-                if (a.tid != 0) nx.str.push_back(a.tid);
-                by_label[a.word].push_back(std::move(nx));
+        if (is_final && cost_of(fg, fa) + st.fwd <= cutoff_) ws_.tarcs.push_back(TArc{sid, 0, fs, -1, fg, fa});
+    }
+
+    void process_transitions(int sid) {
+        const OutState st = states_[sid];
+        std::vector<Elem> &all = ws_.allv;
+        std::vector<int> &lab = ws_.all_label, &idx = ws_.idx;
+        std::vector<double> &pri = ws_.all_prio;
+        all.clear();
+        lab.clear();
+        pri.clear();
+        for (int i = 0; i < st.len; i++) {
+            const Elem e = ws_.pool[st.off + i];
+            for (int k = in_.off[e.state + 1] - 1; k >= in_.off[e.state]; k--) {
+                const FArc &arc = in_.arcs[k];
+                if (arc.il == 0) break;  // sorted: the labelled arcs are at the end
+                // the priority is taken where Kaldi takes it: behind the labelled (first) arc of the chain
+                const Sym &s0 = sy_[arc.s_off];
+                const float ng = e.g + s0.g, na = e.a + s0.a;
+                pri.push_back(cost_of(ng, na) + ws_.bw_first[k]);
+                // the element behind the labelled arc: at the arc's end, or inside its chain (state id n + arc)
+                all.push_back(Elem{arc.s_len == 1 ? arc.next : in_.n + k, s0.tid ? repo_.append(e.str, s0.tid) : e.str, ng, na});
+                lab.push_back(arc.il);
             }
-        for (auto &kv : by_label) {
-            std::vector<Elem> &v = kv.second;
-            std::stable_sort(v.begin(), v.end(), [](const Elem &x, const Elem &y) { return x.state < y.state; });
-            std::vector<Elem> merged;
-            for (Elem &e : v) {
-                if (!merged.empty() && merged.back().state == e.state) {
-                    if (compare_elem(e.w, e.str, merged.back().w, merged.back().str) == 1) merged.back() = std::move(e);
+        }
+        if (all.empty()) return;
+        idx.resize(all.size());
+        for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+        std::sort(idx.begin(), idx.end(), [&](int x, int y) {
+            if (lab[x] != lab[y]) return lab[x] < lab[y];
+            if (all[x].state != all[y].state) return all[x].state < all[y].state;
+            return x < y;
+        });
+        size_t c = 0;
+        while (c < idx.size()) {
+            const int label = lab[idx[c]];
+            double prio = kInfD;
+            const int off = (int)ws_.pool.size();
+            while (c < idx.size() && lab[idx[c]] == label) {
+                const Elem &e = all[idx[c]];
+                prio = std::min(prio, pri[idx[c]]);
+                // MakeSubsetUnique: of several elements with one state the best (weight, then string) stays
+                if ((int)ws_.pool.size() > off && ws_.pool.back().state == e.state) {
+                    Elem &b = ws_.pool.back();
+                    if (compare_ws(e.g, e.a, e.str, b.g, b.a, b.str) == 1) b = e;
                 } else {
-                    merged.push_back(std::move(e));
+                    ws_.pool.push_back(e);
                 }
+                c++;
             }
-            closure(&merged);
-            to_minimal(&merged);
-            if (merged.empty()) continue;
-            Task t;
-            normalize(&merged, &t.w, &t.str);
-            double best_back = kInfD;
-            for (const Elem &e : merged) best_back = std::min(best_back, (double)e.w.cost() + beta_[e.state]);
-            t.prio = fwd + (double)t.w.cost() + best_back;
-            if (!(t.prio <= cutoff_ + 1e-4)) continue;  // beyond the beam (or no way to a final state)
-            t.src = s;
-            t.label = kv.first;
-            t.subset = std::make_shared<std::vector<Elem>>(std::move(merged));
-            tasks_.push(std::move(t));
+            prio += st.fwd;
+            if (prio > cutoff_) {
+                ws_.pool.resize(off);  // beyond the beam: never expanded
+                continue;
+            }
+            tasks_.push(Task{prio, sid, label, off, (int)ws_.pool.size() - off});
         }
     }
 
-    const RLat &in_;
-    float beam_;
-    CLat *out_ = nullptr;
-    std::vector<double> beta_;
-    std::vector<int> topo_, stamp_, slot_;
-    std::vector<char> keepable_;
+    void process_transition(const Task &t) {
+        double fwd = states_[t.src].fwd;
+        Elem *e = &ws_.pool[t.off];
+        float tg, ta;
+        int common;
+        normalize(e, t.len, &tg, &ta, &common);
+        fwd += cost_of(tg, ta);
+        // InitialToStateId
+        const uint64_t h = hash_of(e, t.len);
+        int next, nstr;
+        float ng, na;
+        const int f = ws_.init_tab.find(h, [&](int id) { return inits_[id].len == t.len && same_subset(&ws_.pool[inits_[id].off], e, t.len); });
+        if (f >= 0) {
+            next = inits_[f].state;
+            nstr = inits_[f].str;
+            ng = inits_[f].g;
+            na = inits_[f].a;
+        } else {
+            std::vector<Elem> &sub = ws_.sub;
+            sub.assign(e, e + t.len);
+            closure(&sub);
+            normalize(sub.data(), (int)sub.size(), &ng, &na, &nstr);
+            next = minimal_to_state(sub, fwd + cost_of(ng, na));
+            inits_.push_back(Init{t.off, t.len, next, nstr, ng, na});
+            ws_.init_tab.insert(h, (int)inits_.size() - 1);
+        }
+        ws_.tarcs.push_back(TArc{t.src, t.label, repo_.concat(common, nstr), next, tg + ng, ta + na});
+    }
+
+    Workspace &ws_;
+    const FLat &in_;
+    const Sym *sy_;
+    double beam_, cutoff_ = 0;
+    Repo &repo_;
     int epoch_ = 0;
-    double cutoff_ = 0;
-    std::vector<OutState> states_;  // index = output state id of the subset states (the optional extra start state is added last)
-    std::unordered_map<std::string, std::vector<int>> index_;
+    std::vector<OutState> states_;
+    std::vector<Init> inits_;
     std::priority_queue<Task> tasks_;
 };
-}  // namespace
 
-bool determinize_lattice(const RawLattice &raw, const LatticeCtx &ctx, float beam, CLat *out) {
-    if (raw.n_states <= 0 || raw.start < 0) return false;
-    const RLat r = build_raw(raw, ctx);
-    for (int attempt = 0; attempt < 4; attempt++, beam *= 0.5f) {
-        Determinizer d(r, beam);
-        if (d.run(out)) return true;
-        if ((int)out->num_states() <= kMaxDetStates) return false;  // no complete path: shrinking the beam cannot help
+// output of the phone pass in non-compact form with the phone labels deleted: Kaldi spells every string out as symbols
+// along a chain of new states, weight and label on the first arc of the chain — here one arc with that chain as its span
+void output_pass1(Workspace &ws, int n_det, std::vector<Edge> *edges, std::vector<Sym> *syms, std::vector<float> *fin_g, std::vector<float> *fin_a,
+                  int *n_out) {
+    edges->clear();
+    syms->clear();
+    fin_g->assign(n_det, kInfF);
+    fin_a->assign(n_det, kInfF);
+    int n = n_det;
+    std::vector<int> &seq = ws.tvec;
+    for (const TArc &t : ws.tarcs) {
+        seq.clear();
+        ws.repo.to_vec(t.str, &seq);
+        if (t.next < 0 && seq.empty()) {
+            (*fin_g)[t.src] = t.g;
+            (*fin_a)[t.src] = t.a;
+            continue;
+        }
+        const int off = (int)syms->size();
+        if (seq.empty()) syms->push_back(Sym{0, t.g, t.a});
+        for (size_t i = 0; i < seq.size(); i++) syms->push_back(Sym{seq[i], i == 0 ? t.g : 0.f, i == 0 ? t.a : 0.f});
+        int next = t.next;
+        if (next < 0) {  // a final weight with a string: the chain ends in a new state whose final weight is One
+            next = n++;
+            fin_g->push_back(0.f);
+            fin_a->push_back(0.f);
+        }
+        const int label = t.next < 0 || t.label >= kPhoneBase ? 0 : t.label;  // DeterminizeLatticeDeletePhones
+        edges->push_back(Edge{t.src, FArc{label, off, (int)syms->size() - off, next}});
     }
-    return false;
+    *n_out = n;
 }
 
-void scale_graph_costs(CLat *lat, float scale) {
-    for (auto &as : lat->arcs)
-        for (CLatArc &a : as) a.w.g *= scale;
-    for (size_t s = 0; s < lat->num_states(); s++)
-        if (lat->is_final[s]) lat->final_w[s].g *= scale;
+// output of the word pass in compact form + fst::Connect (drop the states from which no final weight can be reached)
+void compact_output(Workspace &ws, int n_det, CLatF *out) {
+    out->tids.clear();
+    std::vector<int> &off = ws.csr_off;
+    off.assign(n_det + 1, 0);
+    std::vector<char> fin(n_det, 0);
+    for (const TArc &t : ws.tarcs)
+        if (t.next >= 0) off[t.src + 1]++;
+        else fin[t.src] = 1;
+    for (int s = 0; s < n_det; s++) off[s + 1] += off[s];
+    std::vector<int> &idx = ws.csr_idx, &pos = ws.dfs_pos;
+    idx.resize(off[n_det]);
+    pos.assign(off.begin(), off.end() - 1);
+    for (size_t k = 0; k < ws.tarcs.size(); k++)
+        if (ws.tarcs[k].next >= 0) idx[pos[ws.tarcs[k].src]++] = (int)k;
+    // co-accessibility: reverse reachability from the final states
+    std::vector<char> &co = ws.color;
+    co.assign(n_det, 0);
+    {
+        std::vector<int> roff(n_det + 1, 0), ridx(off[n_det]);
+        for (const TArc &t : ws.tarcs)
+            if (t.next >= 0) roff[t.next + 1]++;
+        for (int s = 0; s < n_det; s++) roff[s + 1] += roff[s];
+        std::vector<int> rp(roff.begin(), roff.end() - 1);
+        for (const TArc &t : ws.tarcs)
+            if (t.next >= 0) ridx[rp[t.next]++] = t.src;
+        std::vector<int> &st = ws.dfs_stack;
+        st.clear();
+        for (int s = 0; s < n_det; s++)
+            if (fin[s]) {
+                co[s] = 1;
+                st.push_back(s);
+            }
+        while (!st.empty()) {
+            const int s = st.back();
+            st.pop_back();
+            for (int k = roff[s]; k < roff[s + 1]; k++)
+                if (!co[ridx[k]]) {
+                    co[ridx[k]] = 1;
+                    st.push_back(ridx[k]);
+                }
+        }
+    }
+    // (every output state is accessible from state 0 by construction)
+    std::vector<int> &map = ws.remap;
+    map.assign(n_det, -1);
+    int n = 0;
+    for (int s = 0; s < n_det; s++)
+        if (co[s]) map[s] = n++;
+    out->n = n;
+    out->start = n_det > 0 ? map[0] : -1;
+    out->off.assign(n + 1, 0);
+    out->arcs.clear();
+    out->is_final.assign(n, 0);
+    out->fin_g.assign(n, 0.f);
+    out->fin_a.assign(n, 0.f);
+    out->fin_off.assign(n, 0);
+    out->fin_len.assign(n, 0);
+    for (int s = 0; s < n_det; s++) {
+        if (map[s] < 0) continue;
+        for (int k = off[s]; k < off[s + 1]; k++) {
+            const TArc &t = ws.tarcs[idx[k]];
+            if (map[t.next] < 0) continue;
+            const int o = (int)out->tids.size();
+            ws.repo.to_vec(t.str, &out->tids);
+            out->arcs.push_back(CArcF{t.label, t.g, t.a, o, (int)out->tids.size() - o, map[t.next]});
+        }
+        out->off[map[s] + 1] = (int)out->arcs.size();
+    }
+    for (const TArc &t : ws.tarcs)
+        if (t.next < 0 && map[t.src] >= 0) {
+            const int s = map[t.src], o = (int)out->tids.size();
+            ws.repo.to_vec(t.str, &out->tids);
+            out->is_final[s] = 1;
+            out->fin_g[s] = t.g;
+            out->fin_a[s] = t.a;
+            out->fin_off[s] = o;
+            out->fin_len[s] = (int)out->tids.size() - o;
+        }
+}
+
+// DeterminizeLatticePhonePrunedWrapper
+bool determinize_phone_pruned(Workspace &ws, const RawLattice &raw, const Model &m, double beam, bool phone_pass, CLatF *out,
+                              LatticeStats *stats) {
+    const Graph &g = m.graph;
+    const int n_raw = raw.n_states;
+    if (n_raw <= 0 || raw.start < 0 || raw.start >= n_raw) return false;
+    // Invert (words become the labels determinized on) + DeterminizeLatticeInsertPhones
+    std::vector<Edge> &edges = ws.edges;
+    std::vector<Sym> &syms = ws.sym_in;
+    edges.clear();
+    syms.clear();
+    ws.fin_g.assign(n_raw, kInfF);
+    ws.fin_a.assign(n_raw, kInfF);
+    int n = n_raw;
+    const int n_tids = (int)m.tid_flags.size();
+    for (size_t k = 0; k < raw.src.size(); k++) {
+        const int a = raw.arc[k], s = raw.src[k], d = raw.dst[k];
+        if (s < 0 || s >= n_raw || d < 0 || d >= n_raw || a < 0 || a >= g.num_arcs) continue;
+        const int tid = g.arc_ilabel[a], word = g.arc_olabel[a];
+        FArc arc{word, (int)syms.size(), 1, d};
+        syms.push_back(Sym{tid, g.arc_w[a], raw.acoustic[k]});
+        if (phone_pass && s != raw.start && tid > 0 && tid < n_tids && (m.tid_flags[tid] & 4) && !(m.tid_flags[tid] & 1)) {
+            const int phone_label = kPhoneBase + m.tid2phone[tid];
+            if (word == 0) {
+                arc.il = phone_label;
+            } else {  // a word and a phone start on one arc: the phone label goes on an extra arc behind it
+                const int extra = n++;
+                ws.fin_g.push_back(kInfF);
+                ws.fin_a.push_back(kInfF);
+                arc.next = extra;
+                edges.push_back(Edge{s, arc});
+                edges.push_back(Edge{extra, FArc{phone_label, (int)syms.size(), 1, d}});
+                syms.push_back(Sym{0, 0.f, 0.f});
+                continue;
+            }
+        }
+        edges.push_back(Edge{s, arc});
+    }
+    for (size_t k = 0; k < raw.final_state.size(); k++)
+        if (raw.final_state[k] >= 0 && raw.final_state[k] < n_raw) {
+            ws.fin_g[raw.final_state[k]] = raw.final_cost[k];
+            ws.fin_a[raw.final_state[k]] = 0.f;
+        }
+    g_comp_pass = 1;
+    compress_chains(ws, n, raw.start, edges, ws.fin_g, syms, &ws.edges2, &ws.sym1);
+    if (!build_flat(ws, n, raw.start, ws.edges2, ws.fin_g, ws.fin_a, &ws.sym1, &ws.lat1)) return false;
+    const FLat *in = &ws.lat1;
+    if (phone_pass) {
+        Determinizer d1(ws, ws.lat1, beam);
+        if (!d1.run()) return false;
+        int n2 = 0;
+        output_pass1(ws, d1.num_states(), &edges, &syms, &ws.fin_g, &ws.fin_a, &n2);
+        if (stats) {
+            stats->det1_states = d1.num_states();
+            stats->det1_arcs = (int)edges.size();
+        }
+        g_comp_pass = 2;
+        compress_chains(ws, n2, 0, edges, ws.fin_g, syms, &ws.edges2, &ws.sym2);
+        if (!build_flat(ws, n2, 0, ws.edges2, ws.fin_g, ws.fin_a, &ws.sym2, &ws.lat2)) return false;
+        in = &ws.lat2;
+    }
+    Determinizer d2(ws, *in, beam);
+    if (!d2.run()) return false;
+    compact_output(ws, d2.num_states(), out);
+    if (stats) {
+        stats->det_states = out->n;
+        stats->det_arcs = (int)out->arcs.size();
+    }
+    return out->n > 0 && out->start >= 0;
+}
+
+// fst::ScaleLattice(fst::GraphLatticeScale(s)): ScaleTupleWeight with the double matrix {{s, 0}, {0, 1}}
+inline void scale_weight(double s, float *g, float *a) {
+    if (*g == kInfF) return;
+    const double dg = (double)*g, da = (double)*a;
+    *g = (float)(s * dg + 0.0 * da);
+    *a = (float)(0.0 * dg + 1.0 * da);
+}
+void scale_graph_costs(CLatF *lat, double s) {
+    for (CArcF &a : lat->arcs) scale_weight(s, &a.g, &a.a);
+    for (int i = 0; i < lat->n; i++)
+        if (lat->is_final[i]) scale_weight(s, &lat->fin_g[i], &lat->fin_a[i]);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // WordAlignLattice
 // ------------------------------------------------------------------------------------------------------------
-namespace {
-constexpr int kSilTmp = -1, kPartialTmp = -2;  // temporary labels so that epsilon removal leaves these arcs alone
-
-struct CompState {  // LatticeWordAligner::ComputationState (its weight is always One after Advance)
-    std::vector<int> tids, words;
-    bool operator<(const CompState &o) const { return tids != o.tids ? tids < o.tids : words < o.words; }
-    bool empty() const { return tids.empty() && words.empty(); }
-};
-
 class WordAligner {
    public:
-    WordAligner(const CLat &in, const LatticeCtx &ctx) : ctx_(ctx) {
-        lat_ = in;
-        // CreateSuperFinal: the only final weight left is One on one extra state
-        const int sf = lat_.add_state();
-        for (int s = 0; s < sf; s++)
-            if (lat_.is_final[s]) {
-                lat_.arcs[s].push_back(CLatArc{sf, 0, lat_.final_w[s], lat_.final_tids[s]});
-                lat_.is_final[s] = 0;
-            }
-        lat_.is_final[sf] = 1;
-        lat_.final_w[sf] = LatWeight{};
-        lat_.final_tids[sf].clear();
-    }
+    WordAligner(Workspace &ws, const CLatF &in, const Model &m) : ws_(ws), in_(in), m_(m), out_(ws.ali) {}
 
-    void run(CLat *out) {
-        out_ = out;
-        *out = CLat();
-        if (lat_.start < 0) return;
-        out->start = state_for(lat_.start, CompState());
+    void run() {
+        out_.clear();
+        ws_.seq.clear();
+        ws_.wseq.clear();
+        tuples_.clear();
+        ws_.tup_tab.reset(1 << 12);
+        queue_.clear();
+        if (in_.start < 0) return;
+        // CreateSuperFinal: the only final weight left is One on one extra state `sf_` (arcs into it are implicit)
+        sf_ = in_.n;
+        const int n_final = (int)std::count(in_.is_final.begin(), in_.is_final.end(), (char)1);
+        if (n_final == 1) {
+            for (int s = 0; s < in_.n; s++)
+                if (in_.is_final[s] && in_.fin_g[s] == 0.f && in_.fin_a[s] == 0.f && in_.fin_len[s] == 0 && in_.off[s] == in_.off[s + 1]) sf_ = s;
+        }
+        out_.start = state_for(Tuple{in_.start, 0, 0, 0, 0});
         while (!queue_.empty()) {
-            auto item = queue_.back();
+            const int id = queue_.back();
             queue_.pop_back();
-            process(item.first, item.second);
+            process(id);
         }
         remove_eps_local();
-        for (auto &as : out->arcs)
-            for (CLatArc &a : as)
-                if (a.word < 0) a.word = 0;
+        for (AArc &a : out_.arcs)
+            if (a.label < 0) a.label = 0;
     }
 
    private:
-    int phone_of(int tid) const { return tid >= 0 && tid < (int)ctx_.tid2phone->size() ? (*ctx_.tid2phone)[tid] : -1; }
-    int type_of(int phone) const { return phone >= 0 && phone < (int)ctx_.phone_type->size() ? (*ctx_.phone_type)[phone] : 0; }
-    // chain topology of the model container: tid = 2*tstate+1 self-loop, 2*tstate+2 forward (= final) transition
-    static bool is_final_tid(int tid) { return tid > 0 && (tid % 2) == 0; }
-    static bool is_self_loop(int tid) { return tid > 0 && (tid % 2) == 1; }
+    struct Tuple {
+        int in_state;
+        int t_off, t_len;  // pending transition-ids (span in ws.seq)
+        int w_off, w_len;  // pending word labels (span in ws.wseq)
+    };
+    int phone_of(int tid) const { return tid >= 0 && tid < (int)m_.tid2phone.size() ? m_.tid2phone[tid] : -1; }
+    int type_of(int phone) const { return phone >= 0 && phone < (int)m_.phone_type.size() ? m_.phone_type[phone] : 0; }
+    bool is_final_tid(int tid) const { return tid > 0 && tid < (int)m_.tid_flags.size() && (m_.tid_flags[tid] & 2); }
+    bool is_self_loop(int tid) const { return tid > 0 && tid < (int)m_.tid_flags.size() && (m_.tid_flags[tid] & 1); }
+
+    uint64_t hash_tuple(const Tuple &t) const {
+        uint64_t h = mix((uint64_t)(uint32_t)t.in_state, ((uint64_t)(uint32_t)t.t_len << 32) | (uint32_t)t.w_len);
+        for (int i = 0; i < t.t_len; i++) h = mix(h, (uint64_t)(uint32_t)ws_.seq[t.t_off + i]);
+        for (int i = 0; i < t.w_len; i++) h = mix(h, (uint64_t)(uint32_t)ws_.wseq[t.w_off + i] + 0x51ull);
+        return h;
+    }
+    int state_for(const Tuple &t) {
+        const uint64_t h = hash_tuple(t);
+        const int f = ws_.tup_tab.find(h, [&](int id) {
+            const Tuple &o = tuples_[id];
+            return o.in_state == t.in_state && o.t_len == t.t_len && o.w_len == t.w_len &&
+                   std::equal(ws_.seq.begin() + t.t_off, ws_.seq.begin() + t.t_off + t.t_len, ws_.seq.begin() + o.t_off) &&
+                   std::equal(ws_.wseq.begin() + t.w_off, ws_.wseq.begin() + t.w_off + t.w_len, ws_.wseq.begin() + o.w_off);
+        });
+        if (f >= 0) return f;
+        const int id = out_.add_state();
+        tuples_.push_back(t);
+        ws_.tup_tab.insert(h, id);
+        queue_.push_back(id);
+        return id;
+    }
 
     // number of leading tids that make up one complete phone, or 0 if its end cannot be decided yet (reorder = true:
     // the self-loops follow the final transition, so a phone is only known to be over when the next tid is in sight)
-    static size_t phone_span(const std::vector<int> &t, size_t from) {
-        size_t i = from;
-        const size_t len = t.size();
+    int phone_span(const int *t, int len, int from) const {
+        int i = from;
         for (; i < len; i++)
             if (is_final_tid(t[i])) break;
         if (i == len) return 0;
@@ -463,161 +1030,184 @@ class WordAligner {
         if (i == len) return 0;
         return i;
     }
-
-    bool output_arc(CompState *c, CLatArc *arc) const {
-        if (c->tids.empty()) return false;
-        const int ty = type_of(phone_of(c->tids[0]));
-        if (ty == 1) {  // OutputSilenceArc
-            const size_t i = phone_span(c->tids, 0);
-            if (!i) return false;
-            *arc = CLatArc{-1, kSilTmp, LatWeight{}, std::vector<int>(c->tids.begin(), c->tids.begin() + i)};
-            c->tids.erase(c->tids.begin(), c->tids.begin() + i);
-            return true;
+    // OutputSilenceArc / OutputOnePhoneWordArc / OutputNormalWordArc: tids consumed (0 = nothing to output yet)
+    int output_arc(const Tuple &t, int *label, bool *takes_word) const {
+        if (t.t_len == 0) return 0;
+        const int *tids = &ws_.seq[t.t_off];
+        const int ty = type_of(phone_of(tids[0]));
+        if (ty == 1) {
+            *label = kSilTmp;
+            *takes_word = false;
+            return phone_span(tids, t.t_len, 0);
         }
-        if (c->words.empty()) return false;
-        size_t i = 0;
-        if (ty == 5) {  // OutputOnePhoneWordArc
-            i = phone_span(c->tids, 0);
-            if (!i) return false;
-        } else if (ty == 2) {  // OutputNormalWordArc: begin phone, word-internal phones, end phone
-            i = phone_span(c->tids, 0);
-            if (!i) return false;
-            const size_t len = c->tids.size();
-            while (i < len) {
-                const int t2 = type_of(phone_of(c->tids[i]));
+        if (t.w_len == 0) return 0;
+        *label = ws_.wseq[t.w_off];
+        *takes_word = true;
+        if (ty == 5) return phone_span(tids, t.t_len, 0);
+        if (ty == 2) {  // begin phone, word-internal phones, end phone
+            int i = phone_span(tids, t.t_len, 0);
+            if (!i) return 0;
+            while (i < t.t_len) {
+                const int t2 = type_of(phone_of(tids[i]));
                 if (t2 == 3 || t2 == 5) break;
                 i++;
             }
-            if (i == len) return false;
-            i = phone_span(c->tids, i);
-            if (!i) return false;
-        } else {
-            return false;
+            if (i == t.t_len) return 0;
+            return phone_span(tids, t.t_len, i);
         }
-        *arc = CLatArc{-1, c->words[0], LatWeight{}, std::vector<int>(c->tids.begin(), c->tids.begin() + i)};
-        c->tids.erase(c->tids.begin(), c->tids.begin() + i);
-        c->words.erase(c->words.begin());
-        return true;
+        return 0;
     }
 
-    // OutputArcForce: at a final state whatever is pending goes out as one arc (silence, word, or partial word)
-    void output_arc_force(CompState *c, CLatArc *arc) const {
-        if (!c->tids.empty()) {
-            const int ty = type_of(phone_of(c->tids[0]));
-            int label;
-            if (ty == 1) {
-                label = kSilTmp;
-            } else if (!c->words.empty()) {
-                label = c->words[0];
-                c->words.erase(c->words.begin());
-            } else {
-                label = kPartialTmp;
-            }
-            *arc = CLatArc{-1, label, LatWeight{}, c->tids};
-            c->tids.clear();
-        } else {
-            *arc = CLatArc{-1, c->words[0], LatWeight{}, {}};
-            c->words.erase(c->words.begin());
-        }
-    }
-
-    int state_for(int in_state, const CompState &c) {
-        auto key = std::make_pair(in_state, c);
-        auto it = map_.find(key);
-        if (it != map_.end()) return it->second;
-        const int id = out_->add_state();
-        map_.emplace(key, id);
-        queue_.emplace_back(key, id);
-        return id;
-    }
-
-    void process(const std::pair<int, CompState> &tuple, int out_state) {
-        CompState c = tuple.second;
-        CLatArc arc;
-        if (output_arc(&c, &arc)) {
-            arc.dst = state_for(tuple.first, c);
-            out_->arcs[out_state].push_back(std::move(arc));
+    void process(int id) {
+        const Tuple t = tuples_[id];
+        int label = 0;
+        bool takes_word = false;
+        const int used = output_arc(t, &label, &takes_word);
+        if (used > 0) {
+            const int w = takes_word ? 1 : 0;
+            const int d = state_for(Tuple{t.in_state, t.t_off + used, t.t_len - used, t.w_off + w, t.w_len - w});
+            out_.add_arc(id, AArc{label, 0.f, 0.f, t.t_off, used, d, -1});
             return;
         }
-        // ProcessFinal
-        if (lat_.is_final[tuple.first]) {
-            if (tuple.second.empty()) {
-                out_->is_final[out_state] = 1;
-                out_->final_w[out_state] = lat_.final_w[tuple.first];
-            } else {
-                CompState c2 = tuple.second;
-                output_arc_force(&c2, &arc);
-                arc.dst = state_for(tuple.first, c2);
-                out_->arcs[out_state].push_back(std::move(arc));
+        if (t.in_state == sf_) {  // ProcessFinal
+            if (t.t_len == 0 && t.w_len == 0) {
+                out_.is_final[id] = 1;
+                out_.fin_g[id] = 0.f;
+                out_.fin_a[id] = 0.f;
+            } else {  // OutputArcForce: whatever is pending goes out as one arc (silence, word, or partial word)
+                int lab;
+                int w = 0;
+                if (t.t_len > 0) {
+                    const int ty = type_of(phone_of(ws_.seq[t.t_off]));
+                    if (ty == 1) {
+                        lab = kSilTmp;
+                    } else if (t.w_len > 0) {
+                        lab = ws_.wseq[t.w_off];
+                        w = 1;
+                    } else {
+                        lab = kPartialTmp;
+                    }
+                } else {
+                    lab = ws_.wseq[t.w_off];
+                    w = 1;
+                }
+                const int d = state_for(Tuple{t.in_state, t.t_off + t.t_len, 0, t.w_off + w, t.w_len - w});
+                out_.add_arc(id, AArc{lab, 0.f, 0.f, t.t_off, t.t_len, d, -1});
             }
         }
-        for (const CLatArc &ain : lat_.arcs[tuple.first]) {  // Advance: consume one input arc; its weight goes out on an epsilon arc
-            CompState nx = tuple.second;
-            nx.tids.insert(nx.tids.end(), ain.tids.begin(), ain.tids.end());
-            if (ain.word != 0) nx.words.push_back(ain.word);
-            const int d = state_for(ain.dst, nx);
-            out_->arcs[out_state].push_back(CLatArc{d, 0, ain.w, {}});
+        if (t.in_state == sf_ && sf_ == in_.n) return;  // the implicit super-final state has no arcs
+        // Advance: consume one input arc; its symbols are queued, its weight goes out on an epsilon arc
+        auto advance = [&](int label_in, float g, float a, const int *str, int len, int next) {
+            Tuple nx{next, t.t_off, t.t_len, t.w_off, t.w_len};
+            if (len > 0) {
+                if (t.t_off + t.t_len != (int)ws_.seq.size()) {
+                    nx.t_off = (int)ws_.seq.size();
+                    ws_.seq.resize(ws_.seq.size() + t.t_len);
+                    std::copy_n(ws_.seq.begin() + t.t_off, t.t_len, ws_.seq.begin() + nx.t_off);
+                }
+                ws_.seq.insert(ws_.seq.end(), str, str + len);
+                nx.t_len = t.t_len + len;
+            }
+            if (label_in != 0) {
+                if (t.w_off + t.w_len != (int)ws_.wseq.size()) {
+                    nx.w_off = (int)ws_.wseq.size();
+                    ws_.wseq.resize(ws_.wseq.size() + t.w_len);
+                    std::copy_n(ws_.wseq.begin() + t.w_off, t.w_len, ws_.wseq.begin() + nx.w_off);
+                }
+                ws_.wseq.push_back(label_in);
+                nx.w_len = t.w_len + 1;
+            }
+            const int d = state_for(nx);
+            out_.add_arc(id, AArc{0, g, a, 0, 0, d, -1});
+        };
+        if (t.in_state >= in_.n) return;
+        // (the strings are copied out of in_.tids because ws_.seq may reallocate while it is appended to)
+        for (int k = in_.off[t.in_state]; k < in_.off[t.in_state + 1]; k++) {
+            const CArcF &a = in_.arcs[k];
+            advance(a.label, a.g, a.a, in_.tids.data() + a.t_off, a.t_len, a.next);
         }
+        if (in_.is_final[t.in_state] && t.in_state != sf_)
+            advance(0, in_.fin_g[t.in_state], in_.fin_a[t.in_state], in_.tids.data() + in_.fin_off[t.in_state], in_.fin_len[t.in_state], sf_);
     }
 
     // RemoveEpsLocal: merge an arc with the arc(s) leaving its destination when one of the two is an epsilon and the
     // destination has a single arc in (pattern 1) or a single arc out (pattern 2); never increases the arc count.
-    // (Kaldi also pushes weight for stochasticity; path weights are unchanged by that and it is omitted.)
-    static bool can_combine(const CLatArc &a, const CLatArc &b, CLatArc *c) {
-        if (a.word != 0 && b.word != 0) return false;
-        c->word = a.word != 0 ? a.word : b.word;
-        c->w = times_w(a.w, b.w);
-        c->tids = a.tids;
-        c->tids.insert(c->tids.end(), b.tids.begin(), b.tids.end());
-        c->dst = b.dst;
+    bool can_combine(const AArc &a, const AArc &b, AArc *c) {
+        if (a.label != 0 && b.label != 0) return false;
+        c->label = a.label != 0 ? a.label : b.label;
+        c->g = a.g + b.g;
+        c->a = a.a + b.a;
+        if (a.t_len == 0) {
+            c->t_off = b.t_off;
+            c->t_len = b.t_len;
+        } else if (b.t_len == 0) {
+            c->t_off = a.t_off;
+            c->t_len = a.t_len;
+        } else {
+            c->t_off = (int)ws_.seq.size();
+            c->t_len = a.t_len + b.t_len;
+            ws_.seq.resize(ws_.seq.size() + c->t_len);
+            std::copy_n(ws_.seq.begin() + a.t_off, a.t_len, ws_.seq.begin() + c->t_off);
+            std::copy_n(ws_.seq.begin() + b.t_off, b.t_len, ws_.seq.begin() + c->t_off + a.t_len);
+        }
+        c->next = b.next;
+        c->link = -1;
         return true;
     }
+    void set_final_plus(int s, float g, float a) {  // SetFinal(s, Plus(Final(s), w)); final strings are empty here
+        ALat &f = out_;
+        if (!f.is_final[s]) {
+            ws_.nout[s]++;
+            f.is_final[s] = 1;
+            f.fin_g[s] = g;
+            f.fin_a[s] = a;
+        } else if (compare_w(g, a, f.fin_g[s], f.fin_a[s]) == 1) {
+            f.fin_g[s] = g;
+            f.fin_a[s] = a;
+        }
+    }
     void remove_eps_local() {
-        CLat &f = *out_;
-        const int n = (int)f.num_states();
-        const int dead = -7;
-        std::vector<int> nin(n, 0), nout(n, 0);
+        ALat &f = out_;
+        const int n = f.n();
+        std::vector<int> &nin = ws_.nin, &nout = ws_.nout;
+        nin.assign(n, 0);
+        nout.assign(n, 0);
         for (int s = 0; s < n; s++) {
-            for (const CLatArc &a : f.arcs[s]) {
-                nin[a.dst]++;
+            for (int k = f.head[s]; k >= 0; k = f.arcs[k].link) {
+                nin[f.arcs[k].next]++;
                 nout[s]++;
             }
             if (f.is_final[s]) nout[s]++;
         }
         if (f.start >= 0) nin[f.start]++;
+        std::vector<AArc> add;
         for (int s = 0; s < n; s++) {
-            for (size_t pos = 0; pos < f.arcs[s].size(); pos++) {
-                CLatArc arc = f.arcs[s][pos];
-                const int t = arc.dst;
-                if (t == dead || t == s) continue;
+            for (int pos = f.head[s]; pos >= 0; pos = f.arcs[pos].link) {
+                const AArc arc = f.arcs[pos];
+                const int t = arc.next;
+                if (t == kDead || t == s) continue;
                 if (nin[t] == 1 && nout[t] > 1) {  // pattern 1
                     bool removed = false, kept = false;
-                    std::vector<CLatArc> add;
-                    for (CLatArc &nx : f.arcs[t]) {
-                        if (nx.dst == dead) continue;
-                        CLatArc c;
+                    add.clear();
+                    for (int k = f.head[t]; k >= 0; k = f.arcs[k].link) {
+                        AArc &nx = f.arcs[k];
+                        if (nx.next == kDead) continue;
+                        AArc c;
                         if (can_combine(arc, nx, &c)) {
                             removed = true;
                             nout[t]--;
-                            nin[nx.dst]--;
-                            nx.dst = dead;
-                            add.push_back(std::move(c));
+                            nin[f.arcs[k].next]--;
+                            f.arcs[k].next = kDead;
+                            add.push_back(c);
                         } else {
                             kept = true;
                         }
                     }
                     if (f.is_final[t]) {
-                        if (arc.word == 0 && arc.tids.empty()) {  // CanCombineFinal: an epsilon arc into a final state
+                        if (arc.label == 0) {  // CanCombineFinal: an epsilon arc into a final state
                             removed = true;
+                            set_final_plus(s, arc.g + f.fin_g[t], arc.a + f.fin_a[t]);
                             nout[t]--;
-                            const LatWeight fw = times_w(arc.w, f.final_w[t]);
-                            if (!f.is_final[s]) {
-                                nout[s]++;
-                                f.is_final[s] = 1;
-                                f.final_w[s] = fw;
-                            } else if (compare_w(fw, f.final_w[s]) == 1) {
-                                f.final_w[s] = fw;
-                            }
                             f.is_final[t] = 0;
                         } else {
                             kept = true;
@@ -626,187 +1216,193 @@ class WordAligner {
                     if (removed && !kept) {
                         nout[s]--;
                         nin[t]--;
-                        f.arcs[s][pos].dst = dead;
+                        f.arcs[pos].next = kDead;
                     }
-                    for (CLatArc &c : add) {
+                    for (const AArc &c : add) {
                         nout[s]++;
-                        nin[c.dst]++;
-                        f.arcs[s].push_back(std::move(c));
+                        nin[c.next]++;
+                        f.add_arc(s, c);
                     }
                 } else if (nout[t] == 1) {  // pattern 2
                     bool del = false;
                     if (f.is_final[t]) {
-                        if (arc.word == 0 && arc.tids.empty()) {
-                            const LatWeight fw = times_w(arc.w, f.final_w[t]);
-                            if (nin[t] == 1) f.is_final[t] = 0;
-                            if (!f.is_final[s]) {
-                                nout[s]++;
-                                f.is_final[s] = 1;
-                                f.final_w[s] = fw;
-                            } else if (compare_w(fw, f.final_w[s]) == 1) {
-                                f.final_w[s] = fw;
-                            }
+                        if (arc.label == 0) {
+                            set_final_plus(s, arc.g + f.fin_g[t], arc.a + f.fin_a[t]);
                             del = true;
                         }
                     } else {
-                        CLatArc *nx = nullptr;
-                        for (CLatArc &x : f.arcs[t])
-                            if (x.dst != dead) {
-                                nx = &x;
-                                break;
-                            }
-                        CLatArc c;
-                        if (nx && can_combine(arc, *nx, &c)) {
+                        int k = f.head[t];
+                        while (k >= 0 && f.arcs[k].next == kDead) k = f.arcs[k].link;
+                        AArc c;
+                        if (k >= 0 && can_combine(arc, f.arcs[k], &c)) {
                             del = true;
                             if (nin[t] == 1) {
                                 nout[t]--;
-                                nin[nx->dst]--;
-                                nx->dst = dead;
+                                nin[f.arcs[k].next]--;
+                                f.arcs[k].next = kDead;
                             }
                             nout[s]++;
-                            nin[c.dst]++;
-                            f.arcs[s].push_back(std::move(c));
+                            nin[c.next]++;
+                            f.add_arc(s, c);
                         }
                     }
                     if (del) {
                         nout[s]--;
                         nin[t]--;
-                        f.arcs[s][pos].dst = dead;
+                        f.arcs[pos].next = kDead;
                     }
                 }
             }
         }
-        // drop the deleted arcs and the states that became unreachable
-        std::vector<int> remap(n, -1);
-        std::vector<int> stack;
-        if (f.start >= 0) {
-            remap[f.start] = 0;
-            stack.push_back(f.start);
-        }
-        int cnt = f.start >= 0 ? 1 : 0;
-        while (!stack.empty()) {
-            const int s = stack.back();
-            stack.pop_back();
-            for (const CLatArc &a : f.arcs[s])
-                if (a.dst != dead && remap[a.dst] < 0) {
-                    remap[a.dst] = cnt++;
-                    stack.push_back(a.dst);
-                }
-        }
-        CLat g;
-        for (int i = 0; i < cnt; i++) g.add_state();
-        g.start = f.start >= 0 ? 0 : -1;
-        for (int s = 0; s < n; s++) {
-            if (remap[s] < 0) continue;
-            const int ns = remap[s];
-            g.is_final[ns] = f.is_final[s];
-            g.final_w[ns] = f.final_w[s];
-            for (CLatArc &a : f.arcs[s])
-                if (a.dst != dead) {
-                    a.dst = remap[a.dst];
-                    g.arcs[ns].push_back(std::move(a));
-                }
-        }
-        f = std::move(g);
     }
 
-    LatticeCtx ctx_;
-    CLat lat_;
-    CLat *out_ = nullptr;
-    std::map<std::pair<int, CompState>, int> map_;
-    std::vector<std::pair<std::pair<int, CompState>, int>> queue_;
+    Workspace &ws_;
+    const CLatF &in_;
+    const Model &m_;
+    ALat &out_;
+    int sf_ = -1;
+    std::vector<Tuple> tuples_;
+    std::vector<int> queue_;
 };
-}  // namespace
-
-void word_align_lattice(const CLat &in, const LatticeCtx &ctx, CLat *out) {
-    WordAligner w(in, ctx);
-    w.run(out);
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // MinimumBayesRisk (Xu, Povey, Mangu, Zhu: "Minimum Bayes Risk decoding and system combination based on a
 // recursion for edit distance", as implemented by Kaldi lat/sausages.cc)
 // ------------------------------------------------------------------------------------------------------------
-namespace {
 struct MbrArc {
     int word, start, end;  // 1-based nodes
-    double loglike;
+    float loglike;
+    int t_len;
 };
 inline double log_add(double a, double b) {
     if (a == -kInfD) return b;
     if (b == -kInfD) return a;
-    const double m = std::max(a, b);
-    return m + std::log1p(std::exp(-std::fabs(a - b)));
+    const double hi = std::max(a, b), diff = std::min(a, b) - hi;
+    return hi + std::log1p(std::exp(diff));
 }
-inline double edit_l(int a, int b, bool penalize = false) {
-    if (a == b) return 0.0;
-    return penalize ? 1.0 + 1.0e-05 : 1.0;
-}
-}  // namespace
 
-std::vector<WordSpan> mbr_one_best(const CLat &aligned) {
+std::vector<WordSpan> mbr_one_best(Workspace &ws, LatticeStats *stats) {
     std::vector<WordSpan> result;
-    if (aligned.start < 0 || aligned.num_states() == 0) return result;
-    // CreateSuperFinal + TopSort
-    CLat lat = aligned;
-    const int sf = lat.add_state();
-    bool any_final = false;
-    for (int s = 0; s < sf; s++)
+    const ALat &lat = ws.ali;
+    const int n_all = lat.n();
+    if (lat.start < 0 || n_all == 0) return result;
+    // live arcs in CSR form; Connect (states reachable from the start); CreateSuperFinal; topological numbering
+    std::vector<MEdge> &edges = ws.medges;
+    edges.clear();
+    int sf = n_all, n_final = 0, last_final = -1;
+    for (int s = 0; s < n_all; s++)
         if (lat.is_final[s]) {
-            lat.arcs[s].push_back(CLatArc{sf, 0, lat.final_w[s], lat.final_tids[s]});
-            any_final = true;
+            n_final++;
+            last_final = s;
         }
-    if (!any_final) return result;
-    const int n_all = (int)lat.num_states();
-    auto arcs_of = [&](int s, auto f) {
-        for (const CLatArc &a : lat.arcs[s]) f(a.dst);
-    };
-    std::vector<int> order = topo_order(n_all, lat.start, arcs_of);
-    // the super-final state must come last
-    {
-        auto it = std::find(order.begin(), order.end(), sf);
-        if (it == order.end()) return result;
-        order.erase(it);
-        order.push_back(sf);
+    if (!n_final) return result;
+    if (n_final == 1 && lat.fin_g[last_final] == 0.f && lat.fin_a[last_final] == 0.f) {
+        // CreateSuperFinal: a single final state with weight One and no arcs out already is the super-final state
+        bool live = false;
+        for (int k = lat.head[last_final]; k >= 0; k = lat.arcs[k].link) live = live || lat.arcs[k].next != kDead;
+        if (!live) sf = last_final;
     }
-    const int N = (int)order.size();
-    std::vector<int> node_of(n_all, 0);
-    for (int i = 0; i < N; i++) node_of[order[i]] = i + 1;
-    std::vector<double> state_times(N + 1, 0.0);
+    for (int s = 0; s < n_all; s++) {
+        for (int k = lat.head[s]; k >= 0; k = lat.arcs[k].link) {
+            const AArc &a = lat.arcs[k];
+            if (a.next == kDead) continue;
+            edges.push_back(MEdge{s, a.label, a.t_len, a.next, -(a.g + a.a)});
+        }
+        if (lat.is_final[s] && s != sf) edges.push_back(MEdge{s, 0, 0, sf, -(lat.fin_g[s] + lat.fin_a[s])});
+    }
+    std::vector<int> &off = ws.csr_off, &idx = ws.csr_idx, &order = ws.order, &pos = ws.dfs_pos, &st = ws.dfs_stack, &finish = ws.remap;
+    const int n_tot = n_all + 1;
+    off.assign(n_tot + 1, 0);
+    for (const MEdge &e : edges) off[e.src + 1]++;
+    for (int s = 0; s < n_tot; s++) off[s + 1] += off[s];
+    idx.resize(edges.size());
+    pos.assign(off.begin(), off.end() - 1);
+    for (size_t k = 0; k < edges.size(); k++) idx[pos[edges[k].src]++] = (int)k;
+    order.assign(n_tot, -1);
+    ws.color.assign(n_tot, 0);
+    pos.assign(off.begin(), off.end() - 1);
+    st.clear();
+    finish.clear();
+    st.push_back(lat.start);
+    ws.color[lat.start] = 1;
+    while (!st.empty()) {
+        const int s = st.back();
+        if (pos[s] < off[s + 1]) {
+            const int d = edges[idx[pos[s]++]].next;
+            if (!ws.color[d]) {
+                ws.color[d] = 1;
+                st.push_back(d);
+            }
+        } else {
+            finish.push_back(s);
+            st.pop_back();
+        }
+    }
+    if (!ws.color[sf] || finish[0] != sf) {
+        // the super-final state has no arcs out: the first DFS branch ends there unless it dead-ends in a trimmed-away state
+        auto it = std::find(finish.begin(), finish.end(), sf);
+        if (it == finish.end()) return result;
+        finish.erase(it);
+        finish.insert(finish.begin(), sf);
+    }
+    const int N = (int)finish.size();
+    for (int i = 0; i < N; i++) order[finish[N - 1 - i]] = i + 1;  // 1-based nodes, super-final = N
+    // arcs grouped by end node, in start-node order (pre_[n] of sausages.cc)
     std::vector<MbrArc> arcs;
-    std::vector<std::vector<int>> pre(N + 1);
-    for (int i = 0; i < N; i++) {
-        const int s = order[i];
-        for (const CLatArc &a : lat.arcs[s]) {
-            const int e = node_of[a.dst];
-            if (!e) continue;
-            state_times[e] = state_times[i + 1] + (double)a.tids.size();
-            pre[e].push_back((int)arcs.size());
-            arcs.push_back(MbrArc{a.word, i + 1, e, -((double)a.w.g + (double)a.w.a)});
+    std::vector<int> pre_off(N + 2, 0);
+    {
+        std::vector<MbrArc> tmp;
+        for (int i = N - 1; i >= 0; i--) {
+            const int s = finish[i];  // node N - i
+            for (int k = off[s]; k < off[s + 1]; k++) {
+                const MEdge &e = edges[idx[k]];
+                if (order[e.next] < 0) continue;
+                tmp.push_back(MbrArc{e.word, order[s], order[e.next], e.loglike, e.len});
+            }
         }
+        for (const MbrArc &a : tmp) pre_off[a.end + 1]++;
+        for (int n = 0; n <= N; n++) pre_off[n + 1] += pre_off[n];
+        arcs.resize(tmp.size());
+        std::vector<int> p(pre_off.begin(), pre_off.end() - 1);
+        for (const MbrArc &a : tmp) arcs[p[a.end]++] = a;
     }
+    std::vector<int> state_times(N + 1, 0);
+    for (int n = 2; n <= N; n++)
+        for (int k = pre_off[n]; k < pre_off[n + 1]; k++) state_times[n] = state_times[arcs[k].start] + arcs[k].t_len;
     // initial R: words of the best path
     std::vector<int> R;
     {
         std::vector<double> best(N + 1, kInfD);
         std::vector<int> back(N + 1, -1);
         best[1] = 0;
-        for (int nn = 2; nn <= N; nn++)
-            for (int ai : pre[nn]) {
-                const double c = best[arcs[ai].start] - arcs[ai].loglike;
-                if (c < best[nn]) {
-                    best[nn] = c;
-                    back[nn] = ai;
+        for (int n = 2; n <= N; n++)
+            for (int k = pre_off[n]; k < pre_off[n + 1]; k++) {
+                const double c = best[arcs[k].start] - (double)arcs[k].loglike;
+                if (c < best[n]) {
+                    best[n] = c;
+                    back[n] = k;
                 }
             }
-        for (int nn = N; nn > 1 && back[nn] >= 0; nn = arcs[back[nn]].start)
-            if (arcs[back[nn]].word != 0) R.push_back(arcs[back[nn]].word);
+        for (int n = N; n > 1 && back[n] >= 0; n = arcs[back[n]].start)
+            if (arcs[back[n]].word != 0) R.push_back(arcs[back[n]].word);
         std::reverse(R.begin(), R.end());
     }
-    std::vector<std::vector<std::pair<int, float>>> gamma_out;
-    std::vector<std::vector<std::pair<float, float>>> times_out;
+    if (stats) {
+        stats->ali_states = N;
+        stats->ali_arcs = (int)arcs.size();
+    }
+    struct Acc {
+        int word;
+        double g, tb, te;
+    };
+    std::vector<std::vector<Acc>> acc;
     std::vector<std::pair<float, float>> one_best_times;
     std::vector<float> one_best_conf;
+    std::vector<double> &alpha = ws.alpha, &alpha_dash = ws.alpha_dash, &beta_dash = ws.beta_dash;
+    std::vector<char> &b_all = ws.b_arc;
+    std::vector<double> &post = ws.post;
+    post.resize(arcs.size());
+    constexpr double kPen = 1.0 + 1.0e-05;  // l(a, eps, penalize = true)
     for (int counter = 0;; counter++) {
         {  // NormalizeEps: epsilons between all words and at both ends
             std::vector<int> r2;
@@ -818,16 +1414,13 @@ std::vector<WordSpan> mbr_one_best(const CLat &aligned) {
                 }
             R.swap(r2);
         }
-        const int Q = (int)R.size();
-        auto r = [&](int q) { return R[q - 1]; };
-        // ---- AccStats ----
-        std::vector<double> alpha(N + 1, 0.0);
-        std::vector<std::vector<double>> alpha_dash(N + 1, std::vector<double>(Q + 1, 0.0)), beta_dash(N + 1, std::vector<double>(Q + 1, 0.0));
-        std::vector<double> alpha_dash_arc(Q + 1), beta_dash_arc(Q + 1);
-        std::vector<char> b_arc(Q + 1);
-        // per position q: (word, gamma, tau_b, tau_e) of the few words aligned there; linear search beats a tree here
-        struct Acc { int word; double g, tb, te; };
-        std::vector<std::vector<Acc>> acc(Q + 1);
+        const int Q = (int)R.size(), W = Q + 1;
+        const int *r = R.data() - 1;  // r[q], q = 1..Q
+        alpha.assign(N + 1, 0.0);
+        alpha_dash.assign((size_t)(N + 1) * W, 0.0);
+        beta_dash.assign((size_t)(N + 1) * W, 0.0);
+        b_all.resize(arcs.size() * (size_t)W);
+        acc.assign(Q + 1, {});
         auto add = [&](int q, int word, double g, double tb, double te) {
             for (Acc &x : acc[q])
                 if (x.word == word) {
@@ -838,107 +1431,105 @@ std::vector<WordSpan> mbr_one_best(const CLat &aligned) {
                 }
             acc[q].push_back(Acc{word, g, tb, te});
         };
-        alpha[1] = 0.0;
-        alpha_dash[1][0] = 0.0;
-        for (int q = 1; q <= Q; q++) alpha_dash[1][q] = alpha_dash[1][q - 1] + edit_l(0, r(q));
-        for (int nn = 2; nn <= N; nn++) {
+        // ---- EditDistance (forward) ----
+        {
+            double *ad1 = &alpha_dash[(size_t)1 * W];
+            ad1[0] = 0.0;
+            for (int q = 1; q <= Q; q++) ad1[q] = ad1[q - 1] + (r[q] == 0 ? 0.0 : 1.0);
+        }
+        for (int n = 2; n <= N; n++) {
             double alpha_n = -kInfD;
-            for (int ai : pre[nn]) alpha_n = log_add(alpha_n, alpha[arcs[ai].start] + arcs[ai].loglike);
-            alpha[nn] = alpha_n;
-            for (int ai : pre[nn]) {
-                const MbrArc &arc = arcs[ai];
-                const int s_a = arc.start, w_a = arc.word;
-                const double p_a = arc.loglike;
-                const double arc_post_f = std::exp(alpha[s_a] + p_a - alpha[nn]);
-                for (int q = 0; q <= Q; q++) {
-                    if (q == 0) {
-                        alpha_dash_arc[q] = alpha_dash[s_a][q] + edit_l(w_a, 0, true);
-                    } else {
-                        const double a1 = alpha_dash[s_a][q - 1] + edit_l(w_a, r(q)), a2 = alpha_dash[s_a][q] + edit_l(w_a, 0, true),
-                                     a3 = alpha_dash_arc[q - 1] + edit_l(0, r(q));
-                        alpha_dash_arc[q] = std::min(a1, std::min(a2, a3));
-                    }
-                    alpha_dash[nn][q] += arc_post_f * alpha_dash_arc[q];
+            for (int k = pre_off[n]; k < pre_off[n + 1]; k++) alpha_n = log_add(alpha_n, alpha[arcs[k].start] + arcs[k].loglike);
+            alpha[n] = alpha_n;
+            double *adn = &alpha_dash[(size_t)n * W];
+            for (int k = pre_off[n]; k < pre_off[n + 1]; k++) {
+                const MbrArc &arc = arcs[k];
+                const int w_a = arc.word;
+                const double *ads = &alpha_dash[(size_t)arc.start * W];
+                const double p = std::exp(alpha[arc.start] + arc.loglike - alpha_n);
+                post[k] = p;
+                const double l_eps = w_a == 0 ? 0.0 : kPen;  // l(w_a, eps, true)
+                double prev = ads[0] + l_eps;
+                adn[0] += p * prev;
+                // the back-pointers b_arc(q) of this arc (lines 15-18 of the backward pass recompute exactly these minima)
+                char *bk = &b_all[(size_t)k * W];
+                for (int q = 1; q <= Q; q++) {
+                    const int rq = r[q];
+                    const double a1 = ads[q - 1] + (w_a == rq ? 0.0 : 1.0), a2 = ads[q] + l_eps, a3 = prev + (rq == 0 ? 0.0 : 1.0);
+                    const bool one = a1 <= a2;
+                    const double m12 = one ? a1 : a2;
+                    const bool three = !(m12 <= a3);
+                    prev = three ? a3 : m12;
+                    bk[q] = three ? 3 : (one ? 1 : 2);
+                    adn[q] += p * prev;
                 }
             }
         }
-        beta_dash[N][Q] = 1.0;
-        for (int nn = N; nn >= 2; nn--) {
-            for (int ai : pre[nn]) {
-                const MbrArc &arc = arcs[ai];
+        // ---- backward ----
+        beta_dash[(size_t)N * W + Q] = 1.0;
+        for (int n = N; n >= 2; n--) {
+            const double *bdn = &beta_dash[(size_t)n * W];
+            for (int k = pre_off[n]; k < pre_off[n + 1]; k++) {
+                const MbrArc &arc = arcs[k];
                 const int s_a = arc.start, w_a = arc.word;
-                const double p_a = arc.loglike;
-                alpha_dash_arc[0] = alpha_dash[s_a][0] + edit_l(w_a, 0, true);
-                for (int q = 1; q <= Q; q++) {
-                    const double a1 = alpha_dash[s_a][q - 1] + edit_l(w_a, r(q)), a2 = alpha_dash[s_a][q] + edit_l(w_a, 0, true),
-                                 a3 = alpha_dash_arc[q - 1] + edit_l(0, r(q));
-                    if (a1 <= a2) {
-                        if (a1 <= a3) b_arc[q] = 1; else b_arc[q] = 3;
-                    } else {
-                        if (a2 <= a3) b_arc[q] = 2; else b_arc[q] = 3;
-                    }
-                    alpha_dash_arc[q] = std::min(a1, std::min(a2, a3));
-                }
-                std::fill(beta_dash_arc.begin(), beta_dash_arc.end(), 0.0);
-                const double arc_post = std::exp(alpha[s_a] + p_a - alpha[nn]);
+                double *bds = &beta_dash[(size_t)s_a * W];
+                const char *b_arc = &b_all[(size_t)k * W];
+                const double p = post[k];
+                const double t_s = state_times[s_a], t_n = state_times[n];
+                double carry = 0.0;  // beta_dash_arc(q) accumulated from case 3 of q + 1
                 for (int q = Q; q >= 1; q--) {
-                    beta_dash_arc[q] += arc_post * beta_dash[nn][q];
+                    const double b = carry + p * bdn[q];
+                    carry = 0.0;
+                    if (b == 0.0) continue;  // (adding an exact zero changes no sum; Kaldi's maps would only gain zero entries)
                     switch (b_arc[q]) {
                         case 1:
-                            beta_dash[s_a][q - 1] += beta_dash_arc[q];
-                            add(q, w_a, beta_dash_arc[q], state_times[s_a] * beta_dash_arc[q], state_times[nn] * beta_dash_arc[q]);
+                            bds[q - 1] += b;
+                            add(q, w_a, b, t_s * b, t_n * b);
                             break;
                         case 2:
-                            beta_dash[s_a][q] += beta_dash_arc[q];
+                            bds[q] += b;
                             break;
                         case 3:
-                            beta_dash_arc[q - 1] += beta_dash_arc[q];
-                            add(q, 0, beta_dash_arc[q], state_times[s_a] * beta_dash_arc[q], state_times[s_a] * beta_dash_arc[q]);
+                            carry = b;
+                            add(q, 0, b, t_n * b, t_n * b);
                             break;
                     }
                 }
-                beta_dash_arc[0] += arc_post * beta_dash[nn][0];
-                beta_dash[s_a][0] += beta_dash_arc[0];
+                bds[0] += carry + p * bdn[0];
             }
         }
-        std::fill(beta_dash_arc.begin(), beta_dash_arc.end(), 0.0);
-        for (int q = Q; q >= 1; q--) {
-            beta_dash_arc[q] += beta_dash[1][q];
-            beta_dash_arc[q - 1] += beta_dash_arc[q];
-            add(q, 0, beta_dash_arc[q], state_times[1] * beta_dash_arc[q], state_times[1] * beta_dash_arc[q]);
-        }
-        gamma_out.assign(Q, {});
-        times_out.assign(Q, {});
-        for (int q = 1; q <= Q; q++) {
-            auto &gq = gamma_out[q - 1];
-            std::vector<Acc> &aq = acc[q];
-            std::sort(aq.begin(), aq.end(), [](const Acc &x, const Acc &y) {  // GammaCompare on the float posteriors
-                const float gx = (float)x.g, gy = (float)y.g;
-                if (gx > gy) return true;
-                if (gx < gy) return false;
-                return x.word > y.word;
-            });
-            for (const Acc &x : aq) {
-                const float g = (float)x.g;
-                gq.emplace_back(x.word, g);
-                times_out[q - 1].emplace_back((float)(x.tb / g), (float)(x.te / g));
+        {
+            const double *bd1 = &beta_dash[(size_t)1 * W];
+            double carry = 0.0;
+            for (int q = Q; q >= 1; q--) {
+                const double b = carry + bd1[q];
+                carry = b;
+                add(q, 0, b, state_times[1] * b, state_times[1] * b);
             }
         }
         // ---- MbrDecode step ----
         double delta_Q = 0.0;
         one_best_times.clear();
         one_best_conf.clear();
-        for (int q = 0; q < Q; q++) {
-            const auto &g = gamma_out[q];
-            if (g.empty()) continue;
-            double old_gamma = 0, new_gamma = g[0].second;
-            const int rq = R[q], rhat = g[0].first;
-            for (auto &pr : g)
-                if (pr.first == rq) old_gamma = pr.second;
+        for (int q = 1; q <= Q; q++) {
+            std::vector<Acc> &aq = acc[q];
+            if (aq.empty()) continue;
+            // GammaCompare on the float posteriors: largest first, then the larger word id
+            const Acc *top = &aq[0];
+            for (const Acc &x : aq) {
+                const float gx = (float)x.g, gt = (float)top->g;
+                if (gx > gt || (gx == gt && x.word > top->word)) top = &x;
+            }
+            double old_gamma = 0;
+            const double new_gamma = (float)top->g;
+            const int rq = R[q - 1], rhat = top->word;
+            for (const Acc &x : aq)
+                if (x.word == rq) old_gamma = (float)x.g;
             delta_Q += old_gamma - new_gamma;
-            R[q] = rhat;
-            if (R[q] != 0) {
-                one_best_times.push_back(times_out[q][0]);
+            R[q - 1] = rhat;
+            if (rhat != 0) {
+                const float g = (float)top->g;
+                one_best_times.emplace_back((float)(top->tb / g), (float)(top->te / g));
                 const size_t i = one_best_times.size();
                 if (i > 1 && one_best_times[i - 2].second > one_best_times[i - 1].first) {
                     // overlapping words: both share the union of their spans, split in proportion to their durations
@@ -947,37 +1538,98 @@ std::vector<WordSpan> mbr_one_best(const CLat &aligned) {
                     const float right = std::max(one_best_times[i - 2].second, one_best_times[i - 1].second);
                     const float first_dur = one_best_times[i - 2].second - one_best_times[i - 2].first;
                     const float second_dur = one_best_times[i - 1].second - one_best_times[i - 1].first;
-                    float mid = first_dur > 0 ? left + (right - left) * first_dur / (first_dur + second_dur) : left;
+                    const float mid = first_dur > 0 ? left + (right - left) * first_dur / (first_dur + second_dur) : left;
                     one_best_times[i - 2].first = left;
                     one_best_times[i - 2].second = one_best_times[i - 1].first = mid;
                     one_best_times[i - 1].second = right;
                 }
-                float conf = 0.f;
-                for (auto &pr : g)
-                    if (pr.first == R[q]) {
-                        conf = pr.second;
-                        break;
-                    }
-                one_best_conf.push_back(conf);
+                one_best_conf.push_back(g);
             }
+        }
+        if (stats) {
+            stats->mbr_iters = counter + 1;
+            stats->mbr_q = Q;
         }
         if (delta_Q == 0 || counter > 100) break;
     }
-    std::vector<int> words;
+    size_t i = 0;
     for (int w : R)
-        if (w != 0) words.push_back(w);
-    for (size_t i = 0; i < words.size() && i < one_best_times.size(); i++)
-        result.push_back(WordSpan{words[i], one_best_times[i].first, one_best_times[i].second, one_best_conf[i]});
+        if (w != 0 && i < one_best_times.size()) {
+            result.push_back(WordSpan{w, one_best_times[i].first, one_best_times[i].second, one_best_conf[i]});
+            i++;
+        }
     return result;
 }
 
-std::vector<WordSpan> lattice_to_words(const RawLattice &raw, const Model &m, float lattice_beam, float lm_scale) {
-    LatticeCtx ctx{&m.graph, &m.tid2phone, &m.phone_type};
-    CLat det, aligned;
-    if (!determinize_lattice(raw, ctx, lattice_beam, &det)) return {};
-    scale_graph_costs(&det, lm_scale);
-    word_align_lattice(det, ctx, &aligned);
-    return mbr_one_best(aligned);
+inline double ms_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+}  // namespace
+
+std::vector<WordSpan> lattice_to_words(const RawLattice &raw, const Model &m, float lattice_beam, double lm_scale, LatticeStats *stats) {
+    Workspace &ws = workspace();
+    auto t0 = std::chrono::steady_clock::now();
+    if (stats) {
+        stats->raw_states = raw.n_states;
+        stats->raw_arcs = (int)raw.src.size();
+    }
+    if (!determinize_phone_pruned(ws, raw, m, (double)lattice_beam, true, &ws.clat, stats)) return {};
+    scale_graph_costs(&ws.clat, lm_scale);
+    if (stats) stats->ms_det = ms_since(t0);
+    t0 = std::chrono::steady_clock::now();
+    WordAligner(ws, ws.clat, m).run();
+    if (stats) stats->ms_align = ms_since(t0);
+    t0 = std::chrono::steady_clock::now();
+    std::vector<WordSpan> r = mbr_one_best(ws, stats);
+    if (stats) stats->ms_mbr = ms_since(t0);
+    return r;
+}
+
+std::string lattice_debug_text(const RawLattice &raw, const Model &m, float lattice_beam, int stage, bool phone_pass, double lm_scale) {
+    Workspace &ws = workspace();
+    std::string text;
+    char b[160];
+    auto tids = [](const int *t, int n) {
+        std::string s;
+        for (int i = 0; i < n; i++) s += (i ? "," : "") + std::to_string(t[i]);
+        return s.empty() ? std::string("-") : s;
+    };
+    if (!determinize_phone_pruned(ws, raw, m, (double)lattice_beam, phone_pass, &ws.clat, nullptr)) return "S -1\n";
+    scale_graph_costs(&ws.clat, lm_scale);
+    if (stage == 1) {
+        const CLatF &L = ws.clat;
+        snprintf(b, sizeof b, "S %d\n", L.start);
+        text += b;
+        for (int s = 0; s < L.n; s++) {
+            for (int k = L.off[s]; k < L.off[s + 1]; k++) {
+                const CArcF &a = L.arcs[k];
+                snprintf(b, sizeof b, "A %d %d %d %.9g %.9g ", s, a.next, a.label, a.g, a.a);
+                text += b + tids(L.tids.data() + a.t_off, a.t_len) + "\n";
+            }
+            if (L.is_final[s]) {
+                snprintf(b, sizeof b, "F %d %.9g %.9g ", s, L.fin_g[s], L.fin_a[s]);
+                text += b + tids(L.tids.data() + L.fin_off[s], L.fin_len[s]) + "\n";
+            }
+        }
+        return text;
+    }
+    WordAligner(ws, ws.clat, m).run();
+    const ALat &L = ws.ali;
+    snprintf(b, sizeof b, "S %d\n", L.start);
+    text += b;
+    for (int s = 0; s < L.n(); s++) {
+        for (int k = L.head[s]; k >= 0; k = L.arcs[k].link) {
+            const AArc &a = L.arcs[k];
+            if (a.next == kDead) continue;
+            snprintf(b, sizeof b, "A %d %d %d %.9g %.9g ", s, a.next, a.label, a.g, a.a);
+            text += b + tids(ws.seq.data() + a.t_off, a.t_len) + "\n";
+        }
+        if (L.is_final[s]) {
+            snprintf(b, sizeof b, "F %d %.9g %.9g -\n", s, L.fin_g[s], L.fin_a[s]);
+            text += b;
+        }
+    }
+    return text;
 }
 
 }  // namespace vb

@@ -238,6 +238,7 @@ void Model::load_kaldi_am(const std::string &mdl) {
     }
     tid2pdf = std::move(k.tid2pdf);
     tid2phone = std::move(k.tid2phone);
+    tid_flags = std::move(k.tid_flags);
 }
 
 void Model::load_vbt_am(const std::string &mdl) {
@@ -309,6 +310,10 @@ void Model::load_vbt_am(const std::string &mdl) {
     const Tensor *t2p = find(am, "tid2pdf"), *t2ph = find(am, "tid2phone");
     tid2pdf.assign(t2p->i32(), t2p->i32() + t2p->numel());
     tid2phone.assign(t2ph->i32(), t2ph->i32() + t2ph->numel());
+    // the container's transition model is the chain topology of the generator: one emitting HMM state per phone,
+    // tid = 2*tstate+1 its self-loop, 2*tstate+2 the forward transition into the final state
+    tid_flags.assign(tid2phone.size(), 0);
+    for (size_t tid = 1; tid < tid_flags.size(); tid++) tid_flags[tid] = (uint8_t)(4 | ((tid % 2) == 1 ? 1 : 2));
 }
 
 void Model::load(const std::string &d) {

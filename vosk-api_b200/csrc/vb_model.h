@@ -59,6 +59,9 @@ struct Model {
     std::vector<AmOp> ops;
     std::vector<int> node_dim;  // node 0 = MFCC input, node i+1 = output of op i
     std::vector<int32_t> tid2pdf, tid2phone;
+    // per transition-id: bit 0 self-loop (TransitionModel::IsSelfLoop), bit 1 final = enters the HMM's final state (IsFinal),
+    // bit 2 leaves HMM state 0 (TransitionIdToHmmState == 0); index 0 unused
+    std::vector<uint8_t> tid_flags;
     Graph graph;
     std::vector<std::string> words;
     std::vector<int> phone_type;  // 0 none, 1 nonword, 2 begin, 3 end, 4 internal, 5 singleton

@@ -20,7 +20,8 @@ std::vector<WordSpan> align_words(const Model &m, const std::vector<int> &arcs) 
         if (g.arc_olabel[a] != 0) labels.push_back(g.arc_olabel[a]);
         const int tid = g.arc_ilabel[a];
         if (tid == 0) continue;
-        const bool forward = (tid % 2) == 0;  // chain topology: tid = 2*tstate+1 self-loop, 2*tstate+2 forward
+        // a phone instance begins at every transition-id that is not a self-loop (reorder = true: the self-loops follow)
+        const bool forward = !(tid > 0 && tid < (int)m.tid_flags.size() && (m.tid_flags[tid] & 1));
         if (forward || segs.empty()) segs.push_back({m.tid2phone[tid], t, t + 1});
         else segs.back().e = t + 1;
         t++;

@@ -440,35 +440,24 @@ int vosk_b200_lattice_result(const char *model_dir, int n_states, int start, int
         raw.final_state.assign(final_state, final_state + n_final);
         raw.final_cost.assign(final_cost, final_cost + n_final);
         std::string text;
-        if (stage == 0) {
-            text = vb::result_json(m, vb::lattice_to_words(raw, m, lattice_beam), 0.0f);
-        } else {
-            vb::LatticeCtx ctx{&m.graph, &m.tid2phone, &m.phone_type};
-            vb::CLat det, ali;
-            if (vb::determinize_lattice(raw, ctx, lattice_beam, &det)) {
-                vb::scale_graph_costs(&det, 0.9f);
-                if (stage == 2) vb::word_align_lattice(det, ctx, &ali);
+        if (stage == 0) text = vb::result_json(m, vb::lattice_to_words(raw, m, lattice_beam), 0.0f);
+        else if (stage == 3) text = vb::result_nlsml(m, vb::lattice_to_words(raw, m, lattice_beam));
+        else if (stage == 4) {  // timing / size statistics of the chain on this lattice (repeated to warm the scratch)
+            vb::LatticeStats st, one;
+            for (int rep = 0; rep < 12; rep++) {  // best of 12 (the first repetitions size the scratch)
+                vb::lattice_to_words(raw, m, lattice_beam, 0.9, &one);
+                if (rep == 0) st = one;
+                st.ms_det = std::min(st.ms_det, one.ms_det);
+                st.ms_align = std::min(st.ms_align, one.ms_align);
+                st.ms_mbr = std::min(st.ms_mbr, one.ms_mbr);
             }
-            const vb::CLat &L = stage == 2 ? ali : det;
-            char b[128];
-            snprintf(b, sizeof b, "S %d\n", L.start);
-            text += b;
-            auto tids = [&](const std::vector<int> &t) {
-                std::string s2;
-                for (size_t i = 0; i < t.size(); i++) s2 += (i ? "," : "") + std::to_string(t[i]);
-                return s2.empty() ? std::string("-") : s2;
-            };
-            for (size_t s2 = 0; s2 < L.num_states(); s2++) {
-                for (const vb::CLatArc &a : L.arcs[s2]) {
-                    snprintf(b, sizeof b, "A %zu %d %d %.9g %.9g ", s2, a.dst, a.word, a.w.g, a.w.a);
-                    text += b + tids(a.tids) + "\n";
-                }
-                if (L.is_final[s2]) {
-                    snprintf(b, sizeof b, "F %zu %.9g %.9g ", s2, L.final_w[s2].g, L.final_w[s2].a);
-                    text += b + tids(L.final_tids[s2]) + "\n";
-                }
-            }
-        }
+            char b[512];
+            snprintf(b, sizeof b, "{\"raw_states\": %d, \"raw_arcs\": %d, \"det1_states\": %d, \"det1_arcs\": %d, \"det_states\": %d, \"det_arcs\": %d, "
+                     "\"ali_states\": %d, \"ali_arcs\": %d, \"mbr_iters\": %d, \"mbr_q\": %d, \"ms_det\": %.3f, \"ms_align\": %.3f, \"ms_mbr\": %.3f}",
+                     st.raw_states, st.raw_arcs, st.det1_states, st.det1_arcs, st.det_states, st.det_arcs, st.ali_states, st.ali_arcs, st.mbr_iters,
+                     st.mbr_q, st.ms_det, st.ms_align, st.ms_mbr);
+            text = b;
+        } else text = vb::lattice_debug_text(raw, m, lattice_beam, stage >= 10 ? stage - 10 : stage, stage < 10);
         if (out && cap > 0) {
             size_t k = text.size() < (size_t)cap - 1 ? text.size() : (size_t)cap - 1;
             memcpy(out, text.data(), k);
