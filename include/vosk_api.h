@@ -4,10 +4,12 @@
  * ownership rules of the reference's libvosk [REF src/vosk_api.h:287-346], so the reference's
  * cffi package (cdef generated from the header, dlopen of libvosk.so next to the package —
  * [REF python/vosk_builder.py:6-11], [REF python/vosk/__init__.py:17-32,185-235]) and any other
- * binding that calls the batch API load this library unchanged.  Only the batch path is
- * exported: the CPU recognizer, speaker model and grammar functions of the reference header
- * [REF src/vosk_api.h:58-285] are outside the accelerated path and are not defined
- * here — an ABI-mode binding resolves symbols lazily, so their absence only shows if called.
+ * binding load this library unchanged.  The header declares the WHOLE surface of the reference header, so that
+ * eager binders resolve every symbol (JNA's Native.register [REF java/lib/src/main/java/org/vosk/LibVosk.java:38-41],
+ * cgo, P/Invoke): the batch / GPU / log functions are the accelerated path and are implemented; the CPU recognizer,
+ * speaker-model and grammar functions [REF src/vosk_api.h:58-285] are outside it and are exported as
+ * stubs that log "CPU API not built" and return NULL / -1 / "" — the mirror image of how the reference stubs its batch
+ * half when it is built without CUDA [REF src/vosk_api.cc:198-282].
  *
  * All functions are extern "C"; handles are opaque; no exception crosses the boundary.
  */
@@ -24,6 +26,35 @@ typedef struct VoskBatchModel VoskBatchModel;
 
 /* Opaque handle: one audio stream.  Replaces the object behind [REF src/vosk_api.h:50]. */
 typedef struct VoskBatchRecognizer VoskBatchRecognizer;
+
+/* ---- CPU recognizer API of the reference: declared and exported, NOT implemented (stubs; see the header comment) ---- */
+typedef struct VoskModel VoskModel;            /* [REF src/vosk_api.h:30] */
+typedef struct VoskSpkModel VoskSpkModel;      /* [REF src/vosk_api.h:35] */
+typedef struct VoskRecognizer VoskRecognizer;  /* [REF src/vosk_api.h:41] */
+
+VoskModel *vosk_model_new(const char *model_path);                        /* [REF :58]  stub: NULL */
+void vosk_model_free(VoskModel *model);                                   /* [REF :66]  stub: no-op */
+int vosk_model_find_word(VoskModel *model, const char *word);             /* [REF :74]  stub: -1 */
+VoskSpkModel *vosk_spk_model_new(const char *model_path);                 /* [REF :81]  stub: NULL */
+void vosk_spk_model_free(VoskSpkModel *model);                            /* [REF :89]  stub: no-op */
+VoskRecognizer *vosk_recognizer_new(VoskModel *model, float sample_rate); /* [REF :100] stub: NULL */
+VoskRecognizer *vosk_recognizer_new_spk(VoskModel *model, float sample_rate, VoskSpkModel *spk_model);  /* [REF :115] stub: NULL */
+VoskRecognizer *vosk_recognizer_new_grm(VoskModel *model, float sample_rate, const char *grammar);      /* [REF :137] stub: NULL */
+void vosk_recognizer_set_spk_model(VoskRecognizer *recognizer, VoskSpkModel *spk_model);                /* [REF :146] stub */
+void vosk_recognizer_set_max_alternatives(VoskRecognizer *recognizer, int max_alternatives);            /* [REF :162] stub */
+void vosk_recognizer_set_words(VoskRecognizer *recognizer, int words);                                  /* [REF :198] stub */
+void vosk_recognizer_set_partial_words(VoskRecognizer *recognizer, int partial_words);                  /* [REF :204] stub */
+void vosk_recognizer_set_nlsml(VoskRecognizer *recognizer, int nlsml);                                  /* [REF :209] stub */
+int vosk_recognizer_accept_waveform(VoskRecognizer *recognizer, const char *data, int length);          /* [REF :221] stub: -1 */
+int vosk_recognizer_accept_waveform_s(VoskRecognizer *recognizer, const short *data, int length);       /* [REF :226] stub: -1 */
+int vosk_recognizer_accept_waveform_f(VoskRecognizer *recognizer, const float *data, int length);       /* [REF :231] stub: -1 */
+const char *vosk_recognizer_result(VoskRecognizer *recognizer);           /* [REF :250] stub: "" */
+const char *vosk_recognizer_partial_result(VoskRecognizer *recognizer);   /* [REF :264] stub: "" */
+const char *vosk_recognizer_final_result(VoskRecognizer *recognizer);     /* [REF :273] stub: "" */
+void vosk_recognizer_reset(VoskRecognizer *recognizer);                   /* [REF :279] stub */
+void vosk_recognizer_free(VoskRecognizer *recognizer);                    /* [REF :285] stub */
+
+/* ---- the accelerated path ---- */
 
 /* [REF src/vosk_api.h:294]  0 = info and errors, < 0 = errors only, > 0 = verbose. */
 void vosk_set_log_level(int log_level);

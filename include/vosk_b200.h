@@ -18,7 +18,7 @@ extern "C" {
 /* Like vosk_batch_model_new but with an explicit model directory and "key=value,key=value"
  * options: frames-per-chunk, max-batch-size, num-channels, beam, lattice-beam, max-active,
  * min-active, tok-cap, cand-cap, hash-size, max-seconds, log-tokens-per-frame, tensor-cores, lattice,
- * log-links-per-frame, lat-tok-cap, lat-link-cap, post-threads, partials, pipeline-slots, heavy-tokens, device-resample,
+ * log-links-per-frame, lat-tok-cap, lat-link-cap, post-threads, partials, pipeline-slots, heavy-tokens, device-resample, model-conf,
  * debug-capture, devices (GPU indices separated by ':' or "all").  tensor-cores: 1 = fp16 hi/lo operand split (default),
  * 2 = TF32 hi/lo split, 0 = fp32 FFMA kernel.
  * Env VOSK_BATCH_OPTIONS / VOSK_BATCH_DEVICES are applied first.  NULL on failure. */
@@ -37,7 +37,9 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model);
  * one lane spent in a search launch, [15] largest token count of a frame, [16] lane-launches, [17] host ms spent enqueueing steps,
  * [18] arcs parked below the running cutoff, [19] lattice links logged, [20] lattice arcs kept after pruning,
  * [21..28] / [29..36] SM cycles the 1024-thread / smaller search CTAs spent per phase (cutoff, rank, log, gather,
- * insert, closure, finalize, unused), [37] per-call segments resampled on the device.
+ * insert, closure, finalize, unused), [37] per-call segments resampled on the device, [38] results delivered although a device
+ * capacity overflowed (logged; the result may be truncated), [39] lattice-mode results that fell back to the best path,
+ * [40] host milliseconds spent by the lattice thread pool, [41] its jobs, [42] its threads.
  * Returns the number written. */
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n);
 void vosk_batch_model_reset_stats(VoskBatchModel *model);

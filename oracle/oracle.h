@@ -112,7 +112,7 @@ void orc_free(void *p);
  *      Input = the raw lattice of orc_decoder_lattice.  tid_flags (may be NULL = the generator's chain topology): bit 0 self-loop,
  *      bit 1 final transition, bit 2 leaves HMM state 0.  stage 0 = result text (JSON / NLSML), 1 = determinized + scaled
  *      CompactLattice, 2 = word-aligned CompactLattice as text lines ("S start", "A src dst word graph acoustic tids",
- *      "F state graph acoustic tids").  phone_pass 0 skips the phone-level first determinization pass.
+ *      "F state graph acoustic tids"), 5 = the raw MBR one-best ("word-id begin end confidence" per line, frames).  phone_pass 0 skips the phone-level first determinization pass.
  *      Returns a malloc'd string (orc_free). ---- */
 char *orc_lattice_result(const OrcResultCtx *c, const float *arc_w, const unsigned char *tid_flags, int num_tids, int n_states, int start,
                          int64_t n_links, const int64_t *src, const int64_t *dst, const int *arc, const float *acoustic, int64_t n_final,

@@ -308,17 +308,25 @@ def lattice_result(model, dec, lattice_beam=None, lm_scale=0.9, offset=0.0, nlsm
     return s
 
 
-def recognize(model, wave, frames_per_chunk=51, stages=False, rc=None, **over):
-    """Whole reference path for one stream: int16 samples -> result text (one segment, no endpointing)."""
+def recognize(model, wave, frames_per_chunk=51, stages=False, rc=None, lattice=True, **over):
+    """Whole reference path for one stream: int16 samples -> result text (one segment, no endpointing).
+
+    lattice=True (the reference's only result path [REF src/batch_recognizer.cc:43-107,138-149]): raw lattice within
+    lattice_beam -> phone-pruned determinization -> graph scale 0.9 -> word alignment -> MBR text.  lattice=False: the text of
+    the best path (= the MBR result of a linear lattice, confidence 1), which is what the engine's lattice=0 mode returns."""
     ctx = model_context(model)
     feats = mfcc(wave)
     ends, avail, iv_index = chunk_plan(len(wave), frames_per_chunk, ctx)
     ivecs = ivectors(model, feats, ends, avail)
     ll = nnet_forward(model, feats, ivecs, iv_index)
+    rc = rc or ResultCtx(model)
+    if lattice and "lattice_beam" not in over:
+        over["lattice_beam"] = float(model["conf"].get("lattice-beam", 6.0))
     dec = decode(model, ll, **over) if len(ll) else dict(best_arcs=np.zeros(0, dtype=np.int32))
-    text = result_json(model, dec["best_arcs"], rc=rc)
+    text_best = result_json(model, dec["best_arcs"], rc=rc)
+    text = lattice_result(model, dec, over["lattice_beam"], rc=rc) if lattice and "lattice" in dec else text_best
     if stages:
-        return dict(mfcc=feats, ivectors=ivecs, loglikes=ll, decode=dec, text=text, iv_index=iv_index)
+        return dict(mfcc=feats, ivectors=ivecs, loglikes=ll, decode=dec, text=text, text_best=text_best, iv_index=iv_index)
     return text
 
 
@@ -358,12 +366,13 @@ def endpoint_detected(model, dec, rules, silence_phones):
     return False
 
 
-def recognize_segments(model, wave, frames_per_chunk=51, rule5_seconds=20.0, rc=None, silence_phones=None, rules=None, **over):
+def recognize_segments(model, wave, frames_per_chunk=51, rule5_seconds=20.0, rc=None, silence_phones=None, rules=None, lattice=True, **over):
     """The batch path with reset_on_endpoint [REF src/batch_model.cc:72]: Kaldi's endpoint rules tested after every chunk; a
     segment is finalized there, the search starts over on the next chunk while features and i-vector carry on, and result
     times are offset by the segment start (GetTimeOffsetSeconds [REF src/batch_recognizer.cc:146-147]).  With an empty
     silence-phone list only rule 5 (decoded length >= 20 s) can fire; with silence_phones (a set of phone ids) rules 1-4 run
-    too (`rules` defaults to Kaldi's).  Returns the list of result texts."""
+    too (`rules` defaults to Kaldi's).  lattice: result text through the lattice chain (default, as the reference) or from the
+    best path.  Returns the list of result texts."""
     ctx = model_context(model)
     feats = mfcc(wave)
     ends, avail, iv_index = chunk_plan(len(wave), frames_per_chunk, ctx)
@@ -382,8 +391,15 @@ def recognize_segments(model, wave, frames_per_chunk=51, rule5_seconds=20.0, rc=
             close = endpoint_detected(model, d, rules or ENDPOINT_RULES, silence_phones)
         if close:
             seg = ll[seg_start:dec]
-            if d is None:
-                d = decode(model, seg, **over) if len(seg) else dict(best_arcs=np.zeros(0, dtype=np.int32))
-            texts.append(result_json(model, d["best_arcs"], offset=float(np.float32(seg_start * 0.03)), rc=rc))
+            lb = float(over.get("lattice_beam", model["conf"].get("lattice-beam", 6.0)))
+            if len(seg) and (d is None or (lattice and "lattice" not in d)):
+                d = decode(model, seg, **dict(over, lattice_beam=lb)) if lattice else decode(model, seg, **over)
+            elif d is None:
+                d = dict(best_arcs=np.zeros(0, dtype=np.int32))
+            off = float(np.float32(seg_start * 0.03))
+            if lattice and "lattice" in d:
+                texts.append(lattice_result(model, d, lb, offset=off, rc=rc))
+            else:
+                texts.append(result_json(model, d["best_arcs"], offset=off, rc=rc))
             seg_start = dec
     return texts

@@ -1351,7 +1351,13 @@ extern "C" char *orc_lattice_result(const OrcResultCtx *c, const float *arc_w, c
             const MbrResult r = Mbr(aligned).result();
             const int size = (int)r.words.size();
             auto word = [&](int id) { return std::string(id >= 0 && id < c->num_words ? c->words[id] : ""); };
-            if (nlsml) {
+            if (stage == 5) {  // the raw MBR output: one "word-id begin end confidence" line per word (test hook)
+                char b[128];
+                for (int i = 0; i < size; i++) {
+                    snprintf(b, sizeof b, "%d %.9g %.9g %.9g\n", r.words[i], r.times[i].first, r.times[i].second, r.conf[i]);
+                    out += b;
+                }
+            } else if (nlsml) {
                 std::stringstream ss, text;
                 ss << "<?xml version=\"1.0\"?>\n";
                 ss << "<result grammar=\"default\">\n";

@@ -42,7 +42,7 @@ def run_engine(model_dir, waves, options="", capture=True, bytes_per_call=8000, 
                 d[k] = r.DebugGet(k, np.int32)
             d["tok_cost"] = r.DebugGet("tok_cost", np.float32)
             d["error"] = int(r.DebugGet("error", np.int32)[0])
-            if "lattice=1" in options or "lattice=2" in options:
+            if "lattice=0" not in options:  # lattice generation is the default result path
                 d["lat_hdr"] = r.DebugGet("lat_hdr", np.int32)
                 d["lat_links"] = r.DebugGet("lat_links", np.int32).reshape(-1, 4)
                 d["lat_final"] = r.DebugGet("lat_final", np.int32).reshape(-1, 2)

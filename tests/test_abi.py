@@ -101,3 +101,37 @@ def test_reference_python_package_loads_our_library(tmp_path):
     env = dict(os.environ, PYTHONPATH="")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=str(tmp_path))
     assert "ok True True" in out.stdout, out.stderr[-800:]
+
+
+def test_every_symbol_of_the_reference_header_resolves(lib):
+    """Eager binders (JNA Native.register [REF java/lib/src/main/java/org/vosk/LibVosk.java:38-41], cgo, P/Invoke) bind the
+    whole reference header at load time: every function it declares must be exported — the batch / GPU half implemented,
+    the CPU recognizer half as "not built" stubs (NULL / -1 / ""), the mirror image of [REF src/vosk_api.cc:198-282]."""
+    import re
+    def protos(text):  # declared functions (comments stripped): name -> prototype with single spaces
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        return {re.search(r"(vosk_[a-z_0-9]+)\s*\(", p).group(1): re.sub(r"\s+", " ", p).strip()
+                for p in re.findall(r"[A-Za-z_][A-Za-z_ \*]*\bvosk_[a-z_0-9]+\s*\([^;{]*\)\s*;", text)}
+    ours = protos(open(os.path.join(ROOT, "include", "vosk_api.h")).read())
+    names = list(ours)
+    ref = "/root/reference/src/vosk_api.h"
+    if os.path.exists(ref):
+        theirs = protos(open(ref).read())
+        assert set(theirs) == set(ours), sorted(set(theirs) ^ set(ours))
+        for n in theirs:  # identical prototypes
+            assert theirs[n] == ours[n], (theirs[n], ours[n])
+    assert len(set(names)) == 35  # 21 CPU + 14 batch / GPU / log functions
+    for n in set(names):
+        assert hasattr(lib, n), n
+    lib.vosk_set_log_level(-2)
+    lib.vosk_model_new.restype = ctypes.c_void_p
+    lib.vosk_recognizer_new.restype = ctypes.c_void_p
+    lib.vosk_recognizer_result.restype = ctypes.c_char_p
+    assert not lib.vosk_model_new(b"model")
+    assert not lib.vosk_recognizer_new(None, ctypes.c_float(16000.0))
+    assert lib.vosk_recognizer_accept_waveform(None, b"ab", 2) == -1
+    assert lib.vosk_model_find_word(None, b"x") == -1
+    assert lib.vosk_recognizer_result(None) == b""
+    lib.vosk_recognizer_free(None)
+    lib.vosk_model_free(None)

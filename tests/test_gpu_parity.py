@@ -15,8 +15,8 @@ def _waves(lengths, seed0=100):
     return [vbmodel.synth_audio(s, seed0 + i) for i, s in enumerate(lengths)]
 
 
-def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3, lattice_beam=6.0, mdir=None):
-    ref = oracle.recognize(model, wave, frames_per_chunk=fpc, stages=True)
+def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3, lattice_beam=6.0, mdir=None, options=None):
+    ref = oracle.recognize(model, wave, frames_per_chunk=fpc, stages=True, lattice=False)
     D = int(model["cfg"]["ivector-dim"])
     P = int(model["cfg"]["num-pdfs"])
     assert got["error"] == 0
@@ -59,12 +59,15 @@ def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3, lattice_beam=6.0, 
             for x, y in zip(a, b):
                 np.testing.assert_array_equal(x, y)
             assert got["lat_tok_frame"][hdr[3]] == 0 and got["lat_tok_state"][hdr[3]] == model["graph"]["start"]
-            # result text: the host chain (determinize, scale, align, MBR) on the oracle's lattice, run without the GPU
+            # result text: the ORACLE's chain (phone-pruned determinization, graph scale, word alignment, MBR —
+            # oracle/orc_lattice.cc) on the oracle's lattice of the engine's log-likelihoods: identical, confidences included
             ldec = oracle.decode(model, ll, lattice_beam=lattice_beam)
-            want = helpers.lattice_text(mdir, ldec["lattice"], helpers.oracle_lattice_start(ldec), lattice_beam)
-            assert helpers.results_close(got["text"], want, conf_tol=1e-4), (got["text"], want)
+            if "lattice=2" not in (options or ""):
+                assert got["text"] == helpers.oracle_lattice_text(model, ldec, lattice_beam), (got["text"],)
+            else:
+                assert got["text"] == oracle.result_json(model, dec["best_arcs"])
             return
-    # end to end: identical transcript and word timings against the pure-oracle pipeline
+    # end to end (best-path mode, or nothing to decode): identical transcript and word timings against the pure-oracle pipeline
     assert got["text"] == ref["text"]
 
 
@@ -139,18 +142,19 @@ def test_pipelined_steps_give_the_oracle_transcripts(model_root, oracle_lib):
     mdir = model_root("small")
     model = vbmodel.load_model_dir(mdir)
     waves = _waves([3.3, 1.2, 4.1, 2.6, 0.4, 3.9, 2.2, 1.7, 3.0], seed0=1100)
-    for opts in ("num-channels=6,max-batch-size=4,max-seconds=10,pipeline-slots=3", "num-channels=16,max-batch-size=16,max-seconds=10,lattice=1"):
+    refs = [oracle_lib.recognize(model, w, stages=True) for w in waves]
+    for opts in ("num-channels=6,max-batch-size=4,max-seconds=10,pipeline-slots=3,lattice=0", "num-channels=16,max-batch-size=16,max-seconds=10",
+                 "num-channels=6,max-batch-size=4,max-seconds=10,pipeline-slots=3,post-threads=2"):
         got, stats = helpers.run_engine(mdir, waves, options=opts, capture=False, bytes_per_call=32000)
-        for w, g in zip(waves, got):
-            ref = oracle_lib.recognize(model, w, stages=True)
-            if "lattice=1" in opts:
-                # the engine's log-likelihoods differ from the oracle's by < 1e-3, which can move a lattice arc across the
-                # beam: words and times must agree, confidences closely
-                ldec = oracle_lib.decode(model, ref["loglikes"], lattice_beam=6.0)
-                want = helpers.lattice_text(mdir, ldec["lattice"], helpers.oracle_lattice_start(ldec), 6.0)
-                assert helpers.results_close(g["text"], want, conf_tol=5e-2), (g["text"], want)
+        assert stats["truncated"] == 0 and stats["lattice_fallbacks"] == 0
+        for ref, g in zip(refs, got):
+            if "lattice=0" not in opts:
+                # the whole oracle pipeline (its own log-likelihoods, its own lattice chain).  The engine's log-likelihoods
+                # differ by < 1e-3, which moves the posteriors a little and can move a lattice arc across the beam: words and
+                # times must agree, confidences closely (identical-input identity is tested in _check_stream)
+                assert helpers.results_close(g["text"], ref["text"], conf_tol=5e-2), (g["text"], ref["text"])
             else:
-                assert g["text"] == ref["text"]
+                assert g["text"] == ref["text_best"]
 
 
 def test_partial_results_follow_the_best_path(model_root, oracle_lib):
@@ -193,7 +197,7 @@ def test_partial_results_follow_the_best_path(model_root, oracle_lib):
         r.FinishStream()
         m.Wait()
         assert seen >= 3
-        assert r.Result() == oracle_lib.recognize(model, wave, frames_per_chunk=fpc, stages=True)["text"]
+        assert helpers.results_close(r.Result(), oracle_lib.recognize(model, wave, frames_per_chunk=fpc, stages=True)["text"], conf_tol=5e-2)
         lat = m.Latency()
         assert lat["count"] >= seen and lat["p50"] > 0
         del r, m
@@ -249,22 +253,45 @@ def test_rule5_endpoint_segments(model_root, oracle_lib):
     mdir = model_root("tiny")
     model = vbmodel.load_model_dir(mdir)
     waves = [vbmodel.synth_audio(s, 1900 + i) for i, s in enumerate([25.0, 41.3, 7.0])]
-    for opts in ("", "lattice=2"):
+    want_best = [oracle_lib.recognize_segments(model, w, lattice=False) for w in waves]
+    want_lat = [oracle_lib.recognize_segments(model, w) for w in waves]
+    # lattice=1 (default) with fast feeding: the chunk after a rule-5 cut is queued at once, and must still wait for the cut
+    # segment's traceback and lattice to leave the channel (the stream is held back until that step has completed)
+    for opts, bytes_per_call in (("lattice=0", 32000), ("lattice=2", 32000), ("", 32000), ("pipeline-slots=4", 400000)):
         m = vosk.BatchModel(mdir, options="num-channels=4,max-batch-size=4,max-seconds=24," + opts)
         recs = [vosk.BatchRecognizer(m, 16000.0) for _ in waves]
-        helpers.feed_round_robin(recs, waves, 32000)
+        helpers.feed_round_robin(recs, waves, bytes_per_call)
         m.Wait()
-        for r, w in zip(recs, waves):
+        for r, w, wb, wl in zip(recs, waves, want_best, want_lat):
             got = []
             while True:
                 t = r.Result()
                 if not t:
                     break
                 got.append(t)
-            want = oracle_lib.recognize_segments(model, w)
-            assert len(want) == (2 if len(w) < 40 * 16000 and len(w) > 20 * 16000 else 3 if len(w) > 40 * 16000 else 1)
-            assert got == want
+            assert len(wb) == (2 if len(w) < 40 * 16000 and len(w) > 20 * 16000 else 3 if len(w) > 40 * 16000 else 1)
+            if "lattice=0" in opts or "lattice=2" in opts:
+                assert got == wb
+            else:
+                assert len(got) == len(wl)
+                for a, b in zip(got, wl):
+                    assert helpers.results_close(a, b, conf_tol=5e-2), (a, b)
+        st = m.Stats()
+        assert st["truncated"] == 0 and st["lattice_fallbacks"] == 0
         del recs, m
+    # device-resident streams longer than 20 s (bench.py's `value` leg applies rule 5 too), lattice mode
+    m = vosk.BatchModel(mdir, options="num-channels=4,max-batch-size=4,max-seconds=24")
+    lengths = np.array([len(w) for w in waves], dtype=np.int32)
+    mat = np.zeros((len(waves), int((lengths.max() + 7) // 8 * 8)), dtype=np.int16)
+    for i, w in enumerate(waves):
+        mat[i, :len(w)] = w
+    _, texts = m.RunResident(mat, lengths)
+    for t, wl in zip(texts, want_lat):
+        parts = t.replace("}{", "}\x00{").split("\x00")  # the resident run returns the stream's segment texts concatenated
+        assert len(parts) == len(wl)
+        for a, b in zip(parts, wl):
+            assert helpers.results_close(a, b, conf_tol=5e-2), (a, b)
+    del m
 
 
 def test_kaldi_format_model_dir_decodes_like_the_container(model_root, oracle_lib, tmp_path):
@@ -314,7 +341,7 @@ def test_full_size_batch_is_invariant_to_batch_composition(model_root, oracle_li
     assert list(texts) == [g["text"] for g in big]
     del m
     for i in (0, 101, 255, 388, 511):
-        assert big[i]["text"] == oracle_lib.recognize(model, waves[i], stages=True)["text"], i
+        assert helpers.results_close(big[i]["text"], oracle_lib.recognize(model, waves[i], stages=True)["text"], conf_tol=5e-2), i
 
 
 @pytest.mark.parametrize("rate,bytes_per_call", [(8000, 8000), (44100, 3000), (22050, 17000), (8000, 60)])
@@ -378,9 +405,17 @@ def test_silence_endpoint_rules_segment_like_the_oracle(model_root, oracle_lib, 
             f.write(f"--endpoint.rule{r}.min-utterance-length={utt}\n")
     model = vbmodel.load_model_dir(mdir)
     waves = [vbmodel.synth_audio(s, 2300 + i) for i, s in enumerate([6.3, 3.1, 9.0, 0.4])]
-    want = [oracle_lib.recognize_segments(model, w, silence_phones=silence, rules=rules) for w in waves]
+    want = [oracle_lib.recognize_segments(model, w, silence_phones=silence, rules=rules, lattice=False) for w in waves]
     assert max(len(x) for x in want) >= 3 and sum(len(x) for x in want) < 25, [len(x) for x in want]  # the rules fire, but not at every chunk
-    for opts in ("num-channels=4,max-batch-size=4,max-seconds=12", "num-channels=2,max-batch-size=2,max-seconds=12,partials=1"):
+    # model.conf is only honoured with model-conf=1 (the reference's batch path never reads it): without it one segment per stream
+    m = vosk.BatchModel(mdir, options="num-channels=4,max-batch-size=4,max-seconds=12,lattice=0")
+    recs = [vosk.BatchRecognizer(m, 16000.0) for _ in waves]
+    helpers.feed_round_robin(recs, waves, 8000)
+    m.Wait()
+    for r in recs:
+        assert r.Result() and not r.Result()
+    del recs, m
+    for opts in ("model-conf=1,lattice=0,num-channels=4,max-batch-size=4,max-seconds=12", "model-conf=1,lattice=0,num-channels=2,max-batch-size=2,max-seconds=12,partials=1"):
         m = vosk.BatchModel(mdir, options=opts)
         recs = [vosk.BatchRecognizer(m, 16000.0) for _ in waves]
         helpers.feed_round_robin(recs, waves, 8000)
@@ -404,14 +439,14 @@ def test_odd_model_dimensions_decode_like_the_oracle(model_root, oracle_lib):
     mdir = model_root("tiny", overrides=dict(ivector_dim=14, num_pdfs=90), tag="_odd")
     model = vbmodel.load_model_dir(mdir)
     waves = _waves([1.3, 2.9], seed0=2500)
-    m = vosk.BatchModel(mdir, options="debug-capture=1,num-channels=2,max-batch-size=2,max-seconds=8")
+    m = vosk.BatchModel(mdir, options="debug-capture=1,num-channels=2,max-batch-size=2,max-seconds=8,lattice=0")
     recs = [vosk.BatchRecognizer(m, 16000.0) for _ in waves]
     for r in recs:
         r.DebugCapture()
     helpers.feed_round_robin(recs, waves)
     m.Wait()
     for r, w in zip(recs, waves):
-        ref = oracle_lib.recognize(model, w, stages=True)
+        ref = oracle_lib.recognize(model, w, stages=True, lattice=False)
         ll = r.DebugGet("loglikes", np.float32).reshape(-1, 96)
         assert ll.shape[0] == ref["loglikes"].shape[0]
         assert np.abs(ll[:, :90] - ref["loglikes"]).max() < 1e-3
@@ -449,3 +484,105 @@ def test_gemm_kernels_against_fp64(env):
         assert rc == 0, (M, N, K, rc)
         # relative to the output's rms (about 1): the split GEMM must be as good as the fp32 FFMA kernel, far from fp16 / tf32 inputs (1e-3)
         assert err_tc < 1.5e-5 * max(1.0, rms_ref) and rms_tc < 2e-6 * max(1.0, rms_ref), (env, M, N, K, err_tc, rms_tc)
+
+
+def test_nlsml_result_text(model_root, oracle_lib):
+    """set_nlsml(1): the NLSML text of PushLattice [REF src/batch_recognizer.cc:58-80] — mean MBR confidence printed by
+    ostream << float, the words twice — from the lattice chain; identical to the oracle's chain on the engine's log-likelihoods."""
+    import vbmodel
+    import vosk
+    mdir = model_root("tiny")
+    model = vbmodel.load_model_dir(mdir)
+    P = int(model["cfg"]["num-pdfs"])
+    waves = _waves([1.3, 2.9, 0.2], seed0=2700)
+    m = vosk.BatchModel(mdir, options="debug-capture=1,num-channels=4,max-batch-size=4,max-seconds=8")
+    recs = [vosk.BatchRecognizer(m, 16000.0) for _ in waves]
+    for r in recs:
+        r.DebugCapture()
+        r.SetNLSML(True)
+    helpers.feed_round_robin(recs, waves)
+    m.Wait()
+    n_words = 0
+    for r, w in zip(recs, waves):
+        text = r.Result()
+        assert text.startswith('<?xml version="1.0"?>\n<result grammar="default">\n<interpretation grammar="default" confidence="')
+        assert text.endswith("</instance>\n</interpretation>\n</result>\n")
+        ll = r.DebugGet("loglikes", np.float32).reshape(-1, P)
+        if not ll.size:
+            assert "<input mode=\"speech\"></input>" in text
+            continue
+        dec = oracle_lib.decode(model, ll, lattice_beam=6.0)
+        assert text == helpers.oracle_lattice_text(model, dec, 6.0, nlsml=True)
+        n_words += text.split("<instance>")[1].count(" ") + 1
+    assert n_words >= 5
+    del recs, m
+
+
+def test_large_architecture_long_utterance_loglikes(model_root, oracle_lib):
+    """The 1e-3 log-likelihood bound of north_star on a 16 s utterance of the large (assumed en-us-0.22) architecture: 16
+    TDNN-F layers, K up to 3072, default fp16 hi/lo operand split — the longest stream BASELINE.json's configs use."""
+    import vbmodel
+    mdir = model_root("large", overrides=dict(vocab=3000, succ=8), tag="_smallgraph")
+    model = vbmodel.load_model_dir(mdir)
+    waves = [vbmodel.synth_audio(16.0, 2900)]
+    got, st = helpers.run_engine(mdir, waves, options="num-channels=2,max-batch-size=2,max-seconds=18")
+    ref = oracle_lib.recognize(model, waves[0], stages=True, lattice=False)
+    ll = got[0]["loglikes"].reshape(ref["loglikes"].shape)
+    err = np.abs(ll - ref["loglikes"])
+    assert err.max() < 1e-3, err.max()
+    assert st["truncated"] == 0
+    _check_stream(model, oracle_lib, waves[0], got[0], 51, mdir=mdir)
+
+
+def test_capacity_overflow_is_counted_and_logged(model_root):
+    """A device capacity that is too small (here: the token log) still delivers a result, but the overflow is visible: the
+    engine counts it in stats["truncated"] (and logs it) instead of passing a possibly truncated result off as clean."""
+    import vbmodel
+    mdir = model_root("small")
+    waves = _waves([3.0, 2.0], seed0=3100)
+    got, st = helpers.run_engine(mdir, waves, options="num-channels=2,max-batch-size=2,max-seconds=4,log-tokens-per-frame=8,tok-cap=4096,hash-size=8192", capture=False)
+    assert st["truncated"] >= 1
+    assert all(isinstance(g["text"], str) and g["text"].startswith("{") for g in got)
+    got, st = helpers.run_engine(mdir, waves, options="num-channels=2,max-batch-size=2,max-seconds=4", capture=False)
+    assert st["truncated"] == 0 and st["lattice_fallbacks"] == 0
+
+
+def test_abandoned_recognizers_release_their_channels(model_root, oracle_lib):
+    """A recognizer freed without finish_stream must not keep its engine channel: with 2 channels, 6 abandoned streams and
+    then 2 real ones — the real ones still decode (the destructor closes the stream with an empty last chunk)."""
+    import vbmodel
+    import vosk
+    mdir = model_root("tiny")
+    model = vbmodel.load_model_dir(mdir)
+    m = vosk.BatchModel(mdir, options="num-channels=2,max-batch-size=2,max-seconds=6,lattice=0")
+    wave = vbmodel.synth_audio(1.4, 3300)
+    for k in range(6):
+        r = vosk.BatchRecognizer(m, 16000.0)
+        r.AcceptWaveform(wave[:12000].tobytes())  # more than one chunk: the stream holds a channel
+        m.Wait()
+        del r
+    recs = [vosk.BatchRecognizer(m, 16000.0) for _ in range(2)]
+    helpers.feed_round_robin(recs, [wave, wave])
+    m.Wait()
+    want = oracle_lib.recognize(model, wave, lattice=False)
+    for r in recs:
+        assert r.Result() == want
+    del recs, m
+
+
+def test_stream_result_does_not_depend_on_its_device(model_root):
+    """One BatchModel spanning several GPUs (devices=all; the reference API has one model handle [REF src/vosk_api.cc:198-205]):
+    streams are sharded by id, and a stream's text is the same whichever device it lands on."""
+    import vbmodel
+    import vosk
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    mdir = model_root("tiny")
+    waves = _waves([1.3, 2.9, 0.7, 2.2, 1.9, 3.1], seed0=3500)
+    one, _ = helpers.run_engine(mdir, waves, options="num-channels=8,max-batch-size=8,max-seconds=8,devices=0", capture=False)
+    many, st = helpers.run_engine(mdir, waves, options="num-channels=8,max-batch-size=8,max-seconds=8,devices=all", capture=False)
+    assert [g["text"] for g in one] == [g["text"] for g in many]
+    # a second pass with the streams shifted by one: every stream now lives on another device
+    shifted, _ = helpers.run_engine(mdir, waves[1:] + waves[:1], options="num-channels=8,max-batch-size=8,max-seconds=8,devices=all", capture=False)
+    assert [g["text"] for g in shifted] == [g["text"] for g in one[1:] + one[:1]]

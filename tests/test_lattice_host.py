@@ -122,7 +122,7 @@ def test_linear_lattice_gives_the_best_path_result(model_root, oracle_lib, hook)
         final_cost = float(model["graph"]["final"][model["graph"]["arc_next"][arcs[-1]]])
         lat = dict(n_states=n + 1, start=0, src=np.arange(n), dst=np.arange(1, n + 1), arc=arcs, ac=np.linspace(0.5, 1.5, n, dtype=np.float32),
                    final_state=[n], final_cost=[final_cost if np.isfinite(final_cost) else 0.0])
-        assert hook(mdir, lat, 6.0, 0) == r["text"]
+        assert hook(mdir, lat, 6.0, 0) == r["text_best"]
 
 
 @pytest.mark.parametrize("seed,secs,beam", [(41, 1.2, 2.0), (42, 0.8, 3.0), (43, 1.6, 1.5)])

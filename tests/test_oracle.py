@@ -225,7 +225,7 @@ def test_result_text_matches_reference_json_h(model_root, oracle_lib):
     assert gold[0]["dump"] == '{\n  "text" : ""\n}'
     assert gold[1]["dump"] == '{\n  "result" : [{\n      "conf" : 1.000000,\n      "end" : 1.110000,\n      "start" : 0.840000,\n      "word" : "one"\n    }],\n  "text" : "one"\n}'
     # oracle output for a decoded utterance re-assembled through the same structure
-    r = oracle_lib.recognize(m, vbmodel.synth_audio(1.6, 3), stages=True)
+    r = oracle_lib.recognize(m, vbmodel.synth_audio(1.6, 3), stages=True, lattice=False)
     obj = json.loads(r["text"])
     words, b, e = oracle_lib.align_words(m, r["decode"]["best_arcs"])
     assert [m["words"][int(x)] for x in words] == [x["word"] for x in obj.get("result", [])]
@@ -252,6 +252,21 @@ def test_result_text_live_reference_json_h(model_root, oracle_lib):
     m = vbmodel.load_model_dir(model_root("tiny"))
     for seed in (3, 4):
         r = oracle_lib.recognize(m, vbmodel.synth_audio(1.6, seed), stages=True)
+        # lattice mode: the MBR one-best (raw floats) written by the reference's own json.h, with PushLattice's arithmetic
+        # round(t) * 0.03 + offset [REF src/batch_recognizer.cc:91-93], must give the oracle's lattice-mode text
+        for offset in (0.0, 20.13):
+            raw = [x.split() for x in oracle_lib.lattice_result(m, r["decode"], 6.0, stage=5).splitlines()]
+            n = len(raw)
+            ws = [m["words"][int(x[0])].encode() for x in raw]
+            arr = (ctypes.c_char_p * max(n, 1))(*ws)
+            dbl = lambda v: (ctypes.c_double * max(n, 1))(*v)
+            off = float(np.float32(offset))
+            rnd = lambda t: float(np.round(np.float32(t)))  # times are BaseFloat; halves cannot occur away from .5 ties of np.round vs C round
+            p = lib.ref_json_result(n, arr, dbl([rnd(x[1]) * 0.03 + off for x in raw]), dbl([rnd(x[2]) * 0.03 + off for x in raw]),
+                                    dbl([float(np.float32(x[3])) for x in raw]), b" ".join(ws))
+            assert oracle_lib.lattice_result(m, r["decode"], 6.0, offset=offset) == ctypes.string_at(p).decode()
+            assert n >= 2
+        r = oracle_lib.recognize(m, vbmodel.synth_audio(1.6, seed), stages=True, lattice=False)
         words, b, e = oracle_lib.align_words(m, r["decode"]["best_arcs"])
         n = len(words)
         ws = [m["words"][int(x)].encode() for x in words]

@@ -40,6 +40,7 @@ static void apply_option(Config *c, const std::string &k, const std::string &v) 
     else if (k == "log-links-per-frame") I(&c->log_links_per_frame);
     else if (k == "lat-tok-cap") I(&c->lat_tok_cap);
     else if (k == "lat-link-cap") I(&c->lat_link_cap);
+    else if (k == "model-conf") I(&c->model_conf);
     else if (k == "devices") {}  // handled by the caller
     else throw std::runtime_error("unknown batch option '" + k + "'");
 }
@@ -59,14 +60,17 @@ static std::vector<std::pair<std::string, std::string>> split_options(const std:
 
 BatchModel::BatchModel(const std::string &model_dir, const std::string &options) {
     model_.load(model_dir);
-    // hard-coded reference values are the defaults of vb::Config [REF src/batch_model.cc:69-88];
-    // model.conf / ivector.conf values, then VOSK_BATCH_OPTIONS, then explicit options refine them.
-    model_.apply_conf(&cfg_);
+    // hard-coded reference values are the defaults of vb::Config [REF src/batch_model.cc:69-88]; the feature / i-vector conf
+    // files, then (only with model-conf=1) model.conf, then VOSK_BATCH_OPTIONS, then explicit options refine them.
     std::string devices = "0";
     if (const char *e = getenv("VOSK_BATCH_DEVICES")) devices = e;
     std::string all = options;
     if (const char *e = getenv("VOSK_BATCH_OPTIONS")) all = std::string(e) + "," + all;
-    for (auto &kv : split_options(all)) {
+    const auto opts = split_options(all);
+    for (auto &kv : opts)
+        if (kv.first == "model-conf") apply_option(&cfg_, kv.first, kv.second);
+    model_.apply_conf(&cfg_);
+    for (auto &kv : opts) {
         if (kv.first == "devices") devices = kv.second;
         apply_option(&cfg_, kv.first, kv.second);
     }
@@ -85,6 +89,7 @@ BatchModel::BatchModel(const std::string &model_dir, const std::string &options)
     for (int d : devs) {
         Config c = cfg_;
         c.device = d;
+        c.num_engines = (int)devs.size();
         engines_.emplace_back(new Engine(model_, c));
     }
     samples_per_chunk_ = engines_[0]->samples_per_chunk();  // [REF src/batch_model.cc:98]

@@ -20,14 +20,17 @@ BatchRecognizer::BatchRecognizer(BatchModel *model, float sample_frequency)
     const Model *m = &model->model();
     const float lattice_beam = model->engine_for(id_).config().lattice_beam;
     const bool host_chain = model->engine_for(id_).config().lattice == 1;  // lattice=2: device lattice only, text from the best path
-    stream_->on_result = [sink, m, lattice_beam, host_chain](const BestPath &bp) {
+    Engine *eng = &model->engine_for(id_);
+    stream_->on_result = [sink, m, lattice_beam, host_chain, eng](const BestPath &bp) {
         // lattice=1: PushLattice's chain on the pruned raw lattice [REF src/batch_recognizer.cc:43-56]; otherwise (and if the
         // lattice came back empty or over capacity) the best path, which is the MBR result of a linear lattice
         std::vector<WordSpan> words;
         bool done = false;
-        if (host_chain && bp.lattice && bp.lattice->error == 0 && bp.lattice->n_states > 0) {
-            words = lattice_to_words(*bp.lattice, *m, lattice_beam);
+        if (host_chain) {
+            const RawLattice *lat = bp.raw_lattice();
+            if (lat && lat->error == 0 && lat->n_states > 0) words = lattice_to_words(*lat, *m, lattice_beam);
             done = !words.empty() || bp.arcs.empty();
+            if (!done) eng->count_fallback();  // no usable lattice (capacity error, no complete path): logged by the engine, counted here
         }
         if (!done) words = align_words(*m, bp.arcs);
         std::lock_guard<std::mutex> lk(sink->mu);
@@ -40,7 +43,19 @@ BatchRecognizer::BatchRecognizer(BatchModel *model, float sample_frequency)
     };
 }
 
-BatchRecognizer::~BatchRecognizer() {}
+BatchRecognizer::~BatchRecognizer() {
+    // a stream that was never finished still owns an engine channel: close it with an empty last chunk (whatever was buffered
+    // is dropped; the result lands in the shared sink, which nobody reads any more)
+    if (!finished_) {
+        finished_ = true;
+        try {
+            Stream::Chunk ck;
+            ck.last = true;
+            model_->engine_for(id_).push_chunk(stream_, std::move(ck));
+        } catch (...) {
+        }
+    }
+}
 
 void BatchRecognizer::EnableCapture() { stream_->capture.reset(new Capture); }
 

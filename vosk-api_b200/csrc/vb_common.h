@@ -5,6 +5,7 @@
 // CudaDecoder).  One Engine drives one GPU; streams occupy "channels" (persistent per-stream device
 // state) and every engine step processes one chunk for each of up to max_lanes channels ("lanes").
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -64,7 +65,7 @@ struct Config {
     char endpoint_silence_phones[512] = "";
     int ep_must_contain_nonsilence[4] = {0, 1, 1, 1};
     float ep_min_trailing_silence[4] = {5.0f, 0.5f, 1.0f, 2.0f};
-    float ep_max_relative_cost[4] = {1e30f, 2.0f, 8.0f, 1e30f};
+    float ep_max_relative_cost[4] = {INFINITY, 2.0f, 8.0f, INFINITY};  // inf = no limit (rules 1 and 4 also fire when no final state is active)
     float ep_min_utterance_length[4] = {0.f, 0.f, 0.f, 0.f};
     float mfcc_low_freq = 20.f, mfcc_high_freq = -400.f;  // conf/mfcc.conf [REF training/conf/mfcc.conf:4-5]; high <= 0: offset from Nyquist
     int fe_priority = 0;        // CUDA stream priority of the front-end pipe relative to the search pipe (1 / 0 / -1)
@@ -75,10 +76,15 @@ struct Config {
     int cmn_window = 600, global_frames = 200;
     int use_tensor_cores = 1;   // TDNN-F GEMMs on tcgen05, fp32 accumulate: 1 = fp16 hi/lo split (3 x f16 MMAs), 2 = TF32 hi/lo split; 0 = fp32 FFMA kernel
     int debug_capture = 0;      // allow per-stream capture of intermediates (tests)
-    int lattice = 0;            // lattice generation: link log + lattice_beam pruning on the device, raw lattice to the host
+    int lattice = 1;            // 1 (default, the reference's result path [REF src/batch_recognizer.cc:43-107,138-149]): link log +
+                                // lattice_beam pruning on the device, raw lattice to the host chain (determinization, word
+                                // alignment, MBR); 2: device lattice only, text from the best path; 0: best path only
+    int model_conf = 0;         // 1: also take beam / lattice-beam / max-active / min-active / batch sizes and the silence
+                                // endpointing rules from model.conf (the reference's batch path hard-codes them [REF src/batch_model.cc:69-88])
     int log_links_per_frame = 6144;   // average links per frame the link log is sized for
     int partials = 0;           // partial results: best path so far after every chunk (vosk_batch_recognizer_partial_result)
-    int post_threads = 0;       // host threads turning lattices into results (0 = hardware threads / 2, at most 32)
+    int post_threads = 0;       // host threads turning lattices into results (0 = hardware threads / (engines x local ranks))
+    int num_engines = 1;        // engines sharing this host (set by BatchModel)
     int lat_tok_cap = 131072, lat_link_cap = 262144;  // pruned raw lattice of one stream (states / arcs)
 };
 

@@ -68,8 +68,12 @@ Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg)
     upload_model();
     alloc_state();
     thread_ = std::thread([this] { worker(); });
-    if (cfg_.lattice) {
-        int n = cfg_.post_threads > 0 ? cfg_.post_threads : std::max(1, std::min(32, (int)std::thread::hardware_concurrency() / 2));
+    if (cfg_.lattice == 1) {
+        // the host chain (determinization, alignment, MBR) of finished segments runs on all host threads this engine can claim:
+        // hardware threads / (engines of this model x ranks sharing the host under torchrun)
+        int share = std::max(1, cfg_.num_engines);
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) share *= std::max(1, atoi(e));
+        int n = cfg_.post_threads > 0 ? cfg_.post_threads : std::max(1, (int)std::thread::hardware_concurrency() / share);
         for (int i = 0; i < n; i++) post_threads_.emplace_back([this] { post_worker(); });
     }
 }
@@ -84,10 +88,16 @@ void Engine::post_worker() {
             job = std::move(post_queue_.front());
             post_queue_.pop_front();
         }
+        const auto t0 = std::chrono::steady_clock::now();
         try {
             job();
         } catch (const std::exception &ex) {
             log_msg(-1, "lattice post-processing failed: %s", ex.what());
+        }
+        {
+            std::lock_guard<std::mutex> lk(stats_mu_);
+            stats_.post_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            stats_.post_jobs++;
         }
         {
             std::lock_guard<std::mutex> lk(mu_);
@@ -129,9 +139,7 @@ Engine::~Engine() {
         if (sl.h_partial) cudaFreeHost(sl.h_partial);
         if (sl.h_endp) cudaFreeHost(sl.h_endp);
         if (sl.h_lat_hdr) cudaFreeHost(sl.h_lat_hdr);
-        if (sl.h_lat_links) cudaFreeHost(sl.h_lat_links);
-        if (sl.h_lat_final) cudaFreeHost(sl.h_lat_final);
-        if (sl.h_lat_tok) cudaFreeHost(sl.h_lat_tok);
+        if (sl.h_lat_pool) cudaFreeHost(sl.h_lat_pool);
         for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.fork) cudaEventDestroy(sl.fork);
@@ -476,9 +484,7 @@ void Engine::alloc_state() {
             sd.lat_tok_frame = dev_alloc<int>(allocs_, (size_t)L * cfg_.lat_tok_cap);
             sd.lat_tok_state = cfg_.debug_capture ? dev_alloc<int>(allocs_, (size_t)L * cfg_.lat_tok_cap) : nullptr;
             VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lat_hdr, (size_t)L * sizeof(LatHeader)));
-            VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lat_links, (size_t)cfg_.lat_link_cap * sizeof(int4)));
-            VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lat_final, (size_t)cfg_.tok_cap * sizeof(int2)));
-            VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lat_tok, (size_t)2 * cfg_.lat_tok_cap * sizeof(int)));
+            VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_lat_pool, std::max(kLatPoolBytes, (size_t)cfg_.lat_link_cap * sizeof(int4) + (size_t)cfg_.tok_cap * sizeof(int2) + (size_t)2 * cfg_.lat_tok_cap * sizeof(int) + 64)));
         }
     }
     if (cfg_.debug_capture) {
@@ -576,6 +582,7 @@ StepStats Engine::stats() {
     s.links = c[9];
     s.lat_arcs = c[10];
     for (int k = 0; k < 16; k++) s.phase[k] = c[16 + k];
+    s.lattice_fallbacks = lattice_fallbacks_.load();
     return s;
 }
 void Engine::latency(double *out, bool reset) {
@@ -603,6 +610,7 @@ void Engine::reset_stats() {
     cudaMemset(dec_.counters, 0, 32 * sizeof(unsigned long long));
     std::lock_guard<std::mutex> lk(stats_mu_);
     stats_ = StepStats{};
+    lattice_fallbacks_ = 0;
 }
 
 // The batcher: keeps up to pipeline_slots steps in flight.  Steps complete in launch order (both pipes are in order),
@@ -629,16 +637,20 @@ void Engine::worker() {
             const bool must = n_busy >= nslots || !have_ready;
             if (must || cudaEventQuery(old.done) == cudaSuccess) {
                 try {
+                    if (old.failed) throw std::runtime_error("the step could not be launched");
                     complete_step(old);
                 } catch (const std::exception &ex) {
                     log_msg(-1, "engine step failed: %s", ex.what());
                     for (auto &ln : old.lanes)
-                        if (ln.chunk.last && ln.s->on_result) {
+                        if (ln.seg_end && ln.s->on_result) {  // an (empty) result in the segment's place keeps the stream's results in order
                             BestPath bp;
                             bp.error = 100;
+                            bp.seq = ln.seg_index;
+                            bp.offset = ln.seg_offset;
                             ln.s->on_result(bp);
                         }
                 }
+                old.failed = false;
                 old.busy = false;
                 n_busy--;
                 head = (head + 1) % (int)slots_.size();
@@ -650,10 +662,12 @@ void Engine::worker() {
                             free_channels_.push_back(ln.s->channel);
                             ln.s->channel = -1;
                         }
-                        if (endpointing_ && !ln.s->resident) {
-                            // the stream was held back until the endpoint decision of this chunk: a detected endpoint first
-                            // closes the segment with an empty chunk, then the stream goes on (a new segment) with what is queued
-                            if (ln.endpoint && !ln.chunk.last) {
+                        if (ln.holds) {
+                            // the stream was held back — until the endpoint decision of this chunk (silence endpointing), or because
+                            // the chunk closed a segment in mid-stream and its traceback / lattice still lived in the channel's
+                            // search state.  A detected endpoint first closes the segment with an empty chunk, then the stream
+                            // goes on (a new segment) with what is queued
+                            if (endpointing_ && !ln.s->resident && ln.endpoint && !ln.chunk.last) {
                                 Stream::Chunk fin;
                                 fin.last = false;
                                 fin.close_segment = true;
@@ -703,6 +717,7 @@ void Engine::worker() {
                 if (endpointing_ && !s->resident) {
                     s->in_flight = true;  // the next chunk is queued when this one has completed (endpoint decision)
                     s->queued = false;
+                    ln.holds = true;
                 } else if (!s->pending.empty()) again.push_back(s);  // next chunk: a later step (one chunk per stream per step)
                 else s->queued = false;
                 sl.lanes.push_back(std::move(ln));
@@ -720,7 +735,24 @@ void Engine::worker() {
             launch_step(sl, resident_audio_, resident_stride_);
         } catch (const std::exception &ex) {
             log_msg(-1, "engine launch failed: %s", ex.what());
+            sl.failed = true;
             cudaEventRecord(sl.done, dec_stream_);  // let the completion path release the lanes
+        }
+        {
+            // A chunk that closes a segment in mid-stream (rule 5, or an injected close) leaves its result — path, token log,
+            // link log, the scratch lattice pruning borrows — in the channel until the step has completed; the stream's next
+            // chunk starts a new search in the same channel, so it must not be launched before that: hold the stream back.
+            std::lock_guard<std::mutex> lk(mu_);
+            for (auto &ln : sl.lanes) {
+                if (!ln.seg_end || ln.chunk.last || ln.s->in_flight) continue;
+                ln.s->in_flight = true;
+                ln.holds = true;
+                if (ln.s->queued) {
+                    auto it = std::find(ready_.begin(), ready_.end(), ln.s);
+                    if (it != ready_.end()) ready_.erase(it);
+                    ln.s->queued = false;
+                }
+            }
         }
         sl.busy = true;
         n_busy++;
@@ -1048,58 +1080,111 @@ void Engine::complete_step(Slot &sl) {
         stats_.resample_segments += sl.resample_segs;
         stats_.dec_launches++;
     }
+    std::vector<std::shared_ptr<PackedLattice>> lats;
+    if (cfg_.lattice) fetch_lattices(sl, &lats);
     int n_last = 0;
     for (int i = 0; i < L; i++)
-        if (lanes[i].seg_end) finish_lane(sl, lanes[i], n_last++, i);
+        if (lanes[i].seg_end) finish_lane(sl, lanes[i], n_last++, cfg_.lattice ? lats[i] : nullptr);
 }
 
-// copies one finished lane's pruned lattice to the host (sizes come from the header that arrived with the step)
-std::shared_ptr<RawLattice> Engine::fetch_lattice(Slot &sl, int i) {
+std::shared_ptr<RawLattice> PackedLattice::unpack() const {
     auto lat = std::make_shared<RawLattice>();
-    const LatHeader h = sl.h_lat_hdr[i];
-    cudaStream_t st = sl.stream;
-    lat->n_states = h.n_tok;
-    lat->start = h.start;
-    lat->frames = h.frames;
-    lat->error = h.error;
-    if (h.n_tok <= 0) return lat;
-    const bool with_state = sl.dec.lat_tok_state != nullptr;
-    VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_links, sl.dec.lat_links + (size_t)i * cfg_.lat_link_cap, (size_t)h.n_links * sizeof(int4), cudaMemcpyDeviceToHost, st));
-    VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_final, sl.dec.lat_final + (size_t)i * cfg_.tok_cap, (size_t)h.n_final * sizeof(int2), cudaMemcpyDeviceToHost, st));
-    VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_tok, sl.dec.lat_tok_frame + (size_t)i * cfg_.lat_tok_cap, (size_t)h.n_tok * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (with_state)
-        VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_tok + cfg_.lat_tok_cap, sl.dec.lat_tok_state + (size_t)i * cfg_.lat_tok_cap, (size_t)h.n_tok * sizeof(int), cudaMemcpyDeviceToHost, st));
-    VB_CUDA_CHECK(cudaStreamSynchronize(st));
-    lat->src.resize(h.n_links);
-    lat->dst.resize(h.n_links);
-    lat->arc.resize(h.n_links);
-    lat->acoustic.resize(h.n_links);
-    for (int k = 0; k < h.n_links; k++) {
-        const int4 l = sl.h_lat_links[k];
+    lat->n_states = n_tok;
+    lat->start = start;
+    lat->frames = frames;
+    lat->error = error;
+    const size_t nl = links.size(), nf = finals.size();
+    lat->src.resize(nl);
+    lat->dst.resize(nl);
+    lat->arc.resize(nl);
+    lat->acoustic.resize(nl);
+    for (size_t k = 0; k < nl; k++) {
+        const int4 l = links[k];
         lat->src[k] = l.x;
         lat->dst[k] = l.y;
         lat->arc[k] = l.z;
         memcpy(&lat->acoustic[k], &l.w, 4);
     }
-    lat->final_state.resize(h.n_final);
-    lat->final_cost.resize(h.n_final);
-    for (int k = 0; k < h.n_final; k++) {
-        lat->final_state[k] = sl.h_lat_final[k].x;
-        memcpy(&lat->final_cost[k], &sl.h_lat_final[k].y, 4);
+    lat->final_state.resize(nf);
+    lat->final_cost.resize(nf);
+    for (size_t k = 0; k < nf; k++) {
+        lat->final_state[k] = finals[k].x;
+        memcpy(&lat->final_cost[k], &finals[k].y, 4);
     }
-    lat->state_frame.assign(sl.h_lat_tok, sl.h_lat_tok + h.n_tok);
-    if (with_state) lat->state_graph.assign(sl.h_lat_tok + cfg_.lat_tok_cap, sl.h_lat_tok + cfg_.lat_tok_cap + h.n_tok);
+    lat->state_frame = tok_frame;
+    lat->state_graph = tok_state;
     return lat;
 }
 
-void Engine::finish_lane(Slot &sl, Lane &ln, int k, int lane_pos) {
+// Copies the pruned lattices of the step's finished lanes to the host (sizes come from the headers that arrived with the
+// step): as many lanes per synchronize as fit the pinned bounce buffer, then plain copies into per-lane vectors.
+void Engine::fetch_lattices(Slot &sl, std::vector<std::shared_ptr<PackedLattice>> *out) {
+    const int L = (int)sl.lanes.size();
+    out->assign(L, nullptr);
+    cudaStream_t st = sl.stream;
+    const bool with_state = sl.dec.lat_tok_state != nullptr;
+    struct Pending {
+        int lane;
+        size_t links, finals, tok, tok_state;
+    };
+    std::vector<Pending> batch;
+    size_t used = 0;
+    const size_t cap = std::max(kLatPoolBytes, (size_t)cfg_.lat_link_cap * sizeof(int4) + (size_t)cfg_.tok_cap * sizeof(int2) + (size_t)2 * cfg_.lat_tok_cap * sizeof(int) + 64);
+    auto flush = [&]() {
+        if (batch.empty()) return;
+        VB_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (const Pending &p : batch) {
+            PackedLattice &pl = *(*out)[p.lane];
+            if (!pl.links.empty()) memcpy(pl.links.data(), sl.h_lat_pool + p.links, pl.links.size() * sizeof(int4));
+            if (!pl.finals.empty()) memcpy(pl.finals.data(), sl.h_lat_pool + p.finals, pl.finals.size() * sizeof(int2));
+            if (!pl.tok_frame.empty()) memcpy(pl.tok_frame.data(), sl.h_lat_pool + p.tok, pl.tok_frame.size() * sizeof(int));
+            if (!pl.tok_state.empty()) memcpy(pl.tok_state.data(), sl.h_lat_pool + p.tok_state, pl.tok_state.size() * sizeof(int));
+        }
+        batch.clear();
+        used = 0;
+    };
+    auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    for (int i = 0; i < L; i++) {
+        if (!sl.lanes[i].seg_end) continue;
+        const LatHeader h = sl.h_lat_hdr[i];
+        auto pl = std::make_shared<PackedLattice>();
+        pl->n_tok = h.n_tok;
+        pl->start = h.start;
+        pl->frames = h.frames;
+        pl->error = h.error;
+        (*out)[i] = pl;
+        if (h.n_tok <= 0) continue;
+        const int nl = std::max(0, std::min(h.n_links, cfg_.lat_link_cap)), nf = std::max(0, std::min(h.n_final, cfg_.tok_cap)),
+                  nt = std::max(0, std::min(h.n_tok, cfg_.lat_tok_cap));
+        pl->links.resize(nl);
+        pl->finals.resize(nf);
+        pl->tok_frame.resize(nt);
+        if (with_state) pl->tok_state.resize(nt);
+        const size_t need = align16((size_t)nl * sizeof(int4)) + align16((size_t)nf * sizeof(int2)) + (with_state ? 2 : 1) * align16((size_t)nt * sizeof(int));
+        if (used + need > cap) flush();
+        Pending p{i, used, 0, 0, 0};
+        p.finals = p.links + align16((size_t)nl * sizeof(int4));
+        p.tok = p.finals + align16((size_t)nf * sizeof(int2));
+        p.tok_state = p.tok + align16((size_t)nt * sizeof(int));
+        if (nl) VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_pool + p.links, sl.dec.lat_links + (size_t)i * cfg_.lat_link_cap, (size_t)nl * sizeof(int4), cudaMemcpyDeviceToHost, st));
+        if (nf) VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_pool + p.finals, sl.dec.lat_final + (size_t)i * cfg_.tok_cap, (size_t)nf * sizeof(int2), cudaMemcpyDeviceToHost, st));
+        if (nt) VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_pool + p.tok, sl.dec.lat_tok_frame + (size_t)i * cfg_.lat_tok_cap, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (nt && with_state)
+            VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_pool + p.tok_state, sl.dec.lat_tok_state + (size_t)i * cfg_.lat_tok_cap, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost, st));
+        used += need;
+        batch.push_back(p);
+    }
+    flush();
+}
+
+void Engine::finish_lane(Slot &sl, Lane &ln, int k, std::shared_ptr<PackedLattice> lat) {
     const DecChannelState &cs = sl.h_cs[k];
     BestPath bp;
-    if (cfg_.lattice) {
-        bp.lattice = fetch_lattice(sl, lane_pos);
-        if (bp.lattice->error && !cs.error)
-            log_msg(-1, "stream %llu: lattice capacity error %d", (unsigned long long)ln.s->id, bp.lattice->error);
-        if (ln.s->capture) ln.s->capture->lattice = bp.lattice;
+    if (lat) {
+        bp.packed = std::move(lat);
+        if (bp.packed->error && !cs.error)
+            log_msg(-1, "stream %llu: lattice capacity error %d", (unsigned long long)ln.s->id, bp.packed->error);
+        if (ln.s->capture) ln.s->capture->lattice = bp.packed->unpack();
     }
     bp.cost = cs.best_cost;
     bp.reached_final = cs.reached_final != 0;
@@ -1112,6 +1197,10 @@ void Engine::finish_lane(Slot &sl, Lane &ln, int k, int lane_pos) {
     const int *p = sl.h_path + (size_t)k * path_cap_;
     for (int i = 0; i < n; i++) bp.arcs[i] = p[n - 1 - i];
     if (cs.error) log_msg(-1, "stream %llu: decoder capacity error %d (result may be truncated)", (unsigned long long)ln.s->id, cs.error);
+    if (cs.error || (bp.packed && bp.packed->error)) {
+        std::lock_guard<std::mutex> lk(stats_mu_);
+        stats_.truncated++;
+    }
     if (!ln.s->on_result) return;
     if (post_threads_.empty()) {
         ln.s->on_result(bp);

@@ -33,8 +33,23 @@ struct RawLattice {
     std::vector<int> state_frame, state_graph;  // per lattice state: frame, graph state (graph state only with debug-capture)
 };
 
+// one finished lane's pruned lattice exactly as the device wrote it (copied off the pinned bounce buffer by the batcher
+// thread; turned into a RawLattice where the result is made, on the lattice thread pool)
+struct PackedLattice {
+    int n_tok = 0, start = -1, frames = 0, error = 0;
+    std::vector<int4> links;   // {src, dst, csr arc, acoustic cost bits}
+    std::vector<int2> finals;  // {state, final cost bits}
+    std::vector<int> tok_frame, tok_state;
+    std::shared_ptr<RawLattice> unpack() const;
+};
+
 struct BestPath {
-    std::shared_ptr<RawLattice> lattice;  // set when lattice generation is on
+    std::shared_ptr<PackedLattice> packed;         // set when lattice generation is on
+    mutable std::shared_ptr<RawLattice> lattice;   // unpacked on first use
+    const RawLattice *raw_lattice() const {
+        if (!lattice && packed) lattice = packed->unpack();
+        return lattice.get();
+    }
     std::vector<int> arcs;  // csr arc ids in path order
     float cost = 0.f;
     bool reached_final = false;
@@ -60,7 +75,8 @@ struct Stream {
     uint64_t id = 0;
     int channel = -1;
     bool started = false, finished = false, queued = false;
-    bool in_flight = false;  // silence endpointing: the stream's next chunk waits for the decision taken when this one completes
+    bool in_flight = false;  // the stream's next chunk waits until the step of this one has completed (silence endpointing: the
+                             // endpoint decision; a segment closed in mid-stream: its result still lives in the channel state)
     int64_t samples = 0;     // samples handed to the GPU so far
     int frames = 0;          // MFCC frames computed so far
     int iv_end = 0, in_end = 0, dec_frames = 0, carry = 0;
@@ -104,6 +120,10 @@ struct StepStats {
     double t_feat = 0, t_ivec = 0, t_nnet = 0, t_dec = 0, t_total = 0;  // device ms (only when timing enabled)
     long long dec_launches = 0, gemm_launches = 0, resample_segments = 0;
     double host_launch_ms = 0;  // host time spent enqueueing steps
+    long long truncated = 0;          // results delivered although a device capacity (tokens / candidates / log / links / lattice) overflowed
+    long long lattice_fallbacks = 0;  // lattice-mode results that fell back to the best path (no lattice, capacity error, chain failure)
+    double post_ms = 0;               // host milliseconds the lattice pool spent on results (summed over its threads)
+    long long post_jobs = 0;
 };
 
 class Engine {
@@ -127,6 +147,8 @@ class Engine {
     void latency(double *out5, bool reset);
     void reset_stats();
     void set_timing(bool on) { timing_ = on; }
+    void count_fallback() { lattice_fallbacks_.fetch_add(1); }
+    int post_thread_count() const { return (int)post_threads_.size(); }
     // limits the number of pipeline slots in use (1 = fully serialized steps: per-kernel timings without overlap)
     void set_active_slots(int n) { active_slots_ = std::max(1, std::min(n, (int)slots_.size())); }
 
@@ -144,6 +166,7 @@ class Engine {
         bool seg_end = false;    // this chunk closes a segment: a result is due
         int seg_start = 0;       // decoder frames before the segment this chunk belongs to
         bool endpoint = false;   // set on completion: a silence endpoint was detected after this chunk
+        bool holds = false;      // this lane holds its stream back (Stream::in_flight) until the step has completed
         float seg_offset = 0.f;
         int seg_index = 0;
     };
@@ -173,9 +196,8 @@ class Engine {
         int *h_partial = nullptr;  // [L][kPartialCap] words + [L] counts
         int *h_endp = nullptr;     // [L] trailing silence frames + [L] final relative cost (float bits)
         LatHeader *h_lat_hdr = nullptr;
-        int4 *h_lat_links = nullptr;  // pinned bounce buffers for one finished lane's lattice
-        int2 *h_lat_final = nullptr;
-        int *h_lat_tok = nullptr;
+        char *h_lat_pool = nullptr;  // pinned bounce buffer the finished lanes' lattices are copied through, many per synchronize
+        bool failed = false;         // the launch threw: nothing of this step can be read back
         std::vector<Lane> lanes;
         bool busy = false, timed = false;
         double audio = 0;
@@ -187,8 +209,8 @@ class Engine {
     void complete_step(Slot &sl);
     void upload_model();
     void alloc_state();
-    void finish_lane(Slot &sl, Lane &ln, int lane_idx, int lane_pos);
-    std::shared_ptr<RawLattice> fetch_lattice(Slot &sl, int lane_pos);
+    void finish_lane(Slot &sl, Lane &ln, int lane_idx, std::shared_ptr<PackedLattice> lat);
+    void fetch_lattices(Slot &sl, std::vector<std::shared_ptr<PackedLattice>> *out);  // all finished lanes of the step, indexed by lane position
 
     const Model &model_;
     Config cfg_;
@@ -243,6 +265,8 @@ class Engine {
     uint64_t next_id_ = 0;
     StepStats stats_;
     std::vector<float> latencies_ms_;  // guarded by stats_mu_
+    std::atomic<long long> lattice_fallbacks_{0};
+    static constexpr size_t kLatPoolBytes = (size_t)96 << 20;
     std::mutex stats_mu_;
 };
 

@@ -437,17 +437,17 @@ void Model::apply_conf(Config *cfg) const {
         auto it = m.find(k);
         if (it != m.end() && !it->second.empty()) *v = std::stof(it->second);
     };
-    // the reference overrides these after reading model.conf [REF src/batch_model.cc:78-82]; we take the
-    // conf value when present so that oracle and engine are driven by one file (defaults = the overrides)
-    getf(conf, "beam", &cfg->beam);
-    getf(conf, "lattice-beam", &cfg->lattice_beam);
-    geti(conf, "max-active", &cfg->max_active);
-    geti(conf, "min-active", &cfg->min_active);
-    geti(conf, "frames-per-chunk", &cfg->frames_per_chunk);
-    geti(conf, "max-batch-size", &cfg->max_lanes);
-    geti(conf, "num-channels", &cfg->num_channels);
-    // endpointing [REF src/model.cc:142-145]: Kaldi's OnlineEndpointConfig keys
-    {
+    // The reference's batch path hard-codes its decoding parameters [REF src/batch_model.cc:69-88] and never reads model.conf
+    // (only the CPU recognizer does [REF src/model.cc:130-145]); model.conf values and its endpointing rules are opt-in.
+    if (cfg->model_conf) {
+        getf(conf, "beam", &cfg->beam);
+        getf(conf, "lattice-beam", &cfg->lattice_beam);
+        geti(conf, "max-active", &cfg->max_active);
+        geti(conf, "min-active", &cfg->min_active);
+        geti(conf, "frames-per-chunk", &cfg->frames_per_chunk);
+        geti(conf, "max-batch-size", &cfg->max_lanes);
+        geti(conf, "num-channels", &cfg->num_channels);
+        // endpointing [REF src/model.cc:142-145]: Kaldi's OnlineEndpointConfig keys
         auto it = conf.find("endpoint.silence-phones");
         if (it != conf.end()) snprintf(cfg->endpoint_silence_phones, sizeof cfg->endpoint_silence_phones, "%s", it->second.c_str());
         for (int r = 0; r < 4; r++) {
@@ -457,7 +457,7 @@ void Model::apply_conf(Config *cfg) const {
             getf(conf, (pre + "min-trailing-silence").c_str(), &cfg->ep_min_trailing_silence[r]);
             getf(conf, (pre + "min-utterance-length").c_str(), &cfg->ep_min_utterance_length[r]);
             auto m = conf.find(pre + "max-relative-cost");
-            if (m != conf.end() && !m->second.empty()) cfg->ep_max_relative_cost[r] = m->second == "inf" ? 1e30f : std::stof(m->second);
+            if (m != conf.end() && !m->second.empty()) cfg->ep_max_relative_cost[r] = m->second == "inf" ? INFINITY : std::stof(m->second);
         }
         getf(conf, "endpoint.rule5.min-utterance-length", &cfg->endpoint_rule5_seconds);
     }

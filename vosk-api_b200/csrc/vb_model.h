@@ -74,6 +74,8 @@ struct Model {
     void load_vbt_am(const std::string &mdl);    // am/final.mdl as the generator's tensor container (collapsed network)
     void load_kaldi_am(const std::string &mdl);  // am/final.mdl as Kaldi's TransitionModel + nnet3 file (vb_kaldi.cc)
     void pad_dimensions();  // i-vector dim -> multiple of 4, output width -> multiple of 16 (exact: zero columns / rows)
+    // feature / i-vector conf files always; decoding parameters, batch sizes and silence endpointing of model.conf only
+    // when cfg->model_conf is set (the reference's batch path never reads model.conf)
     void apply_conf(Config *cfg) const;
 };
 

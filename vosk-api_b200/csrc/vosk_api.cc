@@ -147,7 +147,7 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model) { return model ? (
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
     if (!model || !out) return 0;
     BatchModel *bm = (BatchModel *)model;
-    double v[38] = {0};
+    double v[43] = {0};
     for (size_t i = 0; i < bm->num_engines(); i++) {
         vb::StepStats s = bm->engine(i).stats();
         v[0] += s.audio_seconds; v[1] += s.steps; v[2] += s.lanes; v[3] += s.launches;
@@ -157,8 +157,9 @@ int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
         v[18] += s.arcs_staged; v[19] += s.links; v[20] += s.lat_arcs;
         for (int k = 0; k < 16; k++) v[21 + k] += s.phase[k];
         v[37] += s.resample_segments;
+        v[38] += s.truncated; v[39] += s.lattice_fallbacks; v[40] += s.post_ms; v[41] += s.post_jobs; v[42] += bm->engine(i).post_thread_count();
     }
-    int k = n < 38 ? n : 38;
+    int k = n < 43 ? n : 43;
     memcpy(out, v, k * sizeof(double));
     return k;
 }
@@ -199,12 +200,15 @@ double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio
         auto parts = std::make_shared<std::vector<std::map<int, std::string>>>(num_streams);  // segment index -> text, per stream
         auto parts_mu = std::make_shared<std::mutex>();
         // result text is produced where the engine delivers results (the lattice pool when lattice=1), inside the timed region
-        eng.resident_hook = [m, lattice_beam, parts, parts_mu, host_chain](int i, const vb::BestPath &bp) {
+        vb::Engine *engp = &eng;
+        eng.resident_hook = [m, lattice_beam, parts, parts_mu, host_chain, engp](int i, const vb::BestPath &bp) {
             std::vector<vb::WordSpan> words;
             bool done = false;
-            if (host_chain && bp.lattice && bp.lattice->error == 0 && bp.lattice->n_states > 0) {
-                words = vb::lattice_to_words(*bp.lattice, *m, lattice_beam);
+            if (host_chain) {
+                const vb::RawLattice *lat = bp.raw_lattice();
+                if (lat && lat->error == 0 && lat->n_states > 0) words = vb::lattice_to_words(*lat, *m, lattice_beam);
                 done = !words.empty() || bp.arcs.empty();
+                if (!done) engp->count_fallback();
             }
             if (!done) words = vb::align_words(*m, bp.arcs);
             std::string t = vb::result_json(*m, words, bp.offset);
@@ -469,5 +473,35 @@ int vosk_b200_lattice_result(const char *model_dir, int n_states, int start, int
         return -1;
     }
 }
+
+
+// ---- the reference's CPU recognizer / speaker / grammar API [REF src/vosk_api.h:58-285]: outside the accelerated path.
+// Exported so that eager binders (JNA Native.register, cgo, P/Invoke) resolve every symbol of the reference header; each
+// call logs once per function and returns the "not available" value, as the reference does for its batch half without CUDA
+// [REF src/vosk_api.cc:198-282]. ----
+static void cpu_api_stub(const char *fn) {
+    vb::log_msg(-1, "%s: CPU API not built (this libvosk.so implements the batch / GPU path only)", fn);
+}
+VoskModel *vosk_model_new(const char *) { cpu_api_stub("vosk_model_new"); return nullptr; }
+void vosk_model_free(VoskModel *) {}
+int vosk_model_find_word(VoskModel *, const char *) { cpu_api_stub("vosk_model_find_word"); return -1; }
+VoskSpkModel *vosk_spk_model_new(const char *) { cpu_api_stub("vosk_spk_model_new"); return nullptr; }
+void vosk_spk_model_free(VoskSpkModel *) {}
+VoskRecognizer *vosk_recognizer_new(VoskModel *, float) { cpu_api_stub("vosk_recognizer_new"); return nullptr; }
+VoskRecognizer *vosk_recognizer_new_spk(VoskModel *, float, VoskSpkModel *) { cpu_api_stub("vosk_recognizer_new_spk"); return nullptr; }
+VoskRecognizer *vosk_recognizer_new_grm(VoskModel *, float, const char *) { cpu_api_stub("vosk_recognizer_new_grm"); return nullptr; }
+void vosk_recognizer_set_spk_model(VoskRecognizer *, VoskSpkModel *) { cpu_api_stub("vosk_recognizer_set_spk_model"); }
+void vosk_recognizer_set_max_alternatives(VoskRecognizer *, int) { cpu_api_stub("vosk_recognizer_set_max_alternatives"); }
+void vosk_recognizer_set_words(VoskRecognizer *, int) { cpu_api_stub("vosk_recognizer_set_words"); }
+void vosk_recognizer_set_partial_words(VoskRecognizer *, int) { cpu_api_stub("vosk_recognizer_set_partial_words"); }
+void vosk_recognizer_set_nlsml(VoskRecognizer *, int) { cpu_api_stub("vosk_recognizer_set_nlsml"); }
+int vosk_recognizer_accept_waveform(VoskRecognizer *, const char *, int) { cpu_api_stub("vosk_recognizer_accept_waveform"); return -1; }
+int vosk_recognizer_accept_waveform_s(VoskRecognizer *, const short *, int) { cpu_api_stub("vosk_recognizer_accept_waveform_s"); return -1; }
+int vosk_recognizer_accept_waveform_f(VoskRecognizer *, const float *, int) { cpu_api_stub("vosk_recognizer_accept_waveform_f"); return -1; }
+const char *vosk_recognizer_result(VoskRecognizer *) { cpu_api_stub("vosk_recognizer_result"); return ""; }
+const char *vosk_recognizer_partial_result(VoskRecognizer *) { cpu_api_stub("vosk_recognizer_partial_result"); return ""; }
+const char *vosk_recognizer_final_result(VoskRecognizer *) { cpu_api_stub("vosk_recognizer_final_result"); return ""; }
+void vosk_recognizer_reset(VoskRecognizer *) {}
+void vosk_recognizer_free(VoskRecognizer *) {}
 
 }  // extern "C"
