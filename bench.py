@@ -4,11 +4,15 @@
 Workload = BASELINE.json configs[1]: small-en-us architecture (random-init TDNN-F, synthetic ~20 MB HCLG),
 512 concurrent 16 kHz streams of U(8,16) s synthetic speech-like audio per GPU.  One "step" = decoding
 the whole 512-stream batch once.
-  value : device-resident run (samples already in HBM; CUDA events) — whole-job audio-s / s
+Result mode = the reference's: lattice -> phone-pruned determinization -> 0.9 LM scale -> word alignment -> MBR
+[REF src/batch_recognizer.cc:43-107,138-149] (engine default lattice=1; the best-path mode is an extra leg).
+  value : device-resident run (samples already in HBM; CUDA events) — whole-job audio-s / s, results (host lattice chain) included
   e2e   : the reference-facing C ABI (vosk_batch_recognizer_accept_waveform in 8000-byte calls, round robin
           as in [REF python/example/test_gpu_batch.py:27-51], vosk_batch_model_wait, front_result/pop) with
           host buffers, host<->device copies inside the timed region
+  large : BASELINE.json configs[2] / [4] leg in the same line (assumed en-us-0.22 architecture, multi-GB HCLG, 1024 streams per GPU)
   --impl reference : the CPU restatement of the reference's recognizer path (oracle/, "port") on the host cores
+  --inproc : one process, one BatchModel spanning --gpus devices, fed by the native multi-threaded feeder
 """
 import argparse
 import json

@@ -76,6 +76,14 @@ int vosk_batch_model_latency(VoskBatchModel *model, double *out5, int reset);
 void vosk_batch_recognizer_debug_capture(VoskBatchRecognizer *recognizer);
 int64_t vosk_batch_recognizer_debug_get(VoskBatchRecognizer *recognizer, const char *what, void *out, int64_t cap_bytes);
 
+/* Native feeder (measurement helper): n streams of int16 16 kHz samples go through vosk_batch_recognizer_new /
+ * accept_waveform (bytes_per_call per call, round robin as the reference's driver [REF python/example/test_gpu_batch.py:27-51]) /
+ * finish_stream from `threads` host threads, then vosk_batch_model_wait and front_result / pop.  results (may be NULL)
+ * receives one malloc'd string per stream (a stream's segment texts concatenated; free with vosk_b200_free).  0 = ok. */
+int vosk_b200_feed_streams(VoskBatchModel *model, const int16_t *const *samples, const int *lengths, int n, int bytes_per_call, int threads,
+                           char **results);
+void vosk_b200_free(void *p);
+
 /* Host-only hooks (no GPU needed; used by the CPU test suite).
  * device_for_stream: the utterance -> GPU sharding rule (stream id modulo the number of engines).
  * format_result: the engine's result-text writer on explicit words (frames are 30 ms decoder frames).
@@ -92,10 +100,11 @@ int vosk_b200_model_check(const char *model_dir, char *out, int cap);
  * "iv.weights", "iv.means_invvars", "iv.inv_vars", "iv.M", "iv.sigma_inv", "iv.cmvn".  Returns the element count (copies
  * min(count, cap)), 0 for an absent optional object, -1 on error (text in vosk_b200_last_error). */
 int64_t vosk_b200_model_tensor(const char *model_dir, const char *name, double *out, int64_t cap);
-/* lattice_result: the host lattice chain (pruned word determinization, graph scale 0.9, word alignment, MBR) on an
- * explicit raw lattice {states, start, links {src, dst, csr arc, acoustic cost}, finals}; stage 0 = result text,
- * 1 = determinized lattice, 2 = word-aligned lattice as text lines ("S start", "A src dst word graph acoustic tids",
- * "F state graph acoustic tids").  Returns the text length (copies at most cap-1 bytes), -1 on error. */
+/* lattice_result: the host lattice chain (phone-pruned determinization, graph scale 0.9, word alignment, MBR) on an
+ * explicit raw lattice {states, start, links {src, dst, csr arc, acoustic cost}, finals}; stage 0 = result text, 3 = NLSML
+ * text, 1 = determinized lattice, 2 = word-aligned lattice as text lines ("S start", "A src dst word graph acoustic tids",
+ * "F state graph acoustic tids"), 11 / 12 = the same with the phone pass switched off, 4 = sizes and best-of-12 timings of
+ * the chain's stages as JSON.  Returns the text length (copies at most cap-1 bytes), -1 on error. */
 int vosk_b200_lattice_result(const char *model_dir, int n_states, int start, int n_links, const int *src, const int *dst, const int *arc,
                              const float *acoustic, int n_final, const int *final_state, const float *final_cost, float lattice_beam,
                              int stage, char *out, int cap);

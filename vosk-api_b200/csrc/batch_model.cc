@@ -41,6 +41,7 @@ static void apply_option(Config *c, const std::string &k, const std::string &v) 
     else if (k == "lat-tok-cap") I(&c->lat_tok_cap);
     else if (k == "lat-link-cap") I(&c->lat_link_cap);
     else if (k == "model-conf") I(&c->model_conf);
+    else if (k == "acoustic-scale") F(&c->acoustic_scale);
     else if (k == "devices") {}  // handled by the caller
     else throw std::runtime_error("unknown batch option '" + k + "'");
 }

@@ -16,6 +16,8 @@
 #include "batch_recognizer.h"
 #include "vb_lattice.h"
 
+#include <thread>
+
 namespace vb {
 int g_log_level = 0;
 void log_msg(int level, const char *fmt, ...) {
@@ -474,6 +476,69 @@ int vosk_b200_lattice_result(const char *model_dir, int n_states, int start, int
     }
 }
 
+
+// Native multi-threaded feeder (measurement helper): drives n streams through the reference ABI calls — one
+// vosk_batch_recognizer_new per stream, accept_waveform in bytes_per_call pieces fed round robin inside each feeder thread as
+// the reference's driver does [REF python/example/test_gpu_batch.py:27-51], finish_stream, then vosk_batch_model_wait and
+// front_result / pop — from `threads` host threads (stream i belongs to thread i % threads).
+int vosk_b200_feed_streams(VoskBatchModel *model, const int16_t *const *samples, const int *lengths, int n, int bytes_per_call, int threads,
+                           char **results) {
+    if (!model || !samples || !lengths || n <= 0 || bytes_per_call < 2) return -1;
+    try {
+        std::vector<VoskBatchRecognizer *> recs(n, nullptr);
+        for (int i = 0; i < n; i++) {
+            recs[i] = vosk_batch_recognizer_new(model, 16000.0f);
+            if (!recs[i]) throw std::runtime_error("recognizer creation failed");
+        }
+        threads = std::max(1, std::min(threads, n));
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++)
+            pool.emplace_back([&, t] {
+                const int per = bytes_per_call / 2;
+                std::vector<long long> pos(n, 0);
+                bool any = true;
+                while (any) {
+                    any = false;
+                    for (int i = t; i < n; i += threads) {
+                        if (pos[i] < 0) continue;
+                        const long long left = (long long)lengths[i] - pos[i];
+                        if (left <= 0) {
+                            vosk_batch_recognizer_finish_stream(recs[i]);
+                            pos[i] = -1;
+                            continue;
+                        }
+                        const int take = (int)std::min<long long>(left, per);
+                        vosk_batch_recognizer_accept_waveform(recs[i], (const char *)(samples[i] + pos[i]), take * 2);
+                        pos[i] += take;
+                        any = true;
+                    }
+                }
+                for (int i = t; i < n; i += threads)
+                    if (pos[i] >= 0) vosk_batch_recognizer_finish_stream(recs[i]);
+            });
+        for (auto &th : pool) th.join();
+        vosk_batch_model_wait(model);
+        for (int i = 0; i < n; i++) {
+            if (results) {
+                std::string all;
+                for (;;) {
+                    const char *r = vosk_batch_recognizer_front_result(recs[i]);
+                    if (!r || !*r) break;
+                    all += r;
+                    vosk_batch_recognizer_pop(recs[i]);
+                }
+                results[i] = (char *)malloc(all.size() + 1);
+                memcpy(results[i], all.c_str(), all.size() + 1);
+            }
+            vosk_batch_recognizer_free(recs[i]);
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        vb::log_msg(-1, "feed_streams: %s", e.what());
+        return -1;
+    }
+}
+void vosk_b200_free(void *p) { free(p); }
 
 // ---- the reference's CPU recognizer / speaker / grammar API [REF src/vosk_api.h:58-285]: outside the accelerated path.
 // Exported so that eager binders (JNA Native.register, cgo, P/Invoke) resolve every symbol of the reference header; each

@@ -94,6 +94,24 @@ class BatchModel(object):
         _c.vosk_batch_model_latency(self._handle, buf, int(reset))
         return dict(p50=buf[0], p90=buf[1], p99=buf[2], mean=buf[3], count=int(buf[4]))
 
+    def FeedStreams(self, waves, bytes_per_call=8000, threads=8, want_results=True):
+        """Native multi-threaded feeder (vosk_b200_feed_streams): waves = list of int16 numpy arrays; returns the result texts."""
+        import numpy as np
+        arrs = [np.ascontiguousarray(w, dtype=np.int16) for w in waves]
+        n = len(arrs)
+        ptrs = _ffi.new("int16_t *[]", [_ffi.cast("int16_t *", a.ctypes.data) for a in arrs])
+        lens = _ffi.new("int[]", [len(a) for a in arrs])
+        res = _ffi.new("char *[]", n) if want_results else _ffi.NULL
+        rc = _c.vosk_b200_feed_streams(self._handle, ptrs, lens, n, int(bytes_per_call), int(threads), res)
+        if rc != 0:
+            raise Exception("feed_streams failed")
+        out = []
+        if want_results:
+            for i in range(n):
+                out.append(_ffi.string(res[i]).decode("utf-8"))
+                _c.vosk_b200_free(res[i])
+        return out
+
     def ResetStats(self):
         _c.vosk_batch_model_reset_stats(self._handle)
 
