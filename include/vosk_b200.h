@@ -39,7 +39,8 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model);
  * [21..28] / [29..36] SM cycles the 1024-thread / smaller search CTAs spent per phase (cutoff, rank, log, gather,
  * insert, closure, finalize, unused), [37] per-call segments resampled on the device, [38] results delivered although a device
  * capacity overflowed (logged; the result may be truncated), [39] lattice-mode results that fell back to the best path,
- * [40] host milliseconds spent by the lattice thread pool, [41] its jobs, [42] its threads.
+ * [40] host milliseconds spent by the lattice thread pool, [41] its jobs, [42] its threads, [43] device ms of the lattice
+ * pruning launches (timing on), [44] batcher-thread ms spent completing steps, [45] of that, fetching lattices.
  * Returns the number written. */
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n);
 void vosk_batch_model_reset_stats(VoskBatchModel *model);

@@ -299,3 +299,27 @@ def test_phone_pass_matters_beyond_the_beam(model_root, oracle_lib, hook):
     assert inside(one) == inside(two)
     for w in inside(two):
         assert abs(one[w] - two[w]) < 2e-3
+
+
+def test_mbr_near_ties_are_broken_as_without_fma(model_root, oracle_lib, hook):
+    """tests/golden/lattice_tiebreak.npz: lattices on which the MBR edit-distance recursion meets near-ties, so that a chain
+    built with FMA contraction prints other confidences than one built without (Kaldi's build has no FMA).  Both the oracle
+    chain and the engine chain must reproduce the stored texts (tests/golden/make_lattice_tiebreak.py)."""
+    import vbmodel
+    mdir = model_root("small")
+    model = vbmodel.load_model_dir(mdir)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "lattice_tiebreak.npz"))
+    for k in range(2):
+        lat = {name: gold["%s_%d" % (name, k)] for name in ("src", "dst", "arc", "ac", "final_state", "final_cost")}
+        n, start = int(gold["n_states_%d" % k]), int(gold["start_%d" % k])
+        want = str(gold["text_%d" % k])
+        assert '"conf" : 0.' in want
+        lat.update(n_states=n, start=start)
+        assert hook(mdir, lat, 6.0, 0) == want
+        # the oracle's entry point finds the start state as the frame-0 token without an incoming arc
+        frame = np.ones(n, dtype=np.int32)
+        frame[start] = 0
+        tok_arc = np.zeros(n, dtype=np.int32)
+        tok_arc[start] = -1
+        dec = {"lattice": dict(lat, tok_index=np.arange(n), frame=frame), "arc": tok_arc}
+        assert oracle_lib.lattice_result(model, dec, 6.0) == want

@@ -842,6 +842,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     sl.gemms = 0;
     sl.resample_segs = n_segs;
     sl.timed = timing_;
+    sl.pruned = false;
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[0], st));
     VB_CUDA_CHECK(cudaMemcpyAsync(sl.d_lanes, sl.h_lanes, (size_t)L * sizeof(LaneDesc), cudaMemcpyHostToDevice, st));
     if (!d_resident)
@@ -972,7 +973,10 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         // lattice pruning only touches finished channels (nothing else does until they are reused after completion)
         sl.dec.lane_begin = 0;
         sl.dec.lane_end = L;
+        if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[6], st));
         VB_CUDA_CHECK(vbk_lattice_prune(&sl.dec, st));
+        if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[7], st));
+        sl.pruned = true;
         sl.launches++;
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_hdr, sl.dec.lat_hdr, (size_t)L * sizeof(LatHeader), cudaMemcpyDeviceToHost, st));
     }
@@ -988,6 +992,7 @@ void Engine::complete_step(Slot &sl) {
     const int L = (int)lanes.size();
     cudaStream_t st = sl.stream;
     VB_CUDA_CHECK(cudaEventSynchronize(sl.done));
+    const auto host_t0 = std::chrono::steady_clock::now();
     for (int i = 0; i < L; i++) lanes[i].s->load = sl.h_load[i];
     {
         const auto now = std::chrono::steady_clock::now();
@@ -1061,16 +1066,18 @@ void Engine::complete_step(Slot &sl) {
         }
     }
     {
-        float ms[4] = {0, 0, 0, 0};
+        float ms[5] = {0, 0, 0, 0, 0};
         if (sl.timed) {
             for (int k = 0; k < 3; k++) cudaEventElapsedTime(&ms[k], sl.ev[k], sl.ev[k + 1]);
             cudaEventElapsedTime(&ms[3], sl.ev[5], sl.ev[4]);
+            if (sl.pruned) cudaEventElapsedTime(&ms[4], sl.ev[6], sl.ev[7]);
         }
         std::lock_guard<std::mutex> lk(stats_mu_);
         stats_.t_feat += ms[0];
         stats_.t_ivec += ms[1];
         stats_.t_nnet += ms[2];
         stats_.t_dec += ms[3];
+        stats_.t_prune += ms[4];
         stats_.t_total += ms[0] + ms[1] + ms[2] + ms[3];
         stats_.audio_seconds += sl.audio;
         stats_.steps++;
@@ -1081,10 +1088,17 @@ void Engine::complete_step(Slot &sl) {
         stats_.dec_launches++;
     }
     std::vector<std::shared_ptr<PackedLattice>> lats;
+    const auto fetch_t0 = std::chrono::steady_clock::now();
     if (cfg_.lattice) fetch_lattices(sl, &lats);
+    const double fetch_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - fetch_t0).count();
     int n_last = 0;
     for (int i = 0; i < L; i++)
         if (lanes[i].seg_end) finish_lane(sl, lanes[i], n_last++, cfg_.lattice ? lats[i] : nullptr);
+    {
+        std::lock_guard<std::mutex> lk(stats_mu_);
+        stats_.host_fetch_ms += fetch_ms;
+        stats_.host_complete_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+    }
 }
 
 std::shared_ptr<RawLattice> PackedLattice::unpack() const {

@@ -122,6 +122,8 @@ struct StepStats {
     double host_launch_ms = 0;  // host time spent enqueueing steps
     long long truncated = 0;          // results delivered although a device capacity (tokens / candidates / log / links / lattice) overflowed
     long long lattice_fallbacks = 0;  // lattice-mode results that fell back to the best path (no lattice, capacity error, chain failure)
+    double t_prune = 0;               // device ms of the lattice pruning launches (only when timing enabled)
+    double host_complete_ms = 0, host_fetch_ms = 0;  // batcher-thread milliseconds spent completing steps / of that, fetching lattices
     double post_ms = 0;               // host milliseconds the lattice pool spent on results (summed over its threads)
     long long post_jobs = 0;
 };
@@ -180,7 +182,8 @@ class Engine {
         cudaStream_t stream = nullptr;  // utility stream (debug taps, lattice fetch) of the slot
         cudaEvent_t fe_done = nullptr, dec_done = nullptr, fork = nullptr, join[2] = {}, tier_done[3] = {};
         int *d_queue = nullptr;  // [2] lane queues of the two search launches
-        cudaEvent_t ev[6] = {};
+        cudaEvent_t ev[8] = {};  // [6], [7]: around the lattice pruning launch
+        bool pruned = false;
         cudaEvent_t done = nullptr;
         int16_t *d_staging = nullptr, *h_staging = nullptr;
         int16_t *d_raw = nullptr, *h_raw = nullptr;          // raw input-rate samples of the step's resampled lanes (allocated on first use)

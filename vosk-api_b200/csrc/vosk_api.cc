@@ -149,7 +149,7 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model) { return model ? (
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
     if (!model || !out) return 0;
     BatchModel *bm = (BatchModel *)model;
-    double v[43] = {0};
+    double v[46] = {0};
     for (size_t i = 0; i < bm->num_engines(); i++) {
         vb::StepStats s = bm->engine(i).stats();
         v[0] += s.audio_seconds; v[1] += s.steps; v[2] += s.lanes; v[3] += s.launches;
@@ -160,8 +160,9 @@ int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
         for (int k = 0; k < 16; k++) v[21 + k] += s.phase[k];
         v[37] += s.resample_segments;
         v[38] += s.truncated; v[39] += s.lattice_fallbacks; v[40] += s.post_ms; v[41] += s.post_jobs; v[42] += bm->engine(i).post_thread_count();
+        v[43] += s.t_prune; v[44] += s.host_complete_ms; v[45] += s.host_fetch_ms;
     }
-    int k = n < 43 ? n : 43;
+    int k = n < 46 ? n : 46;
     memcpy(out, v, k * sizeof(double));
     return k;
 }

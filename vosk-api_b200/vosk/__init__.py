@@ -79,14 +79,14 @@ class BatchModel(object):
         return _c.vosk_batch_model_samples_per_chunk(self._handle)
 
     def Stats(self):
-        buf = _ffi.new("double[43]")
-        n = _c.vosk_batch_model_stats(self._handle, buf, 43)
+        buf = _ffi.new("double[46]")
+        n = _c.vosk_batch_model_stats(self._handle, buf, 46)
         keys = ["audio_seconds", "steps", "lanes", "launches", "tokens", "arcs_emitting", "arcs_epsilon", "tokens_new",
                 "ms_feat", "ms_ivector", "ms_nnet", "ms_search", "gemm_launches",
                 "lane_cycles_sum", "lane_cycles_max", "max_tokens_per_frame", "lane_launches", "host_launch_ms",
                 "arcs_staged", "links", "lattice_arcs"]
         keys += ["cyc_%s_%s" % (v, ph) for v in ("heavy", "light") for ph in ("cutoff", "rank", "log", "gather", "insert", "closure", "finalize", "x")]
-        keys += ["resample_segments", "truncated", "lattice_fallbacks", "post_ms", "post_jobs", "post_threads"]
+        keys += ["resample_segments", "truncated", "lattice_fallbacks", "post_ms", "post_jobs", "post_threads", "ms_prune", "host_complete_ms", "host_fetch_ms"]
         return {k: buf[i] for i, k in enumerate(keys[:n])}
 
     def Latency(self, reset=False):
