@@ -366,18 +366,23 @@ def endpoint_detected(model, dec, rules, silence_phones):
     return False
 
 
-def recognize_segments(model, wave, frames_per_chunk=51, rule5_seconds=20.0, rc=None, silence_phones=None, rules=None, lattice=True, **over):
+def recognize_segments(model, wave, frames_per_chunk=51, rule5_seconds=20.0, rc=None, silence_phones=None, rules=None, lattice=True, loglikes=None,
+                       **over):
     """The batch path with reset_on_endpoint [REF src/batch_model.cc:72]: Kaldi's endpoint rules tested after every chunk; a
     segment is finalized there, the search starts over on the next chunk while features and i-vector carry on, and result
     times are offset by the segment start (GetTimeOffsetSeconds [REF src/batch_recognizer.cc:146-147]).  With an empty
     silence-phone list only rule 5 (decoded length >= 20 s) can fire; with silence_phones (a set of phone ids) rules 1-4 run
     too (`rules` defaults to Kaldi's).  lattice: result text through the lattice chain (default, as the reference) or from the
-    best path.  Returns the list of result texts."""
+    best path.  loglikes: log-likelihoods to search instead of the oracle's own (a parity test passes the engine's, so that
+    the texts can be compared exactly).  Returns the list of result texts."""
     ctx = model_context(model)
-    feats = mfcc(wave)
     ends, avail, iv_index = chunk_plan(len(wave), frames_per_chunk, ctx)
-    ivecs = ivectors(model, feats, ends, avail)
-    ll = nnet_forward(model, feats, ivecs, iv_index)
+    if loglikes is None:
+        feats = mfcc(wave)
+        ivecs = ivectors(model, feats, ends, avail)
+        ll = nnet_forward(model, feats, ivecs, iv_index)
+    else:
+        ll = np.ascontiguousarray(loglikes, dtype=np.float32)
     rc = rc or ResultCtx(model)
     rule5 = int(np.ceil(rule5_seconds / 0.03 - 1e-6)) if rule5_seconds > 0 else 0
     texts, seg_start = [], 0

@@ -254,15 +254,21 @@ def test_rule5_endpoint_segments(model_root, oracle_lib):
     model = vbmodel.load_model_dir(mdir)
     waves = [vbmodel.synth_audio(s, 1900 + i) for i, s in enumerate([25.0, 41.3, 7.0])]
     want_best = [oracle_lib.recognize_segments(model, w, lattice=False) for w in waves]
-    want_lat = [oracle_lib.recognize_segments(model, w) for w in waves]
+    P = int(model["cfg"]["num-pdfs"])
+    lat_texts = None
     # lattice=1 (default) with fast feeding: the chunk after a rule-5 cut is queued at once, and must still wait for the cut
     # segment's traceback and lattice to leave the channel (the stream is held back until that step has completed)
     for opts, bytes_per_call in (("lattice=0", 32000), ("lattice=2", 32000), ("", 32000), ("pipeline-slots=4", 400000)):
-        m = vosk.BatchModel(mdir, options="num-channels=4,max-batch-size=4,max-seconds=24," + opts)
+        lattice_mode = "lattice=" not in opts
+        m = vosk.BatchModel(mdir, options="num-channels=4,max-batch-size=4,max-seconds=24," + opts + (",debug-capture=1" if lattice_mode else ""))
         recs = [vosk.BatchRecognizer(m, 16000.0) for _ in waves]
+        if lattice_mode:
+            for r in recs:
+                r.DebugCapture()
         helpers.feed_round_robin(recs, waves, bytes_per_call)
         m.Wait()
-        for r, w, wb, wl in zip(recs, waves, want_best, want_lat):
+        texts_now = []
+        for r, w, wb in zip(recs, waves, want_best):
             got = []
             while True:
                 t = r.Result()
@@ -270,27 +276,29 @@ def test_rule5_endpoint_segments(model_root, oracle_lib):
                     break
                 got.append(t)
             assert len(wb) == (2 if len(w) < 40 * 16000 and len(w) > 20 * 16000 else 3 if len(w) > 40 * 16000 else 1)
-            if "lattice=0" in opts or "lattice=2" in opts:
+            if not lattice_mode:
                 assert got == wb
             else:
-                assert len(got) == len(wl)
-                for a, b in zip(got, wl):
-                    assert helpers.results_close(a, b, conf_tol=5e-2), (a, b)
+                # the oracle's segmentation and lattice chain on the ENGINE's log-likelihoods: identical texts, confidences included
+                ll = r.DebugGet("loglikes", np.float32).reshape(-1, P)
+                assert got == oracle_lib.recognize_segments(model, w, loglikes=ll)
+                assert any('"conf" : 0.' in t for t in got)
+            texts_now.append(got)
+        if lattice_mode:
+            assert lat_texts is None or lat_texts == texts_now  # the same whatever the pipelining
+            lat_texts = texts_now
         st = m.Stats()
         assert st["truncated"] == 0 and st["lattice_fallbacks"] == 0
         del recs, m
-    # device-resident streams longer than 20 s (bench.py's `value` leg applies rule 5 too), lattice mode
+    # device-resident streams longer than 20 s (bench.py's `value` leg applies rule 5 too), lattice mode: the same texts
     m = vosk.BatchModel(mdir, options="num-channels=4,max-batch-size=4,max-seconds=24")
     lengths = np.array([len(w) for w in waves], dtype=np.int32)
     mat = np.zeros((len(waves), int((lengths.max() + 7) // 8 * 8)), dtype=np.int16)
     for i, w in enumerate(waves):
         mat[i, :len(w)] = w
     _, texts = m.RunResident(mat, lengths)
-    for t, wl in zip(texts, want_lat):
-        parts = t.replace("}{", "}\x00{").split("\x00")  # the resident run returns the stream's segment texts concatenated
-        assert len(parts) == len(wl)
-        for a, b in zip(parts, wl):
-            assert helpers.results_close(a, b, conf_tol=5e-2), (a, b)
+    for t, wl in zip(texts, lat_texts):
+        assert t == "".join(wl)  # the resident run returns the stream's segment texts concatenated
     del m
 
 

@@ -900,34 +900,57 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
 //   a link survives iff link_extra <= lattice_beam; extra(tok) = min over its surviving links (inf: token dropped)
 // Frames are visited last to first; within a frame the epsilon links are iterated to their fixed point (monotone
 // atomicMin on the ordered-float bits of non-negative costs) before the emitting links push into the previous frame.
+//
+// B200 mapping: one CTA per finished lane sweeps the frames last to first — a chain of ~400 dependent steps, so what counts
+// is the latency of one step.  The extra costs of the two frames in play live in shared memory (global only for a frame
+// wider than the buffer); each thread holds its share of the NEXT frame's links in registers, requested one frame ahead, so
+// that the link log streams in behind the work on the current frame; only the links whose destination is alive (1-2 % of
+// the log) go on to touch costs and graph weights.  Survivors are written out during the sweep (frames descending; the block
+// turns the list around at the end), the epsilon fixed point costs one barrier per round (__syncthreads_or), and the token
+// renumbering is a warp-per-frame pass over per-frame counts instead of a barrier per 256 tokens.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kPruneThreads = 256;
+constexpr int kPruneThreads = 512;
+constexpr int kPruneRegLinks = 4;     // links of a frame held in registers per thread (the rest of a wider frame is read in place)
+constexpr int kPruneSmemToks = 8192;  // tokens of a frame whose extra costs fit the shared-memory buffer
 
-__device__ __forceinline__ float link_extra(const DecArgs &a, const int4 l, const float *cost, const unsigned *extra) {
-    const int dst = l.y & ~kEpsLinkFlag;
-    const float ed = __uint_as_float(__ldcg(extra + dst));
-    if (ed == INFINITY) return INFINITY;
-    const float w = __int_as_float(__ldg(a.g.arcs + l.z).x);
-    float le = ed + (((cost[l.x] + __int_as_float(l.w)) + w) - cost[dst]);
+struct PruneFrame {
+    const DecArgs *a;
+    const float *cost;
+    unsigned *ex_cur, *ex_prev;  // extra costs (float bits; monotone under atomicMin as they are non-negative) of frame f / f-1
+    int t0, p0;                  // first log index of frame f / f-1
+    float lb, off;
+};
+
+// one link of frame f against the current extras.  Returns 0: dead, 1: alive (le <= lattice_beam) and stores le.
+__device__ __forceinline__ int prune_link(const PruneFrame &fr, const int4 lk, float *le_out) {
+    const int dst = lk.y & ~kEpsLinkFlag;
+    const float ed = __uint_as_float(*(volatile unsigned *)(fr.ex_cur + (dst - fr.t0)));
+    if (ed == INFINITY) return 0;
+    const float w = __int_as_float(__ldg(fr.a->g.arcs + lk.z).x);
+    float le = ed + (((fr.cost[lk.x] + __int_as_float(lk.w)) + w) - fr.cost[dst]);
     if (le < 0.f) le = 0.f;
-    return le;
+    *le_out = le;
+    return le <= fr.lb;
 }
 
-__global__ void __launch_bounds__(kPruneThreads) lattice_prune_kernel(DecArgs a) {
+__global__ void __launch_bounds__(kPruneThreads, 2) lattice_prune_kernel(DecArgs a) {
     const int l = blockIdx.x;
     const LaneDesc ln = a.lanes[l];
     if (!ln.dec_last) return;
-    constexpr int NT = kPruneThreads;
-    __shared__ int s_changed, s_count, s_warp[NT / 32], s_nlinks, s_nfinal, s_start;
+    constexpr int NT = kPruneThreads, NW = NT / 32, K = kPruneRegLinks;
+    extern __shared__ __align__(16) unsigned s_dyn[];  // [2][kPruneSmemToks] extras | [max_frames + 3] per-frame counts
+    auto s_ex = [&](int b) { return s_dyn + (b ? kPruneSmemToks : 0); };
+    int *s_cnt = reinterpret_cast<int *>(s_dyn + 2 * kPruneSmemToks);
+    __shared__ int s_nlinks, s_nfinal, s_start;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ch = ln.channel;
     const DecChannelState cs = a.cs[ch];
     const float *cost = a.log_cost + (size_t)ch * a.log_cap;
     const int *log_arc = a.log_arc + (size_t)ch * a.log_cap;
     unsigned *extra = a.lat_extra ? a.lat_extra + (size_t)ch * a.log_cap : reinterpret_cast<unsigned *>(a.log_prev + (size_t)ch * a.log_cap);
-    int *remap = reinterpret_cast<int *>(extra);  // the new state numbers overwrite the extra costs once the links are filtered
+    int *remap = reinterpret_cast<int *>(extra);  // the new state numbers overwrite the extra costs, frame by frame
     const int *frame_off = a.log_frame_off + (size_t)ch * (a.max_frames + 2);
-    int4 *links = a.links + (size_t)ch * a.link_cap;
+    const int4 *links = a.links + (size_t)ch * a.link_cap;
     const int *link_off = a.link_off + (size_t)ch * (a.max_frames + 3);
     const int F = min(cs.frame, a.max_frames);
     const int n_tok = cs.log_count;
@@ -943,91 +966,137 @@ __global__ void __launch_bounds__(kPruneThreads) lattice_prune_kernel(DecArgs a)
         if (tid == 0) *hdr = LatHeader{0, 0, 0, -1, error ? error : 11, F, 0, 0};
         return;
     }
-    for (int i = tid; i < n_tok; i += NT) extra[i] = kInfBits;
     if (tid == 0) {
         s_nlinks = 0;
         s_nfinal = 0;
         s_start = -1;
     }
-    __syncthreads();
     // last frame: all its tokens were logged in list order, so the token list still gives their states
     const int lo_last = frame_off[F], hi_last = frame_off[F + 1];
     const int *t_state = a.tok_state + (size_t)ch * 2 * a.tok_cap + (size_t)cs.parity * a.tok_cap;
+    PruneFrame fr;
+    fr.a = &a;
+    fr.cost = cost;
+    fr.lb = lb;
+    int buf = 0;
+    fr.ex_cur = hi_last - lo_last <= kPruneSmemToks ? s_ex(0) : extra + lo_last;
     for (int i = lo_last + tid; i < hi_last; i += NT) {
         const float fc = cs.reached_final ? __ldg(a.g.final_cost + t_state[i - lo_last]) : 0.f;
         const float e = (cost[i] + fc) - cs.best_cost;
-        extra[i] = e <= lb ? __float_as_uint(fmaxf(e, 0.f)) : kInfBits;
+        fr.ex_cur[i - lo_last] = e <= lb ? __float_as_uint(fmaxf(e, 0.f)) : kInfBits;
+    }
+    const float *frame_offset = a.frame_offset + (size_t)ch * (a.max_frames + 2);
+    // this thread's share of frame F's links
+    int4 cur[K];
+    {
+        const int k0 = link_off[F], k1 = min(link_off[F + 1], a.link_cap);
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int k = k0 + j * NT + tid;
+            cur[j] = k < k1 ? links[k] : make_int4(0, -1, 0, 0);
+        }
     }
     __syncthreads();
     for (int f = F; f >= 0; f--) {
-        const int k0 = link_off[f], k1 = link_off[f + 1];
+        const int k0 = link_off[f], k1 = min(link_off[f + 1], a.link_cap);
+        fr.t0 = frame_off[f];
+        const int n_f = frame_off[f + 1] - fr.t0;
+        fr.p0 = f > 0 ? frame_off[f - 1] : 0;
+        const int n_p = f > 0 ? fr.t0 - fr.p0 : 0;
+        fr.ex_prev = n_p <= kPruneSmemToks ? s_ex(buf ^ 1) : extra + fr.p0;
+        fr.off = f > 0 ? frame_offset[f - 1] : 0.f;
+        // request the next frame's links (in flight while this frame is worked on)
+        int4 nxt[K];
+        {
+            const int q0 = f > 0 ? link_off[f - 1] : 0, q1 = f > 0 ? k0 : 0;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const int k = q0 + j * NT + tid;
+                nxt[j] = k < q1 ? links[k] : make_int4(0, -1, 0, 0);
+            }
+        }
+        for (int i = tid; i < n_p; i += NT) fr.ex_prev[i] = kInfBits;  // (ordered before the emitting pushes by the barriers of the epsilon rounds)
         // epsilon links inside frame f: iterate to the fixed point
         for (;;) {
-            if (tid == 0) s_changed = 0;
-            __syncthreads();
-            bool ch_any = false;
-            for (int k = k0 + tid; k < k1; k += NT) {
-                const int4 lk = links[k];
-                if (lk.y < 0 || !(lk.y & kEpsLinkFlag)) continue;
-                const float le = link_extra(a, lk, cost, extra);
-                if (le <= lb) {
+            int changed = 0;
+            auto relax_eps = [&](const int4 lk) {
+                if (lk.y < 0 || !(lk.y & kEpsLinkFlag)) return;
+                float le;
+                if (prune_link(fr, lk, &le)) {
                     const unsigned b = __float_as_uint(le);
-                    if (b < atomicMin(extra + lk.x, b)) ch_any = true;
+                    if (b < atomicMin(fr.ex_cur + (lk.x - fr.t0), b)) changed = 1;
                 }
-            }
-            if (ch_any) s_changed = 1;
-            __syncthreads();
-            const int again = s_changed;
-            __syncthreads();
-            if (!again) break;
+            };
+#pragma unroll
+            for (int j = 0; j < K; j++) relax_eps(cur[j]);
+            for (int k = k0 + K * NT + tid; k < k1; k += NT) relax_eps(links[k]);
+            if (!__syncthreads_or(changed)) break;
         }
-        // emitting links into frame f: push to their sources in frame f-1
-        for (int k = k0 + tid; k < k1; k += NT) {
-            const int4 lk = links[k];
-            if (lk.y < 0 || (lk.y & kEpsLinkFlag)) continue;
-            const float le = link_extra(a, lk, cost, extra);
-            if (le <= lb) atomicMin(extra + lk.x, __float_as_uint(le));
-        }
+        // every link into frame f is now decided: survivors go out (old token indices for now; GetRawLattice takes the frame's
+        // cost offset back out of the acoustic cost of an emitting arc), emitting survivors push into frame f-1
+        auto settle = [&](const int4 lk) {
+            if (lk.y < 0) return;
+            float le;
+            if (!prune_link(fr, lk, &le)) return;
+            const bool eps = (lk.y & kEpsLinkFlag) != 0;
+            if (!eps) atomicMin(fr.ex_prev + (lk.x - fr.p0), __float_as_uint(le));
+            const int o = agg_inc(&s_nlinks);
+            const float ac = eps ? 0.f : __int_as_float(lk.w) - fr.off;
+            if (o < a.lat_link_cap) out_links[o] = make_int4(lk.x, lk.y & ~kEpsLinkFlag, lk.z, __float_as_int(ac));
+        };
+#pragma unroll
+        for (int j = 0; j < K; j++) settle(cur[j]);
+        for (int k = k0 + K * NT + tid; k < k1; k += NT) settle(links[k]);
         __syncthreads();
+        // frame f is final: its extras go to the global array the renumbering reads (same thread -> same index as the
+        // initialisation of this buffer two frames on, so no barrier is needed in between)
+        if (fr.ex_cur == s_ex(buf))
+            for (int i = tid; i < n_f; i += NT) extra[fr.t0 + i] = fr.ex_cur[i];
+        fr.ex_cur = fr.ex_prev;
+        buf ^= 1;
+#pragma unroll
+        for (int j = 0; j < K; j++) cur[j] = nxt[j];
     }
-    // surviving links -> output (old token indices for now).  GetRawLattice takes the frame's cost offset back out of
-    // the acoustic cost of an emitting arc (segment f holds the arcs from frame f-1 into frame f).
-    const float *frame_offset = a.frame_offset + (size_t)ch * (a.max_frames + 2);
-    for (int f = 0; f <= F; f++) {
-        const int k1 = min(link_off[f + 1], a.link_cap);
-        const float off = f > 0 ? frame_offset[f - 1] : 0.f;
-        for (int k = link_off[f] + tid; k < k1; k += NT) {
-            const int4 lk = links[k];
-            if (lk.y < 0) continue;
-            const float le = link_extra(a, lk, cost, extra);
-            if (le <= lb) {
-                const int o = agg_inc(&s_nlinks);
-                const float ac = (lk.y & kEpsLinkFlag) ? 0.f : __int_as_float(lk.w) - off;
-                if (o < a.lat_link_cap) out_links[o] = make_int4(lk.x, lk.y & ~kEpsLinkFlag, lk.z, __float_as_int(ac));
+    __syncthreads();
+    // surviving tokens, renumbered in log order (frame by frame): per-frame counts (a warp per frame), their prefix, then the
+    // new numbers.  remap[] shares storage with the extra costs: a warp reads a frame's flags before it overwrites them.
+    for (int f = warp; f <= F; f += NW) {
+        const int lo = frame_off[f], hi = frame_off[f + 1];
+        int c = 0;
+        for (int i0 = lo; i0 < hi; i0 += 32) {
+            const int i = i0 + lane;
+            c += __popc(__ballot_sync(0xffffffffu, i < hi && __ldcg(extra + i) != kInfBits));
+        }
+        if (lane == 0) s_cnt[f] = c;
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive prefix of the per-frame counts; s_cnt[F + 1] = total
+        int carry = 0;
+        for (int f0 = 0; f0 <= F + 1; f0 += 32) {
+            const int f = f0 + lane;
+            const int v = f <= F ? s_cnt[f] : 0;
+            int incl = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
             }
+            if (f <= F + 1) s_cnt[f] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
     __syncthreads();
-    // surviving tokens, renumbered in log order (frame by frame); remap[] replaces the extra costs when they share storage,
-    // so the keep flags are taken before the barrier and written after it
-    int base = 0;
-    for (int f = 0; f <= F; f++) {
+    const int n_keep = s_cnt[F + 1];
+    for (int f = warp; f <= F; f += NW) {
         const int lo = frame_off[f], hi = frame_off[f + 1];
-        for (int i0 = lo; i0 < hi; i0 += NT) {
-            const int i = i0 + tid;
+        int base = s_cnt[f];
+        for (int i0 = lo; i0 < hi; i0 += 32) {
+            const int i = i0 + lane;
             const bool keep = i < hi && __ldcg(extra + i) != kInfBits;
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) s_warp[warp] = __popc(bal);
-            __syncthreads();
-            int off = 0, tot = 0;
-            for (int w = 0; w < NT / 32; w++) {
-                if (w < warp) off += s_warp[w];
-                tot += s_warp[w];
-            }
             if (i < hi) {
                 int ni = -1;
                 if (keep) {
-                    ni = base + off + __popc(bal & lanemask_lt());
+                    ni = base + __popc(bal & lanemask_lt());
                     if (ni < a.lat_tok_cap) {
                         out_frame[ni] = f;
                         if (out_state) out_state[ni] = log_state ? log_state[i] : -1;
@@ -1043,22 +1112,27 @@ __global__ void __launch_bounds__(kPruneThreads) lattice_prune_kernel(DecArgs a)
                 }
                 remap[i] = ni;
             }
-            base += tot;
-            __syncthreads();
+            base += __popc(bal);
         }
     }
-    if (base > a.lat_tok_cap) error = error ? error : 8;
+    __syncthreads();
+    if (n_keep > a.lat_tok_cap) error = error ? error : 8;
     if (s_nlinks > a.lat_link_cap) error = error ? error : 9;
     if (s_nfinal > a.lat_final_cap) error = error ? error : 10;
+    // new state numbers into the links; the list is turned around so that the frames ascend again
     const int n_out = min(s_nlinks, a.lat_link_cap);
-    for (int k = tid; k < n_out; k += NT) {
-        int4 lk = out_links[k];
-        lk.x = remap[lk.x];
-        lk.y = remap[lk.y];
-        out_links[k] = lk;
+    for (int k = tid; k < (n_out + 1) / 2; k += NT) {
+        const int k2 = n_out - 1 - k;
+        int4 x = out_links[k], y = out_links[k2];
+        x.x = remap[x.x];
+        x.y = remap[x.y];
+        y.x = remap[y.x];
+        y.y = remap[y.y];
+        out_links[k] = y;
+        if (k2 != k) out_links[k2] = x;
     }
     if (tid == 0) {
-        hdr->n_tok = min(base, a.lat_tok_cap);
+        hdr->n_tok = min(n_keep, a.lat_tok_cap);
         hdr->n_links = n_out;
         hdr->n_final = min(s_nfinal, a.lat_final_cap);
         hdr->start = s_start;
@@ -1070,7 +1144,17 @@ __global__ void __launch_bounds__(kPruneThreads) lattice_prune_kernel(DecArgs a)
 
 extern "C" cudaError_t vbk_lattice_prune(const DecArgs *a, cudaStream_t s) {
     if (!a->lattice || a->num_lanes <= 0) return cudaSuccess;
-    lattice_prune_kernel<<<a->num_lanes, kPruneThreads, 0, s>>>(*a);
+    const int smem = (2 * kPruneSmemToks + a->max_frames + 3) * 4;
+    static int done[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 16) return cudaErrorInvalidDevice;
+    if (done[dev] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(lattice_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        done[dev] = smem;
+    }
+    lattice_prune_kernel<<<a->num_lanes, kPruneThreads, smem, s>>>(*a);
     return cudaGetLastError();
 }
 
