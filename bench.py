@@ -2,8 +2,9 @@
 """bench.py — aggregate real-time factor (audio-seconds decoded per second) of the batch recognition path.
 
 Workload = BASELINE.json configs[1]: small-en-us architecture (random-init TDNN-F, synthetic ~20 MB HCLG),
-512 concurrent 16 kHz streams of U(8,16) s synthetic speech-like audio per GPU.  One "step" = decoding
-the whole 512-stream batch once.
+512 concurrent 16 kHz streams of U(8,16) s synthetic speech-like audio per GPU.  One "step" = decoding the whole
+512-stream batch once.  Steps run back to back as in continuous serving: the streams of step k+1 are queued while the
+lattice chain of step k's results is still running; every result of every step is delivered inside the timed region.
 Result mode = the reference's: lattice -> phone-pruned determinization -> 0.9 LM scale -> word alignment -> MBR
 [REF src/batch_recognizer.cc:43-107,138-149] (engine default lattice=1; the best-path mode is an extra leg).
   value : device-resident run (samples already in HBM; CUDA events) — whole-job audio-s / s, results (host lattice chain) included
@@ -11,6 +12,7 @@ Result mode = the reference's: lattice -> phone-pruned determinization -> 0.9 LM
           as in [REF python/example/test_gpu_batch.py:27-51], vosk_batch_model_wait, front_result/pop) with
           host buffers, host<->device copies inside the timed region
   large : BASELINE.json configs[2] / [4] leg in the same line (assumed en-us-0.22 architecture, multi-GB HCLG, 1024 streams per GPU)
+  parity_sample : 12 of the bench's own streams checked against the CPU oracle (texts identical on the engine's log-likelihoods)
   --impl reference : the CPU restatement of the reference's recognizer path (oracle/, "port") on the host cores
   --inproc : one process, one BatchModel spanning --gpus devices, fed by the native multi-threaded feeder
 """
@@ -99,24 +101,28 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def e2e_pass(vosk, model, pieces, wait_each_round=False):
-    """The reference's batch driver loop [REF python/example/test_gpu_batch.py:27-51]: 8000-byte reads fed round
-    robin to one recognizer per stream, FinishStream at EOF, Wait, then drain the results."""
-    recs = [vosk.BatchRecognizer(model, 16000.0) for _ in pieces]
-    texts = [""] * len(pieces)
+
+
+def e2e_run(vosk, model, pieces, steps):
+    """The reference's batch driver loop [REF python/example/test_gpu_batch.py:27-51]: 8000-byte reads fed round robin to one
+    recognizer per stream, FinishStream at EOF — `steps` times over with new recognizers, back to back (the accept calls never
+    block), then Wait and the results of every recognizer of every step.  Returns the texts of the last step and the number
+    of streams of earlier steps whose text differs from it."""
     rounds = max(len(p) for p in pieces)
-    for r in range(rounds + 1):
-        for i, rec in enumerate(recs):
-            if r < len(pieces[i]):
-                rec.AcceptWaveform(pieces[i][r])
-            elif r == len(pieces[i]):
-                rec.FinishStream()
-        if wait_each_round:
-            model.Wait()
+    all_recs = []
+    for _ in range(steps):
+        recs = [vosk.BatchRecognizer(model, 16000.0) for _ in pieces]
+        for r in range(rounds + 1):
+            for i, rec in enumerate(recs):
+                if r < len(pieces[i]):
+                    rec.AcceptWaveform(pieces[i][r])
+                elif r == len(pieces[i]):
+                    rec.FinishStream()
+        all_recs.append(recs)
     model.Wait()
-    for i, rec in enumerate(recs):
-        texts[i] = rec.Result()
-    return texts
+    texts = [[rec.Result() for rec in recs] for recs in all_recs]
+    bad = sum(1 for t in texts[:-1] for x, y in zip(t, texts[-1]) if x != y)
+    return texts[-1], bad
 
 
 def latency_pass(vosk, mdir, n_streams, seconds, packet_ms=100, fpc=10):
@@ -180,11 +186,12 @@ def job_throughput(audio_seconds_local, seconds_local, device="cpu"):
 
 
 def run_oracle_sample(n_streams, threads):
-    """CPU restatement of the reference recognizer path on a bounded sample; returns (audio_s, wall_s)."""
+    """CPU restatement of the reference recognizer path (lattice -> MBR result, as the reference) on a bounded sample of the
+    bench workload's own streams (rank 0's first n); returns (audio_s, wall_s)."""
     import oracle
     import vbmodel
     model = vbmodel.load_model_dir(model_dir())
-    waves = make_audio(n_streams, 999)
+    waves = make_audio(n_streams, 0)
     rc = oracle.ResultCtx(model)
     oracle.recognize(model, waves[0][:16000], rc=rc)  # warm (table construction, page-in)
     audio = sum(len(w) for w in waves) / 16000.0
@@ -199,56 +206,214 @@ def run_oracle_sample(n_streams, threads):
     return audio, time.perf_counter() - t0
 
 
-def large_lattice(a):
-    """BASELINE.json configs[2] as a single-GPU, device-resident measurement (not the headline line): large architecture
-    (assumed), vocabulary 200 k / 64 successors -> ~1.4e8 arcs (~2.2 GB of arc records in HBM), lattice
-    generation on the device (link log + lattice-beam pruning + compaction, raw lattices copied to the host)."""
-    import vosk
-    streams = a.streams if a.streams != STREAMS else 1024
-    t0 = time.perf_counter()
-    mdir = model_dir("large")
-    t_gen = time.perf_counter() - t0
-    vosk.SetLogLevel(0)
-    opts = ("lattice=2,num-channels=%d,max-batch-size=%d,max-seconds=18,log-links-per-frame=4096,lat-link-cap=131072,lat-tok-cap=65536"
-            % (streams, min(streams, 1024)))
-    if a.options:
-        opts += "," + a.options
-    t0 = time.perf_counter()
-    model = vosk.BatchModel(mdir, options=opts)
-    t_load = time.perf_counter() - t0
-    waves = make_audio(streams, 0)
-    lengths = np.array([len(w) for w in waves], dtype=np.int32)
-    stride = int((lengths.max() + 7) // 8 * 8)
-    mat = np.zeros((streams, stride), dtype=np.int16)
-    for i, w in enumerate(waves):
-        mat[i, :len(w)] = w
-    audio_s = float(lengths.sum()) / 16000.0
-    for _ in range(max(1, a.warmup)):
-        model.RunResident(mat, lengths)
-    model.ResetStats()
-    ms_total = 0.0
-    for _ in range(a.steps):
-        ms, texts = model.RunResident(mat, lengths)
-        ms_total += ms
-    st = model.Stats()
-    model.ResetStats()
-    model.SetTiming(True)
-    model.SetSlots(1)
-    model.RunResident(mat, lengths)
-    ser = model.Stats()
+def parity_sample(vosk, arch, waves, bench_texts, n, extra_opts=""):
+    """n of the bench's own streams against the CPU oracle, and the oracle's single-core speed on them.  The streams run
+    once more through a small engine instance with the test taps on: (1) its text equals the bench run's (a result does not
+    depend on the batch), (2) the ORACLE's search + lattice chain on the engine's log-likelihoods gives the identical text,
+    confidences included, (3) the engine's log-likelihoods are within 1e-3 of the oracle's own."""
+    import oracle
+    import vbmodel
+    mdir = model_dir(arch)
+    model_np = vbmodel.load_model_dir(mdir)
+    rc = oracle.ResultCtx(model_np)
+    oracle.recognize(model_np, waves[0][:16000], rc=rc)
+    m = vosk.BatchModel(mdir, options="num-channels=%d,max-batch-size=%d,max-seconds=18,debug-capture=1%s" % (n, n, "," + extra_opts if extra_opts else ""))
+    recs = [vosk.BatchRecognizer(m, 16000.0) for _ in range(n)]
+    for r, w in zip(recs, waves[:n]):
+        r.DebugCapture()
+        r.AcceptWaveform(w.tobytes())
+        r.FinishStream()
+    m.Wait()
+    P = int(model_np["cfg"]["num-pdfs"])
+    lb = float(model_np["conf"].get("lattice-beam", 6.0))
+    same_bench = same_oracle = same_pipeline = 0
+    max_dll = 0.0
+    cpu_s = 0.0
+    for i, (r, w) in enumerate(zip(recs, waves[:n])):
+        text = r.Result()
+        ll = r.DebugGet("loglikes", np.float32).reshape(-1, P)
+        t0 = time.perf_counter()
+        ref = oracle.recognize(model_np, w, stages=True, rc=rc)   # the whole CPU path, timed: the cpu_baseline sample
+        cpu_s += time.perf_counter() - t0
+        max_dll = max(max_dll, float(np.abs(ll - ref["loglikes"]).max()))
+        dec = oracle.decode(model_np, ll, lattice_beam=lb)
+        want = oracle.lattice_result(model_np, dec, lb, rc=rc)
+        same_oracle += text == want
+        same_bench += bench_texts is None or text == bench_texts[i]
+        same_pipeline += text == ref["text"]
+    del recs, m
+    audio = sum(len(w) for w in waves[:n]) / 16000.0
+    return {"streams": n, "texts_identical_to_oracle_search_and_lattice_chain_on_engine_loglikes": "%d/%d" % (same_oracle, n),
+            "texts_identical_to_bench_run": "%d/%d" % (same_bench, n), "max_abs_loglike_diff_vs_oracle": max_dll, "loglike_tolerance": 1e-3,
+            "texts_identical_to_whole_oracle_pipeline (its own log-likelihoods; informational)": "%d/%d" % (same_pipeline, n)}, audio, cpu_s
+
+
+def peaks_measured():
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks = {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops": pk["bf16_tflops_sustained"], "src": "measured (MEASURED_PEAKS.json; sustained bf16)"}
+    except Exception:
+        pass
+    return peaks
+
+
+def stage_rooflines(ser, lengths, arch, peaks):
+    """Algorithmic bytes / flops of one serialized pass over the batch divided by each stage's device time."""
+    frames = sum(int(1 + (n - 400) // 160) for n in lengths if n >= 400)
+    out_frames = sum((int(1 + (n - 400) // 160) + 2) // 3 for n in lengths if n >= 400)
+    mflop = 7.95e6 if arch == "small" else 47e6
+    D = 40 if arch == "small" else 100
     T, Ae, Aeps, N = ser["tokens"], ser["arcs_emitting"], ser["arcs_epsilon"], ser["tokens_new"]
     search_bytes = T * 16 + (Ae + Aeps) * 20 + Ae * 4 + N * 16
-    out_frames = sum((int(1 + (n - 400) // 160) + 2) // 3 for n in lengths)
-    print(json.dumps({"metric": METRIC, "value": audio_s * a.steps / (ms_total / 1000.0), "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
-                      "ms_per_step": ms_total / a.steps, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "large-lattice (BASELINE.json configs[2]): assumed en-us-0.22 architecture, synthetic HCLG vocab 200k x 64 successors, "
-                                             "%d streams of U(8,16) s, lattice generation on the device (lattice=2)" % streams, "options": opts},
-                      "kernel_ms_per_step": {"mfcc": ser["ms_feat"], "ivector": ser["ms_ivector"], "tdnnf": ser["ms_nnet"], "search": ser["ms_search"]},
-                      "tdnnf_tflops_algorithmic": 47e6 * out_frames / (ser["ms_nnet"] / 1000.0) / 1e12,
-                      "search_gbs_algorithmic": search_bytes / (ser["ms_search"] / 1000.0) / 1e9,
-                      "links_logged_per_step": st["links"] / a.steps, "lattice_arcs_per_step": st["lattice_arcs"] / a.steps,
-                      "nonempty_results": sum(1 for t in texts if '"text" : ""' not in t), "audio_seconds_per_step": audio_s,
-                      "model_generation_s": t_gen, "model_load_s": t_load}))
+    chunks = ser["lanes"]
+    iv_bytes = chunks * 2 * (D + D * (D + 1) // 2) * 4 + frames * 40 * 4
+    prune_bytes = ser["links"] * 16 + ser["tokens"] * 8 + ser["lattice_arcs"] * 16   # link log read once, token costs + extras, survivors written
+    ms = {"mfcc": ser["ms_feat"], "ivector": ser["ms_ivector"], "tdnnf": ser["ms_nnet"], "search": ser["ms_search"], "lattice_prune": ser["ms_prune"]}
+    alg = {"mfcc": (480.0 * frames, "hbm", "480 B per frame"),
+           "ivector": (iv_bytes, "hbm", "2 x (D + D(D+1)/2) x 4 B of statistics per chunk + 160 B per frame"),
+           "tdnnf": (mflop * out_frames, "tensor", "%.2f MFLOP per output frame (the fp16 hi/lo operand split issues 3x that on the tensor pipe)" % (mflop / 1e6)),
+           "search": (search_bytes, "hbm", "T*16 + (Ae+Aeps)*20 + Ae*4 + N*16 bytes from the in-kernel counters"),
+           "lattice_prune": (prune_bytes, "hbm", "16 B per logged link + 8 B per logged token + 16 B per surviving link")}
+    out = {}
+    for k, (work, bound, note) in alg.items():
+        if not ms[k]:
+            continue
+        if bound == "hbm":
+            ach, peak, unit = work / (ms[k] / 1e3) / 1e9, peaks["hbm_gbs"], "GB/s"
+        else:
+            ach, peak, unit = work / (ms[k] / 1e3) / 1e12, peaks["bf16_tflops"], "TFLOP/s"
+        out[k] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "ms": ms[k], "algorithmic": note}
+    return out, search_bytes
+
+
+def resident_leg(vosk, mdir, opts, audio_mat, lengths, warmup, steps):
+    """One model, W warm-up + K timed back-to-back passes over the resident batch; returns a summary dict."""
+    m = vosk.BatchModel(mdir, options=opts)
+    m.RunResident(audio_mat, lengths, passes=max(1, warmup))
+    m.ResetStats()
+    ms, texts = m.RunResident(audio_mat, lengths, passes=steps)
+    st = m.Stats()
+    audio_s = float(lengths.sum()) / 16000.0
+    out = {"value": audio_s * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "options": opts,
+           "results_with_confidence_below_1": sum(1 for t in texts if '"conf" : 0.' in t), "nonempty_results": sum(1 for t in texts if '"text" : ""' not in t),
+           "texts_differing_between_steps": m.resident_mismatches, "lattice_links_logged_per_step": st["links"] / steps,
+           "lattice_arcs_after_pruning_per_step": st["lattice_arcs"] / steps, "host_lattice_chain_cpu_ms_per_step": st["post_ms"] / steps,
+           "host_lattice_threads": st["post_threads"], "truncated": st["truncated"], "lattice_fallbacks": st["lattice_fallbacks"]}
+    del m
+    return out, texts
+
+
+def large_leg(a, rank, world, dist, barrier, peaks):
+    """BASELINE.json configs[2] (1 GPU) / configs[4] (8 GPUs, 8192 streams sharded by utterance): assumed en-us-0.22 architecture
+    (SURVEY.md section 8), synthetic HCLG of vocabulary 200 k x 64 successors (~1.4e8 arcs, ~2.2 GB of arc records in HBM), 1024
+    streams per GPU, the reference's lattice -> MBR result path.  Every rank runs it; rank 0 reports."""
+    import vosk
+    streams = a.large_streams
+    local = {"ok": 0.0, "audio": 0.0, "ms": 1.0}
+    info = {}
+    t0 = time.perf_counter()
+    if rank == 0:
+        try:
+            model_dir("large")   # generated once per box; the other ranks wait here
+        except Exception as e:
+            info = {"error": "model generation: " + str(e)[:200]}
+    t_gen = time.perf_counter() - t0
+    barrier()
+    try:
+        if "error" in info:
+            raise RuntimeError(info["error"])
+        mdir = model_dir("large")
+        opts = "num-channels=%d,max-batch-size=%d,max-seconds=18,log-links-per-frame=4096,lat-link-cap=131072,lat-tok-cap=65536" % (streams, min(streams, 1024))
+        if a.options:
+            opts += "," + a.options
+        t0 = time.perf_counter()
+        model = vosk.BatchModel(mdir, options=opts)
+        t_load = time.perf_counter() - t0
+        waves = make_audio(streams, rank)
+        lengths = np.array([len(w) for w in waves], dtype=np.int32)
+        stride = int((lengths.max() + 7) // 8 * 8)
+        mat = np.zeros((streams, stride), dtype=np.int16)
+        for i, w in enumerate(waves):
+            mat[i, :len(w)] = w
+        audio_s = float(lengths.sum()) / 16000.0
+        model.RunResident(mat, lengths, passes=1)
+        model.ResetStats()
+        ms, texts = model.RunResident(mat, lengths, passes=a.large_steps)   # ranks are independent: job time = max over ranks
+        st = model.Stats()
+        model.ResetStats()
+        model.SetTiming(True)
+        model.SetSlots(1)
+        model.RunResident(mat, lengths)
+        ser = model.Stats()
+        roofs, _ = stage_rooflines(ser, lengths, "large", peaks)
+        dom = max(("mfcc", "ivector", "tdnnf", "search"), key=lambda k: roofs[k]["ms"] if k in roofs else 0)
+        local = {"ok": 1.0, "audio": audio_s * a.large_steps, "ms": ms}
+        info = {"config": {"workload": "BASELINE.json configs[2] / [4]: assumed en-us-0.22 architecture (random-init, 6016 pdfs), synthetic HCLG vocab 200k x 64 successors "
+                                       "(~1.4e8 arcs), %d streams of U(8,16) s per GPU, lattice -> determinization -> MBR results" % streams, "options": opts},
+                "steps": a.large_steps, "ms_per_step": ms / a.large_steps, "audio_seconds_per_step_per_gpu": audio_s,
+                "roofline": dict(roofs[dom], kernel=dom), "roofline_all_stages": roofs,
+                "results_with_confidence_below_1": sum(1 for t in texts if '"conf" : 0.' in t), "nonempty_results": sum(1 for t in texts if '"text" : ""' not in t),
+                "texts_differing_between_steps": model.resident_mismatches, "host_lattice_chain_cpu_ms_per_step": st["post_ms"] / a.large_steps,
+                "truncated": st["truncated"], "lattice_fallbacks": st["lattice_fallbacks"], "model_generation_s": t_gen, "model_load_s": t_load}
+        del model
+        if rank == 0 and not a.no_large_parity:
+            try:
+                ps, _, _ = parity_sample(vosk, "large", waves, texts, 2, "log-links-per-frame=4096,lat-link-cap=131072,lat-tok-cap=65536")
+                info["parity_sample"] = ps
+            except Exception as e:
+                info["parity_sample"] = {"error": str(e)[:200]}
+    except Exception as e:  # never takes the headline line (or the other ranks' collectives) down
+        info = {"error": str(e)[:300]}
+    ok = reduce_over_ranks(local["ok"], "sum", "cuda") if world > 1 else local["ok"]
+    audio = reduce_over_ranks(local["audio"], "sum", "cuda") if world > 1 else local["audio"]
+    ms = reduce_over_ranks(local["ms"], "max", "cuda") if world > 1 else local["ms"]
+    if ok == world and "error" not in info:
+        info["value"] = audio / (ms / 1e3)
+        info["unit"] = UNIT
+        info["n_gpus"] = world
+    elif "error" not in info:
+        info["error"] = "the leg failed on another rank"
+    return info
+
+
+def inproc(a):
+    """One process, one BatchModel spanning --gpus devices (the C-ABI user's multi-GPU path: one engine per device inside the
+    model, streams assigned by id), fed through the reference ABI calls by the library's native multi-threaded feeder."""
+    import vosk
+    mdir = model_dir()
+    vosk.SetLogLevel(-1)
+    n = a.streams * a.gpus
+    opts = "num-channels=%d,max-batch-size=%d,max-seconds=18,devices=%s" % (a.streams, min(a.streams, 1024), ":".join(str(i) for i in range(a.gpus)))
+    if a.options:
+        opts += "," + a.options
+    model = vosk.BatchModel(mdir, options=opts)
+    waves = []
+    for r in range(a.gpus):
+        waves += make_audio(a.streams, r)
+    waves = [waves[(i % a.gpus) * a.streams + i // a.gpus] for i in range(n)]   # stream i lands on engine i % gpus: rank r's set per device
+    audio_s = sum(len(w) for w in waves) / 16000.0
+    threads = a.feeder_threads or min(32, os.cpu_count() or 8)
+    for _ in range(max(1, min(a.warmup, 2))):
+        model.FeedStreams(waves, 8000, threads, want_results=False)
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    texts = None
+    for _ in range(a.steps):
+        texts = model.FeedStreams(waves, 8000, threads)
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    st = model.Stats()
+    v = audio_s * a.steps / wall
+    print(json.dumps({"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": wall * 1e3 / a.steps,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "mode": "inproc",
+                      "config": {"workload": "small-en-us arch, %d streams of U(8,16) s per GPU, ONE process / ONE BatchModel over %d devices, native feeder (%d threads), "
+                                             "reference ABI calls, lattice -> MBR results" % (a.streams, a.gpus, threads), "options": opts},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": st["h2d_bytes"] / (a.steps + max(1, min(a.warmup, 2))),
+                              "d2h_bytes_per_step": st["d2h_bytes"] / (a.steps + max(1, min(a.warmup, 2)))},
+                      "gpu_launches": int(st["launches"]), "clocks": clocks, "nonempty_results": sum(1 for t in texts if '"text" : ""' not in t),
+                      "results_with_confidence_below_1": sum(1 for t in texts if '"conf" : 0.' in t), "timing": "host wall clock around the feeder calls (one process)"}))
     return 0
 
 
@@ -259,27 +424,29 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine")
     ap.add_argument("--streams", type=int, default=STREAMS)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the parity sample / CPU baseline leg")
     ap.add_argument("--options", default="")
-    ap.add_argument("--wait-each-round", action="store_true", help="call Wait() after every feeding round, as the reference example does")
-    ap.add_argument("--no-extras", action="store_true", help="skip the lattice-mode and partial-latency legs")
-    ap.add_argument("--workload", default="small", choices=["small", "large-lattice"],
-                    help="small = BASELINE.json configs[1] (the headline line); large-lattice = configs[2]: assumed en-us-0.22 architecture, "
-                         "synthetic multi-GB HCLG, lattice generation on the device, --streams (default 1024) streams, device-resident leg only")
+    ap.add_argument("--no-extras", action="store_true", help="skip the best-path, device-lattice and partial-latency legs")
+    ap.add_argument("--no-large", action="store_true", help="skip the large-architecture leg (BASELINE.json configs[2] / [4])")
+    ap.add_argument("--no-large-parity", action="store_true")
+    ap.add_argument("--large-streams", type=int, default=1024)
+    ap.add_argument("--large-steps", type=int, default=2)
+    ap.add_argument("--inproc", action="store_true", help="one process, one BatchModel over --gpus devices, native feeder; prints its own line")
+    ap.add_argument("--feeder-threads", type=int, default=0)
     ap.add_argument("--latency-streams", type=int, default=2048)
     ap.add_argument("--latency-seconds", type=float, default=4.0)
     a = ap.parse_args()
+    a.warmup = max(a.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": "small-en-us arch (random-init TDNN-F, synthetic HCLG ~1.0M arcs), %d concurrent 16 kHz streams of U(8,16) s per GPU" % a.streams,
+    config = {"workload": "BASELINE.json configs[1]: small-en-us arch (random-init TDNN-F, synthetic HCLG ~1.0M arcs), %d concurrent 16 kHz streams of U(8,16) s per GPU" % a.streams,
               "streams_per_gpu": a.streams, "frames_per_chunk": 51, "beam": 13.0, "lattice_beam": 6.0, "max_active": 7000,
-              "l2": "inputs+state larger than L2 (audio ~190 MB, token logs GBs)", "sharding": "streams by utterance, no collective",
-              "result_mode": "best path (lattice=0: word-aligned best path, conf 1); lattice generation and the host MBR chain are the separate lattice_mode legs",
+              "l2": "inputs+state larger than L2 (audio ~190 MB, token and link logs GBs)", "sharding": "streams by utterance, no collective",
+              "result_mode": "lattice -> phone-pruned determinization -> 0.9 LM scale -> word alignment -> MBR (the reference's result path; engine default)",
+              "steps": "back to back: the streams of step k+1 are queued while the lattice chain of step k's results runs; all results delivered inside the timed region",
               "tdnnf_arithmetic": "fp32 accumulate; operands split into fp16 hi + scaled fp16 lo, 3 f16 MMAs per product (log-likelihoods within 1e-3 of the fp64-accumulating oracle)"}
 
-    if a.workload == "large-lattice":
-        return large_lattice(a)
     if a.impl == "reference":
         if rank != 0:
             return 0
@@ -294,9 +461,11 @@ def main():
                           "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": config,
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                           "sample": "%d streams of U(8,16) s, one stream per thread, %d threads" % (n, cores)},
+                                           "sample": "%d of the workload's streams (U(8,16) s), one stream per thread, %d threads, lattice -> MBR results" % (n, cores)},
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
+    if a.inproc:
+        return inproc(a)
 
     import torch
     import torch.distributed as dist
@@ -304,12 +473,21 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=600))
     os.environ["VOSK_BATCH_DEVICES"] = str(local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        return reduce_over_ranks(x, "max", "cuda")
+
     if rank == 0:
         model_dir()  # generate once
-    if world > 1:
-        dist.barrier()
+    barrier()
     import vosk
     mdir = model_dir()
     vosk.SetLogLevel(-1)
@@ -324,37 +502,25 @@ def main():
     for i, w in enumerate(waves):
         audio_mat[i, :len(w)] = w
     audio_s = float(lengths.sum()) / 16000.0
+    peaks = peaks_measured()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        return reduce_over_ranks(x, "max", "cuda")
-
-    # ---------------- value: device-resident ----------------
-    texts = None
-    for _ in range(a.warmup):
-        _, texts = model.RunResident(audio_mat, lengths)
+    # ---------------- value: device-resident, K steps back to back ----------------
+    model.RunResident(audio_mat, lengths, passes=a.warmup)
     model.ResetStats()
-    model.SetTiming(True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    dev_ms = 0.0
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        ms, texts = model.RunResident(audio_mat, lengths)
-        dev_ms += ms
+    dev_ms, texts = model.RunResident(audio_mat, lengths, passes=a.steps)
     barrier()
     wall_resident = time.perf_counter() - t0
     clocks = sampler.stop()
     st = model.Stats()
+    resident_bad = model.resident_mismatches
     # one extra pass with the pipeline slots serialized: per-stage device times (CUDA events on the launching
     # stream) free of cross-slot overlap; these are the durations the roofline uses
     model.ResetStats()
+    model.SetTiming(True)
     model.SetSlots(1)
     model.RunResident(audio_mat, lengths)
     ser = model.Stats()
@@ -364,124 +530,88 @@ def main():
     audio_total = reduce_over_ranks(audio_s, "sum", "cuda")   # every rank takes part in every collective
     value = audio_total * a.steps / dev_s
 
-    # ---------------- e2e: through the C ABI with host buffers ----------------
+    # ---------------- e2e: through the C ABI with host buffers, K steps back to back ----------------
     pieces = [[w[i:i + 4000].tobytes() for i in range(0, len(w), 4000)] for w in waves]  # 8000-byte reads, as the reference driver
-    for _ in range(min(a.warmup, 1)):
-        e2e_pass(vosk, model, pieces, a.wait_each_round)
+    e2e_run(vosk, model, pieces, 1)
+    model.ResetStats()
     barrier()
     t0 = time.perf_counter()
-    e2e_texts = None
-    for _ in range(a.steps):
-        e2e_texts = e2e_pass(vosk, model, pieces, a.wait_each_round)
+    e2e_texts, e2e_bad = e2e_run(vosk, model, pieces, a.steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = audio_total * a.steps / e2e_s
+    est = model.Stats()
     same = sum(1 for x, y in zip(texts, e2e_texts) if x == y)
 
-    # ---------------- roofline of the dominant kernel ----------------
-    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+    # ---------------- roofline of the dominant kernel (serialized pass: one step) ----------------
+    roofs, search_bytes = stage_rooflines(ser, lengths, "small", peaks)
+    kernel_ms = {k: v["ms"] for k, v in roofs.items()}
+    dominant = max(kernel_ms, key=kernel_ms.get)
+    kname = {"search": "decode_kernel", "tdnnf": "gemm_tc_kernel", "ivector": "ivector_kernel", "mfcc": "mfcc_kernel", "lattice_prune": "lattice_prune_kernel"}[dominant]
+    roof = {"kernel": kname, "bound": roofs[dominant]["bound"], "achieved": roofs[dominant]["achieved"], "peak": roofs[dominant]["peak"],
+            "unit": roofs[dominant]["unit"], "frac": roofs[dominant]["frac"], "traffic": None, "peak_src": peaks["src"],
+            "algorithmic": roofs[dominant]["algorithmic"], "launch_ms": "sum of the kernel's launches of one serialized step: %.2f ms" % kernel_ms[dominant]}
     try:
-        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peaks = {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops": pk["bf16_tflops_sustained"], "src": "measured"}
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get(kname)
+        if ent:
+            roof["traffic"] = ent["value"]
+            roof["traffic_note"] = ent["unit"] + "; from " + tj["_source"]
+            if dominant == "search":  # the same unit for the algorithmic side: bytes of one search step (512 lanes x 17 frames)
+                roof["algorithmic_bytes_per_search_step"] = search_bytes / max(1.0, ser["steps"])
     except Exception:
         pass
-    kernel_ms_overlapped = {"mfcc": st["ms_feat"] / a.steps, "ivector": st["ms_ivector"] / a.steps, "tdnnf": st["ms_nnet"] / a.steps, "search": st["ms_search"] / a.steps}
-    kernel_ms = {"mfcc": ser["ms_feat"], "ivector": ser["ms_ivector"], "tdnnf": ser["ms_nnet"], "search": ser["ms_search"]}
-    dominant = max(kernel_ms, key=kernel_ms.get)
-    launches_timed = int(st["launches"])
-    st = ser     # counters of the serialized pass (one step) feed the byte model
-    roof_steps = 1
-    out_frames = sum((int(1 + (n - 400) // 160) + 2) // 3 for n in lengths) * roof_steps
-    flop = 7.95e6 * out_frames  # 7.95 MFLOP per output frame, small architecture
-    # SURVEY.md §8(d) beam-search byte model from the in-kernel counters
-    T, Ae, Aeps, N = st["tokens"], st["arcs_emitting"], st["arcs_epsilon"], st["tokens_new"]
-    search_bytes = T * 16 + (Ae + Aeps) * 20 + Ae * 4 + N * 16
-    feat_bytes = 480.0 * sum(int(1 + (n - 400) // 160) for n in lengths) * roof_steps
-    if dominant == "tdnnf":
-        ach = flop / (kernel_ms["tdnnf"] / 1000.0) / 1e12
-        roof = {"kernel": "gemm_tc_kernel (TDNN-F chain, fp16 hi/lo operand split, fp32 accumulate)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_src": peaks["src"] + " bf16 sustained (f16 MMAs, 3 per algorithmic MAC)"}
-    elif dominant == "search":
-        ach = search_bytes / (kernel_ms["search"] / 1000.0) / 1e9
-        roof = {"kernel": "decode_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"]}
-    else:
-        ach = feat_bytes / (kernel_ms[dominant] / 1000.0) / 1e9
-        roof = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"]}
 
-    # ---------------- extras (rank 0): lattice generation on, and the low-latency / partial-result configuration ----------------
+    # ---------------- extras (rank 0) ----------------
     del model
-    lattice_mode = None
+    extras = {}
     partial_latency = None
     if rank == 0 and not a.no_extras:
-        try:
-            res = {}
-            for mode, name in ((2, "device_lattice"), (1, "device_lattice_plus_host_mbr")):
-                lm = vosk.BatchModel(mdir, options=opts + ",lattice=%d" % mode)
-                lm.RunResident(audio_mat, lengths)
-                lm.ResetStats()
-                lm.SetTiming(True)
-                ms, ltexts = lm.RunResident(audio_mat, lengths)
-                lst = lm.Stats()
-                res[name] = {"value": audio_s / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms, "links_logged": lst["links"],
-                             "lattice_arcs_after_pruning": lst["lattice_arcs"], "search_ms_overlapped": lst["ms_search"]}
-                if mode == 1:
-                    res[name]["results_with_confidence_below_1"] = sum(1 for t in ltexts if '"conf" : 0.' in t)
-                    res[name]["host_threads"] = "hardware threads / 2 (lattice pool)"
-                del lm
-            lattice_mode = res
-        except Exception as e:  # the extras never take the headline line down
-            lattice_mode = {"error": str(e)[:200]}
+        for name, o in (("best_path_mode (lattice=0: word-aligned best path, conf 1)", "lattice=0"),
+                        ("device_lattice_only (lattice=2: link log + device pruning, no host chain; results are best-path texts)", "lattice=2")):
+            try:
+                extras[name], _ = resident_leg(vosk, mdir, opts + "," + o, audio_mat, lengths, 1, max(2, a.steps // 2))
+            except Exception as e:  # the extras never take the headline line down
+                extras[name] = {"error": str(e)[:200]}
         try:
             partial_latency = latency_pass(vosk, mdir, a.latency_streams, a.latency_seconds)
         except Exception as e:
             partial_latency = {"error": str(e)[:200]}
 
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = tj.get({"search": "decode_kernel", "tdnnf": "gemm_tc_kernel", "ivector": "ivector_kernel", "mfcc": "mfcc_kernel"}[dominant])
-        if ent:
-            traffic = ent["value"]
-            roof["traffic_note"] = ent["unit"] + "; from " + tj["_source"]
-            if dominant == "search":  # the same unit for the algorithmic side: bytes of one search step (512 lanes x 17 frames)
-                steps_run = max(1.0, st["steps"])
-                roof["algorithmic_bytes_per_search_step"] = search_bytes / steps_run
-    except Exception:
-        pass
-    roof["traffic"] = traffic
-    # the same figures for every stage: algorithmic bytes or flops of one serialized step / its device time
-    roof_all = {
-        "mfcc": {"bound": "hbm", "achieved": feat_bytes / (kernel_ms["mfcc"] / 1000.0) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                 "algorithmic": "480 B per frame"},
-        "tdnnf": {"bound": "tensor", "achieved": flop / (kernel_ms["tdnnf"] / 1000.0) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                  "algorithmic": "7.95 MFLOP per output frame (the fp16 hi/lo split issues 3x that on the tensor pipe)"},
-        "search": {"bound": "hbm", "achieved": search_bytes / (kernel_ms["search"] / 1000.0) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                   "algorithmic": "T*16 + (Ae+Aeps)*20 + Ae*4 + N*16 bytes from the in-kernel counters"},
-    }
-    for v in roof_all.values():
-        v["frac"] = v["achieved"] / v["peak"]
-
     cpu = None
+    parity = None
     if rank == 0 and not a.no_cpu_baseline:
-        ca, cw = run_oracle_sample(12, 1)
-        cpu = {"value": ca / cw, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "12 streams of U(8,16) s decoded one after another on one core (%.1f s of CPU work)" % cw}
+        try:
+            parity, ca, cw = parity_sample(vosk, "small", waves, texts, 12)
+            cpu = {"value": ca / cw, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "12 of the workload's own streams (U(8,16) s) through the whole CPU restatement (features .. lattice -> MBR text) one after another "
+                             "on one core (%.1f s of CPU work)" % cw}
+        except Exception as e:
+            parity = {"error": str(e)[:300]}
+
+    large = None
+    if not a.no_large:
+        large = large_leg(a, rank, world, dist, barrier, peaks)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": dev_s * 1000.0 / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(lengths.sum()) * 2 + a.streams * 64,
-                        "d2h_bytes_per_step": a.streams * (4 * (18 * 100 // 3 + 2) * 4 + 64 * 4 + 32),
-                        "transcripts_equal_to_resident_run": "%d/%d" % (same, len(texts))},
-                "gpu_launches": launches_timed, "clocks": clocks, "roofline": roof, "roofline_all_stages": roof_all, "cpu_baseline": cpu,
-                "kernel_ms_per_step": kernel_ms, "kernel_ms_per_step_overlapped": kernel_ms_overlapped,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(est["h2d_bytes"] / a.steps), "d2h_bytes_per_step": int(est["d2h_bytes"] / a.steps),
+                        "transcripts_equal_to_resident_run": "%d/%d" % (same, len(texts)), "texts_differing_between_steps": e2e_bad,
+                        "bytes": "counted by the engine at every host<->device copy of the timed steps (samples, lane descriptors, results, lattices)"},
+                "gpu_launches": int(st["launches"]), "clocks": clocks, "roofline": roof, "roofline_all_stages": roofs, "cpu_baseline": cpu,
+                "parity_sample": parity,
+                "results": {"with_confidence_below_1": sum(1 for t in texts if '"conf" : 0.' in t), "nonempty": sum(1 for t in texts if '"text" : ""' not in t),
+                            "texts_differing_between_steps": resident_bad, "truncated": st["truncated"], "lattice_fallbacks": st["lattice_fallbacks"]},
+                "kernel_ms_per_step": kernel_ms,
                 "roofline_note": "stage durations from one extra pass with the pipeline slots serialized (no overlap); CUDA events on the launching stream",
+                "host_lattice_chain": {"cpu_ms_per_step": st["post_ms"] / a.steps, "threads": st["post_threads"],
+                                       "note": "determinization / word alignment / MBR of the finished segments on the host lattice pool, beside the device work"},
                 "host_wall_ms_per_step_resident": wall_resident * 1000.0 / a.steps,
-                "search_counters_per_step": {"tokens": T, "arcs_emitting": Ae, "arcs_epsilon": Aeps, "tokens_new": N},
-                "audio_seconds_per_step": audio_total,
-                "lattice_mode": lattice_mode, "partial_latency": partial_latency}
+                "search_counters_per_step": {"tokens": ser["tokens"], "arcs_emitting": ser["arcs_emitting"], "arcs_epsilon": ser["arcs_epsilon"],
+                                             "tokens_new": ser["tokens_new"], "links_logged": ser["links"], "lattice_arcs_kept": ser["lattice_arcs"]},
+                "audio_seconds_per_step": audio_total, "other_modes": extras, "partial_latency": partial_latency, "large": large}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -40,7 +40,8 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model);
  * insert, closure, finalize, unused), [37] per-call segments resampled on the device, [38] results delivered although a device
  * capacity overflowed (logged; the result may be truncated), [39] lattice-mode results that fell back to the best path,
  * [40] host milliseconds spent by the lattice thread pool, [41] its jobs, [42] its threads, [43] device ms of the lattice
- * pruning launches (timing on), [44] batcher-thread ms spent completing steps, [45] of that, fetching lattices.
+ * pruning launches (timing on), [44] batcher-thread ms spent completing steps, [45] of that, fetching lattices, [46] / [47] bytes the steps copied host-to-device /
+ * device-to-host (samples, descriptors, results, lattices).
  * Returns the number written. */
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n);
 void vosk_batch_model_reset_stats(VoskBatchModel *model);
@@ -56,6 +57,12 @@ void vosk_batch_model_set_slots(VoskBatchModel *model, int n);
  * Result texts are kept until the next call; fetch with vosk_batch_model_resident_result. */
 double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream,
                                      const int *lengths);
+/* The same with the streams decoded `passes` times over, back to back, as new streams that are all queued at once: a stream
+ * of pass p+1 starts as soon as a channel is free and the lattice chain of pass p's results runs beside the search of pass
+ * p+1 (continuous serving); returns when every result of every pass has been delivered.  The texts kept are the last
+ * pass's; *mismatches (may be NULL) = streams of earlier passes whose text differs from it (0 unless something is wrong). */
+double vosk_batch_model_run_resident_passes(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream,
+                                            const int *lengths, int passes, int *mismatches);
 const char *vosk_batch_model_resident_result(VoskBatchModel *model, int stream);
 
 /* Partial result (model option partials=1): the best path so far, without final costs, in the CPU API's text layout

@@ -793,7 +793,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         d.in_end_before = d.first ? -ctx : s.in_end;
         d.in_end_after = d.frames_after > 0 ? (ck.last ? d.frames_after + ctx : d.frames_after) : d.in_end_before;
         d.dec_frames_before = s.dec_frames;
-        d.src_row = s.resident ? (int)s.id : i;
+        d.src_row = s.resident ? s.resident_row : i;
         d.src_off = s.resident ? (int)s.samples : 0;
         if (ck.rate && !s.resident) {
             // resampled on the device: stage the raw samples and the segment list of this lane
@@ -839,18 +839,24 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         }
     }
     sl.launches = 0;
+    sl.h2d = 0;
+    sl.d2h = 0;
     sl.gemms = 0;
     sl.resample_segs = n_segs;
     sl.timed = timing_;
     sl.pruned = false;
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[0], st));
     VB_CUDA_CHECK(cudaMemcpyAsync(sl.d_lanes, sl.h_lanes, (size_t)L * sizeof(LaneDesc), cudaMemcpyHostToDevice, st));
-    if (!d_resident)
+    sl.h2d += (size_t)L * sizeof(LaneDesc);
+    if (!d_resident) {
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.d_staging, sl.h_staging, (size_t)L * spc * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        sl.h2d += (size_t)L * spc * sizeof(int16_t);
+    }
     if (n_segs) {
         // K0: the non-16 kHz lanes' chunks are produced on the device (after the staging copy, which they overwrite row-wise)
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.d_raw, sl.h_raw, raw_used * sizeof(int16_t), cudaMemcpyHostToDevice, st));
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.d_segs, sl.h_segs, (size_t)n_segs * sizeof(ResampleSeg), cudaMemcpyHostToDevice, st));
+        sl.h2d += raw_used * sizeof(int16_t) + (size_t)n_segs * sizeof(ResampleSeg);
         ResampleArgs ra{sl.d_segs, n_segs, sl.d_raw, d_resample_tables_, sl.d_staging, spc};
         VB_CUDA_CHECK(vbk_resample(&ra, st));
         sl.launches++;
@@ -952,10 +958,12 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     if (cfg_.partials && n_last < L) {
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_partial, sl.dec.partial_words, (size_t)L * kPartialCap * sizeof(int), cudaMemcpyDeviceToHost, st));
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_partial + (size_t)L * kPartialCap, sl.dec.partial_count, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
+        sl.d2h += (size_t)L * (kPartialCap + 1) * sizeof(int);
     }
     if (endpointing_ && n_last < L) {
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_endp, sl.dec.endp_silence, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_endp + L, sl.dec.endp_relcost, (size_t)L * sizeof(float), cudaMemcpyDeviceToHost, st));
+        sl.d2h += (size_t)L * 8;
     }
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[4], st));
     // results of finished lanes
@@ -966,9 +974,11 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
             VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_cs + k_last, dec_.cs + ch, sizeof(DecChannelState), cudaMemcpyDeviceToHost, st));
             VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_path + (size_t)k_last * path_cap_, dec_.path + (size_t)ch * path_cap_,
                                           (size_t)path_cap_ * sizeof(int), cudaMemcpyDeviceToHost, st));
+            sl.d2h += sizeof(DecChannelState) + (size_t)path_cap_ * sizeof(int);
             k_last++;
         }
     VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_load, sl.d_load, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
+    sl.d2h += (size_t)L * sizeof(int);
     if (cfg_.lattice && n_last > 0) {
         // lattice pruning only touches finished channels (nothing else does until they are reused after completion)
         sl.dec.lane_begin = 0;
@@ -979,6 +989,7 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         sl.pruned = true;
         sl.launches++;
         VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_hdr, sl.dec.lat_hdr, (size_t)L * sizeof(LatHeader), cudaMemcpyDeviceToHost, st));
+        sl.d2h += (size_t)L * sizeof(LatHeader);
     }
     VB_CUDA_CHECK(cudaEventRecord(sl.done, st));
     {
@@ -1097,6 +1108,8 @@ void Engine::complete_step(Slot &sl) {
     {
         std::lock_guard<std::mutex> lk(stats_mu_);
         stats_.host_fetch_ms += fetch_ms;
+        stats_.h2d_bytes += sl.h2d;
+        stats_.d2h_bytes += sl.d2h;
         stats_.host_complete_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     }
 }
@@ -1186,6 +1199,7 @@ void Engine::fetch_lattices(Slot &sl, std::vector<std::shared_ptr<PackedLattice>
         if (nt && with_state)
             VB_CUDA_CHECK(cudaMemcpyAsync(sl.h_lat_pool + p.tok_state, sl.dec.lat_tok_state + (size_t)i * cfg_.lat_tok_cap, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost, st));
         used += need;
+        sl.d2h += (size_t)nl * sizeof(int4) + (size_t)nf * sizeof(int2) + (size_t)(with_state ? 2 : 1) * nt * sizeof(int);
         batch.push_back(p);
     }
     flush();
@@ -1231,24 +1245,31 @@ void Engine::finish_lane(Slot &sl, Lane &ln, int k, std::shared_ptr<PackedLattic
     post_cv_.notify_one();
 }
 
-double Engine::run_resident(const int16_t *d_audio, int num_streams, int stride, const int *lengths, std::vector<BestPath> *out) {
+double Engine::run_resident(const int16_t *d_audio, int num_streams, int stride, const int *lengths, std::vector<BestPath> *out, int passes) {
     // Device-resident run: the streams' chunk descriptors (lengths only) go through the normal batcher, which reads
-    // the samples straight from the resident matrix; no host<->device sample traffic.
+    // the samples straight from the resident matrix; no host<->device sample traffic.  With passes > 1 the same streams
+    // are decoded `passes` times over as new streams (id = pass * num_streams + row), all queued at once: a stream of pass
+    // p+1 starts as soon as a channel is free, and the lattice chain of pass p's results runs beside the search of pass
+    // p+1, as in continuous serving; the call returns when every result of every pass has been delivered.
     if (num_streams > cfg_.num_channels) throw std::runtime_error("run_resident: more streams than channels");
+    if (passes < 1) passes = 1;
     wait();
     const int spc = samples_per_chunk();
-    std::vector<std::shared_ptr<Stream>> ss(num_streams);
+    const int total = num_streams * passes;
+    std::vector<std::shared_ptr<Stream>> ss(total);
     std::vector<BestPath> res(num_streams);
-    for (int i = 0; i < num_streams; i++) {
-        const int len = lengths ? lengths[i] : stride;
+    for (int i = 0; i < total; i++) {
+        const int row = i % num_streams, pass = i / num_streams;
+        const int len = lengths ? lengths[row] : stride;
         if (len < 0 || len > stride) throw std::runtime_error("run_resident: bad stream length");
         ss[i] = std::make_shared<Stream>();
         ss[i]->id = (uint64_t)i;
         ss[i]->resident = true;
-        BestPath *slot = &res[i];
-        ss[i]->on_result = [slot, i, this](const BestPath &bp) {
-            *slot = bp;
-            if (resident_hook) resident_hook(i, bp);
+        ss[i]->resident_row = row;
+        BestPath *slot = pass == passes - 1 ? &res[row] : nullptr;
+        ss[i]->on_result = [slot, row, pass, this](const BestPath &bp) {
+            if (slot) *slot = bp;
+            if (resident_hook) resident_hook(pass, row, bp);
         };
     }
     cudaEvent_t e0, e1;
@@ -1260,8 +1281,8 @@ double Engine::run_resident(const int16_t *d_audio, int num_streams, int stride,
         resident_stride_ = stride;
     }
     VB_CUDA_CHECK(cudaEventRecord(e0, stream_));
-    for (int i = 0; i < num_streams; i++) {
-        const int len = lengths ? lengths[i] : stride;
+    for (int i = 0; i < total; i++) {
+        const int len = lengths ? lengths[i % num_streams] : stride;
         const int nfull = len / spc;
         std::lock_guard<std::mutex> lk(mu_);
         for (int k = 0; k <= nfull; k++) {

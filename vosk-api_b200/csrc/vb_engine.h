@@ -85,7 +85,8 @@ struct Stream {
     int seg_index = 0;       // segments closed so far
     bool seg_open = false;   // the search of the current segment has been initialised
     int last_tier = -1;      // search tier (pipe) that ran the stream's previous chunk
-    bool resident = false;   // samples are read from a device-resident matrix (row = id)
+    bool resident = false;   // samples are read from a device-resident matrix
+    int resident_row = 0;    // its row there
     struct Chunk {
         std::vector<int16_t> samples;
         int n_resident = 0;  // chunk length when the samples live in a device-resident matrix
@@ -122,6 +123,7 @@ struct StepStats {
     double host_launch_ms = 0;  // host time spent enqueueing steps
     long long truncated = 0;          // results delivered although a device capacity (tokens / candidates / log / links / lattice) overflowed
     long long lattice_fallbacks = 0;  // lattice-mode results that fell back to the best path (no lattice, capacity error, chain failure)
+    unsigned long long h2d_bytes = 0, d2h_bytes = 0;  // bytes of the host<->device copies of the steps (samples, descriptors, results, lattices)
     double t_prune = 0;               // device ms of the lattice pruning launches (only when timing enabled)
     double host_complete_ms = 0, host_fetch_ms = 0;  // batcher-thread milliseconds spent completing steps / of that, fetching lattices
     double post_ms = 0;               // host milliseconds the lattice pool spent on results (summed over its threads)
@@ -156,9 +158,10 @@ class Engine {
 
     // Device-resident run for kernel-level benchmarking: `audio` holds num_streams x samples int16 already in
     // HBM; processes every stream chunk by chunk with no host<->device sample traffic.  Returns device ms.
-    double run_resident(const int16_t *d_audio, int num_streams, int stride, const int *lengths, std::vector<BestPath> *out);
-    // called for every finished stream of a resident run, on the thread that delivers results (stream index, result)
-    std::function<void(int, const BestPath &)> resident_hook;
+    // passes > 1: the streams are decoded that many times over, back to back (see the definition); out = results of the last pass.
+    double run_resident(const int16_t *d_audio, int num_streams, int stride, const int *lengths, std::vector<BestPath> *out, int passes = 1);
+    // called for every finished segment of a resident run, on the thread that delivers results (pass, stream index, result)
+    std::function<void(int, int, const BestPath &)> resident_hook;
 
    private:
     struct Lane {
@@ -205,6 +208,7 @@ class Engine {
         bool busy = false, timed = false;
         double audio = 0;
         long long launches = 0, gemms = 0, resample_segs = 0;
+        unsigned long long h2d = 0, d2h = 0;  // bytes copied for this step
     };
     int resample_table(int rate);  // index of the device phase table of an input rate (built on first use)
     void worker();

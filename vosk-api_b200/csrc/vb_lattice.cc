@@ -28,6 +28,20 @@
 namespace vb {
 
 namespace {
+
+#ifdef VB_LAT_PROF
+#include <x86intrin.h>
+static thread_local unsigned long long g_prof[16];
+struct ProfScope {
+    int k;
+    unsigned long long t0;
+    explicit ProfScope(int k_) : k(k_), t0(__rdtsc()) {}
+    ~ProfScope() { g_prof[k] += __rdtsc() - t0; }
+};
+#define LATP(k) ProfScope prof_scope_##k(k)
+#else
+#define LATP(k)
+#endif
 constexpr float kInfF = std::numeric_limits<float>::infinity();
 constexpr double kInfD = std::numeric_limits<double>::infinity();
 constexpr int kMaxDetStates = 400000;
@@ -314,6 +328,7 @@ Workspace &workspace() {
 static int g_comp_pass = 0;
 void compress_chains(Workspace &ws, int n, int start, const std::vector<Edge> &in, const std::vector<float> &fin_g,
                      const std::vector<Sym> &syms_in, std::vector<Edge> *out, std::vector<Sym> *syms_out) {
+    LATP(7);
     std::vector<int> &indeg = ws.nin, &outdeg = ws.nout, &out_edge = ws.remap;
     indeg.assign(n, 0);
     outdeg.assign(n, 0);
@@ -348,6 +363,7 @@ void compress_chains(Workspace &ws, int n, int start, const std::vector<Edge> &i
 // construction with the arcs of a state ordered by il.  fin_g/fin_a are indexed by the old state ids.
 bool build_flat(Workspace &ws, int n_old, int start_old, const std::vector<Edge> &edges, const std::vector<float> &fin_g,
                 const std::vector<float> &fin_a, const std::vector<Sym> *syms, FLat *out) {
+    LATP(6);
     out->start = -1;
     out->n = 0;
     out->arcs.clear();
@@ -424,6 +440,7 @@ class Determinizer {
     Determinizer(Workspace &ws, const FLat &in, double beam) : ws_(ws), in_(in), sy_(in.syms->data()), beam_(beam), repo_(ws.repo) {}
 
     bool run() {
+        LATP(5);
         repo_.reset();
         ws_.pool.clear();
         ws_.tarcs.clear();
@@ -528,6 +545,7 @@ class Determinizer {
     // (state - n), behind its first (labelled) arc: that is where Kaldi's initial subsets live, and what they are keyed on.
     // The result is sorted by state.
     void closure(std::vector<Elem> *sub) {
+        LATP(1);
         std::vector<Elem> &cur = ws_.cur;
         std::vector<int> &heap = ws_.heap;
         cur.clear();
@@ -596,6 +614,7 @@ class Determinizer {
 
     // NormalizeSubset: take the best weight and the longest common string prefix out of the subset
     void normalize(Elem *e, int n, float *tg, float *ta, int *common) {
+        LATP(2);
         if (n == 0) {
             *tg = *ta = kInfF;
             *common = 0;
@@ -659,6 +678,7 @@ class Determinizer {
     }
 
     void process_transitions(int sid) {
+        LATP(3);
         const OutState st = states_[sid];
         std::vector<Elem> &all = ws_.allv;
         std::vector<int> &lab = ws_.all_label, &idx = ws_.idx;
@@ -715,6 +735,7 @@ class Determinizer {
     }
 
     void process_transition(const Task &t) {
+        LATP(4);
         double fwd = states_[t.src].fwd;
         Elem *e = &ws_.pool[t.off];
         float tg, ta;
@@ -758,6 +779,7 @@ class Determinizer {
 // along a chain of new states, weight and label on the first arc of the chain — here one arc with that chain as its span
 void output_pass1(Workspace &ws, int n_det, std::vector<Edge> *edges, std::vector<Sym> *syms, std::vector<float> *fin_g, std::vector<float> *fin_a,
                   int *n_out) {
+    LATP(8);
     edges->clear();
     syms->clear();
     fin_g->assign(n_det, kInfF);
@@ -789,6 +811,7 @@ void output_pass1(Workspace &ws, int n_det, std::vector<Edge> *edges, std::vecto
 
 // output of the word pass in compact form + fst::Connect (drop the states from which no final weight can be reached)
 void compact_output(Workspace &ws, int n_det, CLatF *out) {
+    LATP(9);
     out->tids.clear();
     std::vector<int> &off = ws.csr_off;
     off.assign(n_det + 1, 0);
@@ -871,6 +894,7 @@ void compact_output(Workspace &ws, int n_det, CLatF *out) {
 // DeterminizeLatticePhonePrunedWrapper
 bool determinize_phone_pruned(Workspace &ws, const RawLattice &raw, const Model &m, double beam, bool phone_pass, CLatF *out,
                               LatticeStats *stats) {
+    LATP(0);
     const Graph &g = m.graph;
     const int n_raw = raw.n_states;
     if (n_raw <= 0 || raw.start < 0 || raw.start >= n_raw) return false;
@@ -1567,6 +1591,10 @@ inline double ms_since(std::chrono::steady_clock::time_point t0) {
 }  // namespace
 
 std::vector<WordSpan> lattice_to_words(const RawLattice &raw, const Model &m, float lattice_beam, double lm_scale, LatticeStats *stats) {
+#ifdef VB_LAT_PROF
+    struct Dump { ~Dump() { if (getenv("VB_LAT_PROF_DUMP")) { for (int k = 0; k < 12; k++) fprintf(stderr, "prof[%d]=%.3f Mcyc\n", k, g_prof[k] / 1e6); } } };
+    static thread_local Dump dump;
+#endif
     Workspace &ws = workspace();
     auto t0 = std::chrono::steady_clock::now();
     if (stats) {

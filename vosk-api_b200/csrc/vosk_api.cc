@@ -149,7 +149,7 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model) { return model ? (
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
     if (!model || !out) return 0;
     BatchModel *bm = (BatchModel *)model;
-    double v[46] = {0};
+    double v[48] = {0};
     for (size_t i = 0; i < bm->num_engines(); i++) {
         vb::StepStats s = bm->engine(i).stats();
         v[0] += s.audio_seconds; v[1] += s.steps; v[2] += s.lanes; v[3] += s.launches;
@@ -160,9 +160,9 @@ int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
         for (int k = 0; k < 16; k++) v[21 + k] += s.phase[k];
         v[37] += s.resample_segments;
         v[38] += s.truncated; v[39] += s.lattice_fallbacks; v[40] += s.post_ms; v[41] += s.post_jobs; v[42] += bm->engine(i).post_thread_count();
-        v[43] += s.t_prune; v[44] += s.host_complete_ms; v[45] += s.host_fetch_ms;
+        v[43] += s.t_prune; v[44] += s.host_complete_ms; v[45] += s.host_fetch_ms; v[46] += (double)s.h2d_bytes; v[47] += (double)s.d2h_bytes;
     }
-    int k = n < 46 ? n : 46;
+    int k = n < 48 ? n : 48;
     memcpy(out, v, k * sizeof(double));
     return k;
 }
@@ -183,9 +183,9 @@ void vosk_batch_model_set_slots(VoskBatchModel *model, int n) {
     for (size_t i = 0; i < bm->num_engines(); i++) bm->engine(i).set_active_slots(n);
 }
 
-double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream,
-                                     const int *lengths) {
-    if (!model || !audio || num_streams <= 0 || samples_per_stream <= 0) return -1.0;
+double vosk_batch_model_run_resident_passes(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream,
+                                            const int *lengths, int passes, int *mismatches) {
+    if (!model || !audio || num_streams <= 0 || samples_per_stream <= 0 || passes < 1) return -1.0;
     BatchModel *bm = (BatchModel *)model;
     int16_t *d_audio = nullptr;
     try {
@@ -200,11 +200,12 @@ double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio
         const float lattice_beam = eng.config().lattice_beam;
         const bool host_chain = eng.config().lattice == 1;
         std::vector<std::string> *texts = &bm->resident_results;
-        auto parts = std::make_shared<std::vector<std::map<int, std::string>>>(num_streams);  // segment index -> text, per stream
+        // [pass][stream]: segment index -> text
+        auto parts = std::make_shared<std::vector<std::map<int, std::string>>>((size_t)num_streams * passes);
         auto parts_mu = std::make_shared<std::mutex>();
         // result text is produced where the engine delivers results (the lattice pool when lattice=1), inside the timed region
         vb::Engine *engp = &eng;
-        eng.resident_hook = [m, lattice_beam, parts, parts_mu, host_chain, engp](int i, const vb::BestPath &bp) {
+        eng.resident_hook = [m, lattice_beam, parts, parts_mu, host_chain, engp, num_streams](int pass, int i, const vb::BestPath &bp) {
             std::vector<vb::WordSpan> words;
             bool done = false;
             if (host_chain) {
@@ -216,12 +217,19 @@ double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio
             if (!done) words = vb::align_words(*m, bp.arcs);
             std::string t = vb::result_json(*m, words, bp.offset);
             std::lock_guard<std::mutex> lk(*parts_mu);
-            (*parts)[i][bp.seq] = std::move(t);
+            (*parts)[(size_t)pass * num_streams + i][bp.seq] = std::move(t);
         };
-        double ms = eng.run_resident(d_audio, num_streams, samples_per_stream, lengths, &res);
+        double ms = eng.run_resident(d_audio, num_streams, samples_per_stream, lengths, &res, passes);
         eng.resident_hook = nullptr;
-        for (int i = 0; i < num_streams; i++)  // segments of one stream (rule-5 endpoints) are concatenated in order
-            for (auto &kv : (*parts)[i]) (*texts)[i] += kv.second;
+        int bad = 0;
+        for (int p = passes - 1; p >= 0; p--)
+            for (int i = 0; i < num_streams; i++) {  // segments of one stream (rule-5 endpoints) are concatenated in order
+                std::string all;
+                for (auto &kv : (*parts)[(size_t)p * num_streams + i]) all += kv.second;
+                if (p == passes - 1) (*texts)[i] = std::move(all);
+                else if (all != (*texts)[i]) bad++;
+            }
+        if (mismatches) *mismatches = bad;
         cudaFree(d_audio);
         return ms;
     } catch (const std::exception &e) {
@@ -229,6 +237,10 @@ double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio
         vb::log_msg(-1, "run_resident: %s", e.what());
         return -1.0;
     }
+}
+double vosk_batch_model_run_resident(VoskBatchModel *model, const int16_t *audio, int num_streams, int samples_per_stream,
+                                     const int *lengths) {
+    return vosk_batch_model_run_resident_passes(model, audio, num_streams, samples_per_stream, lengths, 1, nullptr);
 }
 const char *vosk_batch_model_resident_result(VoskBatchModel *model, int stream) {
     if (!model) return "";

@@ -79,14 +79,14 @@ class BatchModel(object):
         return _c.vosk_batch_model_samples_per_chunk(self._handle)
 
     def Stats(self):
-        buf = _ffi.new("double[46]")
-        n = _c.vosk_batch_model_stats(self._handle, buf, 46)
+        buf = _ffi.new("double[48]")
+        n = _c.vosk_batch_model_stats(self._handle, buf, 48)
         keys = ["audio_seconds", "steps", "lanes", "launches", "tokens", "arcs_emitting", "arcs_epsilon", "tokens_new",
                 "ms_feat", "ms_ivector", "ms_nnet", "ms_search", "gemm_launches",
                 "lane_cycles_sum", "lane_cycles_max", "max_tokens_per_frame", "lane_launches", "host_launch_ms",
                 "arcs_staged", "links", "lattice_arcs"]
         keys += ["cyc_%s_%s" % (v, ph) for v in ("heavy", "light") for ph in ("cutoff", "rank", "log", "gather", "insert", "closure", "finalize", "x")]
-        keys += ["resample_segments", "truncated", "lattice_fallbacks", "post_ms", "post_jobs", "post_threads", "ms_prune", "host_complete_ms", "host_fetch_ms"]
+        keys += ["resample_segments", "truncated", "lattice_fallbacks", "post_ms", "post_jobs", "post_threads", "ms_prune", "host_complete_ms", "host_fetch_ms", "h2d_bytes", "d2h_bytes"]
         return {k: buf[i] for i, k in enumerate(keys[:n])}
 
     def Latency(self, reset=False):
@@ -121,16 +121,19 @@ class BatchModel(object):
     def SetSlots(self, n):
         _c.vosk_batch_model_set_slots(self._handle, int(n))
 
-    def RunResident(self, audio, lengths=None):
+    def RunResident(self, audio, lengths=None, passes=1):
         """audio: C-contiguous int16 numpy array [streams, samples] (+ optional valid length per row);
-        returns (device_ms, [result text])."""
+        returns (device_ms, [result text]).  passes > 1: the streams are decoded that many times over, back to back
+        (vosk_batch_model_run_resident_passes); self.resident_mismatches = streams whose text differed between passes."""
         import numpy as np
         a = np.ascontiguousarray(audio, dtype=np.int16)
         lp = _ffi.NULL
         if lengths is not None:
             ln = np.ascontiguousarray(lengths, dtype=np.int32)
             lp = _ffi.cast("int *", ln.ctypes.data)
-        ms = _c.vosk_batch_model_run_resident(self._handle, _ffi.cast("int16_t *", a.ctypes.data), a.shape[0], a.shape[1], lp)
+        bad = _ffi.new("int *")
+        ms = _c.vosk_batch_model_run_resident_passes(self._handle, _ffi.cast("int16_t *", a.ctypes.data), a.shape[0], a.shape[1], lp, int(passes), bad)
+        self.resident_mismatches = int(bad[0])
         if ms < 0:
             raise RuntimeError("run_resident failed")
         return ms, [_ffi.string(_c.vosk_batch_model_resident_result(self._handle, i)).decode() for i in range(a.shape[0])]
