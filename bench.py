@@ -226,8 +226,10 @@ def parity_sample(vosk, arch, waves, bench_texts, n, extra_opts=""):
     m.Wait()
     P = int(model_np["cfg"]["num-pdfs"])
     lb = float(model_np["conf"].get("lattice-beam", 6.0))
+    D = int(model_np["cfg"]["ivector-dim"])
     same_bench = same_oracle = same_pipeline = 0
-    max_dll = 0.0
+    max_dll = max_dnet = max_div = 0.0
+    over = 0
     cpu_s = 0.0
     for i, (r, w) in enumerate(zip(recs, waves[:n])):
         text = r.Result()
@@ -235,7 +237,14 @@ def parity_sample(vosk, arch, waves, bench_texts, n, extra_opts=""):
         t0 = time.perf_counter()
         ref = oracle.recognize(model_np, w, stages=True, rc=rc)   # the whole CPU path, timed: the cpu_baseline sample
         cpu_s += time.perf_counter() - t0
-        max_dll = max(max_dll, float(np.abs(ll - ref["loglikes"]).max()))
+        dll = float(np.abs(ll - ref["loglikes"]).max())
+        max_dll = max(max_dll, dll)
+        over += dll >= 1e-3
+        # the network alone: the oracle's forward pass on the ENGINE's features and i-vectors
+        iv = r.DebugGet("ivectors", np.float32).reshape(-1, D)
+        mf = r.DebugGet("mfcc", np.float32).reshape(-1, 40)
+        max_div = max(max_div, float(np.abs(iv - ref["ivectors"]).max()))
+        max_dnet = max(max_dnet, float(np.abs(ll - oracle.nnet_forward(model_np, mf, iv, ref["iv_index"])).max()))
         dec = oracle.decode(model_np, ll, lattice_beam=lb)
         want = oracle.lattice_result(model_np, dec, lb, rc=rc)
         same_oracle += text == want
@@ -244,7 +253,13 @@ def parity_sample(vosk, arch, waves, bench_texts, n, extra_opts=""):
     del recs, m
     audio = sum(len(w) for w in waves[:n]) / 16000.0
     return {"streams": n, "texts_identical_to_oracle_search_and_lattice_chain_on_engine_loglikes": "%d/%d" % (same_oracle, n),
-            "texts_identical_to_bench_run": "%d/%d" % (same_bench, n), "max_abs_loglike_diff_vs_oracle": max_dll, "loglike_tolerance": 1e-3,
+            "texts_identical_to_bench_run": "%d/%d" % (same_bench, n), "loglike_tolerance": 1e-3,
+            "max_abs_loglike_diff_network (oracle TDNN-F on the engine's features and i-vectors)": max_dnet,
+            "max_abs_loglike_diff_whole_front_end (oracle's own features and i-vectors)": max_dll, "streams_over_tolerance_whole_front_end": int(over),
+            "max_abs_ivector_diff": max_div,
+            "note": "a stream goes over 1e-3 end to end only after a frame whose UBM posterior sits on the min_post / top-5 pruning threshold: the fp32 "
+                    "front end and the fp64 oracle then prune differently (as Kaldi's own CPU and GPU feature code do), the i-vector moves by ~2e-4 and "
+                    "decays back; the network itself stays within the tolerance",
             "texts_identical_to_whole_oracle_pipeline (its own log-likelihoods; informational)": "%d/%d" % (same_pipeline, n)}, audio, cpu_s
 
 
