@@ -41,7 +41,8 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model);
  * capacity overflowed (logged; the result may be truncated), [39] lattice-mode results that fell back to the best path,
  * [40] host milliseconds spent by the lattice thread pool, [41] its jobs, [42] its threads, [43] device ms of the lattice
  * pruning launches (timing on), [44] batcher-thread ms spent completing steps, [45] of that, fetching lattices, [46] / [47] bytes the steps copied host-to-device /
- * device-to-host (samples, descriptors, results, lattices).
+ * device-to-host (samples, descriptors, results, lattices), [48..71] the per-phase SM cycles of the slowest lane-launch of each search
+ * tier (1024 / 512 / 256 threads), [72..74] its cycles, [75..77] its largest token count, [78..80] lane-launches per tier.
  * Returns the number written. */
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n);
 void vosk_batch_model_reset_stats(VoskBatchModel *model);

@@ -80,6 +80,7 @@ struct Shared {
     unsigned red_u[(NT / 32)];
     unsigned long long red_ull[(NT / 32)];
     long long phase[8];  // cycles per phase of this CTA (tid 0), flushed to counters[16..23] of the heavy / [24..31] of the light variants
+    long long lphase[8];  // the same for the lane in hand: the slowest lane's go to counters[32 + 8 * tier ..]
     int own[(NT / 32)][2][32];  // per-warp marker arrays of the arc-window owner scan (two windows in flight)
 };
 
@@ -458,6 +459,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
     if (tid == 0 && a.counters) {                     \
         const long long t_ = clock64();               \
         sh.phase[k] += t_ - tph;                      \
+        sh.lphase[k] += t_ - tph;                     \
         tph = t_;                                     \
     }
     unsigned long long cnt_tok = 0, cnt_arc_e = 0, cnt_arc_eps = 0, cnt_new = 0, cnt_stage = 0, cnt_links = 0;  // per-thread profiling counters
@@ -471,6 +473,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
         const LaneDesc ln = a.lanes[l];
         const int ch = ln.channel;
         const long long clk0 = clock64();
+        if (tid == 0)
+            for (int k = 0; k < 8; k++) sh.lphase[k] = 0;
         int max_tok = 0;
         DecChannelState *cs = a.cs + ch;
         const size_t tbase = (size_t)ch * 2 * a.tok_cap;
@@ -874,6 +878,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 atomicMax(a.counters + 5, cyc);
                 atomicMax(a.counters + 6, (unsigned long long)max_tok);
                 atomicAdd(a.counters + 7, 1ull);
+                constexpr int tier = NT >= 1024 ? 0 : NT >= 512 ? 1 : 2;
+                atomicAdd(a.counters + 59 + tier, 1ull);
+                if (cyc >= atomicMax(a.counters + 11 + tier, cyc)) {  // the slowest lane of this tier so far, give or take a race: a profile, not a result
+                    for (int k = 0; k < 8; k++) a.counters[32 + 8 * tier + k] = (unsigned long long)sh.lphase[k];
+                    a.counters[56 + tier] = (unsigned long long)max_tok;
+                }
             }
             if (a.lane_load) a.lane_load[l] = max_tok;  // fed back to the batcher: heavy streams are grouped together
         }

@@ -393,7 +393,7 @@ void Engine::alloc_state() {
     d.log_state = cfg_.debug_capture ? dev_alloc<int>(allocs_, (size_t)C * log_cap_) : nullptr;
     d.log_frame_off = dev_alloc<int>(allocs_, (size_t)C * (max_frames_ + 2), 0);
     d.path = dev_alloc<int>(allocs_, (size_t)C * path_cap_, 0);
-    d.counters = dev_alloc<unsigned long long>(allocs_, 32, 0);
+    d.counters = dev_alloc<unsigned long long>(allocs_, 64, 0);
     d.lattice = cfg_.lattice;
     d.lattice_beam = cfg_.lattice_beam;
     if (cfg_.lattice) {
@@ -565,7 +565,7 @@ void Engine::wait() {
 }
 
 StepStats Engine::stats() {
-    unsigned long long c[32] = {};
+    unsigned long long c[64] = {};
     cudaSetDevice(cfg_.device);
     cudaMemcpy(c, dec_.counters, sizeof c, cudaMemcpyDeviceToHost);
     std::lock_guard<std::mutex> lk(stats_mu_);
@@ -582,6 +582,12 @@ StepStats Engine::stats() {
     s.links = c[9];
     s.lat_arcs = c[10];
     for (int k = 0; k < 16; k++) s.phase[k] = c[16 + k];
+    for (int k = 0; k < 24; k++) s.phase_slowest[k] = c[32 + k];
+    for (int t = 0; t < 3; t++) {
+        s.tier_slowest_cycles[t] = c[11 + t];
+        s.tier_slowest_tokens[t] = c[56 + t];
+        s.tier_lane_launches[t] = c[59 + t];
+    }
     s.lattice_fallbacks = lattice_fallbacks_.load();
     return s;
 }
@@ -607,7 +613,7 @@ void Engine::latency(double *out, bool reset) {
 
 void Engine::reset_stats() {
     cudaSetDevice(cfg_.device);
-    cudaMemset(dec_.counters, 0, 32 * sizeof(unsigned long long));
+    cudaMemset(dec_.counters, 0, 64 * sizeof(unsigned long long));
     std::lock_guard<std::mutex> lk(stats_mu_);
     stats_ = StepStats{};
     lattice_fallbacks_ = 0;

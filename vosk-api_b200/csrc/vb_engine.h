@@ -117,6 +117,8 @@ struct StepStats {
     unsigned long long tok = 0, arc_e = 0, arc_eps = 0, tok_new = 0;
     unsigned long long lane_cycles_sum = 0, lane_cycles_max = 0, max_tokens = 0, lane_launches = 0;
     unsigned long long arcs_staged = 0, links = 0, lat_arcs = 0;
+    unsigned long long phase_slowest[24] = {};  // the same phases for the slowest lane-launch of each search tier (1024 / 512 / 256 threads)
+    unsigned long long tier_slowest_cycles[3] = {}, tier_slowest_tokens[3] = {}, tier_lane_launches[3] = {};
     unsigned long long phase[16] = {};  // search cycles per phase (cutoff, rank, log, gather, insert, closure, finalize, -) of the heavy / light CTAs  // arcs parked below the running cutoff, links logged, lattice arcs kept
     double t_feat = 0, t_ivec = 0, t_nnet = 0, t_dec = 0, t_total = 0;  // device ms (only when timing enabled)
     long long dec_launches = 0, gemm_launches = 0, resample_segments = 0;

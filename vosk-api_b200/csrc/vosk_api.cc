@@ -149,7 +149,7 @@ int vosk_batch_model_samples_per_chunk(VoskBatchModel *model) { return model ? (
 int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
     if (!model || !out) return 0;
     BatchModel *bm = (BatchModel *)model;
-    double v[48] = {0};
+    double v[81] = {0};
     for (size_t i = 0; i < bm->num_engines(); i++) {
         vb::StepStats s = bm->engine(i).stats();
         v[0] += s.audio_seconds; v[1] += s.steps; v[2] += s.lanes; v[3] += s.launches;
@@ -161,8 +161,14 @@ int vosk_batch_model_stats(VoskBatchModel *model, double *out, int n) {
         v[37] += s.resample_segments;
         v[38] += s.truncated; v[39] += s.lattice_fallbacks; v[40] += s.post_ms; v[41] += s.post_jobs; v[42] += bm->engine(i).post_thread_count();
         v[43] += s.t_prune; v[44] += s.host_complete_ms; v[45] += s.host_fetch_ms; v[46] += (double)s.h2d_bytes; v[47] += (double)s.d2h_bytes;
+        for (int k = 0; k < 24; k++) v[48 + k] = std::max(v[48 + k], (double)s.phase_slowest[k]);
+        for (int t = 0; t < 3; t++) {
+            v[72 + t] = std::max(v[72 + t], (double)s.tier_slowest_cycles[t]);
+            v[75 + t] = std::max(v[75 + t], (double)s.tier_slowest_tokens[t]);
+            v[78 + t] += (double)s.tier_lane_launches[t];
+        }
     }
-    int k = n < 48 ? n : 48;
+    int k = n < 81 ? n : 81;
     memcpy(out, v, k * sizeof(double));
     return k;
 }

@@ -34,10 +34,12 @@ for extra in sys.argv[4:]:
         ms, texts = model.RunResident(mat, lengths)
         st = model.Stats()
         cyc = {k[4:]: round(v / 1e6, 1) for k, v in st.items() if k.startswith("cyc_") and v}
+        slow = {k[8:]: round(v / 1e3, 1) for k, v in st.items() if k.startswith("slowest_") and v}
+        slow.update({k: v for k, v in st.items() if k.startswith("lane_launches_")})
         keep = ("steps", "launches", "ms_feat", "ms_ivector", "ms_nnet", "ms_search", "ms_prune", "host_launch_ms", "host_complete_ms", "host_fetch_ms",
                 "post_ms", "post_jobs", "post_threads", "links", "lattice_arcs", "tokens", "arcs_emitting", "tokens_new", "max_tokens_per_frame",
                 "lane_cycles_sum", "lane_cycles_max", "truncated", "lattice_fallbacks")
         print(json.dumps({"options": extra, "slots": slots, "ms": round(ms, 2), "rtfx": round(audio / ms * 1000.0), "audio_s": round(audio, 1),
-                          **{k: round(st[k], 2) for k in keep if k in st}, "Mcycles": cyc,
+                          **{k: round(st[k], 2) for k in keep if k in st}, "Mcycles": cyc, "slowest_lane_kcycles": slow,
                           "conf_below_1": sum(1 for t in texts if '"conf" : 0.' in t)}), flush=True)
     del model

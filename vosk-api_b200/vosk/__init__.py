@@ -79,14 +79,17 @@ class BatchModel(object):
         return _c.vosk_batch_model_samples_per_chunk(self._handle)
 
     def Stats(self):
-        buf = _ffi.new("double[48]")
-        n = _c.vosk_batch_model_stats(self._handle, buf, 48)
+        buf = _ffi.new("double[81]")
+        n = _c.vosk_batch_model_stats(self._handle, buf, 81)
         keys = ["audio_seconds", "steps", "lanes", "launches", "tokens", "arcs_emitting", "arcs_epsilon", "tokens_new",
                 "ms_feat", "ms_ivector", "ms_nnet", "ms_search", "gemm_launches",
                 "lane_cycles_sum", "lane_cycles_max", "max_tokens_per_frame", "lane_launches", "host_launch_ms",
                 "arcs_staged", "links", "lattice_arcs"]
         keys += ["cyc_%s_%s" % (v, ph) for v in ("heavy", "light") for ph in ("cutoff", "rank", "log", "gather", "insert", "closure", "finalize", "x")]
         keys += ["resample_segments", "truncated", "lattice_fallbacks", "post_ms", "post_jobs", "post_threads", "ms_prune", "host_complete_ms", "host_fetch_ms", "h2d_bytes", "d2h_bytes"]
+        keys += ["slowest_%s_%s" % (v, ph) for v in ("t1024", "t512", "t256") for ph in ("cutoff", "rank", "log", "gather", "insert", "closure", "finalize", "x")]
+        keys += ["slowest_cycles_%s" % v for v in ("t1024", "t512", "t256")] + ["slowest_tokens_%s" % v for v in ("t1024", "t512", "t256")]
+        keys += ["lane_launches_%s" % v for v in ("t1024", "t512", "t256")]
         return {k: buf[i] for i, k in enumerate(keys[:n])}
 
     def Latency(self, reset=False):
