@@ -28,6 +28,7 @@ static void apply_option(Config *c, const std::string &k, const std::string &v) 
     else if (k == "device-resample") I(&c->device_resample);
     else if (k == "heavy-tokens") I(&c->heavy_tokens);
     else if (k == "mid-tokens") I(&c->mid_tokens);
+    else if (k == "load-decay") I(&c->load_decay_percent);
     else if (k == "mid-threads") I(&c->mid_threads);
     else if (k == "heavy-threads") I(&c->heavy_threads);
     else if (k == "light-threads") I(&c->light_threads);

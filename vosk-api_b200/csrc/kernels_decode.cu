@@ -31,6 +31,7 @@
 // PruneForwardLinksFinal / PruneForwardLinks / PruneTokensForFrame: backward extra-cost propagation (epsilon links of
 // a frame to their fixed point, then the emitting links into it), links and tokens above lattice_beam dropped, the
 // survivors renumbered and compacted into the raw lattice the host reads.
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 
@@ -42,11 +43,13 @@ namespace {
 #ifndef VB_DEC_LIGHT_PER_SM
 #define VB_DEC_LIGHT_PER_SM 3
 #endif
-#ifndef VB_DEC_SMEM_SLOTS
-#define VB_DEC_SMEM_SLOTS 4096
-#endif
 constexpr int kDecBlocksPerSM = VB_DEC_LIGHT_PER_SM;   // 256-thread variant; the 1024-thread variant (heavy lanes) runs 1 per SM
-constexpr int kSmemSlots = VB_DEC_SMEM_SLOTS;  // level-1 (shared memory) table entries per CTA
+// level-1 (shared memory) table entries per CTA (Ctx::l1_slots, a power of two chosen per launch): as many as the shared memory of an
+// SM allows at the variant's residency (12 bytes per entry beside the log-likelihood row) — one 1024-thread CTA, two 512-thread CTAs
+// or three 256-thread CTAs per SM.  A lane's
+// search runs on one SM and is bounded by that SM's path to L2 (~64 B / clock): every table access kept in shared memory is a 32-byte
+// sector less on that path
+constexpr int kMaxSlots = 16384;
 constexpr unsigned long long kValMax = ~0ull;
 constexpr int kEmpty = -1;
 constexpr int kAltFlag = 0x40000000;  // candidate did not improve its state's best word; kept as a lattice link only
@@ -101,6 +104,7 @@ struct Ctx {
     int *sv_pref, *sv_a0, *sv_src, *win_owner;
     float *sv_cost;
     int tid, warp, lane;
+    int l1_slots;    // level-1 table size of this launch
     bool use_l1;     // level-1 (shared) table enabled for this frame
     unsigned hmask;  // this frame's table window (power of two - 1): the table is empty between frames, so any
                      // power-of-two prefix of it is a valid table; small frames stay L2-resident
@@ -115,26 +119,26 @@ __device__ __forceinline__ int agg_inc(int *counter) {
     return base + __popc(m & lanemask_lt());
 }
 
-// Table slots: [0, kSmemSlots) = shared-memory level, kSmemSlots + g = global level.  A state lives in level 1 iff
+// Table slots: [0, c.l1_slots) = shared-memory level, c.l1_slots + g = global level.  A state lives in level 1 iff
 // a free or matching slot existed within kProbe1 probes at its first insertion; slots are never freed inside a
 // frame, so every later lookup of the same state takes the same decision.
 constexpr int kProbe1 = 16;
 template <int NT>
 __device__ __forceinline__ unsigned long long tab_val(const Ctx<NT> &c, int slot) {
-    return slot < kSmemSlots ? *(volatile unsigned long long *)(c.sval + slot) : __ldcg(c.hval + (slot - kSmemSlots));
+    return slot < c.l1_slots ? *(volatile unsigned long long *)(c.sval + slot) : __ldcg(c.hval + (slot - c.l1_slots));
 }
 template <int NT>
 __device__ __forceinline__ int tab_key(const Ctx<NT> &c, int slot) {
-    return slot < kSmemSlots ? *(volatile int *)(c.skey + slot) : __ldcg(c.hkey + (slot - kSmemSlots));
+    return slot < c.l1_slots ? *(volatile int *)(c.skey + slot) : __ldcg(c.hkey + (slot - c.l1_slots));
 }
 // after the winners are known the key field of a level-1 slot is reused for the token index
 template <int NT>
 __device__ __forceinline__ void tab_set_tok(const Ctx<NT> &c, int slot, int idx) {
-    if (slot < kSmemSlots) c.skey[slot] = idx; else c.htok[slot - kSmemSlots] = idx;
+    if (slot < c.l1_slots) c.skey[slot] = idx; else c.htok[slot - c.l1_slots] = idx;
 }
 template <int NT>
 __device__ __forceinline__ int tab_tok(const Ctx<NT> &c, int slot) {
-    return slot < kSmemSlots ? *(volatile int *)(c.skey + slot) : __ldcg(c.htok + (slot - kSmemSlots));
+    return slot < c.l1_slots ? *(volatile int *)(c.skey + slot) : __ldcg(c.htok + (slot - c.l1_slots));
 }
 
 // claims / finds the table slot of a state and folds pk into its best word; returns the slot (-1: table full)
@@ -142,7 +146,7 @@ template <int NT>
 __device__ __forceinline__ int table_insert(Ctx<NT> &c, int state, unsigned long long pk, unsigned long long *old_out) {
     const unsigned hash = ((unsigned)state * 2654435761u) >> 7;
     if (c.use_l1) {
-        unsigned h = hash & (kSmemSlots - 1);
+        unsigned h = hash & (c.l1_slots - 1);
 #pragma unroll 1
         for (int p = 0; p < kProbe1; p++) {
             int prev = atomicCAS(c.skey + h, kEmpty, state);
@@ -150,7 +154,7 @@ __device__ __forceinline__ int table_insert(Ctx<NT> &c, int state, unsigned long
                 *old_out = atomicMin(c.sval + h, pk);
                 return (int)h;
             }
-            h = (h + 1) & (kSmemSlots - 1);
+            h = (h + 1) & (c.l1_slots - 1);
         }
     }
     const unsigned mask = c.hmask;
@@ -166,7 +170,7 @@ __device__ __forceinline__ int table_insert(Ctx<NT> &c, int state, unsigned long
         }
     }
     *old_out = atomicMin(c.hval + g, pk);
-    return kSmemSlots + (int)g;
+    return c.l1_slots + (int)g;
 }
 
 // 0: pk became the state's best word (a token candidate); kAltFlag: not the best, but within lattice_beam of the best
@@ -413,9 +417,9 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
             const int z = c.cand[i].z;
             const int slot = z & ~kAltFlag;
             if (z < 0) continue;
-            if (slot >= kSmemSlots) {
-                c.hkey[slot - kSmemSlots] = kEmpty;
-                c.hval[slot - kSmemSlots] = kValMax;
+            if (slot >= c.l1_slots) {
+                c.hkey[slot - c.l1_slots] = kEmpty;
+                c.hval[slot - c.l1_slots] = kValMax;
             } else {  // level 1 is cleared slot by slot too: a full sweep per frame costs more than the frame's few entries
                 c.skey[slot] = kEmpty;
                 c.sval[slot] = kValMax;
@@ -423,7 +427,7 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
         }
     }
     if (c.sh.error == 1 || c.sh.error == 2)
-        for (int i = c.tid; i < kSmemSlots; i += NT) {
+        for (int i = c.tid; i < c.l1_slots; i += NT) {
             c.skey[i] = kEmpty;
             c.sval[i] = kValMax;
         }
@@ -433,15 +437,16 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
 
 template <int NT>
 __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 2 : 1) decode_kernel(DecArgs a) {
-    extern __shared__ __align__(16) float s_ll[];  // [npdf floats | level-1 values u64[kSmemSlots] | level-1 keys int[kSmemSlots]]
+    extern __shared__ __align__(16) float s_ll[];  // [npdf floats | level-1 values u64[l1_slots] | level-1 keys int[l1_slots]]
+    const int l1_slots = a.l1_slots;
     __shared__ Shared<NT> sh;
     __shared__ int s_lane;
     const int tid = threadIdx.x;
     const size_t g = (size_t)a.scratch_base + blockIdx.x;
     const int nwin_cap = a.cand_cap / 32 + 2;
     unsigned long long *s_val = reinterpret_cast<unsigned long long *>(s_ll + ((a.out_node.dim + 3) & ~3));
-    int *s_key = reinterpret_cast<int *>(s_val + kSmemSlots);
-    for (int i = tid; i < kSmemSlots; i += NT) {
+    int *s_key = reinterpret_cast<int *>(s_val + l1_slots);
+    for (int i = tid; i < l1_slots; i += NT) {
         s_key[i] = kEmpty;
         s_val[i] = kValMax;
     }
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
           a.rank + g * a.tok_cap,
           a.sv_pref + g * a.tok_cap, a.sv_a0 + g * a.tok_cap, a.sv_src + g * a.tok_cap, a.win_owner + g * nwin_cap,
           a.sv_cost + g * a.tok_cap,
-          tid, tid >> 5, tid & 31, true, (unsigned)a.hash_size - 1};
+          tid, tid >> 5, tid & 31, l1_slots, true, (unsigned)a.hash_size - 1};
     long long tph = 0;
     if (tid == 0)
         for (int k = 0; k < 8; k++) sh.phase[k] = 0;
@@ -610,7 +615,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 unsigned want = 3u * (unsigned)n_arcs + 1024u, win = 4096;
                 while (win < want && win < (unsigned)a.hash_size) win <<= 1;
                 c.hmask = min(win, (unsigned)a.hash_size) - 1;
-                c.use_l1 = n_arcs <= kSmemSlots + kSmemSlots / 2;  // heavy frames would only collide in level 1
+                c.use_l1 = n_arcs <= c.l1_slots + c.l1_slots / 2;  // heavy frames would only collide in level 1
             }
             if (n_arcs > a.cand_cap) {  // more emitting arcs than candidate slots: flag and truncate
                 if (tid == 0) sh.error = 6;
@@ -1268,7 +1273,6 @@ extern "C" int vbk_decode_max_grid(int device) {
 extern "C" cudaError_t vbk_decode(const DecArgs *a, int heavy, cudaStream_t s) {
     const int n = a->lane_end - a->lane_begin;
     if (n <= 0) return cudaSuccess;
-    int smem = ((a->out_node.dim + 3) & ~3) * 4 + kSmemSlots * 12;
     static int sms[16] = {};
     // the opt-in shared-memory size is a per-device function attribute: set it once per (variant, device, size)
     static int done[3][16] = {};
@@ -1281,6 +1285,29 @@ extern "C" cudaError_t vbk_decode(const DecArgs *a, int heavy, cudaStream_t s) {
     if (grid > n) grid = n;
     if (grid > a->grid - a->scratch_base) grid = a->grid - a->scratch_base;
     if (grid <= 0) return cudaErrorInvalidValue;
+    // level-1 table: the largest power of two that keeps the variant's residency (1 / 2 / 3 CTAs per SM) within the SM's shared memory
+    static int slots_for[3][16] = {};
+    static int slots_dim[3][16] = {};
+    if (!slots_for[v][dev] || slots_dim[v][dev] != a->out_node.dim) {
+        cudaFuncAttributes fa{};
+        cudaError_t e = v == 2 ? cudaFuncGetAttributes(&fa, decode_kernel<1024>) : v == 1 ? cudaFuncGetAttributes(&fa, decode_kernel<512>) : cudaFuncGetAttributes(&fa, decode_kernel<256>);
+        if (e != cudaSuccess) return e;
+        int sm_bytes = 0, cta_max = 0;
+        cudaDeviceGetAttribute(&sm_bytes, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        cudaDeviceGetAttribute(&cta_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const int per_sm = v == 2 ? 1 : v == 1 ? 2 : kDecBlocksPerSM;
+        const int ll_bytes = ((a->out_node.dim + 3) & ~3) * 4;
+        long long avail = (long long)sm_bytes / per_sm - 1024 - (long long)fa.sharedSizeBytes - ll_bytes;
+        avail = std::min<long long>(avail, (long long)cta_max - (long long)fa.sharedSizeBytes - ll_bytes);
+        int slots = 1024;
+        while (slots * 2 <= kMaxSlots && (long long)slots * 2 * 12 <= avail) slots *= 2;
+        if ((long long)slots * 12 > avail) return cudaErrorInvalidConfiguration;
+        slots_for[v][dev] = slots;
+        slots_dim[v][dev] = a->out_node.dim;
+    }
+    DecArgs args = *a;
+    args.l1_slots = slots_for[v][dev];
+    const int smem = ((a->out_node.dim + 3) & ~3) * 4 + args.l1_slots * 12;
     if (done[v][dev] < smem) {
         cudaError_t e = v == 2   ? cudaFuncSetAttribute(decode_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
                         : v == 1 ? cudaFuncSetAttribute(decode_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
@@ -1288,9 +1315,9 @@ extern "C" cudaError_t vbk_decode(const DecArgs *a, int heavy, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         done[v][dev] = smem;
     }
-    if (v == 2) decode_kernel<1024><<<grid, 1024, smem, s>>>(*a);
-    else if (v == 1) decode_kernel<512><<<grid, 512, smem, s>>>(*a);
-    else decode_kernel<256><<<grid, 256, smem, s>>>(*a);
+    if (v == 2) decode_kernel<1024><<<grid, 1024, smem, s>>>(args);
+    else if (v == 1) decode_kernel<512><<<grid, 512, smem, s>>>(args);
+    else decode_kernel<256><<<grid, 256, smem, s>>>(args);
     return cudaGetLastError();
 }
 

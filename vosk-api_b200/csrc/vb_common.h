@@ -57,6 +57,7 @@ struct Config {
     int heavy_tokens = 2500;    // lanes above this many tokens per frame get the 1024-thread search CTAs,
     int mid_tokens = 900;       // ... lanes above this the 512-thread ones, the rest 256
     int heavy_threads = 1024, mid_threads = 512, light_threads = 256;
+    int load_decay_percent = 80;  // a stream's load estimate = max(last chunk's token peak, this share of the previous estimate)
     float endpoint_rule5_seconds = 20.0f;  // reset_on_endpoint [REF src/batch_model.cc:72] with Kaldi's default endpoint rules and the
                                 // reference's empty silence-phone list: only rule 5 (utterance length) can fire; 0 = never
     // Silence endpointing (Kaldi OnlineEndpointConfig rules 1-4), active when model.conf names --endpoint.silence-phones:

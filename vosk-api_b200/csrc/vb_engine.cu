@@ -504,6 +504,7 @@ std::shared_ptr<Stream> Engine::open_stream() {
     auto s = std::make_shared<Stream>();
     std::lock_guard<std::mutex> lk(mu_);
     s->id = next_id_++;
+    s->load = cfg_.mid_tokens + 1;  // no history yet: the middle tier (a first chunk with speech in it is no light lane)
     return s;
 }
 
@@ -1010,7 +1011,9 @@ void Engine::complete_step(Slot &sl) {
     cudaStream_t st = sl.stream;
     VB_CUDA_CHECK(cudaEventSynchronize(sl.done));
     const auto host_t0 = std::chrono::steady_clock::now();
-    for (int i = 0; i < L; i++) lanes[i].s->load = sl.h_load[i];
+    // load feedback for the tiering of the stream's next chunks: the largest token count of this chunk, or what is left of an
+    // earlier peak (token counts swing between chunks, and a lane that lands in too small a tier is the step's critical path)
+    for (int i = 0; i < L; i++) lanes[i].s->load = std::max(sl.h_load[i], (int)((long long)lanes[i].s->load * cfg_.load_decay_percent / 100));
     {
         const auto now = std::chrono::steady_clock::now();
         std::lock_guard<std::mutex> lk(stats_mu_);
@@ -1272,6 +1275,7 @@ double Engine::run_resident(const int16_t *d_audio, int num_streams, int stride,
         ss[i]->id = (uint64_t)i;
         ss[i]->resident = true;
         ss[i]->resident_row = row;
+        ss[i]->load = cfg_.mid_tokens + 1;
         BestPath *slot = pass == passes - 1 ? &res[row] : nullptr;
         ss[i]->on_result = [slot, row, pass, this](const BestPath &bp) {
             if (slot) *slot = bp;

@@ -215,6 +215,7 @@ struct DecArgs {
     // [scratch_base + blockIdx.x]; a step issues up to two launches (1024-thread CTAs for its heavy lanes, 256 for the rest)
     int lane_begin, lane_end, scratch_base;
     int *queue;
+    int l1_slots;            // level-1 (shared memory) table entries of this launch (set by vbk_decode)
 };
 
 extern "C" {
