@@ -94,45 +94,41 @@ struct MEdge {  // arc of the word-aligned lattice as MinimumBayesRisk sees it
 
 // open-addressing table hash -> id (entries are never removed; equality is the caller's)
 struct IdTable {
-    std::vector<uint64_t> hash;
-    std::vector<int> id;
+    struct Slot {
+        uint64_t hash;
+        int id;  // -1 = free
+    };
+    std::vector<Slot> slots;  // (hash and id side by side: one cache line per probe)
     size_t used = 0, mask = 0;
     void reset(size_t cap_pow2) {
-        if (hash.size() != cap_pow2) {
-            hash.assign(cap_pow2, 0);
-            id.assign(cap_pow2, -1);
-        } else {
-            std::fill(id.begin(), id.end(), -1);
-        }
+        if (slots.size() != cap_pow2) slots.assign(cap_pow2, Slot{0, -1});
+        else std::fill(slots.begin(), slots.end(), Slot{0, -1});
         mask = cap_pow2 - 1;
         used = 0;
     }
     template <class Eq>
     int find(uint64_t h, Eq eq) const {
         for (size_t i = h & mask;; i = (i + 1) & mask) {
-            if (id[i] < 0) return -1;
-            if (hash[i] == h && eq(id[i])) return id[i];
+            const Slot &s = slots[i];
+            if (s.id < 0) return -1;
+            if (s.hash == h && eq(s.id)) return s.id;
         }
     }
     void insert(uint64_t h, int v) {
-        if ((used + 1) * 2 > hash.size()) grow();
+        if ((used + 1) * 2 > slots.size()) grow();
         size_t i = h & mask;
-        while (id[i] >= 0) i = (i + 1) & mask;
-        hash[i] = h;
-        id[i] = v;
+        while (slots[i].id >= 0) i = (i + 1) & mask;
+        slots[i] = Slot{h, v};
         used++;
     }
     void grow() {
-        std::vector<uint64_t> oh;
-        std::vector<int> oi;
-        oh.swap(hash);
-        oi.swap(id);
-        hash.assign(oh.size() * 2, 0);
-        id.assign(oi.size() * 2, -1);
-        mask = hash.size() - 1;
+        std::vector<Slot> old;
+        old.swap(slots);
+        slots.assign(old.size() * 2, Slot{0, -1});
+        mask = slots.size() - 1;
         used = 0;
-        for (size_t k = 0; k < oi.size(); k++)
-            if (oi[k] >= 0) insert(oh[k], oi[k]);
+        for (const Slot &s : old)
+            if (s.id >= 0) insert(s.hash, s.id);
     }
 };
 inline uint64_t mix(uint64_t h, uint64_t v) {
@@ -144,50 +140,46 @@ inline uint64_t mix(uint64_t h, uint64_t v) {
 // (hash-consed from the root: equal content = equal id); the strings built while arcs are followed are plain appended
 // nodes (no lookup), compared by content where it matters.
 struct Repo {
-    std::vector<int> parent, label, depth;
-    std::vector<char> canon;
+    struct Node {
+        int parent, label, depth, canon;
+    };
+    std::vector<Node> nodes;  // one record per string node: the walks touch one cache line per step
     IdTable tab;
     std::vector<int> tmp;
     void reset() {
-        parent.assign(1, -1);
-        label.assign(1, 0);
-        depth.assign(1, 0);
-        canon.assign(1, 1);
+        nodes.assign(1, Node{-1, 0, 0, 1});
         tab.reset(1 << 12);
     }
     int append(int id, int lab) {
-        const int k = (int)parent.size();
-        parent.push_back(id);
-        label.push_back(lab);
-        depth.push_back(depth[id] + 1);
-        canon.push_back(0);
+        const int k = (int)nodes.size();
+        nodes.push_back(Node{id, lab, nodes[id].depth + 1, 0});
         return k;
     }
     int succ(int id, int lab) {  // canonical successor of a canonical string
         const uint64_t h = mix((uint64_t)(uint32_t)id, (uint64_t)(uint32_t)lab);
-        const int f = tab.find(h, [&](int k) { return parent[k] == id && label[k] == lab; });
+        const int f = tab.find(h, [&](int k) { return nodes[k].parent == id && nodes[k].label == lab; });
         if (f >= 0) return f;
         const int k = append(id, lab);
-        canon[k] = 1;
+        nodes[k].canon = 1;
         tab.insert(h, k);
         return k;
     }
     // a node of x's ancestry that spells the longest common prefix of x and y (by content)
     int common_prefix(int x, int y) const {
-        while (depth[x] > depth[y]) x = parent[x];
-        while (depth[y] > depth[x]) y = parent[y];
+        while (nodes[x].depth > nodes[y].depth) x = nodes[x].parent;
+        while (nodes[y].depth > nodes[x].depth) y = nodes[y].parent;
         int ans = x;
         while (x != y) {
-            if (label[x] != label[y]) ans = parent[x];
-            x = parent[x];
-            y = parent[y];
+            if (nodes[x].label != nodes[y].label) ans = nodes[x].parent;
+            x = nodes[x].parent;
+            y = nodes[y].parent;
         }
         return ans;
     }
     int remove_prefix(int id, int n) {  // canonical id of the string without its first n symbols
-        if (n == 0 && canon[id]) return id;
+        if (n == 0 && nodes[id].canon) return id;
         tmp.clear();
-        for (int k = id; depth[k] > n; k = parent[k]) tmp.push_back(label[k]);
+        for (int k = id; nodes[k].depth > n; k = nodes[k].parent) tmp.push_back(nodes[k].label);
         int r = 0;
         for (size_t i = tmp.size(); i-- > 0;) r = succ(r, tmp[i]);
         return r;
@@ -196,25 +188,25 @@ struct Repo {
         if (y == 0) return x;
         if (x == 0) return y;
         tmp.clear();
-        for (int k = y; k > 0; k = parent[k]) tmp.push_back(label[k]);
+        for (int k = y; k > 0; k = nodes[k].parent) tmp.push_back(nodes[k].label);
         for (size_t i = tmp.size(); i-- > 0;) x = append(x, tmp[i]);
         return x;
     }
     void to_vec(int id, std::vector<int> *out) const {
         const size_t base = out->size();
-        out->resize(base + depth[id]);
-        for (int k = id, i = depth[id]; k > 0; k = parent[k]) (*out)[base + --i] = label[k];
+        out->resize(base + nodes[id].depth);
+        for (int k = id, i = nodes[id].depth; k > 0; k = nodes[k].parent) (*out)[base + --i] = nodes[k].label;
     }
     // LatticeDeterminizerPruned::Compare on strings: the shorter one is better, then the lexicographically larger (sic)
     int compare(int x, int y) const {
         if (x == y) return 0;
-        if (depth[x] > depth[y]) return -1;
-        if (depth[x] < depth[y]) return 1;
+        if (nodes[x].depth > nodes[y].depth) return -1;
+        if (nodes[x].depth < nodes[y].depth) return 1;
         int res = 0;  // decided by the first differing symbol = the mismatch closest to the root
         while (x != y) {
-            if (label[x] != label[y]) res = label[x] < label[y] ? -1 : 1;
-            x = parent[x];
-            y = parent[y];
+            if (nodes[x].label != nodes[y].label) res = nodes[x].label < nodes[y].label ? -1 : 1;
+            x = nodes[x].parent;
+            y = nodes[y].parent;
         }
         return res;
     }
@@ -314,7 +306,7 @@ struct Workspace {
     IdTable tup_tab;
     std::vector<int> nin, nout, remap, stack;
     // mbr
-    std::vector<double> alpha, alpha_dash, beta_dash, post;
+    std::vector<double> alpha, alpha_dash, beta_dash, post, mbr_cq, mbr_m12a, mbr_m12b, mbr_vala, mbr_valb;
     std::vector<char> b_arc;
     std::vector<int> lo, hi;
 };
@@ -629,7 +621,7 @@ class Determinizer {
             }
             pre = repo_.common_prefix(pre, e[i].str);
         }
-        const int plen = repo_.depth[pre];
+        const int plen = repo_.nodes[pre].depth;
         for (int i = 0; i < n; i++) {
             e[i].g -= bg;
             e[i].a -= ba;
@@ -1461,37 +1453,83 @@ std::vector<WordSpan> mbr_one_best(Workspace &ws, LatticeStats *stats) {
             ad1[0] = 0.0;
             for (int q = 1; q <= Q; q++) ad1[q] = ad1[q - 1] + (r[q] == 0 ? 0.0 : 1.0);
         }
+        // c(q) = l(eps, r(q)): what skipping reference position q costs
+        std::vector<double> &cq = ws.mbr_cq, &m12a = ws.mbr_m12a, &m12b = ws.mbr_m12b, &vala = ws.mbr_vala, &valb = ws.mbr_valb;
+        cq.resize(W);
+        m12a.resize(W);
+        m12b.resize(W);
+        vala.resize(W);
+        valb.resize(W);
+        for (int q = 1; q <= Q; q++) cq[q] = r[q] == 0 ? 0.0 : 1.0;
+        // One arc's row alpha_dash_arc(.) in three passes: the two candidates that do not depend on the row itself (a1: substitute /
+        // match, a2: insert the arc's word) for all q — independent iterations; then the chain a3(q) = row(q-1) + c(q), which is the
+        // only serial part; then the weighted sum into the node.  Two arcs into the same node run their chains side by side.  Every
+        // operation and its order per element are those of the plain loop (sausages.cc lines 9-12 of the paper's algorithm).
+        auto candidates = [&](const MbrArc &arc, double *m12, char *bk) {
+            const double *ads = &alpha_dash[(size_t)arc.start * W];
+            const int w_a = arc.word;
+            const double l_eps = w_a == 0 ? 0.0 : kPen;  // l(w_a, eps, true)
+            for (int q = 1; q <= Q; q++) {
+                const double a1 = ads[q - 1] + (w_a == r[q] ? 0.0 : 1.0), a2 = ads[q] + l_eps;
+                const bool one = a1 <= a2;
+                m12[q] = one ? a1 : a2;
+                bk[q] = one ? 1 : 2;
+            }
+            return ads[0] + l_eps;
+        };
         for (int n = 2; n <= N; n++) {
+            LATP(10);
             double alpha_n = -kInfD;
             for (int k = pre_off[n]; k < pre_off[n + 1]; k++) alpha_n = log_add(alpha_n, alpha[arcs[k].start] + arcs[k].loglike);
             alpha[n] = alpha_n;
             double *adn = &alpha_dash[(size_t)n * W];
-            for (int k = pre_off[n]; k < pre_off[n + 1]; k++) {
-                const MbrArc &arc = arcs[k];
-                const int w_a = arc.word;
-                const double *ads = &alpha_dash[(size_t)arc.start * W];
-                const double p = std::exp(alpha[arc.start] + arc.loglike - alpha_n);
-                post[k] = p;
-                const double l_eps = w_a == 0 ? 0.0 : kPen;  // l(w_a, eps, true)
-                double prev = ads[0] + l_eps;
-                adn[0] += p * prev;
-                // the back-pointers b_arc(q) of this arc (lines 15-18 of the backward pass recompute exactly these minima)
-                char *bk = &b_all[(size_t)k * W];
+            int k = pre_off[n];
+            const int kend = pre_off[n + 1];
+            for (; k + 1 < kend; k += 2) {
+                const double pa = std::exp(alpha[arcs[k].start] + arcs[k].loglike - alpha_n);
+                const double pb = std::exp(alpha[arcs[k + 1].start] + arcs[k + 1].loglike - alpha_n);
+                post[k] = pa;
+                post[k + 1] = pb;
+                char *bka = &b_all[(size_t)k * W], *bkb = &b_all[(size_t)(k + 1) * W];
+                double prev_a = candidates(arcs[k], m12a.data(), bka), prev_b = candidates(arcs[k + 1], m12b.data(), bkb);
+                vala[0] = prev_a;
+                valb[0] = prev_b;
                 for (int q = 1; q <= Q; q++) {
-                    const int rq = r[q];
-                    const double a1 = ads[q - 1] + (w_a == rq ? 0.0 : 1.0), a2 = ads[q] + l_eps, a3 = prev + (rq == 0 ? 0.0 : 1.0);
-                    const bool one = a1 <= a2;
-                    const double m12 = one ? a1 : a2;
-                    const bool three = !(m12 <= a3);
-                    prev = three ? a3 : m12;
-                    bk[q] = three ? 3 : (one ? 1 : 2);
-                    adn[q] += p * prev;
+                    const double c = cq[q];
+                    const double a3a = prev_a + c, a3b = prev_b + c;
+                    const double ma = m12a[q], mb = m12b[q];
+                    const bool ta = !(ma <= a3a), tb = !(mb <= a3b);
+                    prev_a = ta ? a3a : ma;
+                    prev_b = tb ? a3b : mb;
+                    vala[q] = prev_a;
+                    valb[q] = prev_b;
+                    bka[q] = ta ? 3 : bka[q];
+                    bkb[q] = tb ? 3 : bkb[q];
                 }
+                for (int q = 0; q <= Q; q++) adn[q] += pa * vala[q];
+                for (int q = 0; q <= Q; q++) adn[q] += pb * valb[q];
+            }
+            if (k < kend) {
+                const double pa = std::exp(alpha[arcs[k].start] + arcs[k].loglike - alpha_n);
+                post[k] = pa;
+                char *bka = &b_all[(size_t)k * W];
+                double prev_a = candidates(arcs[k], m12a.data(), bka);
+                vala[0] = prev_a;
+                for (int q = 1; q <= Q; q++) {
+                    const double a3a = prev_a + cq[q];
+                    const double ma = m12a[q];
+                    const bool ta = !(ma <= a3a);
+                    prev_a = ta ? a3a : ma;
+                    vala[q] = prev_a;
+                    bka[q] = ta ? 3 : bka[q];
+                }
+                for (int q = 0; q <= Q; q++) adn[q] += pa * vala[q];
             }
         }
         // ---- backward ----
         beta_dash[(size_t)N * W + Q] = 1.0;
         for (int n = N; n >= 2; n--) {
+            LATP(11);
             const double *bdn = &beta_dash[(size_t)n * W];
             for (int k = pre_off[n]; k < pre_off[n + 1]; k++) {
                 const MbrArc &arc = arcs[k];
