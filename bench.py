@@ -206,7 +206,7 @@ def run_oracle_sample(n_streams, threads):
     return audio, time.perf_counter() - t0
 
 
-def parity_sample(vosk, arch, waves, bench_texts, n, extra_opts=""):
+def parity_sample(vosk, arch, waves, bench_texts, n, extra_opts="", acoustic_scale=None):
     """n of the bench's own streams against the CPU oracle, and the oracle's single-core speed on them.  The streams run
     once more through a small engine instance with the test taps on: (1) its text equals the bench run's (a result does not
     depend on the batch), (2) the ORACLE's search + lattice chain on the engine's log-likelihoods gives the identical text,
@@ -245,7 +245,8 @@ def parity_sample(vosk, arch, waves, bench_texts, n, extra_opts=""):
         mf = r.DebugGet("mfcc", np.float32).reshape(-1, 40)
         max_div = max(max_div, float(np.abs(iv - ref["ivectors"]).max()))
         max_dnet = max(max_dnet, float(np.abs(ll - oracle.nnet_forward(model_np, mf, iv, ref["iv_index"])).max()))
-        dec = oracle.decode(model_np, ll, lattice_beam=lb)
+        # (acoustic-scale option: the search sees scale * log-likelihood, one fp32 product)
+        dec = oracle.decode(model_np, ll if acoustic_scale is None else (np.float32(acoustic_scale) * ll).astype(np.float32), lattice_beam=lb)
         want = oracle.lattice_result(model_np, dec, lb, rc=rc)
         same_oracle += text == want
         same_bench += bench_texts is None or text == bench_texts[i]
@@ -588,6 +589,29 @@ def main():
                 extras[name], _ = resident_leg(vosk, mdir, opts + "," + o, audio_mat, lengths, 1, max(2, a.steps // 2))
             except Exception as e:  # the extras never take the headline line down
                 extras[name] = {"error": str(e)[:200]}
+        # a denser search frontier (SURVEY.md section 8d calls 3-7 k tokens per frame typical; the random-init network's posteriors are
+        # peaky): the log-likelihoods are flattened by acoustic-scale 0.5, max-active 7000 binds on the heavy frames
+        try:
+            n_d = min(256, a.streams)
+            dopts = ("num-channels=%d,max-batch-size=%d,max-seconds=18,acoustic-scale=0.5,log-tokens-per-frame=7168,log-links-per-frame=16384,"
+                     "lat-link-cap=262144,lat-tok-cap=131072" % (n_d, n_d))
+            dleg, dtexts = resident_leg(vosk, mdir, dopts, audio_mat[:n_d], lengths[:n_d], 1, 2)
+            dm = vosk.BatchModel(mdir, options=dopts)
+            dm.SetTiming(True)
+            dm.SetSlots(1)
+            dm.RunResident(audio_mat[:n_d], lengths[:n_d])
+            dser = dm.Stats()
+            del dm
+            droofs, _ = stage_rooflines(dser, lengths[:n_d], "small", peaks)
+            dframes = sum((int(1 + (n - 400) // 160) + 2) // 3 for n in lengths[:n_d])
+            dleg.update({"streams": n_d, "tokens_per_frame": dser["tokens"] / dframes, "arcs_per_frame": (dser["arcs_emitting"] + dser["arcs_epsilon"]) / dframes,
+                         "max_tokens_in_a_frame": dser["max_tokens_per_frame"], "roofline_search": droofs.get("search"), "roofline_lattice_prune": droofs.get("lattice_prune")})
+            if not a.no_cpu_baseline:
+                dps, _, _ = parity_sample(vosk, "small", waves, dtexts, 2, dopts.split("max-seconds=18,")[1], acoustic_scale=0.5)
+                dleg["parity_sample"] = {k: v for k, v in dps.items() if "oracle_search" in k or "bench_run" in k or k == "streams"}
+            extras["dense_frontier (acoustic-scale=0.5)"] = dleg
+        except Exception as e:
+            extras["dense_frontier (acoustic-scale=0.5)"] = {"error": str(e)[:300]}
         try:
             partial_latency = latency_pass(vosk, mdir, a.latency_streams, a.latency_seconds)
         except Exception as e:

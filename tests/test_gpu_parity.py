@@ -464,12 +464,11 @@ def test_odd_model_dimensions_decode_like_the_oracle(model_root, oracle_lib):
     del recs, m
 
 
-@pytest.mark.parametrize("env", [{}, {"VB_TC_MODE": "2"}, {"VB_TC_PERSIST": "1"}, {"VB_TC_PERSIST": "1", "VB_TC_BN_CAP": "80"}])
+@pytest.mark.parametrize("env", [{}, {"VB_TC_MODE": "2"}])
 def test_gemm_kernels_against_fp64(env):
     """K2 in isolation (vosk_b200_gemm_selftest: random A / W, one lane, fp64 reference on the host): the default fp16 hi/lo
-    operand split, the TF32 split (tensor-cores=2), and the experimental persistent kernel with one and with two accumulator
-    sets — shapes of the small architecture plus one with more tiles than SMs.  The switches are read once per process, hence
-    the subprocess."""
+    operand split and the TF32 split (tensor-cores=2) — shapes of the small architecture plus one with more tiles than SMs.  The
+    switch is read once per process, hence the subprocess."""
     import json
     import os
     import subprocess

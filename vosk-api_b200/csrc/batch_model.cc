@@ -76,6 +76,10 @@ BatchModel::BatchModel(const std::string &model_dir, const std::string &options)
         if (kv.first == "devices") devices = kv.second;
         apply_option(&cfg_, kv.first, kv.second);
     }
+    // tensor-cores: 1 = fp16 hi/lo operand split (default), 2 = TF32 hi/lo split — two operand formats of the one tcgen05 kernel.
+    // 0 selects the plain fp32 FFMA kernel that the parity tests use as an arithmetic reference: only with the test taps on.
+    if (cfg_.use_tensor_cores < 0 || cfg_.use_tensor_cores > 2 || (cfg_.use_tensor_cores == 0 && !cfg_.debug_capture))
+        throw std::runtime_error("tensor-cores must be 1 or 2 (0, the fp32 reference kernel, needs debug-capture=1)");
     std::vector<int> devs;
     if (devices == "all") {
         int n = 0;

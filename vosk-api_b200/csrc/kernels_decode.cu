@@ -123,6 +123,7 @@ __device__ __forceinline__ int agg_inc(int *counter) {
 // a free or matching slot existed within kProbe1 probes at its first insertion; slots are never freed inside a
 // frame, so every later lookup of the same state takes the same decision.
 constexpr int kProbe1 = 16;
+constexpr int kSmallRound = 32;   // closure rounds of at most this many entries are left to one warp
 template <int NT>
 __device__ __forceinline__ unsigned long long tab_val(const Ctx<NT> &c, int slot) {
     return slot < c.l1_slots ? *(volatile unsigned long long *)(c.sval + slot) : __ldcg(c.hval + (slot - c.l1_slots));
@@ -208,8 +209,8 @@ __device__ float block_min(Ctx<NT> &c, const float *cost, int n, int *arg) {
     for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (c.lane == 0) c.sh.red_ull[c.warp] = m;
     __syncthreads();
-    m = c.sh.red_ull[0];
-    for (int w = 1; w < (NT / 32); w++) m = min(m, c.sh.red_ull[w]);
+    m = c.lane < (NT / 32) ? c.sh.red_ull[c.lane] : kValMax;  // (one entry per lane and a shuffle reduction, not NT / 32 loads per thread)
+    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
     __syncthreads();
     *arg = (int)(unsigned)m;
     return unord((unsigned)(m >> 32));
@@ -292,8 +293,8 @@ __device__ float get_cutoff(Ctx<NT> &c, const float *cost, int n, float *adaptiv
     for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     if (c.lane == 0) c.sh.red_ull[c.warp] = tot;
     __syncthreads();
-    tot = 0;
-    for (int w = 0; w < (NT / 32); w++) tot += c.sh.red_ull[w];
+    tot = c.lane < (NT / 32) ? c.sh.red_ull[c.lane] : 0ull;
+    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     __syncthreads();
     const int n_lt = (int)(tot >> 32), n_le = (int)(unsigned)tot;
     if (n > a.max_active && n_lt > a.max_active) {
@@ -323,28 +324,44 @@ __device__ int closure(Ctx<NT> &c, float cutoff, unsigned long long *arcs_seen) 
     const DecArgs &a = c.a;
     int lo = 0, hi = min(c.sh.n_work, a.cand_cap);
     __syncthreads();
-    while (lo < hi) {
-        for (int w = lo + c.tid; w < hi; w += NT) {
-            const int i = c.work[w];
-            const int4 cd = c.cand[i];
-            const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
-            const float cost = unord((unsigned)cd.y);
-            if (cost < cutoff && tab_val(c, cd.z) == pk) {
-                const int s = c.cand_next[i];
-                const int a0 = __ldg(&a.g.state_arcs[s].y), a1 = __ldg(&a.g.state_arcs[s + 1].x);
-                *arcs_seen += (unsigned)(a1 - a0);
-                for (int arc = a0; arc < a1; arc++) {
-                    const int4 av = __ldg(a.g.arcs + arc);
-                    const float tot = cost + __int_as_float(av.x);
-                    if (tot < cutoff) relax(c, av.y, pack(tot, arc), i, (av.w & kNextHasEps) != 0);
-                }
+    auto expand = [&](int w) {
+        const int i = c.work[w];
+        const int4 cd = c.cand[i];
+        const unsigned long long pk = ((unsigned long long)(unsigned)cd.y << 32) | (unsigned)cd.x;
+        const float cost = unord((unsigned)cd.y);
+        if (cost < cutoff && tab_val(c, cd.z) == pk) {
+            const int s = c.cand_next[i];
+            const int a0 = __ldg(&a.g.state_arcs[s].y), a1 = __ldg(&a.g.state_arcs[s + 1].x);
+            *arcs_seen += (unsigned)(a1 - a0);
+            for (int arc = a0; arc < a1; arc++) {
+                const int4 av = __ldg(a.g.arcs + arc);
+                const float tot = cost + __int_as_float(av.x);
+                if (tot < cutoff) relax(c, av.y, pack(tot, arc), i, (av.w & kNextHasEps) != 0);
             }
         }
+    };
+    while (lo < hi) {
+        if (hi - lo <= kSmallRound) {
+            // the tail of the closure — a few dozen entries per round, each a chain of dependent loads — is run to its fixed point by
+            // one warp with warp barriers, instead of two block barriers per round with every other warp waiting at them
+            if (c.warp == 0) {
+                while (lo < hi) {
+                    for (int w = lo + c.lane; w < hi; w += 32) expand(w);
+                    __syncwarp();
+                    lo = hi;
+                    hi = min(*(volatile int *)&c.sh.n_work, a.cand_cap);
+                    __syncwarp();
+                }
+            }
+            break;
+        }
+        for (int w = lo + c.tid; w < hi; w += NT) expand(w);
         __syncthreads();
         lo = hi;
         hi = min(c.sh.n_work, a.cand_cap);
         __syncthreads();
     }
+    __syncthreads();
     return min(c.sh.n_cand, a.cand_cap);
 }
 
@@ -399,7 +416,7 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
         if (winner && is_eps && dst_tok < a.tok_cap) t_prev[dst_tok] = -2 - src_tok;
         if (a.lattice && src_ok && cd.x >= 0 && cost - unord((unsigned)(best >> 32)) <= a.lattice_beam) {
             float ac = 0.f;
-            if (!is_eps) ac = cost_offset - a.acoustic_scale * c.ll[__ldg(a.g.arcs + cd.x).z];
+            if (!is_eps) ac = cost_offset - __fmul_rn(a.acoustic_scale, c.ll[__ldg(a.g.arcs + cd.x).z]);
             const int k = link_base + agg_inc(&c.sh.n_links);
             if (k < a.link_cap) links[k] = make_int4(is_eps ? -2 - src_tok : cd.w, dst_tok | (is_eps ? kEpsLinkFlag : 0), cd.x, __float_as_int(ac));
             else c.sh.error = 7;
@@ -554,7 +571,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                     unsigned m = 0xffffffffu;
                     for (int arc = sa.x + c.lane; arc < sa.y; arc += 32) {
                         const int4 av = __ldg(a.g.arcs + arc);
-                        const float ac = -best - a.acoustic_scale * s_ll[av.z];
+                        const float ac = -best - __fmul_rn(a.acoustic_scale, s_ll[av.z]);
                         m = min(m, ford(best + ac + __int_as_float(av.x)));
                     }
                     for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -599,16 +616,26 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 }
             }
             __syncthreads();
-            int rbase = 0, ebase = 0, abase = 0, n_surv = 0, n_exp = 0, n_arcs = 0;
-            for (int w = 0; w < (NT / 32); w++) {
-                if (w < c.warp) {
-                    rbase += sh.warp_cnt[w];
-                    ebase += sh.warp_exp[w];
-                    abase += sh.warp_deg[w];
+            int rbase, ebase, abase, n_surv, n_exp, n_arcs;
+            {
+                // exclusive prefix over the warps' counts (at most 32 of them): one value per lane, shuffle scan, this warp's entry
+                constexpr int NW = NT / 32;
+                int vc = c.lane < NW ? sh.warp_cnt[c.lane] : 0, ve = c.lane < NW ? sh.warp_exp[c.lane] : 0, vd = c.lane < NW ? sh.warp_deg[c.lane] : 0;
+                int ic = vc, ie = ve, id = vd;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int uc = __shfl_up_sync(0xffffffffu, ic, o), ue = __shfl_up_sync(0xffffffffu, ie, o), ud = __shfl_up_sync(0xffffffffu, id, o);
+                    if (c.lane >= o) {
+                        ic += uc;
+                        ie += ue;
+                        id += ud;
+                    }
                 }
-                n_surv += sh.warp_cnt[w];
-                n_exp += sh.warp_exp[w];
-                n_arcs += sh.warp_deg[w];
+                rbase = __shfl_sync(0xffffffffu, ic - vc, c.warp);
+                ebase = __shfl_sync(0xffffffffu, ie - ve, c.warp);
+                abase = __shfl_sync(0xffffffffu, id - vd, c.warp);
+                n_surv = __shfl_sync(0xffffffffu, ic, 31);
+                n_exp = __shfl_sync(0xffffffffu, ie, 31);
+                n_arcs = __shfl_sync(0xffffffffu, id, 31);
             }
             {
                 // table window: room for every emitting arc's target plus closure growth, at load factor <= 1/3
@@ -760,8 +787,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                     if (validA) avA = __ldg(a.g.arcs + arcA);
                     if (validB) avB = __ldg(a.g.arcs + arcB);
                     float totA = INFINITY, totB = INFINITY;
-                    if (validA) totA = ocostA + (cost_offset - a.acoustic_scale * s_ll[avA.z]) + __int_as_float(avA.x);
-                    if (validB) totB = ocostB + (cost_offset - a.acoustic_scale * s_ll[avB.z]) + __int_as_float(avB.x);
+                    if (validA) totA = ocostA + (cost_offset - __fmul_rn(a.acoustic_scale, s_ll[avA.z])) + __int_as_float(avA.x);
+                    if (validB) totB = ocostB + (cost_offset - __fmul_rn(a.acoustic_scale, s_ll[avB.z])) + __int_as_float(avB.x);
                     unsigned m = min(ford(totA), ford(totB));
                     for (int d = 16; d; d >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
                     if (c.lane == 0) atomicMin(&sh.min_ord, m);

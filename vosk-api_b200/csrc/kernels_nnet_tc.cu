@@ -469,294 +469,6 @@ gemm_tc_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const _
 }
 
 // ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL (VB_TC_PERSIST=1, off by default): persistent variant of the fp16-split kernel.  One CTA per SM walks over
-// output tiles; barriers and TMEM are set up once, and four dedicated epilogue warps drain tile i while the producer / TMA /
-// MMA warps already work on tile i + 1 (the operand ring runs on across tiles; with two accumulator sets in TMEM — tiles of
-// 80 columns or fewer, VB_TC_BN_CAP=80 — even the MMAs of tile i + 1 overlap the epilogue).  Bit-identical results
-// (tools/gemm_selftest.py incl. multi-tile shapes), but measured SLOWER than the one-tile-per-CTA kernel on the small
-// architecture: TDNN-F chain 25.7 ms vs 22.0 ms per 4.2 k audio-seconds (28 ms with two accumulator sets): with one
-// accumulator set the next tile's MMAs still wait for an epilogue that now runs on four warps instead of eight; with eight
-// epilogue warps (576 threads, 96 registers, 344 bytes of spills) it measured 32.5 ms.  Kept as the starting point for a
-// version that redistributes registers between the roles (setmaxnreg).
-//   warps 0-7   A producers (gather -> fp16 hi / lo split -> swizzled tiles)
-//   warp  8     TMA weight boxes            warp 9   TMEM allocation + MMA issue
-//   warps 10-13 epilogue (warp w owns the TMEM lanes of quarter w % 4)
-constexpr int kPThreads = 448;
-constexpr int kPEpiWarp0 = 10;
-struct PSmem {
-    uint64_t full[4], empty[4], acc_full[2], acc_empty[2];
-    uint32_t tmem_base;
-};
-
-__global__ void __launch_bounds__(kPThreads, 1)
-gemm_tcp_kernel(GemmArgs a, const __grid_constant__ TensorMapBlob map_hi, const __grid_constant__ TensorMapBlob map_lo, int BN,
-                int stages, int tmem_cols, int n_main, int n_sets) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ PSmem ts;
-    const OpDesc &op = a.op;
-    const int total = a.rowoff[a.num_lanes];
-    const int n_col_tiles = (op.N + BN - 1) / BN;
-    const int n_tiles = ((total + TM - 1) / TM) * n_col_tiles;
-    if ((int)blockIdx.x >= n_tiles) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t stage_bytes = 2u * TM * 128u + 2u * (uint32_t)BN * 128u;
-    constexpr int TKE = 64;
-    const int nkb = (op.K + TKE - 1) / TKE;
-    const int set_cols = (n_main + 1) * BN;
-
-    if (tid == kProducerThreads) {
-        for (int s = 0; s < stages; s++) {
-            mbar_init(&ts.full[s], kProducerThreads + 1);
-            mbar_init(&ts.empty[s], 1);
-        }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&ts.acc_full[s], 1);
-            mbar_init(&ts.acc_empty[s], 4);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == kMmaWarp) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ts.tmem_base)), "r"(tmem_cols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = ts.tmem_base;
-
-    if (warp < kTmaWarp) {
-        // =========================== A producers ===========================
-        const int in_dim = a.in.dim, spliced = op.n_off * in_dim;
-        const int c = tid & 7, rsub = tid >> 3;
-        constexpr int RG = kProducerThreads / 8, RPT = TM / RG;
-        const int ring_mask = a.in.ring - 1;
-        int g = 0;  // K-blocks published so far (the operand ring runs on across tiles)
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int row0 = (tile / n_col_tiles) * TM;
-            const float *row_base[RPT], *iv_base[RPT];
-            int row_slot[RPT];
-#pragma unroll
-            for (int it = 0; it < RPT; it++) {
-                const int r = row0 + it * RG + rsub;
-                int2 rc = make_int2(-1, 0);
-                if (r < total) rc = __ldg(a.rows + r);
-                row_base[it] = rc.x >= 0 ? a.in.buf + (size_t)rc.x * a.in.ring * in_dim : nullptr;
-                iv_base[it] = rc.x >= 0 ? a.ivec + (size_t)rc.x * a.ivec_dim : nullptr;
-                row_slot[it] = (rc.y - a.in.t_start) / a.in.step;
-            }
-            auto gather16 = [&](int kb, float4 *v) {
-#pragma unroll
-                for (int pc = 0; pc < 2; pc++) {
-                    const int k = kb * TKE + c * 8 + pc * 4;
-                    const bool in_k = k < op.K, is_iv = k >= spliced;
-                    int seg = 0, col = 0;
-                    if (in_k && !is_iv) {
-                        seg = k / in_dim;
-                        col = k - seg * in_dim;
-                    }
-                    const int off_rows = in_k && !is_iv ? op.offs[seg] / a.in.step : 0;
-#pragma unroll
-                    for (int it = 0; it < RPT; it++) {
-                        v[it * 2 + pc] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row_base[it] && in_k) {
-                            const float *src = is_iv ? iv_base[it] + (k - spliced)
-                                                     : row_base[it] + (size_t)((row_slot[it] + off_rows) & ring_mask) * in_dim + col;
-                            v[it * 2 + pc] = __ldg(reinterpret_cast<const float4 *>(src));
-                        }
-                    }
-                }
-            };
-            auto publish16 = [&](int kb, const float4 *v) {
-                const int s = (g + kb) % stages;
-                const uint32_t par = (uint32_t)(((g + kb) / stages) & 1);
-                mbar_wait(&ts.empty[s], par ^ 1);
-                const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + TM * 128;
-#pragma unroll
-                for (int it = 0; it < RPT; it++) {
-                    const int r = it * RG + rsub;
-                    const float x[8] = {v[it * 2].x, v[it * 2].y, v[it * 2].z, v[it * 2].w, v[it * 2 + 1].x, v[it * 2 + 1].y, v[it * 2 + 1].z, v[it * 2 + 1].w};
-                    uint32_t hp[4], lp[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float x0 = fminf(fmaxf(x[2 * j], -65504.f), 65504.f), x1 = fminf(fmaxf(x[2 * j + 1], -65504.f), 65504.f);
-                        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-                        const __half l0 = __float2half_rn((x0 - __half2float(h0)) * 2048.f), l1 = __float2half_rn((x1 - __half2float(h1)) * 2048.f);
-                        hp[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                        lp[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                    }
-                    const uint32_t o = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "r"(hp[0]), "r"(hp[1]), "r"(hp[2]), "r"(hp[3]) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + o), "r"(lp[0]), "r"(lp[1]), "r"(lp[2]), "r"(lp[3]) : "memory");
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&ts.full[s]);
-            };
-            float4 v0[RPT * 2], v1[RPT * 2];
-            gather16(0, v0);
-            if (nkb > 1) gather16(1, v1);
-            for (int kb = 0; kb < nkb; kb += 2) {
-                publish16(kb, v0);
-                if (kb + 2 < nkb) gather16(kb + 2, v0);
-                if (kb + 1 < nkb) {
-                    publish16(kb + 1, v1);
-                    if (kb + 3 < nkb) gather16(kb + 3, v1);
-                }
-            }
-            g += nkb;
-        }
-    } else if (warp == kTmaWarp) {
-        // =========================== TMA: weight boxes ===========================
-        if (lane == 0) {
-            int g = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int n0 = (tile % n_col_tiles) * BN;
-                for (int kb = 0; kb < nkb; kb++, g++) {
-                    const int s = g % stages;
-                    mbar_wait(&ts.empty[s], (uint32_t)((g / stages) & 1) ^ 1);
-                    unsigned char *B_hi = smem + (size_t)s * stage_bytes + 2 * TM * 128, *B_lo = B_hi + (size_t)BN * 128;
-                    mbar_arrive_expect_tx(&ts.full[s], 2u * (uint32_t)BN * 128u);
-                    const int k0 = kb * TKE;
-                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(B_hi)),
-                                 "l"(&map_hi), "r"(k0), "r"(n0), "r"(smem_u32(&ts.full[s]))
-                                 : "memory");
-                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(B_lo)),
-                                 "l"(&map_lo), "r"(k0), "r"(n0), "r"(smem_u32(&ts.full[s]))
-                                 : "memory");
-                }
-            }
-        }
-    } else if (warp == kMmaWarp) {
-        // =========================== MMA issuer ===========================
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);  // D = f32, A = B = f16, K-major
-        int g = 0, tcount = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tcount++) {
-            const int set = tcount % n_sets;
-            const uint32_t acc0 = tmem + (uint32_t)(set * set_cols);
-            if (tcount >= n_sets) {  // the epilogue must have drained this accumulator set
-                mbar_wait(&ts.acc_empty[set], (uint32_t)((tcount / n_sets - 1) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            for (int kb = 0; kb < nkb; kb++, g++) {
-                const int s = g % stages;
-                mbar_wait(&ts.full[s], (uint32_t)((g / stages) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint64_t dAh = umma_desc(sa), dAl = umma_desc(sa + TM * 128);
-                    const uint64_t dBh = umma_desc(sa + 2 * TM * 128), dBl = umma_desc(sa + 2 * TM * 128 + BN * 128);
-                    auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
-                            "l"(da), "l"(db), "r"(idesc), "r"(acc)
-                            : "memory");
-                    };
-#pragma unroll
-                    for (int k8 = 0; k8 < 4; k8++) {
-                        const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
-                        const int step = kb * 4 + k8;
-                        mma(acc0 + (uint32_t)((step % n_main) * BN), dAh + adv, dBh + adv, step >= n_main ? 1u : 0u);
-                        mma(acc0 + (uint32_t)(n_main * BN), dAl + adv, dBh + adv, step ? 1u : 0u);
-                        mma(acc0 + (uint32_t)(n_main * BN), dAh + adv, dBl + adv, 1u);
-                    }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&ts.empty[s])) : "memory");
-                    if (kb == nkb - 1)
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&ts.acc_full[set])) : "memory");
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        // =========================== epilogue ===========================
-        const int quarter = warp & 3;
-        const int nsteps = nkb * 4;
-        int tcount = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tcount++) {
-            const int set = tcount % n_sets;
-            const int row0 = (tile / n_col_tiles) * TM, n0 = (tile % n_col_tiles) * BN;
-            const int r = row0 + quarter * 32 + lane;
-            int2 rc = make_int2(-1, 0);
-            if (r < total) rc = __ldg(a.rows + r);
-            float *orow = nullptr;
-            const float *brow = nullptr;
-            if (rc.x >= 0) {
-                orow = a.out.buf + ((size_t)rc.x * a.out.ring + (((rc.y - a.out.t_start) / a.out.step) & (a.out.ring - 1))) * a.out.dim;
-                if (op.byp_node >= 0) brow = a.byp.buf + ((size_t)rc.x * a.byp.ring + (((rc.y - a.byp.t_start) / a.byp.step) & (a.byp.ring - 1))) * a.byp.dim;
-            }
-            // the bypass segment of a chunk is requested one chunk ahead (the first one before the accumulator is ready):
-            // it does not depend on the accumulator, and fetched on demand its latency was most of the epilogue
-            float4 bnext[4];
-            auto fetch_bypass = [&](int cb) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) bnext[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (brow && cb < BN && n0 + cb < op.N) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) bnext[j] = __ldg(reinterpret_cast<const float4 *>(brow + n0 + cb + 4 * j));
-                }
-            };
-            fetch_bypass(0);
-            mbar_wait(&ts.acc_full[set], (uint32_t)((tcount / n_sets) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr_row = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * set_cols);
-            for (int cb = 0; cb < BN; cb += 16) {
-                const int n = n0 + cb;
-                float4 byp[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) byp[j] = bnext[j];
-                fetch_bypass(cb + 16);
-                uint32_t v[5][16];
-#pragma unroll
-                for (int q = 0; q < 5; q++) {
-                    const bool live = q <= n_main && !(q < n_main && q >= nsteps);
-                    if (live) {
-                        asm volatile(
-                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                            : "=r"(v[q][0]), "=r"(v[q][1]), "=r"(v[q][2]), "=r"(v[q][3]), "=r"(v[q][4]), "=r"(v[q][5]), "=r"(v[q][6]), "=r"(v[q][7]),
-                              "=r"(v[q][8]), "=r"(v[q][9]), "=r"(v[q][10]), "=r"(v[q][11]), "=r"(v[q][12]), "=r"(v[q][13]), "=r"(v[q][14]), "=r"(v[q][15])
-                            : "r"(taddr_row + (uint32_t)(q * BN + cb)));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; j++) v[q][j] = 0u;
-                    }
-                }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (orow && n < op.N) {
-                    float z[16];
-                    const float *bv = reinterpret_cast<const float *>(byp);
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        float x = 0.f, cr = 0.f;
-#pragma unroll
-                        for (int q = 0; q < 5; q++) {
-                            const float t = __uint_as_float(v[q][j]);
-                            x += q < n_main ? t : 0.f;
-                            cr = q == n_main ? t : cr;
-                        }
-                        x = fmaf(cr, 1.f / 2048.f, x);
-                        if (op.bias) x += __ldg(op.bias + n + j);
-                        if (op.relu) x = fmaxf(x, 0.f);
-                        if (op.has_bn) x = fmaf(x, __ldg(op.bn_scale + n + j), __ldg(op.bn_offset + n + j));
-                        if (brow) x = fmaf(op.bypass_scale, bv[j], x);
-                        z[j] = x;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(orow + n + j) = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ts.acc_empty[set]);
-        }
-    }
-    __syncthreads();
-    if (warp == kMmaWarp) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -779,14 +491,10 @@ static EncodeTiledFn encode_fn() {
 // 256-column tiles) 1.3e-3.  The tolerance decides: 4.  The fp16 split issues half as many MMAs per K (K = 16 each), so two
 // main accumulators give the same number of adds per accumulator, and the tile can be up to 160 columns wide.
 static int main_accs(int K, bool f16) {
-    static int force = getenv("VB_TC_NMAIN") ? atoi(getenv("VB_TC_NMAIN")) : 0;  // experiments
-    if (force > 0 && f16) return force;
     return f16 ? (K >= 2048 ? 4 : K >= 128 ? 2 : 1) : (K >= 128 ? 4 : K >= 64 ? 2 : 1);
 }
 static int tile_n(int N, int K, bool f16) {
     int limit = (512 / (main_accs(K, f16) + 1)) & ~15;
-    static int cap = getenv("VB_TC_BN_CAP") ? atoi(getenv("VB_TC_BN_CAP")) : 0;  // experiments: narrower tiles (two accumulator sets fit from 80 columns down)
-    if (f16 && cap >= 16 && limit > cap) limit = cap & ~15;
     if (!f16) return N < limit ? N : limit;  // (a partial last tile is fine: TMA zero-fills beyond N and the epilogue guards its stores)
     const int ntiles = (N + limit - 1) / limit;  // equal tiles: 512 columns -> 4 x 128 rather than 3 x 160 + 32
     return (((N + ntiles - 1) / ntiles) + 15) & ~15;
@@ -863,7 +571,7 @@ extern "C" cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s) {
     TensorMapBlob mh, ml;
     memcpy(mh.b, a->map_hi, 128);
     memcpy(ml.b, a->map_lo, 128);
-    static int terms = getenv("VB_TC_TERMS") ? atoi(getenv("VB_TC_TERMS")) : 3;
+    const int terms = 3;  // hi*hi + lo*hi + hi*lo
     static int prof = getenv("VB_TC_PROF") ? atoi(getenv("VB_TC_PROF")) : 0;
     const bool prof_this = prof == 1 || (prof == 2 && op.K == 192 && op.N == 512) || (prof == 3 && op.K >= 1024);
     if (prof_this) {
@@ -879,29 +587,6 @@ extern "C" cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s) {
                 fprintf(stderr, "[gemm_tc prof] MMA warp per tile: waiting for operands %.0f, issuing the MMAs %.0f\n", h[8] / n, h[9] / n);
             });
         }
-    }
-    static int persist = getenv("VB_TC_PERSIST") ? atoi(getenv("VB_TC_PERSIST")) : 0;
-    if (f16 && persist) {
-        const int set_cols = (n_main + 1) * BN, n_sets = 2 * set_cols <= 512 ? 2 : 1;
-        int pcols = 32;
-        while (pcols < n_sets * set_cols) pcols <<= 1;
-        int pstages = (int)((200u * 1024u) / stage_bytes);  // (not clamped to the K-blocks of one tile: the ring runs on across tiles)
-        if (pstages > 4) pstages = 4;
-        if (pstages < 1) pstages = 1;
-        const int psmem = (int)(stage_bytes * pstages + 1024);
-        static int pdone[16] = {};
-        static int sms[16] = {};
-        if (dev >= 16) return cudaErrorInvalidDevice;
-        if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-        if (pdone[dev] < psmem) {
-            cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
-            if (e != cudaSuccess) return e;
-            pdone[dev] = psmem;
-        }
-        int pgrid = (int)(grid.x * grid.y);
-        if (pgrid > sms[dev]) pgrid = sms[dev];
-        gemm_tcp_kernel<<<pgrid, kPThreads, psmem, s>>>(*a, mh, ml, BN, pstages, pcols, n_main, n_sets);
-        return cudaGetLastError();
     }
     if (f16) gemm_tc_kernel<true><<<grid, kTcThreads, smem, s>>>(*a, mh, ml, BN, stages, tmem_cols, terms, n_main, prof_this ? 1 : 0);
     else gemm_tc_kernel<false><<<grid, kTcThreads, smem, s>>>(*a, mh, ml, BN, stages, tmem_cols, terms, n_main, prof_this ? 1 : 0);
