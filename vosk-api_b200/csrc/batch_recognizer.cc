@@ -28,8 +28,9 @@ BatchRecognizer::BatchRecognizer(BatchModel *model, float sample_frequency)
         bool done = false;
         if (host_chain) {
             const RawLattice *lat = bp.raw_lattice();
-            if (lat && lat->error == 0 && lat->n_states > 0) words = lattice_to_words(*lat, *m, lattice_beam);
-            done = !words.empty() || bp.arcs.empty();
+            bool ran = false;
+            if (lat && lat->error == 0 && lat->n_states > 0) words = lattice_to_words(*lat, *m, lattice_beam, 0.9, nullptr, &ran);
+            done = ran || bp.arcs.empty();
             if (!done) eng->count_fallback();  // no usable lattice (capacity error, no complete path): logged by the engine, counted here
         }
         if (!done) words = align_words(*m, bp.arcs);

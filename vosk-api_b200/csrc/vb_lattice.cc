@@ -1628,7 +1628,8 @@ inline double ms_since(std::chrono::steady_clock::time_point t0) {
 }
 }  // namespace
 
-std::vector<WordSpan> lattice_to_words(const RawLattice &raw, const Model &m, float lattice_beam, double lm_scale, LatticeStats *stats) {
+std::vector<WordSpan> lattice_to_words(const RawLattice &raw, const Model &m, float lattice_beam, double lm_scale, LatticeStats *stats, bool *ok) {
+    if (ok) *ok = false;
 #ifdef VB_LAT_PROF
     struct Dump { ~Dump() { if (getenv("VB_LAT_PROF_DUMP")) { for (int k = 0; k < 12; k++) fprintf(stderr, "prof[%d]=%.3f Mcyc\n", k, g_prof[k] / 1e6); } } };
     static thread_local Dump dump;
@@ -1640,6 +1641,7 @@ std::vector<WordSpan> lattice_to_words(const RawLattice &raw, const Model &m, fl
         stats->raw_arcs = (int)raw.src.size();
     }
     if (!determinize_phone_pruned(ws, raw, m, (double)lattice_beam, true, &ws.clat, stats)) return {};
+    if (ok) *ok = true;  // the chain ran; an empty result now means a lattice without words (silence), not a failure
     scale_graph_costs(&ws.clat, lm_scale);
     if (stats) stats->ms_det = ms_since(t0);
     t0 = std::chrono::steady_clock::now();

@@ -26,9 +26,10 @@ struct LatticeStats {
     double ms_det = 0, ms_align = 0, ms_mbr = 0;
 };
 
-// the whole chain, as the pipeline + PushLattice run it.  Returns the MBR one-best; empty when the lattice has no complete path.
+// the whole chain, as the pipeline + PushLattice run it.  Returns the MBR one-best; *ok = false when the lattice could not be
+// determinized (no complete path, not a lattice), true when the chain ran — an empty result then is a lattice without words.
 std::vector<WordSpan> lattice_to_words(const RawLattice &raw, const Model &m, float lattice_beam, double lm_scale = 0.9,
-                                       LatticeStats *stats = nullptr);
+                                       LatticeStats *stats = nullptr, bool *ok = nullptr);
 
 // test hook: stage 1 = determinized (and graph-scaled) lattice, 2 = word-aligned lattice, as text lines
 // "S start" / "A src dst word graph acoustic tids" / "F state graph acoustic tids"

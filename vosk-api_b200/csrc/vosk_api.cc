@@ -216,8 +216,9 @@ double vosk_batch_model_run_resident_passes(VoskBatchModel *model, const int16_t
             bool done = false;
             if (host_chain) {
                 const vb::RawLattice *lat = bp.raw_lattice();
-                if (lat && lat->error == 0 && lat->n_states > 0) words = vb::lattice_to_words(*lat, *m, lattice_beam);
-                done = !words.empty() || bp.arcs.empty();
+                bool ran = false;
+                if (lat && lat->error == 0 && lat->n_states > 0) words = vb::lattice_to_words(*lat, *m, lattice_beam, 0.9, nullptr, &ran);
+                done = ran || bp.arcs.empty();
                 if (!done) engp->count_fallback();
             }
             if (!done) words = vb::align_words(*m, bp.arcs);
