@@ -595,8 +595,17 @@ def main():
             n_d = min(256, a.streams)
             dopts = ("num-channels=%d,max-batch-size=%d,max-seconds=18,acoustic-scale=0.5,log-tokens-per-frame=7168,log-links-per-frame=16384,"
                      "lat-link-cap=262144,lat-tok-cap=131072" % (n_d, n_d))
-            dleg, dtexts = resident_leg(vosk, mdir, dopts, audio_mat[:n_d], lengths[:n_d], 1, 2)
-            dm = vosk.BatchModel(mdir, options=dopts)
+            # the search and the device lattice (lattice=2) on 256 streams; the whole result path (host chain: these lattices are ~4x the
+            # default leg's and the pruned determinization grows faster than that) on the first 64 of them
+            dleg, _ = resident_leg(vosk, mdir, dopts + ",lattice=2", audio_mat[:n_d], lengths[:n_d], 1, 2)
+            dleg = {"value_device_lattice_only": dleg["value"], "ms_per_step_device_lattice_only": dleg["ms_per_step"], "unit": UNIT,
+                    "lattice_links_logged_per_step": dleg["lattice_links_logged_per_step"], "lattice_arcs_after_pruning_per_step": dleg["lattice_arcs_after_pruning_per_step"],
+                    "truncated": dleg["truncated"], "options": dopts}
+            n_h = min(64, n_d)
+            hleg, dtexts = resident_leg(vosk, mdir, dopts, audio_mat[:n_h], lengths[:n_h], 1, 1)
+            dleg["whole_result_path_%d_streams" % n_h] = {k: hleg[k] for k in ("value", "ms_per_step", "results_with_confidence_below_1", "host_lattice_chain_cpu_ms_per_step",
+                                                                                 "host_lattice_threads", "truncated", "lattice_fallbacks")}
+            dm = vosk.BatchModel(mdir, options=dopts + ",lattice=2")
             dm.SetTiming(True)
             dm.SetSlots(1)
             dm.RunResident(audio_mat[:n_d], lengths[:n_d])
