@@ -1285,11 +1285,6 @@ class WordAligner {
 // MinimumBayesRisk (Xu, Povey, Mangu, Zhu: "Minimum Bayes Risk decoding and system combination based on a
 // recursion for edit distance", as implemented by Kaldi lat/sausages.cc)
 // ------------------------------------------------------------------------------------------------------------
-struct MbrArc {
-    int word, start, end;  // 1-based nodes
-    float loglike;
-    int t_len;
-};
 inline double log_add(double a, double b) {
     if (a == -kInfD) return b;
     if (b == -kInfD) return a;
@@ -1297,8 +1292,10 @@ inline double log_add(double a, double b) {
     return hi + std::log1p(std::exp(diff));
 }
 
-std::vector<WordSpan> mbr_one_best(Workspace &ws, LatticeStats *stats) {
-    std::vector<WordSpan> result;
+// PrepareLatticeAndInitStats: the word-aligned lattice as MinimumBayesRisk sees it (false: no complete path)
+bool mbr_prepare(Workspace &ws, MbrJob *job, LatticeStats *stats) {
+    const bool result = false;
+    job->N = 0;
     const ALat &lat = ws.ali;
     const int n_all = lat.n();
     if (lat.start < 0 || n_all == 0) return result;
@@ -1382,273 +1379,137 @@ std::vector<WordSpan> mbr_one_best(Workspace &ws, LatticeStats *stats) {
         std::vector<int> p(pre_off.begin(), pre_off.end() - 1);
         for (const MbrArc &a : tmp) arcs[p[a.end]++] = a;
     }
-    std::vector<int> state_times(N + 1, 0);
+    job->N = N;
+    job->arcs.swap(arcs);
+    job->pre_off.swap(pre_off);
+    const std::vector<MbrArc> &A = job->arcs;
+    const std::vector<int> &P = job->pre_off;
+    job->state_times.assign(N + 1, 0);
     for (int n = 2; n <= N; n++)
-        for (int k = pre_off[n]; k < pre_off[n + 1]; k++) state_times[n] = state_times[arcs[k].start] + arcs[k].t_len;
+        for (int k = P[n]; k < P[n + 1]; k++) job->state_times[n] = job->state_times[A[k].start] + A[k].t_len;
     // initial R: words of the best path
-    std::vector<int> R;
+    job->R0.clear();
     {
         std::vector<double> best(N + 1, kInfD);
         std::vector<int> back(N + 1, -1);
         best[1] = 0;
         for (int n = 2; n <= N; n++)
-            for (int k = pre_off[n]; k < pre_off[n + 1]; k++) {
-                const double c = best[arcs[k].start] - (double)arcs[k].loglike;
+            for (int k = P[n]; k < P[n + 1]; k++) {
+                const double c = best[A[k].start] - (double)A[k].loglike;
                 if (c < best[n]) {
                     best[n] = c;
                     back[n] = k;
                 }
             }
-        for (int n = N; n > 1 && back[n] >= 0; n = arcs[back[n]].start)
-            if (arcs[back[n]].word != 0) R.push_back(arcs[back[n]].word);
-        std::reverse(R.begin(), R.end());
+        for (int n = N; n > 1 && back[n] >= 0; n = A[back[n]].start)
+            if (A[back[n]].word != 0) job->R0.push_back(A[back[n]].word);
+        std::reverse(job->R0.begin(), job->R0.end());
+    }
+    // forward log-probabilities and arc posteriors given their end node: the only transcendental part of MinimumBayesRisk
+    // (they do not depend on the hypothesis, so they are computed once; the edit-distance recursion itself is plain arithmetic)
+    std::vector<double> &alpha = ws.alpha;
+    alpha.assign(N + 1, 0.0);
+    job->post.resize(A.size());
+    for (int n = 2; n <= N; n++) {
+        double alpha_n = -kInfD;
+        for (int k = P[n]; k < P[n + 1]; k++) alpha_n = log_add(alpha_n, alpha[A[k].start] + A[k].loglike);
+        alpha[n] = alpha_n;
+        for (int k = P[n]; k < P[n + 1]; k++) job->post[k] = std::exp(alpha[A[k].start] + A[k].loglike - alpha_n);
     }
     if (stats) {
         stats->ali_states = N;
-        stats->ali_arcs = (int)arcs.size();
+        stats->ali_arcs = (int)A.size();
     }
-    struct Acc {
-        int word;
-        double g, tb, te;
+    return true;
+}
+
+}  // namespace
+
+// the edit-distance recursion and the decision loop (vb_mbr.h) on the host, with buffers that grow on demand
+std::vector<WordSpan> mbr_solve_host(const MbrJob &job, LatticeStats *stats) {
+    std::vector<WordSpan> result;
+    if (job.N <= 0) return result;
+    struct Buf {
+        std::vector<double> ad, bd, cq, m12a, m12b, vala, valb, pb, bq;
+        std::vector<char> b_all;
+        std::vector<MbrAcc> acc;
+        std::vector<int> acc_n, R, R2, words, rh;
+        std::vector<float> tb, te, conf, otb, ote, oconf;
     };
-    std::vector<std::vector<Acc>> acc;
-    std::vector<std::pair<float, float>> one_best_times;
-    std::vector<float> one_best_conf;
-    std::vector<double> &alpha = ws.alpha, &alpha_dash = ws.alpha_dash, &beta_dash = ws.beta_dash;
-    std::vector<char> &b_all = ws.b_arc;
-    std::vector<double> &post = ws.post;
-    post.resize(arcs.size());
-    constexpr double kPen = 1.0 + 1.0e-05;  // l(a, eps, penalize = true)
-    for (int counter = 0;; counter++) {
-        {  // NormalizeEps: epsilons between all words and at both ends
-            std::vector<int> r2;
-            r2.push_back(0);
-            for (int w : R)
-                if (w != 0) {
-                    r2.push_back(w);
-                    r2.push_back(0);
-                }
-            R.swap(r2);
+    static thread_local Buf b;
+    int w_cap = 4 * (int)job.R0.size() + 16, acc_cap = 64;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        const size_t nw = (size_t)(job.N + 1) * w_cap;
+        if (b.ad.size() < nw) {
+            b.ad.resize(nw);
+            b.bd.resize(nw);
         }
-        const int Q = (int)R.size(), W = Q + 1;
-        const int *r = R.data() - 1;  // r[q], q = 1..Q
-        alpha.assign(N + 1, 0.0);
-        alpha_dash.assign((size_t)(N + 1) * W, 0.0);
-        beta_dash.assign((size_t)(N + 1) * W, 0.0);
-        b_all.resize(arcs.size() * (size_t)W);
-        acc.assign(Q + 1, {});
-        auto add = [&](int q, int word, double g, double tb, double te) {
-            for (Acc &x : acc[q])
-                if (x.word == word) {
-                    x.g += g;
-                    x.tb += tb;
-                    x.te += te;
-                    return;
-                }
-            acc[q].push_back(Acc{word, g, tb, te});
-        };
-        // ---- EditDistance (forward) ----
-        {
-            double *ad1 = &alpha_dash[(size_t)1 * W];
-            ad1[0] = 0.0;
-            for (int q = 1; q <= Q; q++) ad1[q] = ad1[q - 1] + (r[q] == 0 ? 0.0 : 1.0);
+        if (b.b_all.size() < job.arcs.size() * (size_t)w_cap) b.b_all.resize(job.arcs.size() * (size_t)w_cap);
+        for (std::vector<double> *v : {&b.cq, &b.m12a, &b.m12b, &b.vala, &b.valb, &b.pb, &b.bq})
+            if ((int)v->size() < w_cap) v->resize(w_cap);
+        if (b.acc.size() < (size_t)w_cap * acc_cap) b.acc.resize((size_t)w_cap * acc_cap);
+        for (std::vector<int> *v : {&b.acc_n, &b.R, &b.R2, &b.words, &b.rh})
+            if ((int)v->size() < w_cap) v->resize(w_cap);
+        for (std::vector<float> *v : {&b.tb, &b.te, &b.conf, &b.otb, &b.ote, &b.oconf})
+            if ((int)v->size() < w_cap) v->resize(w_cap);
+        MbrView view{job.N, (int)job.arcs.size(), job.arcs.data(), job.pre_off.data(), job.state_times.data(), job.post.data()};
+        MbrScratch sc{w_cap, acc_cap, b.ad.data(), b.bd.data(), b.b_all.data(), b.cq.data(), b.m12a.data(), b.m12b.data(), b.vala.data(), b.valb.data(),
+                      b.pb.data(), b.bq.data(), b.rh.data(), b.acc.data(), b.acc_n.data(), b.R.data(), b.R2.data(), b.tb.data(), b.te.data(), b.conf.data()};
+        MbrOut out{};
+        mbr_solve(view, sc, job.R0.data(), (int)job.R0.size(), &out, b.words.data(), b.otb.data(), b.ote.data(), b.oconf.data());
+        if (out.status == 1) {
+            w_cap *= 2;
+            continue;
         }
-        // c(q) = l(eps, r(q)): what skipping reference position q costs
-        std::vector<double> &cq = ws.mbr_cq, &m12a = ws.mbr_m12a, &m12b = ws.mbr_m12b, &vala = ws.mbr_vala, &valb = ws.mbr_valb;
-        cq.resize(W);
-        m12a.resize(W);
-        m12b.resize(W);
-        vala.resize(W);
-        valb.resize(W);
-        for (int q = 1; q <= Q; q++) cq[q] = r[q] == 0 ? 0.0 : 1.0;
-        // One arc's row alpha_dash_arc(.) in three passes: the two candidates that do not depend on the row itself (a1: substitute /
-        // match, a2: insert the arc's word) for all q — independent iterations; then the chain a3(q) = row(q-1) + c(q), which is the
-        // only serial part; then the weighted sum into the node.  Two arcs into the same node run their chains side by side.  Every
-        // operation and its order per element are those of the plain loop (sausages.cc lines 9-12 of the paper's algorithm).
-        auto candidates = [&](const MbrArc &arc, double *m12, char *bk) {
-            const double *ads = &alpha_dash[(size_t)arc.start * W];
-            const int w_a = arc.word;
-            const double l_eps = w_a == 0 ? 0.0 : kPen;  // l(w_a, eps, true)
-            for (int q = 1; q <= Q; q++) {
-                const double a1 = ads[q - 1] + (w_a == r[q] ? 0.0 : 1.0), a2 = ads[q] + l_eps;
-                const bool one = a1 <= a2;
-                m12[q] = one ? a1 : a2;
-                bk[q] = one ? 1 : 2;
-            }
-            return ads[0] + l_eps;
-        };
-        for (int n = 2; n <= N; n++) {
-            LATP(10);
-            double alpha_n = -kInfD;
-            for (int k = pre_off[n]; k < pre_off[n + 1]; k++) alpha_n = log_add(alpha_n, alpha[arcs[k].start] + arcs[k].loglike);
-            alpha[n] = alpha_n;
-            double *adn = &alpha_dash[(size_t)n * W];
-            int k = pre_off[n];
-            const int kend = pre_off[n + 1];
-            for (; k + 1 < kend; k += 2) {
-                const double pa = std::exp(alpha[arcs[k].start] + arcs[k].loglike - alpha_n);
-                const double pb = std::exp(alpha[arcs[k + 1].start] + arcs[k + 1].loglike - alpha_n);
-                post[k] = pa;
-                post[k + 1] = pb;
-                char *bka = &b_all[(size_t)k * W], *bkb = &b_all[(size_t)(k + 1) * W];
-                double prev_a = candidates(arcs[k], m12a.data(), bka), prev_b = candidates(arcs[k + 1], m12b.data(), bkb);
-                vala[0] = prev_a;
-                valb[0] = prev_b;
-                for (int q = 1; q <= Q; q++) {
-                    const double c = cq[q];
-                    const double a3a = prev_a + c, a3b = prev_b + c;
-                    const double ma = m12a[q], mb = m12b[q];
-                    const bool ta = !(ma <= a3a), tb = !(mb <= a3b);
-                    prev_a = ta ? a3a : ma;
-                    prev_b = tb ? a3b : mb;
-                    vala[q] = prev_a;
-                    valb[q] = prev_b;
-                    bka[q] = ta ? 3 : bka[q];
-                    bkb[q] = tb ? 3 : bkb[q];
-                }
-                for (int q = 0; q <= Q; q++) adn[q] += pa * vala[q];
-                for (int q = 0; q <= Q; q++) adn[q] += pb * valb[q];
-            }
-            if (k < kend) {
-                const double pa = std::exp(alpha[arcs[k].start] + arcs[k].loglike - alpha_n);
-                post[k] = pa;
-                char *bka = &b_all[(size_t)k * W];
-                double prev_a = candidates(arcs[k], m12a.data(), bka);
-                vala[0] = prev_a;
-                for (int q = 1; q <= Q; q++) {
-                    const double a3a = prev_a + cq[q];
-                    const double ma = m12a[q];
-                    const bool ta = !(ma <= a3a);
-                    prev_a = ta ? a3a : ma;
-                    vala[q] = prev_a;
-                    bka[q] = ta ? 3 : bka[q];
-                }
-                for (int q = 0; q <= Q; q++) adn[q] += pa * vala[q];
-            }
-        }
-        // ---- backward ----
-        beta_dash[(size_t)N * W + Q] = 1.0;
-        for (int n = N; n >= 2; n--) {
-            LATP(11);
-            const double *bdn = &beta_dash[(size_t)n * W];
-            for (int k = pre_off[n]; k < pre_off[n + 1]; k++) {
-                const MbrArc &arc = arcs[k];
-                const int s_a = arc.start, w_a = arc.word;
-                double *bds = &beta_dash[(size_t)s_a * W];
-                const char *b_arc = &b_all[(size_t)k * W];
-                const double p = post[k];
-                const double t_s = state_times[s_a], t_n = state_times[n];
-                double carry = 0.0;  // beta_dash_arc(q) accumulated from case 3 of q + 1
-                for (int q = Q; q >= 1; q--) {
-                    const double b = carry + p * bdn[q];
-                    carry = 0.0;
-                    if (b == 0.0) continue;  // (adding an exact zero changes no sum; Kaldi's maps would only gain zero entries)
-                    switch (b_arc[q]) {
-                        case 1:
-                            bds[q - 1] += b;
-                            add(q, w_a, b, t_s * b, t_n * b);
-                            break;
-                        case 2:
-                            bds[q] += b;
-                            break;
-                        case 3:
-                            carry = b;
-                            add(q, 0, b, t_n * b, t_n * b);
-                            break;
-                    }
-                }
-                bds[0] += carry + p * bdn[0];
-            }
-        }
-        {
-            const double *bd1 = &beta_dash[(size_t)1 * W];
-            double carry = 0.0;
-            for (int q = Q; q >= 1; q--) {
-                const double b = carry + bd1[q];
-                carry = b;
-                add(q, 0, b, state_times[1] * b, state_times[1] * b);
-            }
-        }
-        // ---- MbrDecode step ----
-        double delta_Q = 0.0;
-        one_best_times.clear();
-        one_best_conf.clear();
-        for (int q = 1; q <= Q; q++) {
-            std::vector<Acc> &aq = acc[q];
-            if (aq.empty()) continue;
-            // GammaCompare on the float posteriors: largest first, then the larger word id
-            const Acc *top = &aq[0];
-            for (const Acc &x : aq) {
-                const float gx = (float)x.g, gt = (float)top->g;
-                if (gx > gt || (gx == gt && x.word > top->word)) top = &x;
-            }
-            double old_gamma = 0;
-            const double new_gamma = (float)top->g;
-            const int rq = R[q - 1], rhat = top->word;
-            for (const Acc &x : aq)
-                if (x.word == rq) old_gamma = (float)x.g;
-            delta_Q += old_gamma - new_gamma;
-            R[q - 1] = rhat;
-            if (rhat != 0) {
-                const float g = (float)top->g;
-                one_best_times.emplace_back((float)(top->tb / g), (float)(top->te / g));
-                const size_t i = one_best_times.size();
-                if (i > 1 && one_best_times[i - 2].second > one_best_times[i - 1].first) {
-                    // overlapping words: both share the union of their spans, split in proportion to their durations
-                    const float prev_right = i > 2 ? one_best_times[i - 3].second : 0.0f;
-                    const float left = std::max(prev_right, std::min(one_best_times[i - 2].first, one_best_times[i - 1].first));
-                    const float right = std::max(one_best_times[i - 2].second, one_best_times[i - 1].second);
-                    const float first_dur = one_best_times[i - 2].second - one_best_times[i - 2].first;
-                    const float second_dur = one_best_times[i - 1].second - one_best_times[i - 1].first;
-                    const float mid = first_dur > 0 ? left + (right - left) * first_dur / (first_dur + second_dur) : left;
-                    one_best_times[i - 2].first = left;
-                    one_best_times[i - 2].second = one_best_times[i - 1].first = mid;
-                    one_best_times[i - 1].second = right;
-                }
-                one_best_conf.push_back(g);
-            }
+        if (out.status == 2) {
+            acc_cap *= 4;
+            continue;
         }
         if (stats) {
-            stats->mbr_iters = counter + 1;
-            stats->mbr_q = Q;
+            stats->mbr_iters = out.iters;
+            stats->mbr_q = out.q;
         }
-        if (delta_Q == 0 || counter > 100) break;
+        for (int i = 0; i < out.n_words; i++) result.push_back(WordSpan{b.words[i], b.otb[i], b.ote[i], b.oconf[i]});
+        return result;
     }
-    size_t i = 0;
-    for (int w : R)
-        if (w != 0 && i < one_best_times.size()) {
-            result.push_back(WordSpan{w, one_best_times[i].first, one_best_times[i].second, one_best_conf[i]});
-            i++;
-        }
     return result;
 }
 
+namespace {
 inline double ms_since(std::chrono::steady_clock::time_point t0) {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 }  // namespace
 
-std::vector<WordSpan> lattice_to_words(const RawLattice &raw, const Model &m, float lattice_beam, double lm_scale, LatticeStats *stats, bool *ok) {
-    if (ok) *ok = false;
+bool lattice_to_mbr_job(const RawLattice &raw, const Model &m, float lattice_beam, double lm_scale, MbrJob *job, LatticeStats *stats) {
 #ifdef VB_LAT_PROF
     struct Dump { ~Dump() { if (getenv("VB_LAT_PROF_DUMP")) { for (int k = 0; k < 12; k++) fprintf(stderr, "prof[%d]=%.3f Mcyc\n", k, g_prof[k] / 1e6); } } };
     static thread_local Dump dump;
 #endif
     Workspace &ws = workspace();
+    job->N = 0;
     auto t0 = std::chrono::steady_clock::now();
     if (stats) {
         stats->raw_states = raw.n_states;
         stats->raw_arcs = (int)raw.src.size();
     }
-    if (!determinize_phone_pruned(ws, raw, m, (double)lattice_beam, true, &ws.clat, stats)) return {};
-    if (ok) *ok = true;  // the chain ran; an empty result now means a lattice without words (silence), not a failure
+    if (!determinize_phone_pruned(ws, raw, m, (double)lattice_beam, true, &ws.clat, stats)) return false;
     scale_graph_costs(&ws.clat, lm_scale);
     if (stats) stats->ms_det = ms_since(t0);
     t0 = std::chrono::steady_clock::now();
     WordAligner(ws, ws.clat, m).run();
+    mbr_prepare(ws, job, stats);  // (N = 0: a lattice without a complete aligned path — MinimumBayesRisk then has no words)
     if (stats) stats->ms_align = ms_since(t0);
-    t0 = std::chrono::steady_clock::now();
-    std::vector<WordSpan> r = mbr_one_best(ws, stats);
+    return true;
+}
+
+std::vector<WordSpan> lattice_to_words(const RawLattice &raw, const Model &m, float lattice_beam, double lm_scale, LatticeStats *stats, bool *ok) {
+    if (ok) *ok = false;
+    static thread_local MbrJob job;
+    if (!lattice_to_mbr_job(raw, m, lattice_beam, lm_scale, &job, stats)) return {};
+    if (ok) *ok = true;  // the chain ran; an empty result now means a lattice without words (silence), not a failure
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<WordSpan> r = mbr_solve_host(job, stats);
     if (stats) stats->ms_mbr = ms_since(t0);
     return r;
 }

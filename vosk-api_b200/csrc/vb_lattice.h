@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "vb_engine.h"
+#include "vb_mbr.h"
 #include "vb_model.h"
 #include "vb_result.h"
 
@@ -25,6 +26,21 @@ struct LatticeStats {
     int mbr_iters = 0, mbr_q = 0;
     double ms_det = 0, ms_align = 0, ms_mbr = 0;
 };
+
+// One word-aligned lattice as MinimumBayesRisk sees it (flat arrays; PrepareLatticeAndInitStats + the arc posteriors): the input of
+// mbr_solve (vb_mbr.h), on the host or on the device.  N = 0: nothing to decode (no complete path).
+struct MbrJob {
+    int N = 0;
+    std::vector<MbrArc> arcs;        // grouped by end node, in start-node order
+    std::vector<int> pre_off;        // [N + 2]
+    std::vector<int> state_times;    // [N + 1]
+    std::vector<double> post;        // [arcs]
+    std::vector<int> R0;             // words of the best path
+};
+// determinization + graph scale + word alignment + MBR preparation (false: the lattice could not be determinized)
+bool lattice_to_mbr_job(const RawLattice &raw, const Model &m, float lattice_beam, double lm_scale, MbrJob *job, LatticeStats *stats = nullptr);
+// the MBR decision loop on the host
+std::vector<WordSpan> mbr_solve_host(const MbrJob &job, LatticeStats *stats = nullptr);
 
 // the whole chain, as the pipeline + PushLattice run it.  Returns the MBR one-best; *ok = false when the lattice could not be
 // determinized (no complete path, not a lattice), true when the chain ran — an empty result then is a lattice without words.
