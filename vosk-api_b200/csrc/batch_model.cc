@@ -35,6 +35,7 @@ static void apply_option(Config *c, const std::string &k, const std::string &v) 
     else if (k == "debug-capture") I(&c->debug_capture);
     else if (k == "lattice") I(&c->lattice);
     else if (k == "post-threads") I(&c->post_threads);
+    else if (k == "batcher-sleep") I(&c->batcher_sleep);
     else if (k == "partials") I(&c->partials);
     else if (k == "fe-priority") I(&c->fe_priority);
     else if (k == "endpoint-rule5-seconds") F(&c->endpoint_rule5_seconds);

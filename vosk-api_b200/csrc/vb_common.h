@@ -84,6 +84,7 @@ struct Config {
                                 // endpointing rules from model.conf (the reference's batch path hard-codes them [REF src/batch_model.cc:69-88])
     int log_links_per_frame = 6144;   // average links per frame the link log is sized for
     int partials = 0;           // partial results: best path so far after every chunk (vosk_batch_recognizer_partial_result)
+    int batcher_sleep = 1;      // the batcher thread waits for a step with short sleeps (not a spin) while the host lattice chain runs
     int post_threads = 0;       // host threads turning lattices into results (0 = hardware threads / (engines x local ranks))
     int num_engines = 1;        // engines sharing this host (set by BatchModel)
     int lat_tok_cap = 131072, lat_link_cap = 262144;  // pruned raw lattice of one stream (states / arcs)

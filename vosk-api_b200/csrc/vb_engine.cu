@@ -1009,6 +1009,16 @@ void Engine::complete_step(Slot &sl) {
     std::vector<Lane> &lanes = sl.lanes;
     const int L = (int)lanes.size();
     cudaStream_t st = sl.stream;
+    if (!post_threads_.empty() && cfg_.batcher_sleep) {
+        // with the host lattice chain running, the host is what bounds throughput: the batcher polls with short sleeps instead of
+        // spinning inside the driver, so that its core goes to the lattice pool (costs up to ~0.1 ms per step)
+        for (;;) {
+            const cudaError_t q = cudaEventQuery(sl.done);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) VB_CUDA_CHECK(q);
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
+    }
     VB_CUDA_CHECK(cudaEventSynchronize(sl.done));
     const auto host_t0 = std::chrono::steady_clock::now();
     // load feedback for the tiering of the stream's next chunks: the largest token count of this chunk, or what is left of an
