@@ -298,6 +298,7 @@ struct Workspace {
     std::vector<double> backward;
     std::vector<TArc> tarcs;
     IdTable min_tab, init_tab;
+    std::vector<int> init1, min1;  // single-element subsets by state: index + 1 into the initial-subset records / output states
     std::vector<int> tvec;
     CLatF clat;
     // aligner
@@ -441,6 +442,10 @@ class Determinizer {
         ws_.init_tab.reset(1 << 12);
         inits_.clear();
         const int n = in_.n;
+        // most subsets (about nine in ten on speech lattices) hold one element; normalized, such a subset is {state, empty string,
+        // One}: it is looked up by its state in an array, not through the hash tables
+        ws_.init1.assign((size_t)n + in_.arcs.size(), 0);
+        ws_.min1.assign((size_t)n + in_.arcs.size(), 0);
         if (n == 0 || in_.start < 0) return false;
         // ComputeBackwardWeight (per arc of the uncompressed lattice: the chain is walked from its end)
         ws_.backward.assign(n, kInfD);
@@ -538,6 +543,14 @@ class Determinizer {
     // The result is sorted by state.
     void closure(std::vector<Elem> *sub) {
         LATP(1);
+        if (sub->size() == 1 && (*sub)[0].state < in_.n) {
+            // one element whose state has no epsilon arc (they sort first): the closure is the element itself
+            const int s0 = (*sub)[0].state;
+            if (in_.off[s0] == in_.off[s0 + 1] || in_.arcs[in_.off[s0]].il != 0) {
+                if (!ws_.keepable[s0]) sub->clear();
+                return;
+            }
+        }
         std::vector<Elem> &cur = ws_.cur;
         std::vector<int> &heap = ws_.heap;
         cur.clear();
@@ -637,13 +650,20 @@ class Determinizer {
         const int off = (int)ws_.pool.size();
         ws_.pool.insert(ws_.pool.end(), sub.begin(), sub.end());
         states_.push_back(OutState{off, (int)sub.size(), fwd});
-        ws_.min_tab.insert(hash_of(sub.data(), (int)sub.size()), id);
+        if (plain_single(sub.data(), (int)sub.size())) ws_.min1[sub[0].state] = id + 1;
+        else ws_.min_tab.insert(hash_of(sub.data(), (int)sub.size()), id);
         process_final(id);
         process_transitions(id);
         return id;
     }
+    static bool plain_single(const Elem *e, int n) { return n == 1 && e[0].str == 0 && e[0].g == 0.f && e[0].a == 0.f; }
     int minimal_to_state(const std::vector<Elem> &sub, double fwd) {
         const int n = (int)sub.size();
+        if (plain_single(sub.data(), n)) {
+            int &slot = ws_.min1[sub[0].state];
+            if (!slot) slot = new_state(sub, fwd) + 1;
+            return slot - 1;
+        }
         const int f = ws_.min_tab.find(hash_of(sub.data(), n), [&](int id) {
             return states_[id].len == n && same_subset(&ws_.pool[states_[id].off], sub.data(), n);
         });
@@ -732,13 +752,29 @@ class Determinizer {
         Elem *e = &ws_.pool[t.off];
         float tg, ta;
         int common;
-        normalize(e, t.len, &tg, &ta, &common);
+        const bool single = t.len == 1;
+        if (single) {  // NormalizeSubset of one element: its weight and its whole string come out
+            tg = e[0].g;
+            ta = e[0].a;
+            common = e[0].str;
+            e[0].g = 0.f;
+            e[0].a = 0.f;
+            e[0].str = 0;
+        } else {
+            normalize(e, t.len, &tg, &ta, &common);
+        }
         fwd += cost_of(tg, ta);
         // InitialToStateId
-        const uint64_t h = hash_of(e, t.len);
         int next, nstr;
         float ng, na;
-        const int f = ws_.init_tab.find(h, [&](int id) { return inits_[id].len == t.len && same_subset(&ws_.pool[inits_[id].off], e, t.len); });
+        uint64_t h = 0;
+        int f = -1;
+        if (single) {
+            f = ws_.init1[e[0].state] - 1;
+        } else {
+            h = hash_of(e, t.len);
+            f = ws_.init_tab.find(h, [&](int id) { return inits_[id].len == t.len && same_subset(&ws_.pool[inits_[id].off], e, t.len); });
+        }
         if (f >= 0) {
             next = inits_[f].state;
             nstr = inits_[f].str;
@@ -746,12 +782,23 @@ class Determinizer {
             na = inits_[f].a;
         } else {
             std::vector<Elem> &sub = ws_.sub;
+            const int key_state = e[0].state;
             sub.assign(e, e + t.len);
             closure(&sub);
-            normalize(sub.data(), (int)sub.size(), &ng, &na, &nstr);
+            if (sub.size() == 1) {
+                ng = sub[0].g;
+                na = sub[0].a;
+                nstr = sub[0].str;
+                sub[0].g = 0.f;
+                sub[0].a = 0.f;
+                sub[0].str = 0;
+            } else {
+                normalize(sub.data(), (int)sub.size(), &ng, &na, &nstr);
+            }
             next = minimal_to_state(sub, fwd + cost_of(ng, na));
             inits_.push_back(Init{t.off, t.len, next, nstr, ng, na});
-            ws_.init_tab.insert(h, (int)inits_.size() - 1);
+            if (single) ws_.init1[key_state] = (int)inits_.size();
+            else ws_.init_tab.insert(h, (int)inits_.size() - 1);
         }
         ws_.tarcs.push_back(TArc{t.src, t.label, repo_.concat(common, nstr), next, tg + ng, ta + na});
     }
