@@ -1477,10 +1477,10 @@ std::vector<WordSpan> mbr_solve_host(const MbrJob &job, LatticeStats *stats) {
     std::vector<WordSpan> result;
     if (job.N <= 0) return result;
     struct Buf {
-        std::vector<double> ad, bd, cq, m12a, m12b, vala, valb, pb, bq;
+        std::vector<double> ad, bd, cq, m12a, m12b, vala, valb;
         std::vector<char> b_all;
         std::vector<MbrAcc> acc;
-        std::vector<int> acc_n, R, R2, words, rh;
+        std::vector<int> acc_n, R, R2, words, rh, nz_lo, nz_hi;
         std::vector<float> tb, te, conf, otb, ote, oconf;
     };
     static thread_local Buf b;
@@ -1492,16 +1492,20 @@ std::vector<WordSpan> mbr_solve_host(const MbrJob &job, LatticeStats *stats) {
             b.bd.resize(nw);
         }
         if (b.b_all.size() < job.arcs.size() * (size_t)w_cap) b.b_all.resize(job.arcs.size() * (size_t)w_cap);
-        for (std::vector<double> *v : {&b.cq, &b.m12a, &b.m12b, &b.vala, &b.valb, &b.pb, &b.bq})
+        for (std::vector<double> *v : {&b.cq, &b.m12a, &b.m12b, &b.vala, &b.valb})
             if ((int)v->size() < w_cap) v->resize(w_cap);
         if (b.acc.size() < (size_t)w_cap * acc_cap) b.acc.resize((size_t)w_cap * acc_cap);
         for (std::vector<int> *v : {&b.acc_n, &b.R, &b.R2, &b.words, &b.rh})
             if ((int)v->size() < w_cap) v->resize(w_cap);
+        if ((int)b.nz_lo.size() < job.N + 1) {
+            b.nz_lo.resize(job.N + 1);
+            b.nz_hi.resize(job.N + 1);
+        }
         for (std::vector<float> *v : {&b.tb, &b.te, &b.conf, &b.otb, &b.ote, &b.oconf})
             if ((int)v->size() < w_cap) v->resize(w_cap);
         MbrView view{job.N, (int)job.arcs.size(), job.arcs.data(), job.pre_off.data(), job.state_times.data(), job.post.data()};
         MbrScratch sc{w_cap, acc_cap, b.ad.data(), b.bd.data(), b.b_all.data(), b.cq.data(), b.m12a.data(), b.m12b.data(), b.vala.data(), b.valb.data(),
-                      b.pb.data(), b.bq.data(), b.rh.data(), b.acc.data(), b.acc_n.data(), b.R.data(), b.R2.data(), b.tb.data(), b.te.data(), b.conf.data()};
+                      b.rh.data(), b.nz_lo.data(), b.nz_hi.data(), b.acc.data(), b.acc_n.data(), b.R.data(), b.R2.data(), b.tb.data(), b.te.data(), b.conf.data()};
         MbrOut out{};
         mbr_solve(view, sc, job.R0.data(), (int)job.R0.size(), &out, b.words.data(), b.otb.data(), b.ote.data(), b.oconf.data());
         if (out.status == 1) {

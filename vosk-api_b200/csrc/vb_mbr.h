@@ -41,8 +41,8 @@ struct MbrScratch {
     double *alpha_dash, *beta_dash;           // [(N + 1) * w_cap]
     char *b_all;                              // [n_arcs * w_cap]
     double *cq, *m12a, *m12b, *vala, *valb;   // [w_cap] rows of the arc in hand
-    double *pb, *bq;                          // [w_cap] backward: p * beta_dash(n, q), beta_dash_arc(q)
     int *rh;                                  // [w_cap] decode step: the position's best word
+    int *nz_lo, *nz_hi;                       // [N + 1] backward: range of a node's non-zero beta_dash cells
     MbrAcc *acc;                              // [w_cap * acc_cap]
     int *acc_n;                               // [w_cap]
     int *R, *R2;                              // [w_cap]
@@ -141,23 +141,36 @@ VB_HD void mbr_solve(const MbrView &v, const MbrScratch &s, const int *R0, int n
                     first[j] = ads[0] + l_eps;
                 }
                 VB_MBR_SYNC();
-                for (int j = 0; j < na; j++) {
-                    if (lane != (VB_MBR_LANES > 1 ? j : 0)) continue;
-                    const double *m12 = j ? s.m12b : s.m12a;
-                    double *val = j ? s.valb : s.vala;
-                    char *bk = s.b_all + (long long)(k + j) * W;
-                    double prev = first[j];
-                    val[0] = prev;
+                if (na == 2) {  // two independent chains side by side (the chain is latency-bound: one add and one compare per position)
+                    char *bka = s.b_all + (long long)k * W, *bkb = s.b_all + (long long)(k + 1) * W;
+                    double prev_a = first[0], prev_b = first[1];
+                    s.vala[0] = prev_a;
+                    s.valb[0] = prev_b;
+                    for (int q = 1; q <= Q; q++) {
+                        const double c = s.cq[q];
+                        const double a3a = prev_a + c, a3b = prev_b + c;
+                        const double ma = s.m12a[q], mb = s.m12b[q];
+                        const bool ta = !(ma <= a3a), tb = !(mb <= a3b);
+                        prev_a = ta ? a3a : ma;
+                        prev_b = tb ? a3b : mb;
+                        s.vala[q] = prev_a;
+                        s.valb[q] = prev_b;
+                        bka[q] = ta ? 3 : bka[q];
+                        bkb[q] = tb ? 3 : bkb[q];
+                    }
+                } else {
+                    char *bk = s.b_all + (long long)k * W;
+                    double prev = first[0];
+                    s.vala[0] = prev;
                     for (int q = 1; q <= Q; q++) {
                         const double a3 = prev + s.cq[q];
-                        const double m = m12[q];
+                        const double m = s.m12a[q];
                         const bool three = !(m <= a3);
                         prev = three ? a3 : m;
-                        val[q] = prev;
-                        if (three) bk[q] = 3;
+                        s.vala[q] = prev;
+                        bk[q] = three ? 3 : bk[q];
                     }
                 }
-                VB_MBR_SYNC();
                 for (int j = 0; j < na; j++) {  // (arc order: the sums into the node are those of the plain loop)
                     const double p = v.post[k + j];
                     const double *val = j ? s.valb : s.vala;
@@ -167,12 +180,9 @@ VB_HD void mbr_solve(const MbrView &v, const MbrScratch &s, const int *R0, int n
                 k += na;
             }
         }
-        // ---- backward.  Arcs are taken one at a time, in order (every sum below is order-sensitive across arcs); within an arc the
-        // positions are independent except for (a) the carry of case 3 into q - 1 — a short serial chain on lane 0 — and (b) the two
-        // contributions a cell of the start node can get from one arc: from q + 1 by case 1 and from q by case 2, in that order —
-        // two passes.  The accumulators of a position belong to that position alone. ----
-        if (lane == 0) s.beta_dash[(long long)N * W + Q] = 1.0;
-        VB_MBR_SYNC();
+        // ---- backward: serial (every sum below is order-sensitive).  beta_dash is sparse — only the cells on optimal alignments are
+        // non-zero — so every node carries the range of its non-zero cells and an arc visits that range only (a cell whose
+        // beta_dash_arc is zero contributes nothing: skipping it changes no sum) ----
         auto acc_add = [&](int q, int word, double g, double tb, double te) -> bool {
             MbrAcc *aq = s.acc + (long long)q * s.acc_cap;
             const int na = s.acc_n[q];
@@ -195,70 +205,74 @@ VB_HD void mbr_solve(const MbrView &v, const MbrScratch &s, const int *R0, int n
             }
             return true;
         };
-        int bad = 0;
+        for (int n = 0; n <= N; n++) {
+            s.nz_lo[n] = W;
+            s.nz_hi[n] = -1;
+        }
+        s.beta_dash[(long long)N * W + Q] = 1.0;
+        s.nz_lo[N] = s.nz_hi[N] = Q;
         for (int n = N; n >= 2 && !status; n--) {
+            const int lo_n = s.nz_lo[n], hi_n = s.nz_hi[n];
+            if (hi_n < 0) continue;  // nothing reaches the end from here
             const double *bdn = s.beta_dash + (long long)n * W;
-            for (int k = v.pre_off[n]; k < v.pre_off[n + 1]; k++) {
+            for (int k = v.pre_off[n]; k < v.pre_off[n + 1] && !status; k++) {
                 const MbrArc arc = v.arcs[k];
                 const int s_a = arc.start, w_a = arc.word;
                 double *bds = s.beta_dash + (long long)s_a * W;
                 const char *b_arc = s.b_all + (long long)k * W;
                 const double p = v.post[k];
                 const double t_s = v.state_times[s_a], t_n = v.state_times[n];
-                for (int q = lane; q <= Q; q += VB_MBR_LANES) s.pb[q] = VB_MBR_MUL(p, bdn[q]);
-                VB_MBR_SYNC();
-                if (lane == 0) {
-                    double carry = 0.0;  // beta_dash_arc(q) accumulated from case 3 of q + 1
-                    for (int q = Q; q >= 1; q--) {
-                        const double b = VB_MBR_ADD(carry, s.pb[q]);
-                        s.bq[q] = b;
-                        carry = (b != 0.0 && b_arc[q] == 3) ? b : 0.0;
-                    }
-                    s.bq[0] = VB_MBR_ADD(carry, s.pb[0]);
-                }
-                VB_MBR_SYNC();
-                for (int q = 1 + lane; q <= Q; q += VB_MBR_LANES) {
-                    const double b = s.bq[q];
+                int lo_s = s.nz_lo[s_a], hi_s = s.nz_hi[s_a];
+                double carry = 0.0;  // beta_dash_arc(q) accumulated from case 3 of q + 1
+                int q = hi_n;
+                for (; q >= 1; q--) {
+                    if (q < lo_n && carry == 0.0) break;  // below the node's range and nothing carried: all zero from here on
+                    const double b = carry + p * bdn[q];
+                    carry = 0.0;
                     if (b == 0.0) continue;  // (adding an exact zero changes no sum; Kaldi's maps would only gain zero entries)
-                    const char c = b_arc[q];
-                    if (c == 1) {
-                        bds[q - 1] += b;
-                        if (!acc_add(q, w_a, b, VB_MBR_MUL(t_s, b), VB_MBR_MUL(t_n, b))) bad = 1;
-                    } else if (c == 3) {
-                        const double tt = VB_MBR_MUL(t_n, b);
-                        if (!acc_add(q, 0, b, tt, tt)) bad = 1;
+                    switch (b_arc[q]) {
+                        case 1:
+                            bds[q - 1] += b;
+                            lo_s = q - 1 < lo_s ? q - 1 : lo_s;
+                            hi_s = q - 1 > hi_s ? q - 1 : hi_s;
+                            if (!acc_add(q, w_a, b, t_s * b, t_n * b)) status = 2;
+                            break;
+                        case 2:
+                            bds[q] += b;
+                            lo_s = q < lo_s ? q : lo_s;
+                            hi_s = q > hi_s ? q : hi_s;
+                            break;
+                        case 3: {
+                            carry = b;
+                            const double tt = t_n * b;
+                            if (!acc_add(q, 0, b, tt, tt)) status = 2;
+                            break;
+                        }
                     }
                 }
-                VB_MBR_SYNC();
-                for (int q = 1 + lane; q <= Q; q += VB_MBR_LANES) {
-                    const double b = s.bq[q];
-                    if (b != 0.0 && b_arc[q] == 2) bds[q] += b;
+                if (q == 0) {  // (an early exit means the carry and beta_dash(n, 0) are zero)
+                    const double b0 = carry + p * bdn[0];
+                    bds[0] += b0;
+                    if (b0 != 0.0) {
+                        lo_s = 0;
+                        hi_s = hi_s < 0 ? 0 : hi_s;
+                    }
                 }
-                if (lane == 0) bds[0] += s.bq[0];
-                VB_MBR_SYNC();
+                s.nz_lo[s_a] = lo_s;
+                s.nz_hi[s_a] = hi_s;
             }
-            if (VB_MBR_ANY(bad)) status = 2;
         }
         if (!status) {
             const double *bd1 = s.beta_dash + (long long)1 * W;
             const double t1 = v.state_times[1];
-            if (lane == 0) {
-                double carry = 0.0;
-                for (int q = Q; q >= 1; q--) {
-                    const double b = carry + bd1[q];
-                    carry = b;
-                    s.bq[q] = b;
-                }
+            double carry = 0.0;
+            for (int q = Q; q >= 1; q--) {
+                const double b = carry + bd1[q];
+                carry = b;
+                const double tt = t1 * b;
+                if (!acc_add(q, 0, b, tt, tt)) status = 2;
             }
-            VB_MBR_SYNC();
-            for (int q = 1 + lane; q <= Q; q += VB_MBR_LANES) {
-                const double b = s.bq[q];
-                const double tt = VB_MBR_MUL(t1, b);
-                if (!acc_add(q, 0, b, tt, tt)) bad = 1;
-            }
-            if (VB_MBR_ANY(bad)) status = 2;
         }
-        VB_MBR_SYNC();
         if (status) break;
         // ---- MbrDecode step: the positions' best words side by side, then the serial part (R, delta, one-best times) on lane 0 ----
         for (int q = 1 + lane; q <= Q; q += VB_MBR_LANES) {
