@@ -141,34 +141,57 @@ VB_HD void mbr_solve(const MbrView &v, const MbrScratch &s, const int *R0, int n
                     first[j] = ads[0] + l_eps;
                 }
                 VB_MBR_SYNC();
-                if (na == 2) {  // two independent chains side by side (the chain is latency-bound: one add and one compare per position)
+                // The chain.  The normalized hypothesis alternates epsilon (odd q: c = 0) and word (even q: c = 1), and the row is never
+                // negative, so at the odd positions a3 = prev + 0 is prev itself: the add is left out there (same value, same
+                // comparison), which shortens the dependency chain from an add and a compare per position to three operations per two.
+                if (na == 2) {  // two independent chains side by side (the chain is latency-bound)
                     char *bka = s.b_all + (long long)k * W, *bkb = s.b_all + (long long)(k + 1) * W;
                     double prev_a = first[0], prev_b = first[1];
                     s.vala[0] = prev_a;
                     s.valb[0] = prev_b;
-                    for (int q = 1; q <= Q; q++) {
-                        const double c = s.cq[q];
-                        const double a3a = prev_a + c, a3b = prev_b + c;
-                        const double ma = s.m12a[q], mb = s.m12b[q];
-                        const bool ta = !(ma <= a3a), tb = !(mb <= a3b);
-                        prev_a = ta ? a3a : ma;
-                        prev_b = tb ? a3b : mb;
-                        s.vala[q] = prev_a;
-                        s.valb[q] = prev_b;
-                        bka[q] = ta ? 3 : bka[q];
-                        bkb[q] = tb ? 3 : bkb[q];
+                    for (int q = 1; q <= Q; q += 2) {
+                        {
+                            const double ma = s.m12a[q], mb = s.m12b[q];
+                            const bool ta = !(ma <= prev_a), tb = !(mb <= prev_b);
+                            prev_a = ta ? prev_a : ma;
+                            prev_b = tb ? prev_b : mb;
+                            s.vala[q] = prev_a;
+                            s.valb[q] = prev_b;
+                            bka[q] = ta ? 3 : bka[q];
+                            bkb[q] = tb ? 3 : bkb[q];
+                        }
+                        if (q + 1 <= Q) {
+                            const double a3a = prev_a + 1.0, a3b = prev_b + 1.0;
+                            const double ma = s.m12a[q + 1], mb = s.m12b[q + 1];
+                            const bool ta = !(ma <= a3a), tb = !(mb <= a3b);
+                            prev_a = ta ? a3a : ma;
+                            prev_b = tb ? a3b : mb;
+                            s.vala[q + 1] = prev_a;
+                            s.valb[q + 1] = prev_b;
+                            bka[q + 1] = ta ? 3 : bka[q + 1];
+                            bkb[q + 1] = tb ? 3 : bkb[q + 1];
+                        }
                     }
                 } else {
                     char *bk = s.b_all + (long long)k * W;
                     double prev = first[0];
                     s.vala[0] = prev;
-                    for (int q = 1; q <= Q; q++) {
-                        const double a3 = prev + s.cq[q];
-                        const double m = s.m12a[q];
-                        const bool three = !(m <= a3);
-                        prev = three ? a3 : m;
-                        s.vala[q] = prev;
-                        bk[q] = three ? 3 : bk[q];
+                    for (int q = 1; q <= Q; q += 2) {
+                        {
+                            const double m = s.m12a[q];
+                            const bool three = !(m <= prev);
+                            prev = three ? prev : m;
+                            s.vala[q] = prev;
+                            bk[q] = three ? 3 : bk[q];
+                        }
+                        if (q + 1 <= Q) {
+                            const double a3 = prev + 1.0;
+                            const double m = s.m12a[q + 1];
+                            const bool three = !(m <= a3);
+                            prev = three ? a3 : m;
+                            s.vala[q + 1] = prev;
+                            bk[q + 1] = three ? 3 : bk[q + 1];
+                        }
                     }
                 }
                 for (int j = 0; j < na; j++) {  // (arc order: the sums into the node are those of the plain loop)
