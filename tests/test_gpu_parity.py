@@ -593,3 +593,50 @@ def test_stream_result_does_not_depend_on_its_device(model_root):
     # a second pass with the streams shifted by one: every stream now lives on another device
     shifted, _ = helpers.run_engine(mdir, waves[1:] + waves[:1], options="num-channels=8,max-batch-size=8,max-seconds=8,devices=all", capture=False)
     assert [g["text"] for g in shifted] == [g["text"] for g in one[1:] + one[:1]]
+
+
+def test_native_feeder_and_resident_passes_give_the_same_texts(model_root):
+    """Three ways into the engine, one result: the Python round-robin driver, the library's native multi-threaded feeder
+    (vosk_b200_feed_streams: the reference ABI calls from several host threads) and the device-resident run, the latter decoded
+    three times over back to back (vosk_batch_model_run_resident_passes: the streams of pass p + 1 start while the lattice chain
+    of pass p still runs) — identical texts, no pass differing from another."""
+    import vosk
+    mdir = model_root("tiny")
+    waves = _waves([1.4, 3.3, 0.6, 2.5, 4.1, 0.9, 2.0, 1.1, 3.0, 2.7], seed0=4200)
+    ref, _ = helpers.run_engine(mdir, waves, options="num-channels=6,max-batch-size=4,max-seconds=8", capture=False)
+    want = [g["text"] for g in ref]
+    m = vosk.BatchModel(mdir, options="num-channels=6,max-batch-size=4,max-seconds=8")
+    for threads in (1, 3):
+        assert m.FeedStreams(waves, bytes_per_call=6400, threads=threads) == want
+    lengths = np.array([len(w) for w in waves], dtype=np.int32)
+    mat = np.zeros((len(waves), int((lengths.max() + 7) // 8 * 8)), dtype=np.int16)
+    for i, w in enumerate(waves):
+        mat[i, :len(w)] = w
+    big = vosk.BatchModel(mdir, options="num-channels=10,max-batch-size=10,max-seconds=8")
+    _, texts = big.RunResident(mat, lengths, passes=3)
+    assert list(texts) == want and big.resident_mismatches == 0
+    st = big.Stats()
+    assert st["truncated"] == 0 and st["lattice_fallbacks"] == 0
+    del m, big
+
+
+def test_acoustic_scale_is_a_plain_product(model_root, oracle_lib):
+    """acoustic-scale (bench.py's dense-frontier leg): the search sees fp32(scale * log-likelihood), nothing else changes — token
+    log, lattice and text equal the oracle's on the scaled log-likelihoods, and the frontier is wider than at scale 1."""
+    import vbmodel
+    mdir = model_root("small")
+    model = vbmodel.load_model_dir(mdir)
+    waves = _waves([2.3], seed0=4300)
+    base, st1 = helpers.run_engine(mdir, waves, options="num-channels=2,max-batch-size=2,max-seconds=10")
+    got, st2 = helpers.run_engine(mdir, waves, options="num-channels=2,max-batch-size=2,max-seconds=10,acoustic-scale=0.5")
+    assert st2["tokens"] > 1.5 * st1["tokens"]
+    P = int(model["cfg"]["num-pdfs"])
+    g = got[0]
+    ll = (np.float32(0.5) * g["loglikes"].reshape(-1, P)).astype(np.float32)
+    dec = oracle_lib.decode(model, ll, lattice_beam=6.0)
+    fo = g["frame_off"]
+    np.testing.assert_array_equal(fo.astype(np.int64), dec["offsets"])
+    st, co, ar, pv = helpers.canonical_tokens(fo, g["tok_state"], g["tok_cost"], g["tok_arc"], g["tok_prev"])
+    np.testing.assert_array_equal(st, dec["state"])
+    np.testing.assert_array_equal(co.view(np.uint32), dec["cost"].view(np.uint32))
+    assert g["text"] == helpers.oracle_lattice_text(model, dec, 6.0)
