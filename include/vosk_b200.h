@@ -91,6 +91,10 @@ int64_t vosk_batch_recognizer_debug_get(VoskBatchRecognizer *recognizer, const c
  * receives one malloc'd string per stream (a stream's segment texts concatenated; free with vosk_b200_free).  0 = ok. */
 int vosk_b200_feed_streams(VoskBatchModel *model, const int16_t *const *samples, const int *lengths, int n, int bytes_per_call, int threads,
                            char **results);
+/* The same with the streams fed `passes` times over (new recognizers every pass) before the one vosk_batch_model_wait; results =
+ * the last pass's texts, *mismatches (may be NULL) = streams of earlier passes whose text differs from it. */
+int vosk_b200_feed_streams_passes(VoskBatchModel *model, const int16_t *const *samples, const int *lengths, int n, int bytes_per_call, int threads,
+                                  int passes, char **results, int *mismatches);
 void vosk_b200_free(void *p);
 
 /* Host-only hooks (no GPU needed; used by the CPU test suite).

@@ -606,8 +606,8 @@ def test_native_feeder_and_resident_passes_give_the_same_texts(model_root):
     ref, _ = helpers.run_engine(mdir, waves, options="num-channels=6,max-batch-size=4,max-seconds=8", capture=False)
     want = [g["text"] for g in ref]
     m = vosk.BatchModel(mdir, options="num-channels=6,max-batch-size=4,max-seconds=8")
-    for threads in (1, 3):
-        assert m.FeedStreams(waves, bytes_per_call=6400, threads=threads) == want
+    for threads, passes in ((1, 1), (3, 2)):
+        assert m.FeedStreams(waves, bytes_per_call=6400, threads=threads, passes=passes) == want and m.feed_mismatches == 0
     lengths = np.array([len(w) for w in waves], dtype=np.int32)
     mat = np.zeros((len(waves), int((lengths.max() + 7) // 8 * 8)), dtype=np.int16)
     for i, w in enumerate(waves):

@@ -503,55 +503,74 @@ int vosk_b200_lattice_result(const char *model_dir, int n_states, int start, int
 // front_result / pop — from `threads` host threads (stream i belongs to thread i % threads).
 int vosk_b200_feed_streams(VoskBatchModel *model, const int16_t *const *samples, const int *lengths, int n, int bytes_per_call, int threads,
                            char **results) {
-    if (!model || !samples || !lengths || n <= 0 || bytes_per_call < 2) return -1;
+    return vosk_b200_feed_streams_passes(model, samples, lengths, n, bytes_per_call, threads, 1, results, nullptr);
+}
+// The same with the n streams fed `passes` times over (new recognizers every pass) before the one vosk_batch_model_wait: the
+// accept calls never block, so the streams of pass p + 1 queue up behind pass p and start as channels come free, the lattice
+// chain of one pass runs beside the search of the next.  results = the last pass's texts; *mismatches (may be NULL) = streams
+// of earlier passes whose text differs from it.
+int vosk_b200_feed_streams_passes(VoskBatchModel *model, const int16_t *const *samples, const int *lengths, int n, int bytes_per_call, int threads,
+                                  int passes, char **results, int *mismatches) {
+    if (!model || !samples || !lengths || n <= 0 || bytes_per_call < 2 || passes < 1) return -1;
     try {
-        std::vector<VoskBatchRecognizer *> recs(n, nullptr);
-        for (int i = 0; i < n; i++) {
-            recs[i] = vosk_batch_recognizer_new(model, 16000.0f);
-            if (!recs[i]) throw std::runtime_error("recognizer creation failed");
-        }
+        std::vector<VoskBatchRecognizer *> recs((size_t)n * passes, nullptr);
         threads = std::max(1, std::min(threads, n));
-        std::vector<std::thread> pool;
-        for (int t = 0; t < threads; t++)
-            pool.emplace_back([&, t] {
-                const int per = bytes_per_call / 2;
-                std::vector<long long> pos(n, 0);
-                bool any = true;
-                while (any) {
-                    any = false;
-                    for (int i = t; i < n; i += threads) {
-                        if (pos[i] < 0) continue;
-                        const long long left = (long long)lengths[i] - pos[i];
-                        if (left <= 0) {
-                            vosk_batch_recognizer_finish_stream(recs[i]);
-                            pos[i] = -1;
-                            continue;
+        for (int p = 0; p < passes; p++) {
+            VoskBatchRecognizer **rp = recs.data() + (size_t)p * n;
+            for (int i = 0; i < n; i++) {
+                rp[i] = vosk_batch_recognizer_new(model, 16000.0f);
+                if (!rp[i]) throw std::runtime_error("recognizer creation failed");
+            }
+            std::vector<std::thread> pool;
+            for (int t = 0; t < threads; t++)
+                pool.emplace_back([&, t] {
+                    const int per = bytes_per_call / 2;
+                    std::vector<long long> pos(n, 0);
+                    bool any = true;
+                    while (any) {
+                        any = false;
+                        for (int i = t; i < n; i += threads) {
+                            if (pos[i] < 0) continue;
+                            const long long left = (long long)lengths[i] - pos[i];
+                            if (left <= 0) {
+                                vosk_batch_recognizer_finish_stream(rp[i]);
+                                pos[i] = -1;
+                                continue;
+                            }
+                            const int take = (int)std::min<long long>(left, per);
+                            vosk_batch_recognizer_accept_waveform(rp[i], (const char *)(samples[i] + pos[i]), take * 2);
+                            pos[i] += take;
+                            any = true;
                         }
-                        const int take = (int)std::min<long long>(left, per);
-                        vosk_batch_recognizer_accept_waveform(recs[i], (const char *)(samples[i] + pos[i]), take * 2);
-                        pos[i] += take;
-                        any = true;
                     }
-                }
-                for (int i = t; i < n; i += threads)
-                    if (pos[i] >= 0) vosk_batch_recognizer_finish_stream(recs[i]);
-            });
-        for (auto &th : pool) th.join();
+                    for (int i = t; i < n; i += threads)
+                        if (pos[i] >= 0) vosk_batch_recognizer_finish_stream(rp[i]);
+                });
+            for (auto &th : pool) th.join();
+        }
         vosk_batch_model_wait(model);
-        for (int i = 0; i < n; i++) {
-            if (results) {
+        std::vector<std::string> last(n);
+        int bad = 0;
+        for (int p = passes - 1; p >= 0; p--)
+            for (int i = 0; i < n; i++) {
+                VoskBatchRecognizer *r = recs[(size_t)p * n + i];
                 std::string all;
                 for (;;) {
-                    const char *r = vosk_batch_recognizer_front_result(recs[i]);
-                    if (!r || !*r) break;
-                    all += r;
-                    vosk_batch_recognizer_pop(recs[i]);
+                    const char *t = vosk_batch_recognizer_front_result(r);
+                    if (!t || !*t) break;
+                    all += t;
+                    vosk_batch_recognizer_pop(r);
                 }
-                results[i] = (char *)malloc(all.size() + 1);
-                memcpy(results[i], all.c_str(), all.size() + 1);
+                if (p == passes - 1) last[i] = std::move(all);
+                else if (all != last[i]) bad++;
+                vosk_batch_recognizer_free(r);
             }
-            vosk_batch_recognizer_free(recs[i]);
-        }
+        if (results)
+            for (int i = 0; i < n; i++) {
+                results[i] = (char *)malloc(last[i].size() + 1);
+                memcpy(results[i], last[i].c_str(), last[i].size() + 1);
+            }
+        if (mismatches) *mismatches = bad;
         return 0;
     } catch (const std::exception &e) {
         vb::log_msg(-1, "feed_streams: %s", e.what());

@@ -97,15 +97,19 @@ class BatchModel(object):
         _c.vosk_batch_model_latency(self._handle, buf, int(reset))
         return dict(p50=buf[0], p90=buf[1], p99=buf[2], mean=buf[3], count=int(buf[4]))
 
-    def FeedStreams(self, waves, bytes_per_call=8000, threads=8, want_results=True):
-        """Native multi-threaded feeder (vosk_b200_feed_streams): waves = list of int16 numpy arrays; returns the result texts."""
+    def FeedStreams(self, waves, bytes_per_call=8000, threads=8, want_results=True, passes=1):
+        """Native multi-threaded feeder (vosk_b200_feed_streams_passes): waves = list of int16 numpy arrays, fed `passes` times
+        over before the one Wait; returns the last pass's result texts (self.feed_mismatches = streams of earlier passes whose
+        text differed)."""
         import numpy as np
         arrs = [np.ascontiguousarray(w, dtype=np.int16) for w in waves]
         n = len(arrs)
         ptrs = _ffi.new("int16_t *[]", [_ffi.cast("int16_t *", a.ctypes.data) for a in arrs])
         lens = _ffi.new("int[]", [len(a) for a in arrs])
         res = _ffi.new("char *[]", n) if want_results else _ffi.NULL
-        rc = _c.vosk_b200_feed_streams(self._handle, ptrs, lens, n, int(bytes_per_call), int(threads), res)
+        bad = _ffi.new("int *")
+        rc = _c.vosk_b200_feed_streams_passes(self._handle, ptrs, lens, n, int(bytes_per_call), int(threads), int(passes), res, bad)
+        self.feed_mismatches = int(bad[0])
         if rc != 0:
             raise Exception("feed_streams failed")
         out = []
