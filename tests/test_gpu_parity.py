@@ -72,7 +72,7 @@ def _check_stream(model, oracle, wave, got, fpc, tol_ll=1e-3, lattice_beam=6.0, 
 
 
 @pytest.mark.parametrize("tc", [1, 0])
-@pytest.mark.parametrize("fpc", [51, 9])
+@pytest.mark.parametrize("fpc", [51, 9, 120])  # 120: several 64-frame passes of the i-vector statistics kernel
 def test_tiny_model_all_stages(model_root, oracle_lib, fpc, tc):
     import vbmodel
     mdir = model_root("tiny")

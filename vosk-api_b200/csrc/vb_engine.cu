@@ -207,14 +207,15 @@ void Engine::upload_model() {
         for (int a = 0; a < F; a++)
             for (int k = 0; k <= S; k++) lda_t[(size_t)k * F + a] = lda.f32()[(size_t)a * (S + 1) + k];
         const float *mi = m.iv_dubm.at("means_invvars").f32(), *iv = m.iv_dubm.at("inv_vars").f32();
-        std::vector<float> mi_t((size_t)F * G), iv_t((size_t)F * G);
+        std::vector<float> mi_t((size_t)F * G), niv_t((size_t)F * G);
         for (int g = 0; g < G; g++)
             for (int a = 0; a < F; a++) {
                 mi_t[(size_t)a * G + g] = mi[(size_t)g * F + a];
-                iv_t[(size_t)a * G + g] = iv[(size_t)g * F + a];
+                niv_t[(size_t)a * G + g] = -0.5f * iv[(size_t)g * F + a];
             }
         const float *M = m.iv_ie.at("M").f32(), *Si = m.iv_ie.at("sigma_inv").f32();
-        std::vector<float> sim((size_t)G * F * D), U((size_t)G * D * D);
+        const size_t NT = (size_t)D * (D + 1) / 2;
+        std::vector<float> sim((size_t)G * F * D), U(G * NT);  // U: packed lower triangle (Kaldi keeps it as an SpMatrix)
         std::vector<double> tmp((size_t)F * D);
         for (int g = 0; g < G; g++) {
             const float *Mg = M + (size_t)g * F * D, *Sg = Si + (size_t)g * F * F;
@@ -226,17 +227,17 @@ void Engine::upload_model() {
                     sim[((size_t)g * F + a) * D + d] = (float)s;
                 }
             for (int d = 0; d < D; d++)
-                for (int e2 = 0; e2 < D; e2++) {
+                for (int e2 = 0; e2 <= d; e2++) {
                     double s = 0;
                     for (int a = 0; a < F; a++) s += (double)Mg[a * D + d] * tmp[(size_t)a * D + e2];
-                    U[((size_t)g * D + d) * D + e2] = (float)s;
+                    U[g * NT + (size_t)d * (d + 1) / 2 + e2] = (float)s;
                 }
         }
         const double *cm = m.iv_cmvn.at("stats").f64();
         std::vector<double> gsum(cm, cm + F);
         iv_model_ = IvecModel{F, D, G, S,
                               dev_upload(allocs_, lda_t), dev_upload(allocs_, m.iv_dubm.at("gconsts").f32(), (size_t)G),
-                              dev_upload(allocs_, mi_t), dev_upload(allocs_, iv_t), dev_upload(allocs_, sim), dev_upload(allocs_, U),
+                              dev_upload(allocs_, mi_t), dev_upload(allocs_, niv_t), dev_upload(allocs_, sim), dev_upload(allocs_, U),
                               dev_upload(allocs_, gsum), cm[F], m.prior_offset,
                               cfg_.num_gselect, cfg_.min_post, cfg_.posterior_scale, cfg_.max_count, cfg_.cmn_window, cfg_.global_frames};
     }
@@ -359,9 +360,13 @@ void Engine::alloc_state() {
     iv_state_.cmvn_sum = dev_alloc<double>(allocs_, (size_t)C * F, 0);
     iv_state_.norm_ring = dev_alloc<float>(allocs_, (size_t)C * kNormRing * F, 0);
     iv_state_.lin = dev_alloc<double>(allocs_, (size_t)C * D, 0);
-    iv_state_.quad = dev_alloc<double>(allocs_, (size_t)C * D * D, 0);
+    iv_state_.quad = dev_alloc<double>(allocs_, (size_t)C * D * (D + 1) / 2, 0);
     iv_state_.num_frames = dev_alloc<double>(allocs_, (size_t)C, 0);
     iv_state_.ivec = dev_alloc<float>(allocs_, (size_t)C * D, 0);
+    iv_frames_cap_ = vbk_ivector_frames_cap(spc);
+    d_iv_sel_g_ = dev_alloc<int>(allocs_, (size_t)L * iv_frames_cap_ * 8, 0);
+    d_iv_sel_w_ = dev_alloc<float>(allocs_, (size_t)L * iv_frames_cap_ * 8, 0);
+    d_iv_fu_ = dev_alloc<float>(allocs_, (size_t)L * iv_frames_cap_ * F, 0);
     d_carry_ = dev_alloc<int16_t>(allocs_, (size_t)C * kCarryMax, 0);
     d_node_end_ = dev_alloc<int>(allocs_, (size_t)C * kMaxNodes, 0);
     // decoder: per-channel state shared by all slots
@@ -873,9 +878,9 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     VB_CUDA_CHECK(vbk_mfcc(&fa, st));
     sl.launches++;
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[1], st));
-    IvecArgs ia{sl.d_lanes, L, nodes_[0], ctx, iv_model_, iv_state_};
+    IvecArgs ia{sl.d_lanes, L, nodes_[0], ctx, iv_model_, iv_state_, d_iv_sel_g_, d_iv_sel_w_, d_iv_fu_, iv_frames_cap_};
     VB_CUDA_CHECK(vbk_ivector(&ia, st));
-    sl.launches++;
+    sl.launches += 3;
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[2], st));
     NnetPlanArgs pa{sl.d_lanes, L, nn, d_nodes_, d_node_end_, sl.d_table, sl.d_rowoff, SL, sl.d_rows, rows_cap_};
     VB_CUDA_CHECK(vbk_nnet_plan(&pa, st));

@@ -244,6 +244,9 @@ class Engine {
     ResampleTable *d_resample_tables_ = nullptr;
     // per channel / per step state
     IvecState iv_state_{};
+    int *d_iv_sel_g_ = nullptr;    // scratch between the i-vector frame kernel and its statistics kernel (front-end stream order)
+    float *d_iv_sel_w_ = nullptr, *d_iv_fu_ = nullptr;
+    int iv_frames_cap_ = 0;
     int16_t *d_carry_ = nullptr;
     int *d_node_end_ = nullptr;
     DecArgs dec_{};  // template: graph, options and per-channel arrays; each slot adds its own scratch

@@ -68,9 +68,9 @@ struct IvecModel {           // device pointers
     const float *lda_t;      // [splice_dim+1][feat_dim]  (transposed; last row = offset)
     const float *gconsts;    // [G]
     const float *mi_t;       // [F][G] means*inv_vars, transposed
-    const float *iv_t;       // [F][G] inv_vars, transposed
+    const float *niv_t;      // [F][G] -0.5 * inv_vars, transposed
     const float *sim;        // [G][F][D]   Sigma_i^{-1} M_i
-    const float *U;          // [G][D*D]    M_i^T Sigma_i^{-1} M_i
+    const float *U_tri;      // [G][D(D+1)/2]  M_i^T Sigma_i^{-1} M_i, packed lower triangle (row i: columns 0..i)
     const double *gcmvn_sum; // [F] global cmvn sums
     double gcmvn_count;
     float prior_offset;
@@ -82,7 +82,7 @@ struct IvecState {           // per channel, device
     double *cmvn_sum;        // [C][F]
     float *norm_ring;        // [C][kNormRing][F]
     double *lin;             // [C][D]
-    double *quad;            // [C][D*D]
+    double *quad;            // [C][D(D+1)/2]  packed lower triangle
     double *num_frames;      // [C]
     float *ivec;             // [C][D]   current i-vector (prior offset removed)
 };
@@ -95,6 +95,11 @@ struct IvecArgs {
     int context;
     IvecModel m;
     IvecState st;
+    // per-step scratch between the frame kernel and the statistics kernel: [max_lanes][frames_cap] rows
+    int *sel_g;              // [..][kMaxGselect] selected Gaussians of a frame
+    float *sel_w;            // [..][kMaxGselect] their scaled posteriors (0 = pruned)
+    float *fu;               // [..][F] LDA of the raw splice
+    int frames_cap;          // vbk_ivector_frames_cap(samples_per_chunk)
 };
 
 // ---------------- K2: TDNN-F ----------------
@@ -222,7 +227,8 @@ extern "C" {
 int vbk_feat_smem_bytes(int samples_per_chunk);
 cudaError_t vbk_mfcc(const FeatArgs *a, cudaStream_t s);
 cudaError_t vbk_resample(const ResampleArgs *a, cudaStream_t s);
-cudaError_t vbk_ivector(const IvecArgs *a, cudaStream_t s);
+cudaError_t vbk_ivector(const IvecArgs *a, cudaStream_t s);  // three launches
+int vbk_ivector_frames_cap(int samples_per_chunk);
 cudaError_t vbk_nnet_plan(const NnetPlanArgs *a, cudaStream_t s);
 cudaError_t vbk_gemm_fp32(const GemmArgs *a, cudaStream_t s);
 cudaError_t vbk_gemm_tc(const GemmArgs *a, cudaStream_t s);
