@@ -314,25 +314,27 @@ __global__ void __launch_bounds__(64) ivector_cmn_kernel(IvecArgs a) {
     float *nring = a.st.norm_ring + (size_t)ch * kNormRing * F;
     double s = ln.first ? 0.0 : cm_sum[d];
     const double gshare = m.gcmvn_sum[d] / m.gcmvn_count;
-    for (int t0 = ln.frames_before; t0 < ln.frames_after; t0 += 4) {
-        float x[4], xo[4];
+    constexpr int kB = 16;  // frames whose loads go out together
+    for (int t0 = ln.frames_before; t0 < ln.frames_after; t0 += kB) {
+        float x[kB], xo[kB];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {  // the loads of four frames go out together
+        for (int j = 0; j < kB; j++) {
             const int t = t0 + j;
             x[j] = t < ln.frames_after ? ring_row(a.in_node, ch, t)[d] : 0.f;
             xo[j] = t < ln.frames_after && t >= m.cmn_window ? ring_row(a.in_node, ch, t - m.cmn_window)[d] : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < kB; j++) {
             const int t = t0 + j;
-            if (t >= ln.frames_after) break;
-            s += (double)x[j];
-            if (t >= m.cmn_window) s -= (double)xo[j];
-            const double nn = t + 1 < m.cmn_window ? t + 1 : m.cmn_window;
-            const double fg = nn < m.cmn_window ? fmin((double)m.cmn_window - nn, (double)m.global_frames) : 0.0;
-            double tot = s;
-            if (fg > 0.0) tot += fg * gshare;
-            nring[(t & (kNormRing - 1)) * F + d] = (float)((double)x[j] - tot / (nn + fg));
+            if (t < ln.frames_after) {
+                s += (double)x[j];
+                if (t >= m.cmn_window) s -= (double)xo[j];
+                const double nn = t + 1 < m.cmn_window ? t + 1 : m.cmn_window;
+                const double fg = nn < m.cmn_window ? fmin((double)m.cmn_window - nn, (double)m.global_frames) : 0.0;
+                double tot = s;
+                if (fg > 0.0) tot += fg * gshare;
+                nring[(t & (kNormRing - 1)) * F + d] = (float)((double)x[j] - tot / (nn + fg));
+            }
         }
     }
     cm_sum[d] = s;
@@ -391,7 +393,8 @@ __global__ void __launch_bounds__(kIvThreads, 2) ivector_post_kernel(IvecArgs a)
     extern __shared__ __align__(16) float smf[];
     const LaneDesc ln = a.lanes[blockIdx.x];
     const IvecModel &m = a.m;
-    const int F = m.feat_dim, G = m.num_gauss, S = m.splice_dim;
+    constexpr int F = kNumCeps;  // (the loader accepts no other feature dimension: constant strides keep the address arithmetic out of the loops)
+    const int G = m.num_gauss, S = m.splice_dim;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const IvPostLayout L = iv_post_layout(G, F);
     float *win_raw = smf + L.win_raw, *win_nrm = smf + L.win_nrm, *fnT = smf + L.fnT, *fn2T = smf + L.fn2T, *ll = smf + L.ll;
@@ -422,15 +425,14 @@ __global__ void __launch_bounds__(kIvThreads, 2) ivector_post_kernel(IvecArgs a)
                 const float off = __ldg(m.lda_t + (size_t)S * F + d);
                 float u0 = off, u1 = off, u2 = off, n0 = off, n1 = off, n2 = off;
                 for (int o = 0; o < 7; o++) {
-                    const float *w = m.lda_t + (size_t)o * F * F + d;
+                    const float *w = m.lda_t + o * F * F + d;
                     const float4 *xr0 = reinterpret_cast<const float4 *>(win_raw + (t0 + o) * F), *xr1 = reinterpret_cast<const float4 *>(win_raw + (r1 + o) * F),
                                  *xr2 = reinterpret_cast<const float4 *>(win_raw + (r2 + o) * F);
                     const float4 *xn0 = reinterpret_cast<const float4 *>(win_nrm + (t0 + o) * F), *xn1 = reinterpret_cast<const float4 *>(win_nrm + (r1 + o) * F),
                                  *xn2 = reinterpret_cast<const float4 *>(win_nrm + (r2 + o) * F);
-#pragma unroll 2
+#pragma unroll
                     for (int k4 = 0; k4 < F / 4; k4++) {
-                        const float w0 = __ldg(w + (size_t)(4 * k4) * F), w1 = __ldg(w + (size_t)(4 * k4 + 1) * F), w2 = __ldg(w + (size_t)(4 * k4 + 2) * F),
-                                    w3 = __ldg(w + (size_t)(4 * k4 + 3) * F);
+                        const float w0 = __ldg(w + (4 * k4) * F), w1 = __ldg(w + (4 * k4 + 1) * F), w2 = __ldg(w + (4 * k4 + 2) * F), w3 = __ldg(w + (4 * k4 + 3) * F);
                         const float4 a0 = xr0[k4], a1 = xr1[k4], a2 = xr2[k4], b0 = xn0[k4], b1 = xn1[k4], b2 = xn2[k4];
                         u0 = fmaf(w3, a0.w, fmaf(w2, a0.z, fmaf(w1, a0.y, fmaf(w0, a0.x, u0))));
                         u1 = fmaf(w3, a1.w, fmaf(w2, a1.z, fmaf(w1, a1.y, fmaf(w0, a1.x, u1))));
@@ -469,10 +471,13 @@ __global__ void __launch_bounds__(kIvThreads, 2) ivector_post_kernel(IvecArgs a)
                 acc0[t] = c0;
                 acc1[t] = c1;
             }
-#pragma unroll 2
+            const float2 *u0 = m.ubm_t + g0, *u1 = m.ubm_t + g1c;  // {mean * inv_var, -0.5 inv_var} of a Gaussian: one 8-byte load
+#pragma unroll 4
             for (int d = 0; d < F; d++) {
-                const float mi0 = __ldg(m.mi_t + (size_t)d * G + g0), mi1 = __ldg(m.mi_t + (size_t)d * G + g1c);
-                const float iv0 = __ldg(m.niv_t + (size_t)d * G + g0), iv1 = __ldg(m.niv_t + (size_t)d * G + g1c);
+                const float2 p0 = __ldg(u0), p1 = __ldg(u1);
+                u0 += G;
+                u1 += G;
+                const float mi0 = p0.x, iv0 = p0.y, mi1 = p1.x, iv1 = p1.y;
                 const float4 *x4 = reinterpret_cast<const float4 *>(fnT + d * kIvTB), *q4 = reinterpret_cast<const float4 *>(fn2T + d * kIvTB);
 #pragma unroll
                 for (int q = 0; q < kIvTB / 4; q++) {
@@ -632,9 +637,11 @@ __global__ void __launch_bounds__(kIvThreads) ivector_stats_kernel(IvecArgs a) {
                     const int t = __ffsll((long long)mk) - 1;
                     mk &= mk - 1;
                     float w = 0.f;
-#pragma unroll
-                    for (int r = 0; r < kMaxGselect; r++)
-                        if (r < ng && sel_g[t * kMaxGselect + r] == g) w = sel_w[t * kMaxGselect + r];  // (slots beyond ng hold -1)
+                    for (int r = 0; r < ng; r++)
+                        if (sel_g[t * kMaxGselect + r] == g) {
+                            w = sel_w[t * kMaxGselect + r];
+                            break;
+                        }
                     s = fmaf(w, fu[t * F + f], s);
                 }
                 vbuf[i] = s;
@@ -721,10 +728,10 @@ __global__ void __launch_bounds__(kIvThreads) ivector_stats_kernel(IvecArgs a) {
         return;
     }
     for (int j = 0; j < D; j++) {  // right-looking: scale column j, then the rank-1 update of the trailing triangle (warp per row)
-        const double piv = sqrt(fmax(A[tri(j) + j], 1e-300));
-        for (int i = j + 1 + tid; i < D; i += kIvThreads) A[tri(i) + j] /= piv;
+        const double rinv = rsqrt(fmax(A[tri(j) + j], 1e-300));
+        for (int i = j + 1 + tid; i < D; i += kIvThreads) A[tri(i) + j] *= rinv;
         __syncthreads();
-        if (tid == 0) A[tri(j) + j] = piv;  // (nobody reads the diagonal entry again before the substitution)
+        if (tid == 0) A[tri(j) + j] = rinv;  // the diagonal keeps 1 / L_jj: the substitution multiplies (nobody reads it before)
         for (int i = j + 1 + warp; i < D; i += kIvWarps) {
             const double lij = A[tri(i) + j];
             for (int k = j + 1 + lane; k <= i; k += 32) A[tri(i) + k] -= lij * A[tri(k) + j];
@@ -736,14 +743,14 @@ __global__ void __launch_bounds__(kIvThreads) ivector_stats_kernel(IvecArgs a) {
             double s = 0.0;
             for (int k = lane; k < i; k += 32) s += A[tri(i) + k] * bvec[k];
             for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) bvec[i] = (bvec[i] - s) / A[tri(i) + i];
+            if (lane == 0) bvec[i] = (bvec[i] - s) * A[tri(i) + i];
             __syncwarp();
         }
         for (int i = D - 1; i >= 0; i--) {
             double s = 0.0;
             for (int k = i + 1 + lane; k < D; k += 32) s += A[tri(k) + i] * bvec[k];
             for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) bvec[i] = (bvec[i] - s) / A[tri(i) + i];
+            if (lane == 0) bvec[i] = (bvec[i] - s) * A[tri(i) + i];
             __syncwarp();
         }
         for (int d = lane; d < D; d += 32) out[d] = (float)(bvec[d] - (d == 0 ? (double)m.prior_offset : 0.0));
@@ -752,7 +759,7 @@ __global__ void __launch_bounds__(kIvThreads) ivector_stats_kernel(IvecArgs a) {
 
 extern "C" cudaError_t vbk_ivector(const IvecArgs *a, cudaStream_t s) {
     if (a->num_lanes <= 0) return cudaSuccess;
-    if (a->m.num_gauss > 1024 || a->m.ivec_dim > kIvThreads || a->m.ivec_dim % 4 || a->m.feat_dim > 64 || a->m.feat_dim % 4 ||
+    if (a->m.num_gauss > 1024 || a->m.ivec_dim > kIvThreads || a->m.ivec_dim % 4 || a->m.feat_dim != kNumCeps ||
         a->m.num_gselect > kMaxGselect || a->m.splice_dim != 7 * a->m.feat_dim || !a->sel_g || !a->sel_w || !a->fu || a->frames_cap < kIvTB)
         return cudaErrorInvalidValue;
     const int smem_post = iv_post_layout(a->m.num_gauss, a->m.feat_dim).total_floats * 4;

@@ -207,12 +207,9 @@ void Engine::upload_model() {
         for (int a = 0; a < F; a++)
             for (int k = 0; k <= S; k++) lda_t[(size_t)k * F + a] = lda.f32()[(size_t)a * (S + 1) + k];
         const float *mi = m.iv_dubm.at("means_invvars").f32(), *iv = m.iv_dubm.at("inv_vars").f32();
-        std::vector<float> mi_t((size_t)F * G), niv_t((size_t)F * G);
+        std::vector<float2> ubm_t((size_t)F * G);
         for (int g = 0; g < G; g++)
-            for (int a = 0; a < F; a++) {
-                mi_t[(size_t)a * G + g] = mi[(size_t)g * F + a];
-                niv_t[(size_t)a * G + g] = -0.5f * iv[(size_t)g * F + a];
-            }
+            for (int a = 0; a < F; a++) ubm_t[(size_t)a * G + g] = make_float2(mi[(size_t)g * F + a], -0.5f * iv[(size_t)g * F + a]);
         const float *M = m.iv_ie.at("M").f32(), *Si = m.iv_ie.at("sigma_inv").f32();
         const size_t NT = (size_t)D * (D + 1) / 2;
         std::vector<float> sim((size_t)G * F * D), U(G * NT);  // U: packed lower triangle (Kaldi keeps it as an SpMatrix)
@@ -237,7 +234,7 @@ void Engine::upload_model() {
         std::vector<double> gsum(cm, cm + F);
         iv_model_ = IvecModel{F, D, G, S,
                               dev_upload(allocs_, lda_t), dev_upload(allocs_, m.iv_dubm.at("gconsts").f32(), (size_t)G),
-                              dev_upload(allocs_, mi_t), dev_upload(allocs_, niv_t), dev_upload(allocs_, sim), dev_upload(allocs_, U),
+                              dev_upload(allocs_, ubm_t), dev_upload(allocs_, sim), dev_upload(allocs_, U),
                               dev_upload(allocs_, gsum), cm[F], m.prior_offset,
                               cfg_.num_gselect, cfg_.min_post, cfg_.posterior_scale, cfg_.max_count, cfg_.cmn_window, cfg_.global_frames};
     }

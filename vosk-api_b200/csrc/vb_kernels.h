@@ -67,8 +67,7 @@ struct IvecModel {           // device pointers
     int feat_dim, ivec_dim, num_gauss, splice_dim;
     const float *lda_t;      // [splice_dim+1][feat_dim]  (transposed; last row = offset)
     const float *gconsts;    // [G]
-    const float *mi_t;       // [F][G] means*inv_vars, transposed
-    const float *niv_t;      // [F][G] -0.5 * inv_vars, transposed
+    const float2 *ubm_t;     // [F][G] {mean * inv_var, -0.5 * inv_var}, transposed
     const float *sim;        // [G][F][D]   Sigma_i^{-1} M_i
     const float *U_tri;      // [G][D(D+1)/2]  M_i^T Sigma_i^{-1} M_i, packed lower triangle (row i: columns 0..i)
     const double *gcmvn_sum; // [F] global cmvn sums
