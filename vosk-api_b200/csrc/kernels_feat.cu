@@ -305,39 +305,49 @@ constexpr float kIvFix = 1099511627776.f;  // 2^40: posterior weights as fixed p
 
 extern "C" int vbk_ivector_frames_cap(int samples_per_chunk) { return ((samples_per_chunk / kFrameShift + 8 + kIvTB - 1) / kIvTB) * kIvTB; }
 
-__global__ void __launch_bounds__(64) ivector_cmn_kernel(IvecArgs a) {
+constexpr int kCmnThreads = 256;
+constexpr int kCmnTile = 64;  // frames per pass (a chunk has 51)
+__global__ void __launch_bounds__(kCmnThreads) ivector_cmn_kernel(IvecArgs a) {
     const LaneDesc ln = a.lanes[blockIdx.x];
     const IvecModel &m = a.m;
-    const int F = m.feat_dim, d = threadIdx.x, ch = ln.channel;
-    if (d >= F) return;
+    constexpr int F = kNumCeps;
+    const int tid = threadIdx.x, ch = ln.channel;
+    __shared__ float s_x[kCmnTile][F], s_xo[kCmnTile][F];
+    __shared__ double s_sum[kCmnTile][F];
     double *cm_sum = a.st.cmvn_sum + (size_t)ch * F;
     float *nring = a.st.norm_ring + (size_t)ch * kNormRing * F;
-    double s = ln.first ? 0.0 : cm_sum[d];
-    const double gshare = m.gcmvn_sum[d] / m.gcmvn_count;
-    constexpr int kB = 16;  // frames whose loads go out together
-    for (int t0 = ln.frames_before; t0 < ln.frames_after; t0 += kB) {
-        float x[kB], xo[kB];
-#pragma unroll
-        for (int j = 0; j < kB; j++) {
-            const int t = t0 + j;
-            x[j] = t < ln.frames_after ? ring_row(a.in_node, ch, t)[d] : 0.f;
-            xo[j] = t < ln.frames_after && t >= m.cmn_window ? ring_row(a.in_node, ch, t - m.cmn_window)[d] : 0.f;
+    double run = 0.0;  // (threads < F) the running window sum of this dimension
+    if (tid < F && !ln.first) run = cm_sum[tid];
+    for (int t0 = ln.frames_before; t0 < ln.frames_after; t0 += kCmnTile) {
+        const int n = min(kCmnTile, ln.frames_after - t0);
+        // the tile's rows (and the rows leaving the window), all threads
+        for (int i = tid; i < n * F; i += kCmnThreads) {
+            const int j = i / F, d = i - j * F, t = t0 + j;
+            s_x[j][d] = ring_row(a.in_node, ch, t)[d];
+            s_xo[j][d] = t >= m.cmn_window ? ring_row(a.in_node, ch, t - m.cmn_window)[d] : 0.f;
         }
-#pragma unroll
-        for (int j = 0; j < kB; j++) {
-            const int t = t0 + j;
-            if (t < ln.frames_after) {
-                s += (double)x[j];
-                if (t >= m.cmn_window) s -= (double)xo[j];
-                const double nn = t + 1 < m.cmn_window ? t + 1 : m.cmn_window;
-                const double fg = nn < m.cmn_window ? fmin((double)m.cmn_window - nn, (double)m.global_frames) : 0.0;
-                double tot = s;
-                if (fg > 0.0) tot += fg * gshare;
-                nring[(t & (kNormRing - 1)) * F + d] = (float)((double)x[j] - tot / (nn + fg));
+        __syncthreads();
+        // the serial part: the running sums, thread per dimension (two additions per frame)
+        if (tid < F) {
+            for (int j = 0; j < n; j++) {
+                run += (double)s_x[j][tid];
+                if (t0 + j >= m.cmn_window) run -= (double)s_xo[j][tid];
+                s_sum[j][tid] = run;
             }
         }
+        __syncthreads();
+        // everything else is per (frame, dimension): smoothing with the global statistics, the mean, the normalised value
+        for (int i = tid; i < n * F; i += kCmnThreads) {
+            const int j = i / F, d = i - j * F, t = t0 + j;
+            const double nn = t + 1 < m.cmn_window ? t + 1 : m.cmn_window;
+            const double fg = nn < m.cmn_window ? fmin((double)m.cmn_window - nn, (double)m.global_frames) : 0.0;
+            double tot = s_sum[j][d];
+            if (fg > 0.0) tot += fg * (m.gcmvn_sum[d] / m.gcmvn_count);
+            nring[(t & (kNormRing - 1)) * F + d] = (float)((double)s_x[j][d] - tot / (nn + fg));
+        }
+        __syncthreads();
     }
-    cm_sum[d] = s;
+    if (tid < F) cm_sum[tid] = run;
 }
 
 struct IvPostLayout {  // shared-memory carve-up of the frame kernel, in floats
@@ -774,7 +784,7 @@ extern "C" cudaError_t vbk_ivector(const IvecArgs *a, cudaStream_t s) {
         configured[dev][0] = smem_post;
         configured[dev][1] = smem_stat;
     }
-    ivector_cmn_kernel<<<a->num_lanes, 64, 0, s>>>(*a);
+    ivector_cmn_kernel<<<a->num_lanes, kCmnThreads, 0, s>>>(*a);
     ivector_post_kernel<<<dim3(a->num_lanes, a->frames_cap / kIvTB), kIvThreads, smem_post, s>>>(*a);
     ivector_stats_kernel<<<a->num_lanes, kIvThreads, smem_stat, s>>>(*a);
     return cudaGetLastError();
