@@ -85,6 +85,10 @@ struct Shared {
     long long phase[8];  // cycles per phase of this CTA (tid 0), flushed to counters[16..23] of the heavy / [24..31] of the light variants
     long long lphase[8];  // the same for the lane in hand: the slowest lane's go to counters[32 + 8 * tier ..]
     int own[(NT / 32)][2][32];  // per-warp marker arrays of the arc-window owner scan (two windows in flight)
+    // what GetCutoff needs to know about a token list, gathered while the list is written (two sets: the frame in hand reads one,
+    // its finalize pass fills the other): smallest state among the cheapest tokens, #{cost < best + beam}, #{cost <= best + beam}
+    int nx_state[2], nx_lt[2], nx_le[2];
+    unsigned nx_best[2];  // ordered bits of the list's minimum cost
 };
 
 template <int NT>
@@ -201,21 +205,6 @@ __device__ __forceinline__ void relax(Ctx<NT> &c, int state, unsigned long long 
     }
 }
 
-// minimum cost and the index of one token attaining it
-template <int NT>
-__device__ float block_min(Ctx<NT> &c, const float *cost, int n, int *arg) {
-    unsigned long long m = kValMax;
-    for (int i = c.tid; i < n; i += NT) m = min(m, ((unsigned long long)ford(cost[i]) << 32) | (unsigned)i);
-    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (c.lane == 0) c.sh.red_ull[c.warp] = m;
-    __syncthreads();
-    m = c.lane < (NT / 32) ? c.sh.red_ull[c.lane] : kValMax;  // (one entry per lane and a shuffle reduction, not NT / 32 loads per thread)
-    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-    __syncthreads();
-    *arg = (int)(unsigned)m;
-    return unord((unsigned)(m >> 32));
-}
-
 // exact k-th smallest (0-based) of cost[0..n) by 4-pass radix select on the ordered key
 template <int NT>
 __device__ float block_select(Ctx<NT> &c, const float *cost, int n, int k) {
@@ -273,30 +262,17 @@ __device__ float block_select(Ctx<NT> &c, const float *cost, int n, int k) {
 }
 
 // GetCutoff of LatticeFasterDecoder (see oracle/orc_decode.cc get_cutoff).  The order statistics only matter
-// when they fall on the right side of best+beam, which a counting pass decides:
+// when they fall on the right side of best+beam, which two counts decide:
 //   kth(max_active) <  beam_cutoff  <=>  #{cost <  beam_cutoff} >  max_active
 //   kth(min_active) >  beam_cutoff  <=>  #{cost <= beam_cutoff} <= min_active
-// so the exact radix select runs only on the frames where it changes the result.
+// so the exact radix select runs only on the frames where it changes the result.  The minimum and the two counts are not
+// computed here: the pass that wrote the token list knew the minimum beforehand (the cheapest emitting candidate always
+// becomes a token, and epsilon arcs — weights >= 0 — add to a cost) and counted while it wrote (finalize_tokens), which
+// takes two sweeps over the tokens and four block barriers out of every frame.
 template <int NT>
-__device__ float get_cutoff(Ctx<NT> &c, const float *cost, int n, float *adaptive_beam, float *best_out, int *best_idx) {
+__device__ float cutoff_from_stats(Ctx<NT> &c, const float *cost, int n, float best, int n_lt, int n_le, float *adaptive_beam) {
     const DecArgs &a = c.a;
-    float best = block_min(c, cost, n, best_idx);
-    *best_out = best;
     const float beam_cutoff = best + a.beam;
-    int lt = 0, le = 0;
-    for (int i = c.tid; i < n; i += NT) {
-        float v = cost[i];
-        lt += v < beam_cutoff;
-        le += v <= beam_cutoff;
-    }
-    unsigned long long tot = ((unsigned long long)lt << 32) | (unsigned)le;
-    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (c.lane == 0) c.sh.red_ull[c.warp] = tot;
-    __syncthreads();
-    tot = c.lane < (NT / 32) ? c.sh.red_ull[c.lane] : 0ull;
-    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    __syncthreads();
-    const int n_lt = (int)(tot >> 32), n_le = (int)(unsigned)tot;
     if (n > a.max_active && n_lt > a.max_active) {
         float max_active_cutoff = block_select(c, cost, n, a.max_active);
         *adaptive_beam = max_active_cutoff - best + a.beam_delta;
@@ -370,8 +346,11 @@ __device__ int closure(Ctx<NT> &c, float cutoff, unsigned long long *arcs_seen) 
 // epsilon links, source) field; the next frame's pass translates them to log indices once the survivors are ranked.
 template <int NT>
 __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff, float cost_offset, int4 *links, int link_base,
-                                int *t_state, float *t_cost, int *t_arc, int *t_prev) {
+                                int *t_state, float *t_cost, int *t_arc, int *t_prev, float best_next, int stat_set) {
     const DecArgs &a = c.a;
+    // best_next = the minimum cost of the list being written (known beforehand); the counts GetCutoff needs of it are taken here
+    const float beam_cutoff_next = best_next + a.beam;
+    int my_lt = 0, my_le = 0, my_state = INT_MAX;
     for (int i = c.tid; i < n_cand; i += NT) {
         const int4 cd = c.cand[i];
         if (cd.z < 0 || (cd.z & kAltFlag)) continue;
@@ -380,7 +359,11 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
         if (cost < cutoff && tab_val(c, cd.z) == pk) {
             int idx = agg_inc(&c.sh.n_next);
             if (idx < a.tok_cap) {
-                t_state[idx] = c.cand_next[i];
+                const int st = c.cand_next[i];
+                my_lt += cost < beam_cutoff_next;
+                my_le += cost <= beam_cutoff_next;
+                if (cost == best_next) my_state = min(my_state, st);
+                t_state[idx] = st;
                 t_cost[idx] = cost;
                 t_arc[idx] = cd.x;
                 tab_set_tok(c, cd.z, idx);  // one winner per slot: nobody else reads this slot's key any more
@@ -390,6 +373,21 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
                 tab_set_tok(c, cd.z, 0);
             }
         }
+    }
+    {
+        for (int o = 16; o; o >>= 1) {
+            my_lt += __shfl_xor_sync(0xffffffffu, my_lt, o);
+            my_le += __shfl_xor_sync(0xffffffffu, my_le, o);
+            my_state = min(my_state, __shfl_xor_sync(0xffffffffu, my_state, o));
+        }
+        if (c.lane == 0) {
+            if (my_le) {
+                atomicAdd(&c.sh.nx_lt[stat_set], my_lt);
+                atomicAdd(&c.sh.nx_le[stat_set], my_le);
+            }
+            if (my_state != INT_MAX) atomicMin(&c.sh.nx_state[stat_set], my_state);
+        }
+        if (c.tid == 0) c.sh.nx_best[stat_set] = ford(best_next);
     }
     __syncthreads();
     const int first = a.lattice ? 0 : n_emit;  // without lattice generation only the epsilon winners need this pass
@@ -448,7 +446,8 @@ __device__ void finalize_tokens(Ctx<NT> &c, int n_emit, int n_cand, float cutoff
             c.skey[i] = kEmpty;
             c.sval[i] = kValMax;
         }
-    __syncthreads();
+    // (no barrier here: every caller runs into one — the top of the frame loop / of the lane loop — before the tables or the
+    // shared counters are touched again)
 }
 }  // namespace
 
@@ -517,6 +516,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 sh.n_next = 0;
                 sh.n_links = 0;
                 sh.n_work = 0;
+                sh.nx_state[0] = INT_MAX;
+                sh.nx_lt[0] = 0;
+                sh.nx_le[0] = 0;
                 if (link_off) link_off[0] = 0;
             }
             c.hmask = (unsigned)a.hash_size - 1;
@@ -525,7 +527,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             if (tid == 0) relax(c, a.g.start, pack(0.f, -1), -1, true);
             __syncthreads();
             int nc = closure(c, a.beam, &cnt_arc_eps);
-            finalize_tokens(c, 1, nc, INFINITY, 0.f, links, 0, a.tok_state + tbase, a.tok_cost + tbase, a.tok_arc + tbase, a.tok_prev + tbase);
+            // (the start token costs 0 and epsilon weights are not negative: the list's minimum is 0)
+            finalize_tokens(c, 1, nc, INFINITY, 0.f, links, 0, a.tok_state + tbase, a.tok_cost + tbase, a.tok_arc + tbase, a.tok_prev + tbase, 0.f, 0);
+            __syncthreads();
             n_cur = min(sh.n_next, a.tok_cap);
             link_count = a.lattice ? min(sh.n_links, a.link_cap) : 0;
             parity = 0;
@@ -537,11 +541,18 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             frame = cs->frame;
             log_count = cs->log_count;
             link_count = cs->link_count;
+            if (tid == 0) {  // the statistics of the token list the previous chunk left
+                sh.nx_state[0] = cs->nx_state;
+                sh.nx_lt[0] = cs->nx_lt;
+                sh.nx_le[0] = cs->nx_le;
+                sh.nx_best[0] = cs->nx_best;
+            }
             if (link_off) seg_begin = link_off[min(frame, a.max_frames + 1)];
         }
         const int nf = a.out_table[l].n_rows;
         const int t_first = a.out_table[l].t_begin;
         const int total_frames = nf + (ln.dec_last ? 1 : 0);  // the extra pass logs the final frame's tokens
+        int sset = 0;  // which set of list statistics describes the current token list
         for (int fi = 0; fi < total_frames; fi++) {
             const bool final_pass = fi == nf;
             const int *t_state = a.tok_state + tbase + (size_t)parity * a.tok_cap;
@@ -562,16 +573,19 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                 const float *row = a.out_node.buf + ((size_t)ch * a.out_node.ring +
                                                      (((t_first + fi * a.out_node.step) - a.out_node.t_start) / a.out_node.step & (a.out_node.ring - 1))) * npdf;
                 for (int i = tid * 4; i < npdf; i += NT * 4) *reinterpret_cast<float4 *>(s_ll + i) = *reinterpret_cast<const float4 *>(row + i);
-                int best_idx = 0;
-                cur_cutoff = get_cutoff(c, t_cost, n_cur, &adaptive_beam, &best, &best_idx);
-                // seed the running minimum with the best token's own arcs (as LatticeFasterDecoder does), so the
+                best = unord(sh.nx_best[sset]);
+                const int best_state = sh.nx_state[sset], n_lt = sh.nx_lt[sset], n_le = sh.nx_le[sset];
+                cur_cutoff = cutoff_from_stats(c, t_cost, n_cur, best, n_lt, n_le, &adaptive_beam);
+                // seed the running minimum with a best token's own arcs (as LatticeFasterDecoder does), so the
                 // loose cutoff used while expanding is already close to the final one and few arcs touch the table
                 if (c.warp == 0) {
-                    const int2 sa = __ldg(&a.g.state_arcs[t_state[best_idx]]);
+                    // (no such token only after a capacity overflow dropped it: then the running minimum starts unseeded)
+                    const int2 sa = best_state != INT_MAX ? __ldg(&a.g.state_arcs[best_state]) : make_int2(0, 0);
                     unsigned m = 0xffffffffu;
                     for (int arc = sa.x + c.lane; arc < sa.y; arc += 32) {
                         const int4 av = __ldg(a.g.arcs + arc);
-                        const float ac = -best - __fmul_rn(a.acoustic_scale, s_ll[av.z]);
+                        // (read from the ring row itself: the shared copy is being written by the other warps, and no barrier is spent on it)
+                        const float ac = -best - __fmul_rn(a.acoustic_scale, row[av.z]);
                         m = min(m, ford(best + ac + __int_as_float(av.x)));
                     }
                     for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -581,6 +595,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
                         sh.n_next = 0;
                         sh.n_links = 0;
                         sh.n_work = 0;
+                        sh.nx_state[sset ^ 1] = INT_MAX;  // (the other set: read last at the top of the previous frame)
+                        sh.nx_lt[sset ^ 1] = 0;
+                        sh.nx_le[sset ^ 1] = 0;
                     }
                 }
             } else if (tid == 0) {
@@ -836,7 +853,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             VB_PHASE(4)
             const int nc = closure(c, next_cutoff, &cnt_arc_eps);
             VB_PHASE(5)
-            finalize_tokens(c, n_emit, nc, next_cutoff, cost_offset, links, link_count, n_state, n_cost, n_arc, n_prev);
+            finalize_tokens(c, n_emit, nc, next_cutoff, cost_offset, links, link_count, n_state, n_cost, n_arc, n_prev, unord(sh.min_ord), sset ^ 1);
+            sset ^= 1;
             VB_PHASE(6)
             if (a.lattice) {
                 cnt_links += tid == 0 ? (unsigned)sh.n_links : 0u;
@@ -903,6 +921,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? kDecBlocksPerSM : NT == 512 ? 
             cs->frame = frame;
             cs->log_count = log_count;
             cs->link_count = link_count;
+            cs->nx_state = sh.nx_state[sset];
+            cs->nx_lt = sh.nx_lt[sset];
+            cs->nx_le = sh.nx_le[sset];
+            cs->nx_best = sh.nx_best[sset];
             cs->error = sh.error;
             if (a.counters) {  // lane-level balance: sum and max of the cycles one lane took in this launch
                 const unsigned long long cyc = (unsigned long long)(clock64() - clk0);

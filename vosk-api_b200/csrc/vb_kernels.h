@@ -144,6 +144,10 @@ struct DecChannelState {     // one per channel
     int log_count, path_len, reached_final;
     float best_cost;
     int link_count, pad0, pad1, pad2;
+    // of the current token list (what GetCutoff needs, gathered while the list was written): smallest state among the cheapest
+    // tokens, #{cost < best + beam}, #{cost <= best + beam}, ordered bits of the minimum cost
+    int nx_state, nx_lt, nx_le;
+    unsigned nx_best;
 };
 // pruned raw lattice of one finished stream (lattice=1): written by lattice_prune_kernel, read by the host
 struct LatHeader {
