@@ -1,5 +1,16 @@
-# scratch driver of one gpurun call (edited per call): full GPU suite and the bench line
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/j_py.log 2>&1; tail -3 gpurun_out/j_py.log
-timeout 1500 python bench.py > gpurun_out/j_bench.json 2> gpurun_out/j_bench.err; tail -c 300 gpurun_out/j_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r02d_launch_list.csv python vosk-api_b200/tools/profile_run.py 512 4 > gpurun_out/j_ncu1.log 2>&1; tail -1 gpurun_out/j_ncu1.log | cut -c1-120
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"decode_kernel" -s 4 -c 3 -f -o gpurun_out/r02d_prof_search python vosk-api_b200/tools/profile_run.py 512 4 > gpurun_out/j_ncu2.log 2>&1; tail -1 gpurun_out/j_ncu2.log | cut -c1-120
+# scratch driver of one gpurun call (edited per call): parity, then same-box A/B of two builds of the library
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "tiny or small_model_all_stages or lattice_generation or max_active or full_size or pipelined or rule5 or partial or determin or silence or native or acoustic" > gpurun_out/k_py.log 2>&1; tail -3 gpurun_out/k_py.log
+for rep in 1 2; do
+for v in A main; do
+  if [ $v != main ]; then export VOSK_B200_LIB=$PWD/vosk-api_b200/lib_alt/libvosk_$v.so; else unset VOSK_B200_LIB; fi
+  VB_SLOTS=1 timeout 300 python vosk-api_b200/tools/profile_run.py 512 12 "" 2 > gpurun_out/k_prof1_$v$rep.log 2>&1
+  timeout 300 python vosk-api_b200/tools/profile_run.py 512 12 "lattice=0" 3 > gpurun_out/k_prof_$v$rep.log 2>&1
+  python - $v$rep <<'PY'
+import ast,sys
+t=open('gpurun_out/k_prof1_%s.log'%sys.argv[1]).read().strip().splitlines()
+d=ast.literal_eval(t[-1])
+u=open('gpurun_out/k_prof_%s.log'%sys.argv[1]).read().strip().splitlines()
+print(sys.argv[1], 'search', d['ms_search'], 'max', d['lane_cycles_max'], 'sum', round(d['lane_cycles_sum']/1e6), {k[10:]:round(v/1e6) for k,v in d.items() if k.startswith('cyc_light') and v}, {k[10:]:round(v/1e6) for k,v in d.items() if k.startswith('cyc_heavy') and v}, '| best-path:', u[-2])
+PY
+done
+done
