@@ -1,16 +1,14 @@
-# scratch driver of one gpurun call (edited per call): parity, then same-box A/B of two builds of the library
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "tiny or small_model_all_stages or lattice_generation or max_active or full_size or pipelined or rule5 or partial or determin or silence or native or acoustic" > gpurun_out/k_py.log 2>&1; tail -3 gpurun_out/k_py.log
-for rep in 1 2; do
-for v in A main; do
-  if [ $v != main ]; then export VOSK_B200_LIB=$PWD/vosk-api_b200/lib_alt/libvosk_$v.so; else unset VOSK_B200_LIB; fi
-  VB_SLOTS=1 timeout 300 python vosk-api_b200/tools/profile_run.py 512 12 "" 2 > gpurun_out/k_prof1_$v$rep.log 2>&1
-  timeout 300 python vosk-api_b200/tools/profile_run.py 512 12 "lattice=0" 3 > gpurun_out/k_prof_$v$rep.log 2>&1
-  python - $v$rep <<'PY'
-import ast,sys
-t=open('gpurun_out/k_prof1_%s.log'%sys.argv[1]).read().strip().splitlines()
-d=ast.literal_eval(t[-1])
-u=open('gpurun_out/k_prof_%s.log'%sys.argv[1]).read().strip().splitlines()
-print(sys.argv[1], 'search', d['ms_search'], 'max', d['lane_cycles_max'], 'sum', round(d['lane_cycles_sum']/1e6), {k[10:]:round(v/1e6) for k,v in d.items() if k.startswith('cyc_light') and v}, {k[10:]:round(v/1e6) for k,v in d.items() if k.startswith('cyc_heavy') and v}, '| best-path:', u[-2])
+# One gpurun call: parity of the front end and the search through the C ABI, serialized stage times of the bench-sized workload,
+# and (optionally) a same-box A/B against another build of the library:  bash vosk-api_b200/tools/gpu_call.sh [path/to/other/libvosk.so]
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "tiny or small_model_all_stages or lattice_generation or max_active or full_size or pipelined" > gpurun_out/call_py.log 2>&1; tail -3 gpurun_out/call_py.log
+for v in ${1:+alt} main; do
+  if [ $v = alt ]; then export VOSK_B200_LIB=$1; else unset VOSK_B200_LIB; fi
+  VB_SLOTS=1 timeout 300 python vosk-api_b200/tools/profile_run.py 512 12 "" 2 > gpurun_out/call_prof_$v.log 2>&1
+  python - $v <<'PY'
+import ast, sys
+d = ast.literal_eval(open('gpurun_out/call_prof_%s.log' % sys.argv[1]).read().strip().splitlines()[-1])
+print(sys.argv[1], {k: d[k] for k in ('ms_feat', 'ms_ivector', 'ms_nnet', 'ms_search', 'ms_prune')}, 'lane Mcycles', round(d['lane_cycles_sum'] / 1e6),
+      {k[4:]: round(v / 1e6) for k, v in d.items() if k.startswith('cyc_') and v})
 PY
-done
 done
