@@ -38,6 +38,7 @@ static void apply_option(Config *c, const std::string &k, const std::string &v) 
     else if (k == "batcher-sleep") I(&c->batcher_sleep);
     else if (k == "partials") I(&c->partials);
     else if (k == "fe-priority") I(&c->fe_priority);
+    else if (k == "fe-split") I(&c->fe_split);
     else if (k == "endpoint-rule5-seconds") F(&c->endpoint_rule5_seconds);
     else if (k == "log-links-per-frame") I(&c->log_links_per_frame);
     else if (k == "lat-tok-cap") I(&c->lat_tok_cap);

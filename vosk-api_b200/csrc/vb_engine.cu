@@ -60,6 +60,7 @@ Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg)
         VB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         const int pfe = cfg_.fe_priority > 0 ? hi : cfg_.fe_priority < 0 ? lo : 0, pdec = cfg_.fe_priority > 0 ? lo : cfg_.fe_priority < 0 ? hi : 0;
         VB_CUDA_CHECK(cudaStreamCreateWithPriority(&fe_stream_, cudaStreamNonBlocking, pfe));
+        VB_CUDA_CHECK(cudaStreamCreateWithPriority(&fe_stream2_, cudaStreamNonBlocking, pfe));
         VB_CUDA_CHECK(cudaStreamCreateWithPriority(&dec_stream_, cudaStreamNonBlocking, pdec));
         VB_CUDA_CHECK(cudaStreamCreateWithPriority(&dec_stream2_, cudaStreamNonBlocking, pdec));
         VB_CUDA_CHECK(cudaStreamCreateWithPriority(&dec_stream3_, cudaStreamNonBlocking, pdec));
@@ -122,7 +123,7 @@ Engine::~Engine() {
     for (auto &t : post_threads_) t.join();
     cudaSetDevice(cfg_.device);
     cudaStreamSynchronize(stream_);
-    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_, dec_stream3_, post_stream_})
+    for (cudaStream_t q : {fe_stream_, fe_stream2_, dec_stream_, dec_stream2_, dec_stream3_, post_stream_})
         if (q) cudaStreamSynchronize(q);
     for (void *p : allocs_) cudaFree(p);
     for (Slot &sl : slots_) {
@@ -150,7 +151,7 @@ Engine::~Engine() {
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (h_capture_) cudaFreeHost(h_capture_);
-    for (cudaStream_t q : {fe_stream_, dec_stream_, dec_stream2_, dec_stream3_, post_stream_})
+    for (cudaStream_t q : {fe_stream_, fe_stream2_, dec_stream_, dec_stream2_, dec_stream3_, post_stream_})
         if (q) cudaStreamDestroy(q);
     cudaStreamDestroy(stream_);
 }
@@ -461,6 +462,10 @@ void Engine::alloc_state() {
         sl.d_rowoff = dev_alloc<int>(allocs_, (size_t)nn * (L + 1), 0);
         rows_cap_ = L * (max_in_rows_ + 8);
         sl.d_rows = dev_alloc<int2>(allocs_, (size_t)nn * rows_cap_, 0);
+        if (cfg_.fe_split) {
+            sl.d_rowoff2 = dev_alloc<int>(allocs_, (size_t)nn * (L + 1), 0);
+            sl.d_rows2 = dev_alloc<int2>(allocs_, (size_t)nn * rows_cap_, 0);
+        }
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_cs, (size_t)L * sizeof(DecChannelState)));
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_path, (size_t)L * path_cap_ * sizeof(int)));
         sl.d_load = dev_alloc<int>(allocs_, (size_t)L, 0);
@@ -870,39 +875,63 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         VB_CUDA_CHECK(vbk_resample(&ra, st));
         sl.launches++;
     }
-    FeatArgs fa{sl.d_lanes, L, d_resident ? d_resident : sl.d_staging, d_resident ? (long long)resident_stride : (long long)spc, spc,
-                d_carry_, nodes_[0], ctx, feat_tab_};
-    VB_CUDA_CHECK(vbk_mfcc(&fa, st));
-    sl.launches++;
-    if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[1], st));
-    IvecArgs ia{sl.d_lanes, L, nodes_[0], ctx, iv_model_, iv_state_, d_iv_sel_g_, d_iv_sel_w_, d_iv_fu_, iv_frames_cap_};
-    VB_CUDA_CHECK(vbk_ivector(&ia, st));
-    sl.launches += 3;
-    if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[2], st));
-    NnetPlanArgs pa{sl.d_lanes, L, nn, d_nodes_, d_node_end_, sl.d_table, sl.d_rowoff, SL, sl.d_rows, rows_cap_};
-    VB_CUDA_CHECK(vbk_nnet_plan(&pa, st));
-    sl.launches++;
-    for (size_t o = 0; o < ops_.size(); o++) {
-        const OpDesc &op = ops_[o];
-        GemmArgs ga{};
-        ga.op = op;
-        ga.in = nodes_[op.in_node];
-        ga.out = nodes_[op.out_node];
-        ga.byp = nodes_[op.byp_node >= 0 ? op.byp_node : 0];
-        ga.lanes = sl.d_lanes;
-        ga.num_lanes = L;
-        ga.table = sl.d_table + (size_t)op.out_node * SL;
-        ga.rowoff = sl.d_rowoff + (size_t)op.out_node * (SL + 1);
-        ga.rows = sl.d_rows + (size_t)op.out_node * rows_cap_;
-        ga.ivec = iv_state_.ivec;
-        ga.ivec_dim = model_.ivec_dim;
-        ga.max_rows = (int)(ga.out.step == 1 ? in_rows : in_rows / kSubsample + 2 * L);
-        ga.tc_mode = cfg_.use_tensor_cores;
-        ga.map_hi = maps_[o].hi;
-        ga.map_lo = maps_[o].lo;
-        VB_CUDA_CHECK(cfg_.use_tensor_cores ? vbk_gemm_tc(&ga, st) : vbk_gemm_fp32(&ga, st));
+    // The front end of lanes [first, first + count) as one chain of launches on stream q: features, i-vector, row plan, the
+    // TDNN-F GEMMs.  Its launches cover a fraction of a wave each (79 row tiles for 512 lanes), so a full-width step runs two such
+    // chains side by side, half of the lanes each (fe-split): the lanes of the halves are different channels, nothing is shared
+    // but the read-only model, and the per-lane row table of the output node (what the search reads) is one array for both.
+    auto front_end = [&](int first, int count, cudaStream_t q, int *d_rowoff, int2 *d_rows, long long rows_in, bool timed) {
+        FeatArgs fa{sl.d_lanes + first, count, d_resident ? d_resident : sl.d_staging, d_resident ? (long long)resident_stride : (long long)spc, spc,
+                    d_carry_, nodes_[0], ctx, feat_tab_};
+        VB_CUDA_CHECK(vbk_mfcc(&fa, q));
         sl.launches++;
-        sl.gemms++;
+        if (timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[1], q));
+        IvecArgs ia{sl.d_lanes + first, count, nodes_[0], ctx, iv_model_, iv_state_, d_iv_sel_g_ + (size_t)first * iv_frames_cap_ * 8,
+                    d_iv_sel_w_ + (size_t)first * iv_frames_cap_ * 8, d_iv_fu_ + (size_t)first * iv_frames_cap_ * model_.feat_dim, iv_frames_cap_};
+        VB_CUDA_CHECK(vbk_ivector(&ia, q));
+        sl.launches += 3;
+        if (timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[2], q));
+        NnetPlanArgs pa{sl.d_lanes + first, count, nn, d_nodes_, d_node_end_, sl.d_table + first, d_rowoff, SL, d_rows, rows_cap_};
+        VB_CUDA_CHECK(vbk_nnet_plan(&pa, q));
+        sl.launches++;
+        for (size_t o = 0; o < ops_.size(); o++) {
+            const OpDesc &op = ops_[o];
+            GemmArgs ga{};
+            ga.op = op;
+            ga.in = nodes_[op.in_node];
+            ga.out = nodes_[op.out_node];
+            ga.byp = nodes_[op.byp_node >= 0 ? op.byp_node : 0];
+            ga.lanes = sl.d_lanes + first;
+            ga.num_lanes = count;
+            ga.table = sl.d_table + (size_t)op.out_node * SL + first;
+            ga.rowoff = d_rowoff + (size_t)op.out_node * (SL + 1);
+            ga.rows = d_rows + (size_t)op.out_node * rows_cap_;
+            ga.ivec = iv_state_.ivec;
+            ga.ivec_dim = model_.ivec_dim;
+            ga.max_rows = (int)(ga.out.step == 1 ? rows_in : rows_in / kSubsample + 2 * count);
+            ga.tc_mode = cfg_.use_tensor_cores;
+            ga.map_hi = maps_[o].hi;
+            ga.map_lo = maps_[o].lo;
+            VB_CUDA_CHECK(cfg_.use_tensor_cores ? vbk_gemm_tc(&ga, q) : vbk_gemm_fp32(&ga, q));
+            sl.launches++;
+            sl.gemms++;
+        }
+    };
+    // (stage timing keeps the single chain: its events bracket the stages of one stream)
+    const bool split = cfg_.fe_split && sl.d_rowoff2 && !sl.timed && L >= 128;
+    if (!split) {
+        front_end(0, L, st, sl.d_rowoff, sl.d_rows, in_rows, sl.timed);
+    } else {
+        const int half = L / 2;
+        long long rows_a = 0;
+        for (int i = 0; i < half; i++) rows_a += sl.h_lanes[i].in_end_after - sl.h_lanes[i].in_end_before + 2;
+        // the second chain starts once the lane descriptors / samples are on the device, and after the previous step's front end
+        // (a channel may change halves between steps: the lanes are sorted by load)
+        VB_CUDA_CHECK(cudaEventRecord(sl.fork, st));
+        VB_CUDA_CHECK(cudaStreamWaitEvent(fe_stream2_, sl.fork, 0));
+        front_end(half, L - half, fe_stream2_, sl.d_rowoff2, sl.d_rows2, in_rows - rows_a, false);
+        VB_CUDA_CHECK(cudaEventRecord(sl.join[0], fe_stream2_));
+        front_end(0, half, st, sl.d_rowoff, sl.d_rows, rows_a, false);
+        VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.join[0], 0));
     }
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[3], st));
     VB_CUDA_CHECK(cudaMemsetAsync(sl.d_queue, 0, 4 * sizeof(int), st));

@@ -197,6 +197,8 @@ class Engine {
         NodeLane *d_table = nullptr;
         int *d_rowoff = nullptr;
         int2 *d_rows = nullptr;  // [nodes][rows_cap_] packed row table of the step
+        int *d_rowoff2 = nullptr;  // the same two for the second half of the lanes when the front end runs as two chains
+        int2 *d_rows2 = nullptr;
         DecArgs dec{};
         DecChannelState *h_cs = nullptr;
         int *h_path = nullptr;
@@ -224,6 +226,8 @@ class Engine {
     const Model &model_;
     Config cfg_;
     cudaStream_t stream_ = nullptr;  // setup / utility stream
+    cudaStream_t fe_stream2_ = nullptr;   // second front-end chain of a step (fe-split)
+    cudaEvent_t last_fe_done_ = nullptr;  // front end of the previous step (both chains)
     cudaStream_t fe_stream_ = nullptr, dec_stream_ = nullptr, dec_stream2_ = nullptr, dec_stream3_ = nullptr, post_stream_ = nullptr;  // the two pipes (+ the light-lane search launch)
     std::vector<Slot> slots_;
     bool timing_ = false;

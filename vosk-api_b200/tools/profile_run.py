@@ -23,7 +23,7 @@ stride = int((lengths.max() + 7) // 8 * 8)
 mat = np.zeros((streams, stride), dtype=np.int16)
 for i, w in enumerate(waves):
     mat[i, :len(w)] = w
-model.SetTiming(True)
+model.SetTiming(not os.environ.get("VB_NOTIMING"))  # (stage timing keeps the front end on one stream)
 if os.environ.get("VB_SLOTS"):  # 1 = serialize the steps: per-stage device times free of overlap
     model.SetSlots(int(os.environ["VB_SLOTS"]))
 for _ in range(reps):
