@@ -70,7 +70,7 @@ struct Config {
     float ep_min_utterance_length[4] = {0.f, 0.f, 0.f, 0.f};
     float mfcc_low_freq = 20.f, mfcc_high_freq = -400.f;  // conf/mfcc.conf [REF training/conf/mfcc.conf:4-5]; high <= 0: offset from Nyquist
     int fe_priority = 0;        // CUDA stream priority of the front-end pipe relative to the search pipe (1 / 0 / -1)
-    int fe_split = 1;           // front end of a step on two streams, half of the lanes each (its launches are sub-wave: two chains side by side)
+    int fe_split = 2;           // front-end chains of a full-width step (1-4): its launches are sub-wave, so the lanes are dealt to several chains side by side
     int device_resample = 1;    // resample non-16 kHz input on the GPU (0: on the host, in accept_waveform)
     int pipeline_slots = 4;     // lane groups in flight on separate CUDA streams
     int num_gselect = 5;        // ivector.conf

@@ -60,7 +60,7 @@ Engine::Engine(const Model &model, const Config &cfg) : model_(model), cfg_(cfg)
         VB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         const int pfe = cfg_.fe_priority > 0 ? hi : cfg_.fe_priority < 0 ? lo : 0, pdec = cfg_.fe_priority > 0 ? lo : cfg_.fe_priority < 0 ? hi : 0;
         VB_CUDA_CHECK(cudaStreamCreateWithPriority(&fe_stream_, cudaStreamNonBlocking, pfe));
-        VB_CUDA_CHECK(cudaStreamCreateWithPriority(&fe_stream2_, cudaStreamNonBlocking, pfe));
+        for (cudaStream_t &q : fe_stream2_) VB_CUDA_CHECK(cudaStreamCreateWithPriority(&q, cudaStreamNonBlocking, pfe));
         VB_CUDA_CHECK(cudaStreamCreateWithPriority(&dec_stream_, cudaStreamNonBlocking, pdec));
         VB_CUDA_CHECK(cudaStreamCreateWithPriority(&dec_stream2_, cudaStreamNonBlocking, pdec));
         VB_CUDA_CHECK(cudaStreamCreateWithPriority(&dec_stream3_, cudaStreamNonBlocking, pdec));
@@ -123,7 +123,7 @@ Engine::~Engine() {
     for (auto &t : post_threads_) t.join();
     cudaSetDevice(cfg_.device);
     cudaStreamSynchronize(stream_);
-    for (cudaStream_t q : {fe_stream_, fe_stream2_, dec_stream_, dec_stream2_, dec_stream3_, post_stream_})
+    for (cudaStream_t q : {fe_stream_, fe_stream2_[0], fe_stream2_[1], fe_stream2_[2], dec_stream_, dec_stream2_, dec_stream3_, post_stream_})
         if (q) cudaStreamSynchronize(q);
     for (void *p : allocs_) cudaFree(p);
     for (Slot &sl : slots_) {
@@ -151,7 +151,7 @@ Engine::~Engine() {
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (h_capture_) cudaFreeHost(h_capture_);
-    for (cudaStream_t q : {fe_stream_, fe_stream2_, dec_stream_, dec_stream2_, dec_stream3_, post_stream_})
+    for (cudaStream_t q : {fe_stream_, fe_stream2_[0], fe_stream2_[1], fe_stream2_[2], dec_stream_, dec_stream2_, dec_stream3_, post_stream_})
         if (q) cudaStreamDestroy(q);
     cudaStreamDestroy(stream_);
 }
@@ -462,9 +462,9 @@ void Engine::alloc_state() {
         sl.d_rowoff = dev_alloc<int>(allocs_, (size_t)nn * (L + 1), 0);
         rows_cap_ = L * (max_in_rows_ + 8);
         sl.d_rows = dev_alloc<int2>(allocs_, (size_t)nn * rows_cap_, 0);
-        if (cfg_.fe_split) {
-            sl.d_rowoff2 = dev_alloc<int>(allocs_, (size_t)nn * (L + 1), 0);
-            sl.d_rows2 = dev_alloc<int2>(allocs_, (size_t)nn * rows_cap_, 0);
+        for (int k = 0; k + 1 < std::min(cfg_.fe_split, 4); k++) {
+            sl.d_rowoff2[k] = dev_alloc<int>(allocs_, (size_t)nn * (L + 1), 0);
+            sl.d_rows2[k] = dev_alloc<int2>(allocs_, (size_t)nn * rows_cap_, 0);
         }
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_cs, (size_t)L * sizeof(DecChannelState)));
         VB_CUDA_CHECK(cudaMallocHost((void **)&sl.h_path, (size_t)L * path_cap_ * sizeof(int)));
@@ -917,21 +917,27 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         }
     };
     // (stage timing keeps the single chain: its events bracket the stages of one stream)
-    const bool split = cfg_.fe_split && sl.d_rowoff2 && !sl.timed && L >= 128;
-    if (!split) {
+    const int chains = sl.timed || L < 128 ? 1 : std::max(1, std::min(cfg_.fe_split, 4));
+    if (chains == 1) {
         front_end(0, L, st, sl.d_rowoff, sl.d_rows, in_rows, sl.timed);
     } else {
-        const int half = L / 2;
-        long long rows_a = 0;
-        for (int i = 0; i < half; i++) rows_a += sl.h_lanes[i].in_end_after - sl.h_lanes[i].in_end_before + 2;
-        // the second chain starts once the lane descriptors / samples are on the device, and after the previous step's front end
-        // (a channel may change halves between steps: the lanes are sorted by load)
+        // the other chains start once the lane descriptors / samples are on the device, which is after the previous step's chains
+        // (a channel may change shares between steps: the lanes are sorted by load)
         VB_CUDA_CHECK(cudaEventRecord(sl.fork, st));
-        VB_CUDA_CHECK(cudaStreamWaitEvent(fe_stream2_, sl.fork, 0));
-        front_end(half, L - half, fe_stream2_, sl.d_rowoff2, sl.d_rows2, in_rows - rows_a, false);
-        VB_CUDA_CHECK(cudaEventRecord(sl.join[0], fe_stream2_));
-        front_end(0, half, st, sl.d_rowoff, sl.d_rows, rows_a, false);
-        VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.join[0], 0));
+        int first = L / chains;  // chain 0 (this stream) takes [0, L / chains)
+        for (int k = 1; k < chains; k++) {
+            const int end = k + 1 == chains ? L : (int)((long long)L * (k + 1) / chains);
+            long long rows_k = 0;
+            for (int i = first; i < end; i++) rows_k += sl.h_lanes[i].in_end_after - sl.h_lanes[i].in_end_before + 2;
+            VB_CUDA_CHECK(cudaStreamWaitEvent(fe_stream2_[k - 1], sl.fork, 0));
+            front_end(first, end - first, fe_stream2_[k - 1], sl.d_rowoff2[k - 1], sl.d_rows2[k - 1], rows_k, false);
+            VB_CUDA_CHECK(cudaEventRecord(sl.join[k - 1], fe_stream2_[k - 1]));
+            first = end;
+        }
+        long long rows_0 = 0;
+        for (int i = 0; i < L / chains; i++) rows_0 += sl.h_lanes[i].in_end_after - sl.h_lanes[i].in_end_before + 2;
+        front_end(0, L / chains, st, sl.d_rowoff, sl.d_rows, rows_0, false);
+        for (int k = 1; k < chains; k++) VB_CUDA_CHECK(cudaStreamWaitEvent(st, sl.join[k - 1], 0));
     }
     if (sl.timed) VB_CUDA_CHECK(cudaEventRecord(sl.ev[3], st));
     VB_CUDA_CHECK(cudaMemsetAsync(sl.d_queue, 0, 4 * sizeof(int), st));

@@ -185,7 +185,7 @@ class Engine {
     // the log-likelihood rings.
     struct Slot {
         cudaStream_t stream = nullptr;  // utility stream (debug taps, lattice fetch) of the slot
-        cudaEvent_t fe_done = nullptr, dec_done = nullptr, fork = nullptr, join[2] = {}, tier_done[3] = {};
+        cudaEvent_t fe_done = nullptr, dec_done = nullptr, fork = nullptr, join[3] = {}, tier_done[3] = {};
         int *d_queue = nullptr;  // [2] lane queues of the two search launches
         cudaEvent_t ev[8] = {};  // [6], [7]: around the lattice pruning launch
         bool pruned = false;
@@ -197,8 +197,8 @@ class Engine {
         NodeLane *d_table = nullptr;
         int *d_rowoff = nullptr;
         int2 *d_rows = nullptr;  // [nodes][rows_cap_] packed row table of the step
-        int *d_rowoff2 = nullptr;  // the same two for the second half of the lanes when the front end runs as two chains
-        int2 *d_rows2 = nullptr;
+        int *d_rowoff2[3] = {};  // the same two for the other shares of the lanes when the front end runs as several chains
+        int2 *d_rows2[3] = {};
         DecArgs dec{};
         DecChannelState *h_cs = nullptr;
         int *h_path = nullptr;
@@ -226,7 +226,7 @@ class Engine {
     const Model &model_;
     Config cfg_;
     cudaStream_t stream_ = nullptr;  // setup / utility stream
-    cudaStream_t fe_stream2_ = nullptr;   // second front-end chain of a step (fe-split)
+    cudaStream_t fe_stream2_[3] = {};     // the other front-end chains of a step (fe-split)
     cudaEvent_t last_fe_done_ = nullptr;  // front end of the previous step (both chains)
     cudaStream_t fe_stream_ = nullptr, dec_stream_ = nullptr, dec_stream2_ = nullptr, dec_stream3_ = nullptr, post_stream_ = nullptr;  // the two pipes (+ the light-lane search launch)
     std::vector<Slot> slots_;
