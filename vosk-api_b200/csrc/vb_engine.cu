@@ -917,7 +917,14 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
         }
     };
     // (stage timing keeps the single chain: its events bracket the stages of one stream)
-    const int chains = sl.timed || L < 128 ? 1 : std::max(1, std::min(cfg_.fe_split, 4));
+    // (while the host lattice pool has a backlog the host is what bounds the throughput: the extra launches of several chains
+    // would only take cycles from it)
+    bool host_bound = false;
+    if (!post_threads_.empty()) {
+        std::lock_guard<std::mutex> lk(post_mu_);
+        host_bound = post_queue_.size() > 2 * post_threads_.size();
+    }
+    const int chains = sl.timed || L < 128 || host_bound ? 1 : std::max(1, std::min(cfg_.fe_split, 4));
     if (chains == 1) {
         front_end(0, L, st, sl.d_rowoff, sl.d_rows, in_rows, sl.timed);
     } else {
