@@ -640,3 +640,27 @@ def test_acoustic_scale_is_a_plain_product(model_root, oracle_lib):
     np.testing.assert_array_equal(st, dec["state"])
     np.testing.assert_array_equal(co.view(np.uint32), dec["cost"].view(np.uint32))
     assert g["text"] == helpers.oracle_lattice_text(model, dec, 6.0)
+
+
+def test_front_end_chains_do_not_change_results(model_root):
+    """fe-split: the front end of a full-width step (>= 128 lanes) runs as one, two or four chains of launches side by side, each over
+    its share of the lanes with its own row tables — the texts (words, times, confidences) and the search counters are the same."""
+    import vosk
+    mdir = model_root("tiny")
+    rng = np.random.default_rng(77)
+    waves = _waves(list(rng.uniform(0.6, 2.6, size=160)), seed0=9100)
+    lengths = np.array([len(w) for w in waves], dtype=np.int32)
+    mat = np.zeros((len(waves), int((lengths.max() + 7) // 8 * 8)), dtype=np.int16)
+    for i, w in enumerate(waves):
+        mat[i, :len(w)] = w
+    got = {}
+    for chains in (1, 2, 4):
+        m = vosk.BatchModel(mdir, options=f"num-channels=160,max-batch-size=160,max-seconds=6,fe-split={chains}")
+        _, texts = m.RunResident(mat, lengths)
+        st = m.Stats()
+        assert st["truncated"] == 0 and st["lattice_fallbacks"] == 0
+        got[chains] = (list(texts), st["tokens"], st["arcs_emitting"], st["launches"])
+        del m
+    assert got[1][0] == got[2][0] == got[4][0]
+    assert got[1][1:3] == got[2][1:3] == got[4][1:3]
+    assert got[2][3] > got[1][3]  # (the chains really ran: more launches)
