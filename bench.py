@@ -141,6 +141,30 @@ def latency_pass(vosk, mdir, n_streams, seconds, packet_ms=100, fpc=10):
         r.AcceptWaveform(pk[i % 64][0])
     model.Wait()
     model.Latency(reset=True)
+    # caller-side sample: a second thread polls vosk_batch_recognizer_partial_frames of a few streams and takes, for every packet,
+    # the time from the return of its accept call to the first poll that sees the partial grow (the poll period is part of it)
+    watched = list(range(0, n_streams, max(1, n_streams // 8)))[:8]
+    t_acc = {i: 0.0 for i in watched}
+    seq = {i: 0 for i in watched}
+    caller_lat, stop = [], threading.Event()
+
+    def poll():
+        last_f = {i: recs[i].PartialFrames() for i in watched}
+        done = {i: 0 for i in watched}
+        while not stop.is_set():
+            for i in watched:
+                f = recs[i].PartialFrames()
+                if f > last_f[i]:
+                    last_f[i] = f
+                    sq, ta = seq[i], t_acc[i]
+                    if sq > done[i]:
+                        done[i] = sq
+                        caller_lat.append(time.perf_counter() - ta)
+
+    old_switch = sys.getswitchinterval()
+    sys.setswitchinterval(1e-4)  # the poller must not wait 5 ms for the interpreter while the feeder loops
+    poller = threading.Thread(target=poll, daemon=True)
+    poller.start()
     t0 = time.perf_counter()
     late = 0
     for k in range(1, n_ticks):
@@ -152,8 +176,16 @@ def latency_pass(vosk, mdir, n_streams, seconds, packet_ms=100, fpc=10):
             late += 1
         for i, r in enumerate(recs):
             r.AcceptWaveform(pk[i % 64][k])
+            if i in t_acc:
+                t_acc[i] = time.perf_counter()
+                seq[i] = k
     model.Wait()
     wall = time.perf_counter() - t0
+    time.sleep(0.02)
+    stop.set()
+    poller.join()
+    sys.setswitchinterval(old_switch)
+    cl = np.sort(np.array(caller_lat)) * 1e3 if caller_lat else np.zeros(1)
     lat = model.Latency()
     sample = recs[0].PartialResult()
     for r in recs:
@@ -165,6 +197,10 @@ def latency_pass(vosk, mdir, n_streams, seconds, packet_ms=100, fpc=10):
             "streams": n_streams, "frames_per_chunk": fpc, "packet_ms": packet_ms, "feed": "real-time paced, one packet per stream per tick",
             "ticks": n_ticks - 1, "late_ticks": late, "wall_s": wall, "audio_s_per_stream": (n_ticks - 1) * packet_ms / 1000.0,
             "definition": "acceptance of a chunk's last sample -> partial result covering it retrievable (host clock, engine-side)",
+            "caller_side": {"p50_ms": float(cl[len(cl) // 2]), "p90_ms": float(cl[int(len(cl) * 0.9)]), "max_ms": float(cl[-1]), "packets": int(len(caller_lat)),
+                            "streams_polled": len(watched),
+                            "definition": "return of vosk_batch_recognizer_accept_waveform for a packet -> a polling thread sees "
+                                          "vosk_batch_recognizer_partial_frames grow (Python poller beside the Python feeder; its poll period is included)"},
             "sample_partial": sample[:80]}
 
 
