@@ -921,8 +921,14 @@ void Engine::launch_step(Slot &sl, const int16_t *d_resident, int resident_strid
     // would only take cycles from it)
     bool host_bound = false;
     if (!post_threads_.empty()) {
-        std::lock_guard<std::mutex> lk(post_mu_);
-        host_bound = post_queue_.size() > 2 * post_threads_.size();
+        // a pool that is behind at (nearly) every launch is the bottleneck; one that drains between the bursts of finished streams is not
+        size_t backlog;
+        {
+            std::lock_guard<std::mutex> lk(post_mu_);
+            backlog = post_queue_.size();
+        }
+        post_backlog_ema_ = 0.9f * post_backlog_ema_ + 0.1f * (backlog > post_threads_.size() ? 1.f : 0.f);
+        host_bound = post_backlog_ema_ > 0.85f;
     }
     const int chains = sl.timed || L < 128 || host_bound ? 1 : std::max(1, std::min(cfg_.fe_split, 4));
     if (chains == 1) {

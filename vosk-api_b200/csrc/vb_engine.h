@@ -227,7 +227,7 @@ class Engine {
     Config cfg_;
     cudaStream_t stream_ = nullptr;  // setup / utility stream
     cudaStream_t fe_stream2_[3] = {};     // the other front-end chains of a step (fe-split)
-    cudaEvent_t last_fe_done_ = nullptr;  // front end of the previous step (both chains)
+    float post_backlog_ema_ = 0.f;        // share of the recent launches that found the host lattice pool behind
     cudaStream_t fe_stream_ = nullptr, dec_stream_ = nullptr, dec_stream2_ = nullptr, dec_stream3_ = nullptr, post_stream_ = nullptr;  // the two pipes (+ the light-lane search launch)
     std::vector<Slot> slots_;
     bool timing_ = false;
