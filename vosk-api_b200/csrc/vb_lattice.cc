@@ -177,10 +177,17 @@ struct Repo {
         return ans;
     }
     int remove_prefix(int id, int n) {  // canonical id of the string without its first n symbols
-        if (n == 0 && nodes[id].canon) return id;
         tmp.clear();
-        for (int k = id; nodes[k].depth > n; k = nodes[k].parent) tmp.push_back(nodes[k].label);
         int r = 0;
+        if (n == 0) {
+            // nothing to remove: only the symbols appended on top of the deepest canonical ancestor need a lookup (a canonical
+            // node's ancestors are canonical, the root is)
+            int k = id;
+            for (; !nodes[k].canon; k = nodes[k].parent) tmp.push_back(nodes[k].label);
+            r = k;
+        } else {
+            for (int k = id; nodes[k].depth > n; k = nodes[k].parent) tmp.push_back(nodes[k].label);
+        }
         for (size_t i = tmp.size(); i-- > 0;) r = succ(r, tmp[i]);
         return r;
     }
