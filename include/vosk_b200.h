@@ -19,7 +19,7 @@ extern "C" {
  * options: frames-per-chunk, max-batch-size, num-channels, beam, lattice-beam, max-active,
  * min-active, tok-cap, cand-cap, hash-size, max-seconds, log-tokens-per-frame, tensor-cores, lattice,
  * log-links-per-frame, lat-tok-cap, lat-link-cap, post-threads, partials, pipeline-slots, heavy-tokens, device-resample, model-conf,
- * debug-capture, devices (GPU indices separated by ':' or "all").  tensor-cores: 1 = fp16 hi/lo operand split (default),
+ * fe-split (front-end chains of a full-width step, 1-4, default 2), debug-capture, devices (GPU indices separated by ':' or "all").  tensor-cores: 1 = fp16 hi/lo operand split (default),
  * 2 = TF32 hi/lo split, 0 = fp32 FFMA kernel.
  * Env VOSK_BATCH_OPTIONS / VOSK_BATCH_DEVICES are applied first.  NULL on failure. */
 VoskBatchModel *vosk_batch_model_new_ex(const char *model_dir, const char *options);
