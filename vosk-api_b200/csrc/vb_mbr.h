@@ -99,10 +99,12 @@ VB_HD void mbr_solve(const MbrView &v, const MbrScratch &s, const int *R0, int n
         nR = Q;
         const int W = Q + 1;
         const int *r = R - 1;  // r[q], q = 1..Q
-        for (long long i = lane; i < (long long)(N + 1) * W; i += VB_MBR_LANES) {
-            s.alpha_dash[i] = 0.0;
-            s.beta_dash[i] = 0.0;
-        }
+        // beta_dash is accumulated cell by cell and starts from zero; a row of alpha_dash is the sum over the node's incoming arcs, the
+        // first of which assigns it (0 + x = x for the non-negative x here), so only the rows of nodes without incoming arcs are cleared
+        for (long long i = lane; i < (long long)(N + 1) * W; i += VB_MBR_LANES) s.beta_dash[i] = 0.0;
+        for (int n = 2; n <= N; n++)
+            if (v.pre_off[n] == v.pre_off[n + 1])
+                for (int q = lane; q <= Q; q += VB_MBR_LANES) s.alpha_dash[(long long)n * W + q] = 0.0;
         for (int q = lane; q <= Q; q += VB_MBR_LANES) {
             s.acc_n[q] = 0;
             s.cq[q] = (q >= 1 && r[q] != 0) ? 1.0 : 0.0;  // c(q) = l(eps, r(q)): what skipping reference position q costs
@@ -197,7 +199,11 @@ VB_HD void mbr_solve(const MbrView &v, const MbrScratch &s, const int *R0, int n
                 for (int j = 0; j < na; j++) {  // (arc order: the sums into the node are those of the plain loop)
                     const double p = v.post[k + j];
                     const double *val = j ? s.valb : s.vala;
-                    for (int q = lane; q <= Q; q += VB_MBR_LANES) adn[q] = VB_MBR_ADD(adn[q], VB_MBR_MUL(p, val[q]));
+                    if (k + j == v.pre_off[n]) {  // the node's first arc: 0 + p * val
+                        for (int q = lane; q <= Q; q += VB_MBR_LANES) adn[q] = VB_MBR_MUL(p, val[q]);
+                    } else {
+                        for (int q = lane; q <= Q; q += VB_MBR_LANES) adn[q] = VB_MBR_ADD(adn[q], VB_MBR_MUL(p, val[q]));
+                    }
                 }
                 VB_MBR_SYNC();
                 k += na;
