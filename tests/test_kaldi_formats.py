@@ -327,3 +327,39 @@ def test_reader_on_hand_assembled_bytes(lib, model_root, tmp_path):
     # gconsts were absent: log w - 0.5 (F log 2pi - sum log inv_var + sum mean_invvar^2 / inv_var)
     want = np.log(w.astype(np.float64)) - 0.5 * (F * np.log(2 * np.pi) - np.log(iv).sum(1) + (miv.astype(np.float64) ** 2 / iv).sum(1))
     np.testing.assert_allclose(tensor(lib, dst, "iv.gconsts"), want, rtol=0, atol=1e-4)
+
+
+def test_compressed_matrices_expand_as_kaldi_does(lib, model_root, tmp_path):
+    """Kaldi's CompressedMatrix layouts (CM: one byte per element, per-column percentile headers, stored by columns; CM2: two bytes;
+    CM3: one byte), assembled by hand; the expansion is Kaldi's float arithmetic, restated here in numpy."""
+    import struct
+    F, S = 40, 7 * 40 + 1
+    rng = np.random.default_rng(5)
+    mn, rg = np.float32(-3.5), np.float32(9.25)
+    inc16, f32 = np.float32(1.52590218966964e-05), np.float32
+
+    def check(payload, want):
+        dst = str(tmp_path / ("model_%d" % len(os.listdir(tmp_path))))
+        shutil.copytree(model_root("tiny"), dst)
+        with open(os.path.join(dst, "ivector/final.mat"), "wb") as f:
+            f.write(b"\x00B" + payload)
+        np.testing.assert_array_equal(tensor(lib, dst, "iv.lda").reshape(F, S), want.astype(np.float64))
+
+    head = struct.pack("<ffii", float(mn), float(rg), F, S)
+    # CM3: one byte per element, row-major
+    b3 = rng.integers(0, 256, size=(F, S), dtype=np.uint8)
+    check(b"CM3 " + head + b3.tobytes(), mn + rg * f32(1.0 / 255.0) * b3.astype(np.float32))
+    # CM2: two bytes per element, row-major
+    b2 = rng.integers(0, 65536, size=(F, S)).astype("<u2")
+    check(b"CM2 " + head + b2.tobytes(), mn + rg * inc16 * b2.astype(np.float32))
+    # CM: per-column percentiles (4 x uint16), then the bytes column by column
+    pc = np.sort(rng.integers(0, 65536, size=(S, 4)), axis=1).astype("<u2")
+    b1 = rng.integers(0, 256, size=(S, F), dtype=np.uint8)  # [col][row]
+    p = mn + rg * inc16 * pc.astype(np.float32)  # [col][4]
+    v = b1.astype(np.float32)
+    p0, p25, p75, p100 = (p[:, k:k + 1] for k in range(4))
+    lo = p0 + (p25 - p0) * v * f32(1.0 / 64.0)
+    mid = p25 + (p75 - p25) * (v - f32(64)) * f32(1.0 / 128.0)
+    hi = p75 + (p100 - p75) * (v - f32(192)) * f32(1.0 / 63.0)
+    want = np.where(b1 <= 64, lo, np.where(b1 <= 192, mid, hi)).T
+    check(b"CM " + head + pc.tobytes() + b1.tobytes(), want)

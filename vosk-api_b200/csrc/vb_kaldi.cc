@@ -5,7 +5,7 @@
 // files are named by ivector.conf [REF src/batch_model.cc:77], [REF src/model.cc:251-256].  Kaldi is not part of the
 // reference tree, so the layouts are restated from its published I/O conventions:
 //   binary marker "\0B"; tokens = ASCII + one space; basic types = size byte + little-endian value; bool 'T'/'F';
-//   Matrix "FM "/"DM " rows cols data; Vector "FV "/"DV " dim data; SpMatrix "FP "/"DP " rows + packed lower triangle;
+//   Matrix "FM "/"DM " rows cols data (or a CompressedMatrix "CM "/"CM2 "/"CM3 "); Vector "FV "/"DV " dim data; SpMatrix "FP "/"DP " rows + packed lower triangle;
 //   integer vector = size byte, int32 count, raw data;
 //   nnet3 = "<Nnet3>" + config lines up to a blank line + "<NumComponents>" + {"<ComponentName>" name <Type> .. </Type>}.
 // Component bodies are read as self-describing token/value sequences, so optional fields of different Kaldi versions
@@ -159,7 +159,64 @@ struct KReader {
         }
         p += n * item;
     }
+    // CompressedMatrix ("CM " one byte per element with per-column percentile headers, stored by columns; "CM2 " two bytes per
+    // element; "CM3 " one byte per element), as Kaldi's compressed-matrix.cc lays it out: min_value, range (float), rows, cols
+    // (int32) raw, then the data.  The arithmetic of the expansion is float, as Kaldi's.
+    bool compressed_matrix(KaldiMatrix *m) {
+        int format = 0;
+        if (buf.size() - p >= 3 && memcmp(&buf[p], "CM ", 3) == 0) format = 1, p += 3;
+        else if (buf.size() - p >= 4 && memcmp(&buf[p], "CM2 ", 4) == 0) format = 2, p += 4;
+        else if (buf.size() - p >= 4 && memcmp(&buf[p], "CM3 ", 4) == 0) format = 3, p += 4;
+        else return false;
+        need(16);
+        float min_value, range;
+        int32_t rows, cols;
+        memcpy(&min_value, &buf[p], 4);
+        memcpy(&range, &buf[p + 4], 4);
+        memcpy(&rows, &buf[p + 8], 4);
+        memcpy(&cols, &buf[p + 12], 4);
+        p += 16;
+        if (rows < 0 || cols < 0) fail("negative matrix size");
+        const size_t n = (size_t)rows * cols;
+        m->rows = rows;
+        m->cols = cols;
+        m->v.resize(n);
+        const float inc16 = 1.52590218966964e-05f;  // 1 / 65535
+        if (format == 1) {
+            if ((size_t)cols * 8 > buf.size() - p || n > buf.size() - p - (size_t)cols * 8) fail("truncated compressed matrix");
+            const unsigned char *hdr = &buf[p], *bytes = &buf[p + (size_t)cols * 8];
+            for (int c = 0; c < cols; c++) {
+                uint16_t pc[4];
+                memcpy(pc, hdr + (size_t)c * 8, 8);
+                const float p0 = min_value + range * inc16 * pc[0], p25 = min_value + range * inc16 * pc[1], p75 = min_value + range * inc16 * pc[2],
+                            p100 = min_value + range * inc16 * pc[3];
+                for (int r = 0; r < rows; r++) {
+                    const unsigned char v = bytes[(size_t)c * rows + r];
+                    float x;
+                    if (v <= 64) x = p0 + (p25 - p0) * v * (1.0f / 64.0f);
+                    else if (v <= 192) x = p25 + (p75 - p25) * (v - 64) * (1.0f / 128.0f);
+                    else x = p75 + (p100 - p75) * (v - 192) * (1.0f / 63.0f);
+                    m->v[(size_t)r * cols + c] = x;
+                }
+            }
+            p += (size_t)cols * 8 + n;
+        } else if (format == 2) {
+            if (n > (buf.size() - p) / 2) fail("truncated compressed matrix");
+            for (size_t i = 0; i < n; i++) {
+                uint16_t v;
+                memcpy(&v, &buf[p + 2 * i], 2);
+                m->v[i] = min_value + range * inc16 * v;
+            }
+            p += 2 * n;
+        } else {
+            if (n > buf.size() - p) fail("truncated compressed matrix");
+            for (size_t i = 0; i < n; i++) m->v[i] = min_value + range * (1.0f / 255.0f) * buf[p + i];
+            p += n;
+        }
+        return true;
+    }
     void matrix(KaldiMatrix *m) {
+        if (compressed_matrix(m)) return;
         std::string t = tag();
         if (t[1] != 'M') fail("matrix expected");
         m->rows = i32();
