@@ -188,16 +188,24 @@ __global__ void __launch_bounds__(kFeatThreads) mfcc_kernel(FeatArgs a) {
         // mel energies: four lanes per filter (taps sub, sub + 4, ..), ten rounds of four filters
         {
             const int sub = L & 3, grp = L >> 2;
-#pragma unroll 2
-            for (int r = 0; r < kNumMel / 4; r++) {
-                const int j = 4 * r + grp;
-                const int st = mel_start[j], n = mel_len[j];
-                const float *mw = mel_w + j * kMelStride;
-                float e = 0.f;
-                for (int i = sub; i < n; i += 4) e = fmaf(mw[i], pw[st + i], e);
-                e += __shfl_xor_sync(0xffffffffu, e, 1);
-                e += __shfl_xor_sync(0xffffffffu, e, 2);
-                if (sub == 0) lm[j] = e;
+            for (int r = 0; r < kNumMel / 4; r += 2) {  // two rounds at a time: their sums are independent chains
+                const int j0 = 4 * r + grp, j1 = j0 + 4;
+                const int st0 = mel_start[j0], n0 = mel_len[j0], st1 = mel_start[j1], n1 = mel_len[j1];
+                const float *mw0 = mel_w + j0 * kMelStride, *mw1 = mel_w + j1 * kMelStride;
+                float e0 = 0.f, e1 = 0.f;
+                const int nmax = max(n0, n1);
+                for (int i = sub; i < nmax; i += 4) {
+                    if (i < n0) e0 = fmaf(mw0[i], pw[st0 + i], e0);
+                    if (i < n1) e1 = fmaf(mw1[i], pw[st1 + i], e1);
+                }
+                e0 += __shfl_xor_sync(0xffffffffu, e0, 1);
+                e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
+                e0 += __shfl_xor_sync(0xffffffffu, e0, 2);
+                e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
+                if (sub == 0) {
+                    lm[j0] = e0;
+                    lm[j1] = e1;
+                }
             }
         }
         __syncwarp();
@@ -206,10 +214,13 @@ __global__ void __launch_bounds__(kFeatThreads) mfcc_kernel(FeatArgs a) {
         if (live) {
             float *out = ring_row(a.in_node, ln.channel, ln.frames_before + f);
             for (int k = L; k < kNumCeps; k += 16) {
-                float c = 0.f;
-#pragma unroll 8
-                for (int j = 0; j < kNumMel; j++) c = fmaf(dct_t[j * 40 + k], lm[j], c);
-                out[k] = c * lifter[k];
+                float c0 = 0.f, c1 = 0.f;  // (two chains: even and odd mel bins)
+#pragma unroll 10
+                for (int j = 0; j < kNumMel; j += 2) {
+                    c0 = fmaf(dct_t[j * 40 + k], lm[j], c0);
+                    c1 = fmaf(dct_t[(j + 1) * 40 + k], lm[j + 1], c1);
+                }
+                out[k] = (c0 + c1) * lifter[k];
             }
         }
         __syncwarp();
