@@ -20,12 +20,6 @@ __device__ __forceinline__ float *ring_row(const NodeDesc &n, int ch, int t) {
     return n.buf + ((size_t)ch * n.ring + ring_slot(n, t)) * n.dim;
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 constexpr int kFeatThreads = 256;
 constexpr int kFeatHalfWarps = kFeatThreads / 16;  // a frame is owned by a half-warp: 16 lanes x 16 complex points in registers
 constexpr int kFftTile = 16 * 17;                  // float2 per half-warp: the 16 x 16 transpose tile, padded rows
@@ -77,7 +71,6 @@ __device__ __forceinline__ constexpr int fft16_at(int k) { return 4 * (k & 3) + 
 __global__ void __launch_bounds__(kFeatThreads) mfcc_kernel(FeatArgs a) {
     extern __shared__ __align__(16) float sm[];
     const LaneDesc ln = a.lanes[blockIdx.x];
-    const int spc = a.samples_per_chunk;
     float2 *fft = reinterpret_cast<float2 *>(sm);
     float *logmel = sm + kFeatHalfWarps * kFftTile * 2;
     float *window = logmel + kFeatHalfWarps * 40;
